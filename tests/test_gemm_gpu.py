@@ -1,0 +1,49 @@
+"""tcgen05 GEMM vs torch fp32 reference on the same bf16 inputs (tolerance: bf16 output rounding)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [
+    (128, 256, 64), (128, 256, 256), (256, 512, 128), (100, 256, 64), (300, 264, 200), (1600, 1280, 1176),
+    (1000, 3584, 3584), (5836, 4608, 3584), (77, 1536, 8960), (4096, 3584, 5120), (520, 37888 // 8, 3584),
+]
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_gemm_matches_fp32(M, N, K):
+    from time_r1_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
+    a = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    b = torch.randn(N, K, device="cuda", generator=g).to(torch.bfloat16)
+    ref = a.float() @ b.float().t()
+    out = ops.gemm(a, b)
+    torch.cuda.synchronize()
+    err = (out.float() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= 1e-2 * scale + 1e-3, f"max err {err} vs scale {scale}"
+    out32 = ops.gemm(a, b, out_dtype=torch.float32)
+    err32 = (out32 - ref).abs().max().item()
+    assert err32 <= 2e-5 * scale * (K ** 0.5) + 1e-4, f"fp32-out max err {err32} vs scale {scale}"
+
+
+def test_gemm_bias_accumulate_strided():
+    from time_r1_b200 import ops
+
+    M, N, K = 333, 512, 320
+    g = torch.Generator(device="cuda").manual_seed(5)
+    abuf = torch.randn(M, K + 64, device="cuda", generator=g).to(torch.bfloat16)
+    a = abuf[:, 8:8 + K]  # strided view, 16-byte aligned start
+    b = torch.randn(N, K, device="cuda", generator=g).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda", generator=g).to(torch.bfloat16)
+    ref = a.float() @ b.float().t() + bias.float()
+    out = ops.gemm(a, b, bias=bias, out_dtype=torch.float32)
+    assert (out - ref).abs().max().item() < 1e-3
+    out2 = out.clone()
+    ops.gemm(a, b, out=out2, accumulate=True)
+    ref2 = ref + a.float() @ b.float().t()
+    assert (out2 - ref2).abs().max().item() < 2e-3
+    obf = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, b, out=obf, bias=bias.float())
+    assert (obf.float() - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()

@@ -1,0 +1,294 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a:  D[M,N] (+)= A[M,K] * B[N,K]^T (+ bias[N])
+//
+// Every dense contraction of the Qwen2-VL / Qwen2.5-VL rollout, scoring and backward passes goes through this
+// kernel (reference call sites: the nn.Linear / Conv3d modules inside HF modeling_qwen2_5_vl.py that
+// timer1_trainer.py:452-457 and :569-573 execute through cuBLAS).  Both operands are K-major bf16; the backward
+// pass feeds it explicitly transposed operands (see transpose_bf16 in elementwise.cu).
+//
+// Structure (one CTA per SM, persistent over output tiles):
+//   warp 0      TMA producer   : cp.async.bulk.tensor 2D loads of 128x64 (A) and 256x64 (B) bf16 boxes, SWIZZLE_128B
+//   warp 1      MMA issuer     : one thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=256, K=16)
+//   warp 2      TMEM allocator : 512 columns = two 128x256 fp32 accumulators (double buffered)
+//   warps 4..7  epilogue       : tcgen05.ld 32x32b -> registers -> bias / accumulate / convert -> global
+// Pipelines: smem ring (full/empty mbarriers, 4 stages of 48 KB) and TMEM ring (tmem_full/tmem_empty).
+#include "t1_common.cuh"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BN = 256;
+constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle atom row
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * BK * 2;
+constexpr int B_BYTES = BN * BK * 2;
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 256;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+enum : int {
+  GEMM_OUT_F32 = 1,     // D is fp32 (else bf16)
+  GEMM_ACCUMULATE = 2,  // D += result (else D = result)
+  GEMM_BIAS_F32 = 4,    // bias is fp32 (else bf16)
+};
+
+struct EpiParams {
+  void* D;
+  const void* bias;
+  long long ldd;
+  int flags;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, int M, int N,
+                    int K, EpiParams epi) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* a_tiles = smem;
+  uint8_t* b_tiles = smem + STAGES * A_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_m = (M + BM - 1) / BM;
+  const int num_n = (N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_k = (K + BK - 1) / BK;
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+  }
+  if (warp_idx == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 128);
+    }
+    mbar_fence_init();
+  }
+  if (warp_idx == 2) tmem_alloc<512>(tmem_ptr_smem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp_idx == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile % num_m, n_blk = tile / num_m;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+          tma_load_2d(a_tiles + stage * A_BYTES, &tma_a, &full_bar[stage], kb * BK, m_blk * BM);
+          tma_load_2d(b_tiles + stage * B_BYTES, &tma_b, &full_bar[stage], kb * BK, n_blk * BN);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ===================== MMA issuer (single thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t a_desc = umma_desc_sw128_kmajor(smem_u32(a_tiles + stage * A_BYTES));
+          const uint64_t b_desc = umma_desc_sw128_kmajor(smem_u32(b_tiles + stage * B_BYTES));
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 32 B (= 16 bf16) along K inside the 128 B swizzle atom: +2 in the >>4 encoded address
+            umma_bf16_ss(tmem_d, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc,
+                         (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above retire
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp_idx >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp_idx & 3;  // TMEM lane quadrant this warp may access
+    const bool out_f32 = epi.flags & GEMM_OUT_F32;
+    const bool accum = epi.flags & GEMM_ACCUMULATE;
+    const bool bias_f32 = epi.flags & GEMM_BIAS_F32;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int m_blk = tile % num_m, n_blk = tile / num_m;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const int row = m_blk * BM + q * 32 + lane;
+      const uint32_t taddr_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = n_blk * BN + c * 32;
+        if (col0 >= N) break;  // warp-uniform
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr_row + c * 32, v);
+        tmem_ld_wait();
+        if (row < M) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int col = col0 + g * 8;
+            if (col < N) {  // N % 8 == 0 is enforced on the host
+              float f[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
+              if (epi.bias) {
+                if (bias_f32) {
+                  const float4* bp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(epi.bias) + col);
+                  float4 b0 = bp[0], b1 = bp[1];
+                  f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                  f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+                } else {
+                  uint4 b = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(epi.bias) + col);
+                  float2 t;
+                  t = unpack_bf16x2(b.x); f[0] += t.x; f[1] += t.y;
+                  t = unpack_bf16x2(b.y); f[2] += t.x; f[3] += t.y;
+                  t = unpack_bf16x2(b.z); f[4] += t.x; f[5] += t.y;
+                  t = unpack_bf16x2(b.w); f[6] += t.x; f[7] += t.y;
+                }
+              }
+              if (out_f32) {
+                float4* dp = reinterpret_cast<float4*>(reinterpret_cast<float*>(epi.D) + (long long)row * epi.ldd + col);
+                if (accum) {
+                  float4 o0 = dp[0], o1 = dp[1];
+                  f[0] += o0.x; f[1] += o0.y; f[2] += o0.z; f[3] += o0.w;
+                  f[4] += o1.x; f[5] += o1.y; f[6] += o1.z; f[7] += o1.w;
+                }
+                dp[0] = make_float4(f[0], f[1], f[2], f[3]);
+                dp[1] = make_float4(f[4], f[5], f[6], f[7]);
+              } else {
+                uint4* dp = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(epi.D) + (long long)row * epi.ldd + col);
+                if (accum) {
+                  uint4 o = *dp;
+                  float2 t;
+                  t = unpack_bf16x2(o.x); f[0] += t.x; f[1] += t.y;
+                  t = unpack_bf16x2(o.y); f[2] += t.x; f[3] += t.y;
+                  t = unpack_bf16x2(o.z); f[4] += t.x; f[5] += t.y;
+                  t = unpack_bf16x2(o.w); f[6] += t.x; f[7] += t.y;
+                }
+                uint4 o;
+                o.x = pack_bf16x2(f[0], f[1]);
+                o.y = pack_bf16x2(f[2], f[3]);
+                o.z = pack_bf16x2(f[4], f[5]);
+                o.w = pack_bf16x2(f[6], f[7]);
+                *dp = o;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty_bar[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 2) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// ---- host: tensor-map construction through the driver entry point (no -lcuda link dependency) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// Row-major bf16 [rows, cols] with leading dimension ld (elements); box = box_rows x 64 columns.
+int make_tmap_bf16(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) {
+    t1_set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+    return T1_ERR_CUDA;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    t1_set_error("cuTensorMapEncodeTiled failed: CUresult %d (ptr %p rows %lld cols %lld ld %lld)", (int)r, ptr, rows,
+                 cols, ld);
+    return T1_ERR_CUDA;
+  }
+  return T1_OK;
+}
+
+}  // namespace
+
+// C-ABI: see include/timer1.h
+extern "C" int t1_gemm_bf16_tn(const void* A, long long lda, const void* B, long long ldb, void* D, long long ldd,
+                               int M, int N, int K, const void* bias, int flags, cudaStream_t stream) {
+  T1_CHECK_ARG(A && B && D, "t1_gemm_bf16_tn: null operand");
+  T1_CHECK_ARG(M > 0 && N > 0 && K > 0, "t1_gemm_bf16_tn: empty problem M=%d N=%d K=%d", M, N, K);
+  T1_CHECK_ARG(N % 8 == 0 && ldd % 8 == 0, "t1_gemm_bf16_tn: N and ldd must be multiples of 8 (N=%d ldd=%lld)", N, ldd);
+  T1_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0, "t1_gemm_bf16_tn: lda/ldb must be multiples of 8 (16-byte TMA strides)");
+  T1_CHECK_ARG(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0 && ((uintptr_t)D & 15) == 0,
+               "t1_gemm_bf16_tn: operands must be 16-byte aligned");
+  T1_CHECK_ARG(lda >= K && ldb >= K && ldd >= N, "t1_gemm_bf16_tn: leading dimension smaller than row length");
+  CUtensorMap ta, tb;
+  int rc = make_tmap_bf16(&ta, A, M, K, lda, BM);
+  if (rc) return rc;
+  rc = make_tmap_bf16(&tb, B, N, K, ldb, BN);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) {
+      t1_set_error("t1_gemm_bf16_tn: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return T1_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  const int num_tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  const int grid = num_tiles < t1_num_sms() ? num_tiles : t1_num_sms();
+  EpiParams epi{D, bias, ldd, flags};
+  gemm_bf16_tn_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, M, N, K, epi);
+  T1_CUDA_LAUNCH_CHECK("t1_gemm_bf16_tn");
+  return T1_OK;
+}

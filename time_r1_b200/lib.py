@@ -1,0 +1,97 @@
+"""ctypes binding of libtimer1.so — the C-ABI declared in include/timer1.h.
+
+There is no fallback: if the shared library is missing or fails to load, importing a compute entry point raises.
+Tensors cross the boundary as raw device pointers (`tensor.data_ptr()`), sizes as plain ints and the CUDA stream
+as a `cudaStream_t` handle; no torch types appear in any signature.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtimer1.so")
+
+_lib = None
+
+vp = C.c_void_p
+i32 = C.c_int
+i64 = C.c_longlong
+f32 = C.c_float
+u64 = C.c_ulonglong
+
+# name -> argtypes (restype is int unless listed in _RESTYPES)
+_SIGNATURES: dict[str, list] = {
+    "t1_version": [],
+    "t1_device_info": [C.POINTER(C.c_int)],
+    "t1_count_launch": [],
+    "t1_launch_count": [i32],
+    # gemm_tcgen05.cu
+    "t1_gemm_bf16_tn": [vp, i64, vp, i64, vp, i64, i32, i32, i32, vp, i32, vp],
+}
+_RESTYPES = {"t1_last_error": C.c_char_p, "t1_launch_count": u64, "t1_count_launch": None}
+
+GEMM_OUT_F32 = 1
+GEMM_ACCUMULATE = 2
+GEMM_BIAS_F32 = 4
+
+
+class Timer1Error(RuntimeError):
+    pass
+
+
+def register(name: str, argtypes: list, restype=C.c_int) -> None:
+    _SIGNATURES[name] = argtypes
+    if restype is not C.c_int:
+        _RESTYPES[name] = restype
+
+
+def load(build_if_missing: bool = True):
+    """Load libtimer1.so (building it in-tree with nvcc if it is absent). Raises on failure — never falls back."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        if not build_if_missing:
+            raise Timer1Error(f"{LIB_PATH} is missing; run `python -m time_r1_b200.build`")
+        from . import build as _build
+
+        _build.build()
+    lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    lib.t1_last_error.argtypes = []
+    lib.t1_last_error.restype = C.c_char_p
+    for name, argtypes in _SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPES.get(name, C.c_int)
+    _lib = lib
+    return lib
+
+
+def exported_symbols() -> list[str]:
+    return sorted(_SIGNATURES) + ["t1_last_error"]
+
+
+def last_error() -> str:
+    return (load().t1_last_error() or b"").decode()
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        raise Timer1Error(f"{what} failed (rc={rc}): {last_error()}")
+
+
+def call(name: str, *args) -> None:
+    fn = getattr(load(), name)
+    check(fn(*args), name)
+
+
+def stream_ptr() -> int:
+    import torch
+
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t) -> int:
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return 0 if t is None else t.data_ptr()
