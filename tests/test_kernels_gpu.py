@@ -1,0 +1,456 @@
+"""Every libtimer1 kernel vs a plain torch fp32 reference of the same op on the same bf16-rounded inputs.
+
+Tolerances: outputs are bf16 (rel 2^-8), accumulation fp32; each assert states its bound.
+"""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+BF16 = torch.bfloat16
+DEV = "cuda"
+
+
+def rnd(*shape, seed=0, scale=1.0, dtype=BF16):
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    return (torch.randn(*shape, device=DEV, generator=g) * scale).to(dtype)
+
+
+def close(a, b, atol, rtol, what=""):
+    a, b = a.float(), b.float()
+    err = (a - b).abs()
+    bound = atol + rtol * b.abs()
+    bad = (err > bound).sum().item()
+    assert bad == 0, f"{what}: {bad} elements out of tolerance, max err {err.max().item():.4g}"
+
+
+# ------------------------------------------------------------------ norms
+@pytest.mark.parametrize("T,D", [(7, 256), (130, 1280), (65, 3584), (33, 5120)])
+def test_rmsnorm_fwd_bwd(T, D):
+    from time_r1_b200 import ops
+
+    x, w, delta = rnd(T, D, seed=1), (1 + 0.1 * rnd(D, seed=2).float()).to(BF16), rnd(T, D, seed=3)
+    eps = 1e-6
+    xs = x.clone()
+    y = ops.rmsnorm(xs, w, eps, delta=delta)
+    xr = (x.float() + delta.float()).to(BF16).float()
+    close(xs, xr, 0, 0, "residual")
+    ref = xr * torch.rsqrt(xr.pow(2).mean(-1, keepdim=True) + eps) * w.float()
+    close(y, ref, 1e-2, 1e-2, "rmsnorm fwd")
+    # backward vs autograd
+    xa = xr.clone().requires_grad_(True)
+    wa = w.float().clone().requires_grad_(True)
+    dy = rnd(T, D, seed=4)
+    out = xa * torch.rsqrt(xa.pow(2).mean(-1, keepdim=True) + eps) * wa
+    out.backward(dy.float())
+    dres = rnd(T, D, seed=5)
+    dw = torch.zeros(D, device=DEV)
+    dx = ops.rmsnorm_bwd(dy, xr.to(BF16), w, eps, dw, dres=dres)
+    close(dx, xa.grad + dres.float(), 2e-2, 2e-2, "rmsnorm dx")
+    close(dw, wa.grad, 5e-2, 2e-2, "rmsnorm dw")
+
+
+def test_layernorm_fwd():
+    from time_r1_b200 import ops
+
+    x, w, b = rnd(50, 1280, seed=1), rnd(1280, seed=2), rnd(1280, seed=3)
+    y = ops.layernorm(x.clone(), w, b, 1e-6)
+    ref = torch.nn.functional.layer_norm(x.float(), (1280,), w.float(), b.float(), 1e-6)
+    close(y, ref, 2e-2, 1e-2, "layernorm")
+
+
+# ------------------------------------------------------------------ rope
+@pytest.mark.parametrize("hd,nh", [(128, 6), (80, 4)])
+def test_rope_table_apply_and_inverse(hd, nh):
+    from time_r1_b200 import ops
+
+    T, half = 77, hd // 2
+    pos = torch.randint(0, 5000, (3, T), device=DEV, dtype=torch.int32)
+    axis = (torch.arange(half, device=DEV) % 3).to(torch.int32)
+    inv = (1.0 / (1e6 ** (torch.arange(0, hd, 2, device=DEV).float() / hd))).contiguous()
+    cos, sin = ops.rope_table(pos, axis, inv)
+    ang = pos.float()[axis.long(), :].t() * inv[None, :]
+    close(cos, ang.cos(), 2e-3, 0, "cos table")   # fp32 angles up to 5e3 rad: argument rounding dominates
+    close(sin, ang.sin(), 2e-3, 0, "sin table")
+    ld = nh * hd + 64
+    x = rnd(T, ld, seed=7)
+    x0 = x.clone()
+    out = torch.zeros(T, nh * hd, device=DEV, dtype=BF16)
+    ops.rope_apply(x, 32, nh, hd, cos, sin, out=out)
+    xh = x0[:, 32:32 + nh * hd].float().view(T, nh, hd)
+    a, b = xh[..., :half], xh[..., half:]
+    c, s = cos[:, None, :], sin[:, None, :]
+    ref = torch.cat([a * c - b * s, b * c + a * s], -1).view(T, nh * hd)
+    close(x[:, 32:32 + nh * hd], ref, 2e-2, 1e-2, "rope apply")
+    close(out, ref, 2e-2, 1e-2, "rope copy-out")
+    close(x[:, :32], x0[:, :32], 0, 0, "untouched cols")
+    ops.rope_apply(x, 32, nh, hd, cos, sin, inverse=True)
+    close(x[:, 32:32 + nh * hd], x0[:, 32:32 + nh * hd], 4e-2, 2e-2, "rope inverse round trip")
+
+
+# ------------------------------------------------------------------ activations
+def test_swiglu_and_act_fwd_bwd():
+    from time_r1_b200 import ops
+
+    T, I = 37, 3456
+    gu = rnd(T, 2 * I, seed=1)
+    act = ops.swiglu(gu)
+    ga = gu.float().clone().requires_grad_(True)
+    ref = torch.nn.functional.silu(ga[:, :I]) * ga[:, I:]
+    close(act, ref, 1e-2, 1e-2, "swiglu")
+    d = rnd(T, I, seed=2)
+    ref.backward(d.float())
+    close(ops.swiglu_bwd(d, gu), ga.grad, 2e-2, 2e-2, "swiglu bwd")
+    for mode, fn in ((0, torch.nn.functional.gelu), (1, lambda t: t * torch.sigmoid(1.702 * t))):
+        x = rnd(T, I, seed=3)
+        xa = x.float().clone().requires_grad_(True)
+        y = fn(xa)
+        close(ops.act(x, mode), y, 1e-2, 1e-2, f"act{mode}")
+        y.backward(d.float())
+        close(ops.act_bwd(d, x, mode), xa.grad, 2e-2, 2e-2, f"act{mode} bwd")
+
+
+# ------------------------------------------------------------------ layout ops
+def test_gather_scatter_transpose_colsum():
+    from time_r1_b200 import ops
+
+    src = rnd(100, 256, seed=1)
+    idx = torch.randperm(100, device=DEV)[:60].to(torch.int32)
+    g = ops.gather_rows(src, idx)
+    assert torch.equal(g, src[idx.long()])
+    dst = torch.zeros(100, 256, device=DEV, dtype=BF16)
+    ops.scatter_rows(g, idx, dst)
+    assert torch.equal(dst[idx.long()], g)
+    acc = torch.zeros(4, 256, device=DEV, dtype=BF16)
+    ones = torch.ones(64, 256, device=DEV, dtype=BF16)
+    ops.scatter_rows(ones, torch.zeros(64, device=DEV, dtype=torch.int32) + 2, acc, accumulate=True)
+    assert acc[2].float().eq(64).all() and acc[0].float().eq(0).all()
+    for R, C in [(64, 64), (200, 136), (3584, 520), (8, 4096)]:
+        x = rnd(R, C, seed=R + C)
+        assert torch.equal(ops.transpose(x), x.t().contiguous()), (R, C)
+    x = rnd(777, 514, seed=9)
+    out = torch.zeros(514, device=DEV)
+    ops.colsum(x, out)
+    close(out, x.float().sum(0), 1e-2, 1e-4, "colsum")
+    b = torch.ones(514, device=DEV, dtype=BF16)
+    ops.f32_to_bf16(out, b, accumulate=True)
+    close(b, x.float().sum(0) + 1, 0.3, 1e-2, "f32->bf16 accumulate")
+    y = rnd(64, 64, seed=3)
+    y0 = y.clone()
+    ops.add_(y, x[:64, :64].contiguous())
+    close(y, y0.float() + x[:64, :64].float(), 1e-2, 1e-2, "add")
+
+
+# ------------------------------------------------------------------ attention
+def dense_attention(q, k, v, lo, hi, shared, scale):
+    """q [T,Hq,d], k/v [Tk,Hkv,d] fp32; mask from (lo, hi, shared). Rows with no visible key give 0."""
+    T, Hq, d = q.shape
+    Tk, Hkv, _ = k.shape
+    rep = Hq // Hkv
+    kk = k.repeat_interleave(rep, dim=1)
+    vv = v.repeat_interleave(rep, dim=1)
+    s = torch.einsum("ihd,jhd->hij", q, kk) * scale
+    j = torch.arange(Tk, device=q.device)[None, :]
+    vis = (j < hi[:, None]) & ((j >= lo[:, None]) | (j < shared))
+    s = s.masked_fill(~vis[None], float("-inf"))
+    p = torch.softmax(s, dim=-1)
+    p = torch.nan_to_num(p, nan=0.0)
+    return torch.einsum("hij,jhd->ihd", p, vv)
+
+
+def make_mask(kind, T, P=0, C=0):
+    i = torch.arange(T, device=DEV, dtype=torch.int32)
+    if kind == "causal":
+        return torch.zeros_like(i), i + 1, 0
+    if kind == "packed":
+        lo = torch.where(i < P, torch.zeros_like(i), P + ((i - P) // C) * C)
+        return lo.to(torch.int32), i + 1, P
+    if kind == "window":
+        # ragged windows: sizes cycle through 64, 48, 12, 64, 100
+        sizes, lo, hi, s, n = [64, 48, 12, 64, 100], [], [], 0, 0
+        while s < T:
+            w = min(sizes[n % 5], T - s)
+            lo += [s] * w
+            hi += [s + w] * w
+            s += w
+            n += 1
+        return torch.tensor(lo, device=DEV, dtype=torch.int32), torch.tensor(hi, device=DEV, dtype=torch.int32), 0
+    raise ValueError(kind)
+
+
+@pytest.mark.parametrize("kind,T,P,C,Hq,Hkv,hd", [
+    ("causal", 200, 0, 0, 4, 2, 128), ("causal", 64, 0, 0, 2, 1, 64), ("packed", 531, 203, 41, 14, 2, 128),
+    ("packed", 450, 130, 64, 4, 4, 128), ("window", 1000, 0, 0, 16, 16, 80), ("window", 300, 0, 0, 2, 2, 128),
+])
+def test_attention_forward(kind, T, P, C, Hq, Hkv, hd):
+    from time_r1_b200 import ops
+
+    ld = (Hq + 2 * Hkv) * hd
+    qkv = rnd(T, ld, seed=T + hd)
+    q, k, v = qkv[:, :Hq * hd], qkv[:, Hq * hd:(Hq + Hkv) * hd], qkv[:, (Hq + Hkv) * hd:]
+    lo, hi, shared = make_mask(kind, T, P, C)
+    scale = hd ** -0.5
+    out, lse = ops.attn_fwd(q, k, v, lo, hi, shared, Hq, Hkv, hd, scale)
+    ref = dense_attention(q.float().reshape(T, Hq, hd), k.float().reshape(T, Hkv, hd), v.float().reshape(T, Hkv, hd),
+                          lo, hi, shared, scale)
+    close(out.view(T, Hq, hd), ref, 2e-2, 2e-2, f"attn fwd {kind}")
+    # LSE (log2 domain) vs dense
+    rep = Hq // Hkv
+    s = torch.einsum("ihd,jhd->hij", q.float().reshape(T, Hq, hd), k.float().reshape(T, Hkv, hd).repeat_interleave(rep, 1)) * scale
+    j = torch.arange(T, device=DEV)[None, :]
+    vis = (j < hi[:, None]) & ((j >= lo[:, None]) | (j < shared))
+    lse_ref = torch.logsumexp(s.masked_fill(~vis[None], float("-inf")), -1) / math.log(2.0)
+    close(lse, lse_ref, 2e-2, 1e-3, "lse2")
+
+
+@pytest.mark.parametrize("kind,T,P,C,Hq,Hkv,hd", [
+    ("causal", 200, 0, 0, 4, 2, 128), ("packed", 531, 203, 41, 14, 2, 128), ("packed", 300, 100, 50, 2, 1, 64),
+    ("window", 300, 0, 0, 2, 2, 128),
+])
+def test_attention_backward(kind, T, P, C, Hq, Hkv, hd):
+    from time_r1_b200 import ops
+
+    ld = (Hq + 2 * Hkv) * hd
+    qkv = rnd(T, ld, seed=T + hd + 1, scale=0.7)
+    q, k, v = qkv[:, :Hq * hd], qkv[:, Hq * hd:(Hq + Hkv) * hd], qkv[:, (Hq + Hkv) * hd:]
+    lo, hi, shared = make_mask(kind, T, P, C)
+    scale = hd ** -0.5
+    out, lse = ops.attn_fwd(q, k, v, lo, hi, shared, Hq, Hkv, hd, scale)
+    do = rnd(T, Hq * hd, seed=5)
+    qa = q.float().reshape(T, Hq, hd).clone().requires_grad_(True)
+    ka = k.float().reshape(T, Hkv, hd).clone().requires_grad_(True)
+    va = v.float().reshape(T, Hkv, hd).clone().requires_grad_(True)
+    ref = dense_attention(qa, ka, va, lo, hi, shared, scale)
+    ref.backward(do.float().view(T, Hq, hd))
+    dqkv = torch.zeros_like(qkv)
+    dq, dk, dv = dqkv[:, :Hq * hd], dqkv[:, Hq * hd:(Hq + Hkv) * hd], dqkv[:, (Hq + Hkv) * hd:]
+    ops.attn_bwd(q, k, v, out, do, lse, lo, hi, shared, Hq, Hkv, hd, scale, dq, dk, dv)
+    for name, got, want in (("dq", dq, qa.grad), ("dk", dk, ka.grad), ("dv", dv, va.grad)):
+        want = want.reshape(T, -1)
+        tol = 3e-2 * want.abs().max().item()
+        close(got, want, tol, 3e-2, f"attn bwd {kind} {name}")
+
+
+# ------------------------------------------------------------------ decode kernels
+@pytest.mark.parametrize("M,N,K", [(8, 3584, 3584), (8, 512, 18944), (4, 4096, 256), (16, 1536, 1536), (33, 2048, 512), (64, 256, 1024)])
+def test_skinny_gemm(M, N, K):
+    from time_r1_b200 import ops
+
+    x, w, b = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=0.05), rnd(N, seed=3)
+    ref = x.float() @ w.float().t() + b.float()
+    out = ops.skinny_gemm(x, w, bias=b, out_dtype=torch.float32)
+    close(out, ref, 2e-3 * math.sqrt(K) * 0.05, 1e-4, "skinny fp32")
+    o2 = ops.skinny_gemm(x, w, bias=b)
+    close(o2, ref, 1e-2, 1e-2, "skinny bf16")
+    acc = o2.clone()
+    ops.skinny_gemm(x, w, out=acc, accumulate=True)
+    close(acc, o2.float() + x.float() @ w.float().t(), 3e-2, 2e-2, "skinny accumulate")
+
+
+@pytest.mark.parametrize("B,Hq,Hkv,P,step,cpad", [(8, 28, 4, 1000, 0, 256), (8, 28, 4, 517, 130, 256), (4, 12, 2, 250, 37, 128), (3, 2, 1, 64, 5, 128), (20, 28, 4, 300, 17, 128)])
+def test_decode_attention(B, Hq, Hkv, P, step, cpad):
+    from time_r1_b200 import ops
+    from time_r1_b200.lib import call, ptr, stream_ptr
+
+    hd = 128
+    S = P + B * cpad
+    Kc, Vc = rnd(S, Hkv * hd, seed=1), rnd(S, Hkv * hd, seed=2)
+    q = rnd(B, Hq * hd, seed=3)
+    step_t = torch.tensor([step], device=DEV, dtype=torch.int32)
+    ratio = Hq // Hkv
+    n_chunks = (P + 127) // 128 + B * (cpad // 128)
+    rows_pad = ((B * ratio + 63) // 64) * 64
+    ws_o = torch.empty(n_chunks * Hkv * rows_pad * 128, device=DEV)
+    ws_ml = torch.empty(n_chunks * Hkv * rows_pad * 2, device=DEV)
+    out = torch.empty(B, Hq * hd, device=DEV, dtype=BF16)
+    scale = hd ** -0.5
+    call("t1_decode_attn", ptr(q), q.stride(0), ptr(Kc), ptr(Vc), B, Hq, Hkv, hd, P, cpad, ptr(step_t), ptr(ws_o),
+         ptr(ws_ml), ptr(out), out.stride(0), scale, stream_ptr())
+    for b in range(B):
+        idx = torch.cat([torch.arange(P, device=DEV), P + b * cpad + torch.arange(step + 1, device=DEV)])
+        kk = Kc[idx].float().view(-1, Hkv, hd).repeat_interleave(ratio, 1)
+        vv = Vc[idx].float().view(-1, Hkv, hd).repeat_interleave(ratio, 1)
+        qq = q[b].float().view(Hq, hd)
+        p = torch.softmax(torch.einsum("hd,jhd->hj", qq, kk) * scale, -1)
+        ref = torch.einsum("hj,jhd->hd", p, vv).reshape(-1)
+        close(out[b], ref, 2e-2, 2e-2, f"decode attn seq {b}")
+
+
+def test_decode_rope_append():
+    from time_r1_b200.lib import call, ptr, stream_ptr
+
+    B, Hq, Hkv, hd, P, cpad, step = 3, 4, 2, 128, 10, 128, 6
+    ld = (Hq + 2 * Hkv) * hd
+    qkv = rnd(B, ld, seed=1)
+    q0 = qkv.clone()
+    cos, sin = torch.rand(16, hd // 2, device=DEV), torch.rand(16, hd // 2, device=DEV)
+    Kc = torch.zeros(P + B * cpad, Hkv * hd, device=DEV, dtype=BF16)
+    Vc = torch.zeros_like(Kc)
+    st = torch.tensor([step], device=DEV, dtype=torch.int32)
+    call("t1_decode_rope_append", ptr(qkv), ld, B, Hq, Hkv, hd, ptr(cos), ptr(sin), ptr(st), ptr(Kc), ptr(Vc), P, cpad, stream_ptr())
+    x = q0[:, :(Hq + Hkv) * hd].float().view(B, Hq + Hkv, hd)
+    a, b = x[..., :64], x[..., 64:]
+    ref = torch.cat([a * cos[step] - b * sin[step], b * cos[step] + a * sin[step]], -1)
+    close(qkv[:, :(Hq + Hkv) * hd].view(B, Hq + Hkv, hd), ref, 2e-2, 1e-2, "decode rope")
+    for bi in range(B):
+        slot = P + bi * cpad + step
+        assert torch.equal(Kc[slot], qkv[bi, Hq * hd:(Hq + Hkv) * hd])
+        assert torch.equal(Vc[slot], q0[bi, (Hq + Hkv) * hd:])
+    assert Kc.float().abs().sum(1).ne(0).sum().item() == B
+
+
+def test_sampler_topk_greedy_and_distribution():
+    from time_r1_b200.lib import call, ptr, stream_ptr
+
+    B, V = 8, 152064
+    logits = torch.randn(B, V, device=DEV, generator=torch.Generator(device=DEV).manual_seed(3)) * 3
+    logits[0, 77] = 50.0
+    out = torch.zeros(B, 4, device=DEV, dtype=torch.int32)
+    nxt = torch.zeros(B, device=DEV, dtype=torch.int32)
+    fin = torch.zeros(B, device=DEV, dtype=torch.int32)
+    eos = torch.tensor([151645, 151643], device=DEV, dtype=torch.int32)
+    st = torch.tensor([1], device=DEV, dtype=torch.int32)
+
+    def run(temp, k, seed, step_off=0):
+        call("t1_sample", ptr(logits), V, B, V, float(temp), k, seed, ptr(st), step_off, ptr(eos), 2, 151643, ptr(fin),
+             ptr(out), 4, ptr(nxt), 0, stream_ptr())
+        torch.cuda.synchronize()
+        return nxt.clone()
+
+    g = run(0.0, 50, 1)
+    assert torch.equal(g.long(), logits.argmax(-1)), "greedy = argmax"
+    assert torch.equal(out[:, 1], g)
+    top50 = logits.topk(50, -1).indices
+    hits = torch.zeros(B, 50, device=DEV)
+    n = 400
+    for s in range(n):
+        t = run(1.0, 50, 1000 + s)
+        m = top50 == t[:, None].long()
+        assert m.any(-1).all(), "sampled token must lie inside the top-k set"
+        hits += m.float()
+    # empirical frequencies vs the renormalised top-50 softmax: 400 draws -> ~5 sigma bound
+    p = torch.softmax(torch.gather(logits, 1, top50), -1)
+    sigma = (p * (1 - p) / n).sqrt()
+    assert ((hits / n - p).abs() <= 5 * sigma + 2e-3).all()
+    assert torch.equal(run(1.0, 50, 42), run(1.0, 50, 42)), "same seed/step -> same tokens"
+    assert run(1.0, 50, 7)[0].item() == 77, "a dominant logit is always drawn"
+    # finished sequences emit pad; eos marks finished
+    logits2 = logits.clone()
+    logits[1, 151645] = 80.0
+    t = run(1.0, 50, 9)
+    assert t[1].item() == 151645 and fin[1].item() == 1
+    t = run(1.0, 50, 10)
+    assert t[1].item() == 151643
+    logits.copy_(logits2)
+
+
+# ------------------------------------------------------------------ GRPO kernels vs torch
+def test_logprob_entropy_and_logits_backward():
+    from time_r1_b200 import ops
+
+    R, V = 37, 152064
+    logits = (torch.randn(R, V, device=DEV, generator=torch.Generator(device=DEV).manual_seed(1)) * 2).contiguous()
+    tgt = torch.randint(0, V, (R,), device=DEV, dtype=torch.int32)
+    lp, ent, lse = ops.logprob_entropy(logits, tgt)
+    la = logits.clone().requires_grad_(True)
+    ls = torch.log_softmax(la, -1)
+    ref_lp = ls.gather(1, tgt.long()[:, None])[:, 0]
+    ref_ent = -(ls.exp() * ls).sum(-1)
+    close(lp, ref_lp, 1e-4, 1e-5, "logp")
+    close(ent, ref_ent, 1e-4, 1e-5, "entropy")
+    close(lse, torch.logsumexp(logits, -1), 1e-4, 1e-6, "lse")
+    dlogp = torch.randn(R, device=DEV)
+    ref_lp.backward(dlogp)
+    d = ops.logits_backward(logits, tgt, lse, dlogp)
+    close(d, la.grad, 1e-5, 1e-2, "dlogits (bf16)")
+
+
+@pytest.mark.parametrize("use_grpo", [False, True])
+@pytest.mark.parametrize("beta", [0.0, 0.04])
+def test_grpo_loss_matches_autograd(use_grpo, beta):
+    from time_r1_b200 import ops
+
+    G, C = 8, 57
+    g = torch.Generator(device=DEV).manual_seed(11)
+    logp = -torch.rand(G, C, device=DEV, generator=g) * 3
+    ref_logp = logp + 0.3 * torch.randn(G, C, device=DEV, generator=g)
+    ent = torch.rand(G, C, device=DEV, generator=g)
+    adv = torch.randn(G, device=DEV, generator=g)
+    lengths = torch.randint(1, C + 1, (G,), device=DEV, generator=g)
+    mask = (torch.arange(C, device=DEV)[None, :] < lengths[:, None]).int()
+    loss, dlogp, stats = ops.grpo_loss(logp, ref_logp if beta else None, ent, adv, mask, beta, 0.2, 0.2, use_grpo)
+    lp = logp.clone().requires_grad_(True)
+    kl = torch.exp(ref_logp - lp) - (ref_logp - lp) - 1
+    if use_grpo:
+        ptl = torch.exp(lp - lp.detach()) * adv[:, None]
+        ptl = -(ptl - beta * kl) if beta else -ptl
+        ref = ((ptl * mask).sum(1) / mask.sum(1)).mean()
+    else:
+        c1 = torch.exp(lp - lp.detach())
+        c2 = torch.clamp(c1, 0.8, 1.2)
+        ptl = -torch.min(c1 * adv[:, None], c2 * adv[:, None])
+        if beta:
+            ptl = ptl + beta * kl
+        ref = (ptl * mask).sum() / mask.sum()
+    ref.backward()
+    close(loss, ref.detach().reshape(1), 1e-6, 1e-5, "loss")
+    close(dlogp, lp.grad, 1e-7, 1e-4, "dlogp")
+    if beta:
+        close(stats[1:2], ((kl * mask).sum(1) / mask.sum(1)).mean().detach().reshape(1), 1e-6, 1e-5, "mean kl")
+    close(stats[2:3], ((ent * mask).sum(1) / mask.sum(1).clamp(min=1)).mean().reshape(1), 1e-6, 1e-5, "entropy metric")
+    close(stats[3:4], mask.sum(1).float().mean().reshape(1), 1e-6, 1e-6, "completion length")
+
+
+def test_group_advantage_and_eos_mask():
+    from time_r1_b200 import ops
+
+    G, groups, nf = 8, 5, 2
+    rpf = torch.rand(G * groups, nf, device=DEV)
+    rewards, adv, mean, std = ops.group_advantage(rpf, G)
+    r = rpf.sum(1)
+    m = r.view(-1, G).mean(1)
+    s = r.view(-1, G).std(1)
+    close(rewards, r, 1e-6, 1e-6, "reward sum")
+    close(mean, m, 1e-6, 1e-6, "group mean")
+    close(std, s, 1e-6, 1e-5, "group std (unbiased)")
+    close(adv, (r - m.repeat_interleave(G)) / (s.repeat_interleave(G) + 1e-4), 1e-5, 1e-4, "advantage")
+    # all-equal rewards -> advantage exactly 0 (random-init case)
+    _, adv0, _, std0 = ops.group_advantage(torch.ones(G, 2, device=DEV), G)
+    assert adv0.abs().max().item() == 0 and std0.item() == 0
+    ids = torch.randint(0, 1000, (6, 33), device=DEV, dtype=torch.int32)
+    ids[1, 5] = 151645
+    ids[1, 9] = 151645
+    ids[3, 0] = 151645
+    ids[4, 32] = 151645
+    mask, lengths = ops.eos_mask(ids, 151645)
+    is_eos = ids == 151645
+    eos_idx = torch.full((6,), 33, device=DEV, dtype=torch.long)
+    eos_idx[is_eos.any(1)] = is_eos.int().argmax(1)[is_eos.any(1)]
+    ref = (torch.arange(33, device=DEV)[None, :] <= eos_idx[:, None]).int()
+    assert torch.equal(mask, ref)
+    assert torch.equal(lengths.long(), ref.sum(1))
+
+
+def test_adamw_and_sumsq_match_torch():
+    from time_r1_b200 import ops
+
+    n = 100_000
+    p0 = rnd(n, seed=1, scale=0.02)
+    master = p0.float().clone()
+    m, v = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    param = p0.clone()
+    ref_p = torch.nn.Parameter(p0.float().clone())
+    opt = torch.optim.AdamW([ref_p], lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01)
+    for step in range(1, 4):
+        grad = rnd(n, seed=10 + step, scale=3.0)
+        gsq = torch.zeros(1, device=DEV)
+        ops.sumsq(grad, gsq)
+        close(gsq, grad.float().pow(2).sum().reshape(1), 0, 1e-4, "sumsq")
+        ops.adamw(master, m, v, grad, param, 1e-3, 0.9, 0.999, 1e-8, 0.01, step, gnorm_sq=gsq, max_norm=1.0)
+        ref_p.grad = grad.float().clone()
+        torch.nn.utils.clip_grad_norm_([ref_p], 1.0)
+        opt.step()
+        close(master, ref_p.detach(), 1e-7, 1e-5, f"adamw master step {step}")
+        assert torch.equal(param, master.to(BF16))

@@ -1,0 +1,564 @@
+// Decode-phase kernels of the GRPO rollout (replaces HF GenerationMixin._sample driven from
+// src/time_r1/rl/timer1_trainer.py:568-573): all HBM-bandwidth-bound.
+//   * skinny GEMM      y[M<=64, N] = x[M,K] W[N,K]^T   — streams W once with 16-byte loads, HMMA m16n8k16 with the
+//                      batch rows on the N=8 side and a k-permutation so that each thread's 16-byte load IS its
+//                      fragment (no shared-memory staging of weights)
+//   * decode attention — split-KV over a unified key space [prompt prefix | per-sequence completion slots]; the G
+//                      sequences of a group share ONE copy of the prompt K/V, so (G x q-heads-per-kv-head) query rows
+//                      form a 64-row MMA tile against each prefix key chunk; partial (m, l, O) + a combine kernel
+//   * rope + KV append, sampler (temperature -> top-k -> softmax -> multinomial, Philox4x32-10), step counter
+#include "t1_common.cuh"
+
+namespace {
+
+// =============================================================================================
+// skinny GEMM
+// =============================================================================================
+template <int NB>
+__global__ void __launch_bounds__(256)
+skinny_gemm_kernel(const bf16* __restrict__ x, long long ldx, const bf16* __restrict__ W, long long ldw,
+                   const bf16* __restrict__ bias, void* __restrict__ y, long long ldy, int M, int N, int K,
+                   int out_f32, int accumulate) {
+  __shared__ float red[8][16][8 * NB + 1];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int n0 = blockIdx.x * 16;
+  float acc[NB][4];
+#pragma unroll
+  for (int i = 0; i < NB; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+  const bf16* w0 = W + (long long)(n0 + g) * ldw + t4 * 8;
+  const bf16* w1 = W + (long long)(n0 + g + 8) * ldw + t4 * 8;
+#pragma unroll 4
+  for (int kb = warp * 32; kb < K; kb += 256) {
+    const uint4 wa = __ldg(reinterpret_cast<const uint4*>(w0 + kb));
+    const uint4 wb = __ldg(reinterpret_cast<const uint4*>(w1 + kb));
+    const uint32_t a_lo[4] = {wa.x, wb.x, wa.y, wb.y};
+    const uint32_t a_hi[4] = {wa.z, wb.z, wa.w, wb.w};
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) {
+      const int m = nb * 8 + g;
+      uint4 xb = make_uint4(0, 0, 0, 0);
+      if (m < M) xb = *reinterpret_cast<const uint4*>(x + (long long)m * ldx + kb + t4 * 8);
+      const uint32_t b_lo[2] = {xb.x, xb.y};
+      const uint32_t b_hi[2] = {xb.z, xb.w};
+      mma_bf16_16816(acc[nb], a_lo, b_lo);
+      mma_bf16_16816(acc[nb], a_hi, b_hi);
+    }
+  }
+#pragma unroll
+  for (int nb = 0; nb < NB; ++nb) {
+    red[warp][g][nb * 8 + t4 * 2] = acc[nb][0];
+    red[warp][g][nb * 8 + t4 * 2 + 1] = acc[nb][1];
+    red[warp][g + 8][nb * 8 + t4 * 2] = acc[nb][2];
+    red[warp][g + 8][nb * 8 + t4 * 2 + 1] = acc[nb][3];
+  }
+  __syncthreads();
+  for (int e = tid; e < 16 * 8 * NB; e += 256) {
+    const int f = e & 15, m = e >> 4;
+    if (m < M) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += red[w][f][m];
+      if (bias) s += __bfloat162float(bias[n0 + f]);
+      if (out_f32) {
+        float* yp = reinterpret_cast<float*>(y) + (long long)m * ldy + n0 + f;
+        *yp = accumulate ? *yp + s : s;
+      } else {
+        bf16* yp = reinterpret_cast<bf16*>(y) + (long long)m * ldy + n0 + f;
+        *yp = __float2bfloat16(accumulate ? __bfloat162float(*yp) + s : s);
+      }
+    }
+  }
+}
+
+// =============================================================================================
+// decode rope + KV append. One CTA per sequence. q,k rotated with table row *step_ptr; k,v appended at
+// slot = prefix_len + b * cpad + step of the layer's cache.
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+decode_rope_append_kernel(bf16* __restrict__ qkv, long long ld, int Hq, int Hkv, int HD, const float* __restrict__ cos_t,
+                          const float* __restrict__ sin_t, const int* __restrict__ step_ptr, bf16* __restrict__ Kc,
+                          bf16* __restrict__ Vc, int prefix_len, int cpad) {
+  const int b = blockIdx.x;
+  const int step = *step_ptr;
+  const int half = HD >> 1;
+  const float* c = cos_t + (long long)step * half;
+  const float* s = sin_t + (long long)step * half;
+  bf16* row = qkv + (long long)b * ld;
+  const long long slot = (long long)prefix_len + (long long)b * cpad + step;
+  const int n_rot = (Hq + Hkv) * half;
+  for (int e = threadIdx.x; e < n_rot; e += blockDim.x) {
+    const int h = e / half, i = e - h * half;
+    bf16* p = row + h * HD + i;
+    const float a = __bfloat162float(p[0]), bb = __bfloat162float(p[half]);
+    const float ra = a * c[i] - bb * s[i], rb = bb * c[i] + a * s[i];
+    const bf16 oa = __float2bfloat16(ra), ob = __float2bfloat16(rb);
+    p[0] = oa;
+    p[half] = ob;
+    if (h >= Hq) {
+      bf16* kd = Kc + slot * (Hkv * HD) + (h - Hq) * HD + i;
+      kd[0] = oa;
+      kd[half] = ob;
+    }
+  }
+  const bf16* vsrc = row + (Hq + Hkv) * HD;
+  bf16* vd = Vc + slot * (Hkv * HD);
+  for (int e = threadIdx.x; e < Hkv * HD; e += blockDim.x) vd[e] = vsrc[e];
+}
+
+// =============================================================================================
+// decode attention (HD = 128): grid (n_chunks, Hkv, row_tiles); 128 threads; 128 keys per CTA.
+// Key slot j: j < prefix_len -> prompt key (visible to every row); otherwise seq = (j-P)/cpad, c = (j-P)%cpad,
+// visible iff seq == row's sequence and c <= step.
+// =============================================================================================
+constexpr int DA_KEYS = 128;
+constexpr int DA_LDS = 128 + 8;
+
+__global__ void __launch_bounds__(128)
+decode_attn_kernel(const bf16* __restrict__ q, long long ldq, const bf16* __restrict__ Kc, const bf16* __restrict__ Vc,
+                   int Hq, int Hkv, int B, int prefix_len, int cpad, const int* __restrict__ step_ptr,
+                   float* __restrict__ ws_o, float* __restrict__ ws_ml, int n_prefix_chunks, int rows_pad,
+                   float scale_log2) {
+  constexpr int HD = 128, LDS = DA_LDS;
+  extern __shared__ __align__(16) uint8_t da_smem[];
+  bf16* sQ = reinterpret_cast<bf16*>(da_smem);   // 64 x LDS
+  bf16* sK = sQ + 64 * LDS;                      // 128 x LDS
+  bf16* sV = sK + DA_KEYS * LDS;                 // 128 x LDS
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int chunk = blockIdx.x, hk = blockIdx.y, rt = blockIdx.z;
+  const int ratio = Hq / Hkv;
+  const int n_rows = B * ratio;
+  const int step = *step_ptr;
+  const int chunks_per_seq = cpad / DA_KEYS;
+
+  // key slot range of this chunk
+  int j0, nvalid;  // first slot, number of real keys
+  int chunk_seq = -1;
+  if (chunk < n_prefix_chunks) {
+    j0 = chunk * DA_KEYS;
+    nvalid = min(DA_KEYS, prefix_len - j0);
+  } else {
+    const int sc = chunk - n_prefix_chunks;
+    chunk_seq = sc / chunks_per_seq;
+    const int c0 = (sc - chunk_seq * chunks_per_seq) * DA_KEYS;
+    j0 = prefix_len + chunk_seq * cpad + c0;
+    nvalid = min(DA_KEYS, step + 1 - c0);
+  }
+  const long long ws_row0 = ((long long)chunk * Hkv + hk) * rows_pad + rt * 64;
+  const int row_a = rt * 64 + warp * 16 + g, row_b = row_a + 8;
+  const int seq_a = row_a / ratio, seq_b = row_b / ratio;
+  // rows of other sequences see nothing in a completion chunk
+  const bool tile_has_seq = chunk_seq < 0 || (chunk_seq >= (rt * 64) / ratio && chunk_seq <= min(n_rows - 1, rt * 64 + 63) / ratio);
+  if (nvalid <= 0 || !tile_has_seq) {
+    if (t4 == 0) {
+      ws_ml[(ws_row0 + warp * 16 + g) * 2] = -INFINITY;
+      ws_ml[(ws_row0 + warp * 16 + g) * 2 + 1] = 0.f;
+      ws_ml[(ws_row0 + warp * 16 + g + 8) * 2] = -INFINITY;
+      ws_ml[(ws_row0 + warp * 16 + g + 8) * 2 + 1] = 0.f;
+    }
+    return;
+  }
+  // ---- loads: Q rows (gathered per (seq, head)), K/V chunk ----
+  for (int e = tid; e < 64 * 16; e += 128) {
+    const int r = e >> 4, c = e & 15;
+    const int row = rt * 64 + r;
+    const bool ok = row < n_rows;
+    const int sq = ok ? row / ratio : 0, hq = hk * ratio + (ok ? row % ratio : 0);
+    cp_async_16(smem_u32(sQ + r * LDS + c * 8), q + (long long)sq * ldq + (long long)hq * HD + c * 8, ok);
+  }
+  for (int e = tid; e < DA_KEYS * 16; e += 128) {
+    const int r = e >> 4, c = e & 15;
+    const bool ok = r < nvalid;
+    const long long slot = j0 + (ok ? r : 0);
+    cp_async_16(smem_u32(sK + r * LDS + c * 8), Kc + (slot * Hkv + hk) * HD + c * 8, ok);
+    cp_async_16(smem_u32(sV + r * LDS + c * 8), Vc + (slot * Hkv + hk) * HD + c * 8, ok);
+  }
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
+
+  uint32_t qf[8][4];
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks)
+    ldmatrix_x4(qf[ks], smem_u32(sQ + (warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDS + ks * 16 + (lane >> 4) * 8));
+
+  float o_acc[16][4];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) o_acc[i][0] = o_acc[i][1] = o_acc[i][2] = o_acc[i][3] = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+
+#pragma unroll 1
+  for (int kt = 0; kt < DA_KEYS / 64; ++kt) {
+    if (kt * 64 >= nvalid) break;
+    const bf16* kb = sK + kt * 64 * LDS;
+    const bf16* vb = sV + kt * 64 * LDS;
+    float s[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+        uint32_t kf[4];
+        ldmatrix_x4(kf, smem_u32(kb + (np * 16 + (lane & 7) + (lane >> 4) * 8) * LDS + ks * 16 + ((lane >> 3) & 1) * 8));
+        mma_bf16_16816(s[np * 2], qf[ks], kf);
+        mma_bf16_16816(s[np * 2 + 1], qf[ks], kf + 2);
+      }
+    }
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int kidx = kt * 64 + nt * 8 + t4 * 2 + (e & 1);
+        const int rseq = (e < 2) ? seq_a : seq_b;
+        const bool vis = kidx < nvalid && (chunk_seq < 0 || chunk_seq == rseq);
+        const float val = vis ? s[nt][e] * scale_log2 : -INFINITY;
+        s[nt][e] = val;
+        if (e < 2) mx0 = fmaxf(mx0, val); else mx1 = fmaxf(mx1, val);
+      }
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+    const float mu0 = mn0 == -INFINITY ? 0.f : mn0, mu1 = mn1 == -INFINITY ? 0.f : mn1;
+    const float al0 = exp2f(m0 - mu0), al1 = exp2f(m1 - mu1);
+    m0 = mn0;
+    m1 = mn1;
+    float rs0 = 0.f, rs1 = 0.f;
+    uint32_t pf[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const float p0 = exp2f(s[nt][0] - mu0), p1 = exp2f(s[nt][1] - mu0);
+      const float p2 = exp2f(s[nt][2] - mu1), p3 = exp2f(s[nt][3] - mu1);
+      rs0 += p0 + p1;
+      rs1 += p2 + p3;
+      pf[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16x2(p0, p1);
+      pf[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+    }
+    l0 = l0 * al0 + rs0;
+    l1 = l1 * al1 + rs1;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      o_acc[i][0] *= al0; o_acc[i][1] *= al0; o_acc[i][2] *= al1; o_acc[i][3] *= al1;
+    }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+      for (int dp = 0; dp < 8; ++dp) {
+        uint32_t vf[4];
+        ldmatrix_x4_trans(vf, smem_u32(vb + (kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDS + dp * 16 + (lane >> 4) * 8));
+        mma_bf16_16816(o_acc[dp * 2], pf[kk], vf);
+        mma_bf16_16816(o_acc[dp * 2 + 1], pf[kk], vf + 2);
+      }
+    }
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  // un-normalised partials
+  float* oa = ws_o + (ws_row0 + warp * 16 + g) * HD;
+  float* ob = ws_o + (ws_row0 + warp * 16 + g + 8) * HD;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    *reinterpret_cast<float2*>(oa + i * 8 + t4 * 2) = make_float2(o_acc[i][0], o_acc[i][1]);
+    *reinterpret_cast<float2*>(ob + i * 8 + t4 * 2) = make_float2(o_acc[i][2], o_acc[i][3]);
+  }
+  if (t4 == 0) {
+    ws_ml[(ws_row0 + warp * 16 + g) * 2] = m0;
+    ws_ml[(ws_row0 + warp * 16 + g) * 2 + 1] = l0;
+    ws_ml[(ws_row0 + warp * 16 + g + 8) * 2] = m1;
+    ws_ml[(ws_row0 + warp * 16 + g + 8) * 2 + 1] = l1;
+  }
+}
+
+// combine partials: one CTA (128 threads = head dim) per (seq, q head)
+__global__ void __launch_bounds__(128)
+decode_attn_combine_kernel(const float* __restrict__ ws_o, const float* __restrict__ ws_ml, int n_chunks,
+                           int n_prefix_chunks, int chunks_per_seq, int Hq, int Hkv, int rows_pad,
+                           bf16* __restrict__ out, long long ldo) {
+  const int b = blockIdx.x / Hq, hq = blockIdx.x % Hq;
+  const int ratio = Hq / Hkv, hk = hq / ratio;
+  const int row = b * ratio + (hq - hk * ratio);
+  const int d = threadIdx.x;
+  float M = -INFINITY;
+  for (int c = 0; c < n_chunks; ++c) {
+    if (c >= n_prefix_chunks && (c - n_prefix_chunks) / chunks_per_seq != b) continue;
+    M = fmaxf(M, ws_ml[(((long long)c * Hkv + hk) * rows_pad + row) * 2]);
+  }
+  float L = 0.f, acc = 0.f;
+  for (int c = 0; c < n_chunks; ++c) {
+    if (c >= n_prefix_chunks && (c - n_prefix_chunks) / chunks_per_seq != b) continue;
+    const long long r = ((long long)c * Hkv + hk) * rows_pad + row;
+    const float m = ws_ml[r * 2], l = ws_ml[r * 2 + 1];
+    if (l > 0.f) {
+      const float w = exp2f(m - M);
+      L += w * l;
+      acc += w * ws_o[r * 128 + d];
+    }
+  }
+  out[(long long)b * ldo + hq * 128 + d] = __float2bfloat16(L > 0.f ? acc / L : 0.f);
+}
+
+// =============================================================================================
+// sampler: one CTA per sequence.
+// =============================================================================================
+__device__ __forceinline__ uint32_t float_key(float x) {
+  const uint32_t u = __float_as_uint(x);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ uint32_t mulhilo(uint32_t a, uint32_t b, uint32_t* hi) {
+  const unsigned long long p = (unsigned long long)a * b;
+  *hi = (uint32_t)(p >> 32);
+  return (uint32_t)p;
+}
+// Philox4x32-10 (Salmon et al. 2011), returns 4 uniform 32-bit words for (counter, key).
+__device__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0, hi1;
+    const uint32_t lo0 = mulhilo(0xD2511F53u, c[0], &hi0);
+    const uint32_t lo1 = mulhilo(0xCD9E8D57u, c[2], &hi1);
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+}
+
+__global__ void __launch_bounds__(1024, 1)
+sample_kernel(const float* __restrict__ logits, long long ld, int V, float temperature, int top_k,
+              unsigned long long seed, const int* __restrict__ step_ptr, int step_offset, const int* __restrict__ eos_ids,
+              int n_eos, int pad_id, int* __restrict__ finished, int* __restrict__ out_ids, int out_ld,
+              int* __restrict__ next_ids, float* __restrict__ out_u) {
+  __shared__ unsigned int hist[2048];
+  __shared__ float red[33];
+  __shared__ float wsum[32];
+  __shared__ unsigned int s_prefix, s_krem;
+  __shared__ unsigned long long s_best;
+  __shared__ int s_tok;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int step = (step_ptr ? *step_ptr : 0) + step_offset;
+  const float* x = logits + (long long)b * ld;
+  const bool greedy = !(temperature > 0.f);
+  const float inv_t = greedy ? 1.f : 1.f / temperature;
+  int token = 0;
+
+  if (greedy) {
+    // argmax, lowest index wins ties
+    unsigned long long best = 0;
+    for (int i = tid; i < V; i += blockDim.x) {
+      const unsigned long long cand = ((unsigned long long)float_key(x[i]) << 32) | (uint32_t)(0xFFFFFFFFu - (uint32_t)i);
+      best = cand > best ? cand : best;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+      best = other > best ? other : best;
+    }
+    if (tid == 0) s_best = 0;
+    __syncthreads();
+    if ((tid & 31) == 0) atomicMax(&s_best, best);
+    __syncthreads();
+    token = (int)(0xFFFFFFFFu - (uint32_t)(s_best & 0xFFFFFFFFu));
+  } else {
+    // ---- radix select of the k-th largest scaled logit (11 + 11 + 10 bits) ----
+    uint32_t thr_key = 0;  // keep everything when top_k is disabled
+    if (top_k > 0 && top_k < V) {
+      if (tid == 0) { s_prefix = 0; s_krem = (unsigned)top_k; }
+      const int shifts[3] = {21, 10, 0};
+      const int bits[3] = {11, 11, 10};
+      uint32_t mask = 0;
+      for (int pass = 0; pass < 3; ++pass) {
+        for (int i = tid; i < 2048; i += blockDim.x) hist[i] = 0;
+        __syncthreads();
+        const uint32_t prefix = s_prefix;
+        const int sh = shifts[pass];
+        const uint32_t dmask = (1u << bits[pass]) - 1u;
+        for (int i = tid; i < V; i += blockDim.x) {
+          const uint32_t key = float_key(x[i] * inv_t);
+          if ((key & mask) == prefix) atomicAdd(&hist[(key >> sh) & dmask], 1u);
+        }
+        __syncthreads();
+        if (tid == 0) {
+          unsigned krem = s_krem;
+          int d = (int)dmask;
+          for (; d > 0; --d) {
+            if (hist[d] >= krem) break;
+            krem -= hist[d];
+          }
+          s_prefix = prefix | ((uint32_t)d << sh);
+          s_krem = krem;
+        }
+        mask |= dmask << sh;
+        __syncthreads();
+      }
+      thr_key = s_prefix;
+    }
+    // ---- softmax over the kept set {key >= thr_key}: contiguous index range per thread (deterministic) ----
+    const int per = (V + blockDim.x - 1) / blockDim.x;
+    const int i0 = tid * per, i1 = min(V, i0 + per);
+    float mx = -INFINITY;
+    for (int i = i0; i < i1; ++i) {
+      const float v = x[i] * inv_t;
+      if (float_key(v) >= thr_key) mx = fmaxf(mx, v);
+    }
+    const float gmax = block_max(mx, red);
+    float part = 0.f;
+    for (int i = i0; i < i1; ++i) {
+      const float v = x[i] * inv_t;
+      if (float_key(v) >= thr_key) part += expf(v - gmax);
+    }
+    // block exclusive scan of `part`
+    const int lane = tid & 31, wid = tid >> 5;
+    float inc = part;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float n = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += n;
+    }
+    if (lane == 31) wsum[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+      float w = wsum[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float n = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += n;
+      }
+      wsum[lane] = w;  // inclusive
+    }
+    __syncthreads();
+    const float total = wsum[31];
+    const float excl = inc - part + (wid > 0 ? wsum[wid - 1] : 0.f);
+    uint32_t ctr[4] = {(uint32_t)b, (uint32_t)step, 0u, 0u};
+    philox4x32_10(ctr, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const float u = ((float)(ctr[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);  // (0,1)
+    if (out_u && tid == 0) out_u[b] = u;
+    const float target = u * total;
+    if (tid == 0) s_tok = 0x7fffffff;
+    __syncthreads();
+    if (part > 0.f && target >= excl && target < excl + part) {
+      float run = excl;
+      int pick = -1;
+      for (int i = i0; i < i1; ++i) {
+        const float v = x[i] * inv_t;
+        if (float_key(v) >= thr_key) {
+          run += expf(v - gmax);
+          pick = i;
+          if (target < run) break;
+        }
+      }
+      if (pick >= 0) atomicMin(&s_tok, pick);
+    }
+    __syncthreads();
+    if (s_tok == 0x7fffffff) {
+      // rounding at the very end of the CDF: take the highest kept index
+      if (tid == 0) s_best = 0;
+      __syncthreads();
+      unsigned long long best = 0;
+      for (int i = i0; i < i1; ++i)
+        if (float_key(x[i] * inv_t) >= thr_key) best = (unsigned long long)(i + 1);
+      if (best) atomicMax(&s_best, best);
+      __syncthreads();
+      token = (int)s_best - 1;
+    } else {
+      token = s_tok;
+    }
+  }
+  if (tid == 0) {
+    int fin = finished ? finished[b] : 0;
+    if (fin) token = pad_id;
+    else
+      for (int e = 0; e < n_eos; ++e)
+        if (token == eos_ids[e]) fin = 1;
+    if (finished) finished[b] = fin;
+    if (out_ids) out_ids[(long long)b * out_ld + step] = token;
+    if (next_ids) next_ids[b] = token;
+  }
+}
+
+__global__ void incr_kernel(int* p, int v) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) *p += v;
+}
+
+}  // namespace
+
+extern "C" int t1_skinny_gemm(const void* x, long long ldx, const void* W, long long ldw, const void* bias, void* y,
+                              long long ldy, int M, int N, int K, int out_f32, int accumulate, cudaStream_t stream) {
+  T1_CHECK_ARG(M > 0 && M <= 64, "t1_skinny_gemm: M=%d must be in [1, 64]", M);
+  T1_CHECK_ARG(N % 16 == 0 && K % 32 == 0, "t1_skinny_gemm: N %% 16 and K %% 32 required (N=%d K=%d)", N, K);
+  T1_CHECK_ARG(ldx % 8 == 0 && ldw % 8 == 0, "t1_skinny_gemm: ldx/ldw must be multiples of 8");
+  const bf16* xb = (const bf16*)x;
+  const bf16* wb = (const bf16*)W;
+  const bf16* bb = (const bf16*)bias;
+  const int grid = N / 16;
+  if (M <= 8) skinny_gemm_kernel<1><<<grid, 256, 0, stream>>>(xb, ldx, wb, ldw, bb, y, ldy, M, N, K, out_f32, accumulate);
+  else if (M <= 16) skinny_gemm_kernel<2><<<grid, 256, 0, stream>>>(xb, ldx, wb, ldw, bb, y, ldy, M, N, K, out_f32, accumulate);
+  else if (M <= 32) skinny_gemm_kernel<4><<<grid, 256, 0, stream>>>(xb, ldx, wb, ldw, bb, y, ldy, M, N, K, out_f32, accumulate);
+  else skinny_gemm_kernel<8><<<grid, 256, 0, stream>>>(xb, ldx, wb, ldw, bb, y, ldy, M, N, K, out_f32, accumulate);
+  T1_CUDA_LAUNCH_CHECK("t1_skinny_gemm");
+  return T1_OK;
+}
+
+extern "C" int t1_decode_rope_append(void* qkv, long long ld, int B, int Hq, int Hkv, int head_dim, const float* cos_t,
+                                     const float* sin_t, const int* step_ptr, void* Kc, void* Vc, int prefix_len,
+                                     int cpad, cudaStream_t stream) {
+  T1_CHECK_ARG(B > 0 && head_dim % 2 == 0, "t1_decode_rope_append: bad arguments");
+  decode_rope_append_kernel<<<B, 256, 0, stream>>>((bf16*)qkv, ld, Hq, Hkv, head_dim, cos_t, sin_t, step_ptr, (bf16*)Kc,
+                                                   (bf16*)Vc, prefix_len, cpad);
+  T1_CUDA_LAUNCH_CHECK("t1_decode_rope_append");
+  return T1_OK;
+}
+
+// workspace sizes (floats): ws_o = n_chunks*Hkv*rows_pad*128, ws_ml = n_chunks*Hkv*rows_pad*2,
+// with n_chunks = ceil(prefix_len/128) + B*cpad/128 and rows_pad = ceil(B*Hq/Hkv / 64) * 64
+extern "C" int t1_decode_attn(const void* q, long long ldq, const void* Kc, const void* Vc, int B, int Hq, int Hkv,
+                              int head_dim, int prefix_len, int cpad, const int* step_ptr, float* ws_o, float* ws_ml,
+                              void* out, long long ldo, float scale, cudaStream_t stream) {
+  T1_CHECK_ARG(head_dim == 128, "t1_decode_attn: head_dim must be 128 (got %d)", head_dim);
+  T1_CHECK_ARG(cpad % DA_KEYS == 0 && cpad > 0, "t1_decode_attn: cpad must be a positive multiple of %d", DA_KEYS);
+  T1_CHECK_ARG(B > 0 && Hkv > 0 && Hq % Hkv == 0, "t1_decode_attn: bad head configuration");
+  const int n_prefix_chunks = (prefix_len + DA_KEYS - 1) / DA_KEYS;
+  const int chunks_per_seq = cpad / DA_KEYS;
+  const int n_chunks = n_prefix_chunks + B * chunks_per_seq;
+  const int ratio = Hq / Hkv;
+  const int row_tiles = (B * ratio + 63) / 64;
+  const int rows_pad = row_tiles * 64;
+  constexpr int SMEM = (64 + 2 * DA_KEYS) * DA_LDS * 2;
+  static bool set = false;
+  if (!set) {
+    cudaFuncSetAttribute(decode_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    set = true;
+  }
+  dim3 grid(n_chunks, Hkv, row_tiles);
+  decode_attn_kernel<<<grid, 128, SMEM, stream>>>((const bf16*)q, ldq, (const bf16*)Kc, (const bf16*)Vc, Hq, Hkv, B,
+                                                  prefix_len, cpad, step_ptr, ws_o, ws_ml, n_prefix_chunks, rows_pad,
+                                                  scale * 1.4426950408889634f);
+  T1_CUDA_LAUNCH_CHECK("t1_decode_attn");
+  decode_attn_combine_kernel<<<B * Hq, 128, 0, stream>>>(ws_o, ws_ml, n_chunks, n_prefix_chunks, chunks_per_seq, Hq, Hkv,
+                                                        rows_pad, (bf16*)out, ldo);
+  T1_CUDA_LAUNCH_CHECK("t1_decode_attn.combine");
+  return T1_OK;
+}
+
+extern "C" int t1_sample(const float* logits, long long ld, int B, int V, float temperature, int top_k,
+                         unsigned long long seed, const int* step_ptr, int step_offset, const int* eos_ids, int n_eos,
+                         int pad_id, int* finished, int* out_ids, int out_ld, int* next_ids, float* out_u,
+                         cudaStream_t stream) {
+  T1_CHECK_ARG(B > 0 && V > 0 && logits, "t1_sample: bad arguments");
+  sample_kernel<<<B, 1024, 0, stream>>>(logits, ld, V, temperature, top_k, seed, step_ptr, step_offset, eos_ids, n_eos,
+                                        pad_id, finished, out_ids, out_ld, next_ids, out_u);
+  T1_CUDA_LAUNCH_CHECK("t1_sample");
+  return T1_OK;
+}
+
+extern "C" int t1_incr(int* p, int v, cudaStream_t stream) {
+  incr_kernel<<<1, 32, 0, stream>>>(p, v);
+  T1_CUDA_LAUNCH_CHECK("t1_incr");
+  return T1_OK;
+}

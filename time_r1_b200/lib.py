@@ -28,6 +28,44 @@ _SIGNATURES: dict[str, list] = {
     "t1_launch_count": [i32],
     # gemm_tcgen05.cu
     "t1_gemm_bf16_tn": [vp, i64, vp, i64, vp, i64, i32, i32, i32, vp, i32, vp],
+    # grpo.cu
+    "t1_iou_reward": [i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp],
+    "t1_group_advantage": [vp, i32, i32, i32, f32, vp, vp, vp, vp, vp],
+    "t1_grpo_loss": [vp, vp, vp, vp, vp, vp, i32, i32, f32, f32, f32, i32, f32, vp, vp, vp, vp],
+    "t1_logprob_entropy": [vp, i64, i32, i32, vp, vp, vp, vp, vp],
+    "t1_logits_backward": [vp, i64, i32, i32, vp, vp, vp, vp, i64, vp],
+    "t1_eos_mask": [vp, i32, i32, i32, vp, vp, vp],
+    # elementwise.cu
+    "t1_rmsnorm": [vp, vp, vp, vp, i32, i32, f32, vp],
+    "t1_layernorm": [vp, vp, vp, vp, vp, i32, i32, f32, vp],
+    "t1_rmsnorm_bwd": [vp, vp, vp, vp, vp, vp, i32, i32, f32, vp],
+    "t1_rope_table": [vp, i32, vp, vp, i32, vp, vp, vp],
+    "t1_rope_apply": [vp, i64, i32, i32, i32, vp, vp, i32, i32, vp, i64, vp],
+    "t1_copy_cols": [vp, i64, vp, i64, i32, i32, vp],
+    "t1_swiglu": [vp, vp, i64, i32, vp],
+    "t1_swiglu_bwd": [vp, vp, vp, i64, i32, vp],
+    "t1_act": [vp, vp, i64, i32, vp],
+    "t1_act_bwd": [vp, vp, vp, i64, i32, vp],
+    "t1_gather_rows": [vp, i64, vp, vp, i64, i32, i32, vp],
+    "t1_scatter_rows": [vp, i64, vp, vp, i64, i32, i32, i32, vp],
+    "t1_transpose_bf16": [vp, i64, vp, i64, i32, i32, vp],
+    "t1_colsum": [vp, i64, i32, i32, vp, vp],
+    "t1_f32_to_bf16": [vp, vp, i64, i32, vp],
+    "t1_add_bf16": [vp, vp, i64, vp],
+    # attention.cu
+    "t1_attn_fwd": [vp, i64, vp, i64, vp, i64, vp, i64, vp, vp, vp, i32, i32, i32, i32, i32, i32, f32, vp],
+    "t1_attn_bwd": [vp, i64, vp, i64, vp, i64, vp, i64, vp, i64, vp, vp, vp, vp, i64, vp, i64, vp, i64, vp, vp,
+                    i32, i32, i32, i32, i32, i32, f32, vp],
+    # decode.cu
+    "t1_skinny_gemm": [vp, i64, vp, i64, vp, vp, i64, i32, i32, i32, i32, i32, vp],
+    "t1_decode_rope_append": [vp, i64, i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, i32, vp],
+    "t1_decode_attn": [vp, i64, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, i64, f32, vp],
+    "t1_sample": [vp, i64, i32, i32, f32, i32, u64, vp, i32, vp, i32, i32, vp, vp, i32, vp, vp, vp],
+    "t1_incr": [vp, i32, vp],
+    # optim.cu
+    "t1_sumsq_bf16": [vp, i64, vp, vp],
+    "t1_adamw": [vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, vp, f32, f32, vp],
+    "t1_bf16_to_f32": [vp, vp, i64, vp],
 }
 _RESTYPES = {"t1_last_error": C.c_char_p, "t1_launch_count": u64, "t1_count_launch": None}
 

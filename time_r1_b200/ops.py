@@ -42,3 +42,246 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None = None, bias
     call("t1_gemm_bf16_tn", ptr(a), a.stride(0), ptr(b), b.stride(0), ptr(out), out.stride(0), M, N, K, ptr(bias),
          flags, stream_ptr())
     return out
+
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+I32 = torch.int32
+
+
+def skinny_gemm(x, w, out=None, bias=None, accumulate=False, out_dtype=BF16):
+    """out[M<=64, N] (+)= x[M,K] @ w[N,K]^T (+bias): weight-streaming decode GEMM."""
+    M, K = x.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty((M, N), device=x.device, dtype=out_dtype)
+    call("t1_skinny_gemm", ptr(x), x.stride(0), ptr(w), w.stride(0), ptr(bias), ptr(out), out.stride(0), M, N, K,
+         1 if out.dtype == F32 else 0, 1 if accumulate else 0, stream_ptr())
+    return out
+
+
+def linear(x, w, out=None, bias=None, accumulate=False, out_dtype=BF16):
+    """Dispatch on the row count: <= 64 rows stream the weights (HBM-bound), otherwise the tcgen05 tile kernel."""
+    if x.shape[0] <= 64 and w.shape[0] % 16 == 0 and x.shape[1] % 32 == 0 and (bias is None or bias.dtype == BF16):
+        return skinny_gemm(x, w, out=out, bias=bias, accumulate=accumulate, out_dtype=out_dtype)
+    return gemm(x, w, out=out, bias=bias, accumulate=accumulate, out_dtype=out_dtype)
+
+
+def rmsnorm(x, w, eps, delta=None, out=None):
+    """y = rmsnorm(x (+= delta)) * w.  x is updated in place when delta is given (fused residual add)."""
+    T, D = x.shape
+    assert x.is_contiguous()
+    if out is None:
+        out = torch.empty_like(x)
+    call("t1_rmsnorm", ptr(x), ptr(delta), ptr(w), ptr(out), T, D, float(eps), stream_ptr())
+    return out
+
+
+def layernorm(x, w, b, eps, delta=None, out=None):
+    T, D = x.shape
+    assert x.is_contiguous()
+    if out is None:
+        out = torch.empty_like(x)
+    call("t1_layernorm", ptr(x), ptr(delta), ptr(w), ptr(b), ptr(out), T, D, float(eps), stream_ptr())
+    return out
+
+
+def rmsnorm_bwd(dy, x, w, eps, dw_f32, dres=None, out=None):
+    """dx = (dres +) d rmsnorm(x)·w / dx ; dw_f32 (+)= column reduction (fp32 atomics)."""
+    T, D = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    call("t1_rmsnorm_bwd", ptr(dy), ptr(x), ptr(w), ptr(dres), ptr(out), ptr(dw_f32), T, D, float(eps), stream_ptr())
+    return out
+
+
+def rope_table(pos, axis_id, inv_freq):
+    """pos [n_axes, T] int32 -> (cos, sin) [T, half] fp32 with channel i using axis axis_id[i]."""
+    T = pos.shape[1]
+    half = inv_freq.numel()
+    cos = torch.empty((T, half), device=pos.device, dtype=F32)
+    sin = torch.empty((T, half), device=pos.device, dtype=F32)
+    call("t1_rope_table", ptr(pos), T, ptr(axis_id), ptr(inv_freq), half, ptr(cos), ptr(sin), stream_ptr())
+    return cos, sin
+
+
+def rope_apply(x, col0, n_heads, head_dim, cos, sin, inverse=False, out=None):
+    """Rotate n_heads heads starting at column col0 of x [T, ld] in place (optionally copying them to out)."""
+    T = x.shape[0]
+    call("t1_rope_apply", ptr(x), x.stride(0), col0, n_heads, head_dim, ptr(cos), ptr(sin), 1 if inverse else 0, T,
+         ptr(out), 0 if out is None else out.stride(0), stream_ptr())
+
+
+def copy_cols(src, dst, width):
+    call("t1_copy_cols", ptr(src), src.stride(0), ptr(dst), dst.stride(0), src.shape[0], width, stream_ptr())
+
+
+def swiglu(gate_up, out=None):
+    T, I2 = gate_up.shape
+    assert gate_up.is_contiguous()
+    if out is None:
+        out = torch.empty((T, I2 // 2), device=gate_up.device, dtype=BF16)
+    call("t1_swiglu", ptr(gate_up), ptr(out), T, I2 // 2, stream_ptr())
+    return out
+
+
+def swiglu_bwd(dact, gate_up, out=None):
+    T, I2 = gate_up.shape
+    if out is None:
+        out = torch.empty_like(gate_up)
+    call("t1_swiglu_bwd", ptr(dact), ptr(gate_up), ptr(out), T, I2 // 2, stream_ptr())
+    return out
+
+
+def act(x, mode, out=None):
+    """mode 0: exact GELU; 1: QuickGELU."""
+    assert x.is_contiguous()
+    if out is None:
+        out = torch.empty_like(x)
+    call("t1_act", ptr(x), ptr(out), x.numel(), mode, stream_ptr())
+    return out
+
+
+def act_bwd(dy, x, mode, out=None):
+    if out is None:
+        out = torch.empty_like(x)
+    call("t1_act_bwd", ptr(dy), ptr(x), ptr(out), x.numel(), mode, stream_ptr())
+    return out
+
+
+def gather_rows(src, idx, out=None, width=None):
+    n = idx.numel() if idx is not None else src.shape[0]
+    width = width or src.shape[1]
+    if out is None:
+        out = torch.empty((n, width), device=src.device, dtype=BF16)
+    call("t1_gather_rows", ptr(src), src.stride(0), ptr(idx), ptr(out), out.stride(0), n, width, stream_ptr())
+    return out
+
+
+def scatter_rows(src, idx, dst, accumulate=False, width=None):
+    n = idx.numel() if idx is not None else src.shape[0]
+    width = width or src.shape[1]
+    call("t1_scatter_rows", ptr(src), src.stride(0), ptr(idx), ptr(dst), dst.stride(0), n, width,
+         1 if accumulate else 0, stream_ptr())
+    return dst
+
+
+def transpose(x, out=None):
+    R, C = x.shape
+    if out is None:
+        out = torch.empty((C, R), device=x.device, dtype=BF16)
+    call("t1_transpose_bf16", ptr(x), x.stride(0), ptr(out), out.stride(0), R, C, stream_ptr())
+    return out
+
+
+def colsum(x, out_f32):
+    R, C = x.shape
+    call("t1_colsum", ptr(x), x.stride(0), R, C, ptr(out_f32), stream_ptr())
+    return out_f32
+
+
+def f32_to_bf16(src, dst, accumulate=False):
+    call("t1_f32_to_bf16", ptr(src), ptr(dst), src.numel(), 1 if accumulate else 0, stream_ptr())
+    return dst
+
+
+def add_(y, x):
+    call("t1_add_bf16", ptr(y), ptr(x), y.numel(), stream_ptr())
+    return y
+
+
+def attn_fwd(q, k, v, row_lo, row_hi, shared_len, Hq, Hkv, head_dim, scale, out=None, lse=None, need_lse=True):
+    """q: [T, >=Hq*hd] view, k/v: [Tk, >=Hkv*hd] views (row strides free). Returns (out [T, Hq*hd], lse2 [Hq, T])."""
+    T, Tk = q.shape[0], k.shape[0]
+    if out is None:
+        out = torch.empty((T, Hq * head_dim), device=q.device, dtype=BF16)
+    if lse is None and need_lse:
+        lse = torch.empty((Hq, T), device=q.device, dtype=F32)
+    call("t1_attn_fwd", ptr(q), q.stride(0), ptr(k), k.stride(0), ptr(v), v.stride(0), ptr(out), out.stride(0),
+         ptr(lse), ptr(row_lo), ptr(row_hi), int(shared_len), T, Tk, Hq, Hkv, head_dim, float(scale), stream_ptr())
+    return out, lse
+
+
+def attn_bwd(q, k, v, o, do, lse, row_lo, row_hi, shared_len, Hq, Hkv, head_dim, scale, dq, dk, dv):
+    T, Tk = q.shape[0], k.shape[0]
+    delta = torch.empty((Hq, T), device=q.device, dtype=F32)
+    summ = torch.empty(((T + 63) // 64) * 4, device=q.device, dtype=I32)
+    call("t1_attn_bwd", ptr(q), q.stride(0), ptr(k), k.stride(0), ptr(v), v.stride(0), ptr(o), o.stride(0), ptr(do),
+         do.stride(0), ptr(lse), ptr(delta), ptr(summ), ptr(dq), dq.stride(0), ptr(dk), dk.stride(0), ptr(dv),
+         dv.stride(0), ptr(row_lo), ptr(row_hi), int(shared_len), T, Tk, Hq, Hkv, head_dim, float(scale), stream_ptr())
+    return dq, dk, dv
+
+
+def logprob_entropy(logits, target):
+    R, V = logits.shape
+    lp = torch.empty(R, device=logits.device, dtype=F32)
+    ent = torch.empty(R, device=logits.device, dtype=F32)
+    lse = torch.empty(R, device=logits.device, dtype=F32)
+    call("t1_logprob_entropy", ptr(logits), logits.stride(0), R, V, ptr(target), ptr(lp), ptr(ent), ptr(lse), stream_ptr())
+    return lp, ent, lse
+
+
+def logits_backward(logits, target, lse, dlogp, out=None):
+    R, V = logits.shape
+    if out is None:
+        out = torch.empty((R, V), device=logits.device, dtype=BF16)
+    call("t1_logits_backward", ptr(logits), logits.stride(0), R, V, ptr(target), ptr(lse), ptr(dlogp), ptr(out),
+         out.stride(0), stream_ptr())
+    return out
+
+
+def iou_reward(mode, pred_s, pred_e, valid, gt_s, gt_e, dur):
+    """All inputs float64 device tensors (valid: uint8). Returns (reward64, reward32)."""
+    n = pred_s.numel()
+    o64 = torch.empty(n, device=pred_s.device, dtype=torch.float64)
+    o32 = torch.empty(n, device=pred_s.device, dtype=F32)
+    call("t1_iou_reward", int(mode), ptr(pred_s), ptr(pred_e), ptr(valid), ptr(gt_s), ptr(gt_e), ptr(dur), ptr(o64),
+         ptr(o32), n, stream_ptr())
+    return o64, o32
+
+
+def group_advantage(rewards_per_func, G, eps=1e-4):
+    n, nf = rewards_per_func.shape
+    dev = rewards_per_func.device
+    rewards = torch.empty(n, device=dev, dtype=F32)
+    adv = torch.empty(n, device=dev, dtype=F32)
+    mean = torch.empty(n // G, device=dev, dtype=F32)
+    std = torch.empty(n // G, device=dev, dtype=F32)
+    call("t1_group_advantage", ptr(rewards_per_func), n, nf, G, float(eps), ptr(rewards), ptr(adv), ptr(mean), ptr(std),
+         stream_ptr())
+    return rewards, adv, mean, std
+
+
+def grpo_loss(logp, ref_logp, entropy, adv, mask, beta, eps_lo, eps_hi, use_grpo, loss_scale=1.0, old_logp=None):
+    rows, C = logp.shape
+    dev = logp.device
+    loss = torch.empty(1, device=dev, dtype=F32)
+    dlogp = torch.empty((rows, C), device=dev, dtype=F32)
+    stats = torch.empty(8, device=dev, dtype=F32)
+    call("t1_grpo_loss", ptr(logp), ptr(old_logp), ptr(ref_logp), ptr(entropy), ptr(adv), ptr(mask), rows, C,
+         float(beta), float(eps_lo), float(eps_hi), 1 if use_grpo else 0, float(loss_scale), ptr(loss), ptr(dlogp),
+         ptr(stats), stream_ptr())
+    return loss, dlogp, stats
+
+
+def eos_mask(ids, eos_id):
+    rows, C = ids.shape
+    mask = torch.empty((rows, C), device=ids.device, dtype=I32)
+    lengths = torch.empty(rows, device=ids.device, dtype=I32)
+    call("t1_eos_mask", ptr(ids), rows, C, int(eos_id), ptr(mask), ptr(lengths), stream_ptr())
+    return mask, lengths
+
+
+def sumsq(g, out_accum):
+    call("t1_sumsq_bf16", ptr(g), g.numel(), ptr(out_accum), stream_ptr())
+    return out_accum
+
+
+def adamw(master, m, v, grad, param, lr, beta1, beta2, eps, wd, step, gnorm_sq=None, max_norm=0.0, grad_scale=1.0):
+    call("t1_adamw", ptr(master), ptr(m), ptr(v), ptr(grad), ptr(param), master.numel(), float(lr), float(beta1),
+         float(beta2), float(eps), float(wd), int(step), ptr(gnorm_sq), float(max_norm), float(grad_scale), stream_ptr())
+
+
+def bf16_to_f32(src, dst):
+    call("t1_bf16_to_f32", ptr(src), ptr(dst), src.numel(), stream_ptr())
+    return dst
