@@ -1,0 +1,160 @@
+"""Model / run configuration for the Qwen2-VL and Qwen2.5-VL families (one struct, two ViT variants).
+
+Field meanings follow HF `Qwen2_5_VLConfig` / `Qwen2VLConfig` (configuration_qwen2_5_vl.py); the trainer in the
+reference hard-codes Qwen2.5-VL (src/time_r1/rl/timer1_trainer.py:244,298) while BASELINE.json names Qwen2-VL, so
+both are first-class here.
+"""
+from __future__ import annotations
+
+from dataclasses import asdict, dataclass, field, replace
+
+
+@dataclass
+class ModelConfig:
+    family: str = "qwen2_5_vl"  # or "qwen2_vl"
+    # ---- LLM ----
+    hidden_size: int = 3584
+    intermediate_size: int = 18944
+    num_hidden_layers: int = 28
+    num_attention_heads: int = 28
+    num_key_value_heads: int = 4
+    head_dim: int = 128
+    vocab_size: int = 152064
+    rms_norm_eps: float = 1e-6
+    rope_theta: float = 1e6
+    mrope_section: tuple = (16, 24, 24)
+    tie_word_embeddings: bool = False
+    # ---- ViT ----
+    vit_hidden: int = 1280
+    vit_depth: int = 32
+    vit_heads: int = 16
+    vit_intermediate: int = 3420
+    patch_size: int = 14
+    temporal_patch_size: int = 2
+    spatial_merge_size: int = 2
+    window_size: int = 112
+    fullatt_block_indexes: tuple = (7, 15, 23, 31)
+    in_channels: int = 3
+    tokens_per_second: int = 2
+    # ---- special tokens ----
+    video_token_id: int = 151656
+    image_token_id: int = 151655
+    vision_start_token_id: int = 151652
+    eos_token_id: int = 151645
+    pad_token_id: int = 151643
+    stop_token_ids: tuple = (151645, 151643)
+
+    @property
+    def is_q25(self) -> bool:
+        return self.family == "qwen2_5_vl"
+
+    @property
+    def vit_head_dim(self) -> int:
+        return self.vit_hidden // self.vit_heads
+
+    @property
+    def vit_inter_padded(self) -> int:
+        """ViT MLP width padded to a multiple of 64 (zero rows/cols: exact) so TMA row strides stay 16-byte aligned."""
+        return (self.vit_intermediate + 63) // 64 * 64
+
+    @property
+    def patch_dim(self) -> int:
+        return self.in_channels * self.temporal_patch_size * self.patch_size ** 2
+
+    @property
+    def merge_unit(self) -> int:
+        return self.spatial_merge_size ** 2
+
+    @property
+    def qkv_dim(self) -> int:
+        return (self.num_attention_heads + 2 * self.num_key_value_heads) * self.head_dim
+
+    def to_dict(self) -> dict:
+        return asdict(self)
+
+
+def qwen2_5_vl_7b() -> ModelConfig:
+    return ModelConfig()
+
+
+def qwen2_5_vl_3b() -> ModelConfig:
+    return ModelConfig(hidden_size=2048, intermediate_size=11008, num_hidden_layers=36, num_attention_heads=16,
+                       num_key_value_heads=2, vocab_size=151936, tie_word_embeddings=True)
+
+
+def qwen2_vl_7b() -> ModelConfig:
+    return ModelConfig(family="qwen2_vl", vit_intermediate=5120, fullatt_block_indexes=(), window_size=0,
+                       tokens_per_second=1)
+
+
+def qwen2_vl_2b() -> ModelConfig:
+    return ModelConfig(family="qwen2_vl", hidden_size=1536, intermediate_size=8960, num_hidden_layers=28,
+                       num_attention_heads=12, num_key_value_heads=2, vocab_size=151936, tie_word_embeddings=True,
+                       vit_intermediate=5120, fullatt_block_indexes=(), window_size=0, tokens_per_second=1)
+
+
+def toy(family: str = "qwen2_5_vl", **over) -> ModelConfig:
+    """Small config the CPU oracle finishes in seconds (used by the parity tests and smoke())."""
+    base = dict(family=family, hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=2,
+                num_key_value_heads=1, head_dim=128, vocab_size=2048, vit_hidden=160, vit_depth=3, vit_heads=2,
+                vit_intermediate=200, fullatt_block_indexes=(1,), video_token_id=2040, image_token_id=2041,
+                vision_start_token_id=2042, eos_token_id=2043, pad_token_id=2044, stop_token_ids=(2043, 2044))
+    if family == "qwen2_vl":
+        base.update(fullatt_block_indexes=(), window_size=0, tokens_per_second=1, vit_intermediate=320)
+    base.update(over)
+    return ModelConfig(**base)
+
+
+PRESETS = {
+    "qwen2.5-vl-7b": qwen2_5_vl_7b, "qwen2.5-vl-3b": qwen2_5_vl_3b, "qwen2-vl-7b": qwen2_vl_7b,
+    "qwen2-vl-2b": qwen2_vl_2b, "toy": toy,
+}
+
+
+def from_hf_config(d: dict) -> ModelConfig:
+    """Build from an HF config.json dict (Qwen2VLConfig / Qwen2_5_VLConfig, flat or with text_config)."""
+    t = d.get("text_config", d)
+    v = d.get("vision_config", {})
+    fam = "qwen2_5_vl" if "2_5" in d.get("model_type", "qwen2_5_vl") else "qwen2_vl"
+    rope = t.get("rope_scaling") or t.get("rope_parameters") or {}
+    cfg = ModelConfig(
+        family=fam, hidden_size=t["hidden_size"], intermediate_size=t["intermediate_size"],
+        num_hidden_layers=t["num_hidden_layers"], num_attention_heads=t["num_attention_heads"],
+        num_key_value_heads=t["num_key_value_heads"], head_dim=t["hidden_size"] // t["num_attention_heads"],
+        vocab_size=t["vocab_size"], rms_norm_eps=t.get("rms_norm_eps", 1e-6), rope_theta=t.get("rope_theta", 1e6),
+        mrope_section=tuple(rope.get("mrope_section", (16, 24, 24))),
+        tie_word_embeddings=d.get("tie_word_embeddings", t.get("tie_word_embeddings", False)),
+        vit_hidden=v.get("hidden_size", v.get("embed_dim", 1280)), vit_depth=v.get("depth", 32),
+        vit_heads=v.get("num_heads", 16),
+        vit_intermediate=v.get("intermediate_size", int(v.get("embed_dim", 1280) * v.get("mlp_ratio", 4))),
+        patch_size=v.get("patch_size", 14), temporal_patch_size=v.get("temporal_patch_size", 2),
+        spatial_merge_size=v.get("spatial_merge_size", 2), window_size=v.get("window_size", 0 if fam == "qwen2_vl" else 112),
+        fullatt_block_indexes=tuple(v.get("fullatt_block_indexes", ())), tokens_per_second=v.get("tokens_per_second", 2 if fam == "qwen2_5_vl" else 1),
+        video_token_id=d.get("video_token_id", 151656), image_token_id=d.get("image_token_id", 151655),
+        vision_start_token_id=d.get("vision_start_token_id", 151652),
+    )
+    return cfg
+
+
+@dataclass
+class RunConfig:
+    """Knobs of one GRPO step (defaults = scripts/posttrain/train_rl.sh + trl 0.17 GRPOConfig defaults)."""
+    num_generations: int = 8
+    max_completion_length: int = 200
+    temperature: float = 1.0
+    top_k: int = 50
+    beta: float = 0.04
+    epsilon_low: float = 0.2   # timer1_trainer.py:388-393 hard-codes 0.2 / 0.2
+    epsilon_high: float = 0.2
+    use_grpo: bool = False
+    learning_rate: float = 1e-6
+    adam_beta1: float = 0.9
+    adam_beta2: float = 0.999
+    adam_eps: float = 1e-8
+    weight_decay: float = 0.0
+    max_grad_norm: float = 1.0
+    gradient_accumulation_steps: int = 1
+    fix_vit: bool = True
+    ref_quirk_mrope: bool = True   # scoring pass omits second_per_grid_ts (timer1_trainer.py:601-607)
+    seed: int = 42
+    logit_chunk_rows: int = 2048

@@ -32,11 +32,11 @@ __device__ __forceinline__ void store8(bf16* p, const float* f) {
 // ---------------------------------------------------------------------------------------------
 template <bool kLayerNorm>
 __global__ void __launch_bounds__(256)
-norm_fwd_kernel(bf16* __restrict__ x, const bf16* __restrict__ delta, const bf16* __restrict__ w,
+norm_fwd_kernel(const bf16* x, const bf16* __restrict__ delta, bf16* x_out, const bf16* __restrict__ w,
                 const bf16* __restrict__ b, bf16* __restrict__ y, int D, float eps) {
   __shared__ float red[33];
   const size_t row = blockIdx.x;
-  bf16* xr = x + row * D;
+  const bf16* xr = x + row * D;
   const int nv = D >> 3;
   float sum = 0.f, sq = 0.f;
   // D <= 8 * 256 * 4 handled with up to 4 vectors per thread kept in registers
@@ -51,7 +51,7 @@ norm_fwd_kernel(bf16* __restrict__ x, const bf16* __restrict__ delta, const bf16
         load8(delta + row * D + i * 8, d);
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[it][j] += d[j];
-        store8(xr + i * 8, v[it]);
+        store8(x_out + row * D + i * 8, v[it]);
         // round in registers too, so the norm sees exactly what later consumers of x will read
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[it][j] = __bfloat162float(__float2bfloat16(v[it][j]));
@@ -344,6 +344,25 @@ __global__ void scatter_rows_kernel(const bf16* __restrict__ src, long long lds,
   }
 }
 
+// pixel rows: dst_bf16[i, :] = (bf16) src_f32[idx[i], :]  (window-order permutation fused with the dtype cast)
+__global__ void gather_rows_f32_kernel(const float* __restrict__ src, long long lds, const int* __restrict__ idx,
+                                       bf16* __restrict__ dst, long long ldd, int n, int width) {
+  const int vpr = width >> 3;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (long long)n * vpr) return;
+  const long long i = gid / vpr;
+  const int v = (int)(gid - i * vpr);
+  const long long s = idx ? idx[i] : i;
+  const float4 a = *reinterpret_cast<const float4*>(src + s * lds + v * 8);
+  const float4 b = *reinterpret_cast<const float4*>(src + s * lds + v * 8 + 4);
+  uint4 o;
+  o.x = pack_bf16x2(a.x, a.y);
+  o.y = pack_bf16x2(a.z, a.w);
+  o.z = pack_bf16x2(b.x, b.y);
+  o.w = pack_bf16x2(b.z, b.w);
+  *reinterpret_cast<uint4*>(dst + i * ldd + v * 8) = o;
+}
+
 // bf16 transpose: in [R, C] (ld) -> out [C, R] (ldo). 64x64 tiles through padded shared memory.
 __global__ void __launch_bounds__(256)
 transpose_kernel(const bf16* __restrict__ in, long long ld, bf16* __restrict__ out, long long ldo, int R, int C) {
@@ -414,20 +433,23 @@ inline unsigned blocks_for(long long n, int threads) { return (unsigned)((n + th
 
 }  // namespace
 
-extern "C" int t1_rmsnorm(void* x, const void* delta, const void* w, void* y, int T, int D, float eps,
-                          cudaStream_t stream) {
+// y = norm(x + delta) * w; when delta is given the (bf16-rounded) sum is also written to x_out (may alias x).
+extern "C" int t1_rmsnorm(const void* x, const void* delta, void* x_out, const void* w, void* y, int T, int D,
+                          float eps, cudaStream_t stream) {
   if (T == 0) return T1_OK;
   T1_CHECK_ARG(T > 0 && D > 0 && D % 8 == 0 && D <= 8192, "t1_rmsnorm: D=%d must be a multiple of 8 and <= 8192", D);
-  norm_fwd_kernel<false><<<T, 256, 0, stream>>>((bf16*)x, (const bf16*)delta, (const bf16*)w, nullptr, (bf16*)y, D, eps);
+  T1_CHECK_ARG(!delta || x_out, "t1_rmsnorm: x_out is required when delta is given");
+  norm_fwd_kernel<false><<<T, 256, 0, stream>>>((const bf16*)x, (const bf16*)delta, (bf16*)x_out, (const bf16*)w, nullptr, (bf16*)y, D, eps);
   T1_CUDA_LAUNCH_CHECK("t1_rmsnorm");
   return T1_OK;
 }
 
-extern "C" int t1_layernorm(void* x, const void* delta, const void* w, const void* b, void* y, int T, int D, float eps,
-                            cudaStream_t stream) {
+extern "C" int t1_layernorm(const void* x, const void* delta, void* x_out, const void* w, const void* b, void* y, int T,
+                            int D, float eps, cudaStream_t stream) {
   if (T == 0) return T1_OK;
   T1_CHECK_ARG(T > 0 && D > 0 && D % 8 == 0 && D <= 8192, "t1_layernorm: D=%d must be a multiple of 8 and <= 8192", D);
-  norm_fwd_kernel<true><<<T, 256, 0, stream>>>((bf16*)x, (const bf16*)delta, (const bf16*)w, (const bf16*)b, (bf16*)y, D, eps);
+  T1_CHECK_ARG(!delta || x_out, "t1_layernorm: x_out is required when delta is given");
+  norm_fwd_kernel<true><<<T, 256, 0, stream>>>((const bf16*)x, (const bf16*)delta, (bf16*)x_out, (const bf16*)w, (const bf16*)b, (bf16*)y, D, eps);
   T1_CUDA_LAUNCH_CHECK("t1_layernorm");
   return T1_OK;
 }
@@ -511,6 +533,15 @@ extern "C" int t1_gather_rows(const void* src, long long lds, const int* idx, vo
   T1_CHECK_ARG(width % 8 == 0 && lds % 8 == 0 && ldd % 8 == 0, "t1_gather_rows: widths must be multiples of 8");
   gather_rows_kernel<<<blocks_for((long long)n * (width / 8), 256), 256, 0, stream>>>((const bf16*)src, lds, idx, (bf16*)dst, ldd, n, width);
   T1_CUDA_LAUNCH_CHECK("t1_gather_rows");
+  return T1_OK;
+}
+
+extern "C" int t1_gather_rows_f32(const float* src, long long lds, const int* idx, void* dst, long long ldd, int n,
+                                  int width, cudaStream_t stream) {
+  if (n == 0) return T1_OK;
+  T1_CHECK_ARG(width % 8 == 0 && lds % 4 == 0 && ldd % 8 == 0, "t1_gather_rows_f32: width %% 8, lds %% 4, ldd %% 8 required");
+  gather_rows_f32_kernel<<<blocks_for((long long)n * (width / 8), 256), 256, 0, stream>>>(src, lds, idx, (bf16*)dst, ldd, n, width);
+  T1_CUDA_LAUNCH_CHECK("t1_gather_rows_f32");
   return T1_OK;
 }
 

@@ -1,0 +1,697 @@
+"""GRPO rollout-and-update engine: host-side composition of the libtimer1 kernels.
+
+One prompt-group (one video + question, G sampled completions) is the unit of work, exactly as in the reference
+(`TimeR1_Trainer.compute_loss`, src/time_r1/rl/timer1_trainer.py:512-782, batch size forced to 1 :548-551), but the
+arithmetic is restructured around what is shared inside a group (all exact-math savings):
+
+  * the ViT runs ONCE per prompt (reference: 3 x G times, timer1_trainer.py:594-596); under --fix_vit the frozen
+    blocks also serve the reference model, only the merger differs;
+  * the prompt is prefilled ONCE; the G decode streams share one copy of the prompt K/V (split-KV decode attention
+    over [prefix | per-sequence slots]); the decode step is a CUDA graph replayed C-1 times;
+  * scoring packs [prompt | G completions] into ONE token axis with a prefix-sharing attention mask, so the prompt is
+    scored once and its K/V gradient accumulates from all G completions inside the attention backward;
+  * lm_head is applied only to the G*C rows whose logits are used (reference: all G*(P+C) rows, :452-460);
+  * backward recomputes each layer from its checkpointed input (gradient_checkpointing=true in train_rl.sh:32).
+
+torch is used for allocation, streams, CUDA graphs and torch.distributed only; every numerical step is a libtimer1
+kernel.  There is no CPU / eager fallback: every op raises if the extension is missing.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import indexing, ops
+from .config import ModelConfig, RunConfig
+from .lib import call, ptr, stream_ptr
+from .weights import FlatParams, ModelWeights
+
+BF16, F32, I32 = torch.bfloat16, torch.float32, torch.int32
+
+
+@dataclass
+class Prompt:
+    """One prompt-group's inputs, as produced by the HF processor in the reference (timer1_trainer.py:547-565)."""
+    input_ids: np.ndarray                 # [P] int
+    pixel_values: torch.Tensor            # [N, patch_dim] fp32 on the device (pixel_values_videos)
+    grid_thw: list                        # [(t, h, w)]
+    second_per_grid_ts: list | None = None
+
+
+@dataclass
+class ScoreState:
+    """What the policy scoring pass keeps for backward."""
+    P: int
+    G: int
+    C: int
+    Tp: int
+    ckpt: list
+    cos: torch.Tensor
+    sin: torch.Tensor
+    lo: torch.Tensor
+    hi: torch.Tensor
+    ids_packed: torch.Tensor
+    text_scatter_idx: torch.Tensor
+    vision_rows: torch.Tensor
+    logit_rows: torch.Tensor
+    targets: torch.Tensor
+    hsel: torch.Tensor
+    lse: torch.Tensor
+    x_vit: torch.Tensor
+    plan: indexing.VisionPlan
+
+
+class Engine:
+    def __init__(self, cfg: ModelConfig, weights: ModelWeights, run: RunConfig, with_ref: bool = True,
+                 rank: int = 0, world_size: int = 1, process_group=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("time_r1_b200.Engine needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.cfg, self.w, self.run = cfg, weights, run
+        self.dev = weights.train.buf.device
+        self.rank, self.world, self.pg = rank, world_size, process_group
+        self.ref: FlatParams | None = weights.train.clone() if (with_ref and run.beta != 0.0) else None
+        self.grads = weights.train.like(zero=True)
+        self.grad_fresh = True
+        # ---- ZeRO-style shard of the optimizer state over the flat trainable buffer ----
+        n = weights.train.numel
+        assert n % (world_size * 4) == 0
+        self.shard = n // world_size
+        self.shard_lo = rank * self.shard
+        self.master = torch.empty(self.shard, device=self.dev, dtype=F32)
+        ops.bf16_to_f32(weights.train.buf[self.shard_lo:self.shard_lo + self.shard], self.master)
+        self.adam_m = torch.zeros(self.shard, device=self.dev, dtype=F32)
+        self.adam_v = torch.zeros(self.shard, device=self.dev, dtype=F32)
+        self.opt_step = 0
+        # ---- rotary constants (computed the way HF does, in fp32 on the host) ----
+        hd = cfg.head_dim
+        self.inv_freq_llm = (1.0 / (cfg.rope_theta ** (torch.arange(0, hd, 2, dtype=F32) / hd))).to(self.dev)
+        self.axis_llm = torch.from_numpy(indexing.mrope_channel_axes(cfg)).to(self.dev)
+        vh = cfg.vit_head_dim // 2
+        inv_v = 1.0 / (10000.0 ** (torch.arange(0, vh, 2, dtype=F32) / vh))
+        self.inv_freq_vit = torch.cat([inv_v, inv_v]).to(self.dev)
+        self.axis_vit = torch.cat([torch.zeros(vh // 2, dtype=I32), torch.ones(vh // 2, dtype=I32)]).to(self.dev)
+        self._decode_cache: dict = {}
+        self.metrics_launches = 0
+
+    # ------------------------------------------------------------------------------------------
+    # parameter access
+    # ------------------------------------------------------------------------------------------
+    def p(self, name: str, wset: str = "policy") -> torch.Tensor:
+        if wset == "ref" and self.ref is not None and name in self.ref:
+            return self.ref[name]
+        return self.w.get(name)
+
+    def lm_head(self, wset: str = "policy") -> torch.Tensor:
+        return self.p("model.embed_tokens.weight" if self.cfg.tie_word_embeddings else "lm_head.weight", wset)
+
+    def _i32(self, a) -> torch.Tensor:
+        return torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(self.dev, non_blocking=True)
+
+    # ------------------------------------------------------------------------------------------
+    # ViT
+    # ------------------------------------------------------------------------------------------
+    def vit_blocks(self, pixel_values: torch.Tensor, grid_thw) -> tuple[torch.Tensor, torch.Tensor, indexing.VisionPlan]:
+        """Patch-embed + all vision blocks. Returns (x, pending_delta, plan): the merger's input is x + pending_delta
+        (the last block's MLP output, whose residual add is fused into the merger norm)."""
+        cfg = self.cfg
+        plan = indexing.vision_plan(cfg, grid_thw)
+        N, vd, H, hd = plan.n_patches, cfg.vit_hidden, cfg.vit_heads, cfg.vit_head_dim
+        assert pixel_values.shape == (N, cfg.patch_dim) and pixel_values.dtype == F32
+        perm = self._i32(plan.perm_rows)
+        pix = ops.gather_rows_f32(pixel_values, perm)                       # cast + window-order permutation
+        x = ops.gemm(pix, self.w.get("visual.patch_embed.proj.weight"))     # Conv3d == GEMM
+        cos, sin = ops.rope_table(self._i32(plan.pos_hw), self.axis_vit, self.inv_freq_vit)
+        win_lo, win_hi = self._i32(plan.win_lo), self._i32(plan.win_hi)
+        full_lo, full_hi = self._i32(plan.full_lo), self._i32(plan.full_hi)
+        scale = hd ** -0.5
+        delta = None
+        h = torch.empty_like(x)
+        qkv = torch.empty((N, 3 * vd), device=self.dev, dtype=BF16)
+        attn = torch.empty((N, vd), device=self.dev, dtype=BF16)
+        proj = torch.empty((N, vd), device=self.dev, dtype=BF16)
+        down = torch.empty((N, vd), device=self.dev, dtype=BF16)
+        for i in range(cfg.vit_depth):
+            pre = f"visual.blocks.{i}."
+            g = self.w.get
+            if cfg.is_q25:
+                ops.rmsnorm(x, g(pre + "norm1.weight"), 1e-6, delta=delta, out=h)
+            else:
+                ops.layernorm(x, g(pre + "norm1.weight"), g(pre + "norm1.bias"), 1e-6, delta=delta, out=h)
+            ops.gemm(h, g(pre + "attn.qkv.weight"), out=qkv, bias=g(pre + "attn.qkv.bias"))
+            ops.rope_apply(qkv, 0, 2 * H, hd, cos, sin)                     # q and k heads are contiguous
+            full = (not cfg.is_q25) or (i in cfg.fullatt_block_indexes)
+            lo, hi = (full_lo, full_hi) if full else (win_lo, win_hi)
+            ops.attn_fwd(qkv[:, :vd], qkv[:, vd:2 * vd], qkv[:, 2 * vd:], lo, hi, 0, H, H, hd, scale, out=attn,
+                         need_lse=False)
+            ops.gemm(attn, g(pre + "attn.proj.weight"), out=proj, bias=g(pre + "attn.proj.bias"))
+            if cfg.is_q25:
+                ops.rmsnorm(x, g(pre + "norm2.weight"), 1e-6, delta=proj, out=h)
+                gu = ops.gemm(h, g(pre + "mlp.gate_up.weight"), bias=g(pre + "mlp.gate_up.bias"))
+                act = ops.swiglu(gu)
+                ops.gemm(act, g(pre + "mlp.down_proj.weight"), out=down, bias=g(pre + "mlp.down_proj.bias"))
+            else:
+                ops.layernorm(x, g(pre + "norm2.weight"), g(pre + "norm2.bias"), 1e-6, delta=proj, out=h)
+                f1 = ops.gemm(h, g(pre + "mlp.fc1.weight"), bias=g(pre + "mlp.fc1.bias"))
+                act = ops.act(f1, 1)
+                ops.gemm(act, g(pre + "mlp.fc2.weight"), out=down, bias=g(pre + "mlp.fc2.bias"))
+            delta = down
+        return x, delta, plan
+
+    def merger(self, x_vit: torch.Tensor, delta, plan: indexing.VisionPlan, wset: str = "policy",
+               keep: dict | None = None) -> torch.Tensor:
+        """PatchMerger (+ inverse window permutation). If delta is given, x_vit += delta first (in place)."""
+        cfg = self.cfg
+        N, vd, unit = plan.n_patches, cfg.vit_hidden, cfg.merge_unit
+        if cfg.is_q25:
+            y = ops.rmsnorm(x_vit, self.p("visual.merger.ln_q.weight", wset), 1e-6, delta=delta)
+        else:
+            y = ops.layernorm(x_vit, self.p("visual.merger.ln_q.weight", wset), self.p("visual.merger.ln_q.bias", wset),
+                              1e-6, delta=delta)
+        y4 = y.view(N // unit, unit * vd)
+        a1 = ops.gemm(y4, self.p("visual.merger.mlp.0.weight", wset), bias=self.p("visual.merger.mlp.0.bias", wset))
+        g1 = ops.act(a1, 0)
+        m = ops.gemm(g1, self.p("visual.merger.mlp.2.weight", wset), bias=self.p("visual.merger.mlp.2.bias", wset))
+        if keep is not None:
+            keep.update(y4=y4, a1=a1, g1=g1)
+        if cfg.is_q25:
+            out = torch.empty_like(m)
+            ops.scatter_rows(m, self._i32(plan.window_index), out)          # == m[argsort(window_index)]
+            return out
+        return m
+
+    def vit_forward(self, prompt: Prompt, wset: str = "policy"):
+        x, delta, plan = self.vit_blocks(prompt.pixel_values, prompt.grid_thw)
+        emb = self.merger(x, delta, plan, wset)
+        return emb, x, plan
+
+    # ------------------------------------------------------------------------------------------
+    # LLM forward over a packed token axis
+    # ------------------------------------------------------------------------------------------
+    def _rope_tables(self, pos3: np.ndarray):
+        return ops.rope_table(self._i32(pos3), self.axis_llm, self.inv_freq_llm)
+
+    def _embed(self, ids_dev: torch.Tensor, vision_embeds: torch.Tensor, vision_rows: torch.Tensor) -> torch.Tensor:
+        x = ops.gather_rows(self.p("model.embed_tokens.weight"), ids_dev)
+        ops.scatter_rows(vision_embeds, vision_rows, x)                     # masked_scatter (HF :1309-1315)
+        return x
+
+    def llm_forward(self, x0, cos, sin, lo, hi, shared, wset="policy", ckpt=None, kv_out=None):
+        """x0 [T, D] (consumed). Returns final-norm hidden states [T, D]. ckpt: list of L+1 [T, D] buffers receiving
+        the residual stream at each layer input (+ final); kv_out: per-layer (K, V) caches receiving rows [0, T)."""
+        cfg = self.cfg
+        T, D = x0.shape
+        L, Hq, Hkv, hd, I = cfg.num_hidden_layers, cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim, cfg.intermediate_size
+        qd, kd = Hq * hd, Hkv * hd
+        eps, scale = cfg.rms_norm_eps, hd ** -0.5
+        h = torch.empty((T, D), device=self.dev, dtype=BF16)
+        qkv = torch.empty((T, cfg.qkv_dim), device=self.dev, dtype=BF16)
+        attn = torch.empty((T, qd), device=self.dev, dtype=BF16)
+        o = torch.empty((T, D), device=self.dev, dtype=BF16)
+        gu = torch.empty((T, 2 * I), device=self.dev, dtype=BF16)
+        act = torch.empty((T, I), device=self.dev, dtype=BF16)
+        down = torch.empty((T, D), device=self.dev, dtype=BF16)
+        xm = torch.empty((T, D), device=self.dev, dtype=BF16) if ckpt is not None else None
+        x = x0
+        if ckpt is not None:
+            ckpt[0] = x0
+        for l in range(L):
+            pre = f"model.layers.{l}."
+            if l == 0:
+                ops.rmsnorm(x, self.p(pre + "input_layernorm.weight", wset), eps, out=h)
+            elif ckpt is not None:
+                ckpt[l] = torch.empty((T, D), device=self.dev, dtype=BF16)
+                ops.rmsnorm(xm, self.p(pre + "input_layernorm.weight", wset), eps, delta=down, out=h, x_out=ckpt[l])
+                x = ckpt[l]
+            else:
+                ops.rmsnorm(x, self.p(pre + "input_layernorm.weight", wset), eps, delta=down, out=h)
+            ops.gemm(h, self.p(pre + "self_attn.qkv.weight", wset), out=qkv, bias=self.p(pre + "self_attn.qkv.bias", wset))
+            if kv_out is not None:
+                Kc, Vc = kv_out[l]
+                ops.rope_apply(qkv, 0, Hq, hd, cos, sin)
+                ops.rope_apply(qkv, qd, Hkv, hd, cos, sin, out=Kc)
+                ops.copy_cols(qkv[:, qd + kd:], Vc, kd)
+            else:
+                ops.rope_apply(qkv, 0, Hq + Hkv, hd, cos, sin)
+            ops.attn_fwd(qkv[:, :qd], qkv[:, qd:qd + kd], qkv[:, qd + kd:], lo, hi, shared, Hq, Hkv, hd, scale, out=attn,
+                         need_lse=False)
+            ops.gemm(attn, self.p(pre + "self_attn.o_proj.weight", wset), out=o)
+            if ckpt is not None:
+                ops.rmsnorm(x, self.p(pre + "post_attention_layernorm.weight", wset), eps, delta=o, out=h, x_out=xm)
+            else:
+                ops.rmsnorm(x, self.p(pre + "post_attention_layernorm.weight", wset), eps, delta=o, out=h)
+            ops.gemm(h, self.p(pre + "mlp.gate_up.weight", wset), out=gu)
+            ops.swiglu(gu, out=act)
+            ops.gemm(act, self.p(pre + "mlp.down_proj.weight", wset), out=down)
+        hN = torch.empty((T, D), device=self.dev, dtype=BF16)
+        if ckpt is not None:
+            ckpt[L] = torch.empty((T, D), device=self.dev, dtype=BF16)
+            ops.rmsnorm(xm, self.p("model.norm.weight", wset), eps, delta=down, out=hN, x_out=ckpt[L])
+        else:
+            ops.rmsnorm(x, self.p("model.norm.weight", wset), eps, delta=down, out=hN)
+        return hN
+
+    # ------------------------------------------------------------------------------------------
+    # rollout: prefill once + graph-captured decode
+    # ------------------------------------------------------------------------------------------
+    def _decode_state(self, P: int, G: int, C: int):
+        key = (P, G, C)
+        st = self._decode_cache.get(key)
+        if st is not None:
+            return st
+        cfg = self.cfg
+        if len(self._decode_cache) >= 2:       # bound the KV memory kept alive
+            self._decode_cache.clear()
+        kd = cfg.num_key_value_heads * cfg.head_dim
+        cpad = (C + 127) // 128 * 128
+        S = P + G * cpad
+        L = cfg.num_hidden_layers
+        ratio = cfg.num_attention_heads // cfg.num_key_value_heads
+        n_chunks = (P + 127) // 128 + G * (cpad // 128)
+        rows_pad = (G * ratio + 63) // 64 * 64
+        d = self.dev
+        st = dict(
+            cpad=cpad,
+            kv=[(torch.zeros((S, kd), device=d, dtype=BF16), torch.zeros((S, kd), device=d, dtype=BF16)) for _ in range(L)],
+            x=torch.empty((G, cfg.hidden_size), device=d, dtype=BF16), h=torch.empty((G, cfg.hidden_size), device=d, dtype=BF16),
+            qkv=torch.empty((G, cfg.qkv_dim), device=d, dtype=BF16),
+            attn=torch.empty((G, cfg.num_attention_heads * cfg.head_dim), device=d, dtype=BF16),
+            o=torch.empty((G, cfg.hidden_size), device=d, dtype=BF16),
+            gu=torch.empty((G, 2 * cfg.intermediate_size), device=d, dtype=BF16),
+            act=torch.empty((G, cfg.intermediate_size), device=d, dtype=BF16),
+            down=torch.empty((G, cfg.hidden_size), device=d, dtype=BF16),
+            hN=torch.empty((G, cfg.hidden_size), device=d, dtype=BF16),
+            logits=torch.empty((G, cfg.vocab_size), device=d, dtype=F32),
+            ws_o=torch.empty(n_chunks * cfg.num_key_value_heads * rows_pad * 128, device=d, dtype=F32),
+            ws_ml=torch.empty(n_chunks * cfg.num_key_value_heads * rows_pad * 2, device=d, dtype=F32),
+            step=torch.zeros(1, device=d, dtype=I32), next_ids=torch.zeros(G, device=d, dtype=I32),
+            finished=torch.zeros(G, device=d, dtype=I32), out_ids=torch.zeros((G, C), device=d, dtype=I32),
+            cos=torch.empty((C, cfg.head_dim // 2), device=d, dtype=F32), sin=torch.empty((C, cfg.head_dim // 2), device=d, dtype=F32),
+            eos=self._i32(list(cfg.stop_token_ids)), seed=torch.zeros(1, dtype=torch.int64), graph=None, launches_per_step=0,
+        )
+        self._decode_cache[key] = st
+        return st
+
+    def _decode_step(self, st, P: int, G: int, temperature: float, top_k: int, seed: int):
+        """One token for each of the G sequences (captured into a CUDA graph by rollout())."""
+        cfg = self.cfg
+        L, Hq, Hkv, hd = cfg.num_hidden_layers, cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim
+        eps, scale = cfg.rms_norm_eps, hd ** -0.5
+        s = stream_ptr()
+        x, h, qkv, attn, o, gu, act, down = st["x"], st["h"], st["qkv"], st["attn"], st["o"], st["gu"], st["act"], st["down"]
+        ops.gather_rows(self.p("model.embed_tokens.weight"), st["next_ids"], out=x)
+        for l in range(L):
+            pre = f"model.layers.{l}."
+            ops.rmsnorm(x, self.p(pre + "input_layernorm.weight"), eps, delta=down if l > 0 else None, out=h)
+            ops.skinny_gemm(h, self.p(pre + "self_attn.qkv.weight"), out=qkv, bias=self.p(pre + "self_attn.qkv.bias"))
+            Kc, Vc = st["kv"][l]
+            call("t1_decode_rope_append", ptr(qkv), qkv.stride(0), G, Hq, Hkv, hd, ptr(st["cos"]), ptr(st["sin"]),
+                 ptr(st["step"]), ptr(Kc), ptr(Vc), P, st["cpad"], s)
+            call("t1_decode_attn", ptr(qkv), qkv.stride(0), ptr(Kc), ptr(Vc), G, Hq, Hkv, hd, P, st["cpad"],
+                 ptr(st["step"]), ptr(st["ws_o"]), ptr(st["ws_ml"]), ptr(attn), attn.stride(0), scale, s)
+            ops.skinny_gemm(attn, self.p(pre + "self_attn.o_proj.weight"), out=o)
+            ops.rmsnorm(x, self.p(pre + "post_attention_layernorm.weight"), eps, delta=o, out=h)
+            ops.skinny_gemm(h, self.p(pre + "mlp.gate_up.weight"), out=gu)
+            ops.swiglu(gu, out=act)
+            ops.skinny_gemm(act, self.p(pre + "mlp.down_proj.weight"), out=down)
+        ops.rmsnorm(x, self.p("model.norm.weight"), eps, delta=down, out=st["hN"])
+        ops.skinny_gemm(st["hN"], self.lm_head(), out=st["logits"])
+        call("t1_sample", ptr(st["logits"]), st["logits"].stride(0), G, cfg.vocab_size, float(temperature), int(top_k),
+             int(seed), ptr(st["step"]), 1, ptr(st["eos"]), len(cfg.stop_token_ids), cfg.pad_token_id, ptr(st["finished"]),
+             ptr(st["out_ids"]), st["out_ids"].stride(0), ptr(st["next_ids"]), 0, s)
+        call("t1_incr", ptr(st["step"]), 1, s)
+
+    def rollout(self, prompt: Prompt, vision_embeds: torch.Tensor, G: int, C: int, temperature: float = 1.0,
+                top_k: int = 50, seed: int = 0, use_graph: bool = True, check_every: int = 32) -> torch.Tensor:
+        """Sample G completions of up to C tokens (temperature 0 => greedy). Returns ids [G, C] int32 on the device,
+        pad_token_id after a stop token (HF generate semantics, timer1_trainer.py:568-577)."""
+        cfg = self.cfg
+        ids = np.asarray(prompt.input_ids)
+        P = len(ids)
+        st = self._decode_state(P, G, C)
+        pos3, delta = indexing.mrope_positions(cfg, ids, prompt.grid_thw, prompt.second_per_grid_ts)
+        cos, sin = self._rope_tables(pos3)
+        ids_dev = self._i32(ids)
+        vis_rows = self._i32(np.nonzero(ids == cfg.video_token_id)[0])
+        x0 = self._embed(ids_dev, vision_embeds, vis_rows)
+        lo = torch.zeros(P, device=self.dev, dtype=I32)
+        hi = torch.arange(1, P + 1, device=self.dev, dtype=I32)
+        kv_prefix = [(k[:P], v[:P]) for k, v in st["kv"]]
+        hN = self.llm_forward(x0, cos, sin, lo, hi, 0, kv_out=kv_prefix)
+        logits0 = ops.skinny_gemm(hN[P - 1:P], self.lm_head(), out_dtype=F32)           # [1, V]
+        # decode-position tables: completion token c sits at text position P + c + rope_delta on all three axes
+        dpos = np.tile((P + delta + np.arange(C, dtype=np.int64))[None, :], (3, 1))
+        dcos, dsin = self._rope_tables(dpos)
+        st["cos"].copy_(dcos)
+        st["sin"].copy_(dsin)
+        st["step"].zero_()
+        st["finished"].zero_()
+        st["out_ids"].fill_(cfg.pad_token_id)
+        # first token: G independent draws from the shared last-prompt-position distribution (row stride 0)
+        call("t1_sample", ptr(logits0), 0, G, cfg.vocab_size, float(temperature), int(top_k), int(seed), 0, 0,
+             ptr(st["eos"]), len(cfg.stop_token_ids), cfg.pad_token_id, ptr(st["finished"]), ptr(st["out_ids"]),
+             st["out_ids"].stride(0), ptr(st["next_ids"]), 0, stream_ptr())
+        n_steps = C - 1
+        if n_steps > 0:
+            gkey = (float(temperature), int(top_k), int(seed))
+            if use_graph:
+                if st["graph"] is None or st.get("gkey") != gkey:
+                    # warm-up step outside capture (sets func attributes), then rewind the state it touched
+                    snap = (st["next_ids"].clone(), st["finished"].clone(), st["out_ids"].clone())
+                    self._decode_step(st, P, G, temperature, top_k, seed)
+                    torch.cuda.synchronize()
+                    st["step"].zero_()
+                    st["next_ids"].copy_(snap[0]); st["finished"].copy_(snap[1]); st["out_ids"].copy_(snap[2])
+                    g = torch.cuda.CUDAGraph()
+                    from .lib import load
+                    before = load().t1_launch_count(0)
+                    with torch.cuda.graph(g):
+                        self._decode_step(st, P, G, temperature, top_k, seed)
+                    st["launches_per_step"] = int(load().t1_launch_count(0) - before)
+                    st["graph"], st["gkey"] = g, gkey
+                    st["step"].zero_()
+                    st["next_ids"].copy_(snap[0]); st["finished"].copy_(snap[1]); st["out_ids"].copy_(snap[2])
+                done = 0
+                while done < n_steps:
+                    burst = min(check_every, n_steps - done)
+                    for _ in range(burst):
+                        st["graph"].replay()
+                    self.metrics_launches += burst * st["launches_per_step"]
+                    done += burst
+                    if done < n_steps and bool(st["finished"].all().item()):
+                        break
+            else:
+                for i in range(n_steps):
+                    self._decode_step(st, P, G, temperature, top_k, seed)
+                    if (i + 1) % check_every == 0 and bool(st["finished"].all().item()):
+                        break
+        return st["out_ids"].clone()
+
+    # ------------------------------------------------------------------------------------------
+    # scoring (teacher-forced log-probs of the completions) over the packed layout
+    # ------------------------------------------------------------------------------------------
+    def _score_inputs(self, prompt: Prompt, completion_ids: torch.Tensor):
+        cfg = self.cfg
+        ids = np.asarray(prompt.input_ids)
+        P = len(ids)
+        G, C = completion_ids.shape
+        Tp, lo, hi, logit_rows = indexing.packed_rows(P, G, C)
+        spg = None if self.run.ref_quirk_mrope else prompt.second_per_grid_ts
+        pos3, delta = indexing.mrope_positions(cfg, ids, prompt.grid_thw, spg)
+        pos = np.zeros((3, Tp), np.int64)
+        pos[:, :P] = pos3
+        pos[:, P:P + G * C] = np.tile(P + delta + np.arange(C, dtype=np.int64), G)[None, :]
+        ids_packed = torch.zeros(Tp, device=self.dev, dtype=I32)
+        ids_packed[:P] = self._i32(ids)
+        ids_packed[P:P + G * C] = completion_ids.reshape(-1)
+        is_vis = ids == cfg.video_token_id
+        vision_rows = np.nonzero(is_vis)[0]
+        # embedding-gradient scatter index: token id for text rows, -1 for vision rows and padding
+        text_idx = torch.full((Tp,), -1, device=self.dev, dtype=I32)
+        text_idx[:P + G * C] = ids_packed[:P + G * C]
+        if len(vision_rows):
+            text_idx[self._i32(vision_rows).long()] = -1
+        R = G * C
+        Rp = (R + 63) // 64 * 64
+        rows = np.zeros(Rp, np.int32)
+        rows[:R] = logit_rows
+        targets = torch.zeros(Rp, device=self.dev, dtype=I32)
+        targets[:R] = completion_ids.reshape(-1)
+        return dict(P=P, G=G, C=C, Tp=Tp, lo=self._i32(lo), hi=self._i32(hi), pos=pos, ids_packed=ids_packed,
+                    vision_rows=self._i32(vision_rows), text_idx=text_idx, logit_rows=self._i32(rows), targets=targets,
+                    R=R, Rp=Rp)
+
+    def _head_forward(self, hsel: torch.Tensor, targets: torch.Tensor, wset: str):
+        Rp = hsel.shape[0]
+        lp = torch.empty(Rp, device=self.dev, dtype=F32)
+        ent = torch.empty(Rp, device=self.dev, dtype=F32)
+        lse = torch.empty(Rp, device=self.dev, dtype=F32)
+        W = self.lm_head(wset)
+        step = self.run.logit_chunk_rows
+        for a in range(0, Rp, step):
+            b = min(Rp, a + step)
+            logits = ops.gemm(hsel[a:b], W, out_dtype=F32)
+            call("t1_logprob_entropy", ptr(logits), logits.stride(0), b - a, logits.shape[1], ptr(targets[a:b]),
+                 ptr(lp[a:b]), ptr(ent[a:b]), ptr(lse[a:b]), stream_ptr())
+        return lp, ent, lse
+
+    def score(self, prompt: Prompt, completion_ids: torch.Tensor, vision_embeds: torch.Tensor, wset: str = "policy",
+              save: bool = False, x_vit=None, plan=None):
+        """Returns (logp [G, C], entropy [G, C], state-or-None)."""
+        si = self._score_inputs(prompt, completion_ids)
+        G, C, R = si["G"], si["C"], si["R"]
+        cos, sin = self._rope_tables(si["pos"])
+        x0 = self._embed(si["ids_packed"], vision_embeds, si["vision_rows"])
+        ckpt = [None] * (self.cfg.num_hidden_layers + 1) if save else None
+        hN = self.llm_forward(x0, cos, sin, si["lo"], si["hi"], si["P"], wset=wset, ckpt=ckpt)
+        hsel = ops.gather_rows(hN, si["logit_rows"])
+        lp, ent, lse = self._head_forward(hsel, si["targets"], wset)
+        state = None
+        if save:
+            state = ScoreState(P=si["P"], G=G, C=C, Tp=si["Tp"], ckpt=ckpt, cos=cos, sin=sin, lo=si["lo"], hi=si["hi"],
+                               ids_packed=si["ids_packed"], text_scatter_idx=si["text_idx"], vision_rows=si["vision_rows"],
+                               logit_rows=si["logit_rows"], targets=si["targets"], hsel=hsel, lse=lse, x_vit=x_vit, plan=plan)
+        return lp[:R].view(G, C), ent[:R].view(G, C), state
+
+    # ------------------------------------------------------------------------------------------
+    # backward
+    # ------------------------------------------------------------------------------------------
+    def _gview(self, name: str) -> torch.Tensor:
+        return self.grads[name]
+
+    def _wgrad(self, dy: torch.Tensor, x: torch.Tensor, name: str, acc: bool):
+        """grad[name] (+)= dy^T x   (dy [T, N], x [T, K] -> [N, K]); both operands transposed to K-major."""
+        ops.gemm(ops.transpose(dy), ops.transpose(x), out=self._gview(name), accumulate=acc)
+
+    def _dgrad(self, dy: torch.Tensor, w: torch.Tensor, out=None) -> torch.Tensor:
+        """dx = dy @ w   (dy [T, N], w [N, K])."""
+        return ops.gemm(dy, ops.transpose(w), out=out)
+
+    def _small_grad(self, f32: torch.Tensor, name: str, acc: bool):
+        ops.f32_to_bf16(f32, self._gview(name).view(-1), accumulate=acc)
+
+    def backward(self, st: ScoreState, dlogp: torch.Tensor):
+        """Accumulate d loss / d params into self.grads given d loss / d logp [G, C] (fp32)."""
+        cfg = self.cfg
+        if not self.run.fix_vit:
+            raise NotImplementedError("ViT-block gradients (fix_vit=False) are not built; every reference script sets --fix_vit true")
+        acc = not self.grad_fresh
+        L, Hq, Hkv, hd, I, D = cfg.num_hidden_layers, cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim, cfg.intermediate_size, cfg.hidden_size
+        qd, kd = Hq * hd, Hkv * hd
+        eps, scale = cfg.rms_norm_eps, hd ** -0.5
+        T = st.Tp
+        R, Rp = st.G * st.C, st.hsel.shape[0]
+        dev = self.dev
+        embed_name = "model.embed_tokens.weight"
+        head_name = embed_name if cfg.tie_word_embeddings else "lm_head.weight"
+        if not acc and not cfg.tie_word_embeddings:
+            self._gview(embed_name).zero_()     # only rows of seen tokens are written (scatter-add) below
+
+        # ---- lm_head + log-softmax backward, chunked over logit rows ----
+        dl = torch.zeros(Rp, device=dev, dtype=F32)
+        dl[:R] = dlogp.reshape(-1)
+        W = self.lm_head()
+        Wt = ops.transpose(W)                                               # [D, V]
+        dhsel = torch.empty((Rp, D), device=dev, dtype=BF16)
+        step = self.run.logit_chunk_rows
+        first = True
+        for a in range(0, Rp, step):
+            b = min(Rp, a + step)
+            logits = ops.gemm(st.hsel[a:b], W, out_dtype=F32)               # recompute (1.7 TFLOP at cfg2)
+            dlog = ops.logits_backward(logits, st.targets[a:b], st.lse[a:b], dl[a:b])
+            del logits
+            ops.gemm(dlog, Wt, out=dhsel[a:b])
+            ops.gemm(ops.transpose(dlog), ops.transpose(st.hsel[a:b]), out=self._gview(head_name), accumulate=acc or not first)
+            first = False
+            del dlog
+        del Wt
+        dh = torch.zeros((T, D), device=dev, dtype=BF16)
+        ops.scatter_rows(dhsel, st.logit_rows, dh, accumulate=True)         # prompt row P-1 receives G contributions
+        # ---- final norm ----
+        f32s = torch.zeros(max(cfg.qkv_dim, 2 * D), device=dev, dtype=F32)
+        dx = ops.rmsnorm_bwd(dh, st.ckpt[L], self.p("model.norm.weight"), eps, f32s[:D])
+        self._small_grad(f32s[:D], "model.norm.weight", acc)
+        del dh
+        # ---- layers, last to first, recomputing each from its checkpointed input ----
+        h = torch.empty((T, D), device=dev, dtype=BF16)
+        qkv = torch.empty((T, cfg.qkv_dim), device=dev, dtype=BF16)
+        attn = torch.empty((T, qd), device=dev, dtype=BF16)
+        o = torch.empty((T, D), device=dev, dtype=BF16)
+        xm = torch.empty((T, D), device=dev, dtype=BF16)
+        h2 = torch.empty((T, D), device=dev, dtype=BF16)
+        gu = torch.empty((T, 2 * I), device=dev, dtype=BF16)
+        act = torch.empty((T, I), device=dev, dtype=BF16)
+        dqkv = torch.empty((T, cfg.qkv_dim), device=dev, dtype=BF16)
+        lse2 = torch.empty((Hq, T), device=dev, dtype=F32)
+        for l in range(L - 1, -1, -1):
+            pre = f"model.layers.{l}."
+            x_in = st.ckpt[l]
+            Wqkv, Wo = self.p(pre + "self_attn.qkv.weight"), self.p(pre + "self_attn.o_proj.weight")
+            Wgu, Wd = self.p(pre + "mlp.gate_up.weight"), self.p(pre + "mlp.down_proj.weight")
+            # recompute
+            ops.rmsnorm(x_in, self.p(pre + "input_layernorm.weight"), eps, out=h)
+            ops.gemm(h, Wqkv, out=qkv, bias=self.p(pre + "self_attn.qkv.bias"))
+            ops.rope_apply(qkv, 0, Hq + Hkv, hd, st.cos, st.sin)
+            q, k, v = qkv[:, :qd], qkv[:, qd:qd + kd], qkv[:, qd + kd:]
+            ops.attn_fwd(q, k, v, st.lo, st.hi, st.P, Hq, Hkv, hd, scale, out=attn, lse=lse2)
+            ops.gemm(attn, Wo, out=o)
+            ops.rmsnorm(x_in, self.p(pre + "post_attention_layernorm.weight"), eps, delta=o, out=h2, x_out=xm)
+            ops.gemm(h2, Wgu, out=gu)
+            ops.swiglu(gu, out=act)
+            # MLP backward
+            self._wgrad(dx, act, pre + "mlp.down_proj.weight", acc)
+            dact = self._dgrad(dx, Wd, out=act)                             # act no longer needed: reuse its storage
+            dgu = ops.swiglu_bwd(dact, gu, out=gu)                          # in place over gate_up
+            self._wgrad(dgu, h2, pre + "mlp.gate_up.weight", acc)
+            dh2 = self._dgrad(dgu, Wgu, out=h2)
+            f32s.zero_()
+            dxm = ops.rmsnorm_bwd(dh2, xm, self.p(pre + "post_attention_layernorm.weight"), eps, f32s[:D], dres=dx, out=o)
+            self._small_grad(f32s[:D], pre + "post_attention_layernorm.weight", acc)
+            # attention backward (dxm is also d o_proj output)
+            self._wgrad(dxm, attn, pre + "self_attn.o_proj.weight", acc)
+            dattn = self._dgrad(dxm, Wo)
+            ops.attn_bwd(q, k, v, attn, dattn, lse2, st.lo, st.hi, st.P, Hq, Hkv, hd, scale,
+                         dqkv[:, :qd], dqkv[:, qd:qd + kd], dqkv[:, qd + kd:])
+            del dattn
+            ops.rope_apply(dqkv, 0, Hq + Hkv, hd, st.cos, st.sin, inverse=True)
+            f32s.zero_()
+            ops.colsum(dqkv, f32s[:cfg.qkv_dim])
+            self._small_grad(f32s[:cfg.qkv_dim], pre + "self_attn.qkv.bias", acc)
+            self._wgrad(dqkv, h, pre + "self_attn.qkv.weight", acc)
+            dhh = self._dgrad(dqkv, Wqkv, out=h)
+            f32s.zero_()
+            dx = ops.rmsnorm_bwd(dhh, x_in, self.p(pre + "input_layernorm.weight"), eps, f32s[:D], dres=dxm, out=xm)
+            self._small_grad(f32s[:D], pre + "input_layernorm.weight", acc)
+            dx = dx.clone() if l > 0 else dx                                 # xm is overwritten by the next recompute
+        # ---- embeddings: text rows scatter-add into the table gradient; vision rows flow into the merger ----
+        ops.scatter_rows(dx, st.text_scatter_idx, self._gview(embed_name), accumulate=True)
+        if st.vision_rows.numel() > 0:
+            dve = ops.gather_rows(dx, st.vision_rows)                       # [Nv, D] in original merged-token order
+            self._merger_backward(st, dve, acc)
+        self.grad_fresh = False
+
+    def _merger_backward(self, st: ScoreState, dve: torch.Tensor, acc: bool):
+        cfg = self.cfg
+        if not cfg.is_q25:
+            raise NotImplementedError("merger backward is built for the Qwen2.5-VL (RMSNorm) merger; the Qwen2-VL LayerNorm variant is forward-only")
+        plan, x_vit = st.plan, st.x_vit
+        keep: dict = {}
+        N, vd, unit = plan.n_patches, cfg.vit_hidden, cfg.merge_unit
+        Nv = N // unit
+        assert Nv % 8 == 0, "vision-token count must be a multiple of 8 for the transposed wgrad operands"
+        # recompute the merger forward from the saved ViT output
+        self.merger(x_vit, None, plan, "policy", keep=keep)
+        dm = ops.gather_rows(dve, self._i32(plan.window_index))            # back to window order
+        W0, W2 = self.p("visual.merger.mlp.0.weight"), self.p("visual.merger.mlp.2.weight")
+        f32s = torch.zeros(max(unit * vd, cfg.hidden_size), device=self.dev, dtype=F32)
+        self._wgrad(dm, keep["g1"], "visual.merger.mlp.2.weight", acc)
+        ops.colsum(dm, f32s[:cfg.hidden_size])
+        self._small_grad(f32s[:cfg.hidden_size], "visual.merger.mlp.2.bias", acc)
+        dg1 = self._dgrad(dm, W2)
+        da1 = ops.act_bwd(dg1, keep["a1"], 0)
+        self._wgrad(da1, keep["y4"], "visual.merger.mlp.0.weight", acc)
+        f32s.zero_()
+        ops.colsum(da1, f32s[:unit * vd])
+        self._small_grad(f32s[:unit * vd], "visual.merger.mlp.0.bias", acc)
+        dy4 = self._dgrad(da1, W0)
+        f32s.zero_()
+        ops.rmsnorm_bwd(dy4.view(N, vd), x_vit, self.p("visual.merger.ln_q.weight"), 1e-6, f32s[:vd])
+        self._small_grad(f32s[:vd], "visual.merger.ln_q.weight", acc)
+
+    # ------------------------------------------------------------------------------------------
+    # optimizer: global-norm clip + AdamW on this rank's shard of the flat buffer (ZeRO-2 semantics)
+    # ------------------------------------------------------------------------------------------
+    def optimizer_step(self, lr: float | None = None, grad_scale: float = 1.0) -> torch.Tensor:
+        """Returns the (pre-clip) global gradient norm as a 1-element device tensor."""
+        run = self.run
+        lr = run.learning_rate if lr is None else lr
+        g = self.grads.buf
+        if self.world > 1:
+            import torch.distributed as dist
+
+            shard_g = torch.empty(self.shard, device=self.dev, dtype=BF16)
+            dist.reduce_scatter_tensor(shard_g, g, op=dist.ReduceOp.AVG, group=self.pg)   # DP-mean of the gradients
+        else:
+            shard_g = g
+        gsq = torch.zeros(1, device=self.dev, dtype=F32)
+        ops.sumsq(shard_g, gsq)
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.all_reduce(gsq, group=self.pg)
+        self.opt_step += 1
+        p_shard = self.w.train.buf[self.shard_lo:self.shard_lo + self.shard]
+        ops.adamw(self.master, self.adam_m, self.adam_v, shard_g, p_shard, lr, run.adam_beta1, run.adam_beta2,
+                  run.adam_eps, run.weight_decay, self.opt_step, gnorm_sq=gsq, max_norm=run.max_grad_norm,
+                  grad_scale=grad_scale)
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.all_gather_into_tensor(self.w.train.buf, p_shard.clone(), group=self.pg)
+        self.grad_fresh = True
+        self._invalidate_after_update()
+        return gsq.sqrt() * grad_scale
+
+    def _invalidate_after_update(self):
+        pass  # decode graphs read weights through pointers into the flat buffer, which is updated in place
+
+    # ------------------------------------------------------------------------------------------
+    # one complete GRPO micro-step for one prompt group
+    # ------------------------------------------------------------------------------------------
+    def grpo_step(self, prompt: Prompt, reward_fn, seed: int | None = None, completion_override=None,
+                  loss_scale: float = 1.0, timers: dict | None = None):
+        """rollout -> mask -> policy/ref scoring -> rewards (host callback) -> advantage -> loss -> backward.
+        reward_fn(completion_ids_host [G, C] int64 numpy) -> rewards_per_func [G, n_funcs] float32 numpy.
+        Returns a dict of device tensors / python scalars (loss, stats, rewards, advantages, completion ids)."""
+        run, cfg = self.run, self.cfg
+        G, C = run.num_generations, run.max_completion_length
+        seed = run.seed if seed is None else seed
+
+        def mark(name):
+            if timers is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                timers.setdefault("_events", []).append((name, ev))
+
+        mark("start")
+        x_vit, delta, plan = self.vit_blocks(prompt.pixel_values, prompt.grid_thw)
+        emb = self.merger(x_vit, delta, plan, "policy")                     # x_vit now holds the final ViT stream
+        mark("vit")
+        if completion_override is None:
+            comp = self.rollout(prompt, emb, G, C, run.temperature, run.top_k, seed)
+        else:
+            comp = completion_override.to(device=self.dev, dtype=I32).contiguous()
+        mark("rollout")
+        mask, lengths = ops.eos_mask(comp, cfg.eos_token_id)
+        logp, ent, st = self.score(prompt, comp, emb, "policy", save=True, x_vit=x_vit, plan=plan)
+        mark("score_policy")
+        ref_logp = None
+        if run.beta != 0.0:
+            if self.ref is None:
+                raise RuntimeError("beta != 0 needs the reference parameter set (Engine(with_ref=True))")
+            emb_ref = self.merger(x_vit, None, plan, "ref")
+            ref_logp, _, _ = self.score(prompt, comp, emb_ref, "ref")
+        mark("score_ref")
+        comp_host = comp.cpu().numpy().astype(np.int64)                     # D2H: completions for the host reward fns
+        rpf = np.ascontiguousarray(reward_fn(comp_host), dtype=np.float32).reshape(G, -1)
+        rpf_dev = torch.from_numpy(rpf).to(self.dev)
+        rewards, adv, mean, std = ops.group_advantage(rpf_dev, G)
+        loss, dlogp, stats = ops.grpo_loss(logp, ref_logp, ent, adv, mask, run.beta, run.epsilon_low, run.epsilon_high,
+                                           run.use_grpo, loss_scale=loss_scale)
+        mark("reward_loss")
+        self.backward(st, dlogp)
+        mark("backward")
+        return dict(loss=loss, stats=stats, rewards=rewards, rewards_per_func=rpf_dev, advantages=adv, reward_std=std,
+                    completion_ids=comp, completion_mask=mask, logp=logp, ref_logp=ref_logp, entropy=ent, dlogp=dlogp)
+
+
+def finish_timers(timers: dict) -> dict:
+    """Convert the CUDA events recorded by grpo_step(timers=...) into per-phase milliseconds."""
+    ev = timers.pop("_events", [])
+    torch.cuda.synchronize()
+    out = {}
+    for (n0, e0), (n1, e1) in zip(ev[:-1], ev[1:]):
+        out[n1] = out.get(n1, 0.0) + e0.elapsed_time(e1)
+    return out

@@ -36,8 +36,8 @@ _SIGNATURES: dict[str, list] = {
     "t1_logits_backward": [vp, i64, i32, i32, vp, vp, vp, vp, i64, vp],
     "t1_eos_mask": [vp, i32, i32, i32, vp, vp, vp],
     # elementwise.cu
-    "t1_rmsnorm": [vp, vp, vp, vp, i32, i32, f32, vp],
-    "t1_layernorm": [vp, vp, vp, vp, vp, i32, i32, f32, vp],
+    "t1_rmsnorm": [vp, vp, vp, vp, vp, i32, i32, f32, vp],
+    "t1_layernorm": [vp, vp, vp, vp, vp, vp, i32, i32, f32, vp],
     "t1_rmsnorm_bwd": [vp, vp, vp, vp, vp, vp, i32, i32, f32, vp],
     "t1_rope_table": [vp, i32, vp, vp, i32, vp, vp, vp],
     "t1_rope_apply": [vp, i64, i32, i32, i32, vp, vp, i32, i32, vp, i64, vp],
@@ -47,6 +47,7 @@ _SIGNATURES: dict[str, list] = {
     "t1_act": [vp, vp, i64, i32, vp],
     "t1_act_bwd": [vp, vp, vp, i64, i32, vp],
     "t1_gather_rows": [vp, i64, vp, vp, i64, i32, i32, vp],
+    "t1_gather_rows_f32": [vp, i64, vp, vp, i64, i32, i32, vp],
     "t1_scatter_rows": [vp, i64, vp, vp, i64, i32, i32, i32, vp],
     "t1_transpose_bf16": [vp, i64, vp, i64, i32, i32, vp],
     "t1_colsum": [vp, i64, i32, i32, vp, vp],

@@ -67,22 +67,36 @@ def linear(x, w, out=None, bias=None, accumulate=False, out_dtype=BF16):
     return gemm(x, w, out=out, bias=bias, accumulate=accumulate, out_dtype=out_dtype)
 
 
-def rmsnorm(x, w, eps, delta=None, out=None):
-    """y = rmsnorm(x (+= delta)) * w.  x is updated in place when delta is given (fused residual add)."""
+def rmsnorm(x, w, eps, delta=None, out=None, x_out=None):
+    """y = rmsnorm(x + delta) * w.  With delta, the summed residual stream is written to x_out (default: x in place)."""
     T, D = x.shape
     assert x.is_contiguous()
     if out is None:
         out = torch.empty_like(x)
-    call("t1_rmsnorm", ptr(x), ptr(delta), ptr(w), ptr(out), T, D, float(eps), stream_ptr())
+    if delta is not None and x_out is None:
+        x_out = x
+    call("t1_rmsnorm", ptr(x), ptr(delta), ptr(x_out), ptr(w), ptr(out), T, D, float(eps), stream_ptr())
     return out
 
 
-def layernorm(x, w, b, eps, delta=None, out=None):
+def layernorm(x, w, b, eps, delta=None, out=None, x_out=None):
     T, D = x.shape
     assert x.is_contiguous()
     if out is None:
         out = torch.empty_like(x)
-    call("t1_layernorm", ptr(x), ptr(delta), ptr(w), ptr(b), ptr(out), T, D, float(eps), stream_ptr())
+    if delta is not None and x_out is None:
+        x_out = x
+    call("t1_layernorm", ptr(x), ptr(delta), ptr(x_out), ptr(w), ptr(b), ptr(out), T, D, float(eps), stream_ptr())
+    return out
+
+
+def gather_rows_f32(src, idx, out=None):
+    """out_bf16[i] = bf16(src_f32[idx[i]]) — pixel rows into ViT window order."""
+    n = idx.numel() if idx is not None else src.shape[0]
+    width = src.shape[1]
+    if out is None:
+        out = torch.empty((n, width), device=src.device, dtype=BF16)
+    call("t1_gather_rows_f32", ptr(src), src.stride(0), ptr(idx), ptr(out), out.stride(0), n, width, stream_ptr())
     return out
 
 
