@@ -91,6 +91,7 @@ class FlatParams:
 
     def __init__(self, specs: list[Spec], device, pad_to: int = ALIGN, buf: torch.Tensor | None = None):
         self.specs = specs
+        self.pad_to = pad_to
         self.layout: dict[str, tuple[int, tuple]] = {}
         off = 0
         for sp in specs:
@@ -111,10 +112,10 @@ class FlatParams:
 
     def like(self, zero: bool = True) -> "FlatParams":
         buf = torch.zeros_like(self.buf) if zero else torch.empty_like(self.buf)
-        return FlatParams(self.specs, self.buf.device, buf=buf, pad_to=1)
+        return FlatParams(self.specs, self.buf.device, buf=buf, pad_to=self.pad_to)
 
     def clone(self) -> "FlatParams":
-        return FlatParams(self.specs, self.buf.device, buf=self.buf.clone(), pad_to=1)
+        return FlatParams(self.specs, self.buf.device, buf=self.buf.clone(), pad_to=self.pad_to)
 
 
 class ModelWeights:
