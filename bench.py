@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py — GRPO rollout-samples/s of the hot path (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py --gpus 1 --steps 3 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...        # the reference's CPU path (oracle port) on the host cores
+
+A step = ONE complete GRPO update for one prompt-group per GPU: ViT, prompt prefill, C-token sampled
+rollout of G completions, policy + reference scoring, rewards (host parse + device IoU), group advantage, clipped
+loss, full backward and the sharded AdamW step.  Workload = cfg2: Qwen2.5-VL-7B dims (the class the reference
+instantiates, timer1_trainer.py:244), 16 temporal slots of 448x448 -> grid (16,32,32), 4096 vision tokens, prompt
+~4.2k tokens, G=8, C=200, synthetic N(0,1) pixels, random-init N(0,0.02) bf16 weights, synthetic template rewards.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "grpo_rollout_samples_per_sec"
+UNIT = "samples/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="qwen2.5-vl-7b")
+    ap.add_argument("--slots", type=int, default=16, help="temporal slots of 32x32 patches (16 -> cfg2, 32 -> cfg3, 64 -> cfg5)")
+    ap.add_argument("--group-size", type=int, default=8)
+    ap.add_argument("--completion-len", type=int, default=200)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--phase-times", action="store_true", help="print a per-phase breakdown to stderr")
+    return ap.parse_args()
+
+
+def workload_name(args):
+    return (f"cfg2-family: {args.model} dims, grid ({args.slots},32,32) = {args.slots * 256} vision tokens, "
+            f"G={args.group_size}, C={args.completion_len}, one prompt-group per GPU per step")
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling (nvidia-smi, during the timed region)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc, self.thread = index, [], None, None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline (oracle port on the host cores)
+# ------------------------------------------------------------------------------------------------
+def cpu_reference(args, steps: int, warmup: int) -> dict:
+    import torch
+
+    from oracle import cpu_baseline as B, qwen_vl_oracle as O
+    from time_r1_b200 import config, flops
+
+    full = config.PRESETS[args.model]()
+    ocfg = O.default_cfg(**{k: v for k, v in full.to_dict().items() if k in O.default_cfg()})
+    scfg = B.sample_cfg(ocfg)
+    G_s, C_s, grid_s = 2, 4, [(2, 16, 16)]
+    st = B.ReferenceStyleStep(scfg, grid_s, G=G_s, C=C_s)
+    for _ in range(warmup):
+        st.step()
+    ts = [st.step() for _ in range(steps)]
+    t_sample = sum(ts) / len(ts)
+    # scale the bounded sample to the full workload by reference-style FLOPs
+    import dataclasses
+    s_model = dataclasses.replace(full, num_hidden_layers=1, vit_depth=1, fullatt_block_indexes=(0,), vocab_size=32768)
+    f_sample = flops.reference_style_flops(s_model, grid_s, st.P, G_s, C_s)
+    grid = [(args.slots, 32, 32)]
+    P_full = 4 + args.slots * 256 + 1 + 110 + 5
+    f_full = flops.reference_style_flops(full, grid, P_full, args.group_size, args.completion_len)
+    t_full = t_sample * f_full / f_sample
+    value = args.group_size / t_full
+    return dict(value=value, unit=UNIT, cores=st.threads, kind="port", sample=B.SAMPLE_DESC,
+                sample_s_per_step=round(t_sample, 3), sample_tflop=round(f_sample / 1e12, 4), full_tflop=round(f_full / 1e12, 1),
+                cpu_tflops=round(f_sample / t_sample / 1e12, 3), est_full_step_s=round(t_full, 1))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb = cpu_reference(args, max(1, args.steps), max(1, min(args.warmup, 2)))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": cb["est_full_step_s"] * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": workload_name(args)},
+        "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def synthetic_prompt(cfg, slots: int, rank: int, step: int, device):
+    """SURVEY §8d synthetic inputs (seed 42 mirrors main.py:552)."""
+    import numpy as np
+    import torch
+
+    rng = np.random.default_rng(42 + 1000 * rank + step)
+    N = slots * 32 * 32
+    nv = N // cfg.merge_unit
+    text = rng.integers(0, 151643, 110)
+    ids = np.concatenate([[151644, 872, 198, 151652], np.full(nv, cfg.video_token_id), [151653], text, [151645, 198, 151644, 77091, 198]]).astype(np.int64)
+    g = torch.Generator().manual_seed(42 + 1000 * rank + step)
+    pix_host = torch.randn(N, cfg.patch_dim, generator=g, dtype=torch.float32).pin_memory()
+    return ids, pix_host, [(slots, 32, 32)]
+
+
+class TemplateRewards:
+    """Completions are overwritten post hoc with template strings (random-init models never emit <answer> tags —
+    SURVEY §0); the strings go through the product's reward path (host regex parse + t1_iou_reward kernel)."""
+
+    def __init__(self, G: int, rank: int):
+        import numpy as np
+
+        self.rows = json.load(open(os.path.join(ROOT, "tests", "golden", "iou_train_2k5.json")))
+        self.rng = np.random.default_rng(7 + rank)
+        self.G, self.cursor = G, rank
+
+    def __call__(self, completion_ids):
+        from time_r1_b200 import rewards
+
+        row = self.rows[self.cursor % len(self.rows)]
+        self.cursor += 1
+        dur = row["duration"]
+        texts = []
+        for g in range(self.G):
+            s, e = sorted(self.rng.uniform(0, dur, 2))
+            if g % 4 == 3:
+                texts.append(f"<think>unsure</think> {s:.2f} to {e:.2f}")      # malformed: no <answer> block
+            else:
+                texts.append(f"<think>the event spans these frames</think><answer>{s:.2f} to {e:.2f}</answer>")
+        r1 = rewards.iou_timestamp_reward_v2(texts, [row["gt"]] * self.G, durations=[dur] * self.G)
+        r2 = rewards.format_reward(texts)
+        import numpy as np
+
+        return np.stack([np.asarray(r1, np.float32), np.asarray(r2, np.float32)], 1)
+
+
+def attention_microbench(eng, P: int, G: int, C: int):
+    """Decode-attention kernel alone at mid-rollout (step C/2), L2 flushed between launches: unique K/V bytes / time."""
+    import torch
+
+    from time_r1_b200.lib import call, ptr, stream_ptr
+
+    cfg = eng.cfg
+    st = eng._decode_state(P, G, C)
+    Kc, Vc = st["kv"][0]
+    step = C // 2
+    st["step"].fill_(step)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=eng.dev)
+    Hq, Hkv, hd = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim
+    ts = []
+    for i in range(13):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        call("t1_decode_attn", ptr(st["qkv"]), st["qkv"].stride(0), ptr(Kc), ptr(Vc), G, Hq, Hkv, hd, P, st["cpad"],
+             ptr(st["step"]), ptr(st["ws_o"]), ptr(st["ws_ml"]), ptr(st["attn"]), st["attn"].stride(0), hd ** -0.5, stream_ptr())
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    ms = ts[len(ts) // 2]
+    kv_bytes = 2.0 * Hkv * hd * 2 * (P + G * (step + 1)) + 2.0 * G * Hq * hd * 2
+    return {"kernel": "decode_attn+combine", "unique_kv_bytes": kv_bytes, "ms": round(ms, 5), "gbs": round(kv_bytes / ms / 1e6, 1)}
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from time_r1_b200 import config, engine, flops, lib, ops, weights
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    pg = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        pg = dist.group.WORLD
+    lib.load()
+    cfg = config.PRESETS[args.model]()
+    run = config.RunConfig(num_generations=args.group_size, max_completion_length=args.completion_len)
+    G, C = run.num_generations, run.max_completion_length
+    mw = weights.ModelWeights(cfg, dev, world_size=world)
+    mw.init_random(seed=0)          # same weights on every rank (data parallel)
+    eng = engine.Engine(cfg, mw, run, rank=rank, world_size=world, process_group=pg)
+    rewards = TemplateRewards(G, rank)
+    ids, pix_host, grid = synthetic_prompt(cfg, args.slots, rank, 0, dev)
+    P = len(ids)
+    pix_dev = pix_host.to(dev)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+
+    def one_step(step_idx: int, e2e: bool, timers=None):
+        if e2e:
+            pix = pix_host.to(dev, non_blocking=True)                 # H2D of this step's inputs from pinned memory
+        else:
+            pix = pix_dev
+        prompt = engine.Prompt(input_ids=ids, pixel_values=pix, grid_thw=grid, second_per_grid_ts=[1.0])
+        out = eng.grpo_step(prompt, rewards, seed=run.seed + step_idx * world + rank, timers=timers)
+        gn = eng.optimizer_step()
+        if e2e:
+            return float(out["loss"].item()), float(gn.item())        # D2H of the step's result
+        return out["loss"], gn
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n: int, e2e: bool, base: int):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            one_step(base + i, e2e)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for i in range(args.warmup):
+        one_step(i, False)
+    if args.phase_times and rank == 0:
+        tm = {}
+        one_step(args.warmup, False, timers=tm)
+        print("[phase ms]", json.dumps({k: round(v, 1) for k, v in engine.finish_timers(tm).items()}), file=sys.stderr)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    lib.load().t1_launch_count(1)
+    eng.metrics_launches = 0
+    ops.PROFILER.start()
+    ms_total = timed(args.steps, False, 100)
+    ops.PROFILER.stop()
+    launches = int(lib.load().t1_launch_count(0)) + eng.metrics_launches
+    clocks = sampler.stop() if rank == 0 else {}
+    prof = ops.PROFILER.summary()
+    ms_e2e = timed(args.steps, True, 200)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    ms_per_step = ms_total / args.steps
+    value = world * G / (ms_per_step / 1e3)
+    e2e_value = world * G / (ms_e2e / args.steps / 1e3)
+    gm = prof.get("gemm_bf16_tn", dict(launches=0, flops=0.0, ms=1.0))
+    gemm_tflops = gm["flops"] / max(gm["ms"], 1e-9) / 1e9
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    algo = flops.step_flops(cfg, grid, P, G, C)
+    roofline = {
+        "bound": "tensor", "kernel": "gemm_bf16_tn (tcgen05)", "achieved": round(gemm_tflops, 1), "peak": peak_tf, "unit": "TFLOP/s",
+        "frac": round(gemm_tflops / peak_tf, 4), "traffic": None, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback",
+        "launches_per_step": gm["launches"] // max(1, args.steps), "gemm_ms_per_step": round(gm["ms"] / args.steps, 2),
+        "gemm_tflop_per_step": round(gm["flops"] / args.steps / 1e12, 1),
+        "step_algorithmic_tflop": round(algo["total"] / 1e12, 1),
+        "step_frac_of_flop_roofline": round(algo["total"] / (ms_per_step / 1e3) / 1e12 / peak_tf, 4),
+    }
+    attn = attention_microbench(eng, P, G, C)
+    attn["peak_gbs"] = peaks.get("hbm_gbs", 6650.0)
+    attn["frac"] = round(attn["gbs"] / attn["peak_gbs"], 4)
+    line = {
+        "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(ms_per_step, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": workload_name(args), "prompt_tokens": P, "vision_tokens": args.slots * 256, "group_size": G,
+                   "completion_len": C, "parallelism": f"dp{world}+zero2-sharded-adamw", "l2": "inputs larger than L2 (>=16 GB of weights streamed per pass)"},
+        "clocks": clocks,
+        "e2e": {"value": round(e2e_value, 4), "unit": UNIT, "h2d_bytes_per_step": int(pix_host.numel() * 4 + ids.size * 4), "d2h_bytes_per_step": int(G * C * 4 + 8)},
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "attn": attn,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        del eng
+        torch.cuda.empty_cache()
+        line["cpu_baseline"] = cpu_reference(args, steps=2, warmup=1)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -11,11 +11,10 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
 
 
 def build(family="qwen2_5_vl", beta=0.04, use_grpo=False, G=4, C=12):
-    import qwen_vl_oracle as O
+    from oracle import qwen_vl_oracle as O
     from time_r1_b200 import config, engine, weights
 
     cfg = config.toy(family)

@@ -7,6 +7,48 @@ from . import lib
 from .lib import call, ptr, stream_ptr
 
 
+class KernelProfiler:
+    """Optional per-launch CUDA-event timing of the GEMM kernels (bench.py roofline). Disabled by default."""
+
+    def __init__(self):
+        self.enabled = False
+        self.records: list = []   # (kind, flops, bytes, start_event, end_event)
+
+    def start(self):
+        self.enabled, self.records = True, []
+
+    def stop(self):
+        self.enabled = False
+
+    def begin(self):
+        if not self.enabled:
+            return None
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def end(self, kind, flops, nbytes, e0):
+        if e0 is None:
+            return
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        self.records.append((kind, flops, nbytes, e0, e1))
+
+    def summary(self) -> dict:
+        torch.cuda.synchronize()
+        out: dict = {}
+        for kind, fl, nb, e0, e1 in self.records:
+            d = out.setdefault(kind, dict(launches=0, flops=0.0, bytes=0.0, ms=0.0))
+            d["launches"] += 1
+            d["flops"] += fl
+            d["bytes"] += nb
+            d["ms"] += e0.elapsed_time(e1)
+        return out
+
+
+PROFILER = KernelProfiler()
+
+
 def _chk(t: torch.Tensor, dtype, name: str):
     if not t.is_cuda:
         raise lib.Timer1Error(f"{name}: tensor must live on a CUDA device (no CPU fallback exists)")
@@ -39,8 +81,10 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None = None, bias
             flags |= lib.GEMM_BIAS_F32
         elif bias.dtype != torch.bfloat16:
             raise lib.Timer1Error("gemm: bias must be bf16 or fp32")
+    e0 = PROFILER.begin()
     call("t1_gemm_bf16_tn", ptr(a), a.stride(0), ptr(b), b.stride(0), ptr(out), out.stride(0), M, N, K, ptr(bias),
          flags, stream_ptr())
+    PROFILER.end("gemm_bf16_tn", 2.0 * M * N * K, 2.0 * (M * K + N * K) + out.element_size() * M * N, e0)
     return out
 
 
