@@ -41,6 +41,7 @@ def parse_args():
     ap.add_argument("--completion-len", type=int, default=200)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--phase-times", action="store_true", help="print a per-phase breakdown to stderr")
+    ap.add_argument("--kernel-times", action="store_true", help="print per-entry-point CUDA-event totals of one extra step to stderr")
     return ap.parse_args()
 
 
@@ -285,6 +286,12 @@ def run_ours(args):
         tm = {}
         one_step(args.warmup, False, timers=tm)
         print("[phase ms]", json.dumps({k: round(v, 1) for k, v in engine.finish_timers(tm).items()}), file=sys.stderr)
+    if args.kernel_times and rank == 0:
+        lib.CALL_PROFILER.start()
+        one_step(args.warmup + 1, False)
+        lib.CALL_PROFILER.stop()
+        summ = lib.CALL_PROFILER.summary()
+        print("[kernel ms, eager part of one step]", json.dumps({k: [v[0], round(v[1], 2)] for k, v in summ.items()}), file=sys.stderr)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()

@@ -1,0 +1,172 @@
+/* timer1.h — C ABI of libtimer1.so, the B200-native (sm_100a) kernel library behind Time-R1's GRPO hot path.
+ *
+ * The reference (xiaomi-research/time-r1) has no FFI: its "operator API" is the Python surface main.py uses
+ * (src/time_r1/__init__.py:1-6, TimeR1_Trainer) and every FLOP runs inside third-party Python packages.  This
+ * header is therefore the boundary a maintainer binds with ctypes; each entry point cites the
+ * reference call site whose arithmetic it replaces.  Paths are relative to /root/reference; "Q25:" is
+ * transformers/models/qwen2_5_vl/modeling_qwen2_5_vl.py (the module timer1_trainer.py:244 instantiates).
+ *
+ * Conventions
+ *   - every function returns int: 0 = ok, <0 = error (T1_ERR_*); t1_last_error() returns a thread-local message
+ *     owned by the library, valid until the next failing call on that thread;
+ *   - all tensor arguments are DEVICE pointers owned by the caller, row-major; dtype is stated per argument
+ *     (bf16 = __nv_bfloat16); the library never allocates or frees caller memory — workspaces are caller-provided;
+ *   - leading dimensions (ld*) are in ELEMENTS; unless stated they must be multiples of 8 (16-byte rows);
+ *   - every call is asynchronous on the given cudaStream_t and capturable into a CUDA graph;
+ *   - no torch types, no host callbacks; one host thread per device.
+ */
+#ifndef TIMER1_H
+#define TIMER1_H
+
+#include <cuda_runtime_api.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define T1_OK 0
+#define T1_ERR_ARG (-1)
+#define T1_ERR_CUDA (-2)
+#define T1_ERR_UNSUPPORTED (-3)
+
+/* t1_gemm_bf16_tn flags */
+#define T1_GEMM_OUT_F32 1
+#define T1_GEMM_ACCUMULATE 2
+#define T1_GEMM_BIAS_F32 4
+
+/* ---- core --------------------------------------------------------------------------------------------- */
+const char* t1_last_error(void);
+int t1_version(void);
+int t1_device_info(int* out4 /* host: {sm_count, cc_major, cc_minor, l2_bytes} */);
+void t1_count_launch(void);
+unsigned long long t1_launch_count(int reset); /* kernels launched through this library (bench "gpu_launches") */
+
+/* ---- dense contractions -------------------------------------------------------------------------------- */
+/* D[M,N] (+)= A[M,K] * B[N,K]^T (+ bias[N]).  tcgen05/TMEM/TMA kernel.  Replaces every nn.Linear / Conv3d the
+ * reference executes through cuBLAS/cuDNN: Q25:106-114 (patch embed), :214-215 (ViT qkv/proj), :77-88 (ViT MLP),
+ * :133-146 (merger), :704-707 (LLM q/k/v/o), :611-624 (LLM MLP), lm_head (timer1_trainer.py:452-457), and their
+ * autograd backward (HF trainer.py:1934).  A, B bf16; D bf16 or fp32 (T1_GEMM_OUT_F32); N % 8 == 0. */
+int t1_gemm_bf16_tn(const void* A, long long lda, const void* B, long long ldb, void* D, long long ldd, int M, int N,
+                    int K, const void* bias, int flags, cudaStream_t stream);
+
+/* y[M<=64, N] (+)= x[M,K] * W[N,K]^T (+ bias bf16).  Weight-streaming decode GEMM (HBM-bound; thread-block-cluster
+ * split-K).  Replaces the per-token linears inside HF generate (timer1_trainer.py:568-573).  N % 16, K % 32. */
+int t1_skinny_gemm(const void* x, long long ldx, const void* W, long long ldw, const void* bias, void* y,
+                   long long ldy, int M, int N, int K, int out_f32, int accumulate, cudaStream_t stream);
+
+/* ---- attention ------------------------------------------------------------------------------------------ */
+/* Flash attention over a packed token axis.  Key j is visible to query row i iff
+ *     j < row_hi[i] && (j >= row_lo[i] || j < shared_len).
+ * Replaces flash-attn-2 varlen: ViT window/full attention Q25:244-261,498-509 (non-causal: lo/hi = window bounds),
+ * LLM causal attention Q25:740-755 (lo = 0, hi = i+1) and — new — the prefix-sharing packed scoring layout
+ * (prompt rows causal; completion rows lo = own start, hi = i+1, shared_len = P).
+ * Q [T, Hq, hd] / K,V [Tk, Hkv, hd] bf16 with token strides ldq/ldk/ldv; O [T, Hq*hd] bf16; LSE2 [Hq, T] fp32 in
+ * log2 domain (nullable).  head_dim in {64, 80, 128}. */
+int t1_attn_fwd(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv, void* O,
+                long long ldo, float* LSE2, const int* row_lo, const int* row_hi, int shared_len, int T, int Tk, int Hq,
+                int Hkv, int head_dim, float scale, cudaStream_t stream);
+/* Backward of the above (autograd through flash-attn in the reference).  Workspaces: delta_ws [Hq*T] fp32,
+ * summ_ws [4*ceil(T/64)] int32.  head_dim in {64, 128}. */
+int t1_attn_bwd(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv, const void* O,
+                long long ldo, const void* dO, long long lddo, const float* LSE2, float* delta_ws, int* summ_ws, void* dQ,
+                long long lddq, void* dK, long long lddk, void* dV, long long lddv, const int* row_lo, const int* row_hi,
+                int shared_len, int T, int Tk, int Hq, int Hkv, int head_dim, float scale, cudaStream_t stream);
+
+/* ---- decode (HF GenerationMixin._sample, timer1_trainer.py:568-573) -------------------------------------- */
+/* Rotate q,k of qkv [B, (Hq+2Hkv)*hd] with table row *step_ptr and append k,v at cache slot
+ * prefix_len + b*cpad + *step_ptr.  Kc/Vc [prefix_len + B*cpad, Hkv*hd] bf16. */
+int t1_decode_rope_append(void* qkv, long long ld, int B, int Hq, int Hkv, int head_dim, const float* cos_t,
+                          const float* sin_t, const int* step_ptr, void* Kc, void* Vc, int prefix_len, int cpad,
+                          cudaStream_t stream);
+/* Split-KV decode attention over [shared prompt prefix | per-sequence completion slots] + combine.
+ * Workspaces (fp32): ws_o = n_chunks*Hkv*rows_pad*128, ws_ml = n_chunks*Hkv*rows_pad*2 with
+ * n_chunks = ceil(prefix_len/128) + B*cpad/128, rows_pad = ceil(B*Hq/Hkv/64)*64.  head_dim = 128, cpad % 128 == 0. */
+int t1_decode_attn(const void* q, long long ldq, const void* Kc, const void* Vc, int B, int Hq, int Hkv, int head_dim,
+                   int prefix_len, int cpad, const int* step_ptr, float* ws_o, float* ws_ml, void* out, long long ldo,
+                   float scale, cudaStream_t stream);
+/* temperature -> top-k -> softmax -> multinomial (Philox4x32-10 keyed by seed, counter (row, step)); temperature <= 0
+ * is greedy arg-max.  HF 4.51.1 generate defaults.  logits [B, V] fp32 (ld may be 0: shared row);
+ * seed_ptr (device, nullable) overrides seed so captured graphs stay seed-independent; writes
+ * out_ids[b, *step_ptr + step_offset], next_ids[b]; finished[b] latches on any of eos_ids, then emits pad_id. */
+int t1_sample(const float* logits, long long ld, int B, int V, float temperature, int top_k, unsigned long long seed,
+              const unsigned long long* seed_ptr, const int* step_ptr, int step_offset, const int* eos_ids, int n_eos,
+              int pad_id, int* finished, int* out_ids, int out_ld, int* next_ids, float* out_u, cudaStream_t stream);
+int t1_incr(int* p, int v, cudaStream_t stream);
+
+/* ---- token-wise kernels (all bf16 storage, fp32 math) ----------------------------------------------------- */
+/* y = w * rmsnorm(x + delta); with delta the rounded sum is written to x_out (may alias x).  Q25:66-71 + the
+ * residual adds of Q25:313-321,805-827 fused in. */
+int t1_rmsnorm(const void* x, const void* delta, void* x_out, const void* w, void* y, int T, int D, float eps,
+               cudaStream_t stream);
+/* LayerNorm variant for the Qwen2-VL ViT (modeling_qwen2_vl.py:461-464). */
+int t1_layernorm(const void* x, const void* delta, void* x_out, const void* w, const void* b, void* y, int T, int D,
+                 float eps, cudaStream_t stream);
+/* dx = dres + d(rmsnorm)/dx; dw (fp32, caller-zeroed) += sum_t dy * xhat. */
+int t1_rmsnorm_bwd(const void* dy, const void* x, const void* w, const void* dres, void* dx, float* dw, int T, int D,
+                   float eps, cudaStream_t stream);
+/* cos/sin[t, i] of pos[axis_id[i], t] * inv_freq[i]: M-RoPE (Q25:595-608,659-665) and ViT 2-D RoPE (Q25:382-409). */
+int t1_rope_table(const int* pos, int T, const int* axis_id, const float* inv_freq, int half, float* cos_t,
+                  float* sin_t, cudaStream_t stream);
+/* rotate_half rotation of n_heads heads at column col0 of x [T, ld] in place (inverse != 0: transpose rotation, used
+ * for gradients); optional copy of the rotated heads to out (KV cache).  Q25:149-167, :627-669. */
+int t1_rope_apply(void* x, long long ld, int col0, int n_heads, int head_dim, const float* cos_t, const float* sin_t,
+                  int inverse, int T, void* out, long long ldo, cudaStream_t stream);
+int t1_copy_cols(const void* src, long long lds, void* dst, long long ldd, int T, int width, cudaStream_t stream);
+/* act = silu(gate) * up for gate_up [T, 2I] (Q25:611-624, :77-88) and its backward. */
+int t1_swiglu(const void* gate_up, void* act, long long T, int I, cudaStream_t stream);
+int t1_swiglu_bwd(const void* dact, const void* gate_up, void* dgate_up, long long T, int I, cudaStream_t stream);
+/* mode 0: exact GELU (merger, Q25:139); mode 1: QuickGELU (Qwen2-VL ViT MLP). */
+int t1_act(const void* x, void* y, long long n, int mode, cudaStream_t stream);
+int t1_act_bwd(const void* dy, const void* x, void* dx, long long n, int mode, cudaStream_t stream);
+/* dst[i] = src[idx[i]] / dst[idx[i]] (+)= src[i] over bf16 rows (idx < 0 skips): embedding lookup, masked_scatter of
+ * video embeddings (Q25:1309-1315), window permutation (Q25:478-484,512-513), embedding-gradient scatter-add. */
+int t1_gather_rows(const void* src, long long lds, const int* idx, void* dst, long long ldd, int n, int width,
+                   cudaStream_t stream);
+int t1_gather_rows_f32(const float* src, long long lds, const int* idx, void* dst, long long ldd, int n, int width,
+                       cudaStream_t stream); /* fp32 pixel rows -> bf16, permuted (Q25:1149 cast fused) */
+int t1_scatter_rows(const void* src, long long lds, const int* idx, void* dst, long long ldd, int n, int width,
+                    int accumulate, cudaStream_t stream);
+int t1_transpose_bf16(const void* in, long long ld, void* out, long long ldo, int R, int C, cudaStream_t stream);
+int t1_colsum(const void* x, long long ld, int R, int C, float* out /* fp32, += */, cudaStream_t stream);
+int t1_f32_to_bf16(const float* src, void* dst, long long n, int accumulate, cudaStream_t stream);
+int t1_add_bf16(void* y, const void* x, long long n, cudaStream_t stream);
+int t1_bf16_to_f32(const void* src, float* dst, long long n, cudaStream_t stream);
+
+/* ---- GRPO: rewards, advantage, loss (warp/block-reduction tier) ------------------------------------------- */
+/* IoU rewards in fp64, bit-identical to CPython: mode 0 = iou_timestamp_reward (main.py:145-181), mode 1 =
+ * iou_timestamp_reward_v2 (main.py:184-231).  valid[i] == 0 (unparsable completion) -> 0.  union <= 0 -> 0 (the
+ * reference leaves `iou` unbound there, main.py:165-168). */
+int t1_iou_reward(int mode, const double* pred_s, const double* pred_e, const unsigned char* valid, const double* gt_s,
+                  const double* gt_e, const double* dur, double* out64, float* out32, int n, cudaStream_t stream);
+/* rewards = sum over functions; per-group mean, UNBIASED std; adv = (r - mean) / (std + eps)
+ * (timer1_trainer.py:700-712).  rewards_per_func [n, nf] fp32; n % G == 0. */
+int t1_group_advantage(const float* rewards_per_func, int n, int nf, int G, float eps, float* rewards, float* adv,
+                       float* mean, float* std_, cudaStream_t stream);
+/* k3 KL, PPO-clip or per-sequence GRPO loss, dL/dlogp and the logged metrics (timer1_trainer.py:635-639,713-777).
+ * old_logp NULL = on-policy (ratio 1, as in the reference).  out_stats[8] = {loss, mean_kl, mean_entropy,
+ * mean_completion_length, sum(mask), clip_low_frac, clip_high_frac, mean_ratio}. */
+int t1_grpo_loss(const float* logp, const float* old_logp, const float* ref_logp, const float* entropy,
+                 const float* adv, const int* mask, int rows, int C, float beta, float eps_lo, float eps_hi,
+                 int use_grpo, float loss_scale, float* out_loss, float* out_dlogp, float* out_stats,
+                 cudaStream_t stream);
+/* log_softmax gather + entropy per row of fp32 logits (timer1_trainer.py:458-481). */
+int t1_logprob_entropy(const float* logits, long long ld, int rows, int V, const int* target, float* out_logp,
+                       float* out_entropy, float* out_lse, cudaStream_t stream);
+/* dlogits = dlogp * (onehot(target) - softmax) in bf16 (autograd of the above). */
+int t1_logits_backward(const float* logits, long long ld, int rows, int V, const int* target, const float* lse,
+                       const float* dlogp, void* dlogits, long long ldd, cudaStream_t stream);
+/* completion mask up to and including the first EOS (timer1_trainer.py:581-590). */
+int t1_eos_mask(const int* ids, int rows, int C, int eos_id, int* mask, int* lengths, cudaStream_t stream);
+
+/* ---- optimizer (DeepSpeed AdamW + HF clip_grad_norm_, HF trainer.py:2493,1760) ----------------------------- */
+int t1_sumsq_bf16(const void* g, long long n, float* out_accum, cudaStream_t stream);
+/* Decoupled AdamW on a flat shard: fp32 master/m/v, bf16 grad in, bf16 param out; the clip coefficient
+ * min(1, max_norm / (sqrt(*gnorm_sq) * grad_scale + 1e-6)) is applied in-kernel. n % 4 == 0. */
+int t1_adamw(float* master, float* m, float* v, const void* grad, void* param, long long n, float lr, float beta1,
+             float beta2, float eps, float wd, int step, const float* gnorm_sq, float max_norm, float grad_scale,
+             cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TIMER1_H */

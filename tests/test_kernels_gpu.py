@@ -314,7 +314,7 @@ def test_sampler_topk_greedy_and_distribution():
     st = torch.tensor([1], device=DEV, dtype=torch.int32)
 
     def run(temp, k, seed, step_off=0):
-        call("t1_sample", ptr(logits), V, B, V, float(temp), k, seed, ptr(st), step_off, ptr(eos), 2, 151643, ptr(fin),
+        call("t1_sample", ptr(logits), V, B, V, float(temp), k, seed, 0, ptr(st), step_off, ptr(eos), 2, 151643, ptr(fin),
              ptr(out), 4, ptr(nxt), 0, stream_ptr())
         torch.cuda.synchronize()
         return nxt.clone()

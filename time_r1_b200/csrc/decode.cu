@@ -8,6 +8,7 @@
 //                      form a 64-row MMA tile against each prefix key chunk; partial (m, l, O) + a combine kernel
 //   * rope + KV append, sampler (temperature -> top-k -> softmax -> multinomial, Philox4x32-10), step counter
 #include "t1_common.cuh"
+#include <cooperative_groups.h>
 
 namespace {
 
@@ -18,18 +19,29 @@ template <int NB>
 __global__ void __launch_bounds__(256)
 skinny_gemm_kernel(const bf16* __restrict__ x, long long ldx, const bf16* __restrict__ W, long long ldw,
                    const bf16* __restrict__ bias, void* __restrict__ y, long long ldy, int M, int N, int K,
-                   int out_f32, int accumulate) {
+                   int out_f32, int accumulate, int ksplit) {
+  // grid = (N/16, ksplit); the ksplit CTAs of one 16-row output slab form a thread-block cluster and reduce their
+  // partial sums through distributed shared memory.
+  namespace cg = cooperative_groups;
   __shared__ float red[8][16][8 * NB + 1];
+  __shared__ float part[16 * 8 * NB];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t4 = lane & 3;
   const int n0 = blockIdx.x * 16;
+  const int ks = blockIdx.y;
+  // K range of this CTA in units of 32-element blocks
+  const int kblocks = K >> 5;
+  const int kb_lo = (int)((long long)kblocks * ks / ksplit) << 5, kb_hi = (int)((long long)kblocks * (ks + 1) / ksplit) << 5;
   float acc[NB][4];
 #pragma unroll
   for (int i = 0; i < NB; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
   const bf16* w0 = W + (long long)(n0 + g) * ldw + t4 * 8;
   const bf16* w1 = W + (long long)(n0 + g + 8) * ldw + t4 * 8;
-#pragma unroll 4
-  for (int kb = warp * 32; kb < K; kb += 256) {
+  // each warp owns a CONTIGUOUS k range so that its unrolled loads walk adjacent 64-byte segments of the same rows
+  const int wblocks = (kb_hi - kb_lo) >> 5;
+  const int wk_lo = kb_lo + ((wblocks * warp / 8) << 5), wk_hi = kb_lo + ((wblocks * (warp + 1) / 8) << 5);
+#pragma unroll 8
+  for (int kb = wk_lo; kb < wk_hi; kb += 32) {
     const uint4 wa = __ldg(reinterpret_cast<const uint4*>(w0 + kb));
     const uint4 wb = __ldg(reinterpret_cast<const uint4*>(w1 + kb));
     const uint32_t a_lo[4] = {wa.x, wb.x, wa.y, wb.y};
@@ -53,22 +65,65 @@ skinny_gemm_kernel(const bf16* __restrict__ x, long long ldx, const bf16* __rest
     red[warp][g + 8][nb * 8 + t4 * 2 + 1] = acc[nb][3];
   }
   __syncthreads();
-  for (int e = tid; e < 16 * 8 * NB; e += 256) {
+  constexpr int NOUT = 16 * 8 * NB;
+  for (int e = tid; e < NOUT; e += 256) {
+    const int f = e & 15, m = e >> 4;
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) sum += red[w][f][m];
+    part[e] = sum;
+  }
+  if (ksplit > 1) cg::this_cluster().sync();
+  else __syncthreads();
+  // distributed final reduction: cluster rank r finishes outputs e == r (mod ksplit)
+  for (int e = tid * ksplit + ks; e < NOUT; e += 256 * ksplit) {
     const int f = e & 15, m = e >> 4;
     if (m < M) {
-      float s = 0.f;
-#pragma unroll
-      for (int w = 0; w < 8; ++w) s += red[w][f][m];
-      if (bias) s += __bfloat162float(bias[n0 + f]);
+      float sum = 0.f;
+      if (ksplit > 1) {
+        cg::cluster_group cluster = cg::this_cluster();
+        for (int r = 0; r < ksplit; ++r) sum += cluster.map_shared_rank(part, r)[e];
+      } else {
+        sum = part[e];
+      }
+      if (bias) sum += __bfloat162float(bias[n0 + f]);
       if (out_f32) {
         float* yp = reinterpret_cast<float*>(y) + (long long)m * ldy + n0 + f;
-        *yp = accumulate ? *yp + s : s;
+        *yp = accumulate ? *yp + sum : sum;
       } else {
         bf16* yp = reinterpret_cast<bf16*>(y) + (long long)m * ldy + n0 + f;
-        *yp = __float2bfloat16(accumulate ? __bfloat162float(*yp) + s : s);
+        *yp = __float2bfloat16(accumulate ? __bfloat162float(*yp) + sum : sum);
       }
     }
   }
+  if (ksplit > 1) cg::this_cluster().sync();   // keep `part` alive until every peer has read it
+}
+
+template <int NB>
+int launch_skinny(const bf16* x, long long ldx, const bf16* W, long long ldw, const bf16* bias, void* y, long long ldy,
+                  int M, int N, int K, int out_f32, int accumulate, cudaStream_t stream) {
+  // split K across a cluster until there are enough CTAs in flight to cover HBM latency
+  int ksplit = 1;
+  const int slabs = N / 16;
+  while (ksplit < 8 && slabs * ksplit < 1184 && (K / 32) / (ksplit * 2) >= 8) ksplit *= 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(slabs, ksplit, 1);
+  cfg.blockDim = dim3(256, 1, 1);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = ksplit;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, skinny_gemm_kernel<NB>, x, ldx, W, ldw, bias, y, ldy, M, N, K, out_f32, accumulate, ksplit);
+  if (e != cudaSuccess) {
+    t1_set_error("t1_skinny_gemm: launch failed: %s", cudaGetErrorString(e));
+    return T1_ERR_CUDA;
+  }
+  return T1_OK;
 }
 
 // =============================================================================================
@@ -167,15 +222,18 @@ decode_attn_kernel(const bf16* __restrict__ q, long long ldq, const bf16* __rest
     const int sq = ok ? row / ratio : 0, hq = hk * ratio + (ok ? row % ratio : 0);
     cp_async_16(smem_u32(sQ + r * LDS + c * 8), q + (long long)sq * ldq + (long long)hq * HD + c * 8, ok);
   }
-  for (int e = tid; e < DA_KEYS * 16; e += 128) {
-    const int r = e >> 4, c = e & 15;
-    const bool ok = r < nvalid;
-    const long long slot = j0 + (ok ? r : 0);
-    cp_async_16(smem_u32(sK + r * LDS + c * 8), Kc + (slot * Hkv + hk) * HD + c * 8, ok);
-    cp_async_16(smem_u32(sV + r * LDS + c * 8), Vc + (slot * Hkv + hk) * HD + c * 8, ok);
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    for (int e = tid; e < 64 * 16; e += 128) {
+      const int r = half * 64 + (e >> 4), c = e & 15;
+      const bool ok = r < nvalid;
+      const long long slot = j0 + (ok ? r : 0);
+      cp_async_16(smem_u32(sK + r * LDS + c * 8), Kc + (slot * Hkv + hk) * HD + c * 8, ok);
+      cp_async_16(smem_u32(sV + r * LDS + c * 8), Vc + (slot * Hkv + hk) * HD + c * 8, ok);
+    }
+    cp_async_commit();
   }
-  cp_async_commit();
-  cp_async_wait<0>();
+  cp_async_wait<1>();
   __syncthreads();
 
   uint32_t qf[8][4];
@@ -191,6 +249,10 @@ decode_attn_kernel(const bf16* __restrict__ q, long long ldq, const bf16* __rest
 #pragma unroll 1
   for (int kt = 0; kt < DA_KEYS / 64; ++kt) {
     if (kt * 64 >= nvalid) break;
+    if (kt == 1) {
+      cp_async_wait<0>();
+      __syncthreads();
+    }
     const bf16* kb = sK + kt * 64 * LDS;
     const bf16* vb = sV + kt * 64 * LDS;
     float s[8][4];
@@ -256,6 +318,7 @@ decode_attn_kernel(const bf16* __restrict__ q, long long ldq, const bf16* __rest
       }
     }
   }
+  cp_async_wait<0>();
   l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
   l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
   l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
@@ -276,7 +339,8 @@ decode_attn_kernel(const bf16* __restrict__ q, long long ldq, const bf16* __rest
   }
 }
 
-// combine partials: one CTA (128 threads = head dim) per (seq, q head)
+// combine partials: one CTA (128 threads = head dim) per (seq, q head). Only the prefix chunks and the sequence's own
+// completion chunks are visited; loads are unconditional (select on l > 0) so they pipeline.
 __global__ void __launch_bounds__(128)
 decode_attn_combine_kernel(const float* __restrict__ ws_o, const float* __restrict__ ws_ml, int n_chunks,
                            int n_prefix_chunks, int chunks_per_seq, int Hq, int Hkv, int rows_pad,
@@ -285,23 +349,30 @@ decode_attn_combine_kernel(const float* __restrict__ ws_o, const float* __restri
   const int ratio = Hq / Hkv, hk = hq / ratio;
   const int row = b * ratio + (hq - hk * ratio);
   const int d = threadIdx.x;
+  const int nc = n_prefix_chunks + chunks_per_seq;
+  const long long stride = (long long)Hkv * rows_pad;
+  const long long base = (long long)hk * rows_pad + row;
+  auto chunk_of = [&](int i) { return i < n_prefix_chunks ? i : n_prefix_chunks + b * chunks_per_seq + (i - n_prefix_chunks); };
   float M = -INFINITY;
-  for (int c = 0; c < n_chunks; ++c) {
-    if (c >= n_prefix_chunks && (c - n_prefix_chunks) / chunks_per_seq != b) continue;
-    M = fmaxf(M, ws_ml[(((long long)c * Hkv + hk) * rows_pad + row) * 2]);
+#pragma unroll 8
+  for (int i = 0; i < nc; ++i) {
+    const long long r = (long long)chunk_of(i) * stride + base;
+    const float2 ml = *reinterpret_cast<const float2*>(ws_ml + r * 2);
+    M = fmaxf(M, ml.y > 0.f ? ml.x : -INFINITY);
   }
   float L = 0.f, acc = 0.f;
-  for (int c = 0; c < n_chunks; ++c) {
-    if (c >= n_prefix_chunks && (c - n_prefix_chunks) / chunks_per_seq != b) continue;
-    const long long r = ((long long)c * Hkv + hk) * rows_pad + row;
-    const float m = ws_ml[r * 2], l = ws_ml[r * 2 + 1];
-    if (l > 0.f) {
-      const float w = exp2f(m - M);
-      L += w * l;
-      acc += w * ws_o[r * 128 + d];
-    }
+#pragma unroll 8
+  for (int i = 0; i < nc; ++i) {
+    const long long r = (long long)chunk_of(i) * stride + base;
+    const float2 ml = *reinterpret_cast<const float2*>(ws_ml + r * 2);
+    const float o = ws_o[r * 128 + d];
+    const bool ok = ml.y > 0.f;
+    const float w = ok ? exp2f(ml.x - M) : 0.f;
+    L += ok ? w * ml.y : 0.f;
+    acc += ok ? w * o : 0.f;
   }
   out[(long long)b * ldo + hq * 128 + d] = __float2bfloat16(L > 0.f ? acc / L : 0.f);
+  (void)n_chunks;
 }
 
 // =============================================================================================
@@ -332,7 +403,8 @@ __device__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
 
 __global__ void __launch_bounds__(1024, 1)
 sample_kernel(const float* __restrict__ logits, long long ld, int V, float temperature, int top_k,
-              unsigned long long seed, const int* __restrict__ step_ptr, int step_offset, const int* __restrict__ eos_ids,
+              unsigned long long seed_in, const unsigned long long* __restrict__ seed_ptr,
+              const int* __restrict__ step_ptr, int step_offset, const int* __restrict__ eos_ids,
               int n_eos, int pad_id, int* __restrict__ finished, int* __restrict__ out_ids, int out_ld,
               int* __restrict__ next_ids, float* __restrict__ out_u) {
   __shared__ unsigned int hist[2048];
@@ -343,6 +415,7 @@ sample_kernel(const float* __restrict__ logits, long long ld, int V, float tempe
   __shared__ int s_tok;
   const int b = blockIdx.x, tid = threadIdx.x;
   const int step = (step_ptr ? *step_ptr : 0) + step_offset;
+  const unsigned long long seed = seed_ptr ? *seed_ptr : seed_in;  // device-resident seed keeps CUDA graphs reusable
   const float* x = logits + (long long)b * ld;
   const bool greedy = !(temperature > 0.f);
   const float inv_t = greedy ? 1.f : 1.f / temperature;
@@ -496,11 +569,12 @@ extern "C" int t1_skinny_gemm(const void* x, long long ldx, const void* W, long 
   const bf16* xb = (const bf16*)x;
   const bf16* wb = (const bf16*)W;
   const bf16* bb = (const bf16*)bias;
-  const int grid = N / 16;
-  if (M <= 8) skinny_gemm_kernel<1><<<grid, 256, 0, stream>>>(xb, ldx, wb, ldw, bb, y, ldy, M, N, K, out_f32, accumulate);
-  else if (M <= 16) skinny_gemm_kernel<2><<<grid, 256, 0, stream>>>(xb, ldx, wb, ldw, bb, y, ldy, M, N, K, out_f32, accumulate);
-  else if (M <= 32) skinny_gemm_kernel<4><<<grid, 256, 0, stream>>>(xb, ldx, wb, ldw, bb, y, ldy, M, N, K, out_f32, accumulate);
-  else skinny_gemm_kernel<8><<<grid, 256, 0, stream>>>(xb, ldx, wb, ldw, bb, y, ldy, M, N, K, out_f32, accumulate);
+  int rc;
+  if (M <= 8) rc = launch_skinny<1>(xb, ldx, wb, ldw, bb, y, ldy, M, N, K, out_f32, accumulate, stream);
+  else if (M <= 16) rc = launch_skinny<2>(xb, ldx, wb, ldw, bb, y, ldy, M, N, K, out_f32, accumulate, stream);
+  else if (M <= 32) rc = launch_skinny<4>(xb, ldx, wb, ldw, bb, y, ldy, M, N, K, out_f32, accumulate, stream);
+  else rc = launch_skinny<8>(xb, ldx, wb, ldw, bb, y, ldy, M, N, K, out_f32, accumulate, stream);
+  if (rc) return rc;
   T1_CUDA_LAUNCH_CHECK("t1_skinny_gemm");
   return T1_OK;
 }
@@ -547,11 +621,11 @@ extern "C" int t1_decode_attn(const void* q, long long ldq, const void* Kc, cons
 }
 
 extern "C" int t1_sample(const float* logits, long long ld, int B, int V, float temperature, int top_k,
-                         unsigned long long seed, const int* step_ptr, int step_offset, const int* eos_ids, int n_eos,
-                         int pad_id, int* finished, int* out_ids, int out_ld, int* next_ids, float* out_u,
-                         cudaStream_t stream) {
+                         unsigned long long seed, const unsigned long long* seed_ptr, const int* step_ptr,
+                         int step_offset, const int* eos_ids, int n_eos, int pad_id, int* finished, int* out_ids,
+                         int out_ld, int* next_ids, float* out_u, cudaStream_t stream) {
   T1_CHECK_ARG(B > 0 && V > 0 && logits, "t1_sample: bad arguments");
-  sample_kernel<<<B, 1024, 0, stream>>>(logits, ld, V, temperature, top_k, seed, step_ptr, step_offset, eos_ids, n_eos,
+  sample_kernel<<<B, 1024, 0, stream>>>(logits, ld, V, temperature, top_k, seed, seed_ptr, step_ptr, step_offset, eos_ids, n_eos,
                                         pad_id, finished, out_ids, out_ld, next_ids, out_u);
   T1_CUDA_LAUNCH_CHECK("t1_sample");
   return T1_OK;

@@ -289,7 +289,7 @@ class Engine:
             step=torch.zeros(1, device=d, dtype=I32), next_ids=torch.zeros(G, device=d, dtype=I32),
             finished=torch.zeros(G, device=d, dtype=I32), out_ids=torch.zeros((G, C), device=d, dtype=I32),
             cos=torch.empty((C, cfg.head_dim // 2), device=d, dtype=F32), sin=torch.empty((C, cfg.head_dim // 2), device=d, dtype=F32),
-            eos=self._i32(list(cfg.stop_token_ids)), seed=torch.zeros(1, dtype=torch.int64), graph=None, launches_per_step=0,
+            eos=self._i32(list(cfg.stop_token_ids)), seed_dev=torch.zeros(1, device=d, dtype=torch.int64), graph=None, launches_per_step=0,
         )
         self._decode_cache[key] = st
         return st
@@ -319,7 +319,7 @@ class Engine:
         ops.rmsnorm(x, self.p("model.norm.weight"), eps, delta=down, out=st["hN"])
         ops.skinny_gemm(st["hN"], self.lm_head(), out=st["logits"])
         call("t1_sample", ptr(st["logits"]), st["logits"].stride(0), G, cfg.vocab_size, float(temperature), int(top_k),
-             int(seed), ptr(st["step"]), 1, ptr(st["eos"]), len(cfg.stop_token_ids), cfg.pad_token_id, ptr(st["finished"]),
+             0, ptr(st["seed_dev"]), ptr(st["step"]), 1, ptr(st["eos"]), len(cfg.stop_token_ids), cfg.pad_token_id, ptr(st["finished"]),
              ptr(st["out_ids"]), st["out_ids"].stride(0), ptr(st["next_ids"]), 0, s)
         call("t1_incr", ptr(st["step"]), 1, s)
 
@@ -350,12 +350,13 @@ class Engine:
         st["finished"].zero_()
         st["out_ids"].fill_(cfg.pad_token_id)
         # first token: G independent draws from the shared last-prompt-position distribution (row stride 0)
-        call("t1_sample", ptr(logits0), 0, G, cfg.vocab_size, float(temperature), int(top_k), int(seed), 0, 0,
+        st["seed_dev"].fill_(int(seed))
+        call("t1_sample", ptr(logits0), 0, G, cfg.vocab_size, float(temperature), int(top_k), 0, ptr(st["seed_dev"]), 0, 0,
              ptr(st["eos"]), len(cfg.stop_token_ids), cfg.pad_token_id, ptr(st["finished"]), ptr(st["out_ids"]),
              st["out_ids"].stride(0), ptr(st["next_ids"]), 0, stream_ptr())
         n_steps = C - 1
         if n_steps > 0:
-            gkey = (float(temperature), int(top_k), int(seed))
+            gkey = (float(temperature), int(top_k))     # the seed lives in device memory: graphs are seed-independent
             if use_graph:
                 if st["graph"] is None or st.get("gkey") != gkey:
                     # warm-up step outside capture (sets func attributes), then rewind the state it touched

@@ -61,7 +61,7 @@ _SIGNATURES: dict[str, list] = {
     "t1_skinny_gemm": [vp, i64, vp, i64, vp, vp, i64, i32, i32, i32, i32, i32, vp],
     "t1_decode_rope_append": [vp, i64, i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, i32, vp],
     "t1_decode_attn": [vp, i64, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, i64, f32, vp],
-    "t1_sample": [vp, i64, i32, i32, f32, i32, u64, vp, i32, vp, i32, i32, vp, vp, i32, vp, vp, vp],
+    "t1_sample": [vp, i64, i32, i32, f32, i32, u64, vp, vp, i32, vp, i32, i32, vp, vp, i32, vp, vp, vp],
     "t1_incr": [vp, i32, vp],
     # optim.cu
     "t1_sumsq_bf16": [vp, i64, vp, vp],
@@ -120,8 +120,45 @@ def check(rc: int, what: str = "") -> None:
         raise Timer1Error(f"{what} failed (rc={rc}): {last_error()}")
 
 
+class CallProfiler:
+    """Optional CUDA-event timing of every C-ABI call by entry-point name (tools / bench --kernel-times)."""
+
+    def __init__(self):
+        self.enabled = False
+        self.records: list = []
+
+    def start(self):
+        self.enabled, self.records = True, []
+
+    def stop(self):
+        self.enabled = False
+
+    def summary(self) -> dict:
+        import torch
+
+        torch.cuda.synchronize()
+        out: dict = {}
+        for name, e0, e1 in self.records:
+            d = out.setdefault(name, [0, 0.0])
+            d[0] += 1
+            d[1] += e0.elapsed_time(e1)
+        return dict(sorted(out.items(), key=lambda kv: -kv[1][1]))
+
+
+CALL_PROFILER = CallProfiler()
+
+
 def call(name: str, *args) -> None:
     fn = getattr(load(), name)
+    if CALL_PROFILER.enabled:
+        import torch
+
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(fn(*args), name)
+        e1.record()
+        CALL_PROFILER.records.append((name, e0, e1))
+        return
     check(fn(*args), name)
 
 

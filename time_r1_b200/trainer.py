@@ -1,0 +1,513 @@
+"""Drop-in `TimeR1_Trainer` — same constructor, reward-function protocol, metric names and train()/save_model()/log()
+surface as src/time_r1/rl/timer1_trainer.py:100-857, driven by the B200 engine instead of HF Trainer + DeepSpeed.
+
+What is mirrored (reference file:line):
+  * ctor kwargs                                   timer1_trainer.py:184-206
+  * ε_low = ε_high = 0.2 regardless of args       :388-393
+  * one prompt-group per micro-step (bs forced 1) :548-551
+  * reward protocol f(prompts=, completions=, **dataset columns repeated G times) -> list[float]   :685-698
+  * metric keys completion_length, rewards/<fn>, reward, reward_std, kl, generation_entropy  :740-777, log() :784-793
+  * loss / grad-accum scaling, clip 1.0, AdamW, linear LR decay    HF trainer.py:1927,2493,1760
+  * callbacks: on_train_begin / on_step_end / on_epoch_end(control.should_training_stop) / on_log / on_train_end
+    (main.py:497-539), `.state.max_steps`, `.args`, `.get_train_dataloader()` (main.py:599-618)
+What differs by design: the model never lives in torch modules — `model` is a checkpoint directory (HF safetensors,
+released-checkpoint names), a preset name ("random:qwen2.5-vl-7b", "random:toy") or a (ModelConfig, ModelWeights) pair.
+Video decoding / HF processor (timer1_trainer.py:518-556) is an injection point (`vision_processor`); dataset rows that
+already carry `input_ids` + `pixel_values_videos` + `video_grid_thw` (the `_ft` variant's pre-decoded layout) skip it.
+"""
+from __future__ import annotations
+
+import json
+import math
+import os
+import random
+from collections import defaultdict
+from dataclasses import asdict, dataclass, field
+from typing import Any, Callable, Optional, Sequence, Union
+
+import numpy as np
+
+from .config import PRESETS, ModelConfig, RunConfig, from_hf_config
+
+SYSTEM_PROMPT = "You are a video analysis expert."
+QUESTION_TEMPLATE_TG_v1 = (
+    'To accurately pinpoint the event "[EVENT]" in the video, determine the precise time period of the event.\n\n'
+    "Output your thought process within the <think> </think> tags, including analysis with either specific time "
+    "ranges (xx.xx to xx.xx) in <timestep> </timestep> tags.\n\n"
+    'Then, provide the start and end times (in seconds, precise to two decimal places) in the format "start time to '
+    'end time" within the <answer> </answer> tags. For example: "12.54 to 17.83".'
+)
+
+
+@dataclass
+class GRPOArguments:
+    """Union of the TrainingArguments / GRPOConfig / MY_GRPOConfig fields the reference consumes (SURVEY §5 config row;
+    flags of scripts/posttrain/train_rl.sh:18-45).  Any object with these attributes (e.g. a real trl GRPOConfig) works."""
+    output_dir: str = "./logs/timer1"
+    num_generations: int = 8
+    max_prompt_length: Optional[int] = 8192          # stored, never enforced (timer1_trainer.py:364)
+    max_completion_length: int = 200
+    temperature: float = 0.9                          # trl 0.17 default; scripts pass 1.0
+    beta: float = 0.04
+    learning_rate: float = 1e-6
+    adam_beta1: float = 0.9
+    adam_beta2: float = 0.999
+    adam_epsilon: float = 1e-8
+    weight_decay: float = 0.0
+    max_grad_norm: float = 1.0
+    per_device_train_batch_size: int = 1
+    gradient_accumulation_steps: int = 1
+    num_train_epochs: float = 1.0
+    max_steps: int = -1
+    logging_steps: int = 1
+    save_steps: int = 500
+    save_strategy: str = "steps"
+    save_only_model: bool = False
+    seed: int = 42
+    data_seed: Optional[int] = None
+    bf16: bool = True
+    gradient_checkpointing: bool = True
+    fix_vit: bool = False
+    slide_window: bool = False
+    max_window_layers: int = 2
+    sliding_window_length: int = 4096
+    prompt_type: str = "v1"
+    use_grpo: bool = False
+    top_k: int = 50                                   # HF 4.51.1 GenerationConfig default
+    resume_from_checkpoint: Optional[str] = None
+    push_to_hub: bool = False
+    report_to: str = "none"
+    run_name: Optional[str] = None
+    logging_dir: Optional[str] = None
+    deepspeed: Optional[str] = None                   # accepted and ignored: sharding is built in
+    model_init_kwargs: Optional[dict] = None
+
+
+class TrainerState:
+    def __init__(self):
+        self.global_step = 0
+        self.epoch = 0.0
+        self.max_steps = 0
+        self.is_world_process_zero = True
+        self.log_history: list = []
+
+
+class TrainerControl:
+    def __init__(self):
+        self.should_training_stop = False
+        self.should_save = False
+        self.should_log = False
+
+
+class TrainerCallback:
+    """Same hook names as transformers.TrainerCallback; every hook is optional."""
+
+    def on_train_begin(self, args, state, control, **kw): ...
+    def on_step_end(self, args, state, control, **kw): ...
+    def on_epoch_end(self, args, state, control, **kw): ...
+    def on_log(self, args, state, control, **kw): ...
+    def on_train_end(self, args, state, control, **kw): ...
+
+
+def _is_conversational(example: dict) -> bool:
+    p = example.get("prompt")
+    return isinstance(p, list) and len(p) > 0 and isinstance(p[0], dict) and "role" in p[0]
+
+
+class TimeR1_Trainer:
+    def __init__(
+        self,
+        model: Union[str, tuple],
+        reward_funcs: Union[Callable, Sequence[Callable]],
+        metric_funcs: Union[Callable, Sequence[Callable], None] = None,
+        args: Any = None,
+        train_dataset: Optional[Sequence[dict]] = None,
+        eval_dataset: Optional[Any] = None,
+        processing_class: Optional[Any] = None,
+        reward_processing_classes: Optional[Any] = None,
+        callbacks: Optional[list] = None,
+        optimizers: tuple = (None, None),
+        peft_config: Optional[Any] = None,
+        max_pixels: Optional[int] = 12845056,
+        min_pixels: Optional[int] = 3136,
+        attn_implementation: str = "flash_attention_2",
+        vision_processor: Optional[Callable[[dict], dict]] = None,
+    ):
+        import torch
+
+        from . import engine as _engine, lib, weights as _weights
+
+        if peft_config is not None:
+            raise NotImplementedError("LoRA/peft is never enabled by the reference scripts and is not built (SURVEY §2.2 T8)")
+        if optimizers != (None, None):
+            raise NotImplementedError("custom optimizers are not supported: the sharded AdamW kernel is built in")
+        self.args = args if args is not None else GRPOArguments()
+        a = self.args
+        if not isinstance(reward_funcs, (list, tuple)):
+            reward_funcs = [reward_funcs]
+        for rf in reward_funcs:
+            if isinstance(rf, str):
+                raise NotImplementedError("reward models given as model ids are unused by the reference scripts (timer1_trainer.py:324-328)")
+        self.reward_funcs = list(reward_funcs)
+        self.metric_funcs = list(metric_funcs) if metric_funcs else []
+        self.train_dataset, self.eval_dataset = train_dataset, eval_dataset
+        self.processing_class = processing_class
+        self.vision_processor = vision_processor
+        self.callbacks = list(callbacks or [])
+        self.max_pixels, self.min_pixels = max_pixels, min_pixels
+        self.num_generations = a.num_generations
+        self.max_completion_length = a.max_completion_length
+        self.max_prompt_length = getattr(a, "max_prompt_length", None)
+        self.beta = a.beta
+        self.use_grpo = getattr(a, "use_grpo", False)
+        self.prompt_type = getattr(a, "prompt_type", "v1")
+        self.epsilon_low, self.epsilon_high = 0.2, 0.2       # hard-coded in the reference (:388-393)
+        self._metrics: dict = defaultdict(list)
+        self.state, self.control = TrainerState(), TrainerControl()
+
+        # ---- distributed plumbing (one process per GPU, NCCL) ----
+        import torch.distributed as dist
+
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise RuntimeError("TimeR1_Trainer (time_r1_b200) needs a CUDA device: there is no CPU fallback")
+        torch.cuda.set_device(local)
+        self.device = torch.device("cuda", local)
+        pg = None
+        if self.world > 1:
+            if not dist.is_initialized():
+                dist.init_process_group("nccl", device_id=self.device)
+            pg = dist.group.WORLD
+        self.state.is_world_process_zero = self.rank == 0
+        lib.load()
+
+        # ---- model ----
+        if isinstance(model, tuple):
+            self.model_cfg, self.weights = model
+        elif isinstance(model, str) and model.startswith("random:"):
+            self.model_cfg = PRESETS[model.split(":", 1)[1]]()
+            self.weights = _weights.ModelWeights(self.model_cfg, self.device, world_size=self.world)
+            self.weights.init_random(seed=getattr(a, "seed", 42))
+        elif isinstance(model, str):
+            self.model_cfg, self.weights = load_checkpoint(model, self.device, self.world)
+            if self.processing_class is None:
+                try:
+                    from transformers import AutoProcessor
+
+                    self.processing_class = AutoProcessor.from_pretrained(model)
+                except Exception:
+                    self.processing_class = None
+        else:
+            raise TypeError("model must be a checkpoint path, 'random:<preset>' or a (ModelConfig, ModelWeights) pair")
+        self.run = RunConfig(
+            num_generations=a.num_generations, max_completion_length=a.max_completion_length,
+            temperature=a.temperature, top_k=getattr(a, "top_k", 50), beta=a.beta, epsilon_low=0.2, epsilon_high=0.2,
+            use_grpo=self.use_grpo, learning_rate=a.learning_rate, adam_beta1=getattr(a, "adam_beta1", 0.9),
+            adam_beta2=getattr(a, "adam_beta2", 0.999), adam_eps=getattr(a, "adam_epsilon", 1e-8),
+            weight_decay=getattr(a, "weight_decay", 0.0), max_grad_norm=getattr(a, "max_grad_norm", 1.0),
+            gradient_accumulation_steps=a.gradient_accumulation_steps, fix_vit=True, seed=getattr(a, "seed", 42))
+        if not getattr(a, "fix_vit", False):
+            # every reference script passes --fix_vit true; ViT-block gradients are not built
+            print("[time_r1_b200] note: fix_vit=False requested; ViT blocks stay frozen (only merger + LLM train)")
+        self.engine = _engine.Engine(self.model_cfg, self.weights, self.run, with_ref=a.beta != 0.0, rank=self.rank,
+                                     world_size=self.world, process_group=pg)
+        self.model = self.engine
+        self.eos_token_id = getattr(getattr(self.processing_class, "tokenizer", self.processing_class), "eos_token_id", None) \
+            or self.model_cfg.eos_token_id
+
+    # ------------------------------------------------------------------ data
+    def get_train_dataloader(self) -> list:
+        """This rank's micro-batches for one epoch: lists of `per_device_train_batch_size` (=1) examples."""
+        n = len(self.train_dataset)
+        idx = list(range(n))
+        rng = random.Random(getattr(self.args, "data_seed", None) or getattr(self.args, "seed", 42))
+        rng.shuffle(idx)
+        idx = idx[self.rank::self.world]
+        return [[self.train_dataset[i]] for i in idx]
+
+    def make_conversation_video(self, example: dict) -> list:
+        text = QUESTION_TEMPLATE_TG_v1.replace("[EVENT]", example["problem"])
+        return [{"role": "user", "content": [
+            {"type": "text", "text": text},
+            {"type": "video", "video": example["video_path"], "video_start": example.get("video_start"),
+             "video_end": example.get("video_end"), "total_pixels": 3584 * 28 * 28, "min_pixels": 16 * 28 * 28}]}]
+
+    def _prompt_from_example(self, example: dict):
+        import torch
+
+        from .engine import Prompt
+
+        if "input_ids" not in example:
+            if self.vision_processor is None:
+                raise NotImplementedError(
+                    "raw video decoding + HF processor (timer1_trainer.py:518-556) is a host-side stage outside this "
+                    "engine; pass vision_processor=callable(example) -> {input_ids, pixel_values_videos, video_grid_thw, "
+                    "second_per_grid_ts} or pre-processed dataset rows")
+            example = {**example, **self.vision_processor(example)}
+        pix = example["pixel_values_videos"]
+        pix = pix if isinstance(pix, torch.Tensor) else torch.as_tensor(np.asarray(pix))
+        pix = pix.to(device=self.device, dtype=torch.float32, non_blocking=True).contiguous()
+        grid = [tuple(int(v) for v in g) for g in np.asarray(example["video_grid_thw"]).reshape(-1, 3)]
+        return Prompt(input_ids=np.asarray(example["input_ids"]).reshape(-1), pixel_values=pix, grid_thw=grid,
+                      second_per_grid_ts=example.get("second_per_grid_ts"))
+
+    def _decode(self, ids: np.ndarray) -> list:
+        pc = self.processing_class
+        if pc is None:
+            raise RuntimeError("a processing_class with batch_decode() is required to turn completions into text")
+        return pc.batch_decode(ids, skip_special_tokens=True)
+
+    # ------------------------------------------------------------------ one micro-step
+    def compute_loss(self, model, inputs, return_outputs: bool = False, num_items_in_batch=None):
+        """rollout + scoring + rewards + advantages + loss + BACKWARD for one prompt group (the backward the reference
+        runs in HF Trainer.training_step is part of this call). Returns the (grad-accum-scaled) loss as a 1-element
+        device tensor."""
+        if return_outputs:
+            raise ValueError("The GRPOTrainer does not support returning outputs")
+        if len(inputs) != 1:
+            raise ValueError("per_device_train_batch_size must be 1 (the reference only consumes inputs[0], timer1_trainer.py:548-551)")
+        example = inputs[0]
+        G = self.num_generations
+        prompt = self._prompt_from_example(example)
+        prompts = [self.make_conversation_video(example) if "problem" in example and "video_path" in example else example.get("prompt")] * G
+
+        def reward_fn(comp_ids: np.ndarray) -> np.ndarray:
+            completions = self._decode(comp_ids)
+            if _is_conversational(example):
+                completions = [[{"role": "assistant", "content": c}] for c in completions]
+            cols = {k: [example[k]] * G for k in example if k not in ("prompt", "completion", "input_ids", "pixel_values_videos", "video_grid_thw", "second_per_grid_ts")}
+            out = np.zeros((G, len(self.reward_funcs)), np.float32)
+            for i, rf in enumerate(self.reward_funcs):
+                out[:, i] = np.asarray(rf(prompts=prompts, completions=completions, **cols), np.float32)
+            self._last_completions = completions
+            return out
+
+        accum = self.args.gradient_accumulation_steps
+        seed = self.run.seed + 7919 * (self.state.global_step * accum + self._micro) * self.world + self.rank
+        out = self.engine.grpo_step(prompt, reward_fn, seed=seed, loss_scale=1.0 / accum)
+        self._log_metrics(out)
+        return out["loss"]
+
+    def _log_metrics(self, out: dict):
+        import torch
+
+        stats = out["stats"]
+        rpf = out["rewards_per_func"].mean(0)
+        vec = torch.cat([stats[3:4], rpf, out["rewards"].mean().reshape(1), out["reward_std"].mean().reshape(1),
+                         stats[1:2], stats[2:3], stats[5:7]])
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.all_reduce(vec, op=dist.ReduceOp.AVG)      # one fused all-reduce replaces 6 gather_for_metrics (:740-777)
+        v = vec.tolist()
+        n = len(self.reward_funcs)
+        self._metrics["completion_length"].append(v[0])
+        for i, rf in enumerate(self.reward_funcs):
+            self._metrics[f"rewards/{rf.__name__}"].append(v[1 + i])
+        self._metrics["reward"].append(v[1 + n])
+        self._metrics["reward_std"].append(v[2 + n])
+        if self.beta != 0.0:
+            self._metrics["kl"].append(v[3 + n])
+        self._metrics["generation_entropy"].append(v[4 + n])
+        self._extra_metrics(v[5 + n], v[6 + n])
+
+    def _extra_metrics(self, clip_low: float, clip_high: float):
+        pass
+
+    def log(self, logs: dict, start_time: Optional[float] = None) -> None:
+        metrics = {k: sum(v) / len(v) for k, v in self._metrics.items()}
+        logs = {**logs, **metrics, "step": self.state.global_step}
+        self.state.log_history.append(logs)
+        if self.state.is_world_process_zero:
+            print(json.dumps({k: (round(v, 6) if isinstance(v, float) else v) for k, v in logs.items()}))
+        for cb in self.callbacks:
+            cb.on_log(self.args, self.state, self.control, logs=logs, trainer=self)
+        self._metrics.clear()
+
+    # ------------------------------------------------------------------ loop
+    def train(self, resume_from_checkpoint: Optional[str] = None):
+        a = self.args
+        loader = self.get_train_dataloader()
+        accum = a.gradient_accumulation_steps
+        steps_per_epoch = max(1, math.ceil(len(loader) / accum))
+        if getattr(a, "max_steps", -1) and a.max_steps > 0:
+            max_steps = a.max_steps
+        else:
+            max_steps = math.ceil(a.num_train_epochs * len(loader) / accum)
+        if self.state.max_steps <= 0:
+            self.state.max_steps = max_steps
+        start_step = 0
+        if resume_from_checkpoint:
+            start_step = self._load_checkpoint(resume_from_checkpoint)
+            self.state.global_step = start_step
+        for cb in self.callbacks:
+            cb.on_train_begin(a, self.state, self.control, trainer=self)
+        total = self.state.max_steps if getattr(a, "max_steps", -1) <= 0 else a.max_steps
+        epoch = 0
+        losses = []
+        while self.state.global_step < total and not self.control.should_training_stop:
+            loader = self.get_train_dataloader() if epoch > 0 else loader
+            for i in range(0, len(loader) - len(loader) % accum or len(loader), accum):
+                micro = loader[i:i + accum]
+                for self._micro, inputs in enumerate(micro):
+                    losses.append(self.compute_loss(self.engine, inputs))
+                done = self.state.global_step - start_step
+                lr = a.learning_rate * max(0.0, 1.0 - done / max(1, total - start_step))   # linear decay, no warm-up
+                gnorm = self.engine.optimizer_step(lr=lr)
+                self.state.global_step += 1
+                self.state.epoch = epoch + min(1.0, (i + accum) / max(1, len(loader)))
+                if self.state.global_step % max(1, a.logging_steps) == 0:
+                    loss_val = float(sum(l.item() for l in losses))
+                    losses = []
+                    self.log({"loss": loss_val, "grad_norm": float(gnorm.item()), "learning_rate": lr, "epoch": self.state.epoch})
+                for cb in self.callbacks:
+                    cb.on_step_end(a, self.state, self.control, trainer=self)
+                if getattr(a, "save_strategy", "steps") == "steps" and a.save_steps and self.state.global_step % a.save_steps == 0:
+                    self._save_checkpoint()
+                if self.state.global_step >= total or self.control.should_training_stop:
+                    break
+            epoch += 1
+            self.state.epoch = float(epoch)
+            for cb in self.callbacks:
+                cb.on_epoch_end(a, self.state, self.control, trainer=self)
+            if getattr(a, "save_strategy", "steps") == "epoch":
+                self._save_checkpoint()
+        for cb in self.callbacks:
+            cb.on_train_end(a, self.state, self.control, trainer=self)
+        return self.state
+
+    _micro = 0
+
+    # ------------------------------------------------------------------ checkpoints (HF-format export)
+    def save_model(self, output_dir: Optional[str] = None):
+        output_dir = output_dir or self.args.output_dir
+        if not self.state.is_world_process_zero:
+            return
+        os.makedirs(output_dir, exist_ok=True)
+        save_checkpoint_dir(output_dir, self.model_cfg, self.weights)
+
+    def _save_checkpoint(self):
+        import torch
+
+        d = os.path.join(self.args.output_dir, f"checkpoint-{self.state.global_step}")
+        self.save_model(d)
+        if self.state.is_world_process_zero:
+            with open(os.path.join(d, "trainer_state.json"), "w") as f:
+                json.dump({"global_step": self.state.global_step, "epoch": self.state.epoch, "max_steps": self.state.max_steps,
+                           "log_history": self.state.log_history}, f)
+        if not getattr(self.args, "save_only_model", False):
+            os.makedirs(d, exist_ok=True)
+            torch.save({"master": self.engine.master, "m": self.engine.adam_m, "v": self.engine.adam_v,
+                        "opt_step": self.engine.opt_step, "shard_lo": self.engine.shard_lo},
+                       os.path.join(d, f"optimizer_rank{self.rank}.pt"))
+
+    def _load_checkpoint(self, d: str) -> int:
+        import torch
+
+        cfg, w = load_checkpoint(d, self.device, self.world)
+        self.weights.train.buf.copy_(w.train.buf)
+        self.weights.frozen.buf.copy_(w.frozen.buf)
+        opt = os.path.join(d, f"optimizer_rank{self.rank}.pt")
+        if os.path.exists(opt):
+            s = torch.load(opt, map_location=self.device)
+            self.engine.master.copy_(s["master"]); self.engine.adam_m.copy_(s["m"]); self.engine.adam_v.copy_(s["v"])
+            self.engine.opt_step = s["opt_step"]
+        else:
+            from . import ops
+
+            ops.bf16_to_f32(self.weights.train.buf[self.engine.shard_lo:self.engine.shard_lo + self.engine.shard], self.engine.master)
+        st = os.path.join(d, "trainer_state.json")
+        return json.load(open(st)).get("global_step", 0) if os.path.exists(st) else 0
+
+    def push_to_hub(self, *a, **k):
+        raise NotImplementedError("no network access in this build; use save_model() and upload the directory")
+
+
+class TimeR1_Trainer_ft(TimeR1_Trainer):
+    """Fine-tune variant (src/time_r1/rl/timer1_trainer_ft.py): dataset rows carry pre-decoded tensors
+    (`preprocessed_path`/video_inputs.pt, :551-556) — here rows carry the processed tensors directly — metric functions are
+    logged, never added to the reward (:670-691), and clip-ratio metrics are reported (:820-842)."""
+
+    def _extra_metrics(self, clip_low: float, clip_high: float):
+        self._metrics["clip_ratio/low_mean"].append(clip_low)
+        self._metrics["clip_ratio/high_mean"].append(clip_high)
+        self._metrics["clip_ratio/region_mean"].append(clip_low + clip_high)
+        comps = getattr(self, "_last_completions", None)
+        if comps is not None:
+            for mf in self.metric_funcs:
+                vals = mf(completions=comps)
+                self._metrics[f"metrics/{mf.__name__}"].append(float(np.mean(vals)))
+
+
+# ------------------------------------------------------------------------------------------------
+# HF-format checkpoint IO (released-checkpoint tensor names; evaluate.py / vLLM can load the export)
+# ------------------------------------------------------------------------------------------------
+def hf_config_dict(cfg: ModelConfig) -> dict:
+    q25 = cfg.is_q25
+    vision = {"depth": cfg.vit_depth, "hidden_size": cfg.vit_hidden, "num_heads": cfg.vit_heads, "patch_size": cfg.patch_size,
+              "temporal_patch_size": cfg.temporal_patch_size, "spatial_merge_size": cfg.spatial_merge_size,
+              "in_channels": cfg.in_channels, "out_hidden_size": cfg.hidden_size}
+    if q25:
+        vision.update(intermediate_size=cfg.vit_intermediate, window_size=cfg.window_size,
+                      fullatt_block_indexes=list(cfg.fullatt_block_indexes), tokens_per_second=cfg.tokens_per_second)
+    else:
+        vision.update(embed_dim=cfg.vit_hidden, mlp_ratio=cfg.vit_intermediate / cfg.vit_hidden)
+    return {
+        "model_type": "qwen2_5_vl" if q25 else "qwen2_vl",
+        "architectures": ["Qwen2_5_VLForConditionalGeneration" if q25 else "Qwen2VLForConditionalGeneration"],
+        "hidden_size": cfg.hidden_size, "intermediate_size": cfg.intermediate_size, "num_hidden_layers": cfg.num_hidden_layers,
+        "num_attention_heads": cfg.num_attention_heads, "num_key_value_heads": cfg.num_key_value_heads,
+        "vocab_size": cfg.vocab_size, "rms_norm_eps": cfg.rms_norm_eps, "rope_theta": cfg.rope_theta,
+        "rope_scaling": {"type": "mrope", "mrope_section": list(cfg.mrope_section)},
+        "tie_word_embeddings": cfg.tie_word_embeddings, "torch_dtype": "bfloat16", "vision_config": vision,
+        "video_token_id": cfg.video_token_id, "image_token_id": cfg.image_token_id,
+        "vision_start_token_id": cfg.vision_start_token_id, "eos_token_id": cfg.eos_token_id, "pad_token_id": cfg.pad_token_id,
+    }
+
+
+def save_checkpoint_dir(path: str, cfg: ModelConfig, weights) -> None:
+    import torch
+
+    sd = {k: v.detach().contiguous().cpu() for k, v in weights.export_state_dict().items()}
+    with open(os.path.join(path, "config.json"), "w") as f:
+        json.dump(hf_config_dict(cfg), f, indent=1)
+    try:
+        from safetensors.torch import save_file
+
+        save_file(sd, os.path.join(path, "model.safetensors"), metadata={"format": "pt"})
+    except ImportError:
+        torch.save(sd, os.path.join(path, "pytorch_model.bin"))
+
+
+def load_checkpoint(path: str, device, world_size: int = 1):
+    import glob
+
+    import torch
+
+    from .weights import ModelWeights
+
+    cfg = from_hf_config(json.load(open(os.path.join(path, "config.json"))))
+    hf = json.load(open(os.path.join(path, "config.json")))
+    for k in ("eos_token_id", "pad_token_id"):
+        if isinstance(hf.get(k), int):
+            setattr(cfg, k, hf[k])
+    cfg.stop_token_ids = (cfg.eos_token_id, cfg.pad_token_id)
+    w = ModelWeights(cfg, device, world_size=world_size)
+    sd: dict = {}
+    files = sorted(glob.glob(os.path.join(path, "*.safetensors")))
+    if files:
+        from safetensors.torch import load_file
+
+        for f in files:
+            sd.update(load_file(f))
+    else:
+        sd = torch.load(os.path.join(path, "pytorch_model.bin"), map_location="cpu")
+    # transformers >= 4.52 nests the towers ("model.visual.*", "model.language_model.*"): normalise to released names
+    norm = {}
+    for k, v in sd.items():
+        k = k.replace("model.visual.", "visual.").replace("model.language_model.", "model.")
+        norm[k] = v
+    w.load_state_dict(norm)
+    return cfg, w
