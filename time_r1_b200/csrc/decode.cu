@@ -9,6 +9,7 @@
 //   * rope + KV append, sampler (temperature -> top-k -> softmax -> multinomial, Philox4x32-10), step counter
 #include "t1_common.cuh"
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -105,7 +106,15 @@ int launch_skinny(const bf16* x, long long ldx, const bf16* W, long long ldw, co
   // split K across a cluster until there are enough CTAs in flight to cover HBM latency
   int ksplit = 1;
   const int slabs = N / 16;
-  while (ksplit < 8 && slabs * ksplit < 1184 && (K / 32) / (ksplit * 2) >= 8) ksplit *= 2;
+  // measured on B200 (profiles/r01_skinny_ksplit_sweep.txt): 2-CTA clusters win when one slab per CTA cannot fill
+  // the machine (N <= ~19k); beyond that the DSMEM reduction only costs.
+  if (slabs < 1184 && (K / 32) >= 32) ksplit = 2;
+  static int forced = -1;   // tuning hook: T1_SKINNY_KSPLIT=1|2|4|8
+  if (forced < 0) {
+    const char* e = getenv("T1_SKINNY_KSPLIT");
+    forced = e ? atoi(e) : 0;
+  }
+  if (forced > 0 && slabs * ksplit < 4096) ksplit = forced;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(slabs, ksplit, 1);
   cfg.blockDim = dim3(256, 1, 1);
