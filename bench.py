@@ -39,6 +39,8 @@ def parse_args():
     ap.add_argument("--slots", type=int, default=16, help="temporal slots of 32x32 patches (16 -> cfg2, 32 -> cfg3, 64 -> cfg5)")
     ap.add_argument("--group-size", type=int, default=8)
     ap.add_argument("--completion-len", type=int, default=200)
+    ap.add_argument("--groups-per-step", type=int, default=2,
+                    help="prompt-groups per GPU per optimizer step = gradient_accumulation_steps (2 in scripts/posttrain/train_rl.sh:27)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--phase-times", action="store_true", help="print a per-phase breakdown to stderr")
     ap.add_argument("--kernel-times", action="store_true", help="print per-entry-point CUDA-event totals of one extra step to stderr")
@@ -47,7 +49,8 @@ def parse_args():
 
 def workload_name(args):
     return (f"cfg2-family: {args.model} dims, grid ({args.slots},32,32) = {args.slots * 256} vision tokens, "
-            f"G={args.group_size}, C={args.completion_len}, one prompt-group per GPU per step")
+            f"G={args.group_size}, C={args.completion_len}, {args.groups_per_step} prompt-group(s) per GPU per optimizer step "
+            f"(gradient_accumulation_steps of train_rl.sh:27)")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -192,8 +195,9 @@ def attention_microbench(eng, P: int, G: int, C: int):
     from time_r1_b200.lib import call, ptr, stream_ptr
 
     cfg = eng.cfg
-    st = eng._decode_state(P, G, C)
-    Kc, Vc = st["kv"][0]
+    st = eng._decode_state((P,), G, C)
+    grp = st["groups"][0]
+    Kc, Vc = grp["kv"][0]
     step = C // 2
     st["step"].fill_(step)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=eng.dev)
@@ -204,7 +208,7 @@ def attention_microbench(eng, P: int, G: int, C: int):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         call("t1_decode_attn", ptr(st["qkv"]), st["qkv"].stride(0), ptr(Kc), ptr(Vc), G, Hq, Hkv, hd, P, st["cpad"],
-             ptr(st["step"]), ptr(st["ws_o"]), ptr(st["ws_ml"]), ptr(st["attn"]), st["attn"].stride(0), hd ** -0.5, stream_ptr())
+             ptr(st["step"]), ptr(grp["ws_o"]), ptr(grp["ws_ml"]), ptr(st["attn"]), st["attn"].stride(0), hd ** -0.5, stream_ptr())
         e1.record()
         torch.cuda.synchronize()
         if i >= 3:
@@ -240,10 +244,12 @@ def run_ours(args):
     mw = weights.ModelWeights(cfg, dev, world_size=world)
     mw.init_random(seed=0)          # same weights on every rank (data parallel)
     eng = engine.Engine(cfg, mw, run, rank=rank, world_size=world, process_group=pg)
-    rewards = TemplateRewards(G, rank)
-    ids, pix_host, grid = synthetic_prompt(cfg, args.slots, rank, 0, dev)
+    NG = args.groups_per_step
+    rewards = [TemplateRewards(G, rank * NG + i) for i in range(NG)]
+    inputs = [synthetic_prompt(cfg, args.slots, rank * NG + i, 0, dev) for i in range(NG)]
+    ids, pix_host, grid = inputs[0]
     P = len(ids)
-    pix_dev = pix_host.to(dev)
+    pix_devs = [inp[1].to(dev) for inp in inputs]
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -251,16 +257,15 @@ def run_ours(args):
         pass
 
     def one_step(step_idx: int, e2e: bool, timers=None):
-        if e2e:
-            pix = pix_host.to(dev, non_blocking=True)                 # H2D of this step's inputs from pinned memory
-        else:
-            pix = pix_dev
-        prompt = engine.Prompt(input_ids=ids, pixel_values=pix, grid_thw=grid, second_per_grid_ts=[1.0])
-        out = eng.grpo_step(prompt, rewards, seed=run.seed + step_idx * world + rank, timers=timers)
+        prompts = []
+        for i, (ids_i, pix_host_i, grid_i) in enumerate(inputs):
+            pix = pix_host_i.to(dev, non_blocking=True) if e2e else pix_devs[i]   # e2e: H2D from pinned memory each step
+            prompts.append(engine.Prompt(input_ids=ids_i, pixel_values=pix, grid_thw=grid_i, second_per_grid_ts=[1.0]))
+        outs = eng.grpo_multi_step(prompts, rewards, seed=run.seed + step_idx * world + rank, loss_scale=1.0 / NG, timers=timers)
         gn = eng.optimizer_step()
         if e2e:
-            return float(out["loss"].item()), float(gn.item())        # D2H of the step's result
-        return out["loss"], gn
+            return float(sum(o["loss"].item() for o in outs)), float(gn.item())   # D2H of the step's result
+        return outs[0]["loss"], gn
 
     def barrier():
         if world > 1:
@@ -309,12 +314,12 @@ def run_ours(args):
             dist.destroy_process_group()
         return
     ms_per_step = ms_total / args.steps
-    value = world * G / (ms_per_step / 1e3)
-    e2e_value = world * G / (ms_e2e / args.steps / 1e3)
+    value = world * NG * G / (ms_per_step / 1e3)
+    e2e_value = world * NG * G / (ms_e2e / args.steps / 1e3)
     gm = prof.get("gemm_bf16_tn", dict(launches=0, flops=0.0, ms=1.0))
     gemm_tflops = gm["flops"] / max(gm["ms"], 1e-9) / 1e9
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
-    algo = flops.step_flops(cfg, grid, P, G, C)
+    algo = {k: v * NG for k, v in flops.step_flops(cfg, grid, P, G, C).items()}
     roofline = {
         "bound": "tensor", "kernel": "gemm_bf16_tn (tcgen05)", "achieved": round(gemm_tflops, 1), "peak": peak_tf, "unit": "TFLOP/s",
         "frac": round(gemm_tflops / peak_tf, 4), "traffic": None, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback",
@@ -330,10 +335,10 @@ def run_ours(args):
         "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms_per_step, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": {"workload": workload_name(args), "prompt_tokens": P, "vision_tokens": args.slots * 256, "group_size": G,
+        "config": {"workload": workload_name(args), "prompt_tokens": P, "vision_tokens": args.slots * 256, "group_size": G, "groups_per_step": NG,
                    "completion_len": C, "parallelism": f"dp{world}+zero2-sharded-adamw", "l2": "inputs larger than L2 (>=16 GB of weights streamed per pass)"},
         "clocks": clocks,
-        "e2e": {"value": round(e2e_value, 4), "unit": UNIT, "h2d_bytes_per_step": int(pix_host.numel() * 4 + ids.size * 4), "d2h_bytes_per_step": int(G * C * 4 + 8)},
+        "e2e": {"value": round(e2e_value, 4), "unit": UNIT, "h2d_bytes_per_step": int(NG * (pix_host.numel() * 4 + ids.size * 4)), "d2h_bytes_per_step": int(NG * (G * C * 4 + 4) + 4)},
         "gpu_launches": launches,
         "roofline": roofline,
         "attn": attn,

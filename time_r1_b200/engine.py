@@ -256,8 +256,9 @@ class Engine:
     # ------------------------------------------------------------------------------------------
     # rollout: prefill once + graph-captured decode
     # ------------------------------------------------------------------------------------------
-    def _decode_state(self, P: int, G: int, C: int):
-        key = (P, G, C)
+    def _decode_state(self, Ps: tuple, G: int, C: int):
+        """Static buffers of the decode graph for n = len(Ps) prompt-groups decoded together (B = n*G sequences)."""
+        key = (tuple(Ps), G, C)
         st = self._decode_cache.get(key)
         if st is not None:
             return st
@@ -266,51 +267,62 @@ class Engine:
             self._decode_cache.clear()
         kd = cfg.num_key_value_heads * cfg.head_dim
         cpad = (C + 127) // 128 * 128
-        S = P + G * cpad
         L = cfg.num_hidden_layers
         ratio = cfg.num_attention_heads // cfg.num_key_value_heads
-        n_chunks = (P + 127) // 128 + G * (cpad // 128)
         rows_pad = (G * ratio + 63) // 64 * 64
         d = self.dev
+        n = len(Ps)
+        B = n * G
+        groups = []
+        for P in Ps:
+            S = P + G * cpad
+            n_chunks = (P + 127) // 128 + G * (cpad // 128)
+            groups.append(dict(
+                P=P,
+                kv=[(torch.zeros((S, kd), device=d, dtype=BF16), torch.zeros((S, kd), device=d, dtype=BF16)) for _ in range(L)],
+                ws_o=torch.empty(n_chunks * cfg.num_key_value_heads * rows_pad * 128, device=d, dtype=F32),
+                ws_ml=torch.empty(n_chunks * cfg.num_key_value_heads * rows_pad * 2, device=d, dtype=F32),
+                cos=torch.empty((C, cfg.head_dim // 2), device=d, dtype=F32), sin=torch.empty((C, cfg.head_dim // 2), device=d, dtype=F32)))
         st = dict(
-            cpad=cpad,
-            kv=[(torch.zeros((S, kd), device=d, dtype=BF16), torch.zeros((S, kd), device=d, dtype=BF16)) for _ in range(L)],
-            x=torch.empty((G, cfg.hidden_size), device=d, dtype=BF16), h=torch.empty((G, cfg.hidden_size), device=d, dtype=BF16),
-            qkv=torch.empty((G, cfg.qkv_dim), device=d, dtype=BF16),
-            attn=torch.empty((G, cfg.num_attention_heads * cfg.head_dim), device=d, dtype=BF16),
-            o=torch.empty((G, cfg.hidden_size), device=d, dtype=BF16),
-            gu=torch.empty((G, 2 * cfg.intermediate_size), device=d, dtype=BF16),
-            act=torch.empty((G, cfg.intermediate_size), device=d, dtype=BF16),
-            down=torch.empty((G, cfg.hidden_size), device=d, dtype=BF16),
-            hN=torch.empty((G, cfg.hidden_size), device=d, dtype=BF16),
-            logits=torch.empty((G, cfg.vocab_size), device=d, dtype=F32),
-            ws_o=torch.empty(n_chunks * cfg.num_key_value_heads * rows_pad * 128, device=d, dtype=F32),
-            ws_ml=torch.empty(n_chunks * cfg.num_key_value_heads * rows_pad * 2, device=d, dtype=F32),
-            step=torch.zeros(1, device=d, dtype=I32), next_ids=torch.zeros(G, device=d, dtype=I32),
-            finished=torch.zeros(G, device=d, dtype=I32), out_ids=torch.zeros((G, C), device=d, dtype=I32),
-            cos=torch.empty((C, cfg.head_dim // 2), device=d, dtype=F32), sin=torch.empty((C, cfg.head_dim // 2), device=d, dtype=F32),
+            cpad=cpad, groups=groups, B=B,
+            x=torch.empty((B, cfg.hidden_size), device=d, dtype=BF16), h=torch.empty((B, cfg.hidden_size), device=d, dtype=BF16),
+            qkv=torch.empty((B, cfg.qkv_dim), device=d, dtype=BF16),
+            attn=torch.empty((B, cfg.num_attention_heads * cfg.head_dim), device=d, dtype=BF16),
+            o=torch.empty((B, cfg.hidden_size), device=d, dtype=BF16),
+            gu=torch.empty((B, 2 * cfg.intermediate_size), device=d, dtype=BF16),
+            act=torch.empty((B, cfg.intermediate_size), device=d, dtype=BF16),
+            down=torch.empty((B, cfg.hidden_size), device=d, dtype=BF16),
+            hN=torch.empty((B, cfg.hidden_size), device=d, dtype=BF16),
+            logits=torch.empty((B, cfg.vocab_size), device=d, dtype=F32),
+            step=torch.zeros(1, device=d, dtype=I32), next_ids=torch.zeros(B, device=d, dtype=I32),
+            finished=torch.zeros(B, device=d, dtype=I32), out_ids=torch.zeros((B, C), device=d, dtype=I32),
             eos=self._i32(list(cfg.stop_token_ids)), seed_dev=torch.zeros(1, device=d, dtype=torch.int64), graph=None, launches_per_step=0,
         )
         self._decode_cache[key] = st
         return st
 
-    def _decode_step(self, st, P: int, G: int, temperature: float, top_k: int, seed: int):
-        """One token for each of the G sequences (captured into a CUDA graph by rollout())."""
+    def _decode_step(self, st, G: int, temperature: float, top_k: int):
+        """One token for each of the B = n*G sequences (captured into a CUDA graph by rollout_multi()). The linears
+        run once over all B rows (the weight stream is amortised over the groups); rope/KV-append and the
+        shared-prefix attention run per group because each group has its own prompt."""
         cfg = self.cfg
         L, Hq, Hkv, hd = cfg.num_hidden_layers, cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim
         eps, scale = cfg.rms_norm_eps, hd ** -0.5
         s = stream_ptr()
+        B = st["B"]
         x, h, qkv, attn, o, gu, act, down = st["x"], st["h"], st["qkv"], st["attn"], st["o"], st["gu"], st["act"], st["down"]
         ops.gather_rows(self.p("model.embed_tokens.weight"), st["next_ids"], out=x)
         for l in range(L):
             pre = f"model.layers.{l}."
             ops.rmsnorm(x, self.p(pre + "input_layernorm.weight"), eps, delta=down if l > 0 else None, out=h)
             ops.skinny_gemm(h, self.p(pre + "self_attn.qkv.weight"), out=qkv, bias=self.p(pre + "self_attn.qkv.bias"))
-            Kc, Vc = st["kv"][l]
-            call("t1_decode_rope_append", ptr(qkv), qkv.stride(0), G, Hq, Hkv, hd, ptr(st["cos"]), ptr(st["sin"]),
-                 ptr(st["step"]), ptr(Kc), ptr(Vc), P, st["cpad"], s)
-            call("t1_decode_attn", ptr(qkv), qkv.stride(0), ptr(Kc), ptr(Vc), G, Hq, Hkv, hd, P, st["cpad"],
-                 ptr(st["step"]), ptr(st["ws_o"]), ptr(st["ws_ml"]), ptr(attn), attn.stride(0), scale, s)
+            for gi, grp in enumerate(st["groups"]):
+                Kc, Vc = grp["kv"][l]
+                q_g, a_g = qkv[gi * G:(gi + 1) * G], attn[gi * G:(gi + 1) * G]
+                call("t1_decode_rope_append", ptr(q_g), qkv.stride(0), G, Hq, Hkv, hd, ptr(grp["cos"]), ptr(grp["sin"]),
+                     ptr(st["step"]), ptr(Kc), ptr(Vc), grp["P"], st["cpad"], s)
+                call("t1_decode_attn", ptr(q_g), qkv.stride(0), ptr(Kc), ptr(Vc), G, Hq, Hkv, hd, grp["P"], st["cpad"],
+                     ptr(st["step"]), ptr(grp["ws_o"]), ptr(grp["ws_ml"]), ptr(a_g), attn.stride(0), scale, s)
             ops.skinny_gemm(attn, self.p(pre + "self_attn.o_proj.weight"), out=o)
             ops.rmsnorm(x, self.p(pre + "post_attention_layernorm.weight"), eps, delta=o, out=h)
             ops.skinny_gemm(h, self.p(pre + "mlp.gate_up.weight"), out=gu)
@@ -318,7 +330,7 @@ class Engine:
             ops.skinny_gemm(act, self.p(pre + "mlp.down_proj.weight"), out=down)
         ops.rmsnorm(x, self.p("model.norm.weight"), eps, delta=down, out=st["hN"])
         ops.skinny_gemm(st["hN"], self.lm_head(), out=st["logits"])
-        call("t1_sample", ptr(st["logits"]), st["logits"].stride(0), G, cfg.vocab_size, float(temperature), int(top_k),
+        call("t1_sample", ptr(st["logits"]), st["logits"].stride(0), B, cfg.vocab_size, float(temperature), int(top_k),
              0, ptr(st["seed_dev"]), ptr(st["step"]), 1, ptr(st["eos"]), len(cfg.stop_token_ids), cfg.pad_token_id, ptr(st["finished"]),
              ptr(st["out_ids"]), st["out_ids"].stride(0), ptr(st["next_ids"]), 0, s)
         call("t1_incr", ptr(st["step"]), 1, s)
@@ -327,33 +339,43 @@ class Engine:
                 top_k: int = 50, seed: int = 0, use_graph: bool = True, check_every: int = 32) -> torch.Tensor:
         """Sample G completions of up to C tokens (temperature 0 => greedy). Returns ids [G, C] int32 on the device,
         pad_token_id after a stop token (HF generate semantics, timer1_trainer.py:568-577)."""
+        return self.rollout_multi([prompt], [vision_embeds], G, C, temperature, top_k, seed, use_graph, check_every)[0]
+
+    def rollout_multi(self, prompts: list, vision_embeds: list, G: int, C: int, temperature: float = 1.0,
+                      top_k: int = 50, seed: int = 0, use_graph: bool = True, check_every: int = 32) -> list:
+        """Rollout for several prompt-groups at once (the micro-batches of one optimizer step see the same weights,
+        so their decode streams can share every weight read). Returns one [G, C] int32 tensor per group."""
         cfg = self.cfg
-        ids = np.asarray(prompt.input_ids)
-        P = len(ids)
-        st = self._decode_state(P, G, C)
-        pos3, delta = indexing.mrope_positions(cfg, ids, prompt.grid_thw, prompt.second_per_grid_ts)
-        cos, sin = self._rope_tables(pos3)
-        ids_dev = self._i32(ids)
-        vis_rows = self._i32(np.nonzero(ids == cfg.video_token_id)[0])
-        x0 = self._embed(ids_dev, vision_embeds, vis_rows)
-        lo = torch.zeros(P, device=self.dev, dtype=I32)
-        hi = torch.arange(1, P + 1, device=self.dev, dtype=I32)
-        kv_prefix = [(k[:P], v[:P]) for k, v in st["kv"]]
-        hN = self.llm_forward(x0, cos, sin, lo, hi, 0, kv_out=kv_prefix)
-        logits0 = ops.skinny_gemm(hN[P - 1:P], self.lm_head(), out_dtype=F32)           # [1, V]
-        # decode-position tables: completion token c sits at text position P + c + rope_delta on all three axes
-        dpos = np.tile((P + delta + np.arange(C, dtype=np.int64))[None, :], (3, 1))
-        dcos, dsin = self._rope_tables(dpos)
-        st["cos"].copy_(dcos)
-        st["sin"].copy_(dsin)
+        Ps = tuple(len(np.asarray(p.input_ids)) for p in prompts)
+        st = self._decode_state(Ps, G, C)
+        B = st["B"]
         st["step"].zero_()
         st["finished"].zero_()
         st["out_ids"].fill_(cfg.pad_token_id)
-        # first token: G independent draws from the shared last-prompt-position distribution (row stride 0)
         st["seed_dev"].fill_(int(seed))
-        call("t1_sample", ptr(logits0), 0, G, cfg.vocab_size, float(temperature), int(top_k), 0, ptr(st["seed_dev"]), 0, 0,
-             ptr(st["eos"]), len(cfg.stop_token_ids), cfg.pad_token_id, ptr(st["finished"]), ptr(st["out_ids"]),
-             st["out_ids"].stride(0), ptr(st["next_ids"]), 0, stream_ptr())
+        for gi, (prompt, emb, grp) in enumerate(zip(prompts, vision_embeds, st["groups"])):
+            ids = np.asarray(prompt.input_ids)
+            P = grp["P"]
+            pos3, delta = indexing.mrope_positions(cfg, ids, prompt.grid_thw, prompt.second_per_grid_ts)
+            cos, sin = self._rope_tables(pos3)
+            ids_dev = self._i32(ids)
+            vis_rows = self._i32(np.nonzero(ids == cfg.video_token_id)[0])
+            x0 = self._embed(ids_dev, emb, vis_rows)
+            lo = torch.zeros(P, device=self.dev, dtype=I32)
+            hi = torch.arange(1, P + 1, device=self.dev, dtype=I32)
+            kv_prefix = [(k[:P], v[:P]) for k, v in grp["kv"]]
+            hN = self.llm_forward(x0, cos, sin, lo, hi, 0, kv_out=kv_prefix)
+            logits0 = ops.skinny_gemm(hN[P - 1:P], self.lm_head(), out_dtype=F32)           # [1, V]
+            # decode-position tables: completion token c sits at text position P + c + rope_delta on all three axes
+            dpos = np.tile((P + delta + np.arange(C, dtype=np.int64))[None, :], (3, 1))
+            dcos, dsin = self._rope_tables(dpos)
+            grp["cos"].copy_(dcos)
+            grp["sin"].copy_(dsin)
+            # first token: G independent draws from the shared last-prompt-position distribution (row stride 0)
+            sl = slice(gi * G, (gi + 1) * G)
+            call("t1_sample", ptr(logits0), 0, G, cfg.vocab_size, float(temperature), int(top_k), int(seed) + 7919 * (gi + 1), 0, 0, 0,
+                 ptr(st["eos"]), len(cfg.stop_token_ids), cfg.pad_token_id, ptr(st["finished"][sl]), ptr(st["out_ids"][sl]),
+                 st["out_ids"].stride(0), ptr(st["next_ids"][sl]), 0, stream_ptr())
         n_steps = C - 1
         if n_steps > 0:
             gkey = (float(temperature), int(top_k))     # the seed lives in device memory: graphs are seed-independent
@@ -361,7 +383,7 @@ class Engine:
                 if st["graph"] is None or st.get("gkey") != gkey:
                     # warm-up step outside capture (sets func attributes), then rewind the state it touched
                     snap = (st["next_ids"].clone(), st["finished"].clone(), st["out_ids"].clone())
-                    self._decode_step(st, P, G, temperature, top_k, seed)
+                    self._decode_step(st, G, temperature, top_k)
                     torch.cuda.synchronize()
                     st["step"].zero_()
                     st["next_ids"].copy_(snap[0]); st["finished"].copy_(snap[1]); st["out_ids"].copy_(snap[2])
@@ -369,7 +391,7 @@ class Engine:
                     from .lib import load
                     before = load().t1_launch_count(0)
                     with torch.cuda.graph(g):
-                        self._decode_step(st, P, G, temperature, top_k, seed)
+                        self._decode_step(st, G, temperature, top_k)
                     st["launches_per_step"] = int(load().t1_launch_count(0) - before)
                     st["graph"], st["gkey"] = g, gkey
                     st["step"].zero_()
@@ -385,10 +407,10 @@ class Engine:
                         break
             else:
                 for i in range(n_steps):
-                    self._decode_step(st, P, G, temperature, top_k, seed)
+                    self._decode_step(st, G, temperature, top_k)
                     if (i + 1) % check_every == 0 and bool(st["finished"].all().item()):
                         break
-        return st["out_ids"].clone()
+        return [st["out_ids"][gi * G:(gi + 1) * G].clone() for gi in range(len(prompts))]
 
     # ------------------------------------------------------------------------------------------
     # scoring (teacher-forced log-probs of the completions) over the packed layout
@@ -643,9 +665,18 @@ class Engine:
     # ------------------------------------------------------------------------------------------
     def grpo_step(self, prompt: Prompt, reward_fn, seed: int | None = None, completion_override=None,
                   loss_scale: float = 1.0, timers: dict | None = None):
-        """rollout -> mask -> policy/ref scoring -> rewards (host callback) -> advantage -> loss -> backward.
+        """One prompt-group: see grpo_multi_step."""
+        ov = None if completion_override is None else [completion_override]
+        return self.grpo_multi_step([prompt], [reward_fn], seed=seed, completion_overrides=ov, loss_scale=loss_scale,
+                                    timers=timers)[0]
+
+    def grpo_multi_step(self, prompts: list, reward_fns: list, seed: int | None = None, completion_overrides=None,
+                        loss_scale: float = 1.0, timers: dict | None = None) -> list:
+        """The micro-batches of ONE optimizer step (gradient accumulation, train_rl.sh:27), each a prompt-group:
+        ViT per group -> joint rollout (shared weight stream) -> per group: mask, policy/ref scoring, rewards (host
+        callback), advantage, loss, backward (gradients accumulate).
         reward_fn(completion_ids_host [G, C] int64 numpy) -> rewards_per_func [G, n_funcs] float32 numpy.
-        Returns a dict of device tensors / python scalars (loss, stats, rewards, advantages, completion ids)."""
+        Returns one dict of device tensors per group."""
         run, cfg = self.run, self.cfg
         G, C = run.num_generations, run.max_completion_length
         seed = run.seed if seed is None else seed
@@ -657,35 +688,42 @@ class Engine:
                 timers.setdefault("_events", []).append((name, ev))
 
         mark("start")
-        x_vit, delta, plan = self.vit_blocks(prompt.pixel_values, prompt.grid_thw)
-        emb = self.merger(x_vit, delta, plan, "policy")                     # x_vit now holds the final ViT stream
+        vit = []
+        for prompt in prompts:
+            x_vit, delta, plan = self.vit_blocks(prompt.pixel_values, prompt.grid_thw)
+            emb = self.merger(x_vit, delta, plan, "policy")                 # x_vit now holds the final ViT stream
+            vit.append((emb, x_vit, plan))
         mark("vit")
-        if completion_override is None:
-            comp = self.rollout(prompt, emb, G, C, run.temperature, run.top_k, seed)
+        if completion_overrides is None:
+            comps = self.rollout_multi(prompts, [v[0] for v in vit], G, C, run.temperature, run.top_k, seed)
         else:
-            comp = completion_override.to(device=self.dev, dtype=I32).contiguous()
+            comps = [c.to(device=self.dev, dtype=I32).contiguous() for c in completion_overrides]
         mark("rollout")
-        mask, lengths = ops.eos_mask(comp, cfg.eos_token_id)
-        logp, ent, st = self.score(prompt, comp, emb, "policy", save=True, x_vit=x_vit, plan=plan)
-        mark("score_policy")
-        ref_logp = None
-        if run.beta != 0.0:
-            if self.ref is None:
-                raise RuntimeError("beta != 0 needs the reference parameter set (Engine(with_ref=True))")
-            emb_ref = self.merger(x_vit, None, plan, "ref")
-            ref_logp, _, _ = self.score(prompt, comp, emb_ref, "ref")
-        mark("score_ref")
-        comp_host = comp.cpu().numpy().astype(np.int64)                     # D2H: completions for the host reward fns
-        rpf = np.ascontiguousarray(reward_fn(comp_host), dtype=np.float32).reshape(G, -1)
-        rpf_dev = torch.from_numpy(rpf).to(self.dev)
-        rewards, adv, mean, std = ops.group_advantage(rpf_dev, G)
-        loss, dlogp, stats = ops.grpo_loss(logp, ref_logp, ent, adv, mask, run.beta, run.epsilon_low, run.epsilon_high,
-                                           run.use_grpo, loss_scale=loss_scale)
-        mark("reward_loss")
-        self.backward(st, dlogp)
-        mark("backward")
-        return dict(loss=loss, stats=stats, rewards=rewards, rewards_per_func=rpf_dev, advantages=adv, reward_std=std,
-                    completion_ids=comp, completion_mask=mask, logp=logp, ref_logp=ref_logp, entropy=ent, dlogp=dlogp)
+        outs = []
+        for prompt, reward_fn, comp, (emb, x_vit, plan) in zip(prompts, reward_fns, comps, vit):
+            mask, lengths = ops.eos_mask(comp, cfg.eos_token_id)
+            logp, ent, st = self.score(prompt, comp, emb, "policy", save=True, x_vit=x_vit, plan=plan)
+            mark("score_policy")
+            ref_logp = None
+            if run.beta != 0.0:
+                if self.ref is None:
+                    raise RuntimeError("beta != 0 needs the reference parameter set (Engine(with_ref=True))")
+                emb_ref = self.merger(x_vit, None, plan, "ref")
+                ref_logp, _, _ = self.score(prompt, comp, emb_ref, "ref")
+            mark("score_ref")
+            comp_host = comp.cpu().numpy().astype(np.int64)                 # D2H: completions for the host reward fns
+            rpf = np.ascontiguousarray(reward_fn(comp_host), dtype=np.float32).reshape(G, -1)
+            rpf_dev = torch.from_numpy(rpf).to(self.dev)
+            rewards, adv, mean, std = ops.group_advantage(rpf_dev, G)
+            loss, dlogp, stats = ops.grpo_loss(logp, ref_logp, ent, adv, mask, run.beta, run.epsilon_low, run.epsilon_high,
+                                               run.use_grpo, loss_scale=loss_scale)
+            mark("reward_loss")
+            self.backward(st, dlogp)
+            mark("backward")
+            del st
+            outs.append(dict(loss=loss, stats=stats, rewards=rewards, rewards_per_func=rpf_dev, advantages=adv, reward_std=std,
+                             completion_ids=comp, completion_mask=mask, logp=logp, ref_logp=ref_logp, entropy=ent, dlogp=dlogp))
+        return outs
 
 
 def finish_timers(timers: dict) -> dict:

@@ -260,15 +260,8 @@ class TimeR1_Trainer:
         return pc.batch_decode(ids, skip_special_tokens=True)
 
     # ------------------------------------------------------------------ one micro-step
-    def compute_loss(self, model, inputs, return_outputs: bool = False, num_items_in_batch=None):
-        """rollout + scoring + rewards + advantages + loss + BACKWARD for one prompt group (the backward the reference
-        runs in HF Trainer.training_step is part of this call). Returns the (grad-accum-scaled) loss as a 1-element
-        device tensor."""
-        if return_outputs:
-            raise ValueError("The GRPOTrainer does not support returning outputs")
-        if len(inputs) != 1:
-            raise ValueError("per_device_train_batch_size must be 1 (the reference only consumes inputs[0], timer1_trainer.py:548-551)")
-        example = inputs[0]
+    def _prepare(self, example: dict):
+        """(Prompt, reward callback) for one dataset row — reward protocol of timer1_trainer.py:685-698."""
         G = self.num_generations
         prompt = self._prompt_from_example(example)
         prompts = [self.make_conversation_video(example) if "problem" in example and "video_path" in example else example.get("prompt")] * G
@@ -284,11 +277,29 @@ class TimeR1_Trainer:
             self._last_completions = completions
             return out
 
+        return prompt, reward_fn
+
+    def compute_loss(self, model, inputs, return_outputs: bool = False, num_items_in_batch=None):
+        """rollout + scoring + rewards + advantages + loss + BACKWARD for one prompt group (the backward the reference
+        runs in HF Trainer.training_step is part of this call). Returns the (grad-accum-scaled) loss as a 1-element
+        device tensor."""
+        if return_outputs:
+            raise ValueError("The GRPOTrainer does not support returning outputs")
+        return self._accum_step([inputs])[0]
+
+    def _accum_step(self, micro_batches: list) -> list:
+        """All micro-batches of one optimizer step at once: they see the same weights, so their rollouts are decoded
+        together (one weight stream for all of them); scoring / backward stay per prompt-group."""
+        for inputs in micro_batches:
+            if len(inputs) != 1:
+                raise ValueError("per_device_train_batch_size must be 1 (the reference only consumes inputs[0], timer1_trainer.py:548-551)")
+        prepared = [self._prepare(inputs[0]) for inputs in micro_batches]
         accum = self.args.gradient_accumulation_steps
-        seed = self.run.seed + 7919 * (self.state.global_step * accum + self._micro) * self.world + self.rank
-        out = self.engine.grpo_step(prompt, reward_fn, seed=seed, loss_scale=1.0 / accum)
-        self._log_metrics(out)
-        return out["loss"]
+        seed = self.run.seed + 7919 * (self.state.global_step * self.world + self.rank)
+        outs = self.engine.grpo_multi_step([p for p, _ in prepared], [r for _, r in prepared], seed=seed, loss_scale=1.0 / accum)
+        for out in outs:
+            self._log_metrics(out)
+        return [o["loss"] for o in outs]
 
     def _log_metrics(self, out: dict):
         import torch
@@ -351,8 +362,7 @@ class TimeR1_Trainer:
             loader = self.get_train_dataloader() if epoch > 0 else loader
             for i in range(0, len(loader) - len(loader) % accum or len(loader), accum):
                 micro = loader[i:i + accum]
-                for self._micro, inputs in enumerate(micro):
-                    losses.append(self.compute_loss(self.engine, inputs))
+                losses.extend(self._accum_step(micro))
                 done = self.state.global_step - start_step
                 lr = a.learning_rate * max(0.0, 1.0 - done / max(1, total - start_step))   # linear decay, no warm-up
                 gnorm = self.engine.optimizer_step(lr=lr)
@@ -377,8 +387,6 @@ class TimeR1_Trainer:
         for cb in self.callbacks:
             cb.on_train_end(a, self.state, self.control, trainer=self)
         return self.state
-
-    _micro = 0
 
     # ------------------------------------------------------------------ checkpoints (HF-format export)
     def save_model(self, output_dir: Optional[str] = None):
