@@ -284,7 +284,7 @@ class Engine:
                 ws_ml=torch.empty(n_chunks * cfg.num_key_value_heads * rows_pad * 2, device=d, dtype=F32),
                 cos=torch.empty((C, cfg.head_dim // 2), device=d, dtype=F32), sin=torch.empty((C, cfg.head_dim // 2), device=d, dtype=F32)))
         st = dict(
-            cpad=cpad, groups=groups, B=B,
+            cpad=cpad, groups=groups, B=B, streams=[torch.cuda.Stream(device=d) for _ in range(n - 1)],
             x=torch.empty((B, cfg.hidden_size), device=d, dtype=BF16), h=torch.empty((B, cfg.hidden_size), device=d, dtype=BF16),
             qkv=torch.empty((B, cfg.qkv_dim), device=d, dtype=BF16),
             attn=torch.empty((B, cfg.num_attention_heads * cfg.head_dim), device=d, dtype=BF16),
@@ -316,13 +316,23 @@ class Engine:
             pre = f"model.layers.{l}."
             ops.rmsnorm(x, self.p(pre + "input_layernorm.weight"), eps, delta=down if l > 0 else None, out=h)
             ops.skinny_gemm(h, self.p(pre + "self_attn.qkv.weight"), out=qkv, bias=self.p(pre + "self_attn.qkv.bias"))
+            # per-group rope/KV-append + shared-prefix attention are latency-bound and independent of each other:
+            # fork them onto side streams (parallel branches of the captured graph), join before the o-projection
+            main = torch.cuda.current_stream()
             for gi, grp in enumerate(st["groups"]):
                 Kc, Vc = grp["kv"][l]
                 q_g, a_g = qkv[gi * G:(gi + 1) * G], attn[gi * G:(gi + 1) * G]
-                call("t1_decode_rope_append", ptr(q_g), qkv.stride(0), G, Hq, Hkv, hd, ptr(grp["cos"]), ptr(grp["sin"]),
-                     ptr(st["step"]), ptr(Kc), ptr(Vc), grp["P"], st["cpad"], s)
-                call("t1_decode_attn", ptr(q_g), qkv.stride(0), ptr(Kc), ptr(Vc), G, Hq, Hkv, hd, grp["P"], st["cpad"],
-                     ptr(st["step"]), ptr(grp["ws_o"]), ptr(grp["ws_ml"]), ptr(a_g), attn.stride(0), scale, s)
+                side = main if gi == 0 else st["streams"][gi - 1]
+                if gi > 0:
+                    side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    sp = stream_ptr()
+                    call("t1_decode_rope_append", ptr(q_g), qkv.stride(0), G, Hq, Hkv, hd, ptr(grp["cos"]), ptr(grp["sin"]),
+                         ptr(st["step"]), ptr(Kc), ptr(Vc), grp["P"], st["cpad"], sp)
+                    call("t1_decode_attn", ptr(q_g), qkv.stride(0), ptr(Kc), ptr(Vc), G, Hq, Hkv, hd, grp["P"], st["cpad"],
+                         ptr(st["step"]), ptr(grp["ws_o"]), ptr(grp["ws_ml"]), ptr(a_g), attn.stride(0), scale, sp)
+            for gi in range(1, len(st["groups"])):
+                main.wait_stream(st["streams"][gi - 1])
             ops.skinny_gemm(attn, self.p(pre + "self_attn.o_proj.weight"), out=o)
             ops.rmsnorm(x, self.p(pre + "post_attention_layernorm.weight"), eps, delta=o, out=h)
             ops.skinny_gemm(h, self.p(pre + "mlp.gate_up.weight"), out=gu)
