@@ -31,8 +31,10 @@ def test_multi_group_rollout_matches_single_group_greedy_and_grads_accumulate():
         assert torch.equal(joint_eager[gi], single)
     sampled = eng.rollout_multi(prompts, embs, G, C, temperature=1.0, top_k=50, seed=5)
     assert not torch.equal(sampled[0], sampled[1])
-    # gradient accumulation over the two groups == sum of the per-group gradients
+    # gradient accumulation over the two groups == sum of the per-group gradients.  Distinct random completions:
+    # with identical (greedy) completions and zero-sum advantages the true gradient cancels to rounding noise.
     rw = [rng.random((G, 2)).astype(np.float32) for _ in prompts]
+    joint = [torch.from_numpy(rng.integers(10, 2000, (G, C))).int().cuda() for _ in prompts]
     eng.grpo_multi_step(prompts, [lambda c, r=r: r for r in rw], completion_overrides=joint, loss_scale=0.5)
     g_joint = eng.grads.buf.float().clone()
     eng.grad_fresh = True

@@ -348,39 +348,86 @@ decode_attn_kernel(const bf16* __restrict__ q, long long ldq, const bf16* __rest
   }
 }
 
-// combine partials: one CTA (128 threads = head dim) per (seq, q head). Only the prefix chunks and the sequence's own
-// completion chunks are visited; loads are unconditional (select on l > 0) so they pipeline.
-__global__ void __launch_bounds__(128)
+// combine partials: one CTA of 8 warps per (seq, q head).  Warp w owns chunks w, w+8, ... (prefix chunks + the
+// sequence's own completion chunks only); lane l owns head-dim columns 4l..4l+3 (float4).  All loads of a warp are
+// independent, so the kernel costs ~one memory round trip; the 8 warp partials are merged through shared memory.
+__global__ void __launch_bounds__(256)
 decode_attn_combine_kernel(const float* __restrict__ ws_o, const float* __restrict__ ws_ml, int n_chunks,
                            int n_prefix_chunks, int chunks_per_seq, int Hq, int Hkv, int rows_pad,
                            bf16* __restrict__ out, long long ldo) {
+  __shared__ float s_m[8], s_l[8];
+  __shared__ float4 s_acc[8][32];
   const int b = blockIdx.x / Hq, hq = blockIdx.x % Hq;
   const int ratio = Hq / Hkv, hk = hq / ratio;
   const int row = b * ratio + (hq - hk * ratio);
-  const int d = threadIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nc = n_prefix_chunks + chunks_per_seq;
   const long long stride = (long long)Hkv * rows_pad;
   const long long base = (long long)hk * rows_pad + row;
-  auto chunk_of = [&](int i) { return i < n_prefix_chunks ? i : n_prefix_chunks + b * chunks_per_seq + (i - n_prefix_chunks); };
-  float M = -INFINITY;
-#pragma unroll 8
-  for (int i = 0; i < nc; ++i) {
-    const long long r = (long long)chunk_of(i) * stride + base;
-    const float2 ml = *reinterpret_cast<const float2*>(ws_ml + r * 2);
-    M = fmaxf(M, ml.y > 0.f ? ml.x : -INFINITY);
+  constexpr int MAXC = 8;  // chunks per warp handled in registers (nc <= 64); larger nc loops
+  float m_run = -INFINITY, l_run = 0.f;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i0 = warp; i0 < nc; i0 += 8 * MAXC) {
+    float2 ml[MAXC];
+    float4 o[MAXC];
+#pragma unroll
+    for (int j = 0; j < MAXC; ++j) {
+      const int i = i0 + j * 8;
+      ml[j] = make_float2(-INFINITY, 0.f);
+      o[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < nc) {
+        const int c = i < n_prefix_chunks ? i : n_prefix_chunks + b * chunks_per_seq + (i - n_prefix_chunks);
+        const long long r = (long long)c * stride + base;
+        ml[j] = *reinterpret_cast<const float2*>(ws_ml + r * 2);
+        if (ml[j].y > 0.f) o[j] = *reinterpret_cast<const float4*>(ws_o + r * 128 + lane * 4);
+      }
+    }
+    float m_new = m_run;
+#pragma unroll
+    for (int j = 0; j < MAXC; ++j)
+      if (ml[j].y > 0.f) m_new = fmaxf(m_new, ml[j].x);
+    if (m_new > -INFINITY) {
+      const float sc = exp2f(m_run - m_new);  // m_run == -inf -> 0
+      l_run *= sc;
+      acc.x *= sc; acc.y *= sc; acc.z *= sc; acc.w *= sc;
+#pragma unroll
+      for (int j = 0; j < MAXC; ++j) {
+        if (ml[j].y > 0.f) {
+          const float w = exp2f(ml[j].x - m_new);
+          l_run += w * ml[j].y;
+          acc.x += w * o[j].x; acc.y += w * o[j].y; acc.z += w * o[j].z; acc.w += w * o[j].w;
+        }
+      }
+      m_run = m_new;
+    }
   }
-  float L = 0.f, acc = 0.f;
-#pragma unroll 8
-  for (int i = 0; i < nc; ++i) {
-    const long long r = (long long)chunk_of(i) * stride + base;
-    const float2 ml = *reinterpret_cast<const float2*>(ws_ml + r * 2);
-    const float o = ws_o[r * 128 + d];
-    const bool ok = ml.y > 0.f;
-    const float w = ok ? exp2f(ml.x - M) : 0.f;
-    L += ok ? w * ml.y : 0.f;
-    acc += ok ? w * o : 0.f;
+  if (lane == 0) {
+    s_m[warp] = m_run;
+    s_l[warp] = l_run;
   }
-  out[(long long)b * ldo + hq * 128 + d] = __float2bfloat16(L > 0.f ? acc / L : 0.f);
+  s_acc[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0) {
+    float M = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) M = fmaxf(M, s_m[w]);
+    float L = 0.f;
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      if (s_m[w] > -INFINITY) {
+        const float sc = exp2f(s_m[w] - M);
+        const float4 a = s_acc[w][lane];
+        L += sc * s_l[w];
+        t.x += sc * a.x; t.y += sc * a.y; t.z += sc * a.z; t.w += sc * a.w;
+      }
+    }
+    const float inv = L > 0.f ? 1.f / L : 0.f;
+    uint2 pk;
+    pk.x = pack_bf16x2(t.x * inv, t.y * inv);
+    pk.y = pack_bf16x2(t.z * inv, t.w * inv);
+    *reinterpret_cast<uint2*>(out + (long long)b * ldo + hq * 128 + lane * 4) = pk;
+  }
   (void)n_chunks;
 }
 
@@ -623,7 +670,7 @@ extern "C" int t1_decode_attn(const void* q, long long ldq, const void* Kc, cons
                                                   prefix_len, cpad, step_ptr, ws_o, ws_ml, n_prefix_chunks, rows_pad,
                                                   scale * 1.4426950408889634f);
   T1_CUDA_LAUNCH_CHECK("t1_decode_attn");
-  decode_attn_combine_kernel<<<B * Hq, 128, 0, stream>>>(ws_o, ws_ml, n_chunks, n_prefix_chunks, chunks_per_seq, Hq, Hkv,
+  decode_attn_combine_kernel<<<B * Hq, 256, 0, stream>>>(ws_o, ws_ml, n_chunks, n_prefix_chunks, chunks_per_seq, Hq, Hkv,
                                                         rows_pad, (bf16*)out, ldo);
   T1_CUDA_LAUNCH_CHECK("t1_decode_attn.combine");
   return T1_OK;
