@@ -1,0 +1,320 @@
+// tcgen05 / TMEM / TMA flash-attention forward (head_dim 128) over the packed token axis of attention.cu.
+//
+// Same masking model and call sites as t1_attn_fwd (LLM prefill / packed GRPO scoring; HF Q25:740-755 reached from
+// src/time_r1/rl/timer1_trainer.py:452-457,569-573) — this is the Blackwell-native replacement of the HMMA kernel for
+// the tensor-bound LLM shapes.  One CTA = 128 query rows x one q head, looping over 128-key tiles:
+//   warp 0       TMA producer : Q tile once, K/V tiles (2 x [128 x 64] SWIZZLE_128B boxes each) into a 2-stage ring
+//   warp 1       MMA issuer   : S = Q K^T   (tcgen05.mma M128 N128 K16 x 8, both operands K-major) -> TMEM S[it & 1]
+//                               O += P V    (A = P from smem, K-major; B = V tile consumed in place as an MN-major
+//                               operand — no transpose) -> TMEM O
+//   warps 2..5   softmax      : thread = query row; tcgen05.ld S -> mask, scale, lazy-rescaled online softmax (the
+//                               running max is only refreshed when it grows by > 8 in log2 units, so the O accumulator
+//                               in TMEM is rarely rescaled) -> P (bf16) written to smem in the UMMA K-major swizzle
+// S(it+1) is issued before softmax(it) finishes, so QK^T overlaps the exponentials.
+#include "t1_common.cuh"
+#include <limits.h>
+#include <stdlib.h>
+
+namespace {
+
+constexpr int TQ = 128;   // query rows per CTA
+constexpr int TK = 128;   // keys per tile
+constexpr int HD = 128;
+constexpr int ATOM_BYTES = 128 * 128;            // [128 rows x 64 bf16] box
+constexpr int TILE_BYTES = 2 * ATOM_BYTES;       // [128 x 128] bf16
+constexpr int FA_TC_THREADS = 192;
+constexpr int FA_TC_SMEM = TILE_BYTES /*Q*/ + 2 * TILE_BYTES /*K*/ + 2 * TILE_BYTES /*V*/ + TILE_BYTES /*P*/ + 1024 + 256;
+
+struct Range {
+  int tA_end, tB_start, tB_end;
+  __device__ __forceinline__ int count() const { return tA_end + max(0, tB_end - tB_start); }
+  __device__ __forceinline__ int tile(int idx) const { return idx < tA_end ? idx : tB_start + (idx - tA_end); }
+};
+
+__global__ void __launch_bounds__(FA_TC_THREADS, 1)
+fa_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                 const __grid_constant__ CUtensorMap tm_v, bf16* __restrict__ O, long long ldo, float* __restrict__ LSE2,
+                 const int* __restrict__ row_lo, const int* __restrict__ row_hi, int shared_len, int T, int group,
+                 float scale_log2, uint32_t v_lbo, uint32_t v_sbo) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + TILE_BYTES;            // 2 stages
+  uint8_t* sV = sK + 2 * TILE_BYTES;        // 2 stages
+  uint8_t* sP = sV + 2 * TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + TILE_BYTES);
+  uint64_t* q_full = bars;                  // 1
+  uint64_t* kv_full = bars + 1;             // 2
+  uint64_t* kv_empty = bars + 3;            // 2
+  uint64_t* s_full = bars + 5;              // 2
+  uint64_t* p_full = bars + 7;              // 1 (128 arrivals)
+  uint64_t* pv_done = bars + 8;             // 1
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 9);
+  int* s_red = reinterpret_cast<int*>(bars + 10);  // 4 ints
+
+  const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * TQ;
+  const int h = blockIdx.y, hk = h / group;
+
+  // ---- tile range from the rows' (lo, hi): threads 64..191 (softmax warps) own one row each ----
+  if (threadIdx.x == 0) {
+    s_red[0] = INT_MAX; s_red[1] = INT_MIN; s_red[2] = INT_MAX; s_red[3] = INT_MIN;
+  }
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_k);
+    tma_prefetch_desc(&tm_v);
+  }
+  if (warp_idx == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+    }
+    mbar_init(p_full, 128);
+    mbar_init(pv_done, 1);
+    mbar_fence_init();
+  }
+  if (warp_idx == 1) tmem_alloc<512>(tmem_ptr_smem);
+  __syncthreads();
+  int my_row = -1, my_lo = 0, my_hi = 0;
+  if (warp_idx >= 2) {
+    const int quad = warp_idx & 3;
+    my_row = q0 + quad * 32 + lane;
+    if (my_row < T) {
+      my_lo = row_lo[my_row];
+      my_hi = row_hi[my_row];
+      atomicMin(&s_red[0], my_lo); atomicMax(&s_red[1], my_lo);
+      atomicMin(&s_red[2], my_hi); atomicMax(&s_red[3], my_hi);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const int min_lo = s_red[0], max_lo = s_red[1], min_hi = s_red[2], max_hi = s_red[3];
+  Range tr;
+  if (max_hi <= 0 || min_lo == INT_MAX) {
+    tr.tA_end = tr.tB_start = tr.tB_end = 0;
+  } else {
+    const int a_end = min(min(shared_len, min_lo), max_hi);
+    tr.tA_end = (a_end + TK - 1) / TK;
+    tr.tB_start = max(min_lo / TK, tr.tA_end);
+    tr.tB_end = (max_hi + TK - 1) / TK;
+  }
+  const int ntiles = tr.count();
+
+  if (warp_idx == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0 && ntiles > 0) {
+      mbar_arrive_expect_tx(q_full, TILE_BYTES);
+      tma_load_2d(sQ, &tm_q, q_full, h * HD, q0);
+      tma_load_2d(sQ + ATOM_BYTES, &tm_q, q_full, h * HD + 64, q0);
+      for (int it = 0; it < ntiles; ++it) {
+        const int st = it & 1;
+        mbar_wait(&kv_empty[st], ((it >> 1) & 1) ^ 1);
+        const int j0 = tr.tile(it) * TK;
+        mbar_arrive_expect_tx(&kv_full[st], 2 * TILE_BYTES);
+        tma_load_2d(sK + st * TILE_BYTES, &tm_k, &kv_full[st], hk * HD, j0);
+        tma_load_2d(sK + st * TILE_BYTES + ATOM_BYTES, &tm_k, &kv_full[st], hk * HD + 64, j0);
+        tma_load_2d(sV + st * TILE_BYTES, &tm_v, &kv_full[st], hk * HD, j0);
+        tma_load_2d(sV + st * TILE_BYTES + ATOM_BYTES, &tm_v, &kv_full[st], hk * HD + 64, j0);
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0 && ntiles > 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(TQ, TK);                   // both K-major
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(TQ, HD) | (1u << 16);     // B (= V) MN-major
+      const uint32_t tmem_o = tmem_base + 256;
+      auto issue_s = [&](int it) {
+        const int st = it & 1;
+        mbar_wait(&kv_full[st], (it >> 1) & 1);
+        tc_fence_after();
+        const uint32_t tmem_s = tmem_base + (it & 1) * 128;
+#pragma unroll
+        for (int ks = 0; ks < HD / 16; ++ks) {
+          const uint32_t off = (ks >> 2) * ATOM_BYTES + (ks & 3) * 32;
+          umma_bf16_ss(tmem_s, umma_desc_sw128_kmajor(smem_u32(sQ + off)),
+                       umma_desc_sw128_kmajor(smem_u32(sK + st * TILE_BYTES + off)), idesc_s, ks != 0 ? 1u : 0u);
+        }
+        umma_commit(&s_full[it & 1]);
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      for (int it = 0; it < ntiles; ++it) {
+        if (it + 1 < ntiles) issue_s(it + 1);
+        mbar_wait(p_full, it & 1);
+        tc_fence_after();
+        const int st = it & 1;
+#pragma unroll
+        for (int kk = 0; kk < TK / 16; ++kk) {
+          const uint64_t a_desc = umma_desc_sw128_kmajor(smem_u32(sP + (kk >> 2) * ATOM_BYTES + (kk & 3) * 32));
+          const uint64_t b_desc = umma_desc_sw128_mnmajor(smem_u32(sV + st * TILE_BYTES + kk * 16 * 128), v_lbo, v_sbo);
+          umma_bf16_ss(tmem_o, a_desc, b_desc, idesc_pv, (it | kk) != 0 ? 1u : 0u);
+        }
+        umma_commit(&kv_empty[st]);
+        umma_commit(pv_done);
+      }
+    }
+  } else {
+    // ===================== softmax warps (thread = query row) =====================
+    const int quad = warp_idx & 3;
+    const int r = quad * 32 + lane;                     // row inside the tile == TMEM lane
+    const bool valid = my_row < T;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const uint32_t tmem_o = t_lane + 256;
+    float m_ref = -INFINITY, l = 0.f;
+    for (int it = 0; it < ntiles; ++it) {
+      const int j0 = tr.tile(it) * TK, j1 = j0 + TK;
+      mbar_wait(&s_full[it & 1], (it >> 1) & 1);
+      tc_fence_after();
+      uint32_t sv[4][32];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32(t_lane + (it & 1) * 128 + c * 32, sv[c]);
+      tmem_ld_wait();
+      const bool need_mask = !(j1 <= min_hi && (j0 >= max_lo || j1 <= shared_len));
+      float tmax = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float v = __uint_as_float(sv[c][j]) * scale_log2;
+          if (need_mask) {
+            const int key = j0 + c * 32 + j;
+            const bool vis = valid && key < my_hi && (key >= my_lo || key < shared_len);
+            v = vis ? v : -INFINITY;
+          }
+          sv[c][j] = __float_as_uint(v);
+          tmax = fmaxf(tmax, v);
+        }
+      // lazy rescale: refresh the reference max only when it grows by more than 8 (factor 256)
+      const bool grow = tmax > m_ref + 8.0f;
+      float alpha = 1.0f;
+      if (grow) {
+        alpha = (m_ref == -INFINITY) ? 0.f : exp2f(m_ref - tmax);
+        m_ref = tmax;
+        l *= alpha;
+      }
+      if (it > 0) {
+        mbar_wait(pv_done, (it - 1) & 1);               // P smem free again, O accumulator up to date
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, grow)) {
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t ov[32];
+            tmem_ld_32x32b_x32(tmem_o + c * 32, ov);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) ov[j] = __float_as_uint(__uint_as_float(ov[j]) * alpha);
+            tmem_st_32x32b_x32(tmem_o + c * 32, ov);
+          }
+          tmem_st_wait();
+        }
+      }
+      const float m_use = (m_ref == -INFINITY) ? 0.f : m_ref;
+      float rs = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+#pragma unroll
+        for (int j8 = 0; j8 < 4; ++j8) {
+          float p[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            p[j] = exp2f(__uint_as_float(sv[c][j8 * 8 + j]) - m_use);
+            rs += p[j];
+          }
+          uint4 pk;
+          pk.x = pack_bf16x2(p[0], p[1]);
+          pk.y = pack_bf16x2(p[2], p[3]);
+          pk.z = pack_bf16x2(p[4], p[5]);
+          pk.w = pack_bf16x2(p[6], p[7]);
+          // K-major SW128: key column kc = c*32 + j8*8 -> atom kc/64, 16-byte chunk (kc%64)/8 XOR (row%8)
+          const int kc = c * 32 + j8 * 8;
+          const int chunk = ((kc & 63) >> 3) ^ (r & 7);
+          *reinterpret_cast<uint4*>(sP + (kc >> 6) * ATOM_BYTES + r * 128 + chunk * 16) = pk;
+        }
+      }
+      l += rs;
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(p_full);
+    }
+    // ---- epilogue ----
+    if (ntiles > 0) {
+      mbar_wait(pv_done, (ntiles - 1) & 1);
+      tc_fence_after();
+    }
+    const float inv = l > 0.f ? 1.f / l : 0.f;
+    if (valid && LSE2) LSE2[(long long)h * T + my_row] = l > 0.f ? m_ref + log2f(l) : -INFINITY;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t ov[32];
+      if (ntiles > 0) {
+        tmem_ld_32x32b_x32(tmem_o + c * 32, ov);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) ov[j] = 0;
+      }
+      if (valid) {
+        bf16* op = O + (long long)my_row * ldo + (long long)h * HD + c * 32;
+#pragma unroll
+        for (int j8 = 0; j8 < 4; ++j8) {
+          uint4 pk;
+          pk.x = pack_bf16x2(__uint_as_float(ov[j8 * 8 + 0]) * inv, __uint_as_float(ov[j8 * 8 + 1]) * inv);
+          pk.y = pack_bf16x2(__uint_as_float(ov[j8 * 8 + 2]) * inv, __uint_as_float(ov[j8 * 8 + 3]) * inv);
+          pk.z = pack_bf16x2(__uint_as_float(ov[j8 * 8 + 4]) * inv, __uint_as_float(ov[j8 * 8 + 5]) * inv);
+          pk.w = pack_bf16x2(__uint_as_float(ov[j8 * 8 + 6]) * inv, __uint_as_float(ov[j8 * 8 + 7]) * inv);
+          *reinterpret_cast<uint4*>(op + j8 * 8) = pk;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace
+
+// Same contract as t1_attn_fwd, head_dim == 128 only; Q/K/V token strides must be multiples of 8 and the head
+// column offsets multiples of 64 (true for the fused qkv layout).
+extern "C" int t1_attn_fwd_tc(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv,
+                              void* O, long long ldo, float* LSE2, const int* row_lo, const int* row_hi, int shared_len,
+                              int T, int Tk, int Hq, int Hkv, int head_dim, float scale, cudaStream_t stream) {
+  if (T == 0) return T1_OK;
+  T1_CHECK_ARG(head_dim == 128, "t1_attn_fwd_tc: head_dim must be 128 (got %d)", head_dim);
+  T1_CHECK_ARG(Q && K && V && O && row_lo && row_hi, "t1_attn_fwd_tc: null pointer");
+  T1_CHECK_ARG(Hkv > 0 && Hq % Hkv == 0, "t1_attn_fwd_tc: Hq=%d must be a multiple of Hkv=%d", Hq, Hkv);
+  T1_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0, "t1_attn_fwd_tc: strides must be multiples of 8");
+  T1_CHECK_ARG((((uintptr_t)Q | (uintptr_t)K | (uintptr_t)V | (uintptr_t)O) & 15) == 0, "t1_attn_fwd_tc: 16-byte alignment required");
+  CUtensorMap tq, tk, tv;
+  int rc = t1_make_tmap_bf16(&tq, Q, T, (long long)Hq * HD, ldq, TQ, 64);
+  if (rc) return rc;
+  rc = t1_make_tmap_bf16(&tk, K, Tk, (long long)Hkv * HD, ldk, TK, 64);
+  if (rc) return rc;
+  rc = t1_make_tmap_bf16(&tv, V, Tk, (long long)Hkv * HD, ldv, TK, 64);
+  if (rc) return rc;
+  static bool set = false;
+  static uint32_t lbo = ATOM_BYTES, sbo = 1024;
+  if (!set) {
+    cudaError_t e = cudaFuncSetAttribute(fa_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_TC_SMEM);
+    if (e != cudaSuccess) {
+      t1_set_error("t1_attn_fwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return T1_ERR_CUDA;
+    }
+    if (getenv("T1_FA_LBO")) lbo = (uint32_t)atoi(getenv("T1_FA_LBO"));   // descriptor bring-up hooks
+    if (getenv("T1_FA_SBO")) sbo = (uint32_t)atoi(getenv("T1_FA_SBO"));
+    set = true;
+  }
+  dim3 grid((T + TQ - 1) / TQ, Hq);
+  fa_fwd_tc_kernel<<<grid, FA_TC_THREADS, FA_TC_SMEM, stream>>>(tq, tk, tv, (bf16*)O, ldo, LSE2, row_lo, row_hi, shared_len,
+                                                               T, Hq / Hkv, scale * 1.4426950408889634f, lbo, sbo);
+  T1_CUDA_LAUNCH_CHECK("t1_attn_fwd_tc");
+  return T1_OK;
+}

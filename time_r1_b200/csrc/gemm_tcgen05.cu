@@ -220,45 +220,6 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   }
 }
 
-// ---- host: tensor-map construction through the driver entry point (no -lcuda link dependency) ----
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
-
-// Row-major bf16 [rows, cols] with leading dimension ld (elements); box = box_rows x 64 columns.
-int make_tmap_bf16(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int box_rows) {
-  EncodeTiledFn enc = get_encode_fn();
-  if (!enc) {
-    t1_set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
-    return T1_ERR_CUDA;
-  }
-  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    t1_set_error("cuTensorMapEncodeTiled failed: CUresult %d (ptr %p rows %lld cols %lld ld %lld)", (int)r, ptr, rows,
-                 cols, ld);
-    return T1_ERR_CUDA;
-  }
-  return T1_OK;
-}
-
 }  // namespace
 
 // C-ABI: see include/timer1.h
@@ -272,9 +233,9 @@ extern "C" int t1_gemm_bf16_tn(const void* A, long long lda, const void* B, long
                "t1_gemm_bf16_tn: operands must be 16-byte aligned");
   T1_CHECK_ARG(lda >= K && ldb >= K && ldd >= N, "t1_gemm_bf16_tn: leading dimension smaller than row length");
   CUtensorMap ta, tb;
-  int rc = make_tmap_bf16(&ta, A, M, K, lda, BM);
+  int rc = t1_make_tmap_bf16(&ta, A, M, K, lda, BM, BK);
   if (rc) return rc;
-  rc = make_tmap_bf16(&tb, B, N, K, ldb, BN);
+  rc = t1_make_tmap_bf16(&tb, B, N, K, ldb, BN, BK);
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
