@@ -205,6 +205,33 @@ def test_attention_forward(kind, T, P, C, Hq, Hkv, hd):
     close(lse, lse_ref, 2e-2, 1e-3, "lse2")
 
 
+@pytest.mark.parametrize("kind,T,P,C,Hq,Hkv", [
+    ("causal", 128, 0, 0, 1, 1), ("causal", 333, 0, 0, 4, 2), ("packed", 531, 203, 41, 14, 2), ("packed", 1200, 700, 100, 7, 1),
+    ("window", 700, 0, 0, 2, 2),
+])
+def test_attention_forward_tcgen05(kind, T, P, C, Hq, Hkv):
+    """tcgen05/TMEM kernel vs the dense fp32 reference (same bound as the HMMA kernel)."""
+    from time_r1_b200 import ops
+
+    hd = 128
+    ld = (Hq + 2 * Hkv) * hd
+    qkv = rnd(T, ld, seed=T + 7)
+    q, k, v = qkv[:, :Hq * hd], qkv[:, Hq * hd:(Hq + Hkv) * hd], qkv[:, (Hq + Hkv) * hd:]
+    lo, hi, shared = make_mask(kind, T, P, C)
+    if kind == "packed":      # trailing padding rows see nothing
+        hi[-7:] = 0
+        lo[-7:] = 0
+    scale = hd ** -0.5
+    out, lse = ops.attn_fwd_tc(q, k, v, lo, hi, shared, Hq, Hkv, hd, scale)
+    ref = dense_attention(q.float().reshape(T, Hq, hd), k.float().reshape(T, Hkv, hd), v.float().reshape(T, Hkv, hd),
+                          lo, hi, shared, scale)
+    close(out.view(T, Hq, hd), ref, 2e-2, 2e-2, f"attn fwd tcgen05 {kind}")
+    out2, lse2 = ops.attn_fwd(q, k, v, lo, hi, shared, Hq, Hkv, hd, scale)
+    m = torch.isfinite(lse2)
+    close(lse[m], lse2[m], 1e-4, 1e-5, "lse2 tcgen05 vs hmma")
+    assert torch.isinf(lse[~m]).all()
+
+
 @pytest.mark.parametrize("kind,T,P,C,Hq,Hkv,hd", [
     ("causal", 200, 0, 0, 4, 2, 128), ("packed", 531, 203, 41, 14, 2, 128), ("packed", 300, 100, 50, 2, 1, 64),
     ("window", 300, 0, 0, 2, 2, 128),

@@ -7,7 +7,8 @@
 //   warp 1       MMA issuer   : S = Q K^T   (tcgen05.mma M128 N128 K16 x 8, both operands K-major) -> TMEM S[it & 1]
 //                               O += P V    (A = P from smem, K-major; B = V tile consumed in place as an MN-major
 //                               operand — no transpose) -> TMEM O
-//   warps 2..5   softmax      : thread = query row; tcgen05.ld S -> mask, scale, lazy-rescaled online softmax (the
+//   warps 2..17  softmax      : 4 threads per query row (32 key columns each, so every SM sub-partition has four
+//                               resident softmax warps); tcgen05.ld S -> mask, scale, lazy-rescaled online softmax (the
 //                               running max is only refreshed when it grows by > 8 in log2 units, so the O accumulator
 //                               in TMEM is rarely rescaled) -> P (bf16) written to smem in the UMMA K-major swizzle
 // S(it+1) is issued before softmax(it) finishes, so QK^T overlaps the exponentials.
@@ -22,8 +23,15 @@ constexpr int TK = 128;   // keys per tile
 constexpr int HD = 128;
 constexpr int ATOM_BYTES = 128 * 128;            // [128 rows x 64 bf16] box
 constexpr int TILE_BYTES = 2 * ATOM_BYTES;       // [128 x 128] bf16
-constexpr int FA_TC_THREADS = 192;
-constexpr int FA_TC_SMEM = TILE_BYTES /*Q*/ + 2 * TILE_BYTES /*K*/ + 2 * TILE_BYTES /*V*/ + TILE_BYTES /*P*/ + 1024 + 256;
+constexpr int NS = 4;                  // softmax threads per query row
+constexpr int FA_TC_THREADS = 64 + 128 * NS;   // TMA warp, MMA warp, 4*NS softmax warps
+constexpr int FA_TC_SMEM = TILE_BYTES /*Q*/ + 2 * TILE_BYTES /*K*/ + 2 * TILE_BYTES /*V*/ + TILE_BYTES /*P*/ + 1024 + 256 + 3 * NS * 128 * 4 /*row exchange*/;
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 struct Range {
   int tA_end, tB_start, tB_end;
@@ -44,13 +52,16 @@ fa_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   uint8_t* sP = sV + 2 * TILE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + TILE_BYTES);
   uint64_t* q_full = bars;                  // 1
-  uint64_t* kv_full = bars + 1;             // 2
-  uint64_t* kv_empty = bars + 3;            // 2
-  uint64_t* s_full = bars + 5;              // 2
-  uint64_t* p_full = bars + 7;              // 1 (128 arrivals)
-  uint64_t* pv_done = bars + 8;             // 1
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 9);
-  int* s_red = reinterpret_cast<int*>(bars + 10);  // 4 ints
+  uint64_t* k_full = bars + 1;              // 2
+  uint64_t* k_empty = bars + 3;             // 2  (released as soon as S = Q K^T of the tile retires)
+  uint64_t* v_full = bars + 5;              // 2
+  uint64_t* v_empty = bars + 7;             // 2  (released when O += P V retires)
+  uint64_t* s_full = bars + 9;              // 2
+  uint64_t* p_full = bars + 11;             // 1 (128 arrivals)
+  uint64_t* pv_done = bars + 12;            // 1
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 13);
+  int* s_red = reinterpret_cast<int*>(bars + 14);  // 4 ints
+  float* s_xch = reinterpret_cast<float*>(bars + 16);   // [3*NS][128] floats: per-row partial max (double buffered) and sum
 
   const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * TQ;
@@ -68,11 +79,13 @@ fa_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   if (warp_idx == 1 && lane == 0) {
     mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
       mbar_init(&s_full[i], 1);
     }
-    mbar_init(p_full, 128);
+    mbar_init(p_full, 128 * NS);
     mbar_init(pv_done, 1);
     mbar_fence_init();
   }
@@ -113,13 +126,15 @@ fa_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       tma_load_2d(sQ + ATOM_BYTES, &tm_q, q_full, h * HD + 64, q0);
       for (int it = 0; it < ntiles; ++it) {
         const int st = it & 1;
-        mbar_wait(&kv_empty[st], ((it >> 1) & 1) ^ 1);
         const int j0 = tr.tile(it) * TK;
-        mbar_arrive_expect_tx(&kv_full[st], 2 * TILE_BYTES);
-        tma_load_2d(sK + st * TILE_BYTES, &tm_k, &kv_full[st], hk * HD, j0);
-        tma_load_2d(sK + st * TILE_BYTES + ATOM_BYTES, &tm_k, &kv_full[st], hk * HD + 64, j0);
-        tma_load_2d(sV + st * TILE_BYTES, &tm_v, &kv_full[st], hk * HD, j0);
-        tma_load_2d(sV + st * TILE_BYTES + ATOM_BYTES, &tm_v, &kv_full[st], hk * HD + 64, j0);
+        mbar_wait(&k_empty[st], ((it >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&k_full[st], TILE_BYTES);
+        tma_load_2d(sK + st * TILE_BYTES, &tm_k, &k_full[st], hk * HD, j0);
+        tma_load_2d(sK + st * TILE_BYTES + ATOM_BYTES, &tm_k, &k_full[st], hk * HD + 64, j0);
+        mbar_wait(&v_empty[st], ((it >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&v_full[st], TILE_BYTES);
+        tma_load_2d(sV + st * TILE_BYTES, &tm_v, &v_full[st], hk * HD, j0);
+        tma_load_2d(sV + st * TILE_BYTES + ATOM_BYTES, &tm_v, &v_full[st], hk * HD + 64, j0);
       }
     }
   } else if (warp_idx == 1) {
@@ -130,7 +145,7 @@ fa_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       const uint32_t tmem_o = tmem_base + 256;
       auto issue_s = [&](int it) {
         const int st = it & 1;
-        mbar_wait(&kv_full[st], (it >> 1) & 1);
+        mbar_wait(&k_full[st], (it >> 1) & 1);
         tc_fence_after();
         const uint32_t tmem_s = tmem_base + (it & 1) * 128;
 #pragma unroll
@@ -139,56 +154,67 @@ fa_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           umma_bf16_ss(tmem_s, umma_desc_sw128_kmajor(smem_u32(sQ + off)),
                        umma_desc_sw128_kmajor(smem_u32(sK + st * TILE_BYTES + off)), idesc_s, ks != 0 ? 1u : 0u);
         }
+        umma_commit(&k_empty[st]);
         umma_commit(&s_full[it & 1]);
       };
       mbar_wait(q_full, 0);
       issue_s(0);
       for (int it = 0; it < ntiles; ++it) {
         if (it + 1 < ntiles) issue_s(it + 1);
+        const int st = it & 1;
+        mbar_wait(&v_full[st], (it >> 1) & 1);
         mbar_wait(p_full, it & 1);
         tc_fence_after();
-        const int st = it & 1;
 #pragma unroll
         for (int kk = 0; kk < TK / 16; ++kk) {
           const uint64_t a_desc = umma_desc_sw128_kmajor(smem_u32(sP + (kk >> 2) * ATOM_BYTES + (kk & 3) * 32));
           const uint64_t b_desc = umma_desc_sw128_mnmajor(smem_u32(sV + st * TILE_BYTES + kk * 16 * 128), v_lbo, v_sbo);
           umma_bf16_ss(tmem_o, a_desc, b_desc, idesc_pv, (it | kk) != 0 ? 1u : 0u);
         }
-        umma_commit(&kv_empty[st]);
+        umma_commit(&v_empty[st]);
         umma_commit(pv_done);
       }
     }
   } else {
-    // ===================== softmax warps (thread = query row) =====================
-    const int quad = warp_idx & 3;
+    // ===================== softmax warps: NS threads per query row, 128/NS key columns each =====================
+    constexpr int CW = TK / NS;                         // key columns (and output columns) per thread
+    constexpr int NCH = CW / 32;                        // 32-column TMEM chunks per thread
+    const int quad = warp_idx & 3;                      // TMEM lane quadrant this warp may touch
+    const int part = (warp_idx - 2) >> 2;               // which column slice
     const int r = quad * 32 + lane;                     // row inside the tile == TMEM lane
     const bool valid = my_row < T;
     const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
-    const uint32_t tmem_o = t_lane + 256;
+    const uint32_t tmem_o = t_lane + 256 + part * CW;
     float m_ref = -INFINITY, l = 0.f;
     for (int it = 0; it < ntiles; ++it) {
       const int j0 = tr.tile(it) * TK, j1 = j0 + TK;
       mbar_wait(&s_full[it & 1], (it >> 1) & 1);
       tc_fence_after();
-      uint32_t sv[4][32];
+      uint32_t sv[NCH][32];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32(t_lane + (it & 1) * 128 + c * 32, sv[c]);
+      for (int c = 0; c < NCH; ++c) tmem_ld_32x32b_x32(t_lane + (it & 1) * 128 + part * CW + c * 32, sv[c]);
       tmem_ld_wait();
       const bool need_mask = !(j1 <= min_hi && (j0 >= max_lo || j1 <= shared_len));
-      float tmax = -INFINITY;
+      float tmax = -INFINITY;   // raw (unscaled) scores; scale_log2 > 0 so max commutes with the scaling
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
+      for (int c = 0; c < NCH; ++c)
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          float v = __uint_as_float(sv[c][j]) * scale_log2;
+          float v = __uint_as_float(sv[c][j]);
           if (need_mask) {
-            const int key = j0 + c * 32 + j;
+            const int key = j0 + part * CW + c * 32 + j;
             const bool vis = valid && key < my_hi && (key >= my_lo || key < shared_len);
             v = vis ? v : -INFINITY;
+            sv[c][j] = __float_as_uint(v);
           }
-          sv[c][j] = __float_as_uint(v);
           tmax = fmaxf(tmax, v);
         }
+      // the NS threads of a row exchange their partial maxima (named barrier per TMEM quadrant, 32*NS threads)
+      s_xch[((it & 1) * NS + part) * TQ + r] = tmax;
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "n"(32 * NS) : "memory");
+#pragma unroll
+      for (int o = 0; o < NS; ++o) tmax = fmaxf(tmax, s_xch[((it & 1) * NS + o) * TQ + r]);
+      tmax *= scale_log2;
       // lazy rescale: refresh the reference max only when it grows by more than 8 (factor 256)
       const bool grow = tmax > m_ref + 8.0f;
       float alpha = 1.0f;
@@ -202,7 +228,7 @@ fa_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         tc_fence_after();
         if (__any_sync(0xffffffffu, grow)) {
 #pragma unroll 1
-          for (int c = 0; c < 4; ++c) {
+          for (int c = 0; c < NCH; ++c) {
             uint32_t ov[32];
             tmem_ld_32x32b_x32(tmem_o + c * 32, ov);
             tmem_ld_wait();
@@ -213,16 +239,16 @@ fa_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           tmem_st_wait();
         }
       }
-      const float m_use = (m_ref == -INFINITY) ? 0.f : m_ref;
+      const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
       float rs = 0.f;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < NCH; ++c) {
 #pragma unroll
         for (int j8 = 0; j8 < 4; ++j8) {
           float p[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            p[j] = exp2f(__uint_as_float(sv[c][j8 * 8 + j]) - m_use);
+            p[j] = ex2_approx(fmaf(__uint_as_float(sv[c][j8 * 8 + j]), scale_log2, neg_m));
             rs += p[j];
           }
           uint4 pk;
@@ -230,8 +256,8 @@ fa_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           pk.y = pack_bf16x2(p[2], p[3]);
           pk.z = pack_bf16x2(p[4], p[5]);
           pk.w = pack_bf16x2(p[6], p[7]);
-          // K-major SW128: key column kc = c*32 + j8*8 -> atom kc/64, 16-byte chunk (kc%64)/8 XOR (row%8)
-          const int kc = c * 32 + j8 * 8;
+          // K-major SW128: key column kc -> atom kc/64, 16-byte chunk (kc%64)/8 XOR (row%8)
+          const int kc = part * CW + c * 32 + j8 * 8;
           const int chunk = ((kc & 63) >> 3) ^ (r & 7);
           *reinterpret_cast<uint4*>(sP + (kc >> 6) * ATOM_BYTES + r * 128 + chunk * 16) = pk;
         }
@@ -241,15 +267,20 @@ fa_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       tc_fence_before();
       mbar_arrive(p_full);
     }
-    // ---- epilogue ----
+    // ---- epilogue: combine the partial row sums, normalise, store this thread's output columns ----
+    s_xch[(2 * NS + part) * TQ + r] = l;
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "n"(32 * NS) : "memory");
+    l = 0.f;
+#pragma unroll
+    for (int o = 0; o < NS; ++o) l += s_xch[(2 * NS + o) * TQ + r];
     if (ntiles > 0) {
       mbar_wait(pv_done, (ntiles - 1) & 1);
       tc_fence_after();
     }
     const float inv = l > 0.f ? 1.f / l : 0.f;
-    if (valid && LSE2) LSE2[(long long)h * T + my_row] = l > 0.f ? m_ref + log2f(l) : -INFINITY;
+    if (valid && LSE2 && part == 0) LSE2[(long long)h * T + my_row] = l > 0.f ? m_ref + log2f(l) : -INFINITY;
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < NCH; ++c) {
       uint32_t ov[32];
       if (ntiles > 0) {
         tmem_ld_32x32b_x32(tmem_o + c * 32, ov);
@@ -259,7 +290,7 @@ fa_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         for (int j = 0; j < 32; ++j) ov[j] = 0;
       }
       if (valid) {
-        bf16* op = O + (long long)my_row * ldo + (long long)h * HD + c * 32;
+        bf16* op = O + (long long)my_row * ldo + (long long)h * HD + part * CW + c * 32;
 #pragma unroll
         for (int j8 = 0; j8 < 4; ++j8) {
           uint4 pk;

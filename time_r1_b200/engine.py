@@ -198,6 +198,12 @@ class Engine:
         ops.scatter_rows(vision_embeds, vision_rows, x)                     # masked_scatter (HF :1309-1315)
         return x
 
+    @staticmethod
+    def _attn(q, k, v, lo, hi, shared, Hq, Hkv, hd, scale, out=None, lse=None, need_lse=True):
+        """LLM attention: tcgen05/TMEM kernel for head_dim 128, HMMA kernel otherwise (same contract)."""
+        fn = ops.attn_fwd_tc if hd == 128 else ops.attn_fwd
+        return fn(q, k, v, lo, hi, shared, Hq, Hkv, hd, scale, out=out, lse=lse, need_lse=need_lse)
+
     def llm_forward(self, x0, cos, sin, lo, hi, shared, wset="policy", ckpt=None, kv_out=None):
         """x0 [T, D] (consumed). Returns final-norm hidden states [T, D]. ckpt: list of L+1 [T, D] buffers receiving
         the residual stream at each layer input (+ final); kv_out: per-layer (K, V) caches receiving rows [0, T)."""
@@ -235,8 +241,8 @@ class Engine:
                 ops.copy_cols(qkv[:, qd + kd:], Vc, kd)
             else:
                 ops.rope_apply(qkv, 0, Hq + Hkv, hd, cos, sin)
-            ops.attn_fwd(qkv[:, :qd], qkv[:, qd:qd + kd], qkv[:, qd + kd:], lo, hi, shared, Hq, Hkv, hd, scale, out=attn,
-                         need_lse=False)
+            self._attn(qkv[:, :qd], qkv[:, qd:qd + kd], qkv[:, qd + kd:], lo, hi, shared, Hq, Hkv, hd, scale, out=attn,
+                       need_lse=False)
             ops.gemm(attn, self.p(pre + "self_attn.o_proj.weight", wset), out=o)
             if ckpt is not None:
                 ops.rmsnorm(x, self.p(pre + "post_attention_layernorm.weight", wset), eps, delta=o, out=h, x_out=xm)
@@ -568,7 +574,7 @@ class Engine:
             ops.gemm(h, Wqkv, out=qkv, bias=self.p(pre + "self_attn.qkv.bias"))
             ops.rope_apply(qkv, 0, Hq + Hkv, hd, st.cos, st.sin)
             q, k, v = qkv[:, :qd], qkv[:, qd:qd + kd], qkv[:, qd + kd:]
-            ops.attn_fwd(q, k, v, st.lo, st.hi, st.P, Hq, Hkv, hd, scale, out=attn, lse=lse2)
+            self._attn(q, k, v, st.lo, st.hi, st.P, Hq, Hkv, hd, scale, out=attn, lse=lse2)
             ops.gemm(attn, Wo, out=o)
             ops.rmsnorm(x_in, self.p(pre + "post_attention_layernorm.weight"), eps, delta=o, out=h2, x_out=xm)
             ops.gemm(h2, Wgu, out=gu)
