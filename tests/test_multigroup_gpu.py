@@ -46,3 +46,32 @@ def test_multi_group_rollout_matches_single_group_greedy_and_grads_accumulate():
     ref = g0 + g1
     err = (g_joint - ref).abs().max().item() / (ref.abs().max().item() + 1e-12)
     assert err < 2e-2, f"accumulated gradient differs from the sum of per-group gradients: {err}"
+
+
+def test_prefill_reuse_equals_full_policy_scoring():
+    """Policy scoring that reuses the rollout's prefill for the prompt rows must reproduce the full packed scoring pass
+    (log-probs, loss and gradients)."""
+    from time_r1_b200 import config, engine, weights
+
+    cfg = config.toy()
+    mw = weights.ModelWeights(cfg, "cuda")
+    mw.init_random(seed=4, std=0.05)
+    G, C = 4, 9
+    rng = np.random.default_rng(1)
+    grid = (2, 8, 12)
+    N = grid[0] * grid[1] * grid[2]
+    ids = np.array([5, 6, cfg.vision_start_token_id] + [cfg.video_token_id] * (N // 4) + [9] + list(rng.integers(10, 2000, 7)) + [7])
+    pix = torch.from_numpy(rng.standard_normal((N, cfg.patch_dim)).astype(np.float32)).cuda()
+    prompt = engine.Prompt(input_ids=ids, pixel_values=pix, grid_thw=[grid], second_per_grid_ts=[1.0])
+    rw = rng.random((G, 2)).astype(np.float32)
+    eng = engine.Engine(cfg, mw, config.RunConfig(num_generations=G, max_completion_length=C, beta=0.04, reuse_prefill=True))
+    out_r = eng.grpo_step(prompt, lambda c: rw, seed=3)                    # rollout + reuse path
+    g_r = eng.grads.buf.float().clone()
+    eng.grad_fresh = True
+    out_f = eng.grpo_step(prompt, lambda c: rw, completion_override=out_r["completion_ids"])   # full scoring path
+    g_f = eng.grads.buf.float().clone()
+    assert (out_r["logp"] - out_f["logp"]).abs().max().item() < 2e-2
+    assert abs(out_r["loss"].item() - out_f["loss"].item()) < 2e-3
+    err = (g_r - g_f).abs().max().item() / (g_f.abs().max().item() + 1e-12)
+    cos = torch.nn.functional.cosine_similarity(g_r, g_f, dim=0).item()
+    assert err < 3e-2 and cos > 0.999, (err, cos)

@@ -158,3 +158,4 @@ class RunConfig:
     ref_quirk_mrope: bool = True   # scoring pass omits second_per_grid_ts (timer1_trainer.py:601-607)
     seed: int = 42
     logit_chunk_rows: int = 2048
+    reuse_prefill: bool = True     # policy scoring reuses the rollout's prefill (same weights) for the prompt rows

@@ -42,8 +42,8 @@ struct Range {
 __global__ void __launch_bounds__(FA_TC_THREADS, 1)
 fa_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                  const __grid_constant__ CUtensorMap tm_v, bf16* __restrict__ O, long long ldo, float* __restrict__ LSE2,
-                 const int* __restrict__ row_lo, const int* __restrict__ row_hi, int shared_len, int T, int group,
-                 float scale_log2, uint32_t v_lbo, uint32_t v_sbo) {
+                 const int* __restrict__ row_lo, const int* __restrict__ row_hi, int shared_len, int T, int q_row0,
+                 int group, float scale_log2, uint32_t v_lbo, uint32_t v_sbo) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -64,7 +64,10 @@ fa_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   float* s_xch = reinterpret_cast<float*>(bars + 16);   // [3*NS][128] floats: per-row partial max (double buffered) and sum
 
   const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * TQ;
+  // Q / O / the tensor map of Q are LOCAL to the processed query rows [q_row0, T); row_lo / row_hi / LSE2 and the key
+  // axis use absolute packed-row indices (lets the scoring pass skip the prompt rows whose K/V come from the cache).
+  const int q0l = blockIdx.x * TQ;           // local row of this CTA's first query
+  const int q0 = q_row0 + q0l;               // absolute
   const int h = blockIdx.y, hk = h / group;
 
   // ---- tile range from the rows' (lo, hi): threads 64..191 (softmax warps) own one row each ----
@@ -122,8 +125,8 @@ fa_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     // ===================== TMA producer =====================
     if (lane == 0 && ntiles > 0) {
       mbar_arrive_expect_tx(q_full, TILE_BYTES);
-      tma_load_2d(sQ, &tm_q, q_full, h * HD, q0);
-      tma_load_2d(sQ + ATOM_BYTES, &tm_q, q_full, h * HD + 64, q0);
+      tma_load_2d(sQ, &tm_q, q_full, h * HD, q0l);
+      tma_load_2d(sQ + ATOM_BYTES, &tm_q, q_full, h * HD + 64, q0l);
       for (int it = 0; it < ntiles; ++it) {
         const int st = it & 1;
         const int j0 = tr.tile(it) * TK;
@@ -290,7 +293,7 @@ fa_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         for (int j = 0; j < 32; ++j) ov[j] = 0;
       }
       if (valid) {
-        bf16* op = O + (long long)my_row * ldo + (long long)h * HD + part * CW + c * 32;
+        bf16* op = O + (long long)(my_row - q_row0) * ldo + (long long)h * HD + part * CW + c * 32;
 #pragma unroll
         for (int j8 = 0; j8 < 4; ++j8) {
           uint4 pk;
@@ -313,19 +316,22 @@ fa_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 
 }  // namespace
 
-// Same contract as t1_attn_fwd, head_dim == 128 only; Q/K/V token strides must be multiples of 8 and the head
+// Same contract as t1_attn_fwd, head_dim == 128 only; additionally only query rows [q_row0, T) are processed and Q / O
+// point at row q_row0 (row_lo / row_hi / LSE2 / K / V keep absolute packed-row indexing); Q/K/V token strides must be multiples of 8 and the head
 // column offsets multiples of 64 (true for the fused qkv layout).
 extern "C" int t1_attn_fwd_tc(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv,
                               void* O, long long ldo, float* LSE2, const int* row_lo, const int* row_hi, int shared_len,
-                              int T, int Tk, int Hq, int Hkv, int head_dim, float scale, cudaStream_t stream) {
-  if (T == 0) return T1_OK;
+                              int T, int Tk, int Hq, int Hkv, int head_dim, float scale, int q_row0,
+                              cudaStream_t stream) {
+  if (T - q_row0 <= 0) return T1_OK;
+  T1_CHECK_ARG(q_row0 >= 0, "t1_attn_fwd_tc: q_row0 must be >= 0");
   T1_CHECK_ARG(head_dim == 128, "t1_attn_fwd_tc: head_dim must be 128 (got %d)", head_dim);
   T1_CHECK_ARG(Q && K && V && O && row_lo && row_hi, "t1_attn_fwd_tc: null pointer");
   T1_CHECK_ARG(Hkv > 0 && Hq % Hkv == 0, "t1_attn_fwd_tc: Hq=%d must be a multiple of Hkv=%d", Hq, Hkv);
   T1_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0, "t1_attn_fwd_tc: strides must be multiples of 8");
   T1_CHECK_ARG((((uintptr_t)Q | (uintptr_t)K | (uintptr_t)V | (uintptr_t)O) & 15) == 0, "t1_attn_fwd_tc: 16-byte alignment required");
   CUtensorMap tq, tk, tv;
-  int rc = t1_make_tmap_bf16(&tq, Q, T, (long long)Hq * HD, ldq, TQ, 64);
+  int rc = t1_make_tmap_bf16(&tq, Q, T - q_row0, (long long)Hq * HD, ldq, TQ, 64);
   if (rc) return rc;
   rc = t1_make_tmap_bf16(&tk, K, Tk, (long long)Hkv * HD, ldk, TK, 64);
   if (rc) return rc;
@@ -343,9 +349,9 @@ extern "C" int t1_attn_fwd_tc(const void* Q, long long ldq, const void* K, long 
     if (getenv("T1_FA_SBO")) sbo = (uint32_t)atoi(getenv("T1_FA_SBO"));
     set = true;
   }
-  dim3 grid((T + TQ - 1) / TQ, Hq);
+  dim3 grid((T - q_row0 + TQ - 1) / TQ, Hq);
   fa_fwd_tc_kernel<<<grid, FA_TC_THREADS, FA_TC_SMEM, stream>>>(tq, tk, tv, (bf16*)O, ldo, LSE2, row_lo, row_hi, shared_len,
-                                                               T, Hq / Hkv, scale * 1.4426950408889634f, lbo, sbo);
+                                                               T, q_row0, Hq / Hkv, scale * 1.4426950408889634f, lbo, sbo);
   T1_CUDA_LAUNCH_CHECK("t1_attn_fwd_tc");
   return T1_OK;
 }

@@ -222,13 +222,15 @@ class Engine:
         xm = torch.empty((T, D), device=self.dev, dtype=BF16) if ckpt is not None else None
         x = x0
         if ckpt is not None:
+            assert ckpt[0] is None or ckpt[0].data_ptr() == x0.data_ptr()
             ckpt[0] = x0
         for l in range(L):
             pre = f"model.layers.{l}."
             if l == 0:
                 ops.rmsnorm(x, self.p(pre + "input_layernorm.weight", wset), eps, out=h)
             elif ckpt is not None:
-                ckpt[l] = torch.empty((T, D), device=self.dev, dtype=BF16)
+                if ckpt[l] is None:
+                    ckpt[l] = torch.empty((T, D), device=self.dev, dtype=BF16)
                 ops.rmsnorm(xm, self.p(pre + "input_layernorm.weight", wset), eps, delta=down, out=h, x_out=ckpt[l])
                 x = ckpt[l]
             else:
@@ -253,10 +255,56 @@ class Engine:
             ops.gemm(act, self.p(pre + "mlp.down_proj.weight", wset), out=down)
         hN = torch.empty((T, D), device=self.dev, dtype=BF16)
         if ckpt is not None:
-            ckpt[L] = torch.empty((T, D), device=self.dev, dtype=BF16)
+            if ckpt[L] is None:
+                ckpt[L] = torch.empty((T, D), device=self.dev, dtype=BF16)
             ops.rmsnorm(xm, self.p("model.norm.weight", wset), eps, delta=down, out=hN, x_out=ckpt[L])
         else:
             ops.rmsnorm(x, self.p("model.norm.weight", wset), eps, delta=down, out=hN)
+        return hN
+
+    def llm_forward_suffix(self, ckpt_full, P, cos, sin, lo, hi, kv_prefix):
+        """Policy scoring of the completion rows only: rows [P, Tp) of the packed layout are computed, the prompt
+        rows' K/V (same weights, same positions) come from the rollout's prefill cache and their layer inputs are
+        already in ckpt_full[l][:P].  Fills ckpt_full[l][P:] and returns the final-norm hidden states of rows
+        [P, Tp).  Exactly the arithmetic of llm_forward(ckpt=...) restricted to the rows that are new."""
+        cfg = self.cfg
+        Tp, D = ckpt_full[0].shape
+        Tc = Tp - P
+        L, Hq, Hkv, hd, I = cfg.num_hidden_layers, cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim, cfg.intermediate_size
+        assert hd == 128, "prefix reuse needs the tcgen05 attention kernel (head_dim 128)"
+        qd, kd = Hq * hd, Hkv * hd
+        eps, scale = cfg.rms_norm_eps, hd ** -0.5
+        dev = self.dev
+        h = torch.empty((Tc, D), device=dev, dtype=BF16)
+        qkv = torch.empty((Tp, cfg.qkv_dim), device=dev, dtype=BF16)      # prompt rows: only the K/V columns are filled
+        attn = torch.empty((Tc, qd), device=dev, dtype=BF16)
+        o = torch.empty((Tc, D), device=dev, dtype=BF16)
+        gu = torch.empty((Tc, 2 * I), device=dev, dtype=BF16)
+        act = torch.empty((Tc, I), device=dev, dtype=BF16)
+        down = torch.empty((Tc, D), device=dev, dtype=BF16)
+        xm = torch.empty((Tc, D), device=dev, dtype=BF16)
+        cos_c, sin_c = cos[P:], sin[P:]
+        for l in range(L):
+            pre = f"model.layers.{l}."
+            x = ckpt_full[l][P:]
+            if l == 0:
+                ops.rmsnorm(x, self.p(pre + "input_layernorm.weight"), eps, out=h)
+            else:
+                ops.rmsnorm(xm, self.p(pre + "input_layernorm.weight"), eps, delta=down, out=h, x_out=x)
+            ops.gemm(h, self.p(pre + "self_attn.qkv.weight"), out=qkv[P:], bias=self.p(pre + "self_attn.qkv.bias"))
+            ops.rope_apply(qkv[P:], 0, Hq + Hkv, hd, cos_c, sin_c)
+            Kc, Vc = kv_prefix[l]
+            ops.copy_cols(Kc, qkv[:P, qd:qd + kd], kd)
+            ops.copy_cols(Vc, qkv[:P, qd + kd:], kd)
+            ops.attn_fwd_tc(qkv[P:, :qd], qkv[:, qd:qd + kd], qkv[:, qd + kd:], lo, hi, P, Hq, Hkv, hd, scale, out=attn,
+                            need_lse=False, q_row0=P)
+            ops.gemm(attn, self.p(pre + "self_attn.o_proj.weight"), out=o)
+            ops.rmsnorm(x, self.p(pre + "post_attention_layernorm.weight"), eps, delta=o, out=h, x_out=xm)
+            ops.gemm(h, self.p(pre + "mlp.gate_up.weight"), out=gu)
+            ops.swiglu(gu, out=act)
+            ops.gemm(act, self.p(pre + "mlp.down_proj.weight"), out=down)
+        hN = torch.empty((Tc, D), device=dev, dtype=BF16)
+        ops.rmsnorm(xm, self.p("model.norm.weight"), eps, delta=down, out=hN, x_out=ckpt_full[L][P:])
         return hN
 
     # ------------------------------------------------------------------------------------------
@@ -358,7 +406,8 @@ class Engine:
         return self.rollout_multi([prompt], [vision_embeds], G, C, temperature, top_k, seed, use_graph, check_every)[0]
 
     def rollout_multi(self, prompts: list, vision_embeds: list, G: int, C: int, temperature: float = 1.0,
-                      top_k: int = 50, seed: int = 0, use_graph: bool = True, check_every: int = 32) -> list:
+                      top_k: int = 50, seed: int = 0, use_graph: bool = True, check_every: int = 32,
+                      keep_prefill: bool = False) -> list:
         """Rollout for several prompt-groups at once (the micro-batches of one optimizer step see the same weights,
         so their decode streams can share every weight read). Returns one [G, C] int32 tensor per group."""
         cfg = self.cfg
@@ -376,11 +425,25 @@ class Engine:
             cos, sin = self._rope_tables(pos3)
             ids_dev = self._i32(ids)
             vis_rows = self._i32(np.nonzero(ids == cfg.video_token_id)[0])
-            x0 = self._embed(ids_dev, emb, vis_rows)
             lo = torch.zeros(P, device=self.dev, dtype=I32)
             hi = torch.arange(1, P + 1, device=self.dev, dtype=I32)
             kv_prefix = [(k[:P], v[:P]) for k, v in grp["kv"]]
-            hN = self.llm_forward(x0, cos, sin, lo, hi, 0, kv_out=kv_prefix)
+            ckpt = None
+            if keep_prefill:
+                # layer-input checkpoints of the packed scoring layout; the prefill fills the prompt rows now, the
+                # policy scoring pass fills the completion rows later (engine.score(reuse=...))
+                Tp = indexing.packed_rows(P, G, C)[0]
+                L = cfg.num_hidden_layers
+                ckpt_full = [torch.empty((Tp, cfg.hidden_size), device=self.dev, dtype=BF16) for _ in range(L + 1)]
+                ckpt = [c[:P] for c in ckpt_full]
+                x0 = ops.gather_rows(self.p("model.embed_tokens.weight"), ids_dev, out=ckpt[0])
+                ops.scatter_rows(emb, vis_rows, x0)
+            else:
+                x0 = self._embed(ids_dev, emb, vis_rows)
+            hN = self.llm_forward(x0, cos, sin, lo, hi, 0, ckpt=ckpt, kv_out=kv_prefix)
+            if keep_prefill:
+                grp["prefill"] = dict(ckpt_full=ckpt_full, h_last=hN[P - 1:P].clone(), kv_prefix=kv_prefix,
+                                      spg=None if prompt.second_per_grid_ts is None else list(prompt.second_per_grid_ts))
             logits0 = ops.skinny_gemm(hN[P - 1:P], self.lm_head(), out_dtype=F32)           # [1, V]
             # decode-position tables: completion token c sits at text position P + c + rope_delta on all three axes
             dpos = np.tile((P + delta + np.arange(C, dtype=np.int64))[None, :], (3, 1))
@@ -426,6 +489,7 @@ class Engine:
                     self._decode_step(st, G, temperature, top_k)
                     if (i + 1) % check_every == 0 and bool(st["finished"].all().item()):
                         break
+        self._last_decode_state = st
         return [st["out_ids"][gi * G:(gi + 1) * G].clone() for gi in range(len(prompts))]
 
     # ------------------------------------------------------------------------------------------
@@ -477,14 +541,26 @@ class Engine:
         return lp, ent, lse
 
     def score(self, prompt: Prompt, completion_ids: torch.Tensor, vision_embeds: torch.Tensor, wset: str = "policy",
-              save: bool = False, x_vit=None, plan=None):
+              save: bool = False, x_vit=None, plan=None, prefill=None):
         """Returns (logp [G, C], entropy [G, C], state-or-None)."""
         si = self._score_inputs(prompt, completion_ids)
         G, C, R = si["G"], si["C"], si["R"]
         cos, sin = self._rope_tables(si["pos"])
-        x0 = self._embed(si["ids_packed"], vision_embeds, si["vision_rows"])
-        ckpt = [None] * (self.cfg.num_hidden_layers + 1) if save else None
-        hN = self.llm_forward(x0, cos, sin, si["lo"], si["hi"], si["P"], wset=wset, ckpt=ckpt)
+        P = si["P"]
+        if prefill is not None:
+            # policy == rollout weights: the prompt rows were already computed by the rollout's prefill
+            assert wset == "policy" and save
+            ckpt = prefill["ckpt_full"]
+            assert ckpt[0].shape[0] == si["Tp"]
+            ops.gather_rows(self.p("model.embed_tokens.weight"), si["ids_packed"][P:], out=ckpt[0][P:])
+            hN_c = self.llm_forward_suffix(ckpt, P, cos, sin, si["lo"], si["hi"], prefill["kv_prefix"])
+            hN = torch.empty((si["Tp"], self.cfg.hidden_size), device=self.dev, dtype=BF16)
+            hN[P:] = hN_c
+            hN[P - 1:P] = prefill["h_last"]
+        else:
+            x0 = self._embed(si["ids_packed"], vision_embeds, si["vision_rows"])
+            ckpt = [None] * (self.cfg.num_hidden_layers + 1) if save else None
+            hN = self.llm_forward(x0, cos, sin, si["lo"], si["hi"], P, wset=wset, ckpt=ckpt)
         hsel = ops.gather_rows(hN, si["logit_rows"])
         lp, ent, lse = self._head_forward(hsel, si["targets"], wset)
         state = None
@@ -710,15 +786,25 @@ class Engine:
             emb = self.merger(x_vit, delta, plan, "policy")                 # x_vit now holds the final ViT stream
             vit.append((emb, x_vit, plan))
         mark("vit")
+        prefills = [None] * len(prompts)
         if completion_overrides is None:
-            comps = self.rollout_multi(prompts, [v[0] for v in vit], G, C, run.temperature, run.top_k, seed)
+            reuse = run.reuse_prefill and cfg.head_dim == 128
+            comps = self.rollout_multi(prompts, [v[0] for v in vit], G, C, run.temperature, run.top_k, seed, keep_prefill=reuse)
+            if reuse:
+                for gi, prompt in enumerate(prompts):
+                    pf = self._last_decode_state["groups"][gi].pop("prefill", None)
+                    # the scoring pass may use different temporal M-RoPE positions than the rollout (reference quirk,
+                    # timer1_trainer.py:601-607): reuse only when the prompt positions are identical
+                    same_pos = (not run.ref_quirk_mrope) or pf is None or pf["spg"] is None or all(float(v) == 1.0 for v in pf["spg"]) or not cfg.is_q25
+                    prefills[gi] = pf if same_pos else None
         else:
             comps = [c.to(device=self.dev, dtype=I32).contiguous() for c in completion_overrides]
         mark("rollout")
         outs = []
-        for prompt, reward_fn, comp, (emb, x_vit, plan) in zip(prompts, reward_fns, comps, vit):
+        for gi, (prompt, reward_fn, comp, (emb, x_vit, plan)) in enumerate(zip(prompts, reward_fns, comps, vit)):
             mask, lengths = ops.eos_mask(comp, cfg.eos_token_id)
-            logp, ent, st = self.score(prompt, comp, emb, "policy", save=True, x_vit=x_vit, plan=plan)
+            logp, ent, st = self.score(prompt, comp, emb, "policy", save=True, x_vit=x_vit, plan=plan, prefill=prefills[gi])
+            prefills[gi] = None
             mark("score_policy")
             ref_logp = None
             if run.beta != 0.0:

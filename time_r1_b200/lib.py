@@ -55,7 +55,7 @@ _SIGNATURES: dict[str, list] = {
     "t1_add_bf16": [vp, vp, i64, vp],
     # attention.cu
     "t1_attn_fwd": [vp, i64, vp, i64, vp, i64, vp, i64, vp, vp, vp, i32, i32, i32, i32, i32, i32, f32, vp],
-    "t1_attn_fwd_tc": [vp, i64, vp, i64, vp, i64, vp, i64, vp, vp, vp, i32, i32, i32, i32, i32, i32, f32, vp],
+    "t1_attn_fwd_tc": [vp, i64, vp, i64, vp, i64, vp, i64, vp, vp, vp, i32, i32, i32, i32, i32, i32, f32, i32, vp],
     "t1_attn_bwd": [vp, i64, vp, i64, vp, i64, vp, i64, vp, i64, vp, vp, vp, vp, i64, vp, i64, vp, i64, vp, vp,
                     i32, i32, i32, i32, i32, i32, f32, vp],
     # decode.cu

@@ -260,15 +260,19 @@ def attn_fwd(q, k, v, row_lo, row_hi, shared_len, Hq, Hkv, head_dim, scale, out=
     return out, lse
 
 
-def attn_fwd_tc(q, k, v, row_lo, row_hi, shared_len, Hq, Hkv, head_dim, scale, out=None, lse=None, need_lse=True):
-    """tcgen05/TMEM flash-attention forward (head_dim 128); same contract as attn_fwd."""
-    T, Tk = q.shape[0], k.shape[0]
+def attn_fwd_tc(q, k, v, row_lo, row_hi, shared_len, Hq, Hkv, head_dim, scale, out=None, lse=None, need_lse=True,
+                q_row0=0):
+    """tcgen05/TMEM flash-attention forward (head_dim 128); same contract as attn_fwd.  With q_row0 > 0 only the query
+    rows [q_row0, Tk) are processed and q / out hold just those rows (lo / hi / lse keep absolute row indices)."""
+    Tk = k.shape[0]
+    T = q.shape[0] + q_row0
     if out is None:
-        out = torch.empty((T, Hq * head_dim), device=q.device, dtype=BF16)
+        out = torch.empty((q.shape[0], Hq * head_dim), device=q.device, dtype=BF16)
     if lse is None and need_lse:
         lse = torch.empty((Hq, T), device=q.device, dtype=F32)
     call("t1_attn_fwd_tc", ptr(q), q.stride(0), ptr(k), k.stride(0), ptr(v), v.stride(0), ptr(out), out.stride(0),
-         ptr(lse), ptr(row_lo), ptr(row_hi), int(shared_len), T, Tk, Hq, Hkv, head_dim, float(scale), stream_ptr())
+         ptr(lse), ptr(row_lo), ptr(row_hi), int(shared_len), T, Tk, Hq, Hkv, head_dim, float(scale), int(q_row0),
+         stream_ptr())
     return out, lse
 
 
