@@ -54,6 +54,27 @@ int t1_gemm_bf16_tn(const void* A, long long lda, const void* B, long long ldb, 
 int t1_skinny_gemm(const void* x, long long ldx, const void* W, long long ldw, const void* bias, void* y,
                    long long ldy, int M, int N, int K, int out_f32, int accumulate, cudaStream_t stream);
 
+/* Same contract on the tensor core: y[M<=64, N] = x[M,K] * W[N,K]^T (+ bias bf16), y bf16 or fp32.  Stream-K over
+ * (128-row slab, 64-wide k-block) units, one contiguous range per SM; TMA -> shared-memory ring -> tcgen05.mma with
+ * the weight rows as the UMMA M dimension and the batch rows as N; deterministic last-arriver fix-up for slabs shared
+ * by several CTAs.  Under t1_set_pdl(1) the weight tiles are fetched BEFORE griddepcontrol.wait, so the stream of
+ * launch k+1 overlaps the tail of launch k and the latency-bound kernels between them.  K % 8 == 0.
+ * workspace: t1_stream_gemm_workspace_bytes(max M) bytes, zero-filled once by the caller, never shared by launches
+ * that may run concurrently. */
+long long t1_stream_gemm_workspace_bytes(int max_m);
+int t1_stream_gemm(const void* x, long long ldx, const void* W, long long ldw, const void* bias, void* y, long long ldy,
+                   int M, int N, int K, int out_f32, void* workspace, long long workspace_bytes, cudaStream_t stream);
+/* Tuning: shared-memory ring depth (0 = default, ~108 KB per CTA) and CTAs per SM (1 or 2) of later launches. */
+void t1_stream_gemm_tune(int stages, int ctas_per_sm);
+/* Diagnostics: CTA 0 of launch i writes 4 %globaltimer stamps {start, weight prefetch issued, dependency resolved,
+ * done} to buf[4*(i % slots)] (device memory, uint64); buf = NULL switches it off. */
+void t1_stream_gemm_debug(void* buf, int slots);
+/* Programmatic dependent launch switch for the decode chain (gather_rows, rmsnorm, stream_gemm, decode_*_groups,
+ * swiglu, sample, incr): while on, those entry points launch with
+ * cudaLaunchAttributeProgrammaticStreamSerialization; each of their kernels executes griddepcontrol.wait before
+ * touching memory a predecessor may own.  Process-wide, not thread-safe; default off. */
+void t1_set_pdl(int on);
+
 /* ---- attention ------------------------------------------------------------------------------------------ */
 /* Flash attention over a packed token axis.  Key j is visible to query row i iff
  *     j < row_hi[i] && (j >= row_lo[i] || j < shared_len).
@@ -91,6 +112,27 @@ int t1_decode_rope_append(void* qkv, long long ld, int B, int Hq, int Hkv, int h
 int t1_decode_attn(const void* q, long long ldq, const void* Kc, const void* Vc, int B, int Hq, int Hkv, int head_dim,
                    int prefix_len, int cpad, const int* step_ptr, float* ws_o, float* ws_ml, void* out, long long ldo,
                    float scale, cudaStream_t stream);
+/* Multi-group forms used by the captured decode step: ONE launch covers the n_groups x G sequences of all
+ * prompt-groups decoded together.  `groups` is a device array of n_groups t1_decode_group records (this layer's K/V
+ * caches, split-KV workspaces, decode-position rope tables and prompt length of each group); qkv / q / out rows are
+ * ordered group-major.  G * Hq/Hkv <= 64. */
+typedef struct t1_decode_group {
+  void* K;              /* [prefix_len + G*cpad, Hkv*hd] bf16 */
+  void* V;
+  float* ws_o;          /* n_chunks*Hkv*64*128 floats, n_chunks = ceil(prefix_len/128) + G*cpad/128 */
+  float* ws_ml;         /* n_chunks*Hkv*64*2 floats */
+  const float* cos_t;   /* [C, hd/2] */
+  const float* sin_t;
+  int prefix_len;
+  int reserved;
+} t1_decode_group;
+int t1_decode_rope_append_groups(void* qkv, long long ld, int n_groups, int G, int Hq, int Hkv, int head_dim,
+                                 const void* groups, const int* step_ptr, int cpad, cudaStream_t stream);
+/* fuse_rope != 0: q is the UN-rotated qkv buffer [n_groups*G, (Hq+2Hkv)*hd]; the kernel rotates q on load and the CTA
+ * that owns cache slot *step_ptr rotates k and appends k,v itself (no t1_decode_rope_append_groups launch needed). */
+int t1_decode_attn_groups(const void* q, long long ldq, const void* groups, int n_groups, int G, int Hq, int Hkv,
+                          int head_dim, int max_prefix_len, int cpad, const int* step_ptr, void* out, long long ldo,
+                          float scale, int fuse_rope, cudaStream_t stream);
 /* temperature -> top-k -> softmax -> multinomial (Philox4x32-10 keyed by seed, counter (row, step)); temperature <= 0
  * is greedy arg-max.  HF 4.51.1 generate defaults.  logits [B, V] fp32 (ld may be 0: shared row);
  * seed_ptr (device, nullable) overrides seed so captured graphs stay seed-independent; writes
@@ -98,6 +140,15 @@ int t1_decode_attn(const void* q, long long ldq, const void* Kc, const void* Vc,
 int t1_sample(const float* logits, long long ld, int B, int V, float temperature, int top_k, unsigned long long seed,
               const unsigned long long* seed_ptr, const int* step_ptr, int step_offset, const int* eos_ids, int n_eos,
               int pad_id, int* finished, int* out_ids, int out_ld, int* next_ids, float* out_u, cudaStream_t stream);
+/* Same contract, for greedy or 1 <= top_k <= 64 and V <= 262144: two short kernels instead of one CTA per row (the
+ * row is scanned in 4096-entry chunks by chunks x B CTAs that emit per-chunk top-k candidates; one CTA per row then
+ * selects the global top-k among them and draws).  Same Philox draw and index-ordered CDF walk as t1_sample.
+ * workspace: t1_sample_topk_workspace_bytes(B, V) bytes, 16-byte aligned. */
+long long t1_sample_topk_workspace_bytes(int B, int V);
+int t1_sample_topk(const float* logits, long long ld, int B, int V, float temperature, int top_k, unsigned long long seed,
+                   const unsigned long long* seed_ptr, const int* step_ptr, int step_offset, const int* eos_ids, int n_eos,
+                   int pad_id, int* finished, int* out_ids, int out_ld, int* next_ids, float* out_u, void* workspace,
+                   long long workspace_bytes, cudaStream_t stream);
 int t1_incr(int* p, int v, cudaStream_t stream);
 
 /* ---- token-wise kernels (all bf16 storage, fp32 math) ----------------------------------------------------- */

@@ -276,6 +276,130 @@ def test_skinny_gemm(M, N, K):
     close(acc, o2.float() + x.float() @ w.float().t(), 3e-2, 2e-2, "skinny accumulate")
 
 
+@pytest.mark.parametrize("pdl", [0, 1])
+@pytest.mark.parametrize("M,N,K", [(8, 4608, 3584), (16, 3584, 3584), (16, 512, 18944), (1, 200, 72), (17, 1000, 264),
+                                   (32, 2048, 512), (33, 640, 1024), (64, 37888, 512), (5, 128, 64), (16, 19200, 256)])
+def test_stream_gemm(M, N, K, pdl):
+    """Stream-K tcgen05 decode GEMM vs torch fp32 (covers slabs split across CTAs, ragged N / K tails, all MP variants),
+    launched twice on one workspace to check that the slab counters reset themselves; bit-identical reruns."""
+    from time_r1_b200 import lib, ops
+
+    x, w, b = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=0.05), rnd(N, seed=3)
+    ref = x.float() @ w.float().t() + b.float()
+    ws = ops.stream_gemm_workspace(M, DEV)
+    lib.load().t1_set_pdl(pdl)
+    try:
+        out = ops.stream_gemm(x, w, ws, bias=b, out_dtype=torch.float32)
+        o2 = ops.stream_gemm(x, w, ws, bias=b)
+        o3 = ops.stream_gemm(x, w, ws, bias=b, out_dtype=torch.float32)
+        nob = ops.stream_gemm(x, w, ws, out_dtype=torch.float32)
+    finally:
+        lib.load().t1_set_pdl(0)
+    close(out, ref, 2e-3 * math.sqrt(K) * 0.05, 1e-4, "stream fp32")
+    close(o2, ref, 1e-2, 1e-2, "stream bf16")
+    assert torch.equal(out, o3), "stream_gemm must be deterministic"
+    close(nob, ref - b.float(), 2e-3 * math.sqrt(K) * 0.05, 1e-4, "stream fp32 no bias")
+    assert int(ws[:65536].view(torch.int32).abs().sum().item()) == 0, "slab counters must be left at zero"
+
+
+def test_stream_gemm_chain_under_graph_with_pdl():
+    """A captured chain rmsnorm -> stream_gemm -> swiglu -> stream_gemm with programmatic dependent launch gives the
+    same result as the same chain launched eagerly without it (the weight prefetch must not outrun the dependency)."""
+    from time_r1_b200 import lib, ops
+
+    M, D, I = 16, 512, 1024
+    x0 = rnd(M, D, seed=1)
+    wn = rnd(D, seed=2).abs() + 0.5
+    w1, w2 = rnd(2 * I, D, seed=3, scale=0.05), rnd(D, I, seed=4, scale=0.05)
+    ws = ops.stream_gemm_workspace(M, DEV)
+    h, gu, act, y = torch.empty_like(x0), torch.empty(M, 2 * I, device=DEV, dtype=BF16), torch.empty(M, I, device=DEV, dtype=BF16), torch.empty_like(x0)
+    x = x0.clone()
+
+    def chain():
+        for _ in range(4):                      # y feeds back into x: every launch depends on the previous one
+            ops.rmsnorm(x, wn, 1e-6, delta=y, out=h)
+            ops.stream_gemm(h, w1, ws, out=gu)
+            ops.swiglu(gu, out=act)
+            ops.stream_gemm(act, w2, ws, out=y)
+
+    y.zero_()
+    chain()
+    torch.cuda.synchronize()
+    want_y, want_x = y.clone(), x.clone()
+    x.copy_(x0); y.zero_()
+    lib.load().t1_set_pdl(1)
+    try:
+        chain()                                 # eager with PDL
+        torch.cuda.synchronize()
+        assert torch.equal(y, want_y) and torch.equal(x, want_x)
+        x.copy_(x0); y.zero_()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            chain()
+    finally:
+        lib.load().t1_set_pdl(0)
+    x.copy_(x0); y.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(y, want_y) and torch.equal(x, want_x)
+
+
+def test_decode_groups_match_single_group_kernels():
+    """The grouped rope/append + attention launches (one launch for all prompt-groups) reproduce the per-group ones."""
+    import numpy as np
+    from time_r1_b200.lib import call, ptr, stream_ptr
+
+    G, Hq, Hkv, hd, cpad, step, C = 4, 14, 2, 128, 128, 9, 16
+    Ps = [300, 77, 513]
+    n = len(Ps)
+    ld = (Hq + 2 * Hkv) * hd
+    qkv = rnd(n * G, ld, seed=1)
+    st = torch.tensor([step], device=DEV, dtype=torch.int32)
+    scale = hd ** -0.5
+    groups, rec = [], np.zeros((n, 7), np.int64)
+    for gi, P in enumerate(Ps):
+        S = P + G * cpad
+        nch = (P + 127) // 128 + G * (cpad // 128)
+        d = dict(K=rnd(S, Hkv * hd, seed=10 + gi), V=rnd(S, Hkv * hd, seed=20 + gi), cos=torch.rand(C, hd // 2, device=DEV),
+                 sin=torch.rand(C, hd // 2, device=DEV), ws_o=torch.empty(nch * Hkv * 64 * 128, device=DEV),
+                 ws_ml=torch.empty(nch * Hkv * 64 * 2, device=DEV))
+        groups.append(d)
+        rec[gi] = (d["K"].data_ptr(), d["V"].data_ptr(), d["ws_o"].data_ptr(), d["ws_ml"].data_ptr(), d["cos"].data_ptr(),
+                   d["sin"].data_ptr(), P)
+    # reference: per-group kernels on clones
+    ref_qkv = qkv.clone()
+    ref_out = torch.empty(n * G, Hq * hd, device=DEV, dtype=BF16)
+    refK, refV = [g["K"].clone() for g in groups], [g["V"].clone() for g in groups]
+    for gi, P in enumerate(Ps):
+        rq = ref_qkv[gi * G:(gi + 1) * G]
+        call("t1_decode_rope_append", ptr(rq), ld, G, Hq, Hkv, hd, ptr(groups[gi]["cos"]), ptr(groups[gi]["sin"]), ptr(st),
+             ptr(refK[gi]), ptr(refV[gi]), P, cpad, stream_ptr())
+        wo, wm = torch.empty_like(groups[gi]["ws_o"]), torch.empty_like(groups[gi]["ws_ml"])
+        call("t1_decode_attn", ptr(rq), ld, ptr(refK[gi]), ptr(refV[gi]), G, Hq, Hkv, hd, P, cpad, ptr(st), ptr(wo), ptr(wm),
+             ptr(ref_out[gi * G:(gi + 1) * G]), ref_out.stride(0), scale, stream_ptr())
+    tab = torch.from_numpy(rec).to(DEV)
+    out = torch.empty_like(ref_out)
+    K0, V0 = [g["K"].clone() for g in groups], [g["V"].clone() for g in groups]
+    raw_qkv = qkv.clone()
+    call("t1_decode_rope_append_groups", ptr(qkv), ld, n, G, Hq, Hkv, hd, ptr(tab), ptr(st), cpad, stream_ptr())
+    call("t1_decode_attn_groups", ptr(qkv), ld, ptr(tab), n, G, Hq, Hkv, hd, max(Ps), cpad, ptr(st), ptr(out), out.stride(0),
+         scale, 0, stream_ptr())
+    assert torch.equal(qkv, ref_qkv)
+    for gi in range(n):
+        assert torch.equal(groups[gi]["K"], refK[gi]) and torch.equal(groups[gi]["V"], refV[gi])
+    assert torch.equal(out, ref_out)
+    # fused form: un-rotated qkv in, rope + append done inside the attention kernel
+    for gi in range(n):
+        groups[gi]["K"].copy_(K0[gi]); groups[gi]["V"].copy_(V0[gi])
+    out2 = torch.empty_like(ref_out)
+    call("t1_decode_attn_groups", ptr(raw_qkv), ld, ptr(tab), n, G, Hq, Hkv, hd, max(Ps), cpad, ptr(st), ptr(out2), out.stride(0),
+         scale, 1, stream_ptr())
+    for gi in range(n):
+        assert torch.equal(groups[gi]["K"], refK[gi]) and torch.equal(groups[gi]["V"], refV[gi])
+    assert torch.equal(out2, ref_out)
+
+
+
 @pytest.mark.parametrize("B,Hq,Hkv,P,step,cpad", [(8, 28, 4, 1000, 0, 256), (8, 28, 4, 517, 130, 256), (4, 12, 2, 250, 37, 128), (3, 2, 1, 64, 5, 128), (20, 28, 4, 300, 17, 128)])
 def test_decode_attention(B, Hq, Hkv, P, step, cpad):
     from time_r1_b200 import ops
@@ -328,10 +452,14 @@ def test_decode_rope_append():
     assert Kc.float().abs().sum(1).ne(0).sum().item() == B
 
 
-def test_sampler_topk_greedy_and_distribution():
+@pytest.mark.parametrize("entry", ["t1_sample", "t1_sample_topk"])
+def test_sampler_topk_greedy_and_distribution(entry):
+    from time_r1_b200 import lib
     from time_r1_b200.lib import call, ptr, stream_ptr
 
     B, V = 8, 152064
+    ws = torch.empty(int(lib.load().t1_sample_topk_workspace_bytes(B, V)), device=DEV, dtype=torch.uint8)
+    extra = (ptr(ws), ws.numel()) if entry == "t1_sample_topk" else ()
     logits = torch.randn(B, V, device=DEV, generator=torch.Generator(device=DEV).manual_seed(3)) * 3
     logits[0, 77] = 50.0
     out = torch.zeros(B, 4, device=DEV, dtype=torch.int32)
@@ -341,8 +469,8 @@ def test_sampler_topk_greedy_and_distribution():
     st = torch.tensor([1], device=DEV, dtype=torch.int32)
 
     def run(temp, k, seed, step_off=0):
-        call("t1_sample", ptr(logits), V, B, V, float(temp), k, seed, 0, ptr(st), step_off, ptr(eos), 2, 151643, ptr(fin),
-             ptr(out), 4, ptr(nxt), 0, stream_ptr())
+        call(entry, ptr(logits), V, B, V, float(temp), k, seed, 0, ptr(st), step_off, ptr(eos), 2, 151643, ptr(fin),
+             ptr(out), 4, ptr(nxt), 0, *extra, stream_ptr())
         torch.cuda.synchronize()
         return nxt.clone()
 
@@ -371,6 +499,36 @@ def test_sampler_topk_greedy_and_distribution():
     t = run(1.0, 50, 10)
     assert t[1].item() == 151643
     logits.copy_(logits2)
+
+
+def test_sampler_entry_points_agree():
+    """The chunked two-kernel sampler draws the same tokens as the one-CTA-per-row sampler (same Philox stream, same
+    index-ordered CDF walk); only float summation order differs, so allow a rare boundary flip."""
+    from time_r1_b200 import lib
+    from time_r1_b200.lib import call, ptr, stream_ptr
+
+    for B, V, k in [(16, 152064, 50), (5, 2048, 50), (3, 5000, 1), (8, 151936, 20)]:
+        logits = torch.randn(B, V, device=DEV, generator=torch.Generator(device=DEV).manual_seed(V)) * 2.5
+        ws = torch.empty(int(lib.load().t1_sample_topk_workspace_bytes(B, V)), device=DEV, dtype=torch.uint8)
+        eos = torch.tensor([V - 1], device=DEV, dtype=torch.int32)
+        st = torch.tensor([0], device=DEV, dtype=torch.int32)
+        same = total = 0
+        for seed in range(40):
+            res = []
+            for entry in ("t1_sample", "t1_sample_topk"):
+                nxt = torch.zeros(B, device=DEV, dtype=torch.int32)
+                out = torch.zeros(B, 2, device=DEV, dtype=torch.int32)
+                fin = torch.zeros(B, device=DEV, dtype=torch.int32)
+                u = torch.zeros(B, device=DEV)
+                extra = (ptr(ws), ws.numel()) if entry == "t1_sample_topk" else ()
+                call(entry, ptr(logits), V, B, V, 0.7 if seed % 4 else 0.0, k, seed, 0, ptr(st), 0, ptr(eos), 1, 0, ptr(fin), ptr(out), 2,
+                     ptr(nxt), ptr(u), *extra, stream_ptr())
+                res.append((nxt.clone(), u.clone()))
+            if seed % 4:
+                assert torch.equal(res[0][1], res[1][1]), "same uniform draw"
+            same += int((res[0][0] == res[1][0]).sum())
+            total += B
+        assert same >= total - max(1, total // 100), (B, V, k, same, total)
 
 
 # ------------------------------------------------------------------ GRPO kernels vs torch

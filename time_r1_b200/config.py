@@ -159,3 +159,7 @@ class RunConfig:
     seed: int = 42
     logit_chunk_rows: int = 2048
     reuse_prefill: bool = True     # policy scoring reuses the rollout's prefill (same weights) for the prompt rows
+    # decode step: "stream" = tcgen05 stream-K weight streaming + grouped attention launches chained with programmatic
+    # dependent launch; "legacy" = HMMA skinny GEMM + per-group attention on forked graph branches
+    decode_impl: str = "stream"
+    decode_pdl: bool = True

@@ -40,6 +40,11 @@ extern "C" unsigned long long t1_launch_count(int reset) {
   return v;
 }
 
+// Programmatic-dependent-launch switch (see t1_common.cuh): the host sets it around the decode step it captures.
+static int g_pdl = 0;
+extern "C" void t1_set_pdl(int on) { g_pdl = on ? 1 : 0; }
+int t1_pdl_enabled(void) { return g_pdl; }
+
 // ---- tensor-map construction through the driver entry point (no link-time dependency on libcuda) ----
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,

@@ -170,6 +170,54 @@ decode_rope_append_kernel(bf16* __restrict__ qkv, long long ld, int Hq, int Hkv,
   for (int e = threadIdx.x; e < Hkv * HD; e += blockDim.x) vd[e] = vsrc[e];
 }
 
+// Grouped variant for the PDL decode chain: one launch covers every sequence of every prompt-group; the per-group
+// pointers live in a device-resident table (struct t1_decode_group, include/timer1.h).
+struct DecodeGroup {
+  bf16* K;
+  bf16* V;
+  float* ws_o;
+  float* ws_ml;
+  const float* cos_t;
+  const float* sin_t;
+  int prefix_len;
+  int reserved;
+};
+static_assert(sizeof(DecodeGroup) == 56, "t1_decode_group layout");
+
+__global__ void __launch_bounds__(256)
+decode_rope_append_groups_kernel(bf16* __restrict__ qkv, long long ld, int G, int Hq, int Hkv, int HD,
+                                 const DecodeGroup* __restrict__ groups, const int* __restrict__ step_ptr, int cpad) {
+  pdl_trigger();
+  pdl_wait();
+  const int bg = blockIdx.x;
+  const int gi = bg / G, b = bg - gi * G;
+  const DecodeGroup grp = groups[gi];
+  const int step = *step_ptr;
+  const int half = HD >> 1;
+  const float* c = grp.cos_t + (long long)step * half;
+  const float* s = grp.sin_t + (long long)step * half;
+  bf16* row = qkv + (long long)bg * ld;
+  const long long slot = (long long)grp.prefix_len + (long long)b * cpad + step;
+  const int n_rot = (Hq + Hkv) * half;
+  for (int e = threadIdx.x; e < n_rot; e += blockDim.x) {
+    const int h = e / half, i = e - h * half;
+    bf16* p = row + h * HD + i;
+    const float a = __bfloat162float(p[0]), bb = __bfloat162float(p[half]);
+    const float ra = a * c[i] - bb * s[i], rb = bb * c[i] + a * s[i];
+    const bf16 oa = __float2bfloat16(ra), ob = __float2bfloat16(rb);
+    p[0] = oa;
+    p[half] = ob;
+    if (h >= Hq) {
+      bf16* kd = grp.K + slot * (Hkv * HD) + (h - Hq) * HD + i;
+      kd[0] = oa;
+      kd[half] = ob;
+    }
+  }
+  const bf16* vsrc = row + (Hq + Hkv) * HD;
+  bf16* vd = grp.V + slot * (Hkv * HD);
+  for (int e = threadIdx.x; e < Hkv * HD; e += blockDim.x) vd[e] = vsrc[e];
+}
+
 // =============================================================================================
 // decode attention (HD = 128): grid (n_chunks, Hkv, row_tiles); 128 threads; 128 keys per CTA.
 // Key slot j: j < prefix_len -> prompt key (visible to every row); otherwise seq = (j-P)/cpad, c = (j-P)%cpad,
@@ -178,19 +226,44 @@ decode_rope_append_kernel(bf16* __restrict__ qkv, long long ld, int Hq, int Hkv,
 constexpr int DA_KEYS = 128;
 constexpr int DA_LDS = 128 + 8;
 
+// With `groups` != nullptr the launch covers several prompt-groups: blockIdx.z = group (one 64-row tile per group),
+// and q / Kc / Vc / prefix_len / workspaces come from the group table.
 __global__ void __launch_bounds__(128)
 decode_attn_kernel(const bf16* __restrict__ q, long long ldq, const bf16* __restrict__ Kc, const bf16* __restrict__ Vc,
                    int Hq, int Hkv, int B, int prefix_len, int cpad, const int* __restrict__ step_ptr,
                    float* __restrict__ ws_o, float* __restrict__ ws_ml, int n_prefix_chunks, int rows_pad,
-                   float scale_log2) {
+                   float scale_log2, const DecodeGroup* __restrict__ groups, int fuse_rope) {
   constexpr int HD = 128, LDS = DA_LDS;
+  pdl_trigger();
+  pdl_wait();
+  int rt_override = -1;
+  const float* rope_cos = nullptr;
+  const float* rope_sin = nullptr;
+  bf16* Kw = nullptr;
+  bf16* Vw = nullptr;
+  if (groups) {
+    const DecodeGroup grp = groups[blockIdx.z];
+    rope_cos = grp.cos_t;
+    rope_sin = grp.sin_t;
+    Kw = grp.K;
+    Vw = grp.V;
+    q += (long long)blockIdx.z * B * ldq;
+    Kc = grp.K;
+    Vc = grp.V;
+    ws_o = grp.ws_o;
+    ws_ml = grp.ws_ml;
+    prefix_len = grp.prefix_len;
+    n_prefix_chunks = (prefix_len + DA_KEYS - 1) / DA_KEYS;
+    if ((int)blockIdx.x >= n_prefix_chunks + B * (cpad / DA_KEYS)) return;
+    rt_override = 0;
+  }
   extern __shared__ __align__(16) uint8_t da_smem[];
   bf16* sQ = reinterpret_cast<bf16*>(da_smem);   // 64 x LDS
   bf16* sK = sQ + 64 * LDS;                      // 128 x LDS
   bf16* sV = sK + DA_KEYS * LDS;                 // 128 x LDS
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t4 = lane & 3;
-  const int chunk = blockIdx.x, hk = blockIdx.y, rt = blockIdx.z;
+  const int chunk = blockIdx.x, hk = blockIdx.y, rt = rt_override >= 0 ? rt_override : (int)blockIdx.z;
   const int ratio = Hq / Hkv;
   const int n_rows = B * ratio;
   const int step = *step_ptr;
@@ -242,8 +315,48 @@ decode_attn_kernel(const bf16* __restrict__ q, long long ldq, const bf16* __rest
     }
     cp_async_commit();
   }
-  cp_async_wait<1>();
-  __syncthreads();
+  if (fuse_rope) {
+    // q arrives un-rotated (q points at the qkv rows of this group); this step's k/v row of the chunk's sequence is
+    // still in the qkv buffer: rotate q in shared memory, and let the CTA that owns slot `step` rotate k, patch its
+    // shared-memory tiles and append the row to the global cache (what t1_decode_rope_append does as a separate launch).
+    cp_async_wait<0>();
+    __syncthreads();
+    const float* cs = rope_cos + (long long)step * (HD / 2);
+    const float* sn = rope_sin + (long long)step * (HD / 2);
+    for (int e = tid; e < 64 * (HD / 2); e += 128) {
+      const int r = e / (HD / 2), i = e - r * (HD / 2);
+      if (rt * 64 + r < n_rows) {
+        bf16* pq = sQ + r * LDS + i;
+        const float a = __bfloat162float(pq[0]), bb = __bfloat162float(pq[HD / 2]);
+        pq[0] = __float2bfloat16(a * cs[i] - bb * sn[i]);
+        pq[HD / 2] = __float2bfloat16(bb * cs[i] + a * sn[i]);
+      }
+    }
+    const int lr = step - (j0 - prefix_len - chunk_seq * cpad);   // row of slot `step` inside this chunk
+    if (chunk_seq >= 0 && lr >= 0 && lr < DA_KEYS) {
+      const bf16* src = q + (long long)chunk_seq * ldq;
+      const long long slot = (long long)j0 + lr;
+      if (tid < HD / 2) {
+        const bf16* pk = src + (long long)(Hq + hk) * HD + tid;
+        const float a = __bfloat162float(pk[0]), bb = __bfloat162float(pk[HD / 2]);
+        const bf16 oa = __float2bfloat16(a * cs[tid] - bb * sn[tid]), ob = __float2bfloat16(bb * cs[tid] + a * sn[tid]);
+        sK[lr * LDS + tid] = oa;
+        sK[lr * LDS + tid + HD / 2] = ob;
+        bf16* kd = Kw + (slot * Hkv + hk) * HD + tid;
+        kd[0] = oa;
+        kd[HD / 2] = ob;
+      } else {
+        const int j = (tid - HD / 2) * 2;
+        const __nv_bfloat162 vv = *reinterpret_cast<const __nv_bfloat162*>(src + (long long)(Hq + Hkv + hk) * HD + j);
+        *reinterpret_cast<__nv_bfloat162*>(sV + lr * LDS + j) = vv;
+        *reinterpret_cast<__nv_bfloat162*>(Vw + (slot * Hkv + hk) * HD + j) = vv;
+      }
+    }
+    __syncthreads();
+  } else {
+    cp_async_wait<1>();
+    __syncthreads();
+  }
 
   uint32_t qf[8][4];
 #pragma unroll
@@ -255,6 +368,8 @@ decode_attn_kernel(const bf16* __restrict__ q, long long ldq, const bf16* __rest
   for (int i = 0; i < 16; ++i) o_acc[i][0] = o_acc[i][1] = o_acc[i][2] = o_acc[i][3] = 0.f;
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
 
+  // a completion chunk belongs to ONE sequence: warps whose 16 query rows hold none of its heads have nothing to do
+  const bool warp_active = chunk_seq < 0 || (chunk_seq * ratio < rt * 64 + warp * 16 + 16 && (chunk_seq + 1) * ratio > rt * 64 + warp * 16);
 #pragma unroll 1
   for (int kt = 0; kt < DA_KEYS / 64; ++kt) {
     if (kt * 64 >= nvalid) break;
@@ -262,6 +377,7 @@ decode_attn_kernel(const bf16* __restrict__ q, long long ldq, const bf16* __rest
       cp_async_wait<0>();
       __syncthreads();
     }
+    if (!warp_active) continue;
     const bf16* kb = sK + kt * 64 * LDS;
     const bf16* vb = sV + kt * 64 * LDS;
     float s[8][4];
@@ -332,13 +448,15 @@ decode_attn_kernel(const bf16* __restrict__ q, long long ldq, const bf16* __rest
   l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
   l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
   l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-  // un-normalised partials
+  // un-normalised partials (rows with l == 0 are never read by the combine kernel)
   float* oa = ws_o + (ws_row0 + warp * 16 + g) * HD;
   float* ob = ws_o + (ws_row0 + warp * 16 + g + 8) * HD;
+  if (warp_active) {
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    *reinterpret_cast<float2*>(oa + i * 8 + t4 * 2) = make_float2(o_acc[i][0], o_acc[i][1]);
-    *reinterpret_cast<float2*>(ob + i * 8 + t4 * 2) = make_float2(o_acc[i][2], o_acc[i][3]);
+    for (int i = 0; i < 16; ++i) {
+      *reinterpret_cast<float2*>(oa + i * 8 + t4 * 2) = make_float2(o_acc[i][0], o_acc[i][1]);
+      *reinterpret_cast<float2*>(ob + i * 8 + t4 * 2) = make_float2(o_acc[i][2], o_acc[i][3]);
+    }
   }
   if (t4 == 0) {
     ws_ml[(ws_row0 + warp * 16 + g) * 2] = m0;
@@ -354,10 +472,22 @@ decode_attn_kernel(const bf16* __restrict__ q, long long ldq, const bf16* __rest
 __global__ void __launch_bounds__(256)
 decode_attn_combine_kernel(const float* __restrict__ ws_o, const float* __restrict__ ws_ml, int n_chunks,
                            int n_prefix_chunks, int chunks_per_seq, int Hq, int Hkv, int rows_pad,
-                           bf16* __restrict__ out, long long ldo) {
+                           bf16* __restrict__ out, long long ldo, const DecodeGroup* __restrict__ groups, int G) {
   __shared__ float s_m[8], s_l[8];
   __shared__ float4 s_acc[8][32];
-  const int b = blockIdx.x / Hq, hq = blockIdx.x % Hq;
+  pdl_trigger();
+  pdl_wait();
+  int b = blockIdx.x / Hq;
+  const int hq = blockIdx.x % Hq;
+  if (groups) {
+    const int gi = b / G;
+    const DecodeGroup grp = groups[gi];
+    out += (long long)gi * G * ldo;
+    b -= gi * G;
+    ws_o = grp.ws_o;
+    ws_ml = grp.ws_ml;
+    n_prefix_chunks = (grp.prefix_len + DA_KEYS - 1) / DA_KEYS;
+  }
   const int ratio = Hq / Hkv, hk = hq / ratio;
   const int row = b * ratio + (hq - hk * ratio);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -434,29 +564,6 @@ decode_attn_combine_kernel(const float* __restrict__ ws_o, const float* __restri
 // =============================================================================================
 // sampler: one CTA per sequence.
 // =============================================================================================
-__device__ __forceinline__ uint32_t float_key(float x) {
-  const uint32_t u = __float_as_uint(x);
-  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-__device__ __forceinline__ uint32_t mulhilo(uint32_t a, uint32_t b, uint32_t* hi) {
-  const unsigned long long p = (unsigned long long)a * b;
-  *hi = (uint32_t)(p >> 32);
-  return (uint32_t)p;
-}
-// Philox4x32-10 (Salmon et al. 2011), returns 4 uniform 32-bit words for (counter, key).
-__device__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    uint32_t hi0, hi1;
-    const uint32_t lo0 = mulhilo(0xD2511F53u, c[0], &hi0);
-    const uint32_t lo1 = mulhilo(0xCD9E8D57u, c[2], &hi1);
-    const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
-    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
-    k0 += 0x9E3779B9u;
-    k1 += 0xBB67AE85u;
-  }
-}
-
 __global__ void __launch_bounds__(1024, 1)
 sample_kernel(const float* __restrict__ logits, long long ld, int V, float temperature, int top_k,
               unsigned long long seed_in, const unsigned long long* __restrict__ seed_ptr,
@@ -469,6 +576,8 @@ sample_kernel(const float* __restrict__ logits, long long ld, int V, float tempe
   __shared__ unsigned int s_prefix, s_krem;
   __shared__ unsigned long long s_best;
   __shared__ int s_tok;
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x, tid = threadIdx.x;
   const int step = (step_ptr ? *step_ptr : 0) + step_offset;
   const unsigned long long seed = seed_ptr ? *seed_ptr : seed_in;  // device-resident seed keeps CUDA graphs reusable
@@ -612,6 +721,8 @@ sample_kernel(const float* __restrict__ logits, long long ld, int V, float tempe
 }
 
 __global__ void incr_kernel(int* p, int v) {
+  pdl_trigger();
+  pdl_wait();
   if (threadIdx.x == 0 && blockIdx.x == 0) *p += v;
 }
 
@@ -668,11 +779,58 @@ extern "C" int t1_decode_attn(const void* q, long long ldq, const void* Kc, cons
   dim3 grid(n_chunks, Hkv, row_tiles);
   decode_attn_kernel<<<grid, 128, SMEM, stream>>>((const bf16*)q, ldq, (const bf16*)Kc, (const bf16*)Vc, Hq, Hkv, B,
                                                   prefix_len, cpad, step_ptr, ws_o, ws_ml, n_prefix_chunks, rows_pad,
-                                                  scale * 1.4426950408889634f);
+                                                  scale * 1.4426950408889634f, nullptr, 0);
   T1_CUDA_LAUNCH_CHECK("t1_decode_attn");
   decode_attn_combine_kernel<<<B * Hq, 256, 0, stream>>>(ws_o, ws_ml, n_chunks, n_prefix_chunks, chunks_per_seq, Hq, Hkv,
-                                                        rows_pad, (bf16*)out, ldo);
+                                                        rows_pad, (bf16*)out, ldo, nullptr, 0);
   T1_CUDA_LAUNCH_CHECK("t1_decode_attn.combine");
+  return T1_OK;
+}
+
+// ---- grouped decode entry points (one launch for all prompt-groups; PDL-aware) ----
+extern "C" int t1_decode_rope_append_groups(void* qkv, long long ld, int n_groups, int G, int Hq, int Hkv, int head_dim,
+                                            const void* groups, const int* step_ptr, int cpad, cudaStream_t stream) {
+  T1_CHECK_ARG(n_groups > 0 && G > 0 && head_dim % 2 == 0 && groups, "t1_decode_rope_append_groups: bad arguments");
+  cudaError_t e = t1_launch(decode_rope_append_groups_kernel, dim3(n_groups * G), dim3(256), 0, stream, (bf16*)qkv, ld, G,
+                            Hq, Hkv, head_dim, (const DecodeGroup*)groups, step_ptr, cpad);
+  if (e != cudaSuccess) {
+    t1_set_error("t1_decode_rope_append_groups: launch failed: %s", cudaGetErrorString(e));
+    return T1_ERR_CUDA;
+  }
+  t1_count_launch();
+  return T1_OK;
+}
+
+// Each group's workspaces: ws_o = n_chunks*Hkv*64*128 floats, ws_ml = n_chunks*Hkv*64*2 floats with
+// n_chunks = ceil(prefix_len/128) + G*cpad/128; G*Hq/Hkv <= 64 query rows per KV head.
+extern "C" int t1_decode_attn_groups(const void* q, long long ldq, const void* groups, int n_groups, int G, int Hq,
+                                     int Hkv, int head_dim, int max_prefix_len, int cpad, const int* step_ptr, void* out,
+                                     long long ldo, float scale, int fuse_rope, cudaStream_t stream) {
+  T1_CHECK_ARG(head_dim == 128, "t1_decode_attn_groups: head_dim must be 128 (got %d)", head_dim);
+  T1_CHECK_ARG(cpad % DA_KEYS == 0 && cpad > 0, "t1_decode_attn_groups: cpad must be a positive multiple of %d", DA_KEYS);
+  T1_CHECK_ARG(n_groups > 0 && G > 0 && Hkv > 0 && Hq % Hkv == 0 && G * (Hq / Hkv) <= 64,
+               "t1_decode_attn_groups: G * Hq/Hkv must be <= 64");
+  const int chunks_per_seq = cpad / DA_KEYS;
+  const int max_chunks = (max_prefix_len + DA_KEYS - 1) / DA_KEYS + G * chunks_per_seq;
+  constexpr int SMEM = (64 + 2 * DA_KEYS) * DA_LDS * 2;
+  static bool set = false;
+  if (!set) {
+    cudaFuncSetAttribute(decode_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    set = true;
+  }
+  cudaError_t e = t1_launch(decode_attn_kernel, dim3(max_chunks, Hkv, n_groups), dim3(128), (size_t)SMEM, stream,
+                            (const bf16*)q, ldq, (const bf16*)nullptr, (const bf16*)nullptr, Hq, Hkv, G, 0, cpad, step_ptr,
+                            (float*)nullptr, (float*)nullptr, 0, 64, scale * 1.4426950408889634f, (const DecodeGroup*)groups,
+                            fuse_rope ? 1 : 0);
+  if (e == cudaSuccess)
+    e = t1_launch(decode_attn_combine_kernel, dim3(n_groups * G * Hq), dim3(256), 0, stream, (const float*)nullptr,
+                  (const float*)nullptr, 0, 0, chunks_per_seq, Hq, Hkv, 64, (bf16*)out, ldo, (const DecodeGroup*)groups, G);
+  if (e != cudaSuccess) {
+    t1_set_error("t1_decode_attn_groups: launch failed: %s", cudaGetErrorString(e));
+    return T1_ERR_CUDA;
+  }
+  t1_count_launch();
+  t1_count_launch();
   return T1_OK;
 }
 
@@ -681,14 +839,22 @@ extern "C" int t1_sample(const float* logits, long long ld, int B, int V, float 
                          int step_offset, const int* eos_ids, int n_eos, int pad_id, int* finished, int* out_ids,
                          int out_ld, int* next_ids, float* out_u, cudaStream_t stream) {
   T1_CHECK_ARG(B > 0 && V > 0 && logits, "t1_sample: bad arguments");
-  sample_kernel<<<B, 1024, 0, stream>>>(logits, ld, V, temperature, top_k, seed, seed_ptr, step_ptr, step_offset, eos_ids, n_eos,
-                                        pad_id, finished, out_ids, out_ld, next_ids, out_u);
-  T1_CUDA_LAUNCH_CHECK("t1_sample");
+  cudaError_t le = t1_launch(sample_kernel, dim3(B), dim3(1024), 0, stream, logits, ld, V, temperature, top_k, seed, seed_ptr,
+                             step_ptr, step_offset, eos_ids, n_eos, pad_id, finished, out_ids, out_ld, next_ids, out_u);
+  if (le != cudaSuccess) {
+    t1_set_error("t1_sample: launch failed: %s", cudaGetErrorString(le));
+    return T1_ERR_CUDA;
+  }
+  t1_count_launch();
   return T1_OK;
 }
 
 extern "C" int t1_incr(int* p, int v, cudaStream_t stream) {
-  incr_kernel<<<1, 32, 0, stream>>>(p, v);
-  T1_CUDA_LAUNCH_CHECK("t1_incr");
+  cudaError_t le = t1_launch(incr_kernel, dim3(1), dim3(32), 0, stream, p, v);
+  if (le != cudaSuccess) {
+    t1_set_error("t1_incr: launch failed: %s", cudaGetErrorString(le));
+    return T1_ERR_CUDA;
+  }
+  t1_count_launch();
   return T1_OK;
 }

@@ -35,6 +35,8 @@ __global__ void __launch_bounds__(256)
 norm_fwd_kernel(const bf16* x, const bf16* __restrict__ delta, bf16* x_out, const bf16* __restrict__ w,
                 const bf16* __restrict__ b, bf16* __restrict__ y, int D, float eps) {
   __shared__ float red[33];
+  pdl_trigger();   // no-ops unless launched with the programmatic-serialization attribute (decode chain)
+  pdl_wait();
   const size_t row = blockIdx.x;
   const bf16* xr = x + row * D;
   const int nv = D >> 3;
@@ -240,6 +242,8 @@ __global__ void copy_cols_kernel(const bf16* __restrict__ src, long long lds, bf
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
 __global__ void swiglu_fwd_kernel(const bf16* __restrict__ gu, bf16* __restrict__ act, long long T, int I) {
+  pdl_trigger();
+  pdl_wait();
   const int vpr = I >> 3;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= T * vpr) return;
@@ -315,6 +319,8 @@ __global__ void act_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restri
 // ---------------------------------------------------------------------------------------------
 __global__ void gather_rows_kernel(const bf16* __restrict__ src, long long lds, const int* __restrict__ idx,
                                    bf16* __restrict__ dst, long long ldd, int n, int width) {
+  pdl_trigger();
+  pdl_wait();
   const int vpr = width >> 3;
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= (long long)n * vpr) return;
@@ -439,7 +445,11 @@ extern "C" int t1_rmsnorm(const void* x, const void* delta, void* x_out, const v
   if (T == 0) return T1_OK;
   T1_CHECK_ARG(T > 0 && D > 0 && D % 8 == 0 && D <= 8192, "t1_rmsnorm: D=%d must be a multiple of 8 and <= 8192", D);
   T1_CHECK_ARG(!delta || x_out, "t1_rmsnorm: x_out is required when delta is given");
-  norm_fwd_kernel<false><<<T, 256, 0, stream>>>((const bf16*)x, (const bf16*)delta, (bf16*)x_out, (const bf16*)w, nullptr, (bf16*)y, D, eps);
+  if (t1_launch(norm_fwd_kernel<false>, dim3(T), dim3(256), 0, stream, (const bf16*)x, (const bf16*)delta, (bf16*)x_out,
+                (const bf16*)w, (const bf16*)nullptr, (bf16*)y, D, eps) != cudaSuccess) {
+    t1_set_error("t1_rmsnorm: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return T1_ERR_CUDA;
+  }
   T1_CUDA_LAUNCH_CHECK("t1_rmsnorm");
   return T1_OK;
 }
@@ -497,7 +507,11 @@ extern "C" int t1_copy_cols(const void* src, long long lds, void* dst, long long
 extern "C" int t1_swiglu(const void* gate_up, void* act, long long T, int I, cudaStream_t stream) {
   if (T == 0) return T1_OK;
   T1_CHECK_ARG(I % 8 == 0, "t1_swiglu: I must be a multiple of 8");
-  swiglu_fwd_kernel<<<blocks_for(T * (I / 8), 256), 256, 0, stream>>>((const bf16*)gate_up, (bf16*)act, T, I);
+  if (t1_launch(swiglu_fwd_kernel, dim3(blocks_for(T * (I / 8), 256)), dim3(256), 0, stream, (const bf16*)gate_up, (bf16*)act,
+                T, I) != cudaSuccess) {
+    t1_set_error("t1_swiglu: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return T1_ERR_CUDA;
+  }
   T1_CUDA_LAUNCH_CHECK("t1_swiglu");
   return T1_OK;
 }
@@ -531,7 +545,11 @@ extern "C" int t1_gather_rows(const void* src, long long lds, const int* idx, vo
                               cudaStream_t stream) {
   if (n == 0) return T1_OK;
   T1_CHECK_ARG(width % 8 == 0 && lds % 8 == 0 && ldd % 8 == 0, "t1_gather_rows: widths must be multiples of 8");
-  gather_rows_kernel<<<blocks_for((long long)n * (width / 8), 256), 256, 0, stream>>>((const bf16*)src, lds, idx, (bf16*)dst, ldd, n, width);
+  if (t1_launch(gather_rows_kernel, dim3(blocks_for((long long)n * (width / 8), 256)), dim3(256), 0, stream, (const bf16*)src,
+                lds, idx, (bf16*)dst, ldd, n, width) != cudaSuccess) {
+    t1_set_error("t1_gather_rows: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return T1_ERR_CUDA;
+  }
   T1_CUDA_LAUNCH_CHECK("t1_gather_rows");
   return T1_OK;
 }

@@ -1,0 +1,383 @@
+// Weight-streaming decode GEMM for sm_100a:  y[M<=64, N] = x[M,K] * W[N,K]^T (+ bias[N])
+//
+// Replaces the per-token nn.Linear calls of HF GenerationMixin._sample (driven from
+// src/time_r1/rl/timer1_trainer.py:568-573).  With M = (prompt-groups x G) <= 64 rows the op is a pure stream of the
+// weight matrix: HBM-bound, 2*N*K bytes per launch.  Design:
+//   * operands swapped for the tensor core: the 128 weight rows of a slab are the UMMA M dimension, the (padded) batch
+//     rows MP in {16, 32, 64} are the UMMA N dimension; accumulator = MP fp32 TMEM columns (double buffered);
+//   * stream-K work split: the (slab, 64-wide k-block) units are laid out slab-major and cut into equal contiguous
+//     ranges, one per CTA, so every SM streams the same number of bytes whatever N and K are; a slab shared by
+//     several CTAs is finished by the last one to arrive (partials in an L2-resident workspace, summed in a fixed
+//     order => deterministic);
+//   * warp 0 = TMA producer (128x64 W box + MPx64 x box per stage, SWIZZLE_128B, mbarrier ring), warp 1 = single
+//     thread tcgen05.mma issuer, warps 2..5 = epilogue (tcgen05.ld -> transposed global stores);
+//   * programmatic dependent launch: the producer fills the whole ring with WEIGHT tiles before
+//     griddepcontrol.wait -- weights do not depend on the previous kernel -- so the HBM stream of kernel k+1 runs
+//     under the tail of kernel k and under the latency-bound kernels (norm, rope, attention) in between.
+#include "t1_common.cuh"
+#include <stdlib.h>
+
+namespace {
+
+constexpr int SG_BM = 128;              // weight rows per slab
+constexpr int SG_BK = 64;               // 64 bf16 = one 128-byte swizzle row
+constexpr int SG_W_BYTES = SG_BM * SG_BK * 2;
+constexpr int SG_MAX_STAGES = 24;
+constexpr int SG_HEADER = 1024;         // barriers + tmem pointer + flags
+constexpr int SG_THREADS = 192;
+constexpr int SG_COUNTER_BYTES = 65536; // slab counters at the head of the workspace (N <= 2M rows)
+
+__device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const void* desc, uint64_t* bar, int c0, int c1,
+                                                 uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(desc), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+struct SgParams {
+  void* y;
+  const bf16* bias;
+  float* ws;          // [grid][2][MP][128] fp32 partial tiles
+  int* counters;      // [slabs], zero on entry, reset by the finishing CTA
+  long long ldy;
+  int M, N, K;
+  int kblocks;        // ceil(K / 64)
+  int total_units;    // slabs * kblocks
+  int per_cta;        // units per CTA
+  int stages;
+  int out_f32;
+  unsigned long long* dbg;   // optional [4] globaltimer stamps of CTA 0: start, weights issued, dependency resolved, done
+};
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+template <int MP>
+__global__ void __launch_bounds__(SG_THREADS, 1)
+stream_gemm_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CUtensorMap tma_x, SgParams p) {
+  constexpr int X_BYTES = MP * SG_BK * 2;
+  constexpr int STAGE_BYTES = SG_W_BYTES + X_BYTES;
+  constexpr uint32_t TMEM_COLS = (2 * MP < 32) ? 32 : 2 * MP;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty_bar = full_bar + SG_MAX_STAGES;
+  uint64_t* tmem_full_bar = empty_bar + SG_MAX_STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  int* s_flag = reinterpret_cast<int*>(tmem_ptr_smem + 1);
+  uint8_t* tiles = smem + SG_HEADER;
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int stages = p.stages;
+  const int KB = p.kblocks;
+  const int u0 = blockIdx.x * p.per_cta;
+  const int u1 = min(u0 + p.per_cta, p.total_units);
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_w);
+    tma_prefetch_desc(&tma_x);
+    for (int i = 0; i < stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 128);
+    }
+    mbar_fence_init();
+  }
+  if (warp_idx == 1) tmem_alloc<TMEM_COLS>(tmem_ptr_smem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_trigger();   // the next kernel of the chain may become resident (it blocks in its own griddepcontrol.wait)
+
+  if (warp_idx == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0 && u1 > u0) {
+      const bool dbg = p.dbg && blockIdx.x == 0;
+      if (dbg) p.dbg[0] = gtimer();
+      uint64_t pol_stream, pol_keep;
+      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+      asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+      const int n = u1 - u0;
+      const int pre = min(n, stages);
+      // weights first: they do not depend on the previous kernel
+      for (int i = 0; i < pre; ++i) {
+        const int u = u0 + i;
+        const int slab = u / KB, kb = u - slab * KB;
+        mbar_arrive_expect_tx(&full_bar[i], STAGE_BYTES);
+        tma_load_2d_hint(tiles + i * STAGE_BYTES, &tma_w, &full_bar[i], kb * SG_BK, slab * SG_BM, pol_stream);
+      }
+      if (dbg) p.dbg[1] = gtimer();
+      pdl_wait();
+      if (dbg) p.dbg[2] = gtimer();
+      for (int i = 0; i < pre; ++i) {
+        const int u = u0 + i;
+        const int kb = u % KB;
+        tma_load_2d_hint(tiles + i * STAGE_BYTES + SG_W_BYTES, &tma_x, &full_bar[i], kb * SG_BK, 0, pol_keep);
+      }
+      int stage = pre == stages ? 0 : pre;
+      uint32_t phase = pre == stages ? 1 : 0;   // parity of the NEXT use of `stage`
+      for (int i = pre; i < n; ++i) {
+        const int u = u0 + i;
+        const int slab = u / KB, kb = u - slab * KB;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+        tma_load_2d_hint(tiles + stage * STAGE_BYTES, &tma_w, &full_bar[stage], kb * SG_BK, slab * SG_BM, pol_stream);
+        tma_load_2d_hint(tiles + stage * STAGE_BYTES + SG_W_BYTES, &tma_x, &full_bar[stage], kb * SG_BK, 0, pol_keep);
+        if (++stage == stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ===================== MMA issuer (single thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(SG_BM, MP);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int u = u0; u < u1; ++it) {
+        const int slab = u / KB, kb0 = u - slab * KB;
+        const int kb1 = min(KB, kb0 + (u1 - u));
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * MP;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t a_desc = umma_desc_sw128_kmajor(smem_u32(tiles + stage * STAGE_BYTES));
+          const uint64_t b_desc = umma_desc_sw128_kmajor(smem_u32(tiles + stage * STAGE_BYTES + SG_W_BYTES));
+#pragma unroll
+          for (int k = 0; k < SG_BK / 16; ++k)
+            umma_bf16_ss(tmem_d, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);
+          if (++stage == stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full_bar[acc]);
+        u += kb1 - kb0;
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5 = TMEM lane quadrants 2,3,0,1) =====================
+    pdl_wait();
+    const int q = warp_idx & 3;
+    const int et = (warp_idx - 2) * 32 + lane;   // 0..127
+    const int r = q * 32 + lane;                 // weight row inside the slab == TMEM lane
+    int it = 0;
+    for (int u = u0; u < u1; ++it) {
+      const int slab = u / KB, kb0 = u - slab * KB;
+      const int kb1 = min(KB, kb0 + (u1 - u));
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      uint32_t v[MP];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * MP;
+      if constexpr (MP == 16) {
+        tmem_ld_32x32b_x16(taddr, v);
+      } else {
+#pragma unroll
+        for (int c = 0; c < MP / 32; ++c) tmem_ld_32x32b_x32(taddr + c * 32, v + c * 32);
+      }
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&tmem_empty_bar[acc]);          // accumulator is in registers: the MMA warp may reuse it
+      const int n = slab * SG_BM + r;
+      const bool whole = (kb0 == 0 && kb1 == KB);
+      bool finish = whole;
+      int c_first = 0, c_last = 0;
+      if (!whole) {
+        float* mine = p.ws + ((size_t)(blockIdx.x * 2 + (it == 0 ? 0 : 1)) * MP) * SG_BM;
+#pragma unroll
+        for (int m = 0; m < MP; ++m) mine[m * SG_BM + r] = __uint_as_float(v[m]);
+        __threadfence();
+        epi_bar_sync();
+        c_first = (slab * KB) / p.per_cta;
+        c_last = ((slab + 1) * KB - 1) / p.per_cta;
+        if (et == 0) {
+          const int old = atomicAdd(&p.counters[slab], 1);
+          const int last = (old == c_last - c_first) ? 1 : 0;
+          if (last) p.counters[slab] = 0;         // self-resetting: the next launch finds zeros
+          *s_flag = last;
+        }
+        epi_bar_sync();
+        finish = *s_flag != 0;
+        epi_bar_sync();                            // s_flag may be rewritten by the next segment
+        if (finish) {
+          __threadfence();
+#pragma unroll
+          for (int m = 0; m < MP; ++m) v[m] = 0u;
+          for (int c = c_first; c <= c_last; ++c) {
+            const int slot = (slab == (c * p.per_cta) / KB) ? 0 : 1;
+            const float* part = p.ws + ((size_t)(c * 2 + slot) * MP) * SG_BM;
+#pragma unroll
+            for (int m = 0; m < MP; ++m) v[m] = __float_as_uint(__uint_as_float(v[m]) + __ldcg(part + m * SG_BM + r));
+          }
+        }
+      }
+      if (finish && n < p.N) {
+        const float b = p.bias ? __bfloat162float(p.bias[n]) : 0.f;
+        if (p.out_f32) {
+          float* yp = reinterpret_cast<float*>(p.y) + n;
+#pragma unroll
+          for (int m = 0; m < MP; ++m)
+            if (m < p.M) yp[(long long)m * p.ldy] = __uint_as_float(v[m]) + b;
+        } else {
+          bf16* yp = reinterpret_cast<bf16*>(p.y) + n;
+#pragma unroll
+          for (int m = 0; m < MP; ++m)
+            if (m < p.M) yp[(long long)m * p.ldy] = __float2bfloat16(__uint_as_float(v[m]) + b);
+        }
+      }
+      u += kb1 - kb0;
+    }
+    if (p.dbg && blockIdx.x == 0 && et == 0) p.dbg[3] = gtimer();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 1) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+unsigned long long* g_dbg = nullptr;   // device ring of 4-stamp records (t1_stream_gemm_debug)
+int g_dbg_slots = 0, g_dbg_next = 0;
+int g_stages = -1, g_ctas_per_sm = -1;   // tuning knobs: T1_STREAM_STAGES / T1_STREAM_CTAS_PER_SM or t1_stream_gemm_tune()
+
+template <int MP>
+int launch_stream(const CUtensorMap& tw, const CUtensorMap& tx, SgParams p, int grid, int smem, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(stream_gemm_kernel<MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) {
+      t1_set_error("t1_stream_gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return T1_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  cudaError_t e = t1_launch(stream_gemm_kernel<MP>, dim3(grid), dim3(SG_THREADS), (size_t)smem, stream, tw, tx, p);
+  if (e != cudaSuccess) {
+    t1_set_error("t1_stream_gemm: launch failed: %s", cudaGetErrorString(e));
+    return T1_ERR_CUDA;
+  }
+  return T1_OK;
+}
+
+}  // namespace
+
+// Workspace bytes a caller must provide for t1_stream_gemm with up to max_m rows: slab counters (the first 64 KB, which
+// must be ZERO before the first launch; every launch leaves them zero) followed by the fp32 partial tiles.
+extern "C" long long t1_stream_gemm_workspace_bytes(int max_m) {
+  const long long max_ctas = 2LL * t1_num_sms();
+  const long long mp = max_m <= 16 ? 16 : (max_m <= 32 ? 32 : 64);
+  return SG_COUNTER_BYTES + max_ctas * 2 * mp * SG_BM * 4;
+}
+
+// Diagnostics: when buf != NULL, launch i (counted from this call) makes CTA 0 write 4 %globaltimer stamps
+// {kernel start, weight prefetch issued, dependency resolved, last slab written} to buf[4*(i % slots)].
+extern "C" void t1_stream_gemm_debug(void* buf, int slots) {
+  g_dbg = reinterpret_cast<unsigned long long*>(buf);
+  g_dbg_slots = slots;
+  g_dbg_next = 0;
+}
+
+// Ring depth (0 = default: ~108 KB per CTA) and CTAs per SM (1 or 2) of subsequent launches.
+extern "C" void t1_stream_gemm_tune(int stages, int ctas_per_sm) {
+  g_stages = stages > 0 ? stages : 0;
+  g_ctas_per_sm = ctas_per_sm > 0 ? ctas_per_sm : 1;
+}
+
+extern "C" int t1_stream_gemm(const void* x, long long ldx, const void* W, long long ldw, const void* bias, void* y,
+                              long long ldy, int M, int N, int K, int out_f32, void* workspace, long long workspace_bytes,
+                              cudaStream_t stream) {
+  T1_CHECK_ARG(x && W && y && workspace, "t1_stream_gemm: null operand");
+  T1_CHECK_ARG(M > 0 && M <= 64, "t1_stream_gemm: M=%d must be in [1, 64]", M);
+  T1_CHECK_ARG(N > 0 && K > 0 && K % 8 == 0, "t1_stream_gemm: K %% 8 required (N=%d K=%d)", N, K);
+  T1_CHECK_ARG(ldx % 8 == 0 && ldw % 8 == 0 && ldx >= K && ldw >= K, "t1_stream_gemm: ldx/ldw must be multiples of 8 and >= K");
+  T1_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)W & 15) == 0, "t1_stream_gemm: operands must be 16-byte aligned");
+  const int MP = M <= 16 ? 16 : (M <= 32 ? 32 : 64);
+  const int stage_bytes = SG_W_BYTES + MP * SG_BK * 2;
+  if (g_stages < 0) {
+    g_stages = env_int("T1_STREAM_STAGES", 0);
+    g_ctas_per_sm = env_int("T1_STREAM_CTAS_PER_SM", 1);
+  }
+  const int env_stages = g_stages, env_ctas = g_ctas_per_sm;
+  // default: ~180 KB of ring per CTA (10 stages at MP = 16).  Measured on B200 inside the captured 7B decode step
+  // (profiles/r01_decode_timeline_v2.txt): 10 stages 3.65 ms/step, 6 stages (two kernels co-resident) 3.71 ms.
+  int stages = env_stages > 0 ? env_stages : (180 * 1024) / stage_bytes;
+  if (stages > SG_MAX_STAGES) stages = SG_MAX_STAGES;
+  while (stages > 2 && SG_HEADER + 1024 + stages * stage_bytes > 227 * 1024) --stages;
+  const int smem = SG_HEADER + 1024 + stages * stage_bytes;
+  const int slabs = (N + SG_BM - 1) / SG_BM;
+  const int kblocks = (K + SG_BK - 1) / SG_BK;
+  const long long total = (long long)slabs * kblocks;
+  T1_CHECK_ARG(total < (1LL << 30), "t1_stream_gemm: problem too large");
+  int max_ctas = t1_num_sms() * (env_ctas > 0 ? env_ctas : 1);
+  if (max_ctas > 2 * t1_num_sms()) max_ctas = 2 * t1_num_sms();
+  const int per = (int)((total + max_ctas - 1) / max_ctas);
+  const int grid = (int)((total + per - 1) / per);
+  const long long need = SG_COUNTER_BYTES + (long long)grid * 2 * MP * SG_BM * 4;
+  T1_CHECK_ARG(slabs * 4 <= SG_COUNTER_BYTES, "t1_stream_gemm: N=%d exceeds the counter region", N);
+  T1_CHECK_ARG(workspace_bytes >= need, "t1_stream_gemm: workspace too small (%lld < %lld)", workspace_bytes, need);
+  T1_CHECK_ARG(((uintptr_t)workspace & 15) == 0, "t1_stream_gemm: workspace must be 16-byte aligned");
+  CUtensorMap tw, tx;
+  int rc = t1_make_tmap_bf16(&tw, W, N, K, ldw, SG_BM, SG_BK);
+  if (rc) return rc;
+  rc = t1_make_tmap_bf16(&tx, x, M, K, ldx, MP, SG_BK);
+  if (rc) return rc;
+  SgParams p;
+  p.y = y;
+  p.bias = (const bf16*)bias;
+  p.counters = reinterpret_cast<int*>(workspace);
+  p.ws = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + SG_COUNTER_BYTES);
+  p.ldy = ldy;
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.kblocks = kblocks;
+  p.total_units = (int)total;
+  p.per_cta = per;
+  p.stages = stages;
+  p.out_f32 = out_f32;
+  p.dbg = nullptr;
+  if (g_dbg && g_dbg_slots > 0) {
+    p.dbg = g_dbg + 4 * (size_t)(g_dbg_next % g_dbg_slots);
+    ++g_dbg_next;
+  }
+  if (MP == 16) rc = launch_stream<16>(tw, tx, p, grid, smem, stream);
+  else if (MP == 32) rc = launch_stream<32>(tw, tx, p, grid, smem, stream);
+  else rc = launch_stream<64>(tw, tx, p, grid, smem, stream);
+  if (rc) return rc;
+  t1_count_launch();
+  return T1_OK;
+}

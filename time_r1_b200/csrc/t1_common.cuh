@@ -297,3 +297,61 @@ __device__ __forceinline__ void cp_async_wait() {
 }
 
 #endif  // __CUDACC__
+
+#ifdef __CUDACC__
+// ---- sampler helpers: order-preserving float key, Philox4x32-10 ----
+__device__ __forceinline__ uint32_t float_key(float x) {
+  const uint32_t u = __float_as_uint(x);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ uint32_t mulhilo(uint32_t a, uint32_t b, uint32_t* hi) {
+  const unsigned long long p = (unsigned long long)a * b;
+  *hi = (uint32_t)(p >> 32);
+  return (uint32_t)p;
+}
+// Philox4x32-10 (Salmon et al. 2011), returns 4 uniform 32-bit words for (counter, key).
+__device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0, hi1;
+    const uint32_t lo0 = mulhilo(0xD2511F53u, c[0], &hi0);
+    const uint32_t lo1 = mulhilo(0xCD9E8D57u, c[2], &hi1);
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+}
+
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  The decode step is a chain of short kernels; with PDL edges the next kernel's
+// CTAs become resident while the current one drains, and a weight-streaming kernel can pull its (input-independent)
+// weights into shared memory before griddepcontrol.wait.  Every kernel launched through t1_launch() MUST execute
+// pdl_wait() before it reads or writes anything a predecessor may touch: completion is only transitive if each
+// link of the chain waits.
+// ---------------------------------------------------------------------------------------------
+extern "C" void t1_set_pdl(int on);
+int t1_pdl_enabled(void);
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t t1_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                    Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = t1_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif

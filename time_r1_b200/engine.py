@@ -27,6 +27,7 @@ import torch
 from . import indexing, ops
 from .config import ModelConfig, RunConfig
 from .lib import call, ptr, stream_ptr
+from .lib import load as load_lib
 from .weights import FlatParams, ModelWeights
 
 BF16, F32, I32 = torch.bfloat16, torch.float32, torch.int32
@@ -352,13 +353,82 @@ class Engine:
             finished=torch.zeros(B, device=d, dtype=I32), out_ids=torch.zeros((B, C), device=d, dtype=I32),
             eos=self._i32(list(cfg.stop_token_ids)), seed_dev=torch.zeros(1, device=d, dtype=torch.int64), graph=None, launches_per_step=0,
         )
+        st["sample_ws"] = torch.empty(int(load_lib().t1_sample_topk_workspace_bytes(B, cfg.vocab_size)), device=d, dtype=torch.uint8)
+        st["impl"] = self._decode_impl()
+        if st["impl"] == "stream":
+            assert G * ratio <= 64, "grouped decode attention handles G * Hq/Hkv <= 64 query rows per KV head"
+            st["gemm_ws"] = ops.stream_gemm_workspace(B, d)
+            # device table of t1_decode_group records (include/timer1.h), one row per layer
+            rec = np.zeros((L, n, 7), dtype=np.int64)
+            for gi, grp in enumerate(groups):
+                for l in range(L):
+                    Kc, Vc = grp["kv"][l]
+                    rec[l, gi, :6] = (Kc.data_ptr(), Vc.data_ptr(), grp["ws_o"].data_ptr(), grp["ws_ml"].data_ptr(),
+                                      grp["cos"].data_ptr(), grp["sin"].data_ptr())
+                    rec[l, gi, 6] = grp["P"]          # little-endian: low int32 = prefix_len, high = reserved 0
+            st["group_table"] = torch.from_numpy(rec).to(d)
+            st["max_P"] = max(Ps)
         self._decode_cache[key] = st
         return st
+
+    def _sample(self, st, logits, ld, B, temperature, top_k, seed, seed_ptr, step_ptr, step_offset, finished, out_ids, next_ids):
+        """temperature/top-k sampling of B rows; the chunked two-kernel sampler when top_k fits, else the general one."""
+        cfg = self.cfg
+        common = (ptr(logits), ld, B, cfg.vocab_size, float(temperature), int(top_k), int(seed), seed_ptr, step_ptr, step_offset,
+                  ptr(st["eos"]), len(cfg.stop_token_ids), cfg.pad_token_id, ptr(finished), ptr(out_ids), st["out_ids"].stride(0),
+                  ptr(next_ids), 0)
+        fast = (not temperature > 0.0 or 1 <= top_k <= 64) and cfg.vocab_size <= 262144
+        if fast:
+            call("t1_sample_topk", *common, ptr(st["sample_ws"]), st["sample_ws"].numel(), stream_ptr())
+        else:
+            call("t1_sample", *common, stream_ptr())
+
+    def _decode_impl(self) -> str:
+        cfg = self.cfg
+        ok = cfg.head_dim == 128 and cfg.hidden_size % 8 == 0 and cfg.intermediate_size % 8 == 0
+        return "stream" if (self.run.decode_impl == "stream" and ok) else "legacy"
+
+    def _decode_step_stream(self, st, G: int, temperature: float, top_k: int):
+        """One token for each of the B = n*G sequences as ONE chain of PDL-linked kernels: every linear streams its
+        weights through the stream-K tcgen05 kernel (whose weight prefetch runs ahead of the dependency), rope/KV-append
+        and the shared-prefix attention cover all groups in one launch each."""
+        cfg = self.cfg
+        L, Hq, Hkv, hd = cfg.num_hidden_layers, cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim
+        eps, scale = cfg.rms_norm_eps, hd ** -0.5
+        B, n = st["B"], len(st["groups"])
+        x, h, qkv, attn, o, gu, act, down = st["x"], st["h"], st["qkv"], st["attn"], st["o"], st["gu"], st["act"], st["down"]
+        ws, tab = st["gemm_ws"], st["group_table"]
+        from .lib import load
+        load().t1_set_pdl(1 if self.run.decode_pdl else 0)
+        try:
+            s = stream_ptr()
+            ops.gather_rows(self.p("model.embed_tokens.weight"), st["next_ids"], out=x)
+            for l in range(L):
+                pre = f"model.layers.{l}."
+                ops.rmsnorm(x, self.p(pre + "input_layernorm.weight"), eps, delta=down if l > 0 else None, out=h)
+                ops.stream_gemm(h, self.p(pre + "self_attn.qkv.weight"), ws, out=qkv, bias=self.p(pre + "self_attn.qkv.bias"))
+                # rope + KV append are fused into the attention kernel (fuse_rope = 1)
+                call("t1_decode_attn_groups", ptr(qkv), qkv.stride(0), ptr(tab[l]), n, G, Hq, Hkv, hd, st["max_P"], st["cpad"],
+                     ptr(st["step"]), ptr(attn), attn.stride(0), scale, 1, s)
+                ops.stream_gemm(attn, self.p(pre + "self_attn.o_proj.weight"), ws, out=o)
+                ops.rmsnorm(x, self.p(pre + "post_attention_layernorm.weight"), eps, delta=o, out=h)
+                ops.stream_gemm(h, self.p(pre + "mlp.gate_up.weight"), ws, out=gu)
+                ops.swiglu(gu, out=act)
+                ops.stream_gemm(act, self.p(pre + "mlp.down_proj.weight"), ws, out=down)
+            ops.rmsnorm(x, self.p("model.norm.weight"), eps, delta=down, out=st["hN"])
+            ops.stream_gemm(st["hN"], self.lm_head(), ws, out=st["logits"])
+            self._sample(st, st["logits"], st["logits"].stride(0), B, temperature, top_k, 0, ptr(st["seed_dev"]), ptr(st["step"]), 1,
+                         st["finished"], st["out_ids"], st["next_ids"])
+            call("t1_incr", ptr(st["step"]), 1, s)
+        finally:
+            load().t1_set_pdl(0)
 
     def _decode_step(self, st, G: int, temperature: float, top_k: int):
         """One token for each of the B = n*G sequences (captured into a CUDA graph by rollout_multi()). The linears
         run once over all B rows (the weight stream is amortised over the groups); rope/KV-append and the
         shared-prefix attention run per group because each group has its own prompt."""
+        if st.get("impl") == "stream":
+            return self._decode_step_stream(st, G, temperature, top_k)
         cfg = self.cfg
         L, Hq, Hkv, hd = cfg.num_hidden_layers, cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim
         eps, scale = cfg.rms_norm_eps, hd ** -0.5
@@ -394,9 +464,8 @@ class Engine:
             ops.skinny_gemm(act, self.p(pre + "mlp.down_proj.weight"), out=down)
         ops.rmsnorm(x, self.p("model.norm.weight"), eps, delta=down, out=st["hN"])
         ops.skinny_gemm(st["hN"], self.lm_head(), out=st["logits"])
-        call("t1_sample", ptr(st["logits"]), st["logits"].stride(0), B, cfg.vocab_size, float(temperature), int(top_k),
-             0, ptr(st["seed_dev"]), ptr(st["step"]), 1, ptr(st["eos"]), len(cfg.stop_token_ids), cfg.pad_token_id, ptr(st["finished"]),
-             ptr(st["out_ids"]), st["out_ids"].stride(0), ptr(st["next_ids"]), 0, s)
+        self._sample(st, st["logits"], st["logits"].stride(0), B, temperature, top_k, 0, ptr(st["seed_dev"]), ptr(st["step"]), 1,
+                     st["finished"], st["out_ids"], st["next_ids"])
         call("t1_incr", ptr(st["step"]), 1, s)
 
     def rollout(self, prompt: Prompt, vision_embeds: torch.Tensor, G: int, C: int, temperature: float = 1.0,
@@ -452,9 +521,8 @@ class Engine:
             grp["sin"].copy_(dsin)
             # first token: G independent draws from the shared last-prompt-position distribution (row stride 0)
             sl = slice(gi * G, (gi + 1) * G)
-            call("t1_sample", ptr(logits0), 0, G, cfg.vocab_size, float(temperature), int(top_k), int(seed) + 7919 * (gi + 1), 0, 0, 0,
-                 ptr(st["eos"]), len(cfg.stop_token_ids), cfg.pad_token_id, ptr(st["finished"][sl]), ptr(st["out_ids"][sl]),
-                 st["out_ids"].stride(0), ptr(st["next_ids"][sl]), 0, stream_ptr())
+            self._sample(st, logits0, 0, G, temperature, top_k, int(seed) + 7919 * (gi + 1), 0, 0, 0,
+                         st["finished"][sl], st["out_ids"][sl], st["next_ids"][sl])
         n_steps = C - 1
         if n_steps > 0:
             gkey = (float(temperature), int(top_k))     # the seed lives in device memory: graphs are seed-independent

@@ -60,16 +60,27 @@ _SIGNATURES: dict[str, list] = {
                     i32, i32, i32, i32, i32, i32, f32, vp],
     # decode.cu
     "t1_skinny_gemm": [vp, i64, vp, i64, vp, vp, i64, i32, i32, i32, i32, i32, vp],
+    "t1_stream_gemm": [vp, i64, vp, i64, vp, vp, i64, i32, i32, i32, i32, vp, i64, vp],
+    "t1_stream_gemm_workspace_bytes": [i32],
+    "t1_set_pdl": [i32],
+    "t1_stream_gemm_tune": [i32, i32],
+    "t1_stream_gemm_debug": [vp, i32],
+    "t1_decode_rope_append_groups": [vp, i64, i32, i32, i32, i32, i32, vp, vp, i32, vp],
+    "t1_decode_attn_groups": [vp, i64, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, i64, f32, i32, vp],
     "t1_decode_rope_append": [vp, i64, i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, i32, vp],
     "t1_decode_attn": [vp, i64, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, i64, f32, vp],
     "t1_sample": [vp, i64, i32, i32, f32, i32, u64, vp, vp, i32, vp, i32, i32, vp, vp, i32, vp, vp, vp],
     "t1_incr": [vp, i32, vp],
+    # sampler.cu
+    "t1_sample_topk": [vp, i64, i32, i32, f32, i32, u64, vp, vp, i32, vp, i32, i32, vp, vp, i32, vp, vp, vp, i64, vp],
+    "t1_sample_topk_workspace_bytes": [i32, i32],
     # optim.cu
     "t1_sumsq_bf16": [vp, i64, vp, vp],
     "t1_adamw": [vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, vp, f32, f32, vp],
     "t1_bf16_to_f32": [vp, vp, i64, vp],
 }
-_RESTYPES = {"t1_last_error": C.c_char_p, "t1_launch_count": u64, "t1_count_launch": None}
+_RESTYPES = {"t1_last_error": C.c_char_p, "t1_launch_count": u64, "t1_count_launch": None, "t1_set_pdl": None, "t1_stream_gemm_tune": None, "t1_stream_gemm_debug": None,
+             "t1_stream_gemm_workspace_bytes": i64, "t1_sample_topk_workspace_bytes": i64}
 
 GEMM_OUT_F32 = 1
 GEMM_ACCUMULATE = 2

@@ -104,6 +104,25 @@ def skinny_gemm(x, w, out=None, bias=None, accumulate=False, out_dtype=BF16):
     return out
 
 
+def stream_gemm_workspace(max_m: int, device) -> torch.Tensor:
+    """Zero-filled workspace for stream_gemm launches of up to max_m rows on one stream."""
+    n = int(lib.load().t1_stream_gemm_workspace_bytes(int(max_m)))
+    return torch.zeros(n, device=device, dtype=torch.uint8)
+
+
+def stream_gemm(x, w, workspace, out=None, bias=None, out_dtype=BF16):
+    """out[M<=64, N] = x[M,K] @ w[N,K]^T (+bias) on the stream-K tcgen05 weight-streaming kernel."""
+    M, K = x.shape
+    N = w.shape[0]
+    assert x.stride(1) == 1 and w.stride(1) == 1 and w.shape[1] == K
+    if out is None:
+        out = torch.empty((M, N), device=x.device, dtype=out_dtype)
+    assert out.shape == (M, N) and out.stride(1) == 1
+    call("t1_stream_gemm", ptr(x), x.stride(0), ptr(w), w.stride(0), ptr(bias), ptr(out), out.stride(0), M, N, K,
+         1 if out.dtype == F32 else 0, ptr(workspace), workspace.numel(), stream_ptr())
+    return out
+
+
 def linear(x, w, out=None, bias=None, accumulate=False, out_dtype=BF16):
     """Dispatch on the row count: <= 64 rows stream the weights (HBM-bound), otherwise the tcgen05 tile kernel."""
     if x.shape[0] <= 64 and w.shape[0] % 16 == 0 and x.shape[1] % 32 == 0 and (bias is None or bias.dtype == BF16):
