@@ -100,6 +100,14 @@ int t1_attn_bwd(const void* Q, long long ldq, const void* K, long long ldk, cons
                 long long lddq, void* dK, long long lddk, void* dV, long long lddv, const int* row_lo, const int* row_hi,
                 int shared_len, int T, int Tk, int Hq, int Hkv, int head_dim, float scale, cudaStream_t stream);
 
+/* tcgen05/TMEM backward for head_dim 128 (same contract as t1_attn_bwd; replaces the autograd pass through the
+ * flash-attn call at timer1_trainer.py:452-457 / HF trainer.py:1927-1934).  ws: t1_attn_bwd_tc_workspace_bytes(). */
+long long t1_attn_bwd_tc_workspace_bytes(int T, int Tk, int Hq);
+int t1_attn_bwd_tc(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv, const void* O,
+                   long long ldo, const void* dO, long long lddo, const float* LSE2, void* ws, long long ws_bytes, void* dQ,
+                   long long lddq, void* dK, long long lddk, void* dV, long long lddv, const int* row_lo, const int* row_hi,
+                   int shared_len, int T, int Tk, int Hq, int Hkv, int head_dim, float scale, cudaStream_t stream);
+
 /* ---- decode (HF GenerationMixin._sample, timer1_trainer.py:568-573) -------------------------------------- */
 /* Rotate q,k of qkv [B, (Hq+2Hkv)*hd] with table row *step_ptr and append k,v at cache slot
  * prefix_len + b*cpad + *step_ptr.  Kc/Vc [prefix_len + B*cpad, Hkv*hd] bf16. */

@@ -260,6 +260,41 @@ def test_attention_backward(kind, T, P, C, Hq, Hkv, hd):
         close(got, want, tol, 3e-2, f"attn bwd {kind} {name}")
 
 
+@pytest.mark.parametrize("kind,T,P,C,Hq,Hkv", [
+    ("causal", 128, 0, 0, 1, 1), ("causal", 333, 0, 0, 4, 2), ("packed", 531, 203, 41, 14, 2), ("packed", 1200, 700, 100, 7, 1),
+    ("window", 700, 0, 0, 2, 2),
+])
+def test_attention_backward_tcgen05(kind, T, P, C, Hq, Hkv):
+    """tcgen05/TMEM backward (dKV + dQ kernels, TMEM-resident P / dS operands) vs autograd through the dense fp32
+    reference — same bound as the HMMA backward."""
+    from time_r1_b200 import ops
+
+    hd = 128
+    ld = (Hq + 2 * Hkv) * hd
+    qkv = rnd(T, ld, seed=T + hd + 1, scale=0.7)
+    q, k, v = qkv[:, :Hq * hd], qkv[:, Hq * hd:(Hq + Hkv) * hd], qkv[:, (Hq + Hkv) * hd:]
+    lo, hi, shared = make_mask(kind, T, P, C)
+    if kind == "packed":      # trailing padding rows see nothing and receive no gradient
+        hi[-7:] = 0
+        lo[-7:] = 0
+    scale = hd ** -0.5
+    out, lse = ops.attn_fwd_tc(q, k, v, lo, hi, shared, Hq, Hkv, hd, scale)
+    do = rnd(T, Hq * hd, seed=5)
+    qa = q.float().reshape(T, Hq, hd).clone().requires_grad_(True)
+    ka = k.float().reshape(T, Hkv, hd).clone().requires_grad_(True)
+    va = v.float().reshape(T, Hkv, hd).clone().requires_grad_(True)
+    ref = dense_attention(qa, ka, va, lo, hi, shared, scale)
+    ref.backward(do.float().view(T, Hq, hd))
+    dqkv = torch.full_like(qkv, float("nan"))
+    dq, dk, dv = dqkv[:, :Hq * hd], dqkv[:, Hq * hd:(Hq + Hkv) * hd], dqkv[:, (Hq + Hkv) * hd:]
+    ops.attn_bwd_tc(q, k, v, out, do, lse, lo, hi, shared, Hq, Hkv, hd, scale, dq, dk, dv)
+    for name, got, want in (("dq", dq, qa.grad), ("dk", dk, ka.grad), ("dv", dv, va.grad)):
+        want = want.reshape(T, -1)
+        assert torch.isfinite(got.float()).all(), f"attn bwd tcgen05 {kind} {name}: non-finite values"
+        tol = 3e-2 * want.abs().max().item()
+        close(got, want, tol, 3e-2, f"attn bwd tcgen05 {kind} {name}")
+
+
 # ------------------------------------------------------------------ decode kernels
 @pytest.mark.parametrize("M,N,K", [(8, 3584, 3584), (8, 512, 18944), (4, 4096, 256), (16, 1536, 1536), (33, 2048, 512), (64, 256, 1024)])
 def test_skinny_gemm(M, N, K):

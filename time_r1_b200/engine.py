@@ -708,6 +708,8 @@ class Engine:
         act = torch.empty((T, I), device=dev, dtype=BF16)
         dqkv = torch.empty((T, cfg.qkv_dim), device=dev, dtype=BF16)
         lse2 = torch.empty((Hq, T), device=dev, dtype=F32)
+        bwd_tc = hd == 128                    # tcgen05/TMEM attention backward; HMMA kernel for other head dims
+        bwd_ws = torch.empty(int(load_lib().t1_attn_bwd_tc_workspace_bytes(T, T, Hq)), device=dev, dtype=torch.uint8) if bwd_tc else None
         for l in range(L - 1, -1, -1):
             pre = f"model.layers.{l}."
             x_in = st.ckpt[l]
@@ -735,8 +737,12 @@ class Engine:
             # attention backward (dxm is also d o_proj output)
             self._wgrad(dxm, attn, pre + "self_attn.o_proj.weight", acc)
             dattn = self._dgrad(dxm, Wo)
-            ops.attn_bwd(q, k, v, attn, dattn, lse2, st.lo, st.hi, st.P, Hq, Hkv, hd, scale,
-                         dqkv[:, :qd], dqkv[:, qd:qd + kd], dqkv[:, qd + kd:])
+            if bwd_tc:
+                ops.attn_bwd_tc(q, k, v, attn, dattn, lse2, st.lo, st.hi, st.P, Hq, Hkv, hd, scale,
+                                dqkv[:, :qd], dqkv[:, qd:qd + kd], dqkv[:, qd + kd:], ws=bwd_ws)
+            else:
+                ops.attn_bwd(q, k, v, attn, dattn, lse2, st.lo, st.hi, st.P, Hq, Hkv, hd, scale,
+                             dqkv[:, :qd], dqkv[:, qd:qd + kd], dqkv[:, qd + kd:])
             del dattn
             ops.rope_apply(dqkv, 0, Hq + Hkv, hd, st.cos, st.sin, inverse=True)
             f32s.zero_()

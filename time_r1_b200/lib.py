@@ -56,6 +56,9 @@ _SIGNATURES: dict[str, list] = {
     # attention.cu
     "t1_attn_fwd": [vp, i64, vp, i64, vp, i64, vp, i64, vp, vp, vp, i32, i32, i32, i32, i32, i32, f32, vp],
     "t1_attn_fwd_tc": [vp, i64, vp, i64, vp, i64, vp, i64, vp, vp, vp, i32, i32, i32, i32, i32, i32, f32, i32, vp],
+    "t1_attn_bwd_tc_workspace_bytes": [i32, i32, i32],
+    "t1_attn_bwd_tc": [vp, i64, vp, i64, vp, i64, vp, i64, vp, i64, vp, vp, i64, vp, i64, vp, i64, vp, i64, vp, vp,
+                       i32, i32, i32, i32, i32, i32, f32, vp],
     "t1_attn_bwd": [vp, i64, vp, i64, vp, i64, vp, i64, vp, i64, vp, vp, vp, vp, i64, vp, i64, vp, i64, vp, vp,
                     i32, i32, i32, i32, i32, i32, f32, vp],
     # decode.cu
@@ -80,7 +83,8 @@ _SIGNATURES: dict[str, list] = {
     "t1_bf16_to_f32": [vp, vp, i64, vp],
 }
 _RESTYPES = {"t1_last_error": C.c_char_p, "t1_launch_count": u64, "t1_count_launch": None, "t1_set_pdl": None, "t1_stream_gemm_tune": None, "t1_stream_gemm_debug": None,
-             "t1_stream_gemm_workspace_bytes": i64, "t1_sample_topk_workspace_bytes": i64}
+             "t1_stream_gemm_workspace_bytes": i64, "t1_sample_topk_workspace_bytes": i64,
+             "t1_attn_bwd_tc_workspace_bytes": i64}
 
 GEMM_OUT_F32 = 1
 GEMM_ACCUMULATE = 2

@@ -305,6 +305,18 @@ def attn_bwd(q, k, v, o, do, lse, row_lo, row_hi, shared_len, Hq, Hkv, head_dim,
     return dq, dk, dv
 
 
+def attn_bwd_tc(q, k, v, o, do, lse, row_lo, row_hi, shared_len, Hq, Hkv, head_dim, scale, dq, dk, dv, ws=None):
+    """tcgen05/TMEM flash-attention backward (head_dim 128); same contract as attn_bwd."""
+    T, Tk = q.shape[0], k.shape[0]
+    need = int(lib.load().t1_attn_bwd_tc_workspace_bytes(T, Tk, Hq))
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, device=q.device, dtype=torch.uint8)
+    call("t1_attn_bwd_tc", ptr(q), q.stride(0), ptr(k), k.stride(0), ptr(v), v.stride(0), ptr(o), o.stride(0), ptr(do),
+         do.stride(0), ptr(lse), ptr(ws), ws.numel(), ptr(dq), dq.stride(0), ptr(dk), dk.stride(0), ptr(dv), dv.stride(0),
+         ptr(row_lo), ptr(row_hi), int(shared_len), T, Tk, Hq, Hkv, head_dim, float(scale), stream_ptr())
+    return dq, dk, dv
+
+
 def logprob_entropy(logits, target):
     R, V = logits.shape
     lp = torch.empty(R, device=logits.device, dtype=F32)
