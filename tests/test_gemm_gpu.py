@@ -47,3 +47,29 @@ def test_gemm_bias_accumulate_strided():
     obf = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
     ops.gemm(a, b, out=obf, bias=bias.float())
     assert (obf.float() - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("a_t,b_t", [(False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 128), (3584, 4608, 5888), (1000, 3584, 3584), (200, 264, 1000),
+                                   (152064 // 8, 3584, 1664), (5888, 3584, 18944 // 4)])
+def test_gemm_mn_major_operands(M, N, K, a_t, b_t):
+    """Backward-pass forms: A and/or B handed over as row-major [K, rows] and consumed as MN-major UMMA operands
+    (dgrad: dX = dY @ W with B = W in place; wgrad: dW = dY^T @ X with both in place) vs fp32 on the same inputs."""
+    from time_r1_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(M + N * 3 + K * 5)
+    a = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    b = torch.randn(N, K, device="cuda", generator=g).to(torch.bfloat16)
+    ref = a.float() @ b.float().t()
+    a_in = a.t().contiguous() if a_t else a
+    b_in = b.t().contiguous() if b_t else b
+    out32 = ops.gemm(a_in, b_in, out_dtype=torch.float32, a_t=a_t, b_t=b_t)
+    torch.cuda.synchronize()
+    scale = ref.abs().max().item()
+    err32 = (out32 - ref).abs().max().item()
+    assert err32 <= 2e-5 * scale * (K ** 0.5) + 1e-4, f"fp32-out max err {err32} vs scale {scale}"
+    # same bits as the K-major path on explicitly transposed copies (identical products, identical k order)
+    assert torch.equal(out32, ops.gemm(a, b, out_dtype=torch.float32))
+    acc = out32.clone()
+    ops.gemm(a_in, b_in, out=acc, accumulate=True, a_t=a_t, b_t=b_t)
+    assert (acc - 2 * ref).abs().max().item() <= 4e-5 * scale * (K ** 0.5) + 2e-4

@@ -2,8 +2,9 @@
 //
 // Every dense contraction of the Qwen2-VL / Qwen2.5-VL rollout, scoring and backward passes goes through this
 // kernel (reference call sites: the nn.Linear / Conv3d modules inside HF modeling_qwen2_5_vl.py that
-// timer1_trainer.py:452-457 and :569-573 execute through cuBLAS).  Both operands are K-major bf16; the backward
-// pass feeds it explicitly transposed operands (see transpose_bf16 in elementwise.cu).
+// timer1_trainer.py:452-457 and :569-573 execute through cuBLAS).  Operands are bf16; each may be K-major (row-major
+// [rows, K]) or MN-major (row-major [K, rows], flags GEMM_A_MN / GEMM_B_MN) — the backward pass consumes dY, X and W
+// in place as MN-major UMMA operands (dgrad: B = W; wgrad: A = dY, B = X), no explicit transposes.
 //
 // Structure (one CTA per SM, persistent over output tiles):
 //   warp 0      TMA producer   : cp.async.bulk.tensor 2D loads of 128x64 (A) and 256x64 (B) bf16 boxes, SWIZZLE_128B
@@ -30,7 +31,10 @@ enum : int {
   GEMM_OUT_F32 = 1,     // D is fp32 (else bf16)
   GEMM_ACCUMULATE = 2,  // D += result (else D = result)
   GEMM_BIAS_F32 = 4,    // bias is fp32 (else bf16)
+  GEMM_A_MN = 8,        // A is given as row-major [K, M] (M contiguous)
+  GEMM_B_MN = 16,       // B is given as row-major [K, N] (N contiguous)
 };
+constexpr int MN_ATOM_BYTES = BK * 128;   // MN-major smem atom: [64 k-rows x 64 elements], SWIZZLE_128B
 
 struct EpiParams {
   void* D;
@@ -39,6 +43,7 @@ struct EpiParams {
   int flags;
 };
 
+template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, int M, int N,
                     int K, EpiParams epi) {
@@ -90,8 +95,20 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-          tma_load_2d(a_tiles + stage * A_BYTES, &tma_a, &full_bar[stage], kb * BK, m_blk * BM);
-          tma_load_2d(b_tiles + stage * B_BYTES, &tma_b, &full_bar[stage], kb * BK, n_blk * BN);
+          if constexpr (A_MN) {
+#pragma unroll
+            for (int a = 0; a < BM / 64; ++a)
+              tma_load_2d(a_tiles + stage * A_BYTES + a * MN_ATOM_BYTES, &tma_a, &full_bar[stage], m_blk * BM + a * 64, kb * BK);
+          } else {
+            tma_load_2d(a_tiles + stage * A_BYTES, &tma_a, &full_bar[stage], kb * BK, m_blk * BM);
+          }
+          if constexpr (B_MN) {
+#pragma unroll
+            for (int b = 0; b < BN / 64; ++b)
+              tma_load_2d(b_tiles + stage * B_BYTES + b * MN_ATOM_BYTES, &tma_b, &full_bar[stage], n_blk * BN + b * 64, kb * BK);
+          } else {
+            tma_load_2d(b_tiles + stage * B_BYTES, &tma_b, &full_bar[stage], kb * BK, n_blk * BN);
+          }
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -102,7 +119,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   } else if (warp_idx == 1) {
     // ===================== MMA issuer (single thread) =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN) | (A_MN ? (1u << 15) : 0u) | (B_MN ? (1u << 16) : 0u);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -115,13 +132,16 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint64_t a_desc = umma_desc_sw128_kmajor(smem_u32(a_tiles + stage * A_BYTES));
-          const uint64_t b_desc = umma_desc_sw128_kmajor(smem_u32(b_tiles + stage * B_BYTES));
+          const uint32_t a_addr = smem_u32(a_tiles + stage * A_BYTES), b_addr = smem_u32(b_tiles + stage * B_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            // advance 32 B (= 16 bf16) along K inside the 128 B swizzle atom: +2 in the >>4 encoded address
-            umma_bf16_ss(tmem_d, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc,
-                         (kb | k) != 0 ? 1u : 0u);
+            // K-major: advance 32 B (= 16 bf16) along K inside the 128 B swizzle row; MN-major: advance 16 k-rows
+            // (2 KB) inside the [64 x 64] atoms, 64-element M/N blocks one atom (8 KB) apart
+            const uint64_t a_desc = A_MN ? umma_desc_sw128_mnmajor(a_addr + k * UMMA_K * 128, MN_ATOM_BYTES, 1024)
+                                         : umma_desc_sw128_kmajor(a_addr + k * 32);
+            const uint64_t b_desc = B_MN ? umma_desc_sw128_mnmajor(b_addr + k * UMMA_K * 128, MN_ATOM_BYTES, 1024)
+                                         : umma_desc_sw128_kmajor(b_addr + k * 32);
+            umma_bf16_ss(tmem_d, a_desc, b_desc, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above retire
           if (++stage == STAGES) {
@@ -231,15 +251,21 @@ extern "C" int t1_gemm_bf16_tn(const void* A, long long lda, const void* B, long
   T1_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0, "t1_gemm_bf16_tn: lda/ldb must be multiples of 8 (16-byte TMA strides)");
   T1_CHECK_ARG(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0 && ((uintptr_t)D & 15) == 0,
                "t1_gemm_bf16_tn: operands must be 16-byte aligned");
-  T1_CHECK_ARG(lda >= K && ldb >= K && ldd >= N, "t1_gemm_bf16_tn: leading dimension smaller than row length");
+  const bool a_mn = flags & GEMM_A_MN, b_mn = flags & GEMM_B_MN;
+  T1_CHECK_ARG(lda >= (a_mn ? M : K) && ldb >= (b_mn ? N : K) && ldd >= N,
+               "t1_gemm_bf16_tn: leading dimension smaller than row length");
+  T1_CHECK_ARG(!a_mn || M % 8 == 0, "t1_gemm_bf16_tn: MN-major A needs M %% 8 == 0 (M=%d)", M);
   CUtensorMap ta, tb;
-  int rc = t1_make_tmap_bf16(&ta, A, M, K, lda, BM, BK);
+  int rc = a_mn ? t1_make_tmap_bf16(&ta, A, K, M, lda, BK, 64) : t1_make_tmap_bf16(&ta, A, M, K, lda, BM, BK);
   if (rc) return rc;
-  rc = t1_make_tmap_bf16(&tb, B, N, K, ldb, BN, BK);
+  rc = b_mn ? t1_make_tmap_bf16(&tb, B, K, N, ldb, BK, 64) : t1_make_tmap_bf16(&tb, B, N, K, ldb, BN, BK);
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) {
       t1_set_error("t1_gemm_bf16_tn: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return T1_ERR_CUDA;
@@ -249,7 +275,10 @@ extern "C" int t1_gemm_bf16_tn(const void* A, long long lda, const void* B, long
   const int num_tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int grid = num_tiles < t1_num_sms() ? num_tiles : t1_num_sms();
   EpiParams epi{D, bias, ldd, flags};
-  gemm_bf16_tn_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, M, N, K, epi);
+  if (a_mn && b_mn) gemm_bf16_tn_kernel<true, true><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, M, N, K, epi);
+  else if (a_mn) gemm_bf16_tn_kernel<true, false><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, M, N, K, epi);
+  else if (b_mn) gemm_bf16_tn_kernel<false, true><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, M, N, K, epi);
+  else gemm_bf16_tn_kernel<false, false><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, M, N, K, epi);
   T1_CUDA_LAUNCH_CHECK("t1_gemm_bf16_tn");
   return T1_OK;
 }

@@ -645,12 +645,12 @@ class Engine:
         return self.grads[name]
 
     def _wgrad(self, dy: torch.Tensor, x: torch.Tensor, name: str, acc: bool):
-        """grad[name] (+)= dy^T x   (dy [T, N], x [T, K] -> [N, K]); both operands transposed to K-major."""
-        ops.gemm(ops.transpose(dy), ops.transpose(x), out=self._gview(name), accumulate=acc)
+        """grad[name] (+)= dy^T x   (dy [T, N], x [T, K] -> [N, K]); both operands consumed in place (MN-major)."""
+        ops.gemm(dy, x, out=self._gview(name), accumulate=acc, a_t=True, b_t=True)
 
     def _dgrad(self, dy: torch.Tensor, w: torch.Tensor, out=None) -> torch.Tensor:
-        """dx = dy @ w   (dy [T, N], w [N, K])."""
-        return ops.gemm(dy, ops.transpose(w), out=out)
+        """dx = dy @ w   (dy [T, N], w [N, K] consumed in place as an MN-major B operand)."""
+        return ops.gemm(dy, w, out=out, b_t=True)
 
     def _small_grad(self, f32: torch.Tensor, name: str, acc: bool):
         ops.f32_to_bf16(f32, self._gview(name).view(-1), accumulate=acc)
@@ -676,7 +676,6 @@ class Engine:
         dl = torch.zeros(Rp, device=dev, dtype=F32)
         dl[:R] = dlogp.reshape(-1)
         W = self.lm_head()
-        Wt = ops.transpose(W)                                               # [D, V]
         dhsel = torch.empty((Rp, D), device=dev, dtype=BF16)
         step = self.run.logit_chunk_rows
         first = True
@@ -685,11 +684,10 @@ class Engine:
             logits = ops.gemm(st.hsel[a:b], W, out_dtype=F32)               # recompute (1.7 TFLOP at cfg2)
             dlog = ops.logits_backward(logits, st.targets[a:b], st.lse[a:b], dl[a:b])
             del logits
-            ops.gemm(dlog, Wt, out=dhsel[a:b])
-            ops.gemm(ops.transpose(dlog), ops.transpose(st.hsel[a:b]), out=self._gview(head_name), accumulate=acc or not first)
+            ops.gemm(dlog, W, out=dhsel[a:b], b_t=True)
+            ops.gemm(dlog, st.hsel[a:b], out=self._gview(head_name), accumulate=acc or not first, a_t=True, b_t=True)
             first = False
             del dlog
-        del Wt
         dh = torch.zeros((T, D), device=dev, dtype=BF16)
         ops.scatter_rows(dhsel, st.logit_rows, dh, accumulate=True)         # prompt row P-1 receives G contributions
         # ---- final norm ----

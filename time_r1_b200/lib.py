@@ -89,6 +89,8 @@ _RESTYPES = {"t1_last_error": C.c_char_p, "t1_launch_count": u64, "t1_count_laun
 GEMM_OUT_F32 = 1
 GEMM_ACCUMULATE = 2
 GEMM_BIAS_F32 = 4
+GEMM_A_MN = 8       # A given as row-major [K, M]
+GEMM_B_MN = 16      # B given as row-major [K, N]
 
 
 class Timer1Error(RuntimeError):

@@ -57,12 +57,13 @@ def _chk(t: torch.Tensor, dtype, name: str):
 
 
 def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None = None, bias: torch.Tensor | None = None,
-         accumulate: bool = False, out_dtype=torch.bfloat16) -> torch.Tensor:
-    """out[M,N] (+)= a[M,K] @ b[N,K]^T (+ bias[N]) on the tcgen05 kernel. a/b bf16 row-major (row stride free)."""
+         accumulate: bool = False, out_dtype=torch.bfloat16, a_t: bool = False, b_t: bool = False) -> torch.Tensor:
+    """out[M,N] (+)= A[M,K] @ B[N,K]^T (+ bias[N]) on the tcgen05 kernel. a/b bf16 row-major (row stride free);
+    a_t: `a` holds A^T as [K, M];  b_t: `b` holds B^T as [K, N]  (consumed in place as MN-major UMMA operands)."""
     _chk(a, torch.bfloat16, "gemm.a")
     _chk(b, torch.bfloat16, "gemm.b")
-    M, K = a.shape
-    N, K2 = b.shape
+    M, K = (a.shape[1], a.shape[0]) if a_t else a.shape
+    N, K2 = (b.shape[1], b.shape[0]) if b_t else b.shape
     assert K == K2, (a.shape, b.shape)
     assert a.stride(1) == 1 and b.stride(1) == 1
     if out is None:
@@ -75,6 +76,10 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None = None, bias
         raise lib.Timer1Error("gemm: out must be bf16 or fp32")
     if accumulate:
         flags |= lib.GEMM_ACCUMULATE
+    if a_t:
+        flags |= lib.GEMM_A_MN
+    if b_t:
+        flags |= lib.GEMM_B_MN
     if bias is not None:
         assert bias.numel() == N and bias.is_contiguous()
         if bias.dtype == torch.float32:
