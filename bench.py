@@ -188,18 +188,18 @@ class TemplateRewards:
         return np.stack([np.asarray(r1, np.float32), np.asarray(r2, np.float32)], 1)
 
 
-def attention_microbench(eng, P: int, G: int, C: int):
-    """Decode-attention kernel alone at mid-rollout (step C/2), L2 flushed between launches: unique K/V bytes / time."""
+def attention_microbench(eng, Ps, G: int, C: int):
+    """The decode-attention launch of the captured decode step, alone, at mid-rollout (step C/2) for all prompt-groups
+    of the step, L2 flushed between launches: unique K/V bytes / time (shared-prefix byte count)."""
     import torch
 
     from time_r1_b200.lib import call, ptr, stream_ptr
 
     cfg = eng.cfg
-    st = eng._decode_state((P,), G, C)
-    grp = st["groups"][0]
-    Kc, Vc = grp["kv"][0]
+    st = eng._decode_state(tuple(Ps), G, C)
     step = C // 2
     st["step"].fill_(step)
+    n = len(Ps)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=eng.dev)
     Hq, Hkv, hd = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim
     ts = []
@@ -207,16 +207,17 @@ def attention_microbench(eng, P: int, G: int, C: int):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        call("t1_decode_attn", ptr(st["qkv"]), st["qkv"].stride(0), ptr(Kc), ptr(Vc), G, Hq, Hkv, hd, P, st["cpad"],
-             ptr(st["step"]), ptr(grp["ws_o"]), ptr(grp["ws_ml"]), ptr(st["attn"]), st["attn"].stride(0), hd ** -0.5, stream_ptr())
+        call("t1_decode_attn_cluster", ptr(st["qkv"]), st["qkv"].stride(0), ptr(st["group_table"][0]), st["kv_maps"][0].ctypes.data,
+             n, G, Hq, Hkv, hd, st["cpad"], ptr(st["step"]), ptr(st["attn"]), st["attn"].stride(0), hd ** -0.5, 0, stream_ptr())
         e1.record()
         torch.cuda.synchronize()
         if i >= 3:
             ts.append(e0.elapsed_time(e1))
     ts.sort()
     ms = ts[len(ts) // 2]
-    kv_bytes = 2.0 * Hkv * hd * 2 * (P + G * (step + 1)) + 2.0 * G * Hq * hd * 2
-    return {"kernel": "decode_attn+combine", "unique_kv_bytes": kv_bytes, "ms": round(ms, 5), "gbs": round(kv_bytes / ms / 1e6, 1)}
+    kv_bytes = sum(2.0 * Hkv * hd * 2 * (P + G * (step + 1)) for P in Ps) + 2.0 * n * G * Hq * hd * 2
+    return {"kernel": "decode_attn_tc (1 launch, all groups, cluster merge)", "groups": n, "unique_kv_bytes": kv_bytes,
+            "ms": round(ms, 5), "gbs": round(kv_bytes / ms / 1e6, 1)}
 
 
 def run_ours(args):
@@ -328,7 +329,7 @@ def run_ours(args):
         "step_algorithmic_tflop": round(algo["total"] / 1e12, 1),
         "step_frac_of_flop_roofline": round(algo["total"] / (ms_per_step / 1e3) / 1e12 / peak_tf, 4),
     }
-    attn = attention_microbench(eng, P, G, C)
+    attn = attention_microbench(eng, [len(inp[0]) for inp in inputs], G, C)
     attn["peak_gbs"] = peaks.get("hbm_gbs", 6650.0)
     attn["frac"] = round(attn["gbs"] / attn["peak_gbs"], 4)
     line = {

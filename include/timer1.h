@@ -141,6 +141,18 @@ int t1_decode_rope_append_groups(void* qkv, long long ld, int n_groups, int G, i
 int t1_decode_attn_groups(const void* q, long long ldq, const void* groups, int n_groups, int G, int Hq, int Hkv,
                           int head_dim, int max_prefix_len, int cpad, const int* step_ptr, void* out, long long ldo,
                           float scale, int fuse_rope, cudaStream_t stream);
+/* The captured decode step's attention in ONE launch (tcgen05): a thread-block cluster of cluster_size CTAs (1, 2, 4
+ * or 8; 0 = 8) per (group, KV head) streams an even share of the cached 128-key units by TMA, treats this step's token
+ * (k, v still in the un-rotated qkv rows `q`) as one more split-KV partial while rotating q / k and appending k, v to
+ * the cache, and merges the partials through distributed shared memory (no workspace, no combine launch; ws_o / ws_ml
+ * of the group records are unused).  maps: HOST array [n_groups][2] of 128-byte tensor maps over each group's K and
+ * V cache ([rows, Hkv*128] bf16, box 128 rows x 64 columns) produced by t1_encode_tmap_bf16; they travel as kernel parameters
+ * (n_groups <= 8).  The cache must hold finite values. */
+int t1_encode_tmap_bf16(void* out_128_bytes_host, const void* ptr, long long rows, long long cols, long long ld,
+                        int box_rows, int box_cols);
+int t1_decode_attn_cluster(const void* q, long long ldq, const void* groups, const void* maps, int n_groups, int G,
+                           int Hq, int Hkv, int head_dim, int cpad, const int* step_ptr, void* out, long long ldo,
+                           float scale, int cluster_size, cudaStream_t stream);
 /* temperature -> top-k -> softmax -> multinomial (Philox4x32-10 keyed by seed, counter (row, step)); temperature <= 0
  * is greedy arg-max.  HF 4.51.1 generate defaults.  logits [B, V] fp32 (ld may be 0: shared row);
  * seed_ptr (device, nullable) overrides seed so captured graphs stay seed-independent; writes

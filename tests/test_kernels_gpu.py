@@ -435,6 +435,60 @@ def test_decode_groups_match_single_group_kernels():
 
 
 
+@pytest.mark.parametrize("cluster", [1, 2, 8])
+@pytest.mark.parametrize("G,Hq,Hkv,Ps,step,cpad", [(4, 14, 2, [300, 77, 513], 9, 128), (8, 28, 4, [1000, 4216], 130, 256),
+                                                   (8, 28, 4, [517], 63, 256), (8, 28, 4, [64, 40], 64, 128), (3, 2, 1, [5], 0, 64)])
+def test_decode_attention_cluster(G, Hq, Hkv, Ps, step, cpad, cluster):
+    """Single-launch tcgen05 cluster decode attention (TMA units, DSMEM merge, fused rope + KV append) vs the dense
+    fp32 reference over [prompt prefix | own completion slots]; the appended K/V rows are bit-identical to
+    t1_decode_rope_append."""
+    import numpy as np
+    from time_r1_b200 import ops
+    from time_r1_b200.lib import call, ptr, stream_ptr
+
+    hd, C = 128, cpad
+    n = len(Ps)
+    ld = (Hq + 2 * Hkv) * hd
+    ratio = Hq // Hkv
+    raw = rnd(n * G, ld, seed=1)
+    st = torch.tensor([step], device=DEV, dtype=torch.int32)
+    scale = hd ** -0.5
+    groups, rec = [], np.zeros((n, 7), np.int64)
+    for gi, P in enumerate(Ps):
+        S = P + G * cpad
+        d = dict(K=rnd(S, Hkv * hd, seed=10 + gi), V=rnd(S, Hkv * hd, seed=20 + gi), cos=torch.rand(C, hd // 2, device=DEV),
+                 sin=torch.rand(C, hd // 2, device=DEV))
+        groups.append(d)
+        rec[gi] = (d["K"].data_ptr(), d["V"].data_ptr(), 0, 0, d["cos"].data_ptr(), d["sin"].data_ptr(), P)
+    tab = torch.from_numpy(rec).to(DEV)
+    maps = ops.kv_cache_tensor_maps([t for g in groups for t in (g["K"], g["V"])], Hkv, hd)
+    # reference rope + append with the stand-alone kernel on clones
+    ref_qkv = raw.clone()
+    refK, refV = [g["K"].clone() for g in groups], [g["V"].clone() for g in groups]
+    for gi, P in enumerate(Ps):
+        call("t1_decode_rope_append", ptr(ref_qkv[gi * G:(gi + 1) * G]), ld, G, Hq, Hkv, hd, ptr(groups[gi]["cos"]),
+             ptr(groups[gi]["sin"]), ptr(st), ptr(refK[gi]), ptr(refV[gi]), P, cpad, stream_ptr())
+    out = torch.full((n * G, Hq * hd), float("nan"), device=DEV, dtype=BF16)
+    call("t1_decode_attn_cluster", ptr(raw), ld, ptr(tab), maps.ctypes.data, n, G, Hq, Hkv, hd, cpad, ptr(st), ptr(out), out.stride(0),
+         scale, cluster, stream_ptr())
+    torch.cuda.synchronize()
+    for gi, P in enumerate(Ps):
+        assert torch.equal(groups[gi]["K"], refK[gi]) and torch.equal(groups[gi]["V"], refV[gi])
+        for b in range(G):
+            idx = torch.cat([torch.arange(P, device=DEV), P + b * cpad + torch.arange(step + 1, device=DEV)])
+            kk = refK[gi][idx].float().view(-1, Hkv, hd).repeat_interleave(ratio, 1)
+            vv = refV[gi][idx].float().view(-1, Hkv, hd).repeat_interleave(ratio, 1)
+            qq = ref_qkv[gi * G + b, :Hq * hd].float().view(Hq, hd)
+            p = torch.softmax(torch.einsum("hd,jhd->hj", qq, kk) * scale, -1)
+            ref = torch.einsum("hj,jhd->hd", p, vv).reshape(-1)
+            close(out[gi * G + b], ref, 2e-2, 2e-2, f"cluster decode attn group {gi} seq {b}")
+    # deterministic: a second launch on the same inputs (cache already holds this step's row) gives the same bits
+    out2 = torch.empty_like(out)
+    call("t1_decode_attn_cluster", ptr(raw), ld, ptr(tab), maps.ctypes.data, n, G, Hq, Hkv, hd, cpad, ptr(st), ptr(out2), out.stride(0),
+         scale, cluster, stream_ptr())
+    assert torch.equal(out, out2)
+
+
 @pytest.mark.parametrize("B,Hq,Hkv,P,step,cpad", [(8, 28, 4, 1000, 0, 256), (8, 28, 4, 517, 130, 256), (4, 12, 2, 250, 37, 128), (3, 2, 1, 64, 5, 128), (20, 28, 4, 300, 17, 128)])
 def test_decode_attention(B, Hq, Hkv, P, step, cpad):
     from time_r1_b200 import ops

@@ -21,7 +21,7 @@ NVCC_FLAGS = [
     "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC",
     "-Xptxas", "-v",
-]
+] + os.environ.get("T1_EXTRA_NVCC", "").split()
 
 
 def _nvcc() -> str:

@@ -163,3 +163,6 @@ class RunConfig:
     # dependent launch; "legacy" = HMMA skinny GEMM + per-group attention on forked graph branches
     decode_impl: str = "stream"
     decode_pdl: bool = True
+    # decode attention inside the "stream" step: "cluster" = one launch, split-KV partials merged through distributed
+    # shared memory; "split" = split-KV kernel + combine kernel through a global workspace
+    decode_attn: str = "cluster"

@@ -154,8 +154,8 @@ decode_rope_append_kernel(bf16* __restrict__ qkv, long long ld, int Hq, int Hkv,
   for (int e = threadIdx.x; e < n_rot; e += blockDim.x) {
     const int h = e / half, i = e - h * half;
     bf16* p = row + h * HD + i;
-    const float a = __bfloat162float(p[0]), bb = __bfloat162float(p[half]);
-    const float ra = a * c[i] - bb * s[i], rb = bb * c[i] + a * s[i];
+    float ra, rb;
+    rope_rotate(__bfloat162float(p[0]), __bfloat162float(p[half]), c[i], s[i], ra, rb);
     const bf16 oa = __float2bfloat16(ra), ob = __float2bfloat16(rb);
     p[0] = oa;
     p[half] = ob;
@@ -202,8 +202,8 @@ decode_rope_append_groups_kernel(bf16* __restrict__ qkv, long long ld, int G, in
   for (int e = threadIdx.x; e < n_rot; e += blockDim.x) {
     const int h = e / half, i = e - h * half;
     bf16* p = row + h * HD + i;
-    const float a = __bfloat162float(p[0]), bb = __bfloat162float(p[half]);
-    const float ra = a * c[i] - bb * s[i], rb = bb * c[i] + a * s[i];
+    float ra, rb;
+    rope_rotate(__bfloat162float(p[0]), __bfloat162float(p[half]), c[i], s[i], ra, rb);
     const bf16 oa = __float2bfloat16(ra), ob = __float2bfloat16(rb);
     p[0] = oa;
     p[half] = ob;
@@ -327,9 +327,10 @@ decode_attn_kernel(const bf16* __restrict__ q, long long ldq, const bf16* __rest
       const int r = e / (HD / 2), i = e - r * (HD / 2);
       if (rt * 64 + r < n_rows) {
         bf16* pq = sQ + r * LDS + i;
-        const float a = __bfloat162float(pq[0]), bb = __bfloat162float(pq[HD / 2]);
-        pq[0] = __float2bfloat16(a * cs[i] - bb * sn[i]);
-        pq[HD / 2] = __float2bfloat16(bb * cs[i] + a * sn[i]);
+        float ra, rb;
+        rope_rotate(__bfloat162float(pq[0]), __bfloat162float(pq[HD / 2]), cs[i], sn[i], ra, rb);
+        pq[0] = __float2bfloat16(ra);
+        pq[HD / 2] = __float2bfloat16(rb);
       }
     }
     const int lr = step - (j0 - prefix_len - chunk_seq * cpad);   // row of slot `step` inside this chunk
@@ -338,8 +339,9 @@ decode_attn_kernel(const bf16* __restrict__ q, long long ldq, const bf16* __rest
       const long long slot = (long long)j0 + lr;
       if (tid < HD / 2) {
         const bf16* pk = src + (long long)(Hq + hk) * HD + tid;
-        const float a = __bfloat162float(pk[0]), bb = __bfloat162float(pk[HD / 2]);
-        const bf16 oa = __float2bfloat16(a * cs[tid] - bb * sn[tid]), ob = __float2bfloat16(bb * cs[tid] + a * sn[tid]);
+        float ra, rb;
+        rope_rotate(__bfloat162float(pk[0]), __bfloat162float(pk[HD / 2]), cs[tid], sn[tid], ra, rb);
+        const bf16 oa = __float2bfloat16(ra), ob = __float2bfloat16(rb);
         sK[lr * LDS + tid] = oa;
         sK[lr * LDS + tid + HD / 2] = ob;
         bf16* kd = Kw + (slot * Hkv + hk) * HD + tid;

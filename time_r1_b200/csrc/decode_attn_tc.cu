@@ -1,0 +1,562 @@
+// Single-launch tcgen05 decode attention for the captured decode step (replaces HF GenerationMixin._sample's per-token
+// attention, driven from src/time_r1/rl/timer1_trainer.py:568-573): one thread-block CLUSTER per (prompt-group, KV head).
+//
+// The G sequences of a group share ONE copy of the prompt K/V, so the (G x q-heads-per-kv-head) <= 64 query rows form
+// one query tile against every prefix key.  The cached keys [prompt prefix | per-sequence completion slots < step] are
+// cut into 128-key units and dealt evenly to the S CTAs of the cluster (equal bytes per SM).  Per CTA:
+//   warp 0       TMA producer : K and V unit tiles ([128 x 64] SWIZZLE_128B boxes from the per-layer cache tensor
+//                               maps, which travel as kernel parameters) through a 2-stage mbarrier ring
+//   warp 1       MMA issuer   : S = Q K^T (tcgen05.mma M128 N128 K16 x 8, SS) -> TMEM S[it & 1];
+//                               O += P V (TS: P read from TMEM, V consumed in place as an MN-major operand) -> TMEM O;
+//                               ONE tcgen05.commit per MMA batch (a commit costs the issuing thread ~300 clk)
+//   warps 2..17  softmax      : 4 threads per query row (32 key columns each); rows are spread over the four TMEM lane
+//                               quadrants; lazy-rescaled online softmax; P (bf16) packed back into the S columns
+// This step's token (whose k / v are still in the qkv buffer) is one extra split-KV partial (m = q.k, l = 1, O = v)
+// computed on the CUDA cores by the CTA that also rotates k and appends k, v to the cache, so no tile is patched.
+// The (m, l, O) partials are merged ACROSS the cluster through distributed shared memory: every CTA PUSHES its rows to
+// the CTA that owns them (remote stores pipeline; remote loads measured ~190 clk each, serialised), one cluster barrier,
+// then a local merge.  No global workspace, no combine kernel, no atomics; deterministic.  q is rotated (decode-position
+// rope) while the Q tile is built.
+// HBM-bound: algorithmic bytes per launch = 2 * Hkv * 128 * 2 * sum_groups(P + G * step) (+ q, out).
+// The cache must hold finite values everywhere (it is allocated zeroed): masked keys are multiplied by P = 0.
+#include "t1_common.cuh"
+#include <cooperative_groups.h>
+#include <stdlib.h>
+#include <string.h>
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+struct DecodeGroup {          // == t1_decode_group (include/timer1.h)
+  bf16* K;
+  bf16* V;
+  float* ws_o;
+  float* ws_ml;
+  const float* cos_t;
+  const float* sin_t;
+  int prefix_len;
+  int reserved;
+};
+static_assert(sizeof(DecodeGroup) == 56, "t1_decode_group layout");
+
+constexpr int HD = 128;
+constexpr int UNIT = 128;                        // keys per unit
+constexpr int ATOM = 128 * 128;                  // [128 rows x 64 cols] bf16 SW128 atom
+constexpr int TILE = 2 * ATOM;                   // [128 x 128] bf16
+constexpr int STAGE_BYTES = 2 * TILE;            // K then V
+constexpr int NSTG = 2;
+constexpr int NS = 4;                            // softmax threads per query row
+constexpr int NSOFT = 128 * NS;                  // 16 warps
+constexpr int TC_THREADS = 64 + NSOFT;
+constexpr int MAX_S = 16;
+constexpr int MAX_OWN = 8;                       // sequences whose current token one CTA may own (ceil(G / S))
+constexpr int MAX_GROUPS = 8;                    // prompt-groups per launch (tensor maps travel as kernel parameters)
+struct MapTable {
+  CUtensorMap m[2 * MAX_GROUPS];                 // [group][K, V]
+};
+constexpr int MISC_BYTES = 512 /*barriers*/ + 2 * NS * 128 * 4 /*max xch*/ + NS * 128 * 4 /*l xch*/ +
+                           2 * MAX_OWN * HD * 4 /*k_new, v_new*/;
+constexpr int TC_SMEM = TILE /*Q*/ + NSTG * STAGE_BYTES + 1024 /*align*/ + MISC_BYTES;
+// receive buffers of the cluster merge alias the K/V ring: [64/S rows][2S sources][128] fp32 + [..][2] (m, l)
+static_assert(64 * 2 * HD * 4 + 64 * 2 * 2 * 4 <= NSTG * STAGE_BYTES, "merge buffers must fit in the K/V ring");
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+// byte offset of element (row, col) inside a K-major SWIZZLE_128B tile made of [128 x 64] atoms
+__device__ __forceinline__ int sw128_off(int row, int col) {
+  return (col >> 6) * ATOM + row * 128 + ((((col & 63) >> 3) ^ (row & 7)) << 4) + (col & 7) * 2;
+}
+
+#ifdef T1_DECODE_DBG
+__device__ long long g_dbg[1024];
+#define DBG(cond, idx) do { if ((cond) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) g_dbg[(idx)] = clock64(); } while (0)
+#else
+#define DBG(cond, idx) do { } while (0)
+#endif
+
+struct UnitDesc {
+  int slot0;     // first cache row
+  int nvalid;    // real keys in the unit
+  int seq;       // -1: prompt prefix (visible to every row); else the owning sequence
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+decode_attn_tc_kernel(const bf16* __restrict__ q, long long ldq, int Hq, int Hkv, int G, int cpad,
+                      const int* __restrict__ step_ptr, bf16* __restrict__ out, long long ldo, float scale_log2,
+                      const DecodeGroup* __restrict__ groups, const __grid_constant__ MapTable maps) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int S = (int)cluster.num_blocks();
+  const int rank = (int)cluster.block_rank();
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sKV = sQ + TILE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + NSTG * STAGE_BYTES);
+  uint64_t* full = bars;                       // NSTG   TMA -> MMA
+  uint64_t* done = bars + NSTG;                // NSTG   PV(it) retired: stage free (producer), P / O safe (softmax)
+  uint64_t* s_full = bars + 2 * NSTG;          // 2
+  uint64_t* p_ready = bars + 2 * NSTG + 2;     // 1 (one arrival per softmax warp)
+  uint64_t* q_ready = bars + 2 * NSTG + 3;     // 1 (one arrival per softmax warp)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * NSTG + 4);
+  float* s_xch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);   // [2 it][NS parts][128 lanes]
+  float* s_lx = s_xch + 2 * NS * 128;                                               // [NS parts][128 lanes]
+  float* s_knew = s_lx + NS * 128;                                                  // [MAX_OWN][128]
+  float* s_vnew = s_knew + MAX_OWN * HD;                                            // [MAX_OWN][128]
+
+  const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gi = blockIdx.z, hk = blockIdx.y;
+  // descriptors live in kernel-parameter space (a tensor map in global memory is fetched per TMA instruction)
+  const CUtensorMap* tm_k = &maps.m[gi * 2];
+  const CUtensorMap* tm_v = &maps.m[gi * 2 + 1];
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(tm_k);
+    tma_prefetch_desc(tm_v);
+  }
+  if (warp_idx == 1 && lane == 0) {
+    for (int i = 0; i < NSTG; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&done[i], 1);
+    }
+    mbar_init(&s_full[0], 1);
+    mbar_init(&s_full[1], 1);
+    mbar_init(p_ready, NSOFT / 32);
+    mbar_init(q_ready, NSOFT / 32);
+    mbar_fence_init();
+  }
+  if (warp_idx == 1) tmem_alloc<512>(tmem_ptr_smem);
+  pdl_trigger();
+  pdl_wait();                                  // everything below reads what the previous kernels wrote (q, step)
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t T_S = 0, T_O = 256;           // S[2] x 128 columns, O 128 columns
+
+  DBG(threadIdx.x == 64, 900);
+  const DecodeGroup grp = groups[gi];
+  const int ratio = Hq / Hkv;
+  const int n_rows = G * ratio;
+  const int rpq = (n_rows + 3) >> 2;           // query rows per TMEM lane quadrant
+  const int P = grp.prefix_len;
+  const int step = *step_ptr;                  // cache slots [0, step) of every sequence hold earlier tokens
+  q += (long long)gi * G * ldq;
+  out += (long long)gi * G * ldo;
+
+  // ---- this CTA's units: an even share of the prefix units plus an even share of the completion units ----
+  const int UP = (P + UNIT - 1) / UNIT;
+  const int UPS = (step + UNIT - 1) / UNIT;    // units per sequence holding slots 0..step-1
+  const int UC = G * UPS;
+  const int p_lo = (int)((long long)rank * UP / S), p_hi = (int)((long long)(rank + 1) * UP / S);
+  const int c_lo = (int)((long long)rank * UC / S), c_hi = (int)((long long)(rank + 1) * UC / S);
+  const int n_units = (p_hi - p_lo) + (c_hi - c_lo);
+  auto unit_desc = [&](int i) {
+    UnitDesc d;
+    if (i < p_hi - p_lo) {
+      const int u = p_lo + i;
+      d.slot0 = u * UNIT;
+      d.nvalid = min(UNIT, P - u * UNIT);
+      d.seq = -1;
+    } else {
+      const int cu = c_lo + (i - (p_hi - p_lo));
+      d.seq = cu / UPS;
+      const int c0 = (cu - d.seq * UPS) * UNIT;
+      d.slot0 = P + d.seq * cpad + c0;
+      d.nvalid = min(UNIT, step - c0);
+    }
+    return d;
+  };
+
+  // per-thread state of the softmax warps (used again after the cluster barrier)
+  const int quad = warp_idx & 3;               // TMEM lane quadrant this warp may touch
+  const int part = (warp_idx - 2) >> 2;        // which 32-column slice of S (and of O)
+  const int st_tid = threadIdx.x - 64;         // 0..NSOFT-1 for softmax threads
+  const int L = quad * 32 + lane;              // TMEM lane == Q tile row
+  const int r = (lane < rpq) ? quad * rpq + lane : -1;      // logical query row
+  const bool valid = warp_idx >= 2 && r >= 0 && r < n_rows;
+  const int my_seq = valid ? r / ratio : -1;
+  const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
+  float m_ref = -INFINITY, l = 0.f;
+
+  if (warp_idx == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      for (int it = 0; it < n_units; ++it) {
+        const int st = it % NSTG;
+        const UnitDesc d = unit_desc(it);
+        mbar_wait(&done[st], ((it / NSTG) & 1) ^ 1);
+        mbar_arrive_expect_tx(&full[st], STAGE_BYTES);
+        uint8_t* sK = sKV + st * STAGE_BYTES;
+        uint8_t* sV = sK + TILE;
+        tma_load_2d(sK, tm_k, &full[st], hk * HD, d.slot0);
+        tma_load_2d(sK + ATOM, tm_k, &full[st], hk * HD + 64, d.slot0);
+        tma_load_2d(sV, tm_v, &full[st], hk * HD, d.slot0);
+        tma_load_2d(sV + ATOM, tm_v, &full[st], hk * HD + 64, d.slot0);
+        DBG(it < 100, it * 8 + 0);
+      }
+    }
+    __syncwarp();
+  } else if (warp_idx == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0 && n_units > 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, UNIT);                   // A = Q, B = K, both K-major
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(128, HD) | (1u << 16);       // B = V MN-major
+      auto issue_s = [&](int it) {
+        const int st = it % NSTG;
+        mbar_wait(&full[st], (it / NSTG) & 1);
+        tc_fence_after();
+        DBG(it < 100, it * 8 + 1);
+        const uint32_t tS = tmem_base + T_S + (it & 1) * UNIT;
+        const uint8_t* sK = sKV + st * STAGE_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < HD / 16; ++ks) {
+          const uint32_t off = (ks >> 2) * ATOM + (ks & 3) * 32;
+          umma_bf16_ss(tS, umma_desc_sw128_kmajor(smem_u32(sQ + off)), umma_desc_sw128_kmajor(smem_u32(sK + off)), idesc_s,
+                       ks != 0 ? 1u : 0u);
+        }
+        umma_commit(&s_full[it & 1]);
+      };
+      mbar_wait(q_ready, 0);
+      tc_fence_after();
+      issue_s(0);
+      for (int it = 0; it < n_units; ++it) {
+        if (it + 1 < n_units) issue_s(it + 1);
+        const int st = it % NSTG;
+        mbar_wait(p_ready, it & 1);
+        tc_fence_after();
+        DBG(it < 100, it * 8 + 2);
+        const uint8_t* sV = sKV + st * STAGE_BYTES + TILE;
+        const uint32_t tP = tmem_base + T_S + (it & 1) * UNIT;
+#pragma unroll
+        for (int kk = 0; kk < UNIT / 16; ++kk)
+          umma_bf16_ts(tmem_base + T_O, tP + (uint32_t)((kk >> 1) * 32 + (kk & 1) * 8),
+                       umma_desc_sw128_mnmajor(smem_u32(sV + kk * 16 * 128), ATOM, 1024), idesc_pv, (it | kk) != 0 ? 1u : 0u);
+        umma_commit(&done[st]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== softmax warps: NS threads per query row, 32 key columns each =====================
+    // ---- Q tile: zero, then the rotated query rows (row r at lane 32*(r/rpq) + r%rpq) in the UMMA K-major swizzle ----
+    for (int e = st_tid; e < TILE / 16; e += NSOFT) reinterpret_cast<uint4*>(sQ)[e] = make_uint4(0u, 0u, 0u, 0u);
+    asm volatile("bar.sync 9, %0;" ::"n"(NSOFT) : "memory");
+    const float* cs = grp.cos_t + (long long)step * (HD / 2);
+    const float* sn = grp.sin_t + (long long)step * (HD / 2);
+    for (int e = st_tid; e < n_rows * 8; e += NSOFT) {
+      const int row = e >> 3, c = e & 7;         // 8-channel chunk c pairs with chunk c + 8
+      const int sq = row / ratio, hq = hk * ratio + row % ratio;
+      const bf16* src = q + (long long)sq * ldq + (long long)hq * HD + c * 8;
+      const uint4 ua = *reinterpret_cast<const uint4*>(src), ub = *reinterpret_cast<const uint4*>(src + HD / 2);
+      const uint32_t* pa = reinterpret_cast<const uint32_t*>(&ua);
+      const uint32_t* pb = reinterpret_cast<const uint32_t*>(&ub);
+      uint32_t oa[4], ob[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 a = unpack_bf16x2(pa[j]), b = unpack_bf16x2(pb[j]);
+        float ra0, rb0, ra1, rb1;
+        rope_rotate(a.x, b.x, cs[c * 8 + 2 * j], sn[c * 8 + 2 * j], ra0, rb0);
+        rope_rotate(a.y, b.y, cs[c * 8 + 2 * j + 1], sn[c * 8 + 2 * j + 1], ra1, rb1);
+        oa[j] = pack_bf16x2(ra0, ra1);
+        ob[j] = pack_bf16x2(rb0, rb1);
+      }
+      const int Lr = (row / rpq) * 32 + row % rpq;
+      *reinterpret_cast<uint4*>(sQ + sw128_off(Lr, c * 8)) = make_uint4(oa[0], oa[1], oa[2], oa[3]);
+      *reinterpret_cast<uint4*>(sQ + sw128_off(Lr, c * 8 + 64)) = make_uint4(ob[0], ob[1], ob[2], ob[3]);
+    }
+    // ---- this step's k / v of the sequences this CTA owns: rotate k, append both to the cache, keep fp32 copies ----
+    for (int b = rank, o = 0; b < G && o < MAX_OWN; b += S, ++o) {
+      const bf16* src = q + (long long)b * ldq;
+      const long long slot = (long long)P + (long long)b * cpad + step;
+      if (st_tid < HD / 2) {
+        const bf16* pk = src + (long long)(Hq + hk) * HD + st_tid;
+        float ra, rb;
+        rope_rotate(__bfloat162float(pk[0]), __bfloat162float(pk[HD / 2]), cs[st_tid], sn[st_tid], ra, rb);
+        const bf16 ka = __float2bfloat16(ra), kb = __float2bfloat16(rb);
+        bf16* kd = grp.K + (slot * Hkv + hk) * HD + st_tid;
+        kd[0] = ka;
+        kd[HD / 2] = kb;
+        s_knew[o * HD + st_tid] = __bfloat162float(ka);
+        s_knew[o * HD + st_tid + HD / 2] = __bfloat162float(kb);
+      } else if (st_tid < HD / 2 + HD) {
+        const int j = st_tid - HD / 2;
+        const bf16 vv = src[(long long)(Hq + Hkv + hk) * HD + j];
+        grp.V[(slot * Hkv + hk) * HD + j] = vv;
+        s_vnew[o * HD + j] = __bfloat162float(vv);
+      }
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(q_ready);
+    asm volatile("bar.sync 9, %0;" ::"n"(NSOFT) : "memory");     // Q tile, k_new, v_new visible to all softmax threads
+    DBG(st_tid == 0, 901);
+
+    // ---- split-KV online softmax over the units ----
+    for (int it = 0; it < n_units; ++it) {
+      const UnitDesc d = unit_desc(it);
+      mbar_wait(&s_full[it & 1], (it >> 1) & 1);
+      tc_fence_after();
+      DBG(st_tid == 0 && it < 100, it * 8 + 3);
+      uint32_t sv[32];
+      tmem_ld_32x32b_x32(t_lane + T_S + (it & 1) * UNIT + part * 32, sv);
+      tmem_ld_wait();
+      const bool need_mask = d.seq >= 0 || d.nvalid < UNIT;
+      const bool row_sees = valid && (d.seq < 0 || d.seq == my_seq);
+      float tmax = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float v = __uint_as_float(sv[j]);
+        if (need_mask) {
+          v = (row_sees && part * 32 + j < d.nvalid) ? v : -INFINITY;
+          sv[j] = __float_as_uint(v);
+        }
+        tmax = fmaxf(tmax, v);
+      }
+      s_xch[((it & 1) * NS + part) * 128 + L] = tmax;
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "n"(32 * NS) : "memory");
+#pragma unroll
+      for (int o = 0; o < NS; ++o) tmax = fmaxf(tmax, s_xch[((it & 1) * NS + o) * 128 + L]);
+      tmax *= scale_log2;
+      DBG(st_tid == 0 && it < 100, it * 8 + 4);
+      const bool grow = tmax > m_ref + 8.0f;     // lazy rescale (the NS threads of a row take the same decision)
+      float alpha = 1.0f;
+      if (grow) {
+        alpha = (m_ref == -INFINITY) ? 0.f : exp2f(m_ref - tmax);
+        m_ref = tmax;
+        l *= alpha;
+      }
+      // P(it) overwrites the S columns P(it-2) was read from: PV(it-2) must have retired (it has, long ago)
+      if (it >= 2) mbar_wait(&done[it % NSTG], ((it / NSTG) - 1) & 1);
+      if (it > 0 && __any_sync(0xffffffffu, grow)) {
+        // rare after the first units: the O accumulator is rescaled in place once PV(it-1) has retired
+        mbar_wait(&done[(it - 1) % NSTG], ((it - 1) / NSTG) & 1);
+        tc_fence_after();
+        uint32_t ov[32];
+        tmem_ld_32x32b_x32(t_lane + T_O + part * 32, ov);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) ov[j] = __float_as_uint(__uint_as_float(ov[j]) * alpha);
+        tmem_st_32x32b_x32(t_lane + T_O + part * 32, ov);
+        tmem_st_wait();
+      }
+      const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
+      float rs = 0.f;
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float p0 = ex2_approx(fmaf(__uint_as_float(sv[2 * j]), scale_log2, neg_m));
+        const float p1 = ex2_approx(fmaf(__uint_as_float(sv[2 * j + 1]), scale_log2, neg_m));
+        rs += p0 + p1;
+        pk[j] = pack_bf16x2(p0, p1);
+      }
+      l += rs;
+      tmem_st_32x32b_x16(t_lane + T_S + (it & 1) * UNIT + part * 32, pk);
+      tmem_st_wait();                              // warp-collective: every lane's P columns are in TMEM
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_ready);
+      DBG(st_tid == 0 && it < 100, it * 8 + 5);
+    }
+    DBG(st_tid == 0, 902);
+    // ---- row sum over the NS parts; wait for the last PV ----
+    s_lx[part * 128 + L] = l;
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "n"(32 * NS) : "memory");
+    l = 0.f;
+#pragma unroll
+    for (int o = 0; o < NS; ++o) l += s_lx[o * 128 + L];
+    if (n_units > 0) {
+      mbar_wait(&done[(n_units - 1) % NSTG], ((n_units - 1) / NSTG) & 1);
+      tc_fence_after();
+    }
+  }
+  DBG(threadIdx.x == 64, 903);
+  cluster.sync();            // every CTA of the cluster is done with its K/V ring: it becomes the merge receive buffer
+  DBG(threadIdx.x == 64, 904);
+
+  float* rO = reinterpret_cast<float*>(sKV);            // [64/S local rows][2S sources][128]
+  float* rML = rO + 64 * 2 * HD;                        // [64/S local rows][2S sources][2]
+  if (warp_idx >= 2) {
+    // ---- push: source 2*rank = cached-key partial, source 2*rank+1 = this step's token (owner of the sequence only) ----
+    uint32_t ov[32];
+    if (n_units > 0) {                            // warp-uniform: tcgen05.ld is .sync.aligned
+      tmem_ld_32x32b_x32(t_lane + T_O + part * 32, ov);
+      tmem_ld_wait();
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) ov[j] = 0u;
+    }
+    if (valid) {
+      const int owner = r % S, li = r / S;
+      float* dO = cluster.map_shared_rank(rO, owner) + (long long)(li * 2 * S + 2 * rank) * HD + part * 32;
+      float* dML = cluster.map_shared_rank(rML, owner) + (li * 2 * S + 2 * rank) * 2;
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4)
+        *reinterpret_cast<uint4*>(dO + j4 * 4) = make_uint4(ov[j4 * 4], ov[j4 * 4 + 1], ov[j4 * 4 + 2], ov[j4 * 4 + 3]);
+      const bool own = (my_seq % S) == rank && (my_seq / S) < MAX_OWN;
+      const int o = my_seq / S;
+      if (own) {
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4)
+          *reinterpret_cast<float4*>(dO + HD + j4 * 4) = *reinterpret_cast<const float4*>(s_vnew + o * HD + part * 32 + j4 * 4);
+      }
+      if (part == 0) {
+        float s_new = -INFINITY, l_new = 0.f;
+        if (own) {
+          float acc = 0.f;
+#pragma unroll 4
+          for (int c = 0; c < 16; ++c) {
+            const uint4 u = *reinterpret_cast<const uint4*>(sQ + sw128_off(L, c * 8));
+            const uint32_t* pu = reinterpret_cast<const uint32_t*>(&u);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 qq = unpack_bf16x2(pu[j]);
+              acc = fmaf(qq.x, s_knew[o * HD + c * 8 + 2 * j], acc);
+              acc = fmaf(qq.y, s_knew[o * HD + c * 8 + 2 * j + 1], acc);
+            }
+          }
+          s_new = acc * scale_log2;
+          l_new = 1.f;
+        }
+        *reinterpret_cast<float4*>(dML) = make_float4(m_ref, l, s_new, l_new);
+      }
+    }
+  }
+  DBG(threadIdx.x == 64, 905);
+  cluster.sync();            // all pushes have landed (release / acquire at cluster scope)
+  DBG(threadIdx.x == 64, 906);
+
+  // ---- local merge of the rows this CTA owns (rank, rank + S, ...): one thread per head-dim column ----
+  if (warp_idx >= 2) {
+    const int col = st_tid & (HD - 1), sub = st_tid >> 7;      // NS row slots in flight
+    for (int li = sub;; li += NS) {
+      const int row = rank + li * S;
+      if (row >= n_rows) break;
+      const float* ml = rML + (li * 2 * S) * 2;
+      const float* po = rO + (long long)(li * 2 * S) * HD + col;
+      float M = -INFINITY;
+#pragma unroll
+      for (int src = 0; src < 2 * MAX_S; ++src)
+        if (src < 2 * S && ml[src * 2 + 1] > 0.f) M = fmaxf(M, ml[src * 2]);
+      float Lsum = 0.f, acc = 0.f;
+#pragma unroll
+      for (int src = 0; src < 2 * MAX_S; ++src) {
+        if (src < 2 * S) {
+          const float lv = ml[src * 2 + 1];
+          const bool on = lv > 0.f;
+          const float w = on ? ex2_approx(ml[src * 2] - M) : 0.f;
+          const float ov = po[src * HD];                     // local shared memory; garbage of empty sources is dropped
+          Lsum += w * lv;
+          acc += on ? w * ov : 0.f;
+        }
+      }
+      const int sq = row / ratio, hq = hk * ratio + row % ratio;
+      out[(long long)sq * ldo + (long long)hq * HD + col] = __float2bfloat16(Lsum > 0.f ? acc / Lsum : 0.f);
+    }
+  }
+  DBG(threadIdx.x == 64, 907);
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace
+
+#ifdef T1_DECODE_DBG
+extern "C" int t1_decode_attn_dbg_read(long long* out) {
+  return cudaMemcpyFromSymbol(out, g_dbg, sizeof(long long) * 1024) == cudaSuccess ? 0 : -2;
+}
+#endif
+
+// Encode a 2-D SWIZZLE_128B bf16 tensor map (row-major [rows, cols], leading dimension ld elements, box
+// box_rows x box_cols) into the 128 bytes at `out` (host memory).  Used to build the device-resident per-layer K/V
+// cache map table of t1_decode_attn_cluster.
+extern "C" int t1_encode_tmap_bf16(void* out, const void* ptr, long long rows, long long cols, long long ld, int box_rows,
+                                   int box_cols) {
+  T1_CHECK_ARG(out && ptr, "t1_encode_tmap_bf16: null pointer");
+  CUtensorMap m;
+  const int rc = t1_make_tmap_bf16(&m, ptr, rows, cols, ld, box_rows, box_cols);
+  if (rc) return rc;
+  memcpy(out, &m, sizeof(CUtensorMap));
+  return T1_OK;
+}
+
+// Decode attention of one layer for all prompt-groups in ONE launch (see the header of this file).
+//   q [n_groups*G, ldq] = the UN-rotated fused qkv rows of this step; groups: device array of t1_decode_group;
+//   maps: HOST array [n_groups][2] of 128-byte tensor maps over each group's K and V cache ([rows, Hkv*128], box
+//   64 x 64, from t1_encode_tmap_bf16), copied into the kernel parameters (n_groups <= 8); *step_ptr = number of tokens already cached per sequence (this step's slot index).
+//   cluster_size in {1, 2, 4, 8} (0 = 8) CTAs per (group, KV head).
+extern "C" int t1_decode_attn_cluster(const void* q, long long ldq, const void* groups, const void* maps, int n_groups,
+                                      int G, int Hq, int Hkv, int head_dim, int cpad, const int* step_ptr, void* out,
+                                      long long ldo, float scale, int cluster_size, cudaStream_t stream) {
+  T1_CHECK_ARG(head_dim == HD, "t1_decode_attn_cluster: head_dim must be 128 (got %d)", head_dim);
+  T1_CHECK_ARG(cpad > 0, "t1_decode_attn_cluster: cpad must be positive");
+  T1_CHECK_ARG(n_groups > 0 && G > 0 && Hkv > 0 && Hq % Hkv == 0 && G * (Hq / Hkv) <= 64,
+               "t1_decode_attn_cluster: G * Hq/Hkv must be <= 64");
+  T1_CHECK_ARG(q && groups && maps && step_ptr && out, "t1_decode_attn_cluster: null pointer");
+  T1_CHECK_ARG(ldq % 8 == 0 && ((uintptr_t)q & 15) == 0, "t1_decode_attn_cluster: q must be 16-byte aligned with ldq %% 8 == 0");
+  T1_CHECK_ARG(n_groups <= MAX_GROUPS, "t1_decode_attn_cluster: at most %d prompt-groups per launch (got %d)", MAX_GROUPS, n_groups);
+  MapTable tbl;
+  memset(&tbl, 0, sizeof(tbl));
+  memcpy(&tbl, maps, (size_t)n_groups * 2 * sizeof(CUtensorMap));
+  int S = cluster_size > 0 ? cluster_size : 8;
+  if (getenv("T1_DECODE_CLUSTER")) S = atoi(getenv("T1_DECODE_CLUSTER"));
+  T1_CHECK_ARG(S == 1 || S == 2 || S == 4 || S == 8 || S == 16, "t1_decode_attn_cluster: cluster size %d not in {1,2,4,8,16}", S);
+  T1_CHECK_ARG((G + S - 1) / S <= MAX_OWN, "t1_decode_attn_cluster: G=%d too large for cluster size %d", G, S);
+  static bool set = false;
+  if (!set) {
+    cudaError_t e = cudaFuncSetAttribute(decode_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(decode_attn_tc_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) {
+      t1_set_error("t1_decode_attn_cluster: cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e));
+      return T1_ERR_CUDA;
+    }
+    set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(S, Hkv, n_groups);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = TC_SMEM;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = S;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = t1_pdl_enabled() ? 2 : 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, decode_attn_tc_kernel, (const bf16*)q, ldq, Hq, Hkv, G, cpad, step_ptr, (bf16*)out,
+                                     ldo, scale * 1.4426950408889634f, (const DecodeGroup*)groups, tbl);
+  if (e != cudaSuccess) {
+    t1_set_error("t1_decode_attn_cluster: launch failed: %s", cudaGetErrorString(e));
+    return T1_ERR_CUDA;
+  }
+  t1_count_launch();
+  return T1_OK;
+}

@@ -115,6 +115,13 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   return __bfloat1622float2(v);
 }
 
+// Rotary pair rotation with every product and sum rounded separately (no FMA contraction), so that each kernel
+// that rotates the same (a, b, cos, sin) produces the same bits.
+__device__ __forceinline__ void rope_rotate(float a, float b, float c, float s, float& ra, float& rb) {
+  ra = __fsub_rn(__fmul_rn(a, c), __fmul_rn(b, s));
+  rb = __fadd_rn(__fmul_rn(b, c), __fmul_rn(a, s));
+}
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;
   asm volatile(

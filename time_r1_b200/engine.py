@@ -368,6 +368,9 @@ class Engine:
                     rec[l, gi, 6] = grp["P"]          # little-endian: low int32 = prefix_len, high = reserved 0
             st["group_table"] = torch.from_numpy(rec).to(d)
             st["max_P"] = max(Ps)
+            # per-layer TMA tensor maps over every group's K and V cache (t1_decode_attn_cluster)
+            flat = [t for l in range(L) for grp in groups for t in grp["kv"][l]]
+            st["kv_maps"] = ops.kv_cache_tensor_maps(flat, cfg.num_key_value_heads, cfg.head_dim).reshape(L, n * 2 * 128)
         self._decode_cache[key] = st
         return st
 
@@ -408,8 +411,12 @@ class Engine:
                 ops.rmsnorm(x, self.p(pre + "input_layernorm.weight"), eps, delta=down if l > 0 else None, out=h)
                 ops.stream_gemm(h, self.p(pre + "self_attn.qkv.weight"), ws, out=qkv, bias=self.p(pre + "self_attn.qkv.bias"))
                 # rope + KV append are fused into the attention kernel (fuse_rope = 1)
-                call("t1_decode_attn_groups", ptr(qkv), qkv.stride(0), ptr(tab[l]), n, G, Hq, Hkv, hd, st["max_P"], st["cpad"],
-                     ptr(st["step"]), ptr(attn), attn.stride(0), scale, 1, s)
+                if self.run.decode_attn == "cluster":
+                    call("t1_decode_attn_cluster", ptr(qkv), qkv.stride(0), ptr(tab[l]), st["kv_maps"][l].ctypes.data, n, G, Hq, Hkv, hd,
+                         st["cpad"], ptr(st["step"]), ptr(attn), attn.stride(0), scale, 0, s)
+                else:
+                    call("t1_decode_attn_groups", ptr(qkv), qkv.stride(0), ptr(tab[l]), n, G, Hq, Hkv, hd, st["max_P"], st["cpad"],
+                         ptr(st["step"]), ptr(attn), attn.stride(0), scale, 1, s)
                 ops.stream_gemm(attn, self.p(pre + "self_attn.o_proj.weight"), ws, out=o)
                 ops.rmsnorm(x, self.p(pre + "post_attention_layernorm.weight"), eps, delta=o, out=h)
                 ops.stream_gemm(h, self.p(pre + "mlp.gate_up.weight"), ws, out=gu)

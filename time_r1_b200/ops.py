@@ -322,6 +322,19 @@ def attn_bwd_tc(q, k, v, o, do, lse, row_lo, row_hi, shared_len, Hq, Hkv, head_d
     return dq, dk, dv
 
 
+def kv_cache_tensor_maps(caches, Hkv, head_dim):
+    """Host table (numpy [n, 128] uint8) of 128-byte TMA tensor maps (box 128 rows x 64 columns, SWIZZLE_128B) over a list of
+    [rows, Hkv*head_dim] bf16 cache tensors, in list order — the `maps` argument of t1_decode_attn_cluster."""
+    import ctypes
+    import numpy as np
+
+    buf = np.zeros((len(caches), 128), dtype=np.uint8)
+    for i, c in enumerate(caches):
+        assert c.dtype == BF16 and c.stride(1) == 1 and c.shape[1] == Hkv * head_dim
+        call("t1_encode_tmap_bf16", buf[i].ctypes.data_as(ctypes.c_void_p), ptr(c), c.shape[0], c.shape[1], c.stride(0), 128, 64)
+    return buf
+
+
 def logprob_entropy(logits, target):
     R, V = logits.shape
     lp = torch.empty(R, device=logits.device, dtype=F32)
