@@ -64,6 +64,12 @@ int t1_skinny_gemm(const void* x, long long ldx, const void* W, long long ldw, c
 long long t1_stream_gemm_workspace_bytes(int max_m);
 int t1_stream_gemm(const void* x, long long ldx, const void* W, long long ldw, const void* bias, void* y, long long ldy,
                    int M, int N, int K, int out_f32, void* workspace, long long workspace_bytes, cudaStream_t stream);
+/* y[M, I] = silu(x Wg^T) * (x Wu^T), W = [Wg; Wu] ([2I, K]): the decode step's gate_up projection fused with the SwiGLU
+ * (HF Q25:611-624) in one weight stream; same arithmetic per element as t1_stream_gemm (bf16) + t1_swiglu (bit-identical when
+ * the stream-K cut points coincide, as for the 7B decode shapes).  I % 64 == 0. */
+int t1_stream_gemm_swiglu(const void* x, long long ldx, const void* W, long long ldw, const void* bias, void* y,
+                          long long ldy, int M, int I, int K, void* workspace, long long workspace_bytes,
+                          cudaStream_t stream);
 /* Tuning: shared-memory ring depth (0 = default, ~108 KB per CTA) and CTAs per SM (1 or 2) of later launches. */
 void t1_stream_gemm_tune(int stages, int ctas_per_sm);
 /* Diagnostics: CTA 0 of launch i writes 4 %globaltimer stamps {start, weight prefetch issued, dependency resolved,

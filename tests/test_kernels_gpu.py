@@ -337,6 +337,29 @@ def test_stream_gemm(M, N, K, pdl):
     assert int(ws[:65536].view(torch.int32).abs().sum().item()) == 0, "slab counters must be left at zero"
 
 
+@pytest.mark.parametrize("M,I,K", [(16, 18944, 3584), (8, 1024, 512), (33, 640, 1024), (64, 4480, 264), (1, 64, 72), (16, 9472, 256)])
+def test_stream_gemm_swiglu(M, I, K):
+    """gate_up projection + SwiGLU in one weight stream vs stream_gemm (bf16) followed by swiglu: the same arithmetic per
+    element, bit-identical when the stream-K cut points of the two launches coincide (whole slabs per CTA, e.g. the 7B
+    decode shape), within one bf16 ulp otherwise (different fp32 partial-sum order); covers every MP variant."""
+    from time_r1_b200 import ops
+
+    x, w = rnd(M, K, seed=1), rnd(2 * I, K, seed=2, scale=0.05)
+    ws = ops.stream_gemm_workspace(M, DEV)
+    gu = ops.stream_gemm(x, w, ws)
+    want = ops.swiglu(gu)
+    got = ops.stream_gemm_swiglu(x, w, ws)
+    again = ops.stream_gemm_swiglu(x, w, ws)
+    if (M, I, K) == (16, 18944, 3584):
+        assert torch.equal(got, want), f"max diff {(got.float() - want.float()).abs().max().item()}"
+    close(got, want, 1e-5, 4.0 / 128, "stream swiglu vs gemm + swiglu")   # gate, up one bf16 ulp apart at most
+    assert torch.equal(got, again)
+    ref = x.float() @ w.float().t()
+    ref = torch.nn.functional.silu(ref[:, :I]) * ref[:, I:]
+    close(got, ref, 2e-2, 2e-2, "stream swiglu vs fp32")
+    assert int(ws[:65536].view(torch.int32).abs().sum().item()) == 0, "slab counters must be left at zero"
+
+
 def test_stream_gemm_chain_under_graph_with_pdl():
     """A captured chain rmsnorm -> stream_gemm -> swiglu -> stream_gemm with programmatic dependent launch gives the
     same result as the same chain launched eagerly without it (the weight prefetch must not outrun the dependency)."""

@@ -57,6 +57,8 @@ struct SgParams {
   int per_cta;        // units per CTA
   int stages;
   int out_f32;
+  int swiglu;         // 1: W = [gate rows | up rows] (N = 2 * half_n); a slab pairs 64 gate rows with their 64 up rows and
+  int half_n;         //    the epilogue emits y[M, half_n] = silu(gate) * up (bf16), as t1_swiglu does on the bf16 GEMM output
   unsigned long long* dbg;   // optional [4] globaltimer stamps of CTA 0: start, weights issued, dependency resolved, done
 };
 __device__ __forceinline__ unsigned long long gtimer() {
@@ -80,6 +82,7 @@ stream_gemm_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_const
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
   int* s_flag = reinterpret_cast<int*>(tmem_ptr_smem + 1);
   uint8_t* tiles = smem + SG_HEADER;
+  float* xs = reinterpret_cast<float*>(tiles + p.stages * STAGE_BYTES);   // swiglu: [MP][64] up values
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -123,7 +126,12 @@ stream_gemm_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_const
         const int u = u0 + i;
         const int slab = u / KB, kb = u - slab * KB;
         mbar_arrive_expect_tx(&full_bar[i], STAGE_BYTES);
-        tma_load_2d_hint(tiles + i * STAGE_BYTES, &tma_w, &full_bar[i], kb * SG_BK, slab * SG_BM, pol_stream);
+        if (p.swiglu) {
+          tma_load_2d_hint(tiles + i * STAGE_BYTES, &tma_w, &full_bar[i], kb * SG_BK, slab * 64, pol_stream);
+          tma_load_2d_hint(tiles + i * STAGE_BYTES + 64 * 128, &tma_w, &full_bar[i], kb * SG_BK, p.half_n + slab * 64, pol_stream);
+        } else {
+          tma_load_2d_hint(tiles + i * STAGE_BYTES, &tma_w, &full_bar[i], kb * SG_BK, slab * SG_BM, pol_stream);
+        }
       }
       if (dbg) p.dbg[1] = gtimer();
       pdl_wait();
@@ -140,7 +148,12 @@ stream_gemm_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_const
         const int slab = u / KB, kb = u - slab * KB;
         mbar_wait(&empty_bar[stage], phase ^ 1);
         mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-        tma_load_2d_hint(tiles + stage * STAGE_BYTES, &tma_w, &full_bar[stage], kb * SG_BK, slab * SG_BM, pol_stream);
+        if (p.swiglu) {
+          tma_load_2d_hint(tiles + stage * STAGE_BYTES, &tma_w, &full_bar[stage], kb * SG_BK, slab * 64, pol_stream);
+          tma_load_2d_hint(tiles + stage * STAGE_BYTES + 64 * 128, &tma_w, &full_bar[stage], kb * SG_BK, p.half_n + slab * 64, pol_stream);
+        } else {
+          tma_load_2d_hint(tiles + stage * STAGE_BYTES, &tma_w, &full_bar[stage], kb * SG_BK, slab * SG_BM, pol_stream);
+        }
         tma_load_2d_hint(tiles + stage * STAGE_BYTES + SG_W_BYTES, &tma_x, &full_bar[stage], kb * SG_BK, 0, pol_keep);
         if (++stage == stages) {
           stage = 0;
@@ -239,7 +252,32 @@ stream_gemm_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_const
           }
         }
       }
-      if (finish && n < p.N) {
+      if (p.swiglu) {
+        // lanes 0..63 hold the gate rows, lanes 64..127 the matching up rows: hand the up values over through shared
+        // memory, then y = silu(gate) * up on the bf16-rounded GEMM outputs (bit-identical to gemm -> t1_swiglu)
+        if (finish) {
+          const int col = slab * 64 + (r & 63);
+          if (r >= 64) {
+            const float b = (p.bias && col < p.half_n) ? __bfloat162float(p.bias[p.half_n + col]) : 0.f;
+#pragma unroll
+            for (int m = 0; m < MP; ++m) xs[m * 64 + (r - 64)] = __bfloat162float(__float2bfloat16(__uint_as_float(v[m]) + b));
+          }
+          epi_bar_sync();
+          if (r < 64 && col < p.half_n) {
+            const float b = p.bias ? __bfloat162float(p.bias[col]) : 0.f;
+            bf16* yp = reinterpret_cast<bf16*>(p.y) + col;
+#pragma unroll
+            for (int m = 0; m < MP; ++m) {
+              if (m < p.M) {
+                const float g = __bfloat162float(__float2bfloat16(__uint_as_float(v[m]) + b));
+                const float u = xs[m * 64 + r];
+                yp[(long long)m * p.ldy] = __float2bfloat16(g * (1.0f / (1.0f + __expf(-g))) * u);
+              }
+            }
+          }
+          epi_bar_sync();                          // xs is rewritten by the next finished slab
+        }
+      } else if (finish && n < p.N) {
         const float b = p.bias ? __bfloat162float(p.bias[n]) : 0.f;
         if (p.out_f32) {
           float* yp = reinterpret_cast<float*>(p.y) + n;
@@ -317,9 +355,9 @@ extern "C" void t1_stream_gemm_tune(int stages, int ctas_per_sm) {
   g_ctas_per_sm = ctas_per_sm > 0 ? ctas_per_sm : 1;
 }
 
-extern "C" int t1_stream_gemm(const void* x, long long ldx, const void* W, long long ldw, const void* bias, void* y,
-                              long long ldy, int M, int N, int K, int out_f32, void* workspace, long long workspace_bytes,
-                              cudaStream_t stream) {
+static int stream_gemm_impl(const void* x, long long ldx, const void* W, long long ldw, const void* bias, void* y,
+                            long long ldy, int M, int N, int K, int out_f32, int swiglu, void* workspace,
+                            long long workspace_bytes, cudaStream_t stream) {
   T1_CHECK_ARG(x && W && y && workspace, "t1_stream_gemm: null operand");
   T1_CHECK_ARG(M > 0 && M <= 64, "t1_stream_gemm: M=%d must be in [1, 64]", M);
   T1_CHECK_ARG(N > 0 && K > 0 && K % 8 == 0, "t1_stream_gemm: K %% 8 required (N=%d K=%d)", N, K);
@@ -327,6 +365,9 @@ extern "C" int t1_stream_gemm(const void* x, long long ldx, const void* W, long 
   T1_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)W & 15) == 0, "t1_stream_gemm: operands must be 16-byte aligned");
   const int MP = M <= 16 ? 16 : (M <= 32 ? 32 : 64);
   const int stage_bytes = SG_W_BYTES + MP * SG_BK * 2;
+  const int half_n = N / 2;
+  const int xs_bytes = swiglu ? MP * 64 * 4 : 0;
+  if (swiglu) T1_CHECK_ARG(N % 128 == 0 && !out_f32, "t1_stream_gemm_swiglu: N = 2*I with I %% 64 == 0 and bf16 output required (N=%d)", N);
   if (g_stages < 0) {
     g_stages = env_int("T1_STREAM_STAGES", 0);
     g_ctas_per_sm = env_int("T1_STREAM_CTAS_PER_SM", 1);
@@ -336,9 +377,9 @@ extern "C" int t1_stream_gemm(const void* x, long long ldx, const void* W, long 
   // (profiles/r01_decode_timeline_v2.txt): 10 stages 3.65 ms/step, 6 stages (two kernels co-resident) 3.71 ms.
   int stages = env_stages > 0 ? env_stages : (180 * 1024) / stage_bytes;
   if (stages > SG_MAX_STAGES) stages = SG_MAX_STAGES;
-  while (stages > 2 && SG_HEADER + 1024 + stages * stage_bytes > 227 * 1024) --stages;
-  const int smem = SG_HEADER + 1024 + stages * stage_bytes;
-  const int slabs = (N + SG_BM - 1) / SG_BM;
+  while (stages > 2 && SG_HEADER + 1024 + stages * stage_bytes + xs_bytes > 227 * 1024) --stages;
+  const int smem = SG_HEADER + 1024 + stages * stage_bytes + xs_bytes;
+  const int slabs = swiglu ? half_n / 64 : (N + SG_BM - 1) / SG_BM;
   const int kblocks = (K + SG_BK - 1) / SG_BK;
   const long long total = (long long)slabs * kblocks;
   T1_CHECK_ARG(total < (1LL << 30), "t1_stream_gemm: problem too large");
@@ -351,7 +392,7 @@ extern "C" int t1_stream_gemm(const void* x, long long ldx, const void* W, long 
   T1_CHECK_ARG(workspace_bytes >= need, "t1_stream_gemm: workspace too small (%lld < %lld)", workspace_bytes, need);
   T1_CHECK_ARG(((uintptr_t)workspace & 15) == 0, "t1_stream_gemm: workspace must be 16-byte aligned");
   CUtensorMap tw, tx;
-  int rc = t1_make_tmap_bf16(&tw, W, N, K, ldw, SG_BM, SG_BK);
+  int rc = t1_make_tmap_bf16(&tw, W, N, K, ldw, swiglu ? 64 : SG_BM, SG_BK);
   if (rc) return rc;
   rc = t1_make_tmap_bf16(&tx, x, M, K, ldx, MP, SG_BK);
   if (rc) return rc;
@@ -369,6 +410,8 @@ extern "C" int t1_stream_gemm(const void* x, long long ldx, const void* W, long 
   p.per_cta = per;
   p.stages = stages;
   p.out_f32 = out_f32;
+  p.swiglu = swiglu;
+  p.half_n = half_n;
   p.dbg = nullptr;
   if (g_dbg && g_dbg_slots > 0) {
     p.dbg = g_dbg + 4 * (size_t)(g_dbg_next % g_dbg_slots);
@@ -380,4 +423,21 @@ extern "C" int t1_stream_gemm(const void* x, long long ldx, const void* W, long 
   if (rc) return rc;
   t1_count_launch();
   return T1_OK;
+}
+
+extern "C" int t1_stream_gemm(const void* x, long long ldx, const void* W, long long ldw, const void* bias, void* y,
+                              long long ldy, int M, int N, int K, int out_f32, void* workspace, long long workspace_bytes,
+                              cudaStream_t stream) {
+  return stream_gemm_impl(x, ldx, W, ldw, bias, y, ldy, M, N, K, out_f32, 0, workspace, workspace_bytes, stream);
+}
+
+// y[M, I] = silu(x W_gate^T) * (x W_up^T) with W = [W_gate; W_up] of shape [2I, K] (the fused gate_up weight of the
+// Qwen2 MLP, HF Q25:611-624): the gate_up projection and the SwiGLU of the decode step in one weight stream.
+// Same arithmetic per element as t1_stream_gemm (bf16 output) followed by t1_swiglu; bit-identical when the stream-K
+// cut points of the two launches coincide (whole slabs per CTA, e.g. the 7B decode shapes).  I % 64 == 0.
+extern "C" int t1_stream_gemm_swiglu(const void* x, long long ldx, const void* W, long long ldw, const void* bias, void* y,
+                                     long long ldy, int M, int I, int K, void* workspace, long long workspace_bytes,
+                                     cudaStream_t stream) {
+  T1_CHECK_ARG(I > 0 && I % 64 == 0, "t1_stream_gemm_swiglu: I=%d must be a positive multiple of 64", I);
+  return stream_gemm_impl(x, ldx, W, ldw, bias, y, ldy, M, 2 * I, K, 0, 1, workspace, workspace_bytes, stream);
 }

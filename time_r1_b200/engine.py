@@ -419,8 +419,11 @@ class Engine:
                          ptr(st["step"]), ptr(attn), attn.stride(0), scale, 1, s)
                 ops.stream_gemm(attn, self.p(pre + "self_attn.o_proj.weight"), ws, out=o)
                 ops.rmsnorm(x, self.p(pre + "post_attention_layernorm.weight"), eps, delta=o, out=h)
-                ops.stream_gemm(h, self.p(pre + "mlp.gate_up.weight"), ws, out=gu)
-                ops.swiglu(gu, out=act)
+                if cfg.intermediate_size % 64 == 0:
+                    ops.stream_gemm_swiglu(h, self.p(pre + "mlp.gate_up.weight"), ws, out=act)    # SwiGLU in the epilogue
+                else:
+                    ops.stream_gemm(h, self.p(pre + "mlp.gate_up.weight"), ws, out=gu)
+                    ops.swiglu(gu, out=act)
                 ops.stream_gemm(act, self.p(pre + "mlp.down_proj.weight"), ws, out=down)
             ops.rmsnorm(x, self.p("model.norm.weight"), eps, delta=down, out=st["hN"])
             ops.stream_gemm(st["hN"], self.lm_head(), ws, out=st["logits"])

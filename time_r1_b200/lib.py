@@ -66,6 +66,7 @@ _SIGNATURES: dict[str, list] = {
     # decode.cu
     "t1_skinny_gemm": [vp, i64, vp, i64, vp, vp, i64, i32, i32, i32, i32, i32, vp],
     "t1_stream_gemm": [vp, i64, vp, i64, vp, vp, i64, i32, i32, i32, i32, vp, i64, vp],
+    "t1_stream_gemm_swiglu": [vp, i64, vp, i64, vp, vp, i64, i32, i32, i32, vp, i64, vp],
     "t1_stream_gemm_workspace_bytes": [i32],
     "t1_set_pdl": [i32],
     "t1_stream_gemm_tune": [i32, i32],

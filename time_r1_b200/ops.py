@@ -128,6 +128,20 @@ def stream_gemm(x, w, workspace, out=None, bias=None, out_dtype=BF16):
     return out
 
 
+def stream_gemm_swiglu(x, w_gate_up, workspace, out=None, bias=None):
+    """out[M<=64, I] = silu(x @ Wg^T) * (x @ Wu^T) with w_gate_up = [Wg; Wu] ([2I, K]): gate_up projection + SwiGLU in
+    one weight stream (same per-element arithmetic as stream_gemm followed by swiglu)."""
+    M, K = x.shape
+    I = w_gate_up.shape[0] // 2
+    assert x.stride(1) == 1 and w_gate_up.stride(1) == 1 and w_gate_up.shape[1] == K
+    if out is None:
+        out = torch.empty((M, I), device=x.device, dtype=BF16)
+    assert out.shape == (M, I) and out.stride(1) == 1 and out.dtype == BF16
+    call("t1_stream_gemm_swiglu", ptr(x), x.stride(0), ptr(w_gate_up), w_gate_up.stride(0), ptr(bias), ptr(out), out.stride(0),
+         M, I, K, ptr(workspace), workspace.numel(), stream_ptr())
+    return out
+
+
 def linear(x, w, out=None, bias=None, accumulate=False, out_dtype=BF16):
     """Dispatch on the row count: <= 64 rows stream the weights (HBM-bound), otherwise the tcgen05 tile kernel."""
     if x.shape[0] <= 64 and w.shape[0] % 16 == 0 and x.shape[1] % 32 == 0 and (bias is None or bias.dtype == BF16):
