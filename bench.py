@@ -44,6 +44,10 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--phase-times", action="store_true", help="print a per-phase breakdown to stderr")
     ap.add_argument("--kernel-times", action="store_true", help="print per-entry-point CUDA-event totals of one extra step to stderr")
+    ap.add_argument("--ncu-range", action="store_true",
+                    help="after the warm-up run ONE step inside cudaProfilerStart/Stop with only the first decode-graph replay "
+                         "profiled (ncu --profile-from-start off), then exit: the launch list of a step = its eager launches + "
+                         "one decode step (x C-1 replays)")
     return ap.parse_args()
 
 
@@ -288,6 +292,26 @@ def run_ours(args):
 
     for i in range(args.warmup):
         one_step(i, False)
+    if args.ncu_range:
+        rt = torch.cuda.cudart()
+
+        def hook(i, n):
+            if i == 1:
+                torch.cuda.synchronize()
+                rt.cudaProfilerStop()        # replays 1 .. C-2 repeat replay 0: skipped
+            elif i == n - 1 and n > 2:
+                torch.cuda.synchronize()
+                rt.cudaProfilerStart()
+
+        eng.replay_hook = hook
+        torch.cuda.synchronize()
+        rt.cudaProfilerStart()
+        one_step(args.warmup, False)
+        torch.cuda.synchronize()
+        rt.cudaProfilerStop()
+        print(json.dumps({"ncu_range": "one step: eager launches + decode replays 0 and C-2", "decode_replays_per_step": C - 1,
+                          "launches_per_decode_step": eng._last_decode_state["launches_per_step"]}), flush=True)
+        return
     if args.phase_times and rank == 0:
         tm = {}
         one_step(args.warmup, False, timers=tm)

@@ -13,6 +13,7 @@
 //   warps 4..7  epilogue       : tcgen05.ld 32x32b -> registers -> bias / accumulate / convert -> global
 // Pipelines: smem ring (full/empty mbarriers, 4 stages of 48 KB) and TMEM ring (tmem_full/tmem_empty).
 #include "t1_common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -46,7 +47,7 @@ struct EpiParams {
 template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, int M, int N,
-                    int K, EpiParams epi) {
+                    int K, int group_m, EpiParams epi) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_tiles = smem;
@@ -63,6 +64,16 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   const int num_n = (N + BN - 1) / BN;
   const int num_tiles = num_m * num_n;
   const int num_k = (K + BK - 1) / BK;
+  // Tile rasterisation: m-blocks are walked in groups of group_m; inside a group the n-blocks advance slowest, so the
+  // 148 tiles in flight share group_m A row-blocks and ~148/group_m B row-blocks.  group_m = num_m is plain m-fastest.
+  const int tiles_per_group = group_m * num_n;
+  auto tile_coords = [&](int tile, int& m_blk, int& n_blk) {
+    const int g = tile / tiles_per_group, rem = tile - g * tiles_per_group;
+    const int m0 = g * group_m;
+    const int gm = min(group_m, num_m - m0);
+    n_blk = rem / gm;
+    m_blk = m0 + (rem - n_blk * gm);
+  };
 
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
@@ -91,7 +102,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile % num_m, n_blk = tile / num_m;
+        int m_blk, n_blk;
+        tile_coords(tile, m_blk, n_blk);
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
@@ -160,7 +172,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     const bool bias_f32 = epi.flags & GEMM_BIAS_F32;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int m_blk = tile % num_m, n_blk = tile / num_m;
+      int m_blk, n_blk;
+        tile_coords(tile, m_blk, n_blk);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
@@ -275,10 +288,30 @@ extern "C" int t1_gemm_bf16_tn(const void* A, long long lda, const void* B, long
   const int num_tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int grid = num_tiles < t1_num_sms() ? num_tiles : t1_num_sms();
   EpiParams epi{D, bias, ldd, flags};
-  if (a_mn && b_mn) gemm_bf16_tn_kernel<true, true><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, M, N, K, epi);
-  else if (a_mn) gemm_bf16_tn_kernel<true, false><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, M, N, K, epi);
-  else if (b_mn) gemm_bf16_tn_kernel<false, true><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, M, N, K, epi);
-  else gemm_bf16_tn_kernel<false, false><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, M, N, K, epi);
+  // DRAM-traffic model for the raster order (L2 = 126 MB; measured with ncu on the gate_up wgrad, M=37888 N=3584 K=5888:
+  // m-fastest re-read dY 14x = 6.3 GB per launch).  An operand that fits in ~48 MB of L2 is read once whatever the order;
+  // otherwise keep a group of A row-blocks resident (<= 40 MB) while B streams past it.
+  const int num_m = (M + BM - 1) / BM;
+  int group_m = num_m;
+  {
+    const double a_bytes = 2.0 * M * K, b_bytes = 2.0 * N * K, cap = 48e6;
+    if (a_bytes > cap) {
+      int gm = (int)(40e6 / (2.0 * BM * K));
+      if (gm < 1) gm = 1;
+      if (gm > num_m) gm = num_m;
+      const double grouped = a_bytes + (b_bytes <= cap ? b_bytes : b_bytes * ((num_m + gm - 1) / gm));
+      const int num_n = (N + BN - 1) / BN;
+      const double waves_n = (double)num_n * num_m / t1_num_sms() / (num_m < t1_num_sms() ? 1.0 : (double)num_m / t1_num_sms());
+      const double m_fast = a_bytes * (num_m >= t1_num_sms() ? num_n : (waves_n < 1.0 ? 1.0 : waves_n)) + b_bytes;
+      if (grouped < m_fast) group_m = gm;
+    }
+    static const char* env = getenv("T1_GEMM_GROUP_M");
+    if (env && atoi(env) > 0) group_m = atoi(env) < num_m ? atoi(env) : num_m;
+  }
+  if (a_mn && b_mn) gemm_bf16_tn_kernel<true, true><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, M, N, K, group_m, epi);
+  else if (a_mn) gemm_bf16_tn_kernel<true, false><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, M, N, K, group_m, epi);
+  else if (b_mn) gemm_bf16_tn_kernel<false, true><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, M, N, K, group_m, epi);
+  else gemm_bf16_tn_kernel<false, false><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, M, N, K, group_m, epi);
   T1_CUDA_LAUNCH_CHECK("t1_gemm_bf16_tn");
   return T1_OK;
 }

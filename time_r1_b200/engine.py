@@ -96,6 +96,7 @@ class Engine:
         self.axis_vit = torch.cat([torch.zeros(vh // 2, dtype=I32), torch.ones(vh // 2, dtype=I32)]).to(self.dev)
         self._decode_cache: dict = {}
         self.metrics_launches = 0
+        self.replay_hook = None
 
     # ------------------------------------------------------------------------------------------
     # parameter access
@@ -556,7 +557,9 @@ class Engine:
                 done = 0
                 while done < n_steps:
                     burst = min(check_every, n_steps - done)
-                    for _ in range(burst):
+                    for i in range(burst):
+                        if self.replay_hook is not None:
+                            self.replay_hook(done + i, n_steps)     # profiling windows (bench.py --ncu-range)
                         st["graph"].replay()
                     self.metrics_launches += burst * st["launches_per_step"]
                     done += burst

@@ -52,6 +52,7 @@ def main():
         eng.ref = None
         eng._decode_cache = {}
         eng.metrics_launches = 0
+        eng.replay_hook = None
         hd = cfg.head_dim
         eng.inv_freq_llm = (1.0 / (cfg.rope_theta ** (torch.arange(0, hd, 2, dtype=torch.float32) / hd))).to(dev)
         from time_r1_b200 import indexing

@@ -15,6 +15,7 @@ def make_engine(cfg, mw, run, dev):
     eng.ref = None
     eng._decode_cache = {}
     eng.metrics_launches = 0
+    eng.replay_hook = None
     hd = cfg.head_dim
     eng.inv_freq_llm = (1.0 / (cfg.rope_theta ** (torch.arange(0, hd, 2, dtype=torch.float32) / hd))).to(dev)
     eng.axis_llm = torch.from_numpy(indexing.mrope_channel_axes(cfg)).to(dev)
