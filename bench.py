@@ -25,6 +25,11 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE gemm_bf16_tn launch from the committed ncu --set full capture
+# (profiles/r01_ncu_full_top_kernels_v3.txt): the gate_up projection over the packed scoring rows, the largest GEMM of the
+# step.  Algorithmic bytes of that launch: A 42.2 MB + B 271.6 MB + D 446.2 MB = 760 MB.
+NCU_GEMM_TRAFFIC = {"bytes": 873.8e6, "note": "ncu, one launch M=5888 N=37888 K=3584 (algorithmic 760e6 B, 1.6 TFLOP, 1.090 ms = 1467 TFLOP/s, "
+                                            "tensor pipe 81.6% active); the wgrad form M=37888 N=3584 K=5888 moved 6.6e9 B before the grouped raster"}
 METRIC = "grpo_rollout_samples_per_sec"
 UNIT = "samples/s"
 
@@ -224,6 +229,40 @@ def attention_microbench(eng, Ps, G: int, C: int):
             "ms": round(ms, 5), "gbs": round(kv_bytes / ms / 1e6, 1)}
 
 
+def decode_step_microbench(eng, Ps, G: int, C: int):
+    """The captured decode step (one token for every sequence of the step's prompt-groups: 113 weight-streaming GEMMs,
+    28 attention launches, norms, sampler) replayed at mid-rollout: HBM bytes that MUST move per step (every LLM
+    weight once + the unique K/V of all layers) / time.  CUDA events around 16 graph replays, median of 9."""
+    import torch
+
+    cfg = eng.cfg
+    st = eng._decode_state(tuple(Ps), G, C)
+    if st.get("graph") is None:
+        return None
+    L, D, I, V = cfg.num_hidden_layers, cfg.hidden_size, cfg.intermediate_size, cfg.vocab_size
+    Hq, Hkv, hd = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim
+    step = C // 2
+    w_bytes = 2.0 * (L * (cfg.qkv_dim * D + Hq * hd * D + 2 * I * D + D * I) + V * D)
+    kv_bytes = L * sum(2.0 * Hkv * hd * 2 * (P + G * (step + 1)) for P in Ps)
+    snap = (st["next_ids"].clone(), st["finished"].clone(), st["out_ids"].clone())
+    ts = []
+    for _ in range(9):
+        st["step"].fill_(step)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(16):
+            st["graph"].replay()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) / 16)
+    st["next_ids"].copy_(snap[0]); st["finished"].copy_(snap[1]); st["out_ids"].copy_(snap[2])
+    ts.sort()
+    ms = ts[len(ts) // 2]
+    return {"bound": "hbm", "kernel": "captured decode step (stream_gemm_kernel x%d + decode_attn_tc x%d + norms + sampler)" % (4 * L + 1, L),
+            "launches": st["launches_per_step"], "weight_bytes": w_bytes, "kv_bytes": kv_bytes, "ms": round(ms, 4),
+            "achieved": round((w_bytes + kv_bytes) / ms / 1e6, 1), "unit": "GB/s"}
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -347,15 +386,22 @@ def run_ours(args):
     algo = {k: v * NG for k, v in flops.step_flops(cfg, grid, P, G, C).items()}
     roofline = {
         "bound": "tensor", "kernel": "gemm_bf16_tn (tcgen05)", "achieved": round(gemm_tflops, 1), "peak": peak_tf, "unit": "TFLOP/s",
-        "frac": round(gemm_tflops / peak_tf, 4), "traffic": None, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback",
+        "frac": round(gemm_tflops / peak_tf, 4), "traffic": NCU_GEMM_TRAFFIC["bytes"], "traffic_note": NCU_GEMM_TRAFFIC["note"], "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback",
         "launches_per_step": gm["launches"] // max(1, args.steps), "gemm_ms_per_step": round(gm["ms"] / args.steps, 2),
         "gemm_tflop_per_step": round(gm["flops"] / args.steps / 1e12, 1),
         "step_algorithmic_tflop": round(algo["total"] / 1e12, 1),
         "step_frac_of_flop_roofline": round(algo["total"] / (ms_per_step / 1e3) / 1e12 / peak_tf, 4),
     }
-    attn = attention_microbench(eng, [len(inp[0]) for inp in inputs], G, C)
+    Ps_all = [len(inp[0]) for inp in inputs]
+    attn = attention_microbench(eng, Ps_all, G, C)
     attn["peak_gbs"] = peaks.get("hbm_gbs", 6650.0)
     attn["frac"] = round(attn["gbs"] / attn["peak_gbs"], 4)
+    dec = decode_step_microbench(eng, Ps_all, G, C)
+    if dec is not None:
+        dec["peak"] = peaks.get("hbm_gbs", 6650.0)
+        dec["frac"] = round(dec["achieved"] / dec["peak"], 4)
+        dec["peak_source"] = "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback"
+        dec["share_of_step"] = round(dec["ms"] * (C - 1) / ms_per_step, 4)
     line = {
         "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms_per_step, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
@@ -366,6 +412,7 @@ def run_ours(args):
         "e2e": {"value": round(e2e_value, 4), "unit": UNIT, "h2d_bytes_per_step": int(NG * (pix_host.numel() * 4 + ids.size * 4)), "d2h_bytes_per_step": int(NG * (G * C * 4 + 4) + 4)},
         "gpu_launches": launches,
         "roofline": roofline,
+        "roofline_decode": dec,
         "attn": attn,
     }
     if world == 1 and not args.no_cpu_baseline:

@@ -166,8 +166,8 @@ fa_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   uint64_t* aux_full = bars + 5;             // 2 (32 arrivals)
   uint64_t* s_full = bars + 7;               // 1
   uint64_t* dp_full = bars + 8;              // 1
-  uint64_t* p_ready = bars + 9;              // 1 (512 arrivals)
-  uint64_t* ds_ready = bars + 10;            // 1 (512 arrivals)
+  uint64_t* p_ready = bars + 9;              // 1 (one arrival per element-wise warp)
+  uint64_t* ds_ready = bars + 10;            // 1 (one arrival per element-wise warp)
   uint64_t* acc_done = bars + 11;            // 1
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 12);
 
@@ -188,8 +188,8 @@ fa_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     }
     mbar_init(s_full, 1);
     mbar_init(dp_full, 1);
-    mbar_init(p_ready, 128 * NS);
-    mbar_init(ds_ready, 128 * NS);
+    mbar_init(p_ready, 4 * NS);            // one arrival per element-wise warp
+    mbar_init(ds_ready, 4 * NS);
     mbar_init(acc_done, 1);
     mbar_fence_init();
   }
@@ -341,7 +341,8 @@ fa_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         tmem_st_wait();
       }
       tc_fence_before();
-      mbar_arrive(p_ready);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_ready);
       // ---- dS^T ----
       mbar_wait(dp_full, it & 1);
       tc_fence_after();
@@ -366,7 +367,8 @@ fa_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       tmem_st_32x32b_x16(t_lane + T_DP + part * 32, dk);
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(ds_ready);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ds_ready);
       ++it;
     }
     // ---- epilogue: fp32 partials of this q head ----
@@ -432,8 +434,8 @@ fa_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   uint64_t* v_empty = v_full + 1;            // 1
   uint64_t* s_full = v_full + 2;             // 2
   uint64_t* dp_full = v_full + 4;            // 1
-  uint64_t* dp_taken = v_full + 5;           // 1 (512 arrivals)
-  uint64_t* ds_ready = v_full + 6;           // 1 (512 arrivals)
+  uint64_t* dp_taken = v_full + 5;           // 1 (one arrival per element-wise warp)
+  uint64_t* ds_ready = v_full + 6;           // 1 (one arrival per element-wise warp)
   uint64_t* dq_done = v_full + 7;            // 1
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(v_full + 8);
   int* s_red = reinterpret_cast<int*>(v_full + 9);   // 4 ints
@@ -455,8 +457,8 @@ fa_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     mbar_init(&s_full[0], 1);
     mbar_init(&s_full[1], 1);
     mbar_init(dp_full, 1);
-    mbar_init(dp_taken, 128 * NS);
-    mbar_init(ds_ready, 128 * NS);
+    mbar_init(dp_taken, 4 * NS);           // one arrival per element-wise warp
+    mbar_init(ds_ready, 4 * NS);
     mbar_init(dq_done, 1);
     mbar_fence_init();
   }
@@ -590,7 +592,8 @@ fa_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       tmem_ld_32x32b_x32(t_lane + T_DP + part * 32, dp);
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(dp_taken);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dp_taken);
       mbar_wait(&s_full[it & 1], (it >> 1) & 1);
       tc_fence_after();
       const uint32_t tS = t_lane + T_S0 + (it & 1) * 128 + part * 32;
@@ -617,7 +620,8 @@ fa_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       tmem_st_32x32b_x16(tS, pk);
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(ds_ready);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ds_ready);
     }
     if (n > 0) {
       mbar_wait(dq_done, 0);

@@ -57,7 +57,7 @@ fa_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   uint64_t* v_full = bars + 5;              // 2
   uint64_t* v_empty = bars + 7;             // 2  (released when O += P V retires)
   uint64_t* s_full = bars + 9;              // 2
-  uint64_t* p_full = bars + 11;             // 1 (128 arrivals)
+  uint64_t* p_full = bars + 11;             // 1 (one arrival per softmax warp)
   uint64_t* pv_done = bars + 12;            // 1
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 13);
   int* s_red = reinterpret_cast<int*>(bars + 14);  // 4 ints
@@ -88,7 +88,7 @@ fa_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       mbar_init(&v_empty[i], 1);
       mbar_init(&s_full[i], 1);
     }
-    mbar_init(p_full, 128 * NS);
+    mbar_init(p_full, 4 * NS);             // one arrival per softmax warp
     mbar_init(pv_done, 1);
     mbar_fence_init();
   }
@@ -268,7 +268,8 @@ fa_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       l += rs;
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(p_full);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);     // 16 arrivals per tile instead of 512 same-address shared-memory atomics
     }
     // ---- epilogue: combine the partial row sums, normalise, store this thread's output columns ----
     s_xch[(2 * NS + part) * TQ + r] = l;
