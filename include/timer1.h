@@ -219,7 +219,9 @@ int t1_bf16_to_f32(const void* src, float* dst, long long n, cudaStream_t stream
 /* ---- GRPO: rewards, advantage, loss (warp/block-reduction tier) ------------------------------------------- */
 /* IoU rewards in fp64, bit-identical to CPython: mode 0 = iou_timestamp_reward (main.py:145-181), mode 1 =
  * iou_timestamp_reward_v2 (main.py:184-231).  valid[i] == 0 (unparsable completion) -> 0.  union <= 0 -> 0 (the
- * reference leaves `iou` unbound there, main.py:165-168). */
+ * reference leaves `iou` unbound there, main.py:165-168).  mode 2 = difficulty of the per-epoch sample filter,
+ * 100 * compute_IoU with numpy float64 semantics incl. NaN / inf for an empty union
+ * (src/vllm_inference/calc_difficulty.py:10-37). */
 int t1_iou_reward(int mode, const double* pred_s, const double* pred_e, const unsigned char* valid, const double* gt_s,
                   const double* gt_e, const double* dur, double* out64, float* out32, int n, cudaStream_t stream);
 /* rewards = sum over functions; per-group mean, UNBIASED std; adv = (r - mean) / (std + eps)

@@ -21,7 +21,15 @@ __global__ void iou_reward_kernel(int mode, const double* __restrict__ ps, const
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double reward = 0.0;
-  if (valid[i]) {
+  if (valid[i] && mode == 2) {
+    // difficulty of the per-epoch sample filter: 100 * compute_IoU (src/vllm_inference/calc_difficulty.py:10-37), numpy
+    // float64 semantics: the union is clamped at 0 and 0/0 = NaN, x/0 = inf propagate (dropped later by
+    // get_difficulty_safe, src/utils/process_data.py:11-24)
+    const double s = gs[i], e = ge[i], from = ps[i], to = pe[i];
+    const double inter = fmax(0.0, __dsub_rn(fmin(to, e), fmax(from, s)));
+    const double uni = fmax(0.0, __dsub_rn(fmax(to, e), fmin(from, s)));
+    reward = __dmul_rn(__ddiv_rn(inter, uni), 100.0);
+  } else if (valid[i]) {
     const double s = gs[i], e = ge[i], from = ps[i], to = pe[i];
     const double inter = fmax(0.0, __dsub_rn(fmin(to, e), fmax(from, s)));
     const double uni = __dsub_rn(fmax(to, e), fmin(from, s));
@@ -267,8 +275,9 @@ __global__ void eos_mask_kernel(const int* __restrict__ ids, int rows, int C, in
 extern "C" int t1_iou_reward(int mode, const double* pred_s, const double* pred_e, const unsigned char* valid,
                              const double* gt_s, const double* gt_e, const double* dur, double* out64, float* out32,
                              int n, cudaStream_t stream) {
-  T1_CHECK_ARG(mode == 0 || mode == 1, "t1_iou_reward: mode must be 0 (iou) or 1 (iou_v2)");
-  T1_CHECK_ARG(mode == 0 || dur != nullptr, "t1_iou_reward: iou_v2 needs durations");
+
+  T1_CHECK_ARG(mode >= 0 && mode <= 2, "t1_iou_reward: mode %d not in {0: iou, 1: iou_v2, 2: difficulty}", mode);
+  T1_CHECK_ARG(mode != 1 || dur != nullptr, "t1_iou_reward: iou_v2 needs durations");
   if (n == 0) return T1_OK;
   T1_CHECK_ARG(n > 0 && pred_s && pred_e && valid && gt_s && gt_e, "t1_iou_reward: bad arguments");
   iou_reward_kernel<<<(n + 255) / 256, 256, 0, stream>>>(mode, pred_s, pred_e, valid, gt_s, gt_e, dur, out64, out32, n);

@@ -259,6 +259,23 @@ class TimeR1_Trainer:
             raise RuntimeError("a processing_class with batch_decode() is required to turn completions into text")
         return pc.batch_decode(ids, skip_special_tokens=True)
 
+    # ------------------------------------------------------------------ per-epoch sample filter
+    def filter_samples(self, samples: Optional[list] = None, k: int = 2500, max_new_tokens: int = 1024, batch: int = 4) -> tuple:
+        """One filtering pass of TimeRFT with the CURRENT policy (what scripts/posttrain/train_rl_SF.sh:71-111 runs
+        between training epochs through evaluate.py -> calc_difficulty.py -> process_data.py --task 0070_all): greedy
+        rollout of every sample, difficulty = 100 x IoU, keep 0 < IoU <= 0.7, difficulty-sorted linspace subsample of k.
+        Samples are dataset rows with `qid` and `timestamp` (or `solution`) columns; this rank handles rows
+        rank, rank + world, ... (evaluate.py --curr_idx / --total_idx).  Returns (selected_rows, annotated_rows)."""
+        from .filtering import GreedyFilter
+
+        rows = list(self.train_dataset if samples is None else samples)[self.rank::self.world]
+        rows = [dict(r, qid=r.get("qid", i), timestamp=r.get("timestamp", r.get("solution"))) for i, r in enumerate(rows)]
+        pc = self.processing_class
+        if pc is None:
+            raise RuntimeError("a processing_class with decode() is required to turn completions into text")
+        decode = lambda ids: pc.decode(ids, skip_special_tokens=False)
+        return GreedyFilter(self.engine, self._prompt_from_example, decode, max_new_tokens=max_new_tokens, batch=batch).run(rows, k)
+
     # ------------------------------------------------------------------ one micro-step
     def _prepare(self, example: dict):
         """(Prompt, reward callback) for one dataset row — reward protocol of timer1_trainer.py:685-698."""
