@@ -216,6 +216,16 @@ int t1_f32_to_bf16(const float* src, void* dst, long long n, int accumulate, cud
 int t1_add_bf16(void* y, const void* x, long long n, cudaStream_t stream);
 int t1_bf16_to_f32(const void* src, float* dst, long long n, cudaStream_t stream);
 
+/* ---- video pre-processing (HF Qwen2-VL video processor, timer1_trainer.py:547-556) --------------------------- */
+/* Rescale + normalise + patchify of resized frames [T, 3, H, W] (uint8 when in_u8 != 0, else fp32; values 0..255):
+ * out_f32 [N, 1176] = pixel_values_videos bit-identical to HF models/qwen2_vl/video_processing_qwen2_vl.py:236-272
+ * ((x - mean*255) / (std*255) in fp32, permute (0,1,4,7,5,8,3,2,6,9), odd T padded with the last frame); and / or
+ * out_bf16 [N, 1176] with rows gathered through perm_rows (device int32 [N], nullable) — the ViT window order the
+ * patch-embed GEMM reads.  mean255 / std255: HOST arrays of 3 floats = fp32(mean) * 255, fp32(std) * 255. */
+int t1_video_patchify(const void* frames, int in_u8, int T, int H, int W, int patch, int tpatch, int merge,
+                      const float* mean255, const float* std255, const int* perm_rows, float* out_f32, void* out_bf16,
+                      cudaStream_t stream);
+
 /* ---- GRPO: rewards, advantage, loss (warp/block-reduction tier) ------------------------------------------- */
 /* IoU rewards in fp64, bit-identical to CPython: mode 0 = iou_timestamp_reward (main.py:145-181), mode 1 =
  * iou_timestamp_reward_v2 (main.py:184-231).  valid[i] == 0 (unparsable completion) -> 0.  union <= 0 -> 0 (the

@@ -37,9 +37,12 @@ BF16, F32, I32 = torch.bfloat16, torch.float32, torch.int32
 class Prompt:
     """One prompt-group's inputs, as produced by the HF processor in the reference (timer1_trainer.py:547-565)."""
     input_ids: np.ndarray                 # [P] int
-    pixel_values: torch.Tensor            # [N, patch_dim] fp32 on the device (pixel_values_videos)
+    pixel_values: torch.Tensor | None     # [N, patch_dim] fp32 on the device (pixel_values_videos), or None with `frames`
     grid_thw: list                        # [(t, h, w)]
     second_per_grid_ts: list | None = None
+    # alternative to pixel_values: the resized frames [T, 3, H, W] (uint8 or fp32, 0..255) of ONE video on the device;
+    # the HF processor's rescale / normalise / patchify then runs in t1_video_patchify, fused with the window gather
+    frames: torch.Tensor | None = None
 
 
 @dataclass
@@ -115,15 +118,21 @@ class Engine:
     # ------------------------------------------------------------------------------------------
     # ViT
     # ------------------------------------------------------------------------------------------
-    def vit_blocks(self, pixel_values: torch.Tensor, grid_thw) -> tuple[torch.Tensor, torch.Tensor, indexing.VisionPlan]:
+    def vit_blocks(self, pixel_values, grid_thw, frames=None) -> tuple[torch.Tensor, torch.Tensor, indexing.VisionPlan]:
         """Patch-embed + all vision blocks. Returns (x, pending_delta, plan): the merger's input is x + pending_delta
         (the last block's MLP output, whose residual add is fused into the merger norm)."""
         cfg = self.cfg
         plan = indexing.vision_plan(cfg, grid_thw)
         N, vd, H, hd = plan.n_patches, cfg.vit_hidden, cfg.vit_heads, cfg.vit_head_dim
-        assert pixel_values.shape == (N, cfg.patch_dim) and pixel_values.dtype == F32
         perm = self._i32(plan.perm_rows)
-        pix = ops.gather_rows_f32(pixel_values, perm)                       # cast + window-order permutation
+        if frames is not None:
+            assert len(grid_thw) == 1, "the frames path takes one video per prompt"
+            _, pix, g = ops.video_patchify(frames, cfg.patch_size, cfg.temporal_patch_size, cfg.spatial_merge_size,
+                                           perm_rows=perm, want_f32=False, want_bf16=True)
+            assert tuple(g) == tuple(int(v) for v in grid_thw[0]), (g, grid_thw)
+        else:
+            assert pixel_values.shape == (N, cfg.patch_dim) and pixel_values.dtype == F32
+            pix = ops.gather_rows_f32(pixel_values, perm)                   # cast + window-order permutation
         x = ops.gemm(pix, self.w.get("visual.patch_embed.proj.weight"))     # Conv3d == GEMM
         cos, sin = ops.rope_table(self._i32(plan.pos_hw), self.axis_vit, self.inv_freq_vit)
         win_lo, win_hi = self._i32(plan.win_lo), self._i32(plan.win_hi)
@@ -185,7 +194,7 @@ class Engine:
         return m
 
     def vit_forward(self, prompt: Prompt, wset: str = "policy"):
-        x, delta, plan = self.vit_blocks(prompt.pixel_values, prompt.grid_thw)
+        x, delta, plan = self.vit_blocks(prompt.pixel_values, prompt.grid_thw, frames=prompt.frames)
         emb = self.merger(x, delta, plan, wset)
         return emb, x, plan
 
@@ -867,7 +876,7 @@ class Engine:
         mark("start")
         vit = []
         for prompt in prompts:
-            x_vit, delta, plan = self.vit_blocks(prompt.pixel_values, prompt.grid_thw)
+            x_vit, delta, plan = self.vit_blocks(prompt.pixel_values, prompt.grid_thw, frames=prompt.frames)
             emb = self.merger(x_vit, delta, plan, "policy")                 # x_vit now holds the final ViT stream
             vit.append((emb, x_vit, plan))
         mark("vit")

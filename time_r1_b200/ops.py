@@ -336,6 +336,32 @@ def attn_bwd_tc(q, k, v, o, do, lse, row_lo, row_hi, shared_len, Hq, Hkv, head_d
     return dq, dk, dv
 
 
+OPENAI_CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
+OPENAI_CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
+
+
+def video_patchify(frames, patch=14, tpatch=2, merge=2, mean=OPENAI_CLIP_MEAN, std=OPENAI_CLIP_STD, rescale_factor=1.0 / 255.0,
+                   perm_rows=None, want_f32=True, want_bf16=False):
+    """frames [T, 3, H, W] uint8 or fp32 (0..255) on the device -> (pixel_values_videos [N, 1176] fp32 in HF order or None,
+    bf16 [N, 1176] gathered through perm_rows or None, (grid_t, grid_h, grid_w))."""
+    import ctypes
+    import numpy as np
+
+    assert frames.is_cuda and frames.dim() == 4 and frames.shape[1] == 3 and frames.is_contiguous()
+    assert frames.dtype in (torch.uint8, F32)
+    T, _, H, W = frames.shape
+    gt, gh, gw = (T + tpatch - 1) // tpatch, H // patch, W // patch
+    N, row = gt * gh * gw, 3 * tpatch * patch * patch
+    # fused rescale-and-normalise constants exactly as the HF processor forms them: fp32 tensor * python float
+    m255 = (torch.tensor(mean, dtype=F32) * (1.0 / rescale_factor)).numpy().astype(np.float32)
+    s255 = (torch.tensor(std, dtype=F32) * (1.0 / rescale_factor)).numpy().astype(np.float32)
+    o32 = torch.empty((N, row), device=frames.device, dtype=F32) if want_f32 else None
+    o16 = torch.empty((N, row), device=frames.device, dtype=BF16) if want_bf16 else None
+    call("t1_video_patchify", ptr(frames), 1 if frames.dtype == torch.uint8 else 0, T, H, W, patch, tpatch, merge,
+         m255.ctypes.data_as(ctypes.c_void_p), s255.ctypes.data_as(ctypes.c_void_p), ptr(perm_rows), ptr(o32), ptr(o16), stream_ptr())
+    return o32, o16, (gt, gh, gw)
+
+
 def kv_cache_tensor_maps(caches, Hkv, head_dim):
     """Host table (numpy [n, 128] uint8) of 128-byte TMA tensor maps (box 128 rows x 64 columns, SWIZZLE_128B) over a list of
     [rows, Hkv*head_dim] bf16 cache tensors, in list order — the `maps` argument of t1_decode_attn_cluster."""

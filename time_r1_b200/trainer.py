@@ -246,10 +246,20 @@ class TimeR1_Trainer:
                     "engine; pass vision_processor=callable(example) -> {input_ids, pixel_values_videos, video_grid_thw, "
                     "second_per_grid_ts} or pre-processed dataset rows")
             example = {**example, **self.vision_processor(example)}
+        grid = [tuple(int(v) for v in g) for g in np.asarray(example["video_grid_thw"]).reshape(-1, 3)]
+        if example.get("video_frames") is not None:
+            # resized frames [T, 3, H, W] (uint8 / fp32, 0..255) as fetch_video_v3 returns them (vision_process.py:440-475):
+            # the processor's rescale / normalise / patchify (timer1_trainer.py:547-556) runs on the device
+            fr = example["video_frames"]
+            fr = fr if isinstance(fr, torch.Tensor) else torch.as_tensor(np.asarray(fr))
+            if fr.dtype != torch.uint8:
+                fr = fr.to(torch.float32)
+            return Prompt(input_ids=np.asarray(example["input_ids"]).reshape(-1), pixel_values=None, grid_thw=grid,
+                          second_per_grid_ts=example.get("second_per_grid_ts"),
+                          frames=fr.to(device=self.device, non_blocking=True).contiguous())
         pix = example["pixel_values_videos"]
         pix = pix if isinstance(pix, torch.Tensor) else torch.as_tensor(np.asarray(pix))
         pix = pix.to(device=self.device, dtype=torch.float32, non_blocking=True).contiguous()
-        grid = [tuple(int(v) for v in g) for g in np.asarray(example["video_grid_thw"]).reshape(-1, 3)]
         return Prompt(input_ids=np.asarray(example["input_ids"]).reshape(-1), pixel_values=pix, grid_thw=grid,
                       second_per_grid_ts=example.get("second_per_grid_ts"))
 
@@ -287,7 +297,7 @@ class TimeR1_Trainer:
             completions = self._decode(comp_ids)
             if _is_conversational(example):
                 completions = [[{"role": "assistant", "content": c}] for c in completions]
-            cols = {k: [example[k]] * G for k in example if k not in ("prompt", "completion", "input_ids", "pixel_values_videos", "video_grid_thw", "second_per_grid_ts")}
+            cols = {k: [example[k]] * G for k in example if k not in ("prompt", "completion", "input_ids", "pixel_values_videos", "video_frames", "video_grid_thw", "second_per_grid_ts")}
             out = np.zeros((G, len(self.reward_funcs)), np.float32)
             for i, rf in enumerate(self.reward_funcs):
                 out[:, i] = np.asarray(rf(prompts=prompts, completions=completions, **cols), np.float32)
