@@ -10,7 +10,7 @@ A step = ONE complete GRPO update for one prompt-group per GPU: Vi
 rollout of G completions, policy + reference scoring, rewards (host parse + device IoU), group advantage, clipped
 loss, full backward and the sharded AdamW step.  Workload = cfg2: Qwen2.5-VL-7B dims (the class the reference
 instantiates, timer1_trainer.py:244), 16 temporal slots of 448x448 -> grid (16,32,32), 4096 vision tokens, prompt
-~4.2k tokens, G=8, C=200, synthetic N(0,1) pixels, random-init N(0,0.02) bf16 weights, synthetic template rewards.
+~4.2k tokens, G=8, C=200, synthetic uniform uint8 frames, random-init N(0,0.02) bf16 weights, synthetic template rewards.
 """
 from __future__ import annotations
 
@@ -162,8 +162,10 @@ def synthetic_prompt(cfg, slots: int, rank: int, step: int, device):
     text = rng.integers(0, 151643, 110)
     ids = np.concatenate([[151644, 872, 198, 151652], np.full(nv, cfg.video_token_id), [151653], text, [151645, 198, 151644, 77091, 198]]).astype(np.int64)
     g = torch.Generator().manual_seed(42 + 1000 * rank + step)
-    pix_host = torch.randn(N, cfg.patch_dim, generator=g, dtype=torch.float32).pin_memory()
-    return ids, pix_host, [(slots, 32, 32)]
+    # resized integer-valued frames as fetch_video_v3 hands them to the processor (vision_process.py:440-475):
+    # 2 * slots frames of 448 x 448; the processor stage (rescale / normalise / patchify) runs on the device
+    frames_host = torch.randint(0, 256, (2 * slots, 3, 448, 448), generator=g, dtype=torch.uint8).pin_memory()
+    return ids, frames_host, [(slots, 32, 32)]
 
 
 class TemplateRewards:
@@ -291,9 +293,11 @@ def run_ours(args):
     NG = args.groups_per_step
     rewards = [TemplateRewards(G, rank * NG + i) for i in range(NG)]
     inputs = [synthetic_prompt(cfg, args.slots, rank * NG + i, 0, dev) for i in range(NG)]
-    ids, pix_host, grid = inputs[0]
+    ids, frames_host, grid = inputs[0]
     P = len(ids)
-    pix_devs = [inp[1].to(dev) for inp in inputs]
+    # `value` runs with pixel_values_videos resident in HBM (the processor output, fp32 [N, 1176]); `e2e` starts from the
+    # uint8 frames in pinned host memory
+    pix_devs = [ops.video_patchify(inp[1].to(dev))[0] for inp in inputs]
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -302,9 +306,12 @@ def run_ours(args):
 
     def one_step(step_idx: int, e2e: bool, timers=None):
         prompts = []
-        for i, (ids_i, pix_host_i, grid_i) in enumerate(inputs):
-            pix = pix_host_i.to(dev, non_blocking=True) if e2e else pix_devs[i]   # e2e: H2D from pinned memory each step
-            prompts.append(engine.Prompt(input_ids=ids_i, pixel_values=pix, grid_thw=grid_i, second_per_grid_ts=[1.0]))
+        for i, (ids_i, frames_host_i, grid_i) in enumerate(inputs):
+            if e2e:      # H2D of the step's frames from pinned memory, device pre-processing inside the step
+                prompts.append(engine.Prompt(input_ids=ids_i, pixel_values=None, grid_thw=grid_i, second_per_grid_ts=[1.0],
+                                             frames=frames_host_i.to(dev, non_blocking=True)))
+            else:
+                prompts.append(engine.Prompt(input_ids=ids_i, pixel_values=pix_devs[i], grid_thw=grid_i, second_per_grid_ts=[1.0]))
         outs = eng.grpo_multi_step(prompts, rewards, seed=run.seed + step_idx * world + rank, loss_scale=1.0 / NG, timers=timers)
         gn = eng.optimizer_step()
         if e2e:
@@ -409,7 +416,7 @@ def run_ours(args):
         "config": {"workload": workload_name(args), "prompt_tokens": P, "vision_tokens": args.slots * 256, "group_size": G, "groups_per_step": NG,
                    "completion_len": C, "parallelism": f"dp{world}+zero2-sharded-adamw", "l2": "inputs larger than L2 (>=16 GB of weights streamed per pass)"},
         "clocks": clocks,
-        "e2e": {"value": round(e2e_value, 4), "unit": UNIT, "h2d_bytes_per_step": int(NG * (pix_host.numel() * 4 + ids.size * 4)), "d2h_bytes_per_step": int(NG * (G * C * 4 + 4) + 4)},
+        "e2e": {"value": round(e2e_value, 4), "unit": UNIT, "h2d_bytes_per_step": int(NG * (frames_host.numel() + ids.size * 4)), "input": "uint8 frames [2*slots, 3, 448, 448] from pinned host memory -> t1_video_patchify on the device", "d2h_bytes_per_step": int(NG * (G * C * 4 + 4) + 4)},
         "gpu_launches": launches,
         "roofline": roofline,
         "roofline_decode": dec,
