@@ -19,8 +19,10 @@
 // warps 2..17 = 512 element-wise threads, 4 per TMEM lane (32 columns each).  The bf16 P / dS operands never touch
 // shared memory: each thread overwrites the first half of the 32 fp32 columns it just read, so there is no
 // cross-thread hazard and the in-order tensor pipe guarantees the next S / dP MMA lands after the TS MMA that reads them.
+#define T1_MBAR_NO_HINT   // both kernels sit at the 96-register cap of 576-thread CTAs: the hinted wait spills
 #include "t1_common.cuh"
 #include <limits.h>
+#include <type_traits>
 
 namespace {
 
@@ -145,7 +147,7 @@ __device__ __forceinline__ bool q_tile_sees(const int* __restrict__ summ, int qt
   return s.x != INT_MAX && s.w > j0 && (s.x < j1 || j0 < shared_len);
 }
 
-__global__ void __launch_bounds__(BWD_THREADS, 1)
+__global__ void __launch_bounds__(BWD_THREADS, 1)   // 576 threads: 96 registers is the most that still launches
 fa_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                      const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
                      const float* __restrict__ LSE2, const float* __restrict__ delta, float* __restrict__ part_dk,
@@ -188,8 +190,8 @@ fa_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     }
     mbar_init(s_full, 1);
     mbar_init(dp_full, 1);
-    mbar_init(p_ready, 4 * NS);            // one arrival per element-wise warp
-    mbar_init(ds_ready, 4 * NS);
+    mbar_init(p_ready, 128 * NS);
+    mbar_init(ds_ready, 128 * NS);
     mbar_init(acc_done, 1);
     mbar_fence_init();
   }
@@ -321,7 +323,7 @@ fa_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         float p1 = ex2_approx(fmaf(__uint_as_float(pv[c4 * 4 + 1]), scale_log2, nl.y));
         float p2 = ex2_approx(fmaf(__uint_as_float(pv[c4 * 4 + 2]), scale_log2, nl.z));
         float p3 = ex2_approx(fmaf(__uint_as_float(pv[c4 * 4 + 3]), scale_log2, nl.w));
-        if (need_mask) {
+        if (need_mask) {      // warp-uniform, one branch per 4 elements
           const int4 lo = *reinterpret_cast<const int4*>(&ax.lo[part * 32 + c4 * 4]);
           const int4 hi = *reinterpret_cast<const int4*>(&ax.hi[part * 32 + c4 * 4]);
           const bool sh = key < shared_len;
@@ -341,8 +343,7 @@ fa_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         tmem_st_wait();
       }
       tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(p_ready);
+      mbar_arrive(p_ready);
       // ---- dS^T ----
       mbar_wait(dp_full, it & 1);
       tc_fence_after();
@@ -367,8 +368,7 @@ fa_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       tmem_st_32x32b_x16(t_lane + T_DP + part * 32, dk);
       tmem_st_wait();
       tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(ds_ready);
+      mbar_arrive(ds_ready);
       ++it;
     }
     // ---- epilogue: fp32 partials of this q head ----
@@ -414,7 +414,7 @@ struct Range {
   __device__ __forceinline__ int tile(int idx) const { return idx < tA_end ? idx : tB_start + (idx - tA_end); }
 };
 
-__global__ void __launch_bounds__(BWD_THREADS, 1)
+__global__ void __launch_bounds__(BWD_THREADS, 1)   // 576 threads: 96 registers is the most that still launches
 fa_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                     const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
                     const float* __restrict__ LSE2, const float* __restrict__ delta, bf16* __restrict__ dQ, long long lddq,
@@ -598,25 +598,28 @@ fa_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       tc_fence_after();
       const uint32_t tS = t_lane + T_S0 + (it & 1) * 128 + part * 32;
       uint32_t pk[16];
+      auto ds_phase = [&](auto masked) {      // need_mask is warp-uniform
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t sv[16];
-        tmem_ld_32x32b_x16(tS + half * 16, sv);
-        tmem_ld_wait();
+        for (int half = 0; half < 2; ++half) {
+          uint32_t sv[16];
+          tmem_ld_32x32b_x16(tS + half * 16, sv);
+          tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < 16; c += 2) {
-          float p0 = ex2_approx(fmaf(__uint_as_float(sv[c]), scale_log2, nl));
-          float p1 = ex2_approx(fmaf(__uint_as_float(sv[c + 1]), scale_log2, nl));
-          if (need_mask) {
-            const int k0 = j0 + part * 32 + half * 16 + c;
-            p0 = (valid && k0 < my_hi && (k0 >= my_lo || k0 < shared_len)) ? p0 : 0.f;
-            p1 = (valid && k0 + 1 < my_hi && (k0 + 1 >= my_lo || k0 + 1 < shared_len)) ? p1 : 0.f;
+          for (int c = 0; c < 16; c += 2) {
+            float p0 = ex2_approx(fmaf(__uint_as_float(sv[c]), scale_log2, nl));
+            float p1 = ex2_approx(fmaf(__uint_as_float(sv[c + 1]), scale_log2, nl));
+            if constexpr (decltype(masked)::value) {
+              const int k0 = j0 + part * 32 + half * 16 + c;
+              p0 = (valid && k0 < my_hi && (k0 >= my_lo || k0 < shared_len)) ? p0 : 0.f;
+              p1 = (valid && k0 + 1 < my_hi && (k0 + 1 >= my_lo || k0 + 1 < shared_len)) ? p1 : 0.f;
+            }
+            const float d0 = p0 * (__uint_as_float(dp[half * 16 + c]) - dl) * scale;
+            const float d1 = p1 * (__uint_as_float(dp[half * 16 + c + 1]) - dl) * scale;
+            pk[half * 8 + (c >> 1)] = pack_bf16x2(d0, d1);
           }
-          const float d0 = p0 * (__uint_as_float(dp[half * 16 + c]) - dl) * scale;
-          const float d1 = p1 * (__uint_as_float(dp[half * 16 + c + 1]) - dl) * scale;
-          pk[half * 8 + (c >> 1)] = pack_bf16x2(d0, d1);
         }
-      }
+      };
+      if (need_mask) ds_phase(std::true_type{}); else ds_phase(std::false_type{});
       tmem_st_32x32b_x16(tS, pk);
       tmem_st_wait();
       tc_fence_before();

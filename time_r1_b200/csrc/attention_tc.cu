@@ -5,13 +5,15 @@
 // the tensor-bound LLM shapes.  One CTA = 128 query rows x one q head, looping over 128-key tiles:
 //   warp 0       TMA producer : Q tile once, K/V tiles (2 x [128 x 64] SWIZZLE_128B boxes each) into a 2-stage ring
 //   warp 1       MMA issuer   : S = Q K^T   (tcgen05.mma M128 N128 K16 x 8, both operands K-major) -> TMEM S[it & 1]
-//                               O += P V    (A = P from smem, K-major; B = V tile consumed in place as an MN-major
-//                               operand — no transpose) -> TMEM O
+//                               O += P V    (A = P read from TMEM — the bf16 probabilities are packed back into the S
+//                               columns they came from; B = V tile consumed in place as an MN-major operand) -> TMEM O
 //   warps 2..17  softmax      : 4 threads per query row (32 key columns each, so every SM sub-partition has four
 //                               resident softmax warps); tcgen05.ld S -> mask, scale, lazy-rescaled online softmax (the
 //                               running max is only refreshed when it grows by > 8 in log2 units, so the O accumulator
-//                               in TMEM is rarely rescaled) -> P (bf16) written to smem in the UMMA K-major swizzle
-// S(it+1) is issued before softmax(it) finishes, so QK^T overlaps the exponentials.
+//                               in TMEM is rarely rescaled) -> P (bf16) packed into the first half of each thread's
+//                               own 32 S columns (no shared-memory round trip, no cross-thread hazard)
+// S(it+1) is issued before softmax(it) finishes and the exponentials of tile it do not wait for PV(it-1): only a
+// (rare) rescale of O does, so QK^T, the exponentials and PV of neighbouring tiles overlap.
 #include "t1_common.cuh"
 #include <limits.h>
 #include <stdlib.h>
@@ -25,12 +27,32 @@ constexpr int ATOM_BYTES = 128 * 128;            // [128 rows x 64 bf16] box
 constexpr int TILE_BYTES = 2 * ATOM_BYTES;       // [128 x 128] bf16
 constexpr int NS = 4;                  // softmax threads per query row
 constexpr int FA_TC_THREADS = 64 + 128 * NS;   // TMA warp, MMA warp, 4*NS softmax warps
-constexpr int FA_TC_SMEM = TILE_BYTES /*Q*/ + 2 * TILE_BYTES /*K*/ + 2 * TILE_BYTES /*V*/ + TILE_BYTES /*P*/ + 1024 + 256 + 3 * NS * 128 * 4 /*row exchange*/;
+constexpr int FA_TC_SMEM = TILE_BYTES /*Q*/ + 2 * TILE_BYTES /*K*/ + 2 * TILE_BYTES /*V*/ + 1024 + 256 + 3 * NS * 128 * 4 /*row exchange*/;
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
 }
 
 struct Range {
@@ -39,7 +61,7 @@ struct Range {
   __device__ __forceinline__ int tile(int idx) const { return idx < tA_end ? idx : tB_start + (idx - tA_end); }
 };
 
-__global__ void __launch_bounds__(FA_TC_THREADS, 1)
+__global__ void __launch_bounds__(FA_TC_THREADS, 1)   // 576 threads: 96 registers is the most that still launches
 fa_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                  const __grid_constant__ CUtensorMap tm_v, bf16* __restrict__ O, long long ldo, float* __restrict__ LSE2,
                  const int* __restrict__ row_lo, const int* __restrict__ row_hi, int shared_len, int T, int q_row0,
@@ -49,8 +71,7 @@ fa_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + TILE_BYTES;            // 2 stages
   uint8_t* sV = sK + 2 * TILE_BYTES;        // 2 stages
-  uint8_t* sP = sV + 2 * TILE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + TILE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * TILE_BYTES);
   uint64_t* q_full = bars;                  // 1
   uint64_t* k_full = bars + 1;              // 2
   uint64_t* k_empty = bars + 3;             // 2  (released as soon as S = Q K^T of the tile retires)
@@ -58,10 +79,10 @@ fa_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   uint64_t* v_empty = bars + 7;             // 2  (released when O += P V retires)
   uint64_t* s_full = bars + 9;              // 2
   uint64_t* p_full = bars + 11;             // 1 (one arrival per softmax warp)
-  uint64_t* pv_done = bars + 12;            // 1
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 13);
-  int* s_red = reinterpret_cast<int*>(bars + 14);  // 4 ints
-  float* s_xch = reinterpret_cast<float*>(bars + 16);   // [3*NS][128] floats: per-row partial max (double buffered) and sum
+  uint64_t* pv_done = bars + 12;            // 2 (PV(it) arrives on pv_done[it & 1])
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 14);
+  int* s_red = reinterpret_cast<int*>(bars + 15);  // 4 ints
+  float* s_xch = reinterpret_cast<float*>(bars + 17);   // [3*NS][128] floats: per-row partial max (double buffered) and sum
 
   const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // Q / O / the tensor map of Q are LOCAL to the processed query rows [q_row0, T); row_lo / row_hi / LSE2 and the key
@@ -89,7 +110,8 @@ fa_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       mbar_init(&s_full[i], 1);
     }
     mbar_init(p_full, 4 * NS);             // one arrival per softmax warp
-    mbar_init(pv_done, 1);
+    mbar_init(&pv_done[0], 1);
+    mbar_init(&pv_done[1], 1);
     mbar_fence_init();
   }
   if (warp_idx == 1) tmem_alloc<512>(tmem_ptr_smem);
@@ -168,14 +190,15 @@ fa_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         mbar_wait(&v_full[st], (it >> 1) & 1);
         mbar_wait(p_full, it & 1);
         tc_fence_after();
+        const uint32_t tmem_p = tmem_base + (it & 1) * 128;
 #pragma unroll
         for (int kk = 0; kk < TK / 16; ++kk) {
-          const uint64_t a_desc = umma_desc_sw128_kmajor(smem_u32(sP + (kk >> 2) * ATOM_BYTES + (kk & 3) * 32));
+          // thread `part` packed its 32 probabilities into the first 16 of its own S columns: K-step kk -> part kk / 2
           const uint64_t b_desc = umma_desc_sw128_mnmajor(smem_u32(sV + st * TILE_BYTES + kk * 16 * 128), v_lbo, v_sbo);
-          umma_bf16_ss(tmem_o, a_desc, b_desc, idesc_pv, (it | kk) != 0 ? 1u : 0u);
+          umma_bf16_ts(tmem_o, tmem_p + (uint32_t)((kk >> 1) * 32 + (kk & 1) * 8), b_desc, idesc_pv, (it | kk) != 0 ? 1u : 0u);
         }
         umma_commit(&v_empty[st]);
-        umma_commit(pv_done);
+        umma_commit(&pv_done[it & 1]);
       }
     }
   } else {
@@ -199,19 +222,24 @@ fa_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       tmem_ld_wait();
       const bool need_mask = !(j1 <= min_hi && (j0 >= max_lo || j1 <= shared_len));
       float tmax = -INFINITY;   // raw (unscaled) scores; scale_log2 > 0 so max commutes with the scaling
+      if (need_mask) {          // warp-uniform: the common unmasked tile runs a branch-free max (ncu: the per-element
+                                // branch of the fused form was 42% of all executed instructions)
 #pragma unroll
-      for (int c = 0; c < NCH; ++c)
+        for (int c = 0; c < NCH; ++c)
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float v = __uint_as_float(sv[c][j]);
-          if (need_mask) {
+          for (int j = 0; j < 32; ++j) {
             const int key = j0 + part * CW + c * 32 + j;
             const bool vis = valid && key < my_hi && (key >= my_lo || key < shared_len);
-            v = vis ? v : -INFINITY;
+            const float v = vis ? __uint_as_float(sv[c][j]) : -INFINITY;
             sv[c][j] = __float_as_uint(v);
+            tmax = fmaxf(tmax, v);
           }
-          tmax = fmaxf(tmax, v);
-        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) tmax = fmaxf(tmax, __uint_as_float(sv[c][j]));
+      }
       // the NS threads of a row exchange their partial maxima (named barrier per TMEM quadrant, 32*NS threads)
       s_xch[((it & 1) * NS + part) * TQ + r] = tmax;
       asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "n"(32 * NS) : "memory");
@@ -226,47 +254,37 @@ fa_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         m_ref = tmax;
         l *= alpha;
       }
-      if (it > 0) {
-        mbar_wait(pv_done, (it - 1) & 1);               // P smem free again, O accumulator up to date
+      if (it > 0 && __any_sync(0xffffffffu, grow)) {
+        // rare after the first tiles: O is rescaled in place once PV(it-1) has retired
+        mbar_wait(&pv_done[(it - 1) & 1], ((it - 1) >> 1) & 1);
         tc_fence_after();
-        if (__any_sync(0xffffffffu, grow)) {
 #pragma unroll 1
-          for (int c = 0; c < NCH; ++c) {
-            uint32_t ov[32];
-            tmem_ld_32x32b_x32(tmem_o + c * 32, ov);
-            tmem_ld_wait();
+        for (int c = 0; c < NCH; ++c) {
+          uint32_t ov[32];
+          tmem_ld_32x32b_x32(tmem_o + c * 32, ov);
+          tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) ov[j] = __float_as_uint(__uint_as_float(ov[j]) * alpha);
-            tmem_st_32x32b_x32(tmem_o + c * 32, ov);
-          }
-          tmem_st_wait();
+          for (int j = 0; j < 32; ++j) ov[j] = __float_as_uint(__uint_as_float(ov[j]) * alpha);
+          tmem_st_32x32b_x32(tmem_o + c * 32, ov);
         }
+        tmem_st_wait();
       }
       const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
       float rs = 0.f;
+      static_assert(NCH == 1, "one 32-column chunk per softmax thread");
+      uint32_t pk[16];
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-#pragma unroll
-        for (int j8 = 0; j8 < 4; ++j8) {
-          float p[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            p[j] = ex2_approx(fmaf(__uint_as_float(sv[c][j8 * 8 + j]), scale_log2, neg_m));
-            rs += p[j];
-          }
-          uint4 pk;
-          pk.x = pack_bf16x2(p[0], p[1]);
-          pk.y = pack_bf16x2(p[2], p[3]);
-          pk.z = pack_bf16x2(p[4], p[5]);
-          pk.w = pack_bf16x2(p[6], p[7]);
-          // K-major SW128: key column kc -> atom kc/64, 16-byte chunk (kc%64)/8 XOR (row%8)
-          const int kc = part * CW + c * 32 + j8 * 8;
-          const int chunk = ((kc & 63) >> 3) ^ (r & 7);
-          *reinterpret_cast<uint4*>(sP + (kc >> 6) * ATOM_BYTES + r * 128 + chunk * 16) = pk;
-        }
+      for (int j = 0; j < 16; ++j) {
+        const float p0 = ex2_approx(fmaf(__uint_as_float(sv[0][2 * j]), scale_log2, neg_m));
+        const float p1 = ex2_approx(fmaf(__uint_as_float(sv[0][2 * j + 1]), scale_log2, neg_m));
+        rs += p0 + p1;
+        pk[j] = pack_bf16x2(p0, p1);
       }
       l += rs;
-      fence_proxy_async_smem();
+      // P(it) goes into the S columns P(it-2) was read from: PV(it-2) must have retired (it has, two tiles ago)
+      if (it >= 2) mbar_wait(&pv_done[it & 1], ((it >> 1) - 1) & 1);
+      tmem_st_32x32b_x16(t_lane + (it & 1) * 128 + part * CW, pk);
+      tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);     // 16 arrivals per tile instead of 512 same-address shared-memory atomics
@@ -278,7 +296,7 @@ fa_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 #pragma unroll
     for (int o = 0; o < NS; ++o) l += s_xch[(2 * NS + o) * TQ + r];
     if (ntiles > 0) {
-      mbar_wait(pv_done, (ntiles - 1) & 1);
+      mbar_wait(&pv_done[(ntiles - 1) & 1], ((ntiles - 1) >> 1) & 1);
       tc_fence_after();
     }
     const float inv = l > 0.f ? 1.f / l : 0.f;

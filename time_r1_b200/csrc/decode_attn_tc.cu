@@ -325,14 +325,17 @@ decode_attn_tc_kernel(const bf16* __restrict__ q, long long ldq, int Hq, int Hkv
       const bool need_mask = d.seq >= 0 || d.nvalid < UNIT;
       const bool row_sees = valid && (d.seq < 0 || d.seq == my_seq);
       float tmax = -INFINITY;
+      if (need_mask) {                           // warp-uniform; keeps the unmasked prefix units branch-free
+        const int lim = row_sees ? d.nvalid - part * 32 : 0;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float v = __uint_as_float(sv[j]);
-        if (need_mask) {
-          v = (row_sees && part * 32 + j < d.nvalid) ? v : -INFINITY;
+        for (int j = 0; j < 32; ++j) {
+          const float v = j < lim ? __uint_as_float(sv[j]) : -INFINITY;
           sv[j] = __float_as_uint(v);
+          tmax = fmaxf(tmax, v);
         }
-        tmax = fmaxf(tmax, v);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) tmax = fmaxf(tmax, __uint_as_float(sv[j]));
       }
       s_xch[((it & 1) * NS + part) * 128 + L] = tmax;
       asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "n"(32 * NS) : "memory");

@@ -152,6 +152,8 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
+#ifdef T1_MBAR_NO_HINT
+  // plain form: the suspend-time hint below costs a register in kernels that sit exactly at their register cap
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
@@ -161,6 +163,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "=r"(ok)
       : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
+#else
+  // suspend-time hint: the thread sleeps in hardware instead of burning issue slots in the polling loop (ncu: 22% of
+  // all executed instructions of the attention forward were polling without it)
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "n"(0x989680)
+      : "memory");
+#endif
   return ok != 0;
 }
 // Bounded wait: a protocol bug becomes a trap (sticky launch error) instead of a hung GPU.
