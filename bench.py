@@ -42,6 +42,8 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default="qwen2.5-vl-7b")
     ap.add_argument("--slots", type=int, default=16, help="temporal slots of 32x32 patches (16 -> cfg2, 32 -> cfg3, 64 -> cfg5)")
+    ap.add_argument("--grid", default=None, help="t,h,w patch grid of the video instead of (slots,32,32), e.g. 147,6,12 = a 147 s "
+                    "TimeRFT clip at 84x168 (cfg4, SURVEY 8d); frames are 2t x 3 x 14h x 14w")
     ap.add_argument("--group-size", type=int, default=8)
     ap.add_argument("--completion-len", type=int, default=200)
     ap.add_argument("--groups-per-step", type=int, default=2,
@@ -56,8 +58,13 @@ def parse_args():
     return ap.parse_args()
 
 
+def grid_of(args):
+    return tuple(int(v) for v in args.grid.split(",")) if args.grid else (args.slots, 32, 32)
+
+
 def workload_name(args):
-    return (f"cfg2-family: {args.model} dims, grid ({args.slots},32,32) = {args.slots * 256} vision tokens, "
+    t, h, w = grid_of(args)
+    return (f"cfg2-family: {args.model} dims, grid ({t},{h},{w}) = {t * h * w // 4} vision tokens, "
             f"G={args.group_size}, C={args.completion_len}, {args.groups_per_step} prompt-group(s) per GPU per optimizer step "
             f"(gradient_accumulation_steps of train_rl.sh:27)")
 
@@ -123,8 +130,8 @@ def cpu_reference(args, steps: int, warmup: int) -> dict:
     import dataclasses
     s_model = dataclasses.replace(full, num_hidden_layers=1, vit_depth=1, fullatt_block_indexes=(0,), vocab_size=32768)
     f_sample = flops.reference_style_flops(s_model, grid_s, st.P, G_s, C_s)
-    grid = [(args.slots, 32, 32)]
-    P_full = 4 + args.slots * 256 + 1 + 110 + 5
+    grid = [grid_of(args)]
+    P_full = 4 + grid[0][0] * grid[0][1] * grid[0][2] // 4 + 1 + 110 + 5
     f_full = flops.reference_style_flops(full, grid, P_full, args.group_size, args.completion_len)
     t_full = t_sample * f_full / f_sample
     value = args.group_size / t_full
@@ -151,21 +158,22 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
-def synthetic_prompt(cfg, slots: int, rank: int, step: int, device):
+def synthetic_prompt(cfg, grid, rank: int, step: int, device):
     """SURVEY §8d synthetic inputs (seed 42 mirrors main.py:552)."""
     import numpy as np
     import torch
 
     rng = np.random.default_rng(42 + 1000 * rank + step)
-    N = slots * 32 * 32
+    t, h, w = grid
+    N = t * h * w
     nv = N // cfg.merge_unit
     text = rng.integers(0, 151643, 110)
     ids = np.concatenate([[151644, 872, 198, 151652], np.full(nv, cfg.video_token_id), [151653], text, [151645, 198, 151644, 77091, 198]]).astype(np.int64)
     g = torch.Generator().manual_seed(42 + 1000 * rank + step)
     # resized integer-valued frames as fetch_video_v3 hands them to the processor (vision_process.py:440-475):
     # 2 * slots frames of 448 x 448; the processor stage (rescale / normalise / patchify) runs on the device
-    frames_host = torch.randint(0, 256, (2 * slots, 3, 448, 448), generator=g, dtype=torch.uint8).pin_memory()
-    return ids, frames_host, [(slots, 32, 32)]
+    frames_host = torch.randint(0, 256, (2 * t, 3, 14 * h, 14 * w), generator=g, dtype=torch.uint8).pin_memory()
+    return ids, frames_host, [(t, h, w)]
 
 
 class TemplateRewards:
@@ -292,7 +300,7 @@ def run_ours(args):
     eng = engine.Engine(cfg, mw, run, rank=rank, world_size=world, process_group=pg)
     NG = args.groups_per_step
     rewards = [TemplateRewards(G, rank * NG + i) for i in range(NG)]
-    inputs = [synthetic_prompt(cfg, args.slots, rank * NG + i, 0, dev) for i in range(NG)]
+    inputs = [synthetic_prompt(cfg, grid_of(args), rank * NG + i, 0, dev) for i in range(NG)]
     ids, frames_host, grid = inputs[0]
     P = len(ids)
     # `value` runs with pixel_values_videos resident in HBM (the processor output, fp32 [N, 1176]); `e2e` starts from the
@@ -413,7 +421,7 @@ def run_ours(args):
         "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms_per_step, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": {"workload": workload_name(args), "prompt_tokens": P, "vision_tokens": args.slots * 256, "group_size": G, "groups_per_step": NG,
+        "config": {"workload": workload_name(args), "prompt_tokens": P, "vision_tokens": (P - 120), "group_size": G, "groups_per_step": NG,
                    "completion_len": C, "parallelism": f"dp{world}+zero2-sharded-adamw", "l2": "inputs larger than L2 (>=16 GB of weights streamed per pass)"},
         "clocks": clocks,
         "e2e": {"value": round(e2e_value, 4), "unit": UNIT, "h2d_bytes_per_step": int(NG * (frames_host.numel() + ids.size * 4)), "input": "uint8 frames [2*slots, 3, 448, 448] from pinned host memory -> t1_video_patchify on the device", "d2h_bytes_per_step": int(NG * (G * C * 4 + 4) + 4)},

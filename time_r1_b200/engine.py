@@ -789,7 +789,6 @@ class Engine:
         keep: dict = {}
         N, vd, unit = plan.n_patches, cfg.vit_hidden, cfg.merge_unit
         Nv = N // unit
-        assert Nv % 8 == 0, "vision-token count must be a multiple of 8 for the transposed wgrad operands"
         # recompute the merger forward from the saved ViT output
         self.merger(x_vit, None, plan, "policy", keep=keep)
         dm = ops.gather_rows(dve, self._i32(plan.window_index))            # back to window order
