@@ -64,6 +64,18 @@ int t1_skinny_gemm(const void* x, long long ldx, const void* W, long long ldw, c
 long long t1_stream_gemm_workspace_bytes(int max_m);
 int t1_stream_gemm(const void* x, long long ldx, const void* W, long long ldw, const void* bias, void* y, long long ldy,
                    int M, int N, int K, int out_f32, void* workspace, long long workspace_bytes, cudaStream_t stream);
+/* Scheduling of the weight stream.  0: static stream-K split (equal bytes per CTA; leaves a 15-20% finishing-time spread
+ * because per-SM streaming rates differ).  1 (default): GEMMs with >= 4 slabs per SM (lm_head) hand whole slabs out
+ * through an atomic counter, so faster SMs take more; the others stay static.  2: also split slabs into k-segments
+ * (measured slower: per-item partial tiles). */
+void t1_stream_gemm_dynamic(int on);
+/* y = x W^T (bf16); resid[M, N] += y in place; h_out = rmsnorm(resid, eps) * norm_w: the o / down projection of a decode
+ * layer fused with the residual add and the NEXT RMSNorm (HF Q25:805-827): after a grid-wide arrive counter CTA b
+ * normalises row b (every CTA of the launch is resident: grid <= SM count).
+ * Replaces t1_stream_gemm + t1_rmsnorm(delta = y).  resid / h_out contiguous [M, N], N % 8 == 0. */
+int t1_stream_gemm_resnorm(const void* x, long long ldx, const void* W, long long ldw, void* y, long long ldy, int M, int N,
+                           int K, void* resid, const void* norm_w, float eps, void* h_out, void* workspace,
+                           long long workspace_bytes, cudaStream_t stream);
 /* y[M, I] = silu(x Wg^T) * (x Wu^T), W = [Wg; Wu] ([2I, K]): the decode step's gate_up projection fused with the SwiGLU
  * (HF Q25:611-624) in one weight stream; same arithmetic per element as t1_stream_gemm (bf16) + t1_swiglu (bit-identical when
  * the stream-K cut points coincide, as for the 7B decode shapes).  I % 64 == 0. */

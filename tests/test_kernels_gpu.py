@@ -360,6 +360,55 @@ def test_stream_gemm_swiglu(M, I, K):
     assert int(ws[:65536].view(torch.int32).abs().sum().item()) == 0, "slab counters must be left at zero"
 
 
+@pytest.mark.parametrize("M,N,K", [(16, 3584, 3584), (16, 3584, 18944), (8, 512, 264), (33, 1024, 512), (64, 256, 1024), (1, 200, 72)])
+def test_stream_gemm_resnorm(M, N, K):
+    """Projection + residual add + RMSNorm in one launch (tail run by the last CTA) vs stream_gemm followed by
+    rmsnorm(delta=...): the projection and the updated residual stream are bit-identical, the normalised output
+    agrees to one bf16 ulp (different fp32 summation order of the row variance); launched twice to check the
+    self-resetting completion counter."""
+    from time_r1_b200 import ops
+
+    x, w = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=0.05)
+    resid0, nw = rnd(M, N, seed=3), rnd(N, seed=4).abs() + 0.5
+    ws = ops.stream_gemm_workspace(M, DEV)
+    y_ref = ops.stream_gemm(x, w, ws)
+    r_ref = resid0.clone()
+    h_ref = ops.rmsnorm(r_ref, nw, 1e-6, delta=y_ref)          # updates r_ref in place
+    for _ in range(2):
+        r = resid0.clone()
+        h = torch.full_like(r, float("nan"))
+        y = ops.stream_gemm_resnorm(x, w, ws, r, nw, 1e-6, h)
+        assert torch.equal(y, y_ref)
+        assert torch.equal(r, r_ref)
+        close(h, h_ref, 1e-6, 1.0 / 128, "fused rmsnorm")
+    assert int(ws[:65536].view(torch.int32).abs().sum().item()) == 0, "counters must be left at zero"
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("M,N,K", [(16, 3584, 18944), (16, 4608, 3584), (8, 152064 // 4, 512), (33, 640, 1024), (64, 37888 // 2, 512)])
+def test_stream_gemm_scheduling_modes(M, N, K, mode):
+    """Static stream-K split (0), dynamic whole-slab items for many-slab GEMMs (1, default) and dynamic (slab, k-segment)
+    items (2): same result within fp32 summation order, each mode deterministic and self-resetting."""
+    from time_r1_b200 import lib, ops
+
+    x, w, b = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=0.05), rnd(N, seed=3)
+    ref = x.float() @ w.float().t() + b.float()
+    ws = ops.stream_gemm_workspace(M, DEV)
+    lib.load().t1_stream_gemm_dynamic(mode)
+    try:
+        out = ops.stream_gemm(x, w, ws, bias=b, out_dtype=torch.float32)
+        out2 = ops.stream_gemm(x, w, ws, bias=b, out_dtype=torch.float32)
+        sw = ops.stream_gemm_swiglu(x, w[: (N // 128) * 128], ws) if N % 128 == 0 else None
+    finally:
+        lib.load().t1_stream_gemm_dynamic(1)
+    close(out, ref, 2e-3 * math.sqrt(K) * 0.05, 1e-4, f"stream mode {mode}")
+    assert torch.equal(out, out2)
+    if sw is not None:
+        r = x.float() @ w.float().t()
+        close(sw, torch.nn.functional.silu(r[:, : N // 2]) * r[:, N // 2:], 2e-2, 2e-2, f"stream swiglu mode {mode}")
+    assert int(ws[:65536].view(torch.int32).abs().sum().item()) == 0, "all counters must be left at zero"
+
+
 def test_stream_gemm_chain_under_graph_with_pdl():
     """A captured chain rmsnorm -> stream_gemm -> swiglu -> stream_gemm with programmatic dependent launch gives the
     same result as the same chain launched eagerly without it (the weight prefetch must not outrun the dependency)."""

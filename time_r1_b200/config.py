@@ -166,3 +166,7 @@ class RunConfig:
     # decode attention inside the "stream" step: "cluster" = one launch, split-KV partials merged through distributed
     # shared memory; "split" = split-KV kernel + combine kernel through a global workspace
     decode_attn: str = "cluster"
+    # fuse the residual add + RMSNorm that follows the o / down projection into that stream GEMM (5 kernels per layer
+    # instead of 7).  Measured neutral on B200 (3.53 vs 3.49 ms per step): what looked like kernel-boundary latency is
+    # the finishing-time spread of the 148 streaming CTAs, which the fused tail has to wait out as well.
+    decode_fuse_norm: bool = False

@@ -59,8 +59,23 @@ struct SgParams {
   int out_f32;
   int swiglu;         // 1: W = [gate rows | up rows] (N = 2 * half_n); a slab pairs 64 gate rows with their 64 up rows and
   int half_n;         //    the epilogue emits y[M, half_n] = silu(gate) * up (bf16), as t1_swiglu does on the bf16 GEMM output
+  // fused residual + RMSNorm tail (t1_stream_gemm_resnorm): the LAST CTA to finish adds y to the residual stream and
+  // normalises it, which removes one kernel (and one kernel boundary) per norm from the decode chain
+  bf16* tail_x;       // residual stream [M, N], updated in place: x += y   (nullptr: no tail)
+  const bf16* tail_w; // norm weight [N]
+  bf16* tail_h;       // rmsnorm(x) * w  [M, N]
+  float tail_eps;
+  int* tail_counter;  // [2]: arrivals of all CTAs, completions of the row CTAs; zero on entry, re-armed by the last row CTA
+  // dynamic scheduler (stream_gemm_dyn_kernel): work items = (slab, k-segment), handed out through an atomic counter
+  int segs;           // k-segments per slab
+  int seg_k;          // k-blocks per segment
+  int total_items;    // slabs * segs
+  int* sched_counter; // zero on entry, reset by the CTA that performs the last fetch
   unsigned long long* dbg;   // optional [4] globaltimer stamps of CTA 0: start, weights issued, dependency resolved, done
 };
+#ifdef T1_SG_DBG
+__device__ unsigned long long g_cta_t[3][512];     // per-CTA start / first-data / end stamps of the last launch
+#endif
 __device__ __forceinline__ unsigned long long gtimer() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -110,6 +125,9 @@ stream_gemm_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   pdl_trigger();   // the next kernel of the chain may become resident (it blocks in its own griddepcontrol.wait)
+#ifdef T1_SG_DBG
+  if (threadIdx.x == 0) g_cta_t[0][blockIdx.x] = gtimer();
+#endif
 
   if (warp_idx == 0) {
     // ===================== TMA producer =====================
@@ -293,9 +311,393 @@ stream_gemm_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_const
       }
       u += kb1 - kb0;
     }
+    if (p.tail_x) {
+      // ---- residual + RMSNorm: a grid-wide arrive counter, then CTA b (b < M) normalises row b ----
+      // Every CTA of the launch is resident at the same time (grid <= SM count, one CTA per SM), so the M row-CTAs may
+      // spin on the counter; a single-CTA tail would be latency-bound (16 rows x 3 arrays through one SM).
+      __threadfence();                             // this CTA's y rows are visible device-wide
+      epi_bar_sync();
+      if (et == 0) atomicAdd(p.tail_counter, 1);
+      const int row_ctas = min(p.M, (int)gridDim.x);
+      if ((int)blockIdx.x < row_ctas) {
+        if (et == 0) {
+          while (atomicAdd(p.tail_counter, 0) < (int)gridDim.x) {}
+          __threadfence();
+        }
+        epi_bar_sync();
+        float* s_red = reinterpret_cast<float*>(s_flag + 1);
+        const int nv = p.N >> 3;
+        const bf16* yb = reinterpret_cast<const bf16*>(p.y);
+        constexpr int TB = 4;                                    // 16-byte chunks per thread kept in registers per batch
+        for (int m = blockIdx.x; m < p.M; m += gridDim.x) {
+          bf16* xr = p.tail_x + (long long)m * p.N;
+          bf16* hr = p.tail_h + (long long)m * p.N;
+          float sq = 0.f;
+          for (int c0 = et; c0 < nv; c0 += 128 * TB) {
+            uint4 uy[TB], ux[TB];
+#pragma unroll
+            for (int t = 0; t < TB; ++t) {
+              const int c = c0 + t * 128;
+              if (c < nv) {
+                uy[t] = __ldcg(reinterpret_cast<const uint4*>(yb + (long long)m * p.ldy + c * 8));
+                ux[t] = *reinterpret_cast<const uint4*>(xr + c * 8);
+              }
+            }
+#pragma unroll
+            for (int t = 0; t < TB; ++t) {
+              const int c = c0 + t * 128;
+              if (c < nv) {
+                const uint32_t* py = reinterpret_cast<const uint32_t*>(&uy[t]);
+                const uint32_t* px = reinterpret_cast<const uint32_t*>(&ux[t]);
+                uint32_t o[4];
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                  const float2 a = unpack_bf16x2(px[jj]), b = unpack_bf16x2(py[jj]);
+                  o[jj] = pack_bf16x2(a.x + b.x, a.y + b.y);      // hidden = residual + hidden in bf16 (HF Q25:805-827)
+                  const float2 r2 = unpack_bf16x2(o[jj]);         // the norm sees what later consumers of x read
+                  sq += r2.x * r2.x + r2.y * r2.y;
+                }
+                *reinterpret_cast<uint4*>(xr + c * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+              }
+            }
+          }
+          sq = warp_sum(sq);
+          if (lane == 0) s_red[warp_idx - 2] = sq;
+          epi_bar_sync();
+          const float rstd = rsqrtf((s_red[0] + s_red[1] + s_red[2] + s_red[3]) / (float)p.N + p.tail_eps);
+          epi_bar_sync();                                        // s_red is rewritten by the next row
+          for (int c0 = et; c0 < nv; c0 += 128 * TB) {
+            uint4 ux[TB], uw[TB];
+#pragma unroll
+            for (int t = 0; t < TB; ++t) {
+              const int c = c0 + t * 128;
+              if (c < nv) {
+                ux[t] = *reinterpret_cast<const uint4*>(xr + c * 8);          // this thread's own stores
+                uw[t] = *reinterpret_cast<const uint4*>(p.tail_w + c * 8);
+              }
+            }
+#pragma unroll
+            for (int t = 0; t < TB; ++t) {
+              const int c = c0 + t * 128;
+              if (c < nv) {
+                const uint32_t* px = reinterpret_cast<const uint32_t*>(&ux[t]);
+                const uint32_t* pw = reinterpret_cast<const uint32_t*>(&uw[t]);
+                uint32_t o[4];
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                  const float2 a = unpack_bf16x2(px[jj]), w2 = unpack_bf16x2(pw[jj]);
+                  o[jj] = pack_bf16x2(a.x * rstd * w2.x, a.y * rstd * w2.y);
+                }
+                *reinterpret_cast<uint4*>(hr + c * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+              }
+            }
+          }
+        }
+        epi_bar_sync();
+        if (et == 0) {                              // the last row-CTA re-arms both counters for the next launch
+          const int old = atomicAdd(p.tail_counter + 1, 1);
+          if (old == row_ctas - 1) {
+            p.tail_counter[1] = 0;
+            p.tail_counter[0] = 0;
+          }
+        }
+      }
+    }
     if (p.dbg && blockIdx.x == 0 && et == 0) p.dbg[3] = gtimer();
   }
 
+#ifdef T1_SG_DBG
+  if (threadIdx.x == 64 + 0) g_cta_t[2][blockIdx.x] = gtimer();
+#endif
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 1) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Dynamically scheduled variant.  The 148 CTAs of a static equal split do NOT finish together: per-SM streaming rates
+// differ by ~15% (measured finishing-time spread: 7 us of 49 for gate_up, 41 us of 183 for lm_head), and every later
+// kernel waits for the slowest one.  Here the work is cut into items = (slab, k-segment) several times smaller than a
+// CTA's share; CTA b starts with item b (so its weights can still be prefetched before griddepcontrol.wait) and then
+// pulls items from an atomic counter.  The producer warp fetches one item ahead and publishes the ids to the MMA and
+// epilogue warps through a 4-slot shared-memory queue.  Partials of a slab are reduced by whoever finishes its last
+// segment, always in segment order (deterministic).
+// ---------------------------------------------------------------------------------------------
+constexpr int SG_QN = 4;
+
+template <int MP>
+__global__ void __launch_bounds__(SG_THREADS, 1)
+stream_gemm_dyn_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CUtensorMap tma_x, SgParams p) {
+  constexpr int X_BYTES = MP * SG_BK * 2;
+  constexpr int STAGE_BYTES = SG_W_BYTES + X_BYTES;
+  constexpr uint32_t TMEM_COLS = (2 * MP < 32) ? 32 : 2 * MP;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty_bar = full_bar + SG_MAX_STAGES;
+  uint64_t* tmem_full_bar = empty_bar + SG_MAX_STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint64_t* q_full = tmem_empty_bar + 2;        // SG_QN
+  uint64_t* q_empty = q_full + SG_QN;           // SG_QN (1 MMA arrival + 128 epilogue arrivals)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(q_empty + SG_QN);
+  int* s_flag = reinterpret_cast<int*>(tmem_ptr_smem + 1);
+  int* q_item = s_flag + 8;                     // SG_QN ints (s_flag + 1 .. + 4 hold the norm-tail reduction scratch)
+  uint8_t* tiles = smem + SG_HEADER;
+  float* xs = reinterpret_cast<float*>(tiles + p.stages * STAGE_BYTES);   // swiglu: [MP][64] up values
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int stages = p.stages;
+  const int KB = p.kblocks;
+  const int first = (int)blockIdx.x < p.total_items ? (int)blockIdx.x : -1;
+  auto item_range = [&](int id, int& slab, int& kb0, int& kb1) {
+    slab = id / p.segs;
+    const int sg = id - slab * p.segs;
+    kb0 = sg * p.seg_k;
+    kb1 = min(KB, kb0 + p.seg_k);
+  };
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_w);
+    tma_prefetch_desc(&tma_x);
+    for (int i = 0; i < stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 128);
+    }
+    for (int i = 0; i < SG_QN; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 129);
+    }
+    mbar_fence_init();
+  }
+  if (warp_idx == 1) tmem_alloc<TMEM_COLS>(tmem_ptr_smem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_trigger();
+#ifdef T1_SG_DBG
+  if (threadIdx.x == 0) g_cta_t[0][blockIdx.x] = gtimer();
+#endif
+
+  if (warp_idx == 0) {
+    // ===================== TMA producer + scheduler =====================
+    if (lane == 0 && first >= 0) {
+      const bool dbg = p.dbg && blockIdx.x == 0;
+      if (dbg) p.dbg[0] = gtimer();
+      uint64_t pol_stream, pol_keep;
+      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+      asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+      auto load_w = [&](int st, int slab, int kb) {
+        if (p.swiglu) {
+          tma_load_2d_hint(tiles + st * STAGE_BYTES, &tma_w, &full_bar[st], kb * SG_BK, slab * 64, pol_stream);
+          tma_load_2d_hint(tiles + st * STAGE_BYTES + 64 * 128, &tma_w, &full_bar[st], kb * SG_BK, p.half_n + slab * 64, pol_stream);
+        } else {
+          tma_load_2d_hint(tiles + st * STAGE_BYTES, &tma_w, &full_bar[st], kb * SG_BK, slab * SG_BM, pol_stream);
+        }
+      };
+      int stage = 0;
+      uint32_t phase = 0;          // parity the consumer will wait for on `stage`
+      int slab, kb0, kb1;
+      item_range(first, slab, kb0, kb1);
+      // the first item's weights do not depend on the previous kernel: start streaming them before the dependency resolves
+      const int pre = min(kb1 - kb0, stages);
+      for (int i = 0; i < pre; ++i) {
+        mbar_arrive_expect_tx(&full_bar[i], STAGE_BYTES);
+        load_w(i, slab, kb0 + i);
+      }
+      if (dbg) p.dbg[1] = gtimer();
+      pdl_wait();
+      if (dbg) p.dbg[2] = gtimer();
+      for (int i = 0; i < pre; ++i)
+        tma_load_2d_hint(tiles + i * STAGE_BYTES + SG_W_BYTES, &tma_x, &full_bar[i], (kb0 + i) * SG_BK, 0, pol_keep);
+      stage = pre == stages ? 0 : pre;
+      phase = pre == stages ? 1 : 0;
+      const int F = min((int)gridDim.x, p.total_items);
+      auto fetch = [&]() {
+        const int old = atomicAdd(p.sched_counter, 1);
+        if (old == p.total_items - 1) *p.sched_counter = 0;       // the last fetch of the launch re-arms the counter
+        const int id = F + old;
+        return id < p.total_items ? id : -1;
+      };
+      int nxt = fetch();            // one item ahead: the round trip of the atomic hides under this item's loads
+      int qn = 0;
+      int kb_done = pre;
+      while (true) {
+        for (int kb = kb0 + kb_done; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+          load_w(stage, slab, kb);
+          tma_load_2d_hint(tiles + stage * STAGE_BYTES + SG_W_BYTES, &tma_x, &full_bar[stage], kb * SG_BK, 0, pol_keep);
+          if (++stage == stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        // publish the next item (or -1 = no more work) to the MMA and epilogue warps
+        const int slot = qn % SG_QN;
+        mbar_wait(&q_empty[slot], ((qn / SG_QN) & 1) ^ 1);
+        q_item[slot] = nxt;
+        mbar_arrive(&q_full[slot]);
+        ++qn;
+        if (nxt < 0) break;
+        item_range(nxt, slab, kb0, kb1);
+        kb_done = 0;
+        nxt = fetch();
+      }
+    } else if (lane == 0) {
+      pdl_wait();
+    }
+  } else if (warp_idx == 1) {
+    // ===================== MMA issuer (single thread) =====================
+    if (lane == 0 && first >= 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(SG_BM, MP);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0, qn = 0;
+      int item = first;
+      while (item >= 0) {
+        int slab, kb0, kb1;
+        item_range(item, slab, kb0, kb1);
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * MP;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t a_desc = umma_desc_sw128_kmajor(smem_u32(tiles + stage * STAGE_BYTES));
+          const uint64_t b_desc = umma_desc_sw128_kmajor(smem_u32(tiles + stage * STAGE_BYTES + SG_W_BYTES));
+#pragma unroll
+          for (int k = 0; k < SG_BK / 16; ++k)
+            umma_bf16_ss(tmem_d, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);
+          if (++stage == stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full_bar[acc]);
+        ++it;
+        const int slot = qn % SG_QN;
+        mbar_wait(&q_full[slot], (qn / SG_QN) & 1);
+        item = q_item[slot];
+        mbar_arrive(&q_empty[slot]);
+        ++qn;
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5 = TMEM lane quadrants 2,3,0,1) =====================
+    pdl_wait();
+    const int q = warp_idx & 3;
+    const int et = (warp_idx - 2) * 32 + lane;   // 0..127
+    const int r = q * 32 + lane;                 // weight row inside the slab == TMEM lane
+    int it = 0, qn = 0;
+    int item = first;
+    while (item >= 0) {
+      int slab, kb0, kb1;
+      item_range(item, slab, kb0, kb1);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      uint32_t v[MP];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * MP;
+      if constexpr (MP == 16) {
+        tmem_ld_32x32b_x16(taddr, v);
+      } else {
+#pragma unroll
+        for (int c = 0; c < MP / 32; ++c) tmem_ld_32x32b_x32(taddr + c * 32, v + c * 32);
+      }
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&tmem_empty_bar[acc]);          // accumulator is in registers: the MMA warp may reuse it
+      const int n = slab * SG_BM + r;
+      bool finish = p.segs == 1;
+      if (!finish) {
+        float* mine = p.ws + (size_t)item * MP * SG_BM;
+#pragma unroll
+        for (int m = 0; m < MP; ++m) mine[m * SG_BM + r] = __uint_as_float(v[m]);
+        __threadfence();
+        epi_bar_sync();
+        if (et == 0) {
+          const int old = atomicAdd(&p.counters[slab], 1);
+          const int last = (old == p.segs - 1) ? 1 : 0;
+          if (last) p.counters[slab] = 0;         // self-resetting: the next launch finds zeros
+          *s_flag = last;
+        }
+        epi_bar_sync();
+        finish = *s_flag != 0;
+        epi_bar_sync();                            // s_flag may be rewritten by the next item
+        if (finish) {
+          __threadfence();
+#pragma unroll
+          for (int m = 0; m < MP; ++m) v[m] = 0u;
+          for (int sg = 0; sg < p.segs; ++sg) {    // fixed order: deterministic
+            const float* part = p.ws + (size_t)(slab * p.segs + sg) * MP * SG_BM;
+#pragma unroll
+            for (int m = 0; m < MP; ++m) v[m] = __float_as_uint(__uint_as_float(v[m]) + __ldcg(part + m * SG_BM + r));
+          }
+        }
+      }
+      if (p.swiglu) {
+        if (finish) {
+          const int col = slab * 64 + (r & 63);
+          if (r >= 64) {
+            const float b = (p.bias && col < p.half_n) ? __bfloat162float(p.bias[p.half_n + col]) : 0.f;
+#pragma unroll
+            for (int m = 0; m < MP; ++m) xs[m * 64 + (r - 64)] = __bfloat162float(__float2bfloat16(__uint_as_float(v[m]) + b));
+          }
+          epi_bar_sync();
+          if (r < 64 && col < p.half_n) {
+            const float b = p.bias ? __bfloat162float(p.bias[col]) : 0.f;
+            bf16* yp = reinterpret_cast<bf16*>(p.y) + col;
+#pragma unroll
+            for (int m = 0; m < MP; ++m) {
+              if (m < p.M) {
+                const float g = __bfloat162float(__float2bfloat16(__uint_as_float(v[m]) + b));
+                const float u = xs[m * 64 + r];
+                yp[(long long)m * p.ldy] = __float2bfloat16(g * (1.0f / (1.0f + __expf(-g))) * u);
+              }
+            }
+          }
+          epi_bar_sync();                          // xs is rewritten by the next finished slab
+        }
+      } else if (finish && n < p.N) {
+        const float b = p.bias ? __bfloat162float(p.bias[n]) : 0.f;
+        if (p.out_f32) {
+          float* yp = reinterpret_cast<float*>(p.y) + n;
+#pragma unroll
+          for (int m = 0; m < MP; ++m)
+            if (m < p.M) yp[(long long)m * p.ldy] = __uint_as_float(v[m]) + b;
+        } else {
+          bf16* yp = reinterpret_cast<bf16*>(p.y) + n;
+#pragma unroll
+          for (int m = 0; m < MP; ++m)
+            if (m < p.M) yp[(long long)m * p.ldy] = __float2bfloat16(__uint_as_float(v[m]) + b);
+        }
+      }
+      ++it;
+      const int slot = qn % SG_QN;
+      mbar_wait(&q_full[slot], (qn / SG_QN) & 1);
+      item = q_item[slot];
+      mbar_arrive(&q_empty[slot]);
+      ++qn;
+    }
+    if (p.dbg && blockIdx.x == 0 && et == 0) p.dbg[3] = gtimer();
+  }
+#ifdef T1_SG_DBG
+  if (threadIdx.x == 64 + 0) g_cta_t[2][blockIdx.x] = gtimer();
+#endif
   tc_fence_before();
   __syncthreads();
   if (warp_idx == 1) {
@@ -310,7 +712,27 @@ int env_int(const char* name, int dflt) {
 }
 unsigned long long* g_dbg = nullptr;   // device ring of 4-stamp records (t1_stream_gemm_debug)
 int g_dbg_slots = 0, g_dbg_next = 0;
+int g_dynamic = -1;                      // T1_STREAM_DYNAMIC (default 1): dynamically scheduled kernel
 int g_stages = -1, g_ctas_per_sm = -1;   // tuning knobs: T1_STREAM_STAGES / T1_STREAM_CTAS_PER_SM or t1_stream_gemm_tune()
+
+template <int MP>
+int launch_stream_dyn(const CUtensorMap& tw, const CUtensorMap& tx, SgParams p, int grid, int smem, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(stream_gemm_dyn_kernel<MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) {
+      t1_set_error("t1_stream_gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return T1_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  cudaError_t e = t1_launch(stream_gemm_dyn_kernel<MP>, dim3(grid), dim3(SG_THREADS), (size_t)smem, stream, tw, tx, p);
+  if (e != cudaSuccess) {
+    t1_set_error("t1_stream_gemm: launch failed: %s", cudaGetErrorString(e));
+    return T1_ERR_CUDA;
+  }
+  return T1_OK;
+}
 
 template <int MP>
 int launch_stream(const CUtensorMap& tw, const CUtensorMap& tx, SgParams p, int grid, int smem, cudaStream_t stream) {
@@ -336,9 +758,10 @@ int launch_stream(const CUtensorMap& tw, const CUtensorMap& tx, SgParams p, int 
 // Workspace bytes a caller must provide for t1_stream_gemm with up to max_m rows: slab counters (the first 64 KB, which
 // must be ZERO before the first launch; every launch leaves them zero) followed by the fp32 partial tiles.
 extern "C" long long t1_stream_gemm_workspace_bytes(int max_m) {
-  const long long max_ctas = 2LL * t1_num_sms();
   const long long mp = max_m <= 16 ? 16 : (max_m <= 32 ? 32 : 64);
-  return SG_COUNTER_BYTES + max_ctas * 2 * mp * SG_BM * 4;
+  // static split: two partial tiles per CTA (<= 2 CTAs per SM); dynamic scheduler: one per (slab, k-segment) item, at
+  // most 8 items per SM when slabs are split
+  return SG_COUNTER_BYTES + 8LL * t1_num_sms() * mp * SG_BM * 4;
 }
 
 // Diagnostics: when buf != NULL, launch i (counted from this call) makes CTA 0 write 4 %globaltimer stamps
@@ -350,14 +773,23 @@ extern "C" void t1_stream_gemm_debug(void* buf, int slots) {
 }
 
 // Ring depth (0 = default: ~108 KB per CTA) and CTAs per SM (1 or 2) of subsequent launches.
+extern "C" void t1_stream_gemm_dynamic(int on) { g_dynamic = on < 0 ? 0 : on; }
+
 extern "C" void t1_stream_gemm_tune(int stages, int ctas_per_sm) {
   g_stages = stages > 0 ? stages : 0;
   g_ctas_per_sm = ctas_per_sm > 0 ? ctas_per_sm : 1;
 }
 
+struct SgTail {
+  void* resid = nullptr;
+  const void* norm_w = nullptr;
+  void* h_out = nullptr;
+  float eps = 0.f;
+};
+
 static int stream_gemm_impl(const void* x, long long ldx, const void* W, long long ldw, const void* bias, void* y,
                             long long ldy, int M, int N, int K, int out_f32, int swiglu, void* workspace,
-                            long long workspace_bytes, cudaStream_t stream) {
+                            long long workspace_bytes, cudaStream_t stream, SgTail tail = SgTail()) {
   T1_CHECK_ARG(x && W && y && workspace, "t1_stream_gemm: null operand");
   T1_CHECK_ARG(M > 0 && M <= 64, "t1_stream_gemm: M=%d must be in [1, 64]", M);
   T1_CHECK_ARG(N > 0 && K > 0 && K % 8 == 0, "t1_stream_gemm: K %% 8 required (N=%d K=%d)", N, K);
@@ -412,12 +844,50 @@ static int stream_gemm_impl(const void* x, long long ldx, const void* W, long lo
   p.out_f32 = out_f32;
   p.swiglu = swiglu;
   p.half_n = half_n;
+  p.tail_x = reinterpret_cast<bf16*>(tail.resid);
+  p.tail_w = reinterpret_cast<const bf16*>(tail.norm_w);
+  p.tail_h = reinterpret_cast<bf16*>(tail.h_out);
+  p.tail_eps = tail.eps;
+  p.segs = 1;
+  p.seg_k = kblocks;
+  p.total_items = slabs;
+  p.sched_counter = nullptr;
+  p.tail_counter = reinterpret_cast<int*>(workspace) + SG_COUNTER_BYTES / 4 - 2;     // last two words of the counter region
+  T1_CHECK_ARG(slabs * 4 <= SG_COUNTER_BYTES - 8, "t1_stream_gemm: N=%d exceeds the counter region", N);
+  T1_CHECK_ARG(!tail.resid || grid <= t1_num_sms(), "t1_stream_gemm_resnorm: needs every CTA resident (grid %d > %d SMs)", grid, t1_num_sms());
   p.dbg = nullptr;
   if (g_dbg && g_dbg_slots > 0) {
     p.dbg = g_dbg + 4 * (size_t)(g_dbg_next % g_dbg_slots);
     ++g_dbg_next;
   }
-  if (MP == 16) rc = launch_stream<16>(tw, tx, p, grid, smem, stream);
+  if (g_dynamic < 0) g_dynamic = env_int("T1_STREAM_DYNAMIC", 1);
+  // Measured on B200 (tools/stream_gemm_spread.py, profiles/r01_stream_gemm_spread.txt): whole-slab items (no k-split)
+  // pay off when there are many slabs per SM (lm_head: last CTA done at 177 us vs 187 us static); splitting slabs into
+  // k-segments does not (gate_up 57 vs 50 us, down 68 vs 30 us: per-item partial tiles + the segment reduction cost more
+  // than the balance gains), so mode 1 only takes GEMMs with >= 4 slabs per SM.  Mode 2 forces the k-split (experiments).
+  if (g_dynamic && !tail.resid && (g_dynamic >= 2 || slabs >= 4 * t1_num_sms())) {
+    // items = (slab, k-segment): at most 8 per SM, segments of >= 8 k-blocks (128 KB of weights)
+    const int max_items = 8 * t1_num_sms();
+    int segs = 1;
+    if (g_dynamic >= 2 && slabs < max_items) {
+      segs = kblocks / 8;
+      if (segs > max_items / slabs) segs = max_items / slabs;
+      if (segs < 1) segs = 1;
+    }
+    const int seg_k = (kblocks + segs - 1) / segs;
+    segs = (kblocks + seg_k - 1) / seg_k;
+    p.segs = segs;
+    p.seg_k = seg_k;
+    p.total_items = slabs * segs;
+    p.sched_counter = reinterpret_cast<int*>(workspace) + SG_COUNTER_BYTES / 4 - 3;
+    T1_CHECK_ARG(slabs * 4 <= SG_COUNTER_BYTES - 12, "t1_stream_gemm: N=%d exceeds the counter region", N);
+    const long long need_dyn = SG_COUNTER_BYTES + (segs > 1 ? (long long)p.total_items * MP * SG_BM * 4 : 0);
+    T1_CHECK_ARG(workspace_bytes >= need_dyn, "t1_stream_gemm: workspace too small (%lld < %lld)", workspace_bytes, need_dyn);
+    const int grid_dyn = p.total_items < t1_num_sms() ? p.total_items : t1_num_sms();
+    if (MP == 16) rc = launch_stream_dyn<16>(tw, tx, p, grid_dyn, smem, stream);
+    else if (MP == 32) rc = launch_stream_dyn<32>(tw, tx, p, grid_dyn, smem, stream);
+    else rc = launch_stream_dyn<64>(tw, tx, p, grid_dyn, smem, stream);
+  } else if (MP == 16) rc = launch_stream<16>(tw, tx, p, grid, smem, stream);
   else if (MP == 32) rc = launch_stream<32>(tw, tx, p, grid, smem, stream);
   else rc = launch_stream<64>(tw, tx, p, grid, smem, stream);
   if (rc) return rc;
@@ -441,3 +911,28 @@ extern "C" int t1_stream_gemm_swiglu(const void* x, long long ldx, const void* W
   T1_CHECK_ARG(I > 0 && I % 64 == 0, "t1_stream_gemm_swiglu: I=%d must be a positive multiple of 64", I);
   return stream_gemm_impl(x, ldx, W, ldw, bias, y, ldy, M, 2 * I, K, 0, 1, workspace, workspace_bytes, stream);
 }
+
+// y[M, N] = x W^T (bf16), then  resid[M, N] += y  (in place, bf16 add as HF Q25:805-827) and
+// h_out[M, N] = rmsnorm(resid, eps) * norm_w — the projection, the residual add and the NEXT RMSNorm of a decode layer
+// in one launch (after a grid-wide arrive counter, CTA b normalises row b; replaces t1_stream_gemm + t1_rmsnorm(delta = y)).  N % 8 == 0,
+// resid / h_out contiguous [M, N].
+extern "C" int t1_stream_gemm_resnorm(const void* x, long long ldx, const void* W, long long ldw, void* y, long long ldy,
+                                      int M, int N, int K, void* resid, const void* norm_w, float eps, void* h_out,
+                                      void* workspace, long long workspace_bytes, cudaStream_t stream) {
+  T1_CHECK_ARG(resid && norm_w && h_out, "t1_stream_gemm_resnorm: null pointer");
+  T1_CHECK_ARG(N % 8 == 0 && ldy % 8 == 0, "t1_stream_gemm_resnorm: N and ldy must be multiples of 8");
+  T1_CHECK_ARG((((uintptr_t)resid | (uintptr_t)norm_w | (uintptr_t)h_out | (uintptr_t)y) & 15) == 0,
+               "t1_stream_gemm_resnorm: 16-byte alignment required");
+  SgTail t;
+  t.resid = resid;
+  t.norm_w = norm_w;
+  t.h_out = h_out;
+  t.eps = eps;
+  return stream_gemm_impl(x, ldx, W, ldw, nullptr, y, ldy, M, N, K, 0, 0, workspace, workspace_bytes, stream, t);
+}
+
+#ifdef T1_SG_DBG
+extern "C" int t1_stream_gemm_cta_times(unsigned long long* out) {
+  return cudaMemcpyFromSymbol(out, g_cta_t, sizeof(unsigned long long) * 3 * 512) == cudaSuccess ? 0 : -2;
+}
+#endif

@@ -416,26 +416,39 @@ class Engine:
         try:
             s = stream_ptr()
             ops.gather_rows(self.p("model.embed_tokens.weight"), st["next_ids"], out=x)
+            fuse_norm = self.run.decode_fuse_norm and cfg.hidden_size % 8 == 0
             for l in range(L):
                 pre = f"model.layers.{l}."
-                ops.rmsnorm(x, self.p(pre + "input_layernorm.weight"), eps, delta=down if l > 0 else None, out=h)
+                if l == 0 or not fuse_norm:
+                    ops.rmsnorm(x, self.p(pre + "input_layernorm.weight"), eps, delta=down if (l > 0 and not fuse_norm) else None, out=h)
                 ops.stream_gemm(h, self.p(pre + "self_attn.qkv.weight"), ws, out=qkv, bias=self.p(pre + "self_attn.qkv.bias"))
-                # rope + KV append are fused into the attention kernel (fuse_rope = 1)
+                # rope + KV append are fused into the attention kernel
                 if self.run.decode_attn == "cluster":
                     call("t1_decode_attn_cluster", ptr(qkv), qkv.stride(0), ptr(tab[l]), st["kv_maps"][l].ctypes.data, n, G, Hq, Hkv, hd,
                          st["cpad"], ptr(st["step"]), ptr(attn), attn.stride(0), scale, 0, s)
                 else:
                     call("t1_decode_attn_groups", ptr(qkv), qkv.stride(0), ptr(tab[l]), n, G, Hq, Hkv, hd, st["max_P"], st["cpad"],
                          ptr(st["step"]), ptr(attn), attn.stride(0), scale, 1, s)
-                ops.stream_gemm(attn, self.p(pre + "self_attn.o_proj.weight"), ws, out=o)
-                ops.rmsnorm(x, self.p(pre + "post_attention_layernorm.weight"), eps, delta=o, out=h)
+                if fuse_norm:      # o projection + residual add + post-attention RMSNorm in one launch
+                    ops.stream_gemm_resnorm(attn, self.p(pre + "self_attn.o_proj.weight"), ws, x,
+                                            self.p(pre + "post_attention_layernorm.weight"), eps, h, out=o)
+                else:
+                    ops.stream_gemm(attn, self.p(pre + "self_attn.o_proj.weight"), ws, out=o)
+                    ops.rmsnorm(x, self.p(pre + "post_attention_layernorm.weight"), eps, delta=o, out=h)
                 if cfg.intermediate_size % 64 == 0:
                     ops.stream_gemm_swiglu(h, self.p(pre + "mlp.gate_up.weight"), ws, out=act)    # SwiGLU in the epilogue
                 else:
                     ops.stream_gemm(h, self.p(pre + "mlp.gate_up.weight"), ws, out=gu)
                     ops.swiglu(gu, out=act)
-                ops.stream_gemm(act, self.p(pre + "mlp.down_proj.weight"), ws, out=down)
-            ops.rmsnorm(x, self.p("model.norm.weight"), eps, delta=down, out=st["hN"])
+                if fuse_norm:      # down projection + residual add + the NEXT layer's input RMSNorm (or the final norm)
+                    last = l == L - 1
+                    ops.stream_gemm_resnorm(act, self.p(pre + "mlp.down_proj.weight"), ws, x,
+                                            self.p("model.norm.weight" if last else f"model.layers.{l + 1}.input_layernorm.weight"),
+                                            eps, st["hN"] if last else h, out=down)
+                else:
+                    ops.stream_gemm(act, self.p(pre + "mlp.down_proj.weight"), ws, out=down)
+            if not fuse_norm:
+                ops.rmsnorm(x, self.p("model.norm.weight"), eps, delta=down, out=st["hN"])
             ops.stream_gemm(st["hN"], self.lm_head(), ws, out=st["logits"])
             self._sample(st, st["logits"], st["logits"].stride(0), B, temperature, top_k, 0, ptr(st["seed_dev"]), ptr(st["step"]), 1,
                          st["finished"], st["out_ids"], st["next_ids"])

@@ -142,6 +142,21 @@ def stream_gemm_swiglu(x, w_gate_up, workspace, out=None, bias=None):
     return out
 
 
+def stream_gemm_resnorm(x, w, workspace, resid, norm_w, eps, h_out, out=None):
+    """out = x @ w^T;  resid += out (in place);  h_out = rmsnorm(resid, eps) * norm_w — projection, residual add and the
+    next RMSNorm of a decode layer in one launch."""
+    M, K = x.shape
+    N = w.shape[0]
+    assert x.stride(1) == 1 and w.stride(1) == 1 and w.shape[1] == K
+    assert resid.shape == (M, N) and resid.is_contiguous() and h_out.shape == (M, N) and h_out.is_contiguous()
+    if out is None:
+        out = torch.empty((M, N), device=x.device, dtype=BF16)
+    assert out.dtype == BF16 and out.stride(1) == 1
+    call("t1_stream_gemm_resnorm", ptr(x), x.stride(0), ptr(w), w.stride(0), ptr(out), out.stride(0), M, N, K, ptr(resid),
+         ptr(norm_w), float(eps), ptr(h_out), ptr(workspace), workspace.numel(), stream_ptr())
+    return out
+
+
 def linear(x, w, out=None, bias=None, accumulate=False, out_dtype=BF16):
     """Dispatch on the row count: <= 64 rows stream the weights (HBM-bound), otherwise the tcgen05 tile kernel."""
     if x.shape[0] <= 64 and w.shape[0] % 16 == 0 and x.shape[1] % 32 == 0 and (bias is None or bias.dtype == BF16):
