@@ -18,15 +18,14 @@
 namespace {
 
 constexpr int BM = 128;
-constexpr int BN = 256;
+constexpr int BN_MAX = 256;   // output-tile width is a template parameter BN in {256, 224, 192}; 256 is the default
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle atom row
 constexpr int STAGES = 4;
 constexpr int A_BYTES = BM * BK * 2;
-constexpr int B_BYTES = BN * BK * 2;
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int B_BYTES_MAX = BN_MAX * BK * 2;
 constexpr int UMMA_K = 16;
 constexpr int NUM_THREADS = 256;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES_MAX) + 1024 /*align slack*/ + 256 /*barriers*/;
 
 enum : int {
   GEMM_OUT_F32 = 1,     // D is fp32 (else bf16)
@@ -44,15 +43,18 @@ struct EpiParams {
   int flags;
 };
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, int M, int N,
                     int K, int group_m, EpiParams epi) {
+  static_assert(BN % 16 == 0 && BN <= BN_MAX && (!B_MN || BN % 64 == 0), "tile width");
+  constexpr int B_BYTES = BN * BK * 2;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_tiles = smem;
   uint8_t* b_tiles = smem + STAGES * A_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * (A_BYTES + B_BYTES_MAX));
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
@@ -90,7 +92,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     }
     mbar_fence_init();
   }
-  if (warp_idx == 2) tmem_alloc<512>(tmem_ptr_smem);
+  if (warp_idx == 2) tmem_alloc<512>(tmem_ptr_smem);      // two BN-column accumulators (2 * BN <= 512)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -181,7 +183,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       const int row = m_blk * BM + q * 32 + lane;
       const uint32_t taddr_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = 0; c < BN / 32; ++c) {      // BN is a multiple of 32 for every instantiated width
         const int col0 = n_blk * BN + c * 32;
         if (col0 >= N) break;  // warp-uniform
         uint32_t v[32];
@@ -268,30 +270,29 @@ extern "C" int t1_gemm_bf16_tn(const void* A, long long lda, const void* B, long
   T1_CHECK_ARG(lda >= (a_mn ? M : K) && ldb >= (b_mn ? N : K) && ldd >= N,
                "t1_gemm_bf16_tn: leading dimension smaller than row length");
   T1_CHECK_ARG(!a_mn || M % 8 == 0, "t1_gemm_bf16_tn: MN-major A needs M %% 8 == 0 (M=%d)", M);
+  // ---- output-tile width ----
+  // 224 / 192-wide tiles fill the last wave better for N = 3584 (4.35 -> 4.97 waves), but measured on B200 the whole step's
+  // GEMM time went 626.9 -> 637.3 ms with the fullest-last-wave choice: the narrower SS MMAs are shared-memory bound
+  // (more operand bytes per FLOP).  256 stays the default; T1_GEMM_BN = 224 | 192 selects the others for experiments.
+  const int num_m = (M + BM - 1) / BM;
+  const int sms = t1_num_sms();
+  int BN = 256;
+  {
+    static const char* env = getenv("T1_GEMM_BN");
+    if (env && (atoi(env) == 192 || (atoi(env) == 224 && !b_mn))) BN = atoi(env);
+  }
   CUtensorMap ta, tb;
   int rc = a_mn ? t1_make_tmap_bf16(&ta, A, K, M, lda, BK, 64) : t1_make_tmap_bf16(&ta, A, M, K, lda, BM, BK);
   if (rc) return rc;
   rc = b_mn ? t1_make_tmap_bf16(&tb, B, K, N, ldb, BK, 64) : t1_make_tmap_bf16(&tb, B, N, K, ldb, BN, BK);
   if (rc) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e != cudaSuccess) {
-      t1_set_error("t1_gemm_bf16_tn: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      return T1_ERR_CUDA;
-    }
-    attr_set = true;
-  }
-  const int num_tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
-  const int grid = num_tiles < t1_num_sms() ? num_tiles : t1_num_sms();
+  const int num_n = (N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int grid = num_tiles < sms ? num_tiles : sms;
   EpiParams epi{D, bias, ldd, flags};
   // DRAM-traffic model for the raster order (L2 = 126 MB; measured with ncu on the gate_up wgrad, M=37888 N=3584 K=5888:
   // m-fastest re-read dY 14x = 6.3 GB per launch).  An operand that fits in ~48 MB of L2 is read once whatever the order;
   // otherwise keep a group of A row-blocks resident (<= 40 MB) while B streams past it.
-  const int num_m = (M + BM - 1) / BM;
   int group_m = num_m;
   {
     const double a_bytes = 2.0 * M * K, b_bytes = 2.0 * N * K, cap = 48e6;
@@ -300,18 +301,43 @@ extern "C" int t1_gemm_bf16_tn(const void* A, long long lda, const void* B, long
       if (gm < 1) gm = 1;
       if (gm > num_m) gm = num_m;
       const double grouped = a_bytes + (b_bytes <= cap ? b_bytes : b_bytes * ((num_m + gm - 1) / gm));
-      const int num_n = (N + BN - 1) / BN;
-      const double waves_n = (double)num_n * num_m / t1_num_sms() / (num_m < t1_num_sms() ? 1.0 : (double)num_m / t1_num_sms());
-      const double m_fast = a_bytes * (num_m >= t1_num_sms() ? num_n : (waves_n < 1.0 ? 1.0 : waves_n)) + b_bytes;
+      const double waves_n = (double)num_n * num_m / sms / (num_m < sms ? 1.0 : (double)num_m / sms);
+      const double m_fast = a_bytes * (num_m >= sms ? num_n : (waves_n < 1.0 ? 1.0 : waves_n)) + b_bytes;
       if (grouped < m_fast) group_m = gm;
     }
     static const char* env = getenv("T1_GEMM_GROUP_M");
     if (env && atoi(env) > 0) group_m = atoi(env) < num_m ? atoi(env) : num_m;
   }
-  if (a_mn && b_mn) gemm_bf16_tn_kernel<true, true><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, M, N, K, group_m, epi);
-  else if (a_mn) gemm_bf16_tn_kernel<true, false><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, M, N, K, group_m, epi);
-  else if (b_mn) gemm_bf16_tn_kernel<false, true><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, M, N, K, group_m, epi);
-  else gemm_bf16_tn_kernel<false, false><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, M, N, K, group_m, epi);
+  cudaError_t le = cudaSuccess;
+#define T1_GEMM_LAUNCH(AMN, BMN, BNV)                                                                                         \
+  do {                                                                                                                        \
+    static bool attr_set = false;                                                                                             \
+    if (!attr_set) {                                                                                                          \
+      le = cudaFuncSetAttribute(gemm_bf16_tn_kernel<AMN, BMN, BNV>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES); \
+      attr_set = (le == cudaSuccess);                                                                                         \
+    }                                                                                                                         \
+    if (le == cudaSuccess)                                                                                                    \
+      gemm_bf16_tn_kernel<AMN, BMN, BNV><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, M, N, K, group_m, epi);            \
+  } while (0)
+#define T1_GEMM_BY_MAJOR(BNV)                                   \
+  do {                                                          \
+    if (a_mn && b_mn) T1_GEMM_LAUNCH(true, true, BNV);          \
+    else if (a_mn) T1_GEMM_LAUNCH(true, false, BNV);            \
+    else if (b_mn) T1_GEMM_LAUNCH(false, true, BNV);            \
+    else T1_GEMM_LAUNCH(false, false, BNV);                     \
+  } while (0)
+  if (BN == 256) T1_GEMM_BY_MAJOR(256);
+  else if (BN == 192) T1_GEMM_BY_MAJOR(192);
+  else {
+    if (a_mn) T1_GEMM_LAUNCH(true, false, 224);
+    else T1_GEMM_LAUNCH(false, false, 224);
+  }
+#undef T1_GEMM_BY_MAJOR
+#undef T1_GEMM_LAUNCH
+  if (le != cudaSuccess) {
+    t1_set_error("t1_gemm_bf16_tn: cudaFuncSetAttribute: %s", cudaGetErrorString(le));
+    return T1_ERR_CUDA;
+  }
   T1_CUDA_LAUNCH_CHECK("t1_gemm_bf16_tn");
   return T1_OK;
 }
