@@ -172,3 +172,33 @@ def test_optimizer_step_moves_weights_like_torch_adamw():
     assert torch.allclose(eng.master, ref.detach(), atol=1e-6, rtol=1e-4)
     assert torch.equal(eng.w.train.buf, eng.master.to(torch.bfloat16))
     assert eng.grad_fresh
+
+
+def test_rollout_stops_at_eos_pads_and_masks_like_the_reference():
+    """HF generate semantics the trainer relies on (timer1_trainer.py:568-590): a sequence that emits a stop token keeps it,
+    every later position is pad_token_id, the completion mask covers tokens up to AND INCLUDING the first EOS, and the
+    decode loop ends early once every sequence has finished."""
+    import dataclasses
+
+    from time_r1_b200 import config, engine, ops, weights
+
+    O, cfg, ocfg, w_or, eng, prompt, pix, ids, grid = build(beta=0.0)
+    G, C = 4, 40
+    emb, _, _ = eng.vit_forward(prompt)
+    base = eng.rollout(prompt, emb, G, C, temperature=0.0, top_k=0, seed=1)[0].cpu().tolist()
+    k = next(i for i in range(1, C) if base[i] not in base[:i])      # first step whose token did not occur earlier
+    stop_tok = base[k]
+    cfg2 = dataclasses.replace(cfg, eos_token_id=stop_tok, stop_token_ids=(stop_tok, cfg.pad_token_id))
+    mw = weights.ModelWeights(cfg2, "cuda")
+    mw.load_state_dict(w_or)
+    eng2 = engine.Engine(cfg2, mw, config.RunConfig(num_generations=G, max_completion_length=C, beta=0.0), with_ref=False)
+    emb2, _, _ = eng2.vit_forward(prompt)
+    comp = eng2.rollout(prompt, emb2, G, C, temperature=0.0, top_k=0, seed=1)
+    for g in range(G):
+        row = comp[g].cpu().tolist()
+        assert row[:k + 1] == base[:k + 1]
+        assert all(t == cfg2.pad_token_id for t in row[k + 1:]), row
+    mask, lengths = ops.eos_mask(comp, cfg2.eos_token_id)
+    assert mask.sum(1).tolist() == [k + 1] * G and lengths.tolist() == [k + 1] * G
+    # early exit: the step counter stopped at the first all-finished check (check_every = 32), not at C - 1
+    assert int(eng2._last_decode_state["step"].item()) <= 32
