@@ -49,6 +49,8 @@ def parse_args():
     ap.add_argument("--groups-per-step", type=int, default=2,
                     help="prompt-groups per GPU per optimizer step = gradient_accumulation_steps (2 in scripts/posttrain/train_rl.sh:27)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-vit-prefetch", dest="vit_prefetch", action="store_false",
+                    help="do not overlap the next step's frozen ViT blocks with this step's optimizer phase")
     ap.add_argument("--phase-times", action="store_true", help="print a per-phase breakdown to stderr")
     ap.add_argument("--kernel-times", action="store_true", help="print per-entry-point CUDA-event totals of one extra step to stderr")
     ap.add_argument("--ncu-range", action="store_true",
@@ -312,7 +314,9 @@ def run_ours(args):
     except Exception:
         pass
 
-    def one_step(step_idx: int, e2e: bool, timers=None):
+    pending = {}      # ViT prefetch of the NEXT step's prompts, issued before this step's optimizer phase
+
+    def make_prompts(e2e: bool):
         prompts = []
         for i, (ids_i, frames_host_i, grid_i) in enumerate(inputs):
             if e2e:      # H2D of the step's frames from pinned memory, device pre-processing inside the step
@@ -320,7 +324,19 @@ def run_ours(args):
                                              frames=frames_host_i.to(dev, non_blocking=True)))
             else:
                 prompts.append(engine.Prompt(input_ids=ids_i, pixel_values=pix_devs[i], grid_thw=grid_i, second_per_grid_ts=[1.0]))
-        outs = eng.grpo_multi_step(prompts, rewards, seed=run.seed + step_idx * world + rank, loss_scale=1.0 / NG, timers=timers)
+        return prompts
+
+    def one_step(step_idx: int, e2e: bool, timers=None):
+        # the trainer's dataloader knows the next batch: its frozen ViT blocks run on a side stream under this step's
+        # optimizer phase (--fix_vit: they depend on no trained weight); every step still runs its own ViT exactly once
+        prompts, handle = pending.pop(e2e, (None, None))
+        if prompts is None:
+            prompts = make_prompts(e2e)
+        outs = eng.grpo_multi_step(prompts, rewards, seed=run.seed + step_idx * world + rank, loss_scale=1.0 / NG, timers=timers,
+                                   vit_prefetch=handle)
+        if args.vit_prefetch:
+            nxt = make_prompts(e2e)                  # e2e: the H2D copy of the next step's frames is issued here
+            pending[e2e] = (nxt, eng.prefetch_vit(nxt))
         gn = eng.optimizer_step()
         if e2e:
             return float(sum(o["loss"].item() for o in outs)), float(gn.item())   # D2H of the step's result

@@ -75,3 +75,23 @@ def test_prefill_reuse_equals_full_policy_scoring():
     err = (g_r - g_f).abs().max().item() / (g_f.abs().max().item() + 1e-12)
     cos = torch.nn.functional.cosine_similarity(g_r, g_f, dim=0).item()
     assert err < 3e-2 and cos > 0.999, (err, cos)
+
+
+def test_vit_prefetch_on_side_stream_changes_nothing():
+    """The frozen ViT blocks of the next step's prompts may run on a side stream under the optimizer phase
+    (Engine.prefetch_vit): a step fed by the prefetch handle produces bit-identical results."""
+    from test_engine_gpu import build
+
+    outs = []
+    for use_prefetch in (False, True):
+        O, cfg, ocfg, w_or, eng, prompt, pix, ids, grid = build(beta=0.04)
+        rewards = np.random.default_rng(0).random((4, 2)).astype(np.float32)
+        handle = eng.prefetch_vit([prompt]) if use_prefetch else None
+        out = eng.grpo_multi_step([prompt], [lambda c: rewards], seed=3, vit_prefetch=handle)[0]
+        gn = eng.optimizer_step()
+        torch.cuda.synchronize()
+        outs.append((out["completion_ids"].clone(), out["logp"].clone(), out["loss"].clone(), gn.clone()))
+    for a, b in zip(outs[0][:3], outs[1][:3]):
+        assert torch.equal(a, b)
+    # the gradient norm goes through fp32 atomics (norm-weight gradients): equal up to summation order
+    assert abs(outs[0][3].item() - outs[1][3].item()) <= 1e-3 * outs[0][3].item()

@@ -193,6 +193,28 @@ class Engine:
             return out
         return m
 
+    def prefetch_vit(self, prompts: list):
+        """Run the FROZEN part of the vision tower (patch-embed + blocks; --fix_vit, timer1_trainer.py:272-280) for the NEXT
+        step's prompts on a side stream.  It depends on no trained weight, so it can overlap this step's optimizer phase
+        (gradient reduce-scatter, the HBM-bound AdamW kernel, parameter all-gather).  Pass the returned handle to
+        grpo_multi_step(vit_prefetch=...); the merger (trained) still runs inside the step."""
+        if not self.run.fix_vit:
+            return None
+        if getattr(self, "_vit_stream", None) is None:
+            self._vit_stream = torch.cuda.Stream(device=self.dev)
+        main = torch.cuda.current_stream()
+        side = self._vit_stream
+        side.wait_stream(main)                      # the prompts' pixel tensors / H2D copies were issued on `main`
+        with torch.cuda.stream(side):
+            res = [self.vit_blocks(p.pixel_values, p.grid_thw, frames=p.frames) for p in prompts]
+            ev = torch.cuda.Event()
+            ev.record(side)
+        for x, delta, _ in res:                      # consumed on the main stream later
+            x.record_stream(main)
+            if delta is not None:
+                delta.record_stream(main)
+        return dict(results=res, event=ev, n=len(prompts))
+
     def vit_forward(self, prompt: Prompt, wset: str = "policy"):
         x, delta, plan = self.vit_blocks(prompt.pixel_values, prompt.grid_thw, frames=prompt.frames)
         emb = self.merger(x, delta, plan, wset)
@@ -862,14 +884,14 @@ class Engine:
     # one complete GRPO micro-step for one prompt group
     # ------------------------------------------------------------------------------------------
     def grpo_step(self, prompt: Prompt, reward_fn, seed: int | None = None, completion_override=None,
-                  loss_scale: float = 1.0, timers: dict | None = None):
+                  loss_scale: float = 1.0, timers: dict | None = None, vit_prefetch: dict | None = None):
         """One prompt-group: see grpo_multi_step."""
         ov = None if completion_override is None else [completion_override]
         return self.grpo_multi_step([prompt], [reward_fn], seed=seed, completion_overrides=ov, loss_scale=loss_scale,
-                                    timers=timers)[0]
+                                    timers=timers, vit_prefetch=vit_prefetch)[0]
 
     def grpo_multi_step(self, prompts: list, reward_fns: list, seed: int | None = None, completion_overrides=None,
-                        loss_scale: float = 1.0, timers: dict | None = None) -> list:
+                        loss_scale: float = 1.0, timers: dict | None = None, vit_prefetch: dict | None = None) -> list:
         """The micro-batches of ONE optimizer step (gradient accumulation, train_rl.sh:27), each a prompt-group:
         ViT per group -> joint rollout (shared weight stream) -> per group: mask, policy/ref scoring, rewards (host
         callback), advantage, loss, backward (gradients accumulate).
@@ -887,8 +909,14 @@ class Engine:
 
         mark("start")
         vit = []
-        for prompt in prompts:
-            x_vit, delta, plan = self.vit_blocks(prompt.pixel_values, prompt.grid_thw, frames=prompt.frames)
+        if vit_prefetch is not None:
+            assert vit_prefetch["n"] == len(prompts)
+            torch.cuda.current_stream().wait_event(vit_prefetch["event"])
+        for pi, prompt in enumerate(prompts):
+            if vit_prefetch is not None:
+                x_vit, delta, plan = vit_prefetch["results"][pi]
+            else:
+                x_vit, delta, plan = self.vit_blocks(prompt.pixel_values, prompt.grid_thw, frames=prompt.frames)
             emb = self.merger(x_vit, delta, plan, "policy")                 # x_vit now holds the final ViT stream
             vit.append((emb, x_vit, plan))
         mark("vit")
