@@ -320,13 +320,27 @@ class TimeR1_Trainer:
         for inputs in micro_batches:
             if len(inputs) != 1:
                 raise ValueError("per_device_train_batch_size must be 1 (the reference only consumes inputs[0], timer1_trainer.py:548-551)")
-        prepared = [self._prepare(inputs[0]) for inputs in micro_batches]
+        pre = getattr(self, "_prefetched", None)
+        self._prefetched = None
+        if pre is not None and pre[0] is micro_batches:
+            prepared, handle = pre[1], pre[2]
+        else:
+            prepared, handle = [self._prepare(inputs[0]) for inputs in micro_batches], None
         accum = self.args.gradient_accumulation_steps
         seed = self.run.seed + 7919 * (self.state.global_step * self.world + self.rank)
-        outs = self.engine.grpo_multi_step([p for p, _ in prepared], [r for _, r in prepared], seed=seed, loss_scale=1.0 / accum)
+        outs = self.engine.grpo_multi_step([p for p, _ in prepared], [r for _, r in prepared], seed=seed, loss_scale=1.0 / accum,
+                                           vit_prefetch=handle)
         for out in outs:
             self._log_metrics(out)
         return [o["loss"] for o in outs]
+
+    def _prefetch_next(self, micro_batches: list):
+        """Look-ahead on the dataloader: prepare the NEXT optimizer step's prompts and run their frozen ViT blocks on a
+        side stream while this step's optimizer phase (reduce-scatter, AdamW, all-gather) runs."""
+        if not self.run.fix_vit:
+            return
+        prepared = [self._prepare(inputs[0]) for inputs in micro_batches]
+        self._prefetched = (micro_batches, prepared, self.engine.prefetch_vit([p for p, _ in prepared]))
 
     def _log_metrics(self, out: dict):
         import torch
@@ -387,9 +401,13 @@ class TimeR1_Trainer:
         losses = []
         while self.state.global_step < total and not self.control.should_training_stop:
             loader = self.get_train_dataloader() if epoch > 0 else loader
-            for i in range(0, len(loader) - len(loader) % accum or len(loader), accum):
-                micro = loader[i:i + accum]
+            stop = len(loader) - len(loader) % accum or len(loader)
+            micro = loader[0:accum]
+            for i in range(0, stop, accum):
                 losses.extend(self._accum_step(micro))
+                nxt = loader[i + accum:i + 2 * accum] if i + accum < stop else None
+                if nxt and self.state.global_step + 1 < total:
+                    self._prefetch_next(nxt)
                 done = self.state.global_step - start_step
                 lr = a.learning_rate * max(0.0, 1.0 - done / max(1, total - start_step))   # linear decay, no warm-up
                 gnorm = self.engine.optimizer_step(lr=lr)
@@ -405,6 +423,7 @@ class TimeR1_Trainer:
                     self._save_checkpoint()
                 if self.state.global_step >= total or self.control.should_training_stop:
                     break
+                micro = nxt
             epoch += 1
             self.state.epoch = float(epoch)
             for cb in self.callbacks:
