@@ -48,6 +48,11 @@ unsigned long long t1_launch_count(int reset); /* kernels launched through this 
  * autograd backward (HF trainer.py:1934).  A, B bf16; D bf16 or fp32 (T1_GEMM_OUT_F32); N % 8 == 0. */
 int t1_gemm_bf16_tn(const void* A, long long lda, const void* B, long long ldb, void* D, long long ldd, int M, int N,
                     int K, const void* bias, int flags, cudaStream_t stream);
+/* act[M, I] = silu(A Wg^T + bg) * (A Wu^T + bu), W = [Wg; Wu] ([2I, K] K-major), bias [2I] bf16 or NULL: gate_up projection
+ * with the SwiGLU (HF Q25:611-624, ViT Q25:82-88) in the GEMM epilogue; gate_up ([M, 2I] bf16 or NULL) also receives the
+ * projection for the backward pass.  Bit-identical to t1_gemm_bf16_tn + t1_swiglu. */
+int t1_gemm_swiglu(const void* A, long long lda, const void* W, long long ldw, const void* bias, void* act, long long ld_act,
+                   void* gate_up, long long ld_gate_up, int M, int I, int K, cudaStream_t stream);
 
 /* y[M<=64, N] (+)= x[M,K] * W[N,K]^T (+ bias bf16).  Weight-streaming decode GEMM (HBM-bound; thread-block-cluster
  * split-K).  Replaces the per-token linears inside HF generate (timer1_trainer.py:568-573).  N % 16, K % 32. */

@@ -73,3 +73,22 @@ def test_gemm_mn_major_operands(M, N, K, a_t, b_t):
     acc = out32.clone()
     ops.gemm(a_in, b_in, out=acc, accumulate=True, a_t=a_t, b_t=b_t)
     assert (acc - 2 * ref).abs().max().item() <= 4e-5 * scale * (K ** 0.5) + 2e-4
+
+
+@pytest.mark.parametrize("M,I,K,with_bias", [(5888, 18944, 3584, False), (300, 512, 264, True), (16384 // 4, 3456, 1280, True), (77, 200, 72, False)])
+def test_gemm_swiglu_epilogue(M, I, K, with_bias):
+    """gate_up projection with the SwiGLU in the GEMM epilogue == gemm (bf16) followed by swiglu, bit for bit; the optional
+    copy of the projection equals the plain GEMM output."""
+    from time_r1_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(M + I + K)
+    a = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    w = (torch.randn(2 * I, K, device="cuda", generator=g) * 0.05).to(torch.bfloat16)
+    b = torch.randn(2 * I, device="cuda", generator=g).to(torch.bfloat16) if with_bias else None
+    gu_ref = ops.gemm(a, w, bias=b)
+    want = ops.swiglu(gu_ref)
+    gu = torch.full_like(gu_ref, float("nan"))
+    got = ops.gemm_swiglu(a, w, bias=b, gate_up_out=gu)
+    assert torch.equal(got, want), (got.float() - want.float()).abs().max().item()
+    assert torch.equal(gu, gu_ref)
+    assert torch.equal(ops.gemm_swiglu(a, w, bias=b), want)

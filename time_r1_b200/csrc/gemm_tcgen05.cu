@@ -33,6 +33,8 @@ enum : int {
   GEMM_BIAS_F32 = 4,    // bias is fp32 (else bf16)
   GEMM_A_MN = 8,        // A is given as row-major [K, M] (M contiguous)
   GEMM_B_MN = 16,       // B is given as row-major [K, N] (N contiguous)
+  GEMM_SWIGLU = 32,     // B = [W_gate; W_up] ([2N, K], K-major): D[M, N] = silu(A Wg^T + bg) * (A Wu^T + bu), bf16; each
+                        // 256-wide tile pairs 128 gate rows with their 128 up rows (t1_gemm_swiglu)
 };
 constexpr int MN_ATOM_BYTES = BK * 128;   // MN-major smem atom: [64 k-rows x 64 elements], SWIZZLE_128B
 
@@ -41,6 +43,8 @@ struct EpiParams {
   const void* bias;
   long long ldd;
   int flags;
+  void* D2;         // SWIGLU: optional [M, 2N] bf16 copy of the gate_up projection (kept for the backward pass)
+  long long ldd2;
 };
 
 template <bool A_MN, bool B_MN, int BN>
@@ -63,7 +67,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_m = (M + BM - 1) / BM;
-  const int num_n = (N + BN - 1) / BN;
+  const bool swiglu = epi.flags & GEMM_SWIGLU;
+  const int BNO = swiglu ? BN / 2 : BN;                    // output columns per tile
+  const int num_n = (N + BNO - 1) / BNO;
   const int num_tiles = num_m * num_n;
   const int num_k = (K + BK - 1) / BK;
   // Tile rasterisation: m-blocks are walked in groups of group_m; inside a group the n-blocks advance slowest, so the
@@ -120,6 +126,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 #pragma unroll
             for (int b = 0; b < BN / 64; ++b)
               tma_load_2d(b_tiles + stage * B_BYTES + b * MN_ATOM_BYTES, &tma_b, &full_bar[stage], n_blk * BN + b * 64, kb * BK);
+          } else if (swiglu) {
+            tma_load_2d(b_tiles + stage * B_BYTES, &tma_b, &full_bar[stage], kb * BK, n_blk * BNO);                          // gate rows
+            tma_load_2d(b_tiles + stage * B_BYTES + BNO * BK * 2, &tma_b, &full_bar[stage], kb * BK, N + n_blk * BNO);       // up rows
           } else {
             tma_load_2d(b_tiles + stage * B_BYTES, &tma_b, &full_bar[stage], kb * BK, n_blk * BN);
           }
@@ -182,6 +191,55 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       tc_fence_after();
       const int row = m_blk * BM + q * 32 + lane;
       const uint32_t taddr_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+      if (swiglu) {
+        // TMEM columns [0, BN/2) hold the gate projection of output columns n_blk*BNO + j, columns [BN/2, BN) the up
+        // projection of the same columns: y = silu(g) * u on the bf16-rounded projections (== gemm -> t1_swiglu)
+#pragma unroll 1
+        for (int c = 0; c < BNO / 32; ++c) {
+          const int col0 = n_blk * BNO + c * 32;
+          if (col0 >= N) break;  // warp-uniform
+          uint32_t vg[32], vu[32];
+          tmem_ld_32x32b_x32(taddr_row + c * 32, vg);
+          tmem_ld_32x32b_x32(taddr_row + BNO + c * 32, vu);
+          tmem_ld_wait();
+          if (row < M) {
+#pragma unroll
+            for (int g8 = 0; g8 < 4; ++g8) {
+              const int col = col0 + g8 * 8;
+              if (col < N) {
+                float fg[8], fu[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { fg[j] = __uint_as_float(vg[g8 * 8 + j]); fu[j] = __uint_as_float(vu[g8 * 8 + j]); }
+                if (epi.bias) {      // bf16 bias [2N]: gate part then up part
+                  const uint4 bg = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(epi.bias) + col);
+                  const uint4 bu = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(epi.bias) + N + col);
+                  const uint32_t* pg = reinterpret_cast<const uint32_t*>(&bg);
+                  const uint32_t* pu = reinterpret_cast<const uint32_t*>(&bu);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const float2 a = unpack_bf16x2(pg[j]), b = unpack_bf16x2(pu[j]);
+                    fg[2 * j] += a.x; fg[2 * j + 1] += a.y; fu[2 * j] += b.x; fu[2 * j + 1] += b.y;
+                  }
+                }
+                uint32_t og[4], ou[4], oy[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  og[j] = pack_bf16x2(fg[2 * j], fg[2 * j + 1]);
+                  ou[j] = pack_bf16x2(fu[2 * j], fu[2 * j + 1]);
+                  const float2 gg = unpack_bf16x2(og[j]), uu = unpack_bf16x2(ou[j]);
+                  oy[j] = pack_bf16x2(gg.x * (1.0f / (1.0f + __expf(-gg.x))) * uu.x, gg.y * (1.0f / (1.0f + __expf(-gg.y))) * uu.y);
+                }
+                *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(epi.D) + (long long)row * epi.ldd + col) = make_uint4(oy[0], oy[1], oy[2], oy[3]);
+                if (epi.D2) {
+                  bf16* d2 = reinterpret_cast<bf16*>(epi.D2) + (long long)row * epi.ldd2;
+                  *reinterpret_cast<uint4*>(d2 + col) = make_uint4(og[0], og[1], og[2], og[3]);
+                  *reinterpret_cast<uint4*>(d2 + N + col) = make_uint4(ou[0], ou[1], ou[2], ou[3]);
+                }
+              }
+            }
+          }
+        }
+      } else
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {      // BN is a multiple of 32 for every instantiated width
         const int col0 = n_blk * BN + c * 32;
@@ -257,9 +315,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 
 }  // namespace
 
-// C-ABI: see include/timer1.h
-extern "C" int t1_gemm_bf16_tn(const void* A, long long lda, const void* B, long long ldb, void* D, long long ldd,
-                               int M, int N, int K, const void* bias, int flags, cudaStream_t stream) {
+static int gemm_impl(const void* A, long long lda, const void* B, long long ldb, void* D, long long ldd, int M, int N, int K,
+                     const void* bias, int flags, void* D2, long long ldd2, cudaStream_t stream) {
   T1_CHECK_ARG(A && B && D, "t1_gemm_bf16_tn: null operand");
   T1_CHECK_ARG(M > 0 && N > 0 && K > 0, "t1_gemm_bf16_tn: empty problem M=%d N=%d K=%d", M, N, K);
   T1_CHECK_ARG(N % 8 == 0 && ldd % 8 == 0, "t1_gemm_bf16_tn: N and ldd must be multiples of 8 (N=%d ldd=%lld)", N, ldd);
@@ -284,18 +341,26 @@ extern "C" int t1_gemm_bf16_tn(const void* A, long long lda, const void* B, long
   CUtensorMap ta, tb;
   int rc = a_mn ? t1_make_tmap_bf16(&ta, A, K, M, lda, BK, 64) : t1_make_tmap_bf16(&ta, A, M, K, lda, BM, BK);
   if (rc) return rc;
-  rc = b_mn ? t1_make_tmap_bf16(&tb, B, K, N, ldb, BK, 64) : t1_make_tmap_bf16(&tb, B, N, K, ldb, BN, BK);
+  const bool swiglu = flags & GEMM_SWIGLU;
+  if (swiglu) {
+    T1_CHECK_ARG(!a_mn && !b_mn && !(flags & (GEMM_OUT_F32 | GEMM_ACCUMULATE | GEMM_BIAS_F32)) && BN == 256,
+                 "t1_gemm_swiglu: K-major operands, bf16 output, bf16 bias, no accumulate");
+    T1_CHECK_ARG(!D2 || (ldd2 % 8 == 0 && ldd2 >= 2LL * N && ((uintptr_t)D2 & 15) == 0), "t1_gemm_swiglu: bad gate_up output");
+  }
+  rc = b_mn ? t1_make_tmap_bf16(&tb, B, K, N, ldb, BK, 64)
+            : (swiglu ? t1_make_tmap_bf16(&tb, B, 2LL * N, K, ldb, BN / 2, BK) : t1_make_tmap_bf16(&tb, B, N, K, ldb, BN, BK));
   if (rc) return rc;
-  const int num_n = (N + BN - 1) / BN;
+  const int BNO = swiglu ? BN / 2 : BN;                    // output columns per tile
+  const int num_n = (N + BNO - 1) / BNO;
   const int num_tiles = num_m * num_n;
   const int grid = num_tiles < sms ? num_tiles : sms;
-  EpiParams epi{D, bias, ldd, flags};
+  EpiParams epi{D, bias, ldd, flags, swiglu ? D2 : nullptr, ldd2};
   // DRAM-traffic model for the raster order (L2 = 126 MB; measured with ncu on the gate_up wgrad, M=37888 N=3584 K=5888:
   // m-fastest re-read dY 14x = 6.3 GB per launch).  An operand that fits in ~48 MB of L2 is read once whatever the order;
   // otherwise keep a group of A row-blocks resident (<= 40 MB) while B streams past it.
   int group_m = num_m;
   {
-    const double a_bytes = 2.0 * M * K, b_bytes = 2.0 * N * K, cap = 48e6;
+    const double a_bytes = 2.0 * M * K, b_bytes = 2.0 * N * K * (swiglu ? 2 : 1), cap = 48e6;
     if (a_bytes > cap) {
       int gm = (int)(40e6 / (2.0 * BM * K));
       if (gm < 1) gm = 1;
@@ -340,4 +405,20 @@ extern "C" int t1_gemm_bf16_tn(const void* A, long long lda, const void* B, long
   }
   T1_CUDA_LAUNCH_CHECK("t1_gemm_bf16_tn");
   return T1_OK;
+}
+
+// C-ABI: see include/timer1.h
+extern "C" int t1_gemm_bf16_tn(const void* A, long long lda, const void* B, long long ldb, void* D, long long ldd,
+                               int M, int N, int K, const void* bias, int flags, cudaStream_t stream) {
+  T1_CHECK_ARG(!(flags & GEMM_SWIGLU), "t1_gemm_bf16_tn: use t1_gemm_swiglu");
+  return gemm_impl(A, lda, B, ldb, D, ldd, M, N, K, bias, flags, nullptr, 0, stream);
+}
+
+// act[M, I] = silu(A Wg^T + bg) * (A Wu^T + bu) with W = [Wg; Wu] ([2I, K], K-major) and bias [2I] bf16 (nullable): the
+// gate_up projection of the Qwen2 MLP (HF Q25:611-624; the ViT MLP Q25:82-88 has biases) with the SwiGLU in the GEMM
+// epilogue; gate_up (nullable, [M, 2I] bf16) receives the projection itself when the backward pass needs it.
+// Bit-identical to t1_gemm_bf16_tn (bf16) followed by t1_swiglu.  I % 8 == 0.
+extern "C" int t1_gemm_swiglu(const void* A, long long lda, const void* W, long long ldw, const void* bias, void* act,
+                              long long ld_act, void* gate_up, long long ld_gate_up, int M, int I, int K, cudaStream_t stream) {
+  return gemm_impl(A, lda, W, ldw, act, ld_act, M, I, K, bias, GEMM_SWIGLU, gate_up, ld_gate_up, stream);
 }

@@ -160,8 +160,7 @@ class Engine:
             ops.gemm(attn, g(pre + "attn.proj.weight"), out=proj, bias=g(pre + "attn.proj.bias"))
             if cfg.is_q25:
                 ops.rmsnorm(x, g(pre + "norm2.weight"), 1e-6, delta=proj, out=h)
-                gu = ops.gemm(h, g(pre + "mlp.gate_up.weight"), bias=g(pre + "mlp.gate_up.bias"))
-                act = ops.swiglu(gu)
+                act = ops.gemm_swiglu(h, g(pre + "mlp.gate_up.weight"), bias=g(pre + "mlp.gate_up.bias"))   # SwiGLU in the epilogue
                 ops.gemm(act, g(pre + "mlp.down_proj.weight"), out=down, bias=g(pre + "mlp.down_proj.bias"))
             else:
                 ops.layernorm(x, g(pre + "norm2.weight"), g(pre + "norm2.bias"), 1e-6, delta=proj, out=h)
@@ -283,8 +282,7 @@ class Engine:
                 ops.rmsnorm(x, self.p(pre + "post_attention_layernorm.weight", wset), eps, delta=o, out=h, x_out=xm)
             else:
                 ops.rmsnorm(x, self.p(pre + "post_attention_layernorm.weight", wset), eps, delta=o, out=h)
-            ops.gemm(h, self.p(pre + "mlp.gate_up.weight", wset), out=gu)
-            ops.swiglu(gu, out=act)
+            ops.gemm_swiglu(h, self.p(pre + "mlp.gate_up.weight", wset), out=act)             # SwiGLU in the GEMM epilogue
             ops.gemm(act, self.p(pre + "mlp.down_proj.weight", wset), out=down)
         hN = torch.empty((T, D), device=self.dev, dtype=BF16)
         if ckpt is not None:
@@ -333,8 +331,7 @@ class Engine:
                             need_lse=False, q_row0=P)
             ops.gemm(attn, self.p(pre + "self_attn.o_proj.weight"), out=o)
             ops.rmsnorm(x, self.p(pre + "post_attention_layernorm.weight"), eps, delta=o, out=h, x_out=xm)
-            ops.gemm(h, self.p(pre + "mlp.gate_up.weight"), out=gu)
-            ops.swiglu(gu, out=act)
+            ops.gemm_swiglu(h, self.p(pre + "mlp.gate_up.weight"), out=act)
             ops.gemm(act, self.p(pre + "mlp.down_proj.weight"), out=down)
         hN = torch.empty((Tc, D), device=dev, dtype=BF16)
         ops.rmsnorm(xm, self.p("model.norm.weight"), eps, delta=down, out=hN, x_out=ckpt_full[L][P:])
@@ -778,8 +775,7 @@ class Engine:
             self._attn(q, k, v, st.lo, st.hi, st.P, Hq, Hkv, hd, scale, out=attn, lse=lse2)
             ops.gemm(attn, Wo, out=o)
             ops.rmsnorm(x_in, self.p(pre + "post_attention_layernorm.weight"), eps, delta=o, out=h2, x_out=xm)
-            ops.gemm(h2, Wgu, out=gu)
-            ops.swiglu(gu, out=act)
+            ops.gemm_swiglu(h2, Wgu, out=act, gate_up_out=gu)          # the backward needs the projection as well
             # MLP backward
             self._wgrad(dx, act, pre + "mlp.down_proj.weight", acc)
             dact = self._dgrad(dx, Wd, out=act)                             # act no longer needed: reuse its storage

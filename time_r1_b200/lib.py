@@ -28,6 +28,7 @@ _SIGNATURES: dict[str, list] = {
     "t1_launch_count": [i32],
     # gemm_tcgen05.cu
     "t1_gemm_bf16_tn": [vp, i64, vp, i64, vp, i64, i32, i32, i32, vp, i32, vp],
+    "t1_gemm_swiglu": [vp, i64, vp, i64, vp, vp, i64, vp, i64, i32, i32, i32, vp],
     # grpo.cu
     "t1_iou_reward": [i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp],
     "t1_group_advantage": [vp, i32, i32, i32, f32, vp, vp, vp, vp, vp],

@@ -98,6 +98,26 @@ F32 = torch.float32
 I32 = torch.int32
 
 
+def gemm_swiglu(a, w_gate_up, bias=None, out=None, gate_up_out=None):
+    """out[M, I] = silu(a @ Wg^T + bg) * (a @ Wu^T + bu) with w_gate_up = [Wg; Wu] ([2I, K]): gate_up projection + SwiGLU in
+    the GEMM epilogue (bit-identical to gemm followed by swiglu); gate_up_out [M, 2I] optionally keeps the projection."""
+    M, K = a.shape
+    I = w_gate_up.shape[0] // 2
+    assert a.stride(1) == 1 and w_gate_up.stride(1) == 1 and w_gate_up.shape[1] == K and I % 8 == 0
+    if out is None:
+        out = torch.empty((M, I), device=a.device, dtype=BF16)
+    assert out.shape == (M, I) and out.dtype == BF16 and out.stride(1) == 1
+    if gate_up_out is not None:
+        assert gate_up_out.shape == (M, 2 * I) and gate_up_out.dtype == BF16 and gate_up_out.stride(1) == 1
+    if bias is not None:
+        assert bias.dtype == BF16 and bias.numel() == 2 * I and bias.is_contiguous()
+    e0 = PROFILER.begin()
+    call("t1_gemm_swiglu", ptr(a), a.stride(0), ptr(w_gate_up), w_gate_up.stride(0), ptr(bias), ptr(out), out.stride(0),
+         ptr(gate_up_out), gate_up_out.stride(0) if gate_up_out is not None else 0, M, I, K, stream_ptr())
+    PROFILER.end("gemm_bf16_tn", 4.0 * M * I * K, 2.0 * (M * K + 2 * I * K) + 2.0 * M * I, e0)
+    return out
+
+
 def skinny_gemm(x, w, out=None, bias=None, accumulate=False, out_dtype=BF16):
     """out[M<=64, N] (+)= x[M,K] @ w[N,K]^T (+bias): weight-streaming decode GEMM."""
     M, K = x.shape
