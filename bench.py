@@ -442,6 +442,8 @@ def run_ours(args):
         "clocks": clocks,
         "e2e": {"value": round(e2e_value, 4), "unit": UNIT, "h2d_bytes_per_step": int(NG * (frames_host.numel() + ids.size * 4)), "input": "uint8 frames [2*slots, 3, 448, 448] from pinned host memory -> t1_video_patchify on the device", "d2h_bytes_per_step": int(NG * (G * C * 4 + 4) + 4)},
         "gpu_launches": launches,
+        "hbm_gb": {"max_allocated": round(torch.cuda.max_memory_allocated(dev) / 1e9, 1), "max_reserved": round(torch.cuda.max_memory_reserved(dev) / 1e9, 1),
+                   "total": round(torch.cuda.get_device_properties(dev).total_memory / 1e9, 1)},
         "roofline": roofline,
         "roofline_decode": dec,
         "attn": attn,

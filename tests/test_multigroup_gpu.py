@@ -95,3 +95,26 @@ def test_vit_prefetch_on_side_stream_changes_nothing():
         assert torch.equal(a, b)
     # the gradient norm goes through fp32 atomics (norm-weight gradients): equal up to summation order
     assert abs(outs[0][3].item() - outs[1][3].item()) <= 1e-3 * outs[0][3].item()
+
+
+def test_saved_gate_up_gives_the_same_gradients_as_recompute():
+    """RunConfig.save_gate_up keeps the gate_up projection of every layer from the forward passes (prefill rows from the
+    rollout, completion rows from the scoring pass) so the backward skips that GEMM: same log-probs, same gradients."""
+    import dataclasses
+
+    from test_engine_gpu import build
+    from time_r1_b200 import engine
+
+    res = []
+    for save in (False, True):
+        O, cfg, ocfg, w_or, eng, prompt, pix, ids, grid = build(beta=0.04)
+        eng.save_gate_up = save
+        rewards = np.random.default_rng(0).random((4, 2)).astype(np.float32)
+        out = eng.grpo_multi_step([prompt], [lambda c: rewards], seed=3)[0]
+        torch.cuda.synchronize()
+        res.append((out["completion_ids"].clone(), out["logp"].clone(), eng.grads.buf.clone()))
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+    a, b = res[0][2].float(), res[1][2].float()
+    # bf16 gradient buffer: the two routes may differ by an ulp on a few elements (fp32 atomics in the norm backward feed dx)
+    assert (a - b).abs().max().item() <= 1e-2 * a.abs().max().item(), ((a - b).abs().max().item(), a.abs().max().item())
+    assert torch.nn.functional.cosine_similarity(a, b, dim=0).item() > 0.9999

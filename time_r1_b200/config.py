@@ -158,6 +158,7 @@ class RunConfig:
     ref_quirk_mrope: bool = True   # scoring pass omits second_per_grid_ts (timer1_trainer.py:601-607)
     seed: int = 42
     logit_chunk_rows: int = 2048
+    save_gate_up: object = "auto"  # True / False / "auto" (when HBM allows): keep gate_up projections for the backward
     reuse_prefill: bool = True     # policy scoring reuses the rollout's prefill (same weights) for the prompt rows
     # decode step: "stream" = tcgen05 stream-K weight streaming + grouped attention launches chained with programmatic
     # dependent launch; "legacy" = HMMA skinny GEMM + per-group attention on forked graph branches

@@ -66,6 +66,7 @@ class ScoreState:
     lse: torch.Tensor
     x_vit: torch.Tensor
     plan: indexing.VisionPlan
+    gu: list | None = None      # per-layer gate_up projection [Tp, 2I] kept from the forward passes (RunConfig.save_gate_up)
 
 
 class Engine:
@@ -100,6 +101,17 @@ class Engine:
         self._decode_cache: dict = {}
         self.metrics_launches = 0
         self.replay_hook = None
+        # keep the gate_up projection [Tp, 2I] of every layer from the forward passes (12.5 GB per prompt-group at cfg2) when
+        # HBM allows: the backward's recompute then skips its largest GEMM.  "auto" decides per step from the free memory.
+        self.save_gate_up = getattr(run, "save_gate_up", "auto")
+
+    def _may_save_gate_up(self, n_groups: int, Tp: int) -> bool:
+        if self.save_gate_up != "auto":
+            return bool(self.save_gate_up)
+        need = 2.0 * n_groups * self.cfg.num_hidden_layers * Tp * 2 * self.cfg.intermediate_size
+        free, _ = torch.cuda.mem_get_info(self.dev)
+        avail = free + torch.cuda.memory_reserved(self.dev) - torch.cuda.memory_allocated(self.dev)
+        return avail - need > 14e9          # head-room for the backward's transients and the logits chunks
 
     # ------------------------------------------------------------------------------------------
     # parameter access
@@ -236,7 +248,7 @@ class Engine:
         fn = ops.attn_fwd_tc if hd == 128 else ops.attn_fwd
         return fn(q, k, v, lo, hi, shared, Hq, Hkv, hd, scale, out=out, lse=lse, need_lse=need_lse)
 
-    def llm_forward(self, x0, cos, sin, lo, hi, shared, wset="policy", ckpt=None, kv_out=None):
+    def llm_forward(self, x0, cos, sin, lo, hi, shared, wset="policy", ckpt=None, kv_out=None, gu_out=None):
         """x0 [T, D] (consumed). Returns final-norm hidden states [T, D]. ckpt: list of L+1 [T, D] buffers receiving
         the residual stream at each layer input (+ final); kv_out: per-layer (K, V) caches receiving rows [0, T)."""
         cfg = self.cfg
@@ -248,7 +260,6 @@ class Engine:
         qkv = torch.empty((T, cfg.qkv_dim), device=self.dev, dtype=BF16)
         attn = torch.empty((T, qd), device=self.dev, dtype=BF16)
         o = torch.empty((T, D), device=self.dev, dtype=BF16)
-        gu = torch.empty((T, 2 * I), device=self.dev, dtype=BF16)
         act = torch.empty((T, I), device=self.dev, dtype=BF16)
         down = torch.empty((T, D), device=self.dev, dtype=BF16)
         xm = torch.empty((T, D), device=self.dev, dtype=BF16) if ckpt is not None else None
@@ -282,7 +293,8 @@ class Engine:
                 ops.rmsnorm(x, self.p(pre + "post_attention_layernorm.weight", wset), eps, delta=o, out=h, x_out=xm)
             else:
                 ops.rmsnorm(x, self.p(pre + "post_attention_layernorm.weight", wset), eps, delta=o, out=h)
-            ops.gemm_swiglu(h, self.p(pre + "mlp.gate_up.weight", wset), out=act)             # SwiGLU in the GEMM epilogue
+            ops.gemm_swiglu(h, self.p(pre + "mlp.gate_up.weight", wset), out=act,             # SwiGLU in the GEMM epilogue
+                            gate_up_out=gu_out[l] if gu_out is not None else None)
             ops.gemm(act, self.p(pre + "mlp.down_proj.weight", wset), out=down)
         hN = torch.empty((T, D), device=self.dev, dtype=BF16)
         if ckpt is not None:
@@ -293,7 +305,7 @@ class Engine:
             ops.rmsnorm(x, self.p("model.norm.weight", wset), eps, delta=down, out=hN)
         return hN
 
-    def llm_forward_suffix(self, ckpt_full, P, cos, sin, lo, hi, kv_prefix):
+    def llm_forward_suffix(self, ckpt_full, P, cos, sin, lo, hi, kv_prefix, gu_out=None):
         """Policy scoring of the completion rows only: rows [P, Tp) of the packed layout are computed, the prompt
         rows' K/V (same weights, same positions) come from the rollout's prefill cache and their layer inputs are
         already in ckpt_full[l][:P].  Fills ckpt_full[l][P:] and returns the final-norm hidden states of rows
@@ -310,7 +322,6 @@ class Engine:
         qkv = torch.empty((Tp, cfg.qkv_dim), device=dev, dtype=BF16)      # prompt rows: only the K/V columns are filled
         attn = torch.empty((Tc, qd), device=dev, dtype=BF16)
         o = torch.empty((Tc, D), device=dev, dtype=BF16)
-        gu = torch.empty((Tc, 2 * I), device=dev, dtype=BF16)
         act = torch.empty((Tc, I), device=dev, dtype=BF16)
         down = torch.empty((Tc, D), device=dev, dtype=BF16)
         xm = torch.empty((Tc, D), device=dev, dtype=BF16)
@@ -331,7 +342,7 @@ class Engine:
                             need_lse=False, q_row0=P)
             ops.gemm(attn, self.p(pre + "self_attn.o_proj.weight"), out=o)
             ops.rmsnorm(x, self.p(pre + "post_attention_layernorm.weight"), eps, delta=o, out=h, x_out=xm)
-            ops.gemm_swiglu(h, self.p(pre + "mlp.gate_up.weight"), out=act)
+            ops.gemm_swiglu(h, self.p(pre + "mlp.gate_up.weight"), out=act, gate_up_out=gu_out[l] if gu_out is not None else None)
             ops.gemm(act, self.p(pre + "mlp.down_proj.weight"), out=down)
         hN = torch.empty((Tc, D), device=dev, dtype=BF16)
         ops.rmsnorm(xm, self.p("model.norm.weight"), eps, delta=down, out=hN, x_out=ckpt_full[L][P:])
@@ -539,6 +550,7 @@ class Engine:
         st["finished"].zero_()
         st["out_ids"].fill_(cfg.pad_token_id)
         st["seed_dev"].fill_(int(seed))
+        save_gu = keep_prefill and self._may_save_gate_up(len(prompts), max(indexing.packed_rows(P_, G, C)[0] for P_ in Ps))
         for gi, (prompt, emb, grp) in enumerate(zip(prompts, vision_embeds, st["groups"])):
             ids = np.asarray(prompt.input_ids)
             P = grp["P"]
@@ -557,13 +569,17 @@ class Engine:
                 L = cfg.num_hidden_layers
                 ckpt_full = [torch.empty((Tp, cfg.hidden_size), device=self.dev, dtype=BF16) for _ in range(L + 1)]
                 ckpt = [c[:P] for c in ckpt_full]
+                if save_gu:                # the backward then skips the gate_up GEMM of its recompute (74% of its FLOPs)
+                    gu_full = [torch.empty((Tp, 2 * cfg.intermediate_size), device=self.dev, dtype=BF16) for _ in range(L)]
                 x0 = ops.gather_rows(self.p("model.embed_tokens.weight"), ids_dev, out=ckpt[0])
                 ops.scatter_rows(emb, vis_rows, x0)
             else:
                 x0 = self._embed(ids_dev, emb, vis_rows)
-            hN = self.llm_forward(x0, cos, sin, lo, hi, 0, ckpt=ckpt, kv_out=kv_prefix)
+            gu_full = gu_full if (keep_prefill and save_gu) else None
+            hN = self.llm_forward(x0, cos, sin, lo, hi, 0, ckpt=ckpt, kv_out=kv_prefix,
+                                  gu_out=[g[:P] for g in gu_full] if gu_full is not None else None)
             if keep_prefill:
-                grp["prefill"] = dict(ckpt_full=ckpt_full, h_last=hN[P - 1:P].clone(), kv_prefix=kv_prefix,
+                grp["prefill"] = dict(ckpt_full=ckpt_full, h_last=hN[P - 1:P].clone(), kv_prefix=kv_prefix, gu_full=gu_full,
                                       spg=None if prompt.second_per_grid_ts is None else list(prompt.second_per_grid_ts))
             logits0 = ops.skinny_gemm(hN[P - 1:P], self.lm_head(), out_dtype=F32)           # [1, V]
             # decode-position tables: completion token c sits at text position P + c + rope_delta on all three axes
@@ -675,21 +691,28 @@ class Engine:
             ckpt = prefill["ckpt_full"]
             assert ckpt[0].shape[0] == si["Tp"]
             ops.gather_rows(self.p("model.embed_tokens.weight"), si["ids_packed"][P:], out=ckpt[0][P:])
-            hN_c = self.llm_forward_suffix(ckpt, P, cos, sin, si["lo"], si["hi"], prefill["kv_prefix"])
+            gu_full = prefill.get("gu_full")
+            hN_c = self.llm_forward_suffix(ckpt, P, cos, sin, si["lo"], si["hi"], prefill["kv_prefix"],
+                                           gu_out=[g[P:] for g in gu_full] if gu_full is not None else None)
             hN = torch.empty((si["Tp"], self.cfg.hidden_size), device=self.dev, dtype=BF16)
             hN[P:] = hN_c
             hN[P - 1:P] = prefill["h_last"]
         else:
             x0 = self._embed(si["ids_packed"], vision_embeds, si["vision_rows"])
             ckpt = [None] * (self.cfg.num_hidden_layers + 1) if save else None
-            hN = self.llm_forward(x0, cos, sin, si["lo"], si["hi"], P, wset=wset, ckpt=ckpt)
+            gu_full = None
+            if save and self._may_save_gate_up(1, si["Tp"]):
+                gu_full = [torch.empty((si["Tp"], 2 * self.cfg.intermediate_size), device=self.dev, dtype=BF16)
+                           for _ in range(self.cfg.num_hidden_layers)]
+            hN = self.llm_forward(x0, cos, sin, si["lo"], si["hi"], P, wset=wset, ckpt=ckpt, gu_out=gu_full)
         hsel = ops.gather_rows(hN, si["logit_rows"])
         lp, ent, lse = self._head_forward(hsel, si["targets"], wset)
         state = None
         if save:
             state = ScoreState(P=si["P"], G=G, C=C, Tp=si["Tp"], ckpt=ckpt, cos=cos, sin=sin, lo=si["lo"], hi=si["hi"],
                                ids_packed=si["ids_packed"], text_scatter_idx=si["text_idx"], vision_rows=si["vision_rows"],
-                               logit_rows=si["logit_rows"], targets=si["targets"], hsel=hsel, lse=lse, x_vit=x_vit, plan=plan)
+                               logit_rows=si["logit_rows"], targets=si["targets"], hsel=hsel, lse=lse, x_vit=x_vit, plan=plan,
+                               gu=gu_full)
         return lp[:R].view(G, C), ent[:R].view(G, C), state
 
     # ------------------------------------------------------------------------------------------
@@ -756,7 +779,7 @@ class Engine:
         o = torch.empty((T, D), device=dev, dtype=BF16)
         xm = torch.empty((T, D), device=dev, dtype=BF16)
         h2 = torch.empty((T, D), device=dev, dtype=BF16)
-        gu = torch.empty((T, 2 * I), device=dev, dtype=BF16)
+        gu = torch.empty((T, 2 * I), device=dev, dtype=BF16) if st.gu is None else None
         act = torch.empty((T, I), device=dev, dtype=BF16)
         dqkv = torch.empty((T, cfg.qkv_dim), device=dev, dtype=BF16)
         lse2 = torch.empty((Hq, T), device=dev, dtype=F32)
@@ -775,7 +798,12 @@ class Engine:
             self._attn(q, k, v, st.lo, st.hi, st.P, Hq, Hkv, hd, scale, out=attn, lse=lse2)
             ops.gemm(attn, Wo, out=o)
             ops.rmsnorm(x_in, self.p(pre + "post_attention_layernorm.weight"), eps, delta=o, out=h2, x_out=xm)
-            ops.gemm_swiglu(h2, Wgu, out=act, gate_up_out=gu)          # the backward needs the projection as well
+            if st.gu is not None:            # projection kept from the forward pass: only the activation is redone
+                gu = st.gu[l]
+                st.gu[l] = None
+                ops.swiglu(gu, out=act)
+            else:
+                ops.gemm_swiglu(h2, Wgu, out=act, gate_up_out=gu)      # the backward needs the projection as well
             # MLP backward
             self._wgrad(dx, act, pre + "mlp.down_proj.weight", acc)
             dact = self._dgrad(dx, Wd, out=act)                             # act no longer needed: reuse its storage
