@@ -114,8 +114,8 @@ int t1_attn_fwd(const void* Q, long long ldq, const void* K, long long ldk, cons
  * rows [q_row0, T) are processed; Q and O point at row q_row0 (lets policy scoring reuse the prompt K/V of the
  * rollout's prefill instead of re-scoring the prompt). */
 int t1_attn_fwd_tc(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv, void* O,
-                   long long ldo, float* LSE2, const int* row_lo, const int* row_hi, int shared_len, int T, int Tk,
-                   int Hq, int Hkv, int head_dim, float scale, int q_row0, cudaStream_t stream);
+                   long long ldo, float* LSE2, long long lse_ld, const int* row_lo, const int* row_hi, int shared_len, int T,
+                   int Tk, int Hq, int Hkv, int head_dim, float scale, int q_row0, cudaStream_t stream);
 /* Backward of the above (autograd through flash-attn in the reference).  Workspaces: delta_ws [Hq*T] fp32,
  * summ_ws [4*ceil(T/64)] int32.  head_dim in {64, 128}. */
 int t1_attn_bwd(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv, const void* O,

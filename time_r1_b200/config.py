@@ -158,7 +158,9 @@ class RunConfig:
     ref_quirk_mrope: bool = True   # scoring pass omits second_per_grid_ts (timer1_trainer.py:601-607)
     seed: int = 42
     logit_chunk_rows: int = 2048
-    save_gate_up: object = "auto"  # True / False / "auto" (when HBM allows): keep gate_up projections for the backward
+    # what the forward passes keep for the backward besides the layer inputs: 0 / False = nothing (recompute all),
+    # 1 = gate_up projections, 2 / True = + q/k/v, attention output, LSE; "auto" = as much as the free HBM allows
+    save_gate_up: object = "auto"
     reuse_prefill: bool = True     # policy scoring reuses the rollout's prefill (same weights) for the prompt rows
     # decode step: "stream" = tcgen05 stream-K weight streaming + grouped attention launches chained with programmatic
     # dependent launch; "legacy" = HMMA skinny GEMM + per-group attention on forked graph branches

@@ -63,7 +63,7 @@ struct Range {
 
 __global__ void __launch_bounds__(FA_TC_THREADS, 1)   // 576 threads: 96 registers is the most that still launches
 fa_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
-                 const __grid_constant__ CUtensorMap tm_v, bf16* __restrict__ O, long long ldo, float* __restrict__ LSE2,
+                 const __grid_constant__ CUtensorMap tm_v, bf16* __restrict__ O, long long ldo, float* __restrict__ LSE2, long long lse_ld,
                  const int* __restrict__ row_lo, const int* __restrict__ row_hi, int shared_len, int T, int q_row0,
                  int group, float scale_log2, uint32_t v_lbo, uint32_t v_sbo) {
   extern __shared__ uint8_t smem_raw[];
@@ -300,7 +300,7 @@ fa_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       tc_fence_after();
     }
     const float inv = l > 0.f ? 1.f / l : 0.f;
-    if (valid && LSE2 && part == 0) LSE2[(long long)h * T + my_row] = l > 0.f ? m_ref + log2f(l) : -INFINITY;
+    if (valid && LSE2 && part == 0) LSE2[(long long)h * lse_ld + my_row] = l > 0.f ? m_ref + log2f(l) : -INFINITY;
 #pragma unroll 1
     for (int c = 0; c < NCH; ++c) {
       uint32_t ov[32];
@@ -336,11 +336,11 @@ fa_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 }  // namespace
 
 // Same contract as t1_attn_fwd, head_dim == 128 only; additionally only query rows [q_row0, T) are processed and Q / O
-// point at row q_row0 (row_lo / row_hi / LSE2 / K / V keep absolute packed-row indexing); Q/K/V token strides must be multiples of 8 and the head
+// point at row q_row0 (row_lo / row_hi / LSE2 / K / V keep absolute packed-row indexing; LSE2 is [Hq, lse_ld], lse_ld <= 0 -> T); Q/K/V token strides must be multiples of 8 and the head
 // column offsets multiples of 64 (true for the fused qkv layout).
 extern "C" int t1_attn_fwd_tc(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv,
-                              void* O, long long ldo, float* LSE2, const int* row_lo, const int* row_hi, int shared_len,
-                              int T, int Tk, int Hq, int Hkv, int head_dim, float scale, int q_row0,
+                              void* O, long long ldo, float* LSE2, long long lse_ld, const int* row_lo, const int* row_hi,
+                              int shared_len, int T, int Tk, int Hq, int Hkv, int head_dim, float scale, int q_row0,
                               cudaStream_t stream) {
   if (T - q_row0 <= 0) return T1_OK;
   T1_CHECK_ARG(q_row0 >= 0, "t1_attn_fwd_tc: q_row0 must be >= 0");
@@ -369,7 +369,7 @@ extern "C" int t1_attn_fwd_tc(const void* Q, long long ldq, const void* K, long 
     set = true;
   }
   dim3 grid((T - q_row0 + TQ - 1) / TQ, Hq);
-  fa_fwd_tc_kernel<<<grid, FA_TC_THREADS, FA_TC_SMEM, stream>>>(tq, tk, tv, (bf16*)O, ldo, LSE2, row_lo, row_hi, shared_len,
+  fa_fwd_tc_kernel<<<grid, FA_TC_THREADS, FA_TC_SMEM, stream>>>(tq, tk, tv, (bf16*)O, ldo, LSE2, lse_ld > 0 ? lse_ld : T, row_lo, row_hi, shared_len,
                                                                T, q_row0, Hq / Hkv, scale * 1.4426950408889634f, lbo, sbo);
   T1_CUDA_LAUNCH_CHECK("t1_attn_fwd_tc");
   return T1_OK;

@@ -67,6 +67,9 @@ class ScoreState:
     x_vit: torch.Tensor
     plan: indexing.VisionPlan
     gu: list | None = None      # per-layer gate_up projection [Tp, 2I] kept from the forward passes (RunConfig.save_gate_up)
+    k_qkv: list | None = None   # per-layer post-rope q, k, v [Tp, qkv_dim], attention output [Tp, Hq*hd] and LSE [Hq, Tp]
+    k_attn: list | None = None  #   kept from the forward passes: the backward then also skips the qkv GEMM, rope and the
+    k_lse: list | None = None   #   attention forward of its recompute
 
 
 class Engine:
@@ -105,13 +108,41 @@ class Engine:
         # HBM allows: the backward's recompute then skips its largest GEMM.  "auto" decides per step from the free memory.
         self.save_gate_up = getattr(run, "save_gate_up", "auto")
 
-    def _may_save_gate_up(self, n_groups: int, Tp: int) -> bool:
+    def _save_level(self, n_groups: int, Tp: int) -> int:
+        """How much of the forward passes to keep for the backward: 0 = layer inputs only (recompute everything),
+        1 = + gate_up projections, 2 = + q/k/v, attention output and LSE.  "auto" decides from the free HBM."""
+        cfg = self.cfg
+        top = 2 if cfg.head_dim == 128 else 1      # the kept LSE layout needs the tcgen05 attention forward
         if self.save_gate_up != "auto":
-            return bool(self.save_gate_up)
-        need = 2.0 * n_groups * self.cfg.num_hidden_layers * Tp * 2 * self.cfg.intermediate_size
+            return min(top, 2 if self.save_gate_up is True else int(self.save_gate_up))
+        L = cfg.num_hidden_layers
+        need_gu = 2.0 * n_groups * L * Tp * 2 * cfg.intermediate_size
+        need_at = 2.0 * n_groups * L * Tp * (cfg.qkv_dim + cfg.num_attention_heads * cfg.head_dim)
         free, _ = torch.cuda.mem_get_info(self.dev)
         avail = free + torch.cuda.memory_reserved(self.dev) - torch.cuda.memory_allocated(self.dev)
-        return avail - need > 14e9          # head-room for the backward's transients and the logits chunks
+        margin = 14e9                        # head-room for the backward's transients and the logits chunks
+        if top == 2 and avail - need_gu - need_at > margin:
+            return 2
+        return 1 if avail - need_gu > margin else 0
+
+    def _alloc_keep(self, level: int, Tp: int):
+        cfg = self.cfg
+        L, d = cfg.num_hidden_layers, self.dev
+        keep = {}
+        if level >= 1:
+            keep["gu"] = [torch.empty((Tp, 2 * cfg.intermediate_size), device=d, dtype=BF16) for _ in range(L)]
+        if level >= 2:
+            keep["qkv"] = [torch.empty((Tp, cfg.qkv_dim), device=d, dtype=BF16) for _ in range(L)]
+            keep["attn"] = [torch.empty((Tp, cfg.num_attention_heads * cfg.head_dim), device=d, dtype=BF16) for _ in range(L)]
+            keep["lse"] = [torch.empty((cfg.num_attention_heads, Tp), device=d, dtype=F32) for _ in range(L)]
+        return keep or None
+
+    @staticmethod
+    def _keep_rows(keep, lo, hi):
+        """Row window [lo, hi) of every kept per-layer buffer (LSE keeps its absolute [Hq, Tp] layout)."""
+        if keep is None:
+            return None
+        return {k: (v if k == "lse" else [t[lo:hi] for t in v]) for k, v in keep.items()}
 
     # ------------------------------------------------------------------------------------------
     # parameter access
@@ -248,7 +279,7 @@ class Engine:
         fn = ops.attn_fwd_tc if hd == 128 else ops.attn_fwd
         return fn(q, k, v, lo, hi, shared, Hq, Hkv, hd, scale, out=out, lse=lse, need_lse=need_lse)
 
-    def llm_forward(self, x0, cos, sin, lo, hi, shared, wset="policy", ckpt=None, kv_out=None, gu_out=None):
+    def llm_forward(self, x0, cos, sin, lo, hi, shared, wset="policy", ckpt=None, kv_out=None, keep=None):
         """x0 [T, D] (consumed). Returns final-norm hidden states [T, D]. ckpt: list of L+1 [T, D] buffers receiving
         the residual stream at each layer input (+ final); kv_out: per-layer (K, V) caches receiving rows [0, T)."""
         cfg = self.cfg
@@ -257,8 +288,10 @@ class Engine:
         qd, kd = Hq * hd, Hkv * hd
         eps, scale = cfg.rms_norm_eps, hd ** -0.5
         h = torch.empty((T, D), device=self.dev, dtype=BF16)
-        qkv = torch.empty((T, cfg.qkv_dim), device=self.dev, dtype=BF16)
-        attn = torch.empty((T, qd), device=self.dev, dtype=BF16)
+        keep_attn = keep is not None and "qkv" in keep
+        gu_out = keep["gu"] if keep is not None and "gu" in keep else None
+        qkv = None if keep_attn else torch.empty((T, cfg.qkv_dim), device=self.dev, dtype=BF16)
+        attn = None if keep_attn else torch.empty((T, qd), device=self.dev, dtype=BF16)
         o = torch.empty((T, D), device=self.dev, dtype=BF16)
         act = torch.empty((T, I), device=self.dev, dtype=BF16)
         down = torch.empty((T, D), device=self.dev, dtype=BF16)
@@ -278,6 +311,8 @@ class Engine:
                 x = ckpt[l]
             else:
                 ops.rmsnorm(x, self.p(pre + "input_layernorm.weight", wset), eps, delta=down, out=h)
+            if keep_attn:      # q, k, v (post-rope), the attention output and its LSE stay for the backward
+                qkv, attn = keep["qkv"][l], keep["attn"][l]
             ops.gemm(h, self.p(pre + "self_attn.qkv.weight", wset), out=qkv, bias=self.p(pre + "self_attn.qkv.bias", wset))
             if kv_out is not None:
                 Kc, Vc = kv_out[l]
@@ -287,7 +322,7 @@ class Engine:
             else:
                 ops.rope_apply(qkv, 0, Hq + Hkv, hd, cos, sin)
             self._attn(qkv[:, :qd], qkv[:, qd:qd + kd], qkv[:, qd + kd:], lo, hi, shared, Hq, Hkv, hd, scale, out=attn,
-                       need_lse=False)
+                       lse=keep["lse"][l] if keep_attn else None, need_lse=keep_attn)
             ops.gemm(attn, self.p(pre + "self_attn.o_proj.weight", wset), out=o)
             if ckpt is not None:
                 ops.rmsnorm(x, self.p(pre + "post_attention_layernorm.weight", wset), eps, delta=o, out=h, x_out=xm)
@@ -305,7 +340,7 @@ class Engine:
             ops.rmsnorm(x, self.p("model.norm.weight", wset), eps, delta=down, out=hN)
         return hN
 
-    def llm_forward_suffix(self, ckpt_full, P, cos, sin, lo, hi, kv_prefix, gu_out=None):
+    def llm_forward_suffix(self, ckpt_full, P, cos, sin, lo, hi, kv_prefix, keep=None):
         """Policy scoring of the completion rows only: rows [P, Tp) of the packed layout are computed, the prompt
         rows' K/V (same weights, same positions) come from the rollout's prefill cache and their layer inputs are
         already in ckpt_full[l][:P].  Fills ckpt_full[l][P:] and returns the final-norm hidden states of rows
@@ -319,8 +354,10 @@ class Engine:
         eps, scale = cfg.rms_norm_eps, hd ** -0.5
         dev = self.dev
         h = torch.empty((Tc, D), device=dev, dtype=BF16)
-        qkv = torch.empty((Tp, cfg.qkv_dim), device=dev, dtype=BF16)      # prompt rows: only the K/V columns are filled
-        attn = torch.empty((Tc, qd), device=dev, dtype=BF16)
+        keep_attn = keep is not None and "qkv" in keep     # full [Tp, ...] buffers whose prompt rows the prefill filled
+        gu_out = [g[P:] for g in keep["gu"]] if keep is not None and "gu" in keep else None
+        qkv = None if keep_attn else torch.empty((Tp, cfg.qkv_dim), device=dev, dtype=BF16)   # prompt rows: only K/V columns filled
+        attn = None if keep_attn else torch.empty((Tc, qd), device=dev, dtype=BF16)
         o = torch.empty((Tc, D), device=dev, dtype=BF16)
         act = torch.empty((Tc, I), device=dev, dtype=BF16)
         down = torch.empty((Tc, D), device=dev, dtype=BF16)
@@ -333,13 +370,16 @@ class Engine:
                 ops.rmsnorm(x, self.p(pre + "input_layernorm.weight"), eps, out=h)
             else:
                 ops.rmsnorm(xm, self.p(pre + "input_layernorm.weight"), eps, delta=down, out=h, x_out=x)
+            if keep_attn:
+                qkv, attn = keep["qkv"][l], keep["attn"][l][P:]
             ops.gemm(h, self.p(pre + "self_attn.qkv.weight"), out=qkv[P:], bias=self.p(pre + "self_attn.qkv.bias"))
             ops.rope_apply(qkv[P:], 0, Hq + Hkv, hd, cos_c, sin_c)
-            Kc, Vc = kv_prefix[l]
-            ops.copy_cols(Kc, qkv[:P, qd:qd + kd], kd)
-            ops.copy_cols(Vc, qkv[:P, qd + kd:], kd)
+            if not keep_attn:      # otherwise the prompt rows of qkv already hold the prefill's rotated k and v
+                Kc, Vc = kv_prefix[l]
+                ops.copy_cols(Kc, qkv[:P, qd:qd + kd], kd)
+                ops.copy_cols(Vc, qkv[:P, qd + kd:], kd)
             ops.attn_fwd_tc(qkv[P:, :qd], qkv[:, qd:qd + kd], qkv[:, qd + kd:], lo, hi, P, Hq, Hkv, hd, scale, out=attn,
-                            need_lse=False, q_row0=P)
+                            lse=keep["lse"][l] if keep_attn else None, need_lse=keep_attn, q_row0=P)
             ops.gemm(attn, self.p(pre + "self_attn.o_proj.weight"), out=o)
             ops.rmsnorm(x, self.p(pre + "post_attention_layernorm.weight"), eps, delta=o, out=h, x_out=xm)
             ops.gemm_swiglu(h, self.p(pre + "mlp.gate_up.weight"), out=act, gate_up_out=gu_out[l] if gu_out is not None else None)
@@ -550,7 +590,7 @@ class Engine:
         st["finished"].zero_()
         st["out_ids"].fill_(cfg.pad_token_id)
         st["seed_dev"].fill_(int(seed))
-        save_gu = keep_prefill and self._may_save_gate_up(len(prompts), max(indexing.packed_rows(P_, G, C)[0] for P_ in Ps))
+        save_level = self._save_level(len(prompts), max(indexing.packed_rows(P_, G, C)[0] for P_ in Ps)) if keep_prefill else 0
         for gi, (prompt, emb, grp) in enumerate(zip(prompts, vision_embeds, st["groups"])):
             ids = np.asarray(prompt.input_ids)
             P = grp["P"]
@@ -569,17 +609,15 @@ class Engine:
                 L = cfg.num_hidden_layers
                 ckpt_full = [torch.empty((Tp, cfg.hidden_size), device=self.dev, dtype=BF16) for _ in range(L + 1)]
                 ckpt = [c[:P] for c in ckpt_full]
-                if save_gu:                # the backward then skips the gate_up GEMM of its recompute (74% of its FLOPs)
-                    gu_full = [torch.empty((Tp, 2 * cfg.intermediate_size), device=self.dev, dtype=BF16) for _ in range(L)]
+                keep_full = self._alloc_keep(save_level, Tp)    # what the backward will not have to recompute
                 x0 = ops.gather_rows(self.p("model.embed_tokens.weight"), ids_dev, out=ckpt[0])
                 ops.scatter_rows(emb, vis_rows, x0)
             else:
                 x0 = self._embed(ids_dev, emb, vis_rows)
-            gu_full = gu_full if (keep_prefill and save_gu) else None
-            hN = self.llm_forward(x0, cos, sin, lo, hi, 0, ckpt=ckpt, kv_out=kv_prefix,
-                                  gu_out=[g[:P] for g in gu_full] if gu_full is not None else None)
+            keep_full = keep_full if keep_prefill else None
+            hN = self.llm_forward(x0, cos, sin, lo, hi, 0, ckpt=ckpt, kv_out=kv_prefix, keep=self._keep_rows(keep_full, 0, P))
             if keep_prefill:
-                grp["prefill"] = dict(ckpt_full=ckpt_full, h_last=hN[P - 1:P].clone(), kv_prefix=kv_prefix, gu_full=gu_full,
+                grp["prefill"] = dict(ckpt_full=ckpt_full, h_last=hN[P - 1:P].clone(), kv_prefix=kv_prefix, keep=keep_full,
                                       spg=None if prompt.second_per_grid_ts is None else list(prompt.second_per_grid_ts))
             logits0 = ops.skinny_gemm(hN[P - 1:P], self.lm_head(), out_dtype=F32)           # [1, V]
             # decode-position tables: completion token c sits at text position P + c + rope_delta on all three axes
@@ -691,20 +729,16 @@ class Engine:
             ckpt = prefill["ckpt_full"]
             assert ckpt[0].shape[0] == si["Tp"]
             ops.gather_rows(self.p("model.embed_tokens.weight"), si["ids_packed"][P:], out=ckpt[0][P:])
-            gu_full = prefill.get("gu_full")
-            hN_c = self.llm_forward_suffix(ckpt, P, cos, sin, si["lo"], si["hi"], prefill["kv_prefix"],
-                                           gu_out=[g[P:] for g in gu_full] if gu_full is not None else None)
+            keep_full = prefill.get("keep")
+            hN_c = self.llm_forward_suffix(ckpt, P, cos, sin, si["lo"], si["hi"], prefill["kv_prefix"], keep=keep_full)
             hN = torch.empty((si["Tp"], self.cfg.hidden_size), device=self.dev, dtype=BF16)
             hN[P:] = hN_c
             hN[P - 1:P] = prefill["h_last"]
         else:
             x0 = self._embed(si["ids_packed"], vision_embeds, si["vision_rows"])
             ckpt = [None] * (self.cfg.num_hidden_layers + 1) if save else None
-            gu_full = None
-            if save and self._may_save_gate_up(1, si["Tp"]):
-                gu_full = [torch.empty((si["Tp"], 2 * self.cfg.intermediate_size), device=self.dev, dtype=BF16)
-                           for _ in range(self.cfg.num_hidden_layers)]
-            hN = self.llm_forward(x0, cos, sin, si["lo"], si["hi"], P, wset=wset, ckpt=ckpt, gu_out=gu_full)
+            keep_full = self._alloc_keep(self._save_level(1, si["Tp"]), si["Tp"]) if save else None
+            hN = self.llm_forward(x0, cos, sin, si["lo"], si["hi"], P, wset=wset, ckpt=ckpt, keep=keep_full)
         hsel = ops.gather_rows(hN, si["logit_rows"])
         lp, ent, lse = self._head_forward(hsel, si["targets"], wset)
         state = None
@@ -712,7 +746,7 @@ class Engine:
             state = ScoreState(P=si["P"], G=G, C=C, Tp=si["Tp"], ckpt=ckpt, cos=cos, sin=sin, lo=si["lo"], hi=si["hi"],
                                ids_packed=si["ids_packed"], text_scatter_idx=si["text_idx"], vision_rows=si["vision_rows"],
                                logit_rows=si["logit_rows"], targets=si["targets"], hsel=hsel, lse=lse, x_vit=x_vit, plan=plan,
-                               gu=gu_full)
+                               **({("gu" if k == "gu" else "k_" + k): v for k, v in keep_full.items()} if keep_full else {}))
         return lp[:R].view(G, C), ent[:R].view(G, C), state
 
     # ------------------------------------------------------------------------------------------
@@ -790,12 +824,17 @@ class Engine:
             x_in = st.ckpt[l]
             Wqkv, Wo = self.p(pre + "self_attn.qkv.weight"), self.p(pre + "self_attn.o_proj.weight")
             Wgu, Wd = self.p(pre + "mlp.gate_up.weight"), self.p(pre + "mlp.down_proj.weight")
-            # recompute
+            # recompute (whatever the forward passes did not keep)
             ops.rmsnorm(x_in, self.p(pre + "input_layernorm.weight"), eps, out=h)
-            ops.gemm(h, Wqkv, out=qkv, bias=self.p(pre + "self_attn.qkv.bias"))
-            ops.rope_apply(qkv, 0, Hq + Hkv, hd, st.cos, st.sin)
-            q, k, v = qkv[:, :qd], qkv[:, qd:qd + kd], qkv[:, qd + kd:]
-            self._attn(q, k, v, st.lo, st.hi, st.P, Hq, Hkv, hd, scale, out=attn, lse=lse2)
+            if st.k_qkv is not None:
+                qkv, attn, lse2 = st.k_qkv[l], st.k_attn[l], st.k_lse[l]
+                st.k_qkv[l] = st.k_attn[l] = st.k_lse[l] = None
+                q, k, v = qkv[:, :qd], qkv[:, qd:qd + kd], qkv[:, qd + kd:]
+            else:
+                ops.gemm(h, Wqkv, out=qkv, bias=self.p(pre + "self_attn.qkv.bias"))
+                ops.rope_apply(qkv, 0, Hq + Hkv, hd, st.cos, st.sin)
+                q, k, v = qkv[:, :qd], qkv[:, qd:qd + kd], qkv[:, qd + kd:]
+                self._attn(q, k, v, st.lo, st.hi, st.P, Hq, Hkv, hd, scale, out=attn, lse=lse2)
             ops.gemm(attn, Wo, out=o)
             ops.rmsnorm(x_in, self.p(pre + "post_attention_layernorm.weight"), eps, delta=o, out=h2, x_out=xm)
             if st.gu is not None:            # projection kept from the forward pass: only the activation is redone

@@ -344,8 +344,8 @@ def attn_fwd_tc(q, k, v, row_lo, row_hi, shared_len, Hq, Hkv, head_dim, scale, o
     if lse is None and need_lse:
         lse = torch.empty((Hq, T), device=q.device, dtype=F32)
     call("t1_attn_fwd_tc", ptr(q), q.stride(0), ptr(k), k.stride(0), ptr(v), v.stride(0), ptr(out), out.stride(0),
-         ptr(lse), ptr(row_lo), ptr(row_hi), int(shared_len), T, Tk, Hq, Hkv, head_dim, float(scale), int(q_row0),
-         stream_ptr())
+         ptr(lse), lse.stride(0) if lse is not None else 0, ptr(row_lo), ptr(row_hi), int(shared_len), T, Tk, Hq, Hkv, head_dim,
+         float(scale), int(q_row0), stream_ptr())
     return out, lse
 
 
