@@ -296,6 +296,10 @@ def run_ours(args):
     lib.load()
     cfg = config.PRESETS[args.model]()
     run = config.RunConfig(num_generations=args.group_size, max_completion_length=args.completion_len)
+    if os.environ.get("T1_SIDE_CTAS"):
+        run.side_ctas = int(os.environ["T1_SIDE_CTAS"])
+    if os.environ.get("T1_DECODE_CTAS"):
+        run.decode_ctas = int(os.environ["T1_DECODE_CTAS"])
     G, C = run.num_generations, run.max_completion_length
     mw = weights.ModelWeights(cfg, dev, world_size=world)
     mw.init_random(seed=0)          # same weights on every rank (data parallel)

@@ -53,6 +53,9 @@ int t1_gemm_bf16_tn(const void* A, long long lda, const void* B, long long ldb, 
  * projection for the backward pass.  Bit-identical to t1_gemm_bf16_tn + t1_swiglu. */
 int t1_gemm_swiglu(const void* A, long long lda, const void* W, long long ldw, const void* bias, void* act, long long ld_act,
                    void* gate_up, long long ld_gate_up, int M, int I, int K, cudaStream_t stream);
+/* Cap on the persistent grid of subsequent t1_gemm_* launches (0 = one CTA per SM): a side stream that overlaps a
+ * bandwidth-bound phase (the decode) keeps to a few SMs. */
+void t1_gemm_max_ctas(int n);
 
 /* y[M<=64, N] (+)= x[M,K] * W[N,K]^T (+ bias bf16).  Weight-streaming decode GEMM (HBM-bound; thread-block-cluster
  * split-K).  Replaces the per-token linears inside HF generate (timer1_trainer.py:568-573).  N % 16, K % 32. */
@@ -74,6 +77,8 @@ int t1_stream_gemm(const void* x, long long ldx, const void* W, long long ldw, c
  * through an atomic counter, so faster SMs take more; the others stay static.  2: also split slabs into k-segments
  * (measured slower: per-item partial tiles). */
 void t1_stream_gemm_dynamic(int on);
+/* Cap on the number of CTAs of subsequent t1_stream_gemm* launches (0 = one per SM): leaves SMs to a concurrent stream. */
+void t1_stream_gemm_max_ctas(int n);
 /* y = x W^T (bf16); resid[M, N] += y in place; h_out = rmsnorm(resid, eps) * norm_w: the o / down projection of a decode
  * layer fused with the residual add and the NEXT RMSNorm (HF Q25:805-827): after a grid-wide arrive counter CTA b
  * normalises row b (every CTA of the launch is resident: grid <= SM count).

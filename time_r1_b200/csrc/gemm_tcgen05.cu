@@ -315,6 +315,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 
 }  // namespace
 
+static int g_gemm_max_ctas = 0;   // t1_gemm_max_ctas(): cap on the persistent grid (0 = one CTA per SM)
+extern "C" void t1_gemm_max_ctas(int n) { g_gemm_max_ctas = n > 0 ? n : 0; }
+
 static int gemm_impl(const void* A, long long lda, const void* B, long long ldb, void* D, long long ldd, int M, int N, int K,
                      const void* bias, int flags, void* D2, long long ldd2, cudaStream_t stream) {
   T1_CHECK_ARG(A && B && D, "t1_gemm_bf16_tn: null operand");
@@ -353,7 +356,8 @@ static int gemm_impl(const void* A, long long lda, const void* B, long long ldb,
   const int BNO = swiglu ? BN / 2 : BN;                    // output columns per tile
   const int num_n = (N + BNO - 1) / BNO;
   const int num_tiles = num_m * num_n;
-  const int grid = num_tiles < sms ? num_tiles : sms;
+  int grid = num_tiles < sms ? num_tiles : sms;
+  if (g_gemm_max_ctas > 0 && g_gemm_max_ctas < grid) grid = g_gemm_max_ctas;     // leave the other SMs to a concurrent stream
   EpiParams epi{D, bias, ldd, flags, swiglu ? D2 : nullptr, ldd2};
   // DRAM-traffic model for the raster order (L2 = 126 MB; measured with ncu on the gate_up wgrad, M=37888 N=3584 K=5888:
   // m-fastest re-read dY 14x = 6.3 GB per launch).  An operand that fits in ~48 MB of L2 is read once whatever the order;

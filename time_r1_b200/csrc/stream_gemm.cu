@@ -712,6 +712,7 @@ int env_int(const char* name, int dflt) {
 }
 unsigned long long* g_dbg = nullptr;   // device ring of 4-stamp records (t1_stream_gemm_debug)
 int g_dbg_slots = 0, g_dbg_next = 0;
+int g_max_ctas = 0;                      // t1_stream_gemm_max_ctas(): cap on the grid (0 = one CTA per SM)
 int g_dynamic = -1;                      // T1_STREAM_DYNAMIC (default 1): dynamically scheduled kernel
 int g_stages = -1, g_ctas_per_sm = -1;   // tuning knobs: T1_STREAM_STAGES / T1_STREAM_CTAS_PER_SM or t1_stream_gemm_tune()
 
@@ -773,6 +774,8 @@ extern "C" void t1_stream_gemm_debug(void* buf, int slots) {
 }
 
 // Ring depth (0 = default: ~108 KB per CTA) and CTAs per SM (1 or 2) of subsequent launches.
+extern "C" void t1_stream_gemm_max_ctas(int n) { g_max_ctas = n > 0 ? n : 0; }
+
 extern "C" void t1_stream_gemm_dynamic(int on) { g_dynamic = on < 0 ? 0 : on; }
 
 extern "C" void t1_stream_gemm_tune(int stages, int ctas_per_sm) {
@@ -817,6 +820,7 @@ static int stream_gemm_impl(const void* x, long long ldx, const void* W, long lo
   T1_CHECK_ARG(total < (1LL << 30), "t1_stream_gemm: problem too large");
   int max_ctas = t1_num_sms() * (env_ctas > 0 ? env_ctas : 1);
   if (max_ctas > 2 * t1_num_sms()) max_ctas = 2 * t1_num_sms();
+  if (g_max_ctas > 0 && g_max_ctas < max_ctas) max_ctas = g_max_ctas;     // leave SMs to a concurrent stream (experiments)
   const int per = (int)((total + max_ctas - 1) / max_ctas);
   const int grid = (int)((total + per - 1) / per);
   const long long need = SG_COUNTER_BYTES + (long long)grid * 2 * MP * SG_BM * 4;
@@ -883,7 +887,8 @@ static int stream_gemm_impl(const void* x, long long ldx, const void* W, long lo
     T1_CHECK_ARG(slabs * 4 <= SG_COUNTER_BYTES - 12, "t1_stream_gemm: N=%d exceeds the counter region", N);
     const long long need_dyn = SG_COUNTER_BYTES + (segs > 1 ? (long long)p.total_items * MP * SG_BM * 4 : 0);
     T1_CHECK_ARG(workspace_bytes >= need_dyn, "t1_stream_gemm: workspace too small (%lld < %lld)", workspace_bytes, need_dyn);
-    const int grid_dyn = p.total_items < t1_num_sms() ? p.total_items : t1_num_sms();
+    int grid_dyn = p.total_items < t1_num_sms() ? p.total_items : t1_num_sms();
+    if (g_max_ctas > 0 && g_max_ctas < grid_dyn) grid_dyn = g_max_ctas;
     if (MP == 16) rc = launch_stream_dyn<16>(tw, tx, p, grid_dyn, smem, stream);
     else if (MP == 32) rc = launch_stream_dyn<32>(tw, tx, p, grid_dyn, smem, stream);
     else rc = launch_stream_dyn<64>(tw, tx, p, grid_dyn, smem, stream);

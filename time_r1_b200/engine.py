@@ -257,6 +257,43 @@ class Engine:
                 delta.record_stream(main)
         return dict(results=res, event=ev, n=len(prompts))
 
+    def ref_prefill_async(self, prompt: Prompt, emb_ref: torch.Tensor, G: int, C: int):
+        """Prompt rows of the REFERENCE-model scoring pass (timer1_trainer.py:613-632) on a side stream.  They depend on the
+        prompt only, not on the sampled tokens, and they are tensor-bound while the decode is HBM-bound: the side stream's
+        GEMMs keep to RunConfig.side_ctas SMs and the decode (on a high-priority stream) to the others.  Returns the handle
+        score(..., wset="ref", prefill=handle) consumes: the reference K/V of the prompt rows and its last hidden state."""
+        cfg, run = self.cfg, self.run
+        ids = np.asarray(prompt.input_ids)
+        P = len(ids)
+        L, kd = cfg.num_hidden_layers, cfg.num_key_value_heads * cfg.head_dim
+        spg = None if run.ref_quirk_mrope else prompt.second_per_grid_ts
+        pos3, _ = indexing.mrope_positions(cfg, ids, prompt.grid_thw, spg)
+        if getattr(self, "_side_stream", None) is None:
+            self._side_stream = torch.cuda.Stream(device=self.dev)            # default (lowest) priority
+        main, side = torch.cuda.current_stream(), self._side_stream
+        side.wait_stream(main)                                                  # emb_ref is ready
+        lib = load_lib()
+        with torch.cuda.stream(side):
+            lib.t1_gemm_max_ctas(int(run.side_ctas))
+            try:
+                cos, sin = self._rope_tables(pos3)
+                vis_rows = self._i32(np.nonzero(ids == cfg.video_token_id)[0])
+                x0 = self._embed(self._i32(ids), emb_ref, vis_rows, "ref")
+                kv = [(torch.empty((P, kd), device=self.dev, dtype=BF16), torch.empty((P, kd), device=self.dev, dtype=BF16)) for _ in range(L)]
+                lo = torch.zeros(P, device=self.dev, dtype=I32)
+                hi = torch.arange(1, P + 1, device=self.dev, dtype=I32)
+                hN = self.llm_forward(x0, cos, sin, lo, hi, 0, wset="ref", kv_out=kv)
+                h_last = hN[P - 1:P].clone()
+            finally:
+                lib.t1_gemm_max_ctas(0)
+            ev = torch.cuda.Event()
+            ev.record(side)
+        for k_, v_ in kv:
+            k_.record_stream(main)
+            v_.record_stream(main)
+        h_last.record_stream(main)
+        return dict(kv_prefix=kv, h_last=h_last, event=ev, P=P, ref=True)
+
     def vit_forward(self, prompt: Prompt, wset: str = "policy"):
         x, delta, plan = self.vit_blocks(prompt.pixel_values, prompt.grid_thw, frames=prompt.frames)
         emb = self.merger(x, delta, plan, wset)
@@ -268,8 +305,8 @@ class Engine:
     def _rope_tables(self, pos3: np.ndarray):
         return ops.rope_table(self._i32(pos3), self.axis_llm, self.inv_freq_llm)
 
-    def _embed(self, ids_dev: torch.Tensor, vision_embeds: torch.Tensor, vision_rows: torch.Tensor) -> torch.Tensor:
-        x = ops.gather_rows(self.p("model.embed_tokens.weight"), ids_dev)
+    def _embed(self, ids_dev: torch.Tensor, vision_embeds: torch.Tensor, vision_rows: torch.Tensor, wset: str = "policy") -> torch.Tensor:
+        x = ops.gather_rows(self.p("model.embed_tokens.weight", wset), ids_dev)
         ops.scatter_rows(vision_embeds, vision_rows, x)                     # masked_scatter (HF :1309-1315)
         return x
 
@@ -340,7 +377,7 @@ class Engine:
             ops.rmsnorm(x, self.p("model.norm.weight", wset), eps, delta=down, out=hN)
         return hN
 
-    def llm_forward_suffix(self, ckpt_full, P, cos, sin, lo, hi, kv_prefix, keep=None):
+    def llm_forward_suffix(self, ckpt_full, P, cos, sin, lo, hi, kv_prefix, keep=None, wset="policy"):
         """Policy scoring of the completion rows only: rows [P, Tp) of the packed layout are computed, the prompt
         rows' K/V (same weights, same positions) come from the rollout's prefill cache and their layer inputs are
         already in ckpt_full[l][:P].  Fills ckpt_full[l][P:] and returns the final-norm hidden states of rows
@@ -367,12 +404,12 @@ class Engine:
             pre = f"model.layers.{l}."
             x = ckpt_full[l][P:]
             if l == 0:
-                ops.rmsnorm(x, self.p(pre + "input_layernorm.weight"), eps, out=h)
+                ops.rmsnorm(x, self.p(pre + "input_layernorm.weight", wset), eps, out=h)
             else:
-                ops.rmsnorm(xm, self.p(pre + "input_layernorm.weight"), eps, delta=down, out=h, x_out=x)
+                ops.rmsnorm(xm, self.p(pre + "input_layernorm.weight", wset), eps, delta=down, out=h, x_out=x)
             if keep_attn:
                 qkv, attn = keep["qkv"][l], keep["attn"][l][P:]
-            ops.gemm(h, self.p(pre + "self_attn.qkv.weight"), out=qkv[P:], bias=self.p(pre + "self_attn.qkv.bias"))
+            ops.gemm(h, self.p(pre + "self_attn.qkv.weight", wset), out=qkv[P:], bias=self.p(pre + "self_attn.qkv.bias", wset))
             ops.rope_apply(qkv[P:], 0, Hq + Hkv, hd, cos_c, sin_c)
             if not keep_attn:      # otherwise the prompt rows of qkv already hold the prefill's rotated k and v
                 Kc, Vc = kv_prefix[l]
@@ -380,12 +417,12 @@ class Engine:
                 ops.copy_cols(Vc, qkv[:P, qd + kd:], kd)
             ops.attn_fwd_tc(qkv[P:, :qd], qkv[:, qd:qd + kd], qkv[:, qd + kd:], lo, hi, P, Hq, Hkv, hd, scale, out=attn,
                             lse=keep["lse"][l] if keep_attn else None, need_lse=keep_attn, q_row0=P)
-            ops.gemm(attn, self.p(pre + "self_attn.o_proj.weight"), out=o)
-            ops.rmsnorm(x, self.p(pre + "post_attention_layernorm.weight"), eps, delta=o, out=h, x_out=xm)
-            ops.gemm_swiglu(h, self.p(pre + "mlp.gate_up.weight"), out=act, gate_up_out=gu_out[l] if gu_out is not None else None)
-            ops.gemm(act, self.p(pre + "mlp.down_proj.weight"), out=down)
+            ops.gemm(attn, self.p(pre + "self_attn.o_proj.weight", wset), out=o)
+            ops.rmsnorm(x, self.p(pre + "post_attention_layernorm.weight", wset), eps, delta=o, out=h, x_out=xm)
+            ops.gemm_swiglu(h, self.p(pre + "mlp.gate_up.weight", wset), out=act, gate_up_out=gu_out[l] if gu_out is not None else None)
+            ops.gemm(act, self.p(pre + "mlp.down_proj.weight", wset), out=down)
         hN = torch.empty((Tc, D), device=dev, dtype=BF16)
-        ops.rmsnorm(xm, self.p("model.norm.weight"), eps, delta=down, out=hN, x_out=ckpt_full[L][P:])
+        ops.rmsnorm(xm, self.p("model.norm.weight", wset), eps, delta=down, out=hN, x_out=ckpt_full[L][P:])
         return hN
 
     # ------------------------------------------------------------------------------------------
@@ -483,6 +520,7 @@ class Engine:
         ws, tab = st["gemm_ws"], st["group_table"]
         from .lib import load
         load().t1_set_pdl(1 if self.run.decode_pdl else 0)
+        load().t1_stream_gemm_max_ctas(int(st.get("decode_ctas", 0)))      # leave SMs to the overlapped reference prefill
         try:
             s = stream_ptr()
             ops.gather_rows(self.p("model.embed_tokens.weight"), st["next_ids"], out=x)
@@ -525,6 +563,7 @@ class Engine:
             call("t1_incr", ptr(st["step"]), 1, s)
         finally:
             load().t1_set_pdl(0)
+            load().t1_stream_gemm_max_ctas(0)
 
     def _decode_step(self, st, G: int, temperature: float, top_k: int):
         """One token for each of the B = n*G sequences (captured into a CUDA graph by rollout_multi()). The linears
@@ -579,13 +618,19 @@ class Engine:
 
     def rollout_multi(self, prompts: list, vision_embeds: list, G: int, C: int, temperature: float = 1.0,
                       top_k: int = 50, seed: int = 0, use_graph: bool = True, check_every: int = 32,
-                      keep_prefill: bool = False) -> list:
+                      keep_prefill: bool = False, shared_sms: bool = False, before_decode=None) -> list:
         """Rollout for several prompt-groups at once (the micro-batches of one optimizer step see the same weights,
         so their decode streams can share every weight read). Returns one [G, C] int32 tensor per group."""
         cfg = self.cfg
         Ps = tuple(len(np.asarray(p.input_ids)) for p in prompts)
         st = self._decode_state(Ps, G, C)
         B = st["B"]
+        # shared_sms: a side stream (the reference model's prompt prefill) runs during the decode: the weight-streaming
+        # GEMMs keep to decode_ctas SMs and the captured step is replayed on a HIGH-priority stream, so that at every kernel
+        # boundary the decode's CTAs are placed before the side stream's pending ones
+        want_ctas = int(self.run.decode_ctas) if (shared_sms and st["impl"] == "stream") else 0
+        if st.get("decode_ctas", 0) != want_ctas:
+            st["decode_ctas"], st["graph"] = want_ctas, None
         st["step"].zero_()
         st["finished"].zero_()
         st["out_ids"].fill_(cfg.pad_token_id)
@@ -630,6 +675,8 @@ class Engine:
             self._sample(st, logits0, 0, G, temperature, top_k, int(seed) + 7919 * (gi + 1), 0, 0, 0,
                          st["finished"][sl], st["out_ids"][sl], st["next_ids"][sl])
         n_steps = C - 1
+        if before_decode is not None:
+            before_decode()          # side-stream work that overlaps the decode loop is enqueued after the prompt prefills
         if n_steps > 0:
             gkey = (float(temperature), int(top_k))     # the seed lives in device memory: graphs are seed-independent
             if use_graph:
@@ -643,19 +690,26 @@ class Engine:
                     g = torch.cuda.CUDAGraph()
                     from .lib import load
                     before = load().t1_launch_count(0)
-                    with torch.cuda.graph(g):
+                    if getattr(self, "_hi_stream", None) is None:
+                        import os as _os
+                        self._hi_stream = torch.cuda.Stream(device=self.dev, priority=0 if _os.environ.get("T1_NO_HI_PRIO") else -1)
+                    with torch.cuda.graph(g, stream=self._hi_stream):      # kernel nodes inherit the capture stream's priority
                         self._decode_step(st, G, temperature, top_k)
                     st["launches_per_step"] = int(load().t1_launch_count(0) - before)
                     st["graph"], st["gkey"] = g, gkey
                     st["step"].zero_()
                     st["next_ids"].copy_(snap[0]); st["finished"].copy_(snap[1]); st["out_ids"].copy_(snap[2])
                 done = 0
+                main, hi = torch.cuda.current_stream(), self._hi_stream
                 while done < n_steps:
                     burst = min(check_every, n_steps - done)
-                    for i in range(burst):
-                        if self.replay_hook is not None:
-                            self.replay_hook(done + i, n_steps)     # profiling windows (bench.py --ncu-range)
-                        st["graph"].replay()
+                    hi.wait_stream(main)
+                    with torch.cuda.stream(hi):
+                        for i in range(burst):
+                            if self.replay_hook is not None:
+                                self.replay_hook(done + i, n_steps)     # profiling windows (bench.py --ncu-range)
+                            st["graph"].replay()
+                    main.wait_stream(hi)
                     self.metrics_launches += burst * st["launches_per_step"]
                     done += burst
                     if done < n_steps and bool(st["finished"].all().item()):
@@ -723,7 +777,20 @@ class Engine:
         G, C, R = si["G"], si["C"], si["R"]
         cos, sin = self._rope_tables(si["pos"])
         P = si["P"]
-        if prefill is not None:
+        if prefill is not None and prefill.get("ref"):
+            # reference model: the prompt rows were computed on the side stream while the rollout decoded
+            assert wset == "ref" and not save and prefill["P"] == P
+            torch.cuda.current_stream().wait_event(prefill["event"])
+            xbuf = torch.empty((si["Tp"], self.cfg.hidden_size), device=self.dev, dtype=BF16)
+            ckpt = [xbuf] * (self.cfg.num_hidden_layers + 1)          # no backward through the reference: one layer-input buffer
+            ops.gather_rows(self.p("model.embed_tokens.weight", "ref"), si["ids_packed"][P:], out=xbuf[P:])
+            hN_c = self.llm_forward_suffix(ckpt, P, cos, sin, si["lo"], si["hi"], prefill["kv_prefix"], wset="ref")
+            hN = torch.empty((si["Tp"], self.cfg.hidden_size), device=self.dev, dtype=BF16)
+            hN[P:] = hN_c
+            hN[P - 1:P] = prefill["h_last"]
+            ckpt = None
+            keep_full = None
+        elif prefill is not None:
             # policy == rollout weights: the prompt rows were already computed by the rollout's prefill
             assert wset == "policy" and save
             ckpt = prefill["ckpt_full"]
@@ -984,9 +1051,17 @@ class Engine:
             vit.append((emb, x_vit, plan))
         mark("vit")
         prefills = [None] * len(prompts)
+        ref_handles = [None] * len(prompts)
+        overlap_ref = (completion_overrides is None and run.beta != 0.0 and self.ref is not None and run.side_ctas > 0
+                       and cfg.head_dim == 128 and self._decode_impl() == "stream")
+        def launch_ref_prefills():
+            for gi, (prompt, (emb, x_vit, plan)) in enumerate(zip(prompts, vit)):
+                ref_handles[gi] = self.ref_prefill_async(prompt, self.merger(x_vit, None, plan, "ref"), G, C)
+
         if completion_overrides is None:
             reuse = run.reuse_prefill and cfg.head_dim == 128
-            comps = self.rollout_multi(prompts, [v[0] for v in vit], G, C, run.temperature, run.top_k, seed, keep_prefill=reuse)
+            comps = self.rollout_multi(prompts, [v[0] for v in vit], G, C, run.temperature, run.top_k, seed, keep_prefill=reuse,
+                                       shared_sms=overlap_ref, before_decode=launch_ref_prefills if overlap_ref else None)
             if reuse:
                 for gi, prompt in enumerate(prompts):
                     pf = self._last_decode_state["groups"][gi].pop("prefill", None)
@@ -1007,8 +1082,12 @@ class Engine:
             if run.beta != 0.0:
                 if self.ref is None:
                     raise RuntimeError("beta != 0 needs the reference parameter set (Engine(with_ref=True))")
-                emb_ref = self.merger(x_vit, None, plan, "ref")
-                ref_logp, _, _ = self.score(prompt, comp, emb_ref, "ref")
+                if ref_handles[gi] is not None:
+                    ref_logp, _, _ = self.score(prompt, comp, None, "ref", prefill=ref_handles[gi])
+                    ref_handles[gi] = None
+                else:
+                    emb_ref = self.merger(x_vit, None, plan, "ref")
+                    ref_logp, _, _ = self.score(prompt, comp, emb_ref, "ref")
             mark("score_ref")
             comp_host = comp.cpu().numpy().astype(np.int64)                 # D2H: completions for the host reward fns
             rpf = np.ascontiguousarray(reward_fn(comp_host), dtype=np.float32).reshape(G, -1)

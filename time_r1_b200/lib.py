@@ -68,7 +68,9 @@ _SIGNATURES: dict[str, list] = {
     # decode.cu
     "t1_skinny_gemm": [vp, i64, vp, i64, vp, vp, i64, i32, i32, i32, i32, i32, vp],
     "t1_stream_gemm": [vp, i64, vp, i64, vp, vp, i64, i32, i32, i32, i32, vp, i64, vp],
+    "t1_gemm_max_ctas": [i32],
     "t1_stream_gemm_dynamic": [i32],
+    "t1_stream_gemm_max_ctas": [i32],
     "t1_stream_gemm_resnorm": [vp, i64, vp, i64, vp, i64, i32, i32, i32, vp, vp, f32, vp, vp, i64, vp],
     "t1_stream_gemm_swiglu": [vp, i64, vp, i64, vp, vp, i64, i32, i32, i32, vp, i64, vp],
     "t1_stream_gemm_workspace_bytes": [i32],
@@ -89,7 +91,7 @@ _SIGNATURES: dict[str, list] = {
     "t1_adamw": [vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, vp, f32, f32, vp],
     "t1_bf16_to_f32": [vp, vp, i64, vp],
 }
-_RESTYPES = {"t1_last_error": C.c_char_p, "t1_launch_count": u64, "t1_count_launch": None, "t1_set_pdl": None, "t1_stream_gemm_tune": None, "t1_stream_gemm_dynamic": None, "t1_stream_gemm_debug": None,
+_RESTYPES = {"t1_last_error": C.c_char_p, "t1_launch_count": u64, "t1_count_launch": None, "t1_set_pdl": None, "t1_stream_gemm_tune": None, "t1_stream_gemm_dynamic": None, "t1_stream_gemm_max_ctas": None, "t1_gemm_max_ctas": None, "t1_stream_gemm_debug": None,
              "t1_stream_gemm_workspace_bytes": i64, "t1_sample_topk_workspace_bytes": i64,
              "t1_attn_bwd_tc_workspace_bytes": i64}
 

@@ -45,6 +45,9 @@ def main():
         embs.append((torch.randn(nv, cfg.hidden_size, device=dev) * 0.02).to(torch.bfloat16))
     variants = [("legacy", False, 0, 1), ("stream", False, 0, 1), ("stream", True, 0, 1), ("stream", True, 4, 1), ("stream", True, 10, 1),
                 ("stream", True, 5, 2), ("stream", True, 3, 2)]
+    if os.environ.get("T1_BENCH_MAX_CTAS"):
+        variants = [("stream", True, 0, 1)]
+        lib.load().t1_stream_gemm_max_ctas(int(os.environ["T1_BENCH_MAX_CTAS"]))
     for impl, pdl, stages, ctas in variants:
         run = config.RunConfig(num_generations=G, max_completion_length=C, beta=0.0, decode_impl=impl, decode_pdl=pdl)
         eng = engine.Engine.__new__(engine.Engine)      # decode only: skip the optimizer-state allocation
