@@ -435,10 +435,12 @@ fa_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   uint64_t* s_full = v_full + 2;             // 2
   uint64_t* dp_full = v_full + 4;            // 1
   uint64_t* dp_taken = v_full + 5;           // 1 (one arrival per element-wise warp)
-  uint64_t* ds_ready = v_full + 6;           // 1 (one arrival per element-wise warp)
-  uint64_t* dq_done = v_full + 7;            // 1
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(v_full + 8);
-  int* s_red = reinterpret_cast<int*>(v_full + 9);   // 4 ints
+  // ds_ready is double-buffered by tile parity: dP(it+1) is issued before ds_ready(it) completes, so a fast warp can
+  // arrive for tile it+1 while a slow one has not arrived for tile it
+  uint64_t* ds_ready = v_full + 6;           // 2 (one arrival per element-wise warp)
+  uint64_t* dq_done = v_full + 8;            // 1
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(v_full + 9);
+  int* s_red = reinterpret_cast<int*>(v_full + 10);   // 4 ints
 
   const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = (int)gridDim.x - 1 - (int)blockIdx.x;      // long rows (most visible keys) first
@@ -458,7 +460,8 @@ fa_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     mbar_init(&s_full[1], 1);
     mbar_init(dp_full, 1);
     mbar_init(dp_taken, 4 * NS);           // one arrival per element-wise warp
-    mbar_init(ds_ready, 4 * NS);
+    mbar_init(&ds_ready[0], 4 * NS);
+    mbar_init(&ds_ready[1], 4 * NS);
     mbar_init(dq_done, 1);
     mbar_fence_init();
   }
@@ -558,7 +561,7 @@ fa_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         mbar_wait(dp_taken, it & 1);             // every thread holds dP(it) in registers: the dP columns are free
         tc_fence_after();
         if (it + 1 < n) issue_dp(it + 1);
-        mbar_wait(ds_ready, it & 1);
+        mbar_wait(&ds_ready[it & 1], (it >> 1) & 1);
         tc_fence_after();
         const uint32_t tS = tmem_base + T_S0 + (it & 1) * 128;
 #pragma unroll
@@ -624,7 +627,7 @@ fa_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(ds_ready);
+      if (lane == 0) mbar_arrive(&ds_ready[it & 1]);
     }
     if (n > 0) {
       mbar_wait(dq_done, 0);

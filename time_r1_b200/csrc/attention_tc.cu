@@ -78,11 +78,13 @@ fa_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   uint64_t* v_full = bars + 5;              // 2
   uint64_t* v_empty = bars + 7;             // 2  (released when O += P V retires)
   uint64_t* s_full = bars + 9;              // 2
-  uint64_t* p_full = bars + 11;             // 1 (one arrival per softmax warp)
-  uint64_t* pv_done = bars + 12;            // 2 (PV(it) arrives on pv_done[it & 1])
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 14);
-  int* s_red = reinterpret_cast<int*>(bars + 15);  // 4 ints
-  float* s_xch = reinterpret_cast<float*>(bars + 17);   // [3*NS][128] floats: per-row partial max (double buffered) and sum
+  // p_full is double-buffered by tile parity: a softmax warp may run one tile ahead of the slowest one (S(it+1) is issued
+  // before p_full(it) completes), and its early arrival must not count towards the previous tile's phase
+  uint64_t* p_full = bars + 11;             // 2 (one arrival per softmax warp)
+  uint64_t* pv_done = bars + 13;            // 2 (PV(it) arrives on pv_done[it & 1])
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 15);
+  int* s_red = reinterpret_cast<int*>(bars + 16);  // 4 ints
+  float* s_xch = reinterpret_cast<float*>(bars + 18);   // [3*NS][128] floats: per-row partial max (double buffered) and sum
 
   const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // Q / O / the tensor map of Q are LOCAL to the processed query rows [q_row0, T); row_lo / row_hi / LSE2 and the key
@@ -109,7 +111,8 @@ fa_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       mbar_init(&v_empty[i], 1);
       mbar_init(&s_full[i], 1);
     }
-    mbar_init(p_full, 4 * NS);             // one arrival per softmax warp
+    mbar_init(&p_full[0], 4 * NS);         // one arrival per softmax warp
+    mbar_init(&p_full[1], 4 * NS);
     mbar_init(&pv_done[0], 1);
     mbar_init(&pv_done[1], 1);
     mbar_fence_init();
@@ -188,7 +191,7 @@ fa_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         if (it + 1 < ntiles) issue_s(it + 1);
         const int st = it & 1;
         mbar_wait(&v_full[st], (it >> 1) & 1);
-        mbar_wait(p_full, it & 1);
+        mbar_wait(&p_full[it & 1], (it >> 1) & 1);
         tc_fence_after();
         const uint32_t tmem_p = tmem_base + (it & 1) * 128;
 #pragma unroll
@@ -287,7 +290,7 @@ fa_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);     // 16 arrivals per tile instead of 512 same-address shared-memory atomics
+      if (lane == 0) mbar_arrive(&p_full[it & 1]);     // 16 arrivals per tile instead of 512 same-address shared-memory atomics
     }
     // ---- epilogue: combine the partial row sums, normalise, store this thread's output columns ----
     s_xch[(2 * NS + part) * TQ + r] = l;

@@ -118,9 +118,11 @@ decode_attn_tc_kernel(const bf16* __restrict__ q, long long ldq, int Hq, int Hkv
   uint64_t* full = bars;                       // NSTG   TMA -> MMA
   uint64_t* done = bars + NSTG;                // NSTG   PV(it) retired: stage free (producer), P / O safe (softmax)
   uint64_t* s_full = bars + 2 * NSTG;          // 2
-  uint64_t* p_ready = bars + 2 * NSTG + 2;     // 1 (one arrival per softmax warp)
-  uint64_t* q_ready = bars + 2 * NSTG + 3;     // 1 (one arrival per softmax warp)
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * NSTG + 4);
+  // p_ready is double-buffered by unit parity: a softmax warp may run one unit ahead of the slowest one (S(it+1) is
+  // issued before p_ready(it) completes) and its early arrival must not count towards the previous unit's phase
+  uint64_t* p_ready = bars + 2 * NSTG + 2;     // 2 (one arrival per softmax warp)
+  uint64_t* q_ready = bars + 2 * NSTG + 4;     // 1 (one arrival per softmax warp)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * NSTG + 5);
   float* s_xch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);   // [2 it][NS parts][128 lanes]
   float* s_lx = s_xch + 2 * NS * 128;                                               // [NS parts][128 lanes]
   float* s_knew = s_lx + NS * 128;                                                  // [MAX_OWN][128]
@@ -143,7 +145,8 @@ decode_attn_tc_kernel(const bf16* __restrict__ q, long long ldq, int Hq, int Hkv
     }
     mbar_init(&s_full[0], 1);
     mbar_init(&s_full[1], 1);
-    mbar_init(p_ready, NSOFT / 32);
+    mbar_init(&p_ready[0], NSOFT / 32);
+    mbar_init(&p_ready[1], NSOFT / 32);
     mbar_init(q_ready, NSOFT / 32);
     mbar_fence_init();
   }
@@ -245,7 +248,7 @@ decode_attn_tc_kernel(const bf16* __restrict__ q, long long ldq, int Hq, int Hkv
       for (int it = 0; it < n_units; ++it) {
         if (it + 1 < n_units) issue_s(it + 1);
         const int st = it % NSTG;
-        mbar_wait(p_ready, it & 1);
+        mbar_wait(&p_ready[it & 1], (it >> 1) & 1);
         tc_fence_after();
         DBG(it < 100, it * 8 + 2);
         const uint8_t* sV = sKV + st * STAGE_BYTES + TILE;
@@ -379,7 +382,7 @@ decode_attn_tc_kernel(const bf16* __restrict__ q, long long ldq, int Hq, int Hkv
       tmem_st_wait();                              // warp-collective: every lane's P columns are in TMEM
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_ready);
+      if (lane == 0) mbar_arrive(&p_ready[it & 1]);
       DBG(st_tid == 0 && it < 100, it * 8 + 5);
     }
     DBG(st_tid == 0, 902);
