@@ -126,7 +126,12 @@ stream_gemm_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_const
   const uint32_t tmem_base = *tmem_ptr_smem;
   pdl_trigger();   // the next kernel of the chain may become resident (it blocks in its own griddepcontrol.wait)
 #ifdef T1_SG_DBG
-  if (threadIdx.x == 0) g_cta_t[0][blockIdx.x] = gtimer();
+  if (threadIdx.x == 0) {
+    g_cta_t[0][blockIdx.x] = gtimer();
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    g_cta_t[1][blockIdx.x] = smid;
+  }
 #endif
 
   if (warp_idx == 0) {
@@ -485,7 +490,12 @@ stream_gemm_dyn_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_c
   const uint32_t tmem_base = *tmem_ptr_smem;
   pdl_trigger();
 #ifdef T1_SG_DBG
-  if (threadIdx.x == 0) g_cta_t[0][blockIdx.x] = gtimer();
+  if (threadIdx.x == 0) {
+    g_cta_t[0][blockIdx.x] = gtimer();
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    g_cta_t[1][blockIdx.x] = smid;
+  }
 #endif
 
   if (warp_idx == 0) {
