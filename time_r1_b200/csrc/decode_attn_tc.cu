@@ -45,9 +45,10 @@ constexpr int UNIT = 128;                        // keys per unit
 constexpr int ATOM = 128 * 128;                  // [128 rows x 64 cols] bf16 SW128 atom
 constexpr int TILE = 2 * ATOM;                   // [128 x 128] bf16
 constexpr int STAGE_BYTES = 2 * TILE;            // K then V
-constexpr int NSTG = 2;
+constexpr int NSTG = 2;                          // == the two S buffers: s_full doubles as "K tile free"
 constexpr int NS = 4;                            // softmax threads per query row
 constexpr int NSOFT = 128 * NS;                  // 16 warps
+static_assert(NSOFT >= 64 * 8, "the Q-tile build takes one (row, 8-channel chunk) per softmax thread");
 constexpr int TC_THREADS = 64 + NSOFT;
 constexpr int MAX_S = 16;
 constexpr int MAX_OWN = 8;                       // sequences whose current token one CTA may own (ceil(G / S))
@@ -115,14 +116,17 @@ decode_attn_tc_kernel(const bf16* __restrict__ q, long long ldq, int Hq, int Hkv
   uint8_t* sQ = smem;
   uint8_t* sKV = sQ + TILE;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + NSTG * STAGE_BYTES);
-  uint64_t* full = bars;                       // NSTG   TMA -> MMA
-  uint64_t* done = bars + NSTG;                // NSTG   PV(it) retired: stage free (producer), P / O safe (softmax)
+  uint64_t* full = bars;                       // NSTG   TMA -> MMA: K tile of the stage landed
+  uint64_t* done = bars + NSTG;                // NSTG   PV(it) retired: V tile free (producer), P / O safe (softmax)
   uint64_t* s_full = bars + 2 * NSTG;          // 2
   // p_ready is double-buffered by unit parity: a softmax warp may run one unit ahead of the slowest one (S(it+1) is
   // issued before p_ready(it) completes) and its early arrival must not count towards the previous unit's phase
   uint64_t* p_ready = bars + 2 * NSTG + 2;     // 2 (one arrival per softmax warp)
   uint64_t* q_ready = bars + 2 * NSTG + 4;     // 1 (one arrival per softmax warp)
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * NSTG + 5);
+  // K and V tiles of a stage are tracked separately: the K tile is free as soon as S(it) has retired (s_full, which the
+  // producer also waits on), long before PV(it) frees the V tile, so K(it+2) is in flight while softmax(it) still runs
+  uint64_t* v_full = bars + 2 * NSTG + 5;      // NSTG   TMA -> MMA: V tile of the stage landed
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 3 * NSTG + 5);
   float* s_xch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);   // [2 it][NS parts][128 lanes]
   float* s_lx = s_xch + 2 * NS * 128;                                               // [NS parts][128 lanes]
   float* s_knew = s_lx + NS * 128;                                                  // [MAX_OWN][128]
@@ -141,6 +145,7 @@ decode_attn_tc_kernel(const bf16* __restrict__ q, long long ldq, int Hq, int Hkv
   if (warp_idx == 1 && lane == 0) {
     for (int i = 0; i < NSTG; ++i) {
       mbar_init(&full[i], 1);
+      mbar_init(&v_full[i], 1);
       mbar_init(&done[i], 1);
     }
     mbar_init(&s_full[0], 1);
@@ -152,10 +157,14 @@ decode_attn_tc_kernel(const bf16* __restrict__ q, long long ldq, int Hq, int Hkv
   }
   if (warp_idx == 1) tmem_alloc<512>(tmem_ptr_smem);
   pdl_trigger();
-  pdl_wait();                                  // everything below reads what the previous kernels wrote (q, step)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // Only q was written by the previous kernel, and only the softmax warps read it -- they execute griddepcontrol.wait.
+  // The TMA producer does not: the cached K/V rows and *step_ptr were written several kernels up the chain (every
+  // kernel of the chain waits, so completion is transitive), and its first NSTG units travel under the tail of the
+  // qkv GEMM and the Q-tile build.  The MMA warp only touches shared memory / TMEM behind mbarriers.
+  // The softmax warps wait inside their branch, after the part of the Q-tile build that does not need q.
   const uint32_t tmem_base = *tmem_ptr_smem;
   const uint32_t T_S = 0, T_O = 256;           // S[2] x 128 columns, O 128 columns
 
@@ -210,14 +219,17 @@ decode_attn_tc_kernel(const bf16* __restrict__ q, long long ldq, int Hq, int Hkv
       for (int it = 0; it < n_units; ++it) {
         const int st = it % NSTG;
         const UnitDesc d = unit_desc(it);
-        mbar_wait(&done[st], ((it / NSTG) & 1) ^ 1);
-        mbar_arrive_expect_tx(&full[st], STAGE_BYTES);
         uint8_t* sK = sKV + st * STAGE_BYTES;
         uint8_t* sV = sK + TILE;
+        // S(it - NSTG) read this K tile; it cannot complete a later phase before K(it) is loaded, so the parity is exact
+        if (it >= NSTG) mbar_wait(&s_full[(it - NSTG) & 1], ((it - NSTG) >> 1) & 1);
+        mbar_arrive_expect_tx(&full[st], TILE);
         tma_load_2d(sK, tm_k, &full[st], hk * HD, d.slot0);
         tma_load_2d(sK + ATOM, tm_k, &full[st], hk * HD + 64, d.slot0);
-        tma_load_2d(sV, tm_v, &full[st], hk * HD, d.slot0);
-        tma_load_2d(sV + ATOM, tm_v, &full[st], hk * HD + 64, d.slot0);
+        mbar_wait(&done[st], ((it / NSTG) & 1) ^ 1);
+        mbar_arrive_expect_tx(&v_full[st], TILE);
+        tma_load_2d(sV, tm_v, &v_full[st], hk * HD, d.slot0);
+        tma_load_2d(sV + ATOM, tm_v, &v_full[st], hk * HD + 64, d.slot0);
         DBG(it < 100, it * 8 + 0);
       }
     }
@@ -248,6 +260,7 @@ decode_attn_tc_kernel(const bf16* __restrict__ q, long long ldq, int Hq, int Hkv
       for (int it = 0; it < n_units; ++it) {
         if (it + 1 < n_units) issue_s(it + 1);
         const int st = it % NSTG;
+        mbar_wait(&v_full[st], (it / NSTG) & 1);
         mbar_wait(&p_ready[it & 1], (it >> 1) & 1);
         tc_fence_after();
         DBG(it < 100, it * 8 + 2);
@@ -265,11 +278,22 @@ decode_attn_tc_kernel(const bf16* __restrict__ q, long long ldq, int Hq, int Hkv
     // ===================== softmax warps: NS threads per query row, 32 key columns each =====================
     // ---- Q tile: zero, then the rotated query rows (row r at lane 32*(r/rpq) + r%rpq) in the UMMA K-major swizzle ----
     for (int e = st_tid; e < TILE / 16; e += NSOFT) reinterpret_cast<uint4*>(sQ)[e] = make_uint4(0u, 0u, 0u, 0u);
-    asm volatile("bar.sync 9, %0;" ::"n"(NSOFT) : "memory");
     const float* cs = grp.cos_t + (long long)step * (HD / 2);
     const float* sn = grp.sin_t + (long long)step * (HD / 2);
-    for (int e = st_tid; e < n_rows * 8; e += NSOFT) {
-      const int row = e >> 3, c = e & 7;         // 8-channel chunk c pairs with chunk c + 8
+    // one (row, 8-channel chunk) per thread; chunk c pairs with chunk c + 8.  The rope factors do not depend on q.
+    const int q_row = st_tid >> 3, q_c = st_tid & 7;
+    const bool q_on = q_row < n_rows;
+    float c8[8], s8[8];
+    if (q_on) {
+      *reinterpret_cast<float4*>(c8) = *reinterpret_cast<const float4*>(cs + q_c * 8);
+      *reinterpret_cast<float4*>(c8 + 4) = *reinterpret_cast<const float4*>(cs + q_c * 8 + 4);
+      *reinterpret_cast<float4*>(s8) = *reinterpret_cast<const float4*>(sn + q_c * 8);
+      *reinterpret_cast<float4*>(s8 + 4) = *reinterpret_cast<const float4*>(sn + q_c * 8 + 4);
+    }
+    pdl_wait();                                  // q (the fused qkv rows of this step) is complete and visible
+    asm volatile("bar.sync 9, %0;" ::"n"(NSOFT) : "memory");
+    if (q_on) {
+      const int row = q_row, c = q_c;
       const int sq = row / ratio, hq = hk * ratio + row % ratio;
       const bf16* src = q + (long long)sq * ldq + (long long)hq * HD + c * 8;
       const uint4 ua = *reinterpret_cast<const uint4*>(src), ub = *reinterpret_cast<const uint4*>(src + HD / 2);
@@ -280,8 +304,8 @@ decode_attn_tc_kernel(const bf16* __restrict__ q, long long ldq, int Hq, int Hkv
       for (int j = 0; j < 4; ++j) {
         const float2 a = unpack_bf16x2(pa[j]), b = unpack_bf16x2(pb[j]);
         float ra0, rb0, ra1, rb1;
-        rope_rotate(a.x, b.x, cs[c * 8 + 2 * j], sn[c * 8 + 2 * j], ra0, rb0);
-        rope_rotate(a.y, b.y, cs[c * 8 + 2 * j + 1], sn[c * 8 + 2 * j + 1], ra1, rb1);
+        rope_rotate(a.x, b.x, c8[2 * j], s8[2 * j], ra0, rb0);
+        rope_rotate(a.y, b.y, c8[2 * j + 1], s8[2 * j + 1], ra1, rb1);
         oa[j] = pack_bf16x2(ra0, ra1);
         ob[j] = pack_bf16x2(rb0, rb1);
       }
@@ -398,14 +422,16 @@ decode_attn_tc_kernel(const bf16* __restrict__ q, long long ldq, int Hq, int Hkv
     }
   }
   DBG(threadIdx.x == 64, 903);
-  cluster.sync();            // every CTA of the cluster is done with its K/V ring: it becomes the merge receive buffer
-  DBG(threadIdx.x == 64, 904);
-
+  // Split-phase cluster barrier: arrive = "this CTA is done with its K/V ring" (which becomes a merge receive buffer of
+  // the cluster); the work that needs no remote memory (O out of TMEM, the score of this step's token) runs before the wait.
+  cluster.barrier_arrive();
   float* rO = reinterpret_cast<float*>(sKV);            // [64/S local rows][2S sources][128]
   float* rML = rO + 64 * 2 * HD;                        // [64/S local rows][2S sources][2]
+  uint32_t ov[32];
+  float s_new = -INFINITY, l_new = 0.f;
+  const bool own = valid && (my_seq % S) == rank && (my_seq / S) < MAX_OWN;
+  const int own_o = own ? my_seq / S : 0;
   if (warp_idx >= 2) {
-    // ---- push: source 2*rank = cached-key partial, source 2*rank+1 = this step's token (owner of the sequence only) ----
-    uint32_t ov[32];
     if (n_units > 0) {                            // warp-uniform: tcgen05.ld is .sync.aligned
       tmem_ld_32x32b_x32(t_lane + T_O + part * 32, ov);
       tmem_ld_wait();
@@ -413,72 +439,86 @@ decode_attn_tc_kernel(const bf16* __restrict__ q, long long ldq, int Hq, int Hkv
 #pragma unroll
       for (int j = 0; j < 32; ++j) ov[j] = 0u;
     }
-    if (valid) {
-      const int owner = r % S, li = r / S;
-      float* dO = cluster.map_shared_rank(rO, owner) + (long long)(li * 2 * S + 2 * rank) * HD + part * 32;
-      float* dML = cluster.map_shared_rank(rML, owner) + (li * 2 * S + 2 * rank) * 2;
+    if (own && part == 0) {
+      float acc = 0.f;
+#pragma unroll 4
+      for (int c = 0; c < 16; ++c) {
+        const uint4 u = *reinterpret_cast<const uint4*>(sQ + sw128_off(L, c * 8));
+        const uint32_t* pu = reinterpret_cast<const uint32_t*>(&u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 qq = unpack_bf16x2(pu[j]);
+          acc = fmaf(qq.x, s_knew[own_o * HD + c * 8 + 2 * j], acc);
+          acc = fmaf(qq.y, s_knew[own_o * HD + c * 8 + 2 * j + 1], acc);
+        }
+      }
+      s_new = acc * scale_log2;
+      l_new = 1.f;
+    }
+  }
+  cluster.barrier_wait();    // every CTA of the cluster is done with its K/V ring
+  DBG(threadIdx.x == 64, 904);
+
+  if (valid) {
+    // ---- push: source 2*rank = cached-key partial, source 2*rank+1 = this step's token (owner of the sequence only) ----
+    const int owner = r % S, li = r / S;
+    float* dO = cluster.map_shared_rank(rO, owner) + (long long)(li * 2 * S + 2 * rank) * HD + part * 32;
+    float* dML = cluster.map_shared_rank(rML, owner) + (li * 2 * S + 2 * rank) * 2;
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4)
+      *reinterpret_cast<uint4*>(dO + j4 * 4) = make_uint4(ov[j4 * 4], ov[j4 * 4 + 1], ov[j4 * 4 + 2], ov[j4 * 4 + 3]);
+    if (own) {
 #pragma unroll
       for (int j4 = 0; j4 < 8; ++j4)
-        *reinterpret_cast<uint4*>(dO + j4 * 4) = make_uint4(ov[j4 * 4], ov[j4 * 4 + 1], ov[j4 * 4 + 2], ov[j4 * 4 + 3]);
-      const bool own = (my_seq % S) == rank && (my_seq / S) < MAX_OWN;
-      const int o = my_seq / S;
-      if (own) {
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4)
-          *reinterpret_cast<float4*>(dO + HD + j4 * 4) = *reinterpret_cast<const float4*>(s_vnew + o * HD + part * 32 + j4 * 4);
-      }
-      if (part == 0) {
-        float s_new = -INFINITY, l_new = 0.f;
-        if (own) {
-          float acc = 0.f;
-#pragma unroll 4
-          for (int c = 0; c < 16; ++c) {
-            const uint4 u = *reinterpret_cast<const uint4*>(sQ + sw128_off(L, c * 8));
-            const uint32_t* pu = reinterpret_cast<const uint32_t*>(&u);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 qq = unpack_bf16x2(pu[j]);
-              acc = fmaf(qq.x, s_knew[o * HD + c * 8 + 2 * j], acc);
-              acc = fmaf(qq.y, s_knew[o * HD + c * 8 + 2 * j + 1], acc);
-            }
-          }
-          s_new = acc * scale_log2;
-          l_new = 1.f;
-        }
-        *reinterpret_cast<float4*>(dML) = make_float4(m_ref, l, s_new, l_new);
-      }
+        *reinterpret_cast<float4*>(dO + HD + j4 * 4) = *reinterpret_cast<const float4*>(s_vnew + own_o * HD + part * 32 + j4 * 4);
     }
+    if (part == 0) *reinterpret_cast<float4*>(dML) = make_float4(m_ref, l, s_new, l_new);
   }
   DBG(threadIdx.x == 64, 905);
   cluster.sync();            // all pushes have landed (release / acquire at cluster scope)
   DBG(threadIdx.x == 64, 906);
 
-  // ---- local merge of the rows this CTA owns (rank, rank + S, ...): one thread per head-dim column ----
+  // ---- local merge of the rows this CTA owns (rank, rank + S, ...) ----
   if (warp_idx >= 2) {
-    const int col = st_tid & (HD - 1), sub = st_tid >> 7;      // NS row slots in flight
-    for (int li = sub;; li += NS) {
-      const int row = rank + li * S;
-      if (row >= n_rows) break;
+    // pass 1, one warp per row: lane = source; w = 2^(m - M) (0 for empty sources), L = sum w * l
+    float* s_w = s_xch;                           // [local rows][2S]  (the exchange buffers are free now)
+    float* s_L = s_lx;                            // [local rows]
+    const int n_local = rank < n_rows ? (n_rows - rank + S - 1) / S : 0;
+    for (int li = warp_idx - 2; li < n_local; li += NSOFT / 32) {
       const float* ml = rML + (li * 2 * S) * 2;
-      const float* po = rO + (long long)(li * 2 * S) * HD + col;
-      float M = -INFINITY;
-#pragma unroll
-      for (int src = 0; src < 2 * MAX_S; ++src)
-        if (src < 2 * S && ml[src * 2 + 1] > 0.f) M = fmaxf(M, ml[src * 2]);
-      float Lsum = 0.f, acc = 0.f;
-#pragma unroll
-      for (int src = 0; src < 2 * MAX_S; ++src) {
-        if (src < 2 * S) {
-          const float lv = ml[src * 2 + 1];
-          const bool on = lv > 0.f;
-          const float w = on ? ex2_approx(ml[src * 2] - M) : 0.f;
-          const float ov = po[src * HD];                     // local shared memory; garbage of empty sources is dropped
-          Lsum += w * lv;
-          acc += on ? w * ov : 0.f;
-        }
+      float mv = -INFINITY, lv = 0.f;
+      if (lane < 2 * S) {
+        mv = ml[lane * 2];
+        lv = ml[lane * 2 + 1];
       }
+      const bool on = lv > 0.f;
+      float M = on ? mv : -INFINITY;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o));
+      const float w = on ? ex2_approx(mv - M) : 0.f;
+      float Ls = w * lv;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) Ls += __shfl_xor_sync(0xffffffffu, Ls, o);
+      if (lane < 2 * S) s_w[li * 2 * S + lane] = w;
+      if (lane == 0) s_L[li] = Ls;
+    }
+    asm volatile("bar.sync 9, %0;" ::"n"(NSOFT) : "memory");
+    // pass 2, one thread per (row, head-dim column)
+    for (int e = st_tid; e < n_local * HD; e += NSOFT) {
+      const int li = e >> 7, col = e & (HD - 1);
+      const float* po = rO + (long long)(li * 2 * S) * HD + col;
+      const float* w = s_w + li * 2 * S;
+      float acc = 0.f;
+#pragma unroll 4
+      for (int src = 0; src < 2 * S; ++src) {
+        const float ws = w[src];
+        const float o = po[src * HD];             // local shared memory; garbage of empty sources is dropped
+        acc += ws > 0.f ? ws * o : 0.f;
+      }
+      const float Ls = s_L[li];
+      const int row = rank + li * S;
       const int sq = row / ratio, hq = hk * ratio + row % ratio;
-      out[(long long)sq * ldo + (long long)hq * HD + col] = __float2bfloat16(Lsum > 0.f ? acc / Lsum : 0.f);
+      out[(long long)sq * ldo + (long long)hq * HD + col] = __float2bfloat16(Ls > 0.f ? acc / Ls : 0.f);
     }
   }
   DBG(threadIdx.x == 64, 907);
