@@ -256,6 +256,25 @@ int t1_video_patchify(const void* frames, int in_u8, int T, int H, int W, int pa
  * (src/vllm_inference/calc_difficulty.py:10-37). */
 int t1_iou_reward(int mode, const double* pred_s, const double* pred_e, const unsigned char* valid, const double* gt_s,
                   const double* gt_e, const double* dur, double* out64, float* out32, int n, cudaStream_t stream);
+/* Completion text on the device: replaces the device->host copy + tokenizer.batch_decode +
+ * Python regexes between the scoring passes and the loss (timer1_trainer.py:642-698 -> main.py:122-239).
+ * t1_detokenize: ids [n, C] int32 -> UTF-8 bytes [n, cap] + byte length [n], i.e. the byte string tokenizers' ByteLevel
+ * decoder builds for batch_decode (timer1_trainer.py:642-644).  row_tokens [n] int32 (nullable: all C) = tokens of each
+ * row to decode; tok_off [V + 1] int32 + tok_bytes = the vocabulary's byte strings; tok_skip [V] uint8 (nullable) marks
+ * the special tokens skip_special_tokens=True drops; ids outside [0, V) produce nothing.  max_tok_bytes = longest entry of
+ * the table; cap >= C * max_tok_bytes is required (no row can be truncated).  All pointers are device pointers. */
+int t1_detokenize(const int* ids, int n, int C, const int* row_tokens, const int* tok_off, const unsigned char* tok_bytes,
+                  const unsigned char* tok_skip, int V, int max_tok_bytes, unsigned char* out_bytes, int cap, int* out_len,
+                  cudaStream_t stream);
+/* t1_parse_answers: byte-exact restatement of the reference's regexes + float() on text [n, cap] / len [n]
+ * (invalid UTF-8 behaves as the U+FFFD of decode(errors="replace"); `\d`, `\s`, strip() are Unicode-aware as in CPython;
+ * float() is correctly rounded for any digit count).  mode 0: parse_timestamp_output (main.py:122-142: last
+ * `<num> to|and <num>`, case-insensitive, inside the last <answer>..</answer>) and format_reward (main.py:234-239);
+ * mode 1: extract_answer (evaluate.py:125-151); mode 2: mode 1, then the first two numbers when it finds nothing
+ * (src/vllm_inference/calc_difficulty.py:40-60).  out_s / out_e [n] fp64, out_valid [n] uint8 feed t1_iou_reward;
+ * out_format [n] uint8 and out_format_f32 [n] (the format_reward column) are nullable. */
+int t1_parse_answers(const unsigned char* text, const int* len, int n, int cap, int mode, double* out_s, double* out_e,
+                     unsigned char* out_valid, unsigned char* out_format, float* out_format_f32, cudaStream_t stream);
 /* rewards = sum over functions; per-group mean, UNBIASED std; adv = (r - mean) / (std + eps)
  * (timer1_trainer.py:700-712).  rewards_per_func [n, nf] fp32; n % G == 0. */
 int t1_group_advantage(const float* rewards_per_func, int n, int nf, int G, float eps, float* rewards, float* adv,

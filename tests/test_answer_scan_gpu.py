@@ -1,0 +1,180 @@
+"""Device detokeniser + answer scanner (t1_detokenize / t1_parse_answers) through the C-ABI: bit-exact against CPython's
+`re` / `float()` on the reference's patterns (same corpora as the CPU harness test), against the unmodified reference's
+reward outputs (tests/golden/rewards_golden.json), and the trainer's device reward route against its host route."""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+import scan_cases as sc
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def device_scan(rows, mode):
+    from time_r1_b200 import ops
+
+    n = len(rows)
+    cap = max(16, max(len(r) for r in rows))
+    buf = np.zeros((n, cap), np.uint8)
+    for i, r in enumerate(rows):
+        buf[i, :len(r)] = np.frombuffer(r, np.uint8)
+    text = torch.from_numpy(buf).cuda()
+    lens = torch.tensor([len(r) for r in rows], dtype=torch.int32, device="cuda")
+    s, e, v, f, f32 = ops.parse_answers(text, lens, mode)
+    torch.cuda.synchronize()
+    assert torch.equal(f32, f.float())
+    return s.cpu().numpy(), e.cpu().numpy(), v.cpu().numpy(), f.cpu().numpy()
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_scanner_matches_cpython_re(mode):
+    rows = [t.encode("utf-8") for t in sc.HAND + sc.fuzz_texts()] + sc.fuzz_byte_rows()
+    rows += [b"", b"<answer>" + b"1" * 100000 + b" to 2</answer>", b" " * 70000 + b"<think></think><answer>3 and 4.</answer>" + b"\n" * 999]
+    sc.assert_rows_match(rows, mode, *device_scan(rows, mode))
+
+
+def test_float_conversion_is_correctly_rounded_on_the_device():
+    cases = sc.float_cases()
+    rows = [f"<answer>{a} to {b}</answer>".encode() for a, b in zip(cases, cases[1:] + cases[:1])]
+    rows += ["<answer>٣.٥ and 1٣</answer>".encode(), "<answer>\U0001D7D8\U0001D7D9.5 to １２３</answer>".encode()]
+    s, e, v, f = device_scan(rows, 0)
+    assert v.all()
+    for a, b, x, y in zip(cases, cases[1:] + cases[:1], s, e):
+        assert sc.bits(x) == sc.bits(float(a)) and sc.bits(y) == sc.bits(float(b)), (a[:50], b[:50], x, y)
+    assert (s[-2], e[-2], s[-1], e[-1]) == (3.5, 13.0, 23.5, 123.0)
+
+
+def _random_table(rng, V, device="cuda"):
+    from time_r1_b200.detok import DetokTable
+
+    entries = []
+    for i in range(V):
+        k = rng.choice([0, 1, 1, 2, 3, 5, 9, 33, 130])
+        entries.append(bytes(rng.randrange(256) for _ in range(k)))
+    special = rng.sample(range(V), 5)
+    return DetokTable.from_byte_strings(entries, special), DetokTable.from_byte_strings(entries, special, device)
+
+
+@pytest.mark.parametrize("C", [1, 7, 256, 257, 700])
+def test_detokenize_matches_table_walk(C):
+    from time_r1_b200 import ops
+
+    rng = random.Random(C)
+    V = 500
+    host, dev = _random_table(rng, V)
+    n = 33
+    ids = np.array([[rng.randrange(-3, V + 3) for _ in range(C)] for _ in range(n)], np.int32)
+    ntok = np.array([rng.randint(0, C) for _ in range(n)], np.int32)
+    ids_d = torch.from_numpy(ids).cuda()
+    for skip in (True, False):
+        for row_tokens in (None, torch.from_numpy(ntok).cuda()):
+            out, out_len = ops.detokenize(ids_d, dev, row_tokens=row_tokens, skip_special_tokens=skip)
+            out, out_len = out.cpu().numpy(), out_len.cpu().numpy()
+            for i in range(n):
+                k = C if row_tokens is None else int(ntok[i])
+                want = host.decode_bytes_host(ids[i, :k], skip_special_tokens=skip)
+                assert out_len[i] == len(want) and out[i, :len(want)].tobytes() == want, (i, k, skip)
+
+
+def test_detokenize_rejects_a_buffer_that_could_truncate():
+    from time_r1_b200 import lib
+    from time_r1_b200.lib import call, ptr
+
+    _, dev = _random_table(random.Random(1), 64)
+    ids = torch.zeros((2, 8), dtype=torch.int32, device="cuda")
+    out = torch.empty((2, 16), dtype=torch.uint8, device="cuda")
+    out_len = torch.empty(2, dtype=torch.int32, device="cuda")
+    with pytest.raises(lib.Timer1Error):
+        call("t1_detokenize", ptr(ids), 2, 8, 0, ptr(dev.offsets), ptr(dev.data), 0, 64, dev.max_token_bytes, ptr(out), 16, ptr(out_len), 0)
+
+
+def _byte_vocab_table():
+    """256 single-byte tokens + two specials (pad 256, eos 257): text -> ids is text.encode()."""
+    from time_r1_b200.detok import DetokTable
+
+    return DetokTable.from_byte_strings([bytes([b]) for b in range(256)] + [b"<|endoftext|>", b"<|im_end|>"], [256, 257], "cuda")
+
+
+def test_device_rewards_match_the_unmodified_reference():
+    """ids -> t1_detokenize -> t1_parse_answers -> t1_iou_reward vs outputs of the reference's own reward functions
+    (oracle/gen_golden_rewards.py imports /root/reference/main.py)."""
+    from time_r1_b200 import rewards
+
+    rows = json.load(open(os.path.join(GOLD, "rewards_golden.json")))
+    table = _byte_vocab_table()
+    funcs = [rewards.iou_timestamp_reward, rewards.iou_timestamp_reward_v2, rewards.format_reward]
+    dr = rewards.DeviceRewards(funcs, table)
+    C = max(len(r["text"].encode()) for r in rows) + 3
+    for r in rows:
+        b = r["text"].encode()
+        ids = torch.full((2, C), 256, dtype=torch.int32)
+        ids[0, :len(b)] = torch.tensor(list(b), dtype=torch.int32)
+        ids[0, len(b)] = 257                                                   # eos, then pad: both dropped
+        ids[1, 1:len(b) + 1] = torch.tensor(list(b), dtype=torch.int32)        # specials in front as well
+        got = dr(ids.cuda(), r["solution"], r["duration"]).cpu().numpy()
+        want = np.array([0.0 if r["iou"] is None else r["iou"], 0.0 if r["iou"] is None else r["iou_v2"], r["format"]]).astype(np.float32)
+        assert np.array_equal(got[0], want) and np.array_equal(got[1], want), (r["text"], got, want)
+    assert not rewards.DeviceRewards.supports([lambda **k: [0.0]]) and not rewards.DeviceRewards.supports([])
+
+
+class FragmentTokenizer:
+    """Byte-level vocabulary for the toy model (2043 ordinary ids + eos/pad): ids 0..255 are the raw bytes, the rest are
+    whole template answers, so random completions produce parsable and unparsable texts, with and without the format."""
+    eos_token_id = 2043
+
+    def __init__(self):
+        from time_r1_b200.detok import DetokTable, byte_level_alphabet
+
+        inv = {b: ch for ch, b in byte_level_alphabet().items()}
+        enc = lambda s: "".join(inv[b] for b in s.encode("utf-8"))
+        self.vocab = {inv[b]: b for b in range(256)}
+        for k in range(256, 2043):
+            s = k % 17
+            frag = [f"<think>t{k}</think><answer>{s}.5 to {s + 1 + k % 13}</answer>", f"{k}: <answer>{s} and {s + 2}.25</answer>", f" {k} ",
+                    f"<think>{k}</think>\n<answer>no span</answer>"][k % 4]
+            self.vocab[enc(frag)] = k
+        self.vocab["<|im_end|>"], self.vocab["<|endoftext|>"] = 2043, 2044
+        self.all_special_ids = [2043, 2044]
+        self._table = DetokTable.from_tokenizer(self)
+        self.host_decodes = 0
+
+    def get_vocab(self):
+        return dict(self.vocab)
+
+    def batch_decode(self, ids, skip_special_tokens=True):
+        self.host_decodes += 1
+        return [self._table.decode_bytes_host(row, skip_special_tokens).decode("utf-8", errors="replace") for row in np.asarray(ids)]
+
+
+def test_trainer_device_reward_route_equals_host_route(tmp_path):
+    from test_trainer_gpu import make_dataset
+
+    from time_r1_b200 import config, rewards, weights
+    from time_r1_b200.trainer import GRPOArguments, TimeR1_Trainer
+
+    logs = {}
+    for route in (True, False):
+        cfg = config.toy()
+        mw = weights.ModelWeights(cfg, "cuda")
+        mw.init_random(seed=1, std=0.05)
+        tok = FragmentTokenizer()
+        args = GRPOArguments(output_dir=str(tmp_path / str(route)), num_generations=4, max_completion_length=6, temperature=1.0, beta=0.04,
+                             learning_rate=1e-4, gradient_accumulation_steps=2, max_steps=3, logging_steps=1, fix_vit=True,
+                             save_strategy="no", device_rewards=route)
+        tr = TimeR1_Trainer(model=(cfg, mw), reward_funcs=[rewards.iou_timestamp_reward, rewards.iou_timestamp_reward_v2, rewards.format_reward],
+                            args=args, train_dataset=make_dataset(cfg), processing_class=tok)
+        tr.train()
+        assert (tok.host_decodes == 0) == route, "device route must not decode on the host; host route must"
+        logs[route] = tr.state.log_history
+    assert len(logs[True]) == len(logs[False]) == 3
+    # step 1 starts from identical weights and seeds: identical completions, so every logged number must agree exactly
+    a, b = logs[True][0], logs[False][0]
+    for key in ("loss", "grad_norm", "reward", "reward_std", "rewards/iou_timestamp_reward", "rewards/iou_timestamp_reward_v2",
+                "rewards/format_reward", "completion_length", "kl"):
+        assert a[key] == b[key], (key, a[key], b[key])
+    assert any(l["reward"] > 0 for l in logs[True]), "the fragment vocabulary should have produced a parsable completion"

@@ -1025,7 +1025,9 @@ class Engine:
         """The micro-batches of ONE optimizer step (gradient accumulation, train_rl.sh:27), each a prompt-group:
         ViT per group -> joint rollout (shared weight stream) -> per group: mask, policy/ref scoring, rewards (host
         callback), advantage, loss, backward (gradients accumulate).
-        reward_fn(completion_ids_host [G, C] int64 numpy) -> rewards_per_func [G, n_funcs] float32 numpy.
+        reward_fn(completion_ids_host [G, C] int64 numpy) -> rewards_per_func [G, n_funcs] float32 numpy; a reward_fn
+        carrying a `.device` attribute (callable: completion ids [G, C] int32 device tensor -> [G, n_funcs] fp32 device
+        tensor, e.g. rewards.DeviceRewards) is evaluated on the device instead and the completions are not copied out.
         Returns one dict of device tensors per group."""
         run, cfg = self.run, self.cfg
         G, C = run.num_generations, run.max_completion_length
@@ -1089,9 +1091,14 @@ class Engine:
                     emb_ref = self.merger(x_vit, None, plan, "ref")
                     ref_logp, _, _ = self.score(prompt, comp, emb_ref, "ref")
             mark("score_ref")
-            comp_host = comp.cpu().numpy().astype(np.int64)                 # D2H: completions for the host reward fns
-            rpf = np.ascontiguousarray(reward_fn(comp_host), dtype=np.float32).reshape(G, -1)
-            rpf_dev = torch.from_numpy(rpf).to(self.dev)
+            on_device = getattr(reward_fn, "device", None)
+            if on_device is not None:
+                # registry rewards: detokenise + parse + IoU on the device, no host round trip before the loss
+                rpf_dev = on_device(comp).to(F32).reshape(G, -1).contiguous()
+            else:
+                comp_host = comp.cpu().numpy().astype(np.int64)             # D2H: completions for the host reward fns
+                rpf = np.ascontiguousarray(reward_fn(comp_host), dtype=np.float32).reshape(G, -1)
+                rpf_dev = torch.from_numpy(rpf).to(self.dev)
             rewards, adv, mean, std = ops.group_advantage(rpf_dev, G)
             loss, dlogp, stats = ops.grpo_loss(logp, ref_logp, ent, adv, mask, run.beta, run.epsilon_low, run.epsilon_high,
                                                run.use_grpo, loss_scale=loss_scale)

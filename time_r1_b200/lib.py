@@ -36,6 +36,9 @@ _SIGNATURES: dict[str, list] = {
     "t1_logprob_entropy": [vp, i64, i32, i32, vp, vp, vp, vp, vp],
     "t1_logits_backward": [vp, i64, i32, i32, vp, vp, vp, vp, i64, vp],
     "t1_eos_mask": [vp, i32, i32, i32, vp, vp, vp],
+    # answer_scan.cu
+    "t1_detokenize": [vp, i32, i32, vp, vp, vp, vp, i32, i32, vp, i32, vp, vp],
+    "t1_parse_answers": [vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp],
     # elementwise.cu
     "t1_rmsnorm": [vp, vp, vp, vp, vp, i32, i32, f32, vp],
     "t1_layernorm": [vp, vp, vp, vp, vp, vp, i32, i32, f32, vp],

@@ -438,6 +438,35 @@ def iou_reward(mode, pred_s, pred_e, valid, gt_s, gt_e, dur):
     return o64, o32
 
 
+def detokenize(ids, table, row_tokens=None, skip_special_tokens=True):
+    """ids [n, C] int32 (device) -> (bytes [n, cap] uint8, byte_len [n] int32): the byte string batch_decode builds
+    (timer1_trainer.py:642-644).  `table`: detok.DetokTable on the same device."""
+    n, C = ids.shape
+    _chk(ids, I32, "ids")
+    cap = max(16, -(-C * max(1, table.max_token_bytes) // 16) * 16)
+    out = torch.empty((n, cap), device=ids.device, dtype=torch.uint8)
+    out_len = torch.empty(n, device=ids.device, dtype=I32)
+    call("t1_detokenize", ptr(ids), n, C, ptr(row_tokens), ptr(table.offsets), ptr(table.data),
+         ptr(table.skip) if skip_special_tokens else None, table.vocab_size, table.max_token_bytes, ptr(out), cap, ptr(out_len),
+         stream_ptr())
+    return out, out_len
+
+
+def parse_answers(text, text_len, mode=0):
+    """text [n, cap] uint8 + text_len [n] int32 -> (start [n] f64, end [n] f64, valid [n] u8, format [n] u8, format [n] f32);
+    mode 0 = training rewards (main.py:122-142, 234-239), 1 / 2 = the filtering epochs' extract_answer (+ force fallback)."""
+    n, cap = text.shape
+    dev = text.device
+    s = torch.empty(n, device=dev, dtype=torch.float64)
+    e = torch.empty(n, device=dev, dtype=torch.float64)
+    valid = torch.empty(n, device=dev, dtype=torch.uint8)
+    fmt = torch.empty(n, device=dev, dtype=torch.uint8)
+    fmt32 = torch.empty(n, device=dev, dtype=F32)
+    call("t1_parse_answers", ptr(text), ptr(text_len), n, cap, int(mode), ptr(s), ptr(e), ptr(valid), ptr(fmt), ptr(fmt32),
+         stream_ptr())
+    return s, e, valid, fmt, fmt32
+
+
 def group_advantage(rewards_per_func, G, eps=1e-4):
     n, nf = rewards_per_func.shape
     dev = rewards_per_func.device

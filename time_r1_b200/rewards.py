@@ -1,8 +1,13 @@
 """Verifiable rewards of Time-R1 (drop-in for main.py:122-239 / reward_funcs_registry :416-420).
 
-Text parsing stays on the host (user reward callables are arbitrary Python and receive decoded strings, protocol at
-src/time_r1/rl/timer1_trainer.py:685-698); the IoU arithmetic of a whole group runs in the `t1_iou_reward` kernel in
-fp64, bit-identical to the CPython float arithmetic of the reference.
+Two routes, same numbers:
+
+* protocol route — the functions below take decoded strings like the reference's (protocol at
+  src/time_r1/rl/timer1_trainer.py:685-698; user reward callables are arbitrary Python): regex parsing on the host, the
+  IoU arithmetic of the whole group in the `t1_iou_reward` kernel in fp64, bit-identical to CPython's float arithmetic;
+* device route — `DeviceRewards`: when every configured reward function is one of this registry's, the trainer never
+  decodes on the host: `t1_detokenize` -> `t1_parse_answers` (byte-exact restatement of the regexes and float()) ->
+  `t1_iou_reward`, completions and rewards stay in HBM and the step has no device->host sync before the loss.
 """
 from __future__ import annotations
 
@@ -76,5 +81,48 @@ reward_funcs_registry = {
     "iou_v2": iou_timestamp_reward_v2,
     "format": format_reward,
 }
+
+
+class DeviceRewards:
+    """rewards_per_func [G, n_funcs] fp32 for one prompt-group without leaving the device.
+
+    Replaces, for registry reward functions only, timer1_trainer.py:642-698: batch_decode(skip_special_tokens=True) ->
+    reward_func(completions=..., solution=..., durations=...) -> torch.tensor(..., dtype=float32)."""
+
+    _MODES = {iou_timestamp_reward: 0, iou_timestamp_reward_v2: 1}
+
+    def __init__(self, reward_funcs: Sequence, table):
+        if not self.supports(reward_funcs):
+            raise ValueError("DeviceRewards only covers iou_timestamp_reward, iou_timestamp_reward_v2 and format_reward")
+        self.funcs, self.table = list(reward_funcs), table
+
+    @classmethod
+    def supports(cls, reward_funcs: Sequence) -> bool:
+        return len(reward_funcs) > 0 and all(f in cls._MODES or f is format_reward for f in reward_funcs)
+
+    def __call__(self, completion_ids, solution, duration=None):
+        """completion_ids [G, C] int32 device tensor; solution = (gt_start, gt_end) of the prompt; duration for iou_v2."""
+        import torch
+
+        from . import ops
+
+        G = completion_ids.shape[0]
+        dev = completion_ids.device
+        text, text_len = ops.detokenize(completion_ids, self.table)
+        ps, pe, valid, _, fmt32 = ops.parse_answers(text, text_len, 0)
+        full = lambda v: torch.full((G,), float(v), device=dev, dtype=torch.float64)
+        cols = []
+        for f in self.funcs:
+            if f is format_reward:
+                cols.append(fmt32)
+                continue
+            mode = self._MODES[f]
+            if mode == 1 and duration is None:
+                raise TypeError("iou_timestamp_reward_v2 needs the `durations` column (main.py:190)")
+            _, o32 = ops.iou_reward(mode, ps, pe, valid, full(solution[0]), full(solution[1]), full(duration if mode == 1 else 1.0))
+            cols.append(o32)
+        return torch.stack(cols, dim=1).contiguous()
+
+
 # metric functions of timer1_trainer_ft.py are logging-only host regexes (SURVEY §2.1 #3: out of scope)
 metric_funcs_registry: dict = {}

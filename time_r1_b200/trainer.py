@@ -80,6 +80,7 @@ class GRPOArguments:
     run_name: Optional[str] = None
     logging_dir: Optional[str] = None
     deepspeed: Optional[str] = None                   # accepted and ignored: sharding is built in
+    device_rewards: bool = True                       # registry rewards parsed on the device (rewards.DeviceRewards)
     model_init_kwargs: Optional[dict] = None
 
 
@@ -304,7 +305,28 @@ class TimeR1_Trainer:
             self._last_completions = completions
             return out
 
+        dr = self._device_reward_path()
+        if dr is not None and "solution" in example:
+            # registry rewards: ids -> bytes -> parsed timestamps -> IoU / format flags, all on the device
+            reward_fn.device = lambda comp: dr(comp, example["solution"], example.get("durations"))
         return prompt, reward_fn
+
+    def _device_reward_path(self):
+        """rewards.DeviceRewards when every reward function is one of the registry's, the tokenizer is byte-level BPE
+        with a readable vocabulary and nothing else needs the decoded strings (metric functions, `device_rewards=False`
+        in the arguments); None otherwise -> the host protocol of timer1_trainer.py:642-698."""
+        if not hasattr(self, "_device_rewards"):
+            self._device_rewards = None
+            from .rewards import DeviceRewards
+
+            tok = getattr(self.processing_class, "tokenizer", self.processing_class)
+            if (getattr(self.args, "device_rewards", True) and not self.metric_funcs and DeviceRewards.supports(self.reward_funcs)
+                    and hasattr(tok, "get_vocab") and hasattr(tok, "all_special_ids")):
+                from .detok import DetokTable
+
+                table = DetokTable.from_tokenizer(tok, self.device, vocab_size=self.model_cfg.vocab_size)
+                self._device_rewards = DeviceRewards(self.reward_funcs, table)
+        return self._device_rewards
 
     def compute_loss(self, model, inputs, return_outputs: bool = False, num_items_in_batch=None):
         """rollout + scoring + rewards + advantages + loss + BACKWARD for one prompt group (the backward the reference
