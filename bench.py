@@ -7,7 +7,7 @@
     python bench.py --impl reference ...        # the reference's CPU path (oracle port) on the host cores
 
 A step = ONE complete GRPO update for one prompt-group per GPU: ViT, prompt prefill, C-token sampled
-rollout of G completions, policy + reference scoring, rewards (host parse + device IoU), group advantage, clipped
+rollout of G completions, policy + reference scoring, rewards (device detokenise + parse + IoU), group advantage, clipped
 loss, full backward and the sharded AdamW step.  Workload = cfg2: Qwen2.5-VL-7B dims (the class the reference
 instantiates, timer1_trainer.py:244), 16 temporal slots of 448x448 -> grid (16,32,32), 4096 vision tokens, prompt
 ~4.2k tokens, G=8, C=200, synthetic uniform uint8 frames, random-init N(0,0.02) bf16 weights, synthetic template rewards.
@@ -49,6 +49,8 @@ def parse_args():
     ap.add_argument("--groups-per-step", type=int, default=2,
                     help="prompt-groups per GPU per optimizer step = gradient_accumulation_steps (2 in scripts/posttrain/train_rl.sh:27)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--reward-route", default="device", choices=["device", "host"],
+                    help="device: template completions are detokenised, parsed and scored on the GPU; host: regex parse on the host")
     ap.add_argument("--no-vit-prefetch", dest="vit_prefetch", action="store_false",
                     help="do not overlap the next step's frozen ViT blocks with this step's optimizer phase")
     ap.add_argument("--phase-times", action="store_true", help="print a per-phase breakdown to stderr")
@@ -180,18 +182,23 @@ def synthetic_prompt(cfg, grid, rank: int, step: int, device):
 
 class TemplateRewards:
     """Completions are overwritten post hoc with template strings (random-init models never emit <answer> tags —
-    SURVEY §0); the strings go through the product's reward path (host regex parse + t1_iou_reward kernel)."""
+    SURVEY §0); the strings go through the product's reward path.  route "device" (default): the templates enter as token
+    ids of a byte-level vocabulary and are detokenised, parsed and scored on the GPU (t1_detokenize -> t1_parse_answers ->
+    t1_iou_reward; nothing is copied back before the loss); route "host": regex parse on the host + t1_iou_reward."""
 
-    def __init__(self, G: int, rank: int):
+    PAD = 256
+
+    def __init__(self, G: int, rank: int, route: str = "device"):
         import numpy as np
 
         self.rows = json.load(open(os.path.join(ROOT, "tests", "golden", "iou_train_2k5.json")))
         self.rng = np.random.default_rng(7 + rank)
         self.G, self.cursor = G, rank
+        if route == "device":
+            self.device = self._device_route      # the attribute Engine.grpo_multi_step looks for
+            self._dr = None
 
-    def __call__(self, completion_ids):
-        from time_r1_b200 import rewards
-
+    def _templates(self):
         row = self.rows[self.cursor % len(self.rows)]
         self.cursor += 1
         dur = row["duration"]
@@ -202,10 +209,36 @@ class TemplateRewards:
                 texts.append(f"<think>unsure</think> {s:.2f} to {e:.2f}")      # malformed: no <answer> block
             else:
                 texts.append(f"<think>the event spans these frames</think><answer>{s:.2f} to {e:.2f}</answer>")
-        r1 = rewards.iou_timestamp_reward_v2(texts, [row["gt"]] * self.G, durations=[dur] * self.G)
-        r2 = rewards.format_reward(texts)
+        return row, dur, texts
+
+    def _device_route(self, completion_ids):
+        import numpy as np
+        import torch
+
+        from time_r1_b200 import rewards
+        from time_r1_b200.detok import DetokTable
+
+        if self._dr is None:
+            table = DetokTable.from_byte_strings([bytes([b]) for b in range(256)] + [b"<|endoftext|>", b"<|im_end|>"], [256, 257],
+                                                 completion_ids.device)
+            self._dr = rewards.DeviceRewards([rewards.iou_timestamp_reward_v2, rewards.format_reward], table)
+        row, dur, texts = self._templates()
+        C = completion_ids.shape[1]
+        ids = np.full((self.G, max(C, max(len(t) for t in texts) + 1)), self.PAD, np.int32)
+        for g, t in enumerate(texts):
+            b = np.frombuffer(t.encode("utf-8"), np.uint8)
+            ids[g, :len(b)] = b
+            ids[g, len(b)] = 257                                               # <|im_end|>, then padding
+        return self._dr(torch.from_numpy(ids).to(completion_ids.device, non_blocking=True), row["gt"], dur)
+
+    def __call__(self, completion_ids):
         import numpy as np
 
+        from time_r1_b200 import rewards
+
+        row, dur, texts = self._templates()
+        r1 = rewards.iou_timestamp_reward_v2(texts, [row["gt"]] * self.G, durations=[dur] * self.G)
+        r2 = rewards.format_reward(texts)
         return np.stack([np.asarray(r1, np.float32), np.asarray(r2, np.float32)], 1)
 
 
@@ -305,7 +338,7 @@ def run_ours(args):
     mw.init_random(seed=0)          # same weights on every rank (data parallel)
     eng = engine.Engine(cfg, mw, run, rank=rank, world_size=world, process_group=pg)
     NG = args.groups_per_step
-    rewards = [TemplateRewards(G, rank * NG + i) for i in range(NG)]
+    rewards = [TemplateRewards(G, rank * NG + i, args.reward_route) for i in range(NG)]
     inputs = [synthetic_prompt(cfg, grid_of(args), rank * NG + i, 0, dev) for i in range(NG)]
     ids, frames_host, grid = inputs[0]
     P = len(ids)
@@ -444,8 +477,10 @@ def run_ours(args):
         "config": {"workload": workload_name(args), "prompt_tokens": P, "vision_tokens": (P - 120), "group_size": G, "groups_per_step": NG,
                    "completion_len": C, "parallelism": f"dp{world}+zero2-sharded-adamw", "l2": "inputs larger than L2 (>=16 GB of weights streamed per pass)"},
         "clocks": clocks,
-        "e2e": {"value": round(e2e_value, 4), "unit": UNIT, "h2d_bytes_per_step": int(NG * (frames_host.numel() + ids.size * 4)), "input": "uint8 frames [2*slots, 3, 448, 448] from pinned host memory -> t1_video_patchify on the device", "d2h_bytes_per_step": int(NG * (G * C * 4 + 4) + 4)},
+        "e2e": {"value": round(e2e_value, 4), "unit": UNIT, "h2d_bytes_per_step": int(NG * (frames_host.numel() + ids.size * 4)), "input": "uint8 frames [2*slots, 3, 448, 448] from pinned host memory -> t1_video_patchify on the device", "d2h_bytes_per_step": int(NG * ((G * C * 4 if args.reward_route == "host" else 0) + 4) + 4),
+                "d2h": "per-group loss + grad norm" + (" + completion ids for the host reward parse" if args.reward_route == "host" else "; completions are detokenised and parsed on the device")},
         "gpu_launches": launches,
+        "reward_route": args.reward_route,
         "hbm_gb": {"max_allocated": round(torch.cuda.max_memory_allocated(dev) / 1e9, 1), "max_reserved": round(torch.cuda.max_memory_reserved(dev) / 1e9, 1),
                    "total": round(torch.cuda.get_device_properties(dev).total_memory / 1e9, 1)},
         "roofline": roofline,
