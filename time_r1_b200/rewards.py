@@ -12,7 +12,7 @@ Two routes, same numbers:
 from __future__ import annotations
 
 import re
-from typing import Optional, Sequence
+from typing import Callable, Optional, Sequence
 
 import numpy as np
 
@@ -124,5 +124,54 @@ class DeviceRewards:
         return torch.stack(cols, dim=1).contiguous()
 
 
-# metric functions of timer1_trainer_ft.py are logging-only host regexes (out of scope)
-metric_funcs_registry: dict = {}
+# ---- logging-only metric functions (main.py:240-376; logged as metrics/<name> by timer1_trainer_ft.py:670-691,790-795,
+# never added to the reward).  Host string logic like the reference's: they see the decoded completions. -----------------
+_THINK_RE = re.compile(r"<think>(.*?)</think>", re.DOTALL)
+_TIMESTEP_RE = re.compile(r"<timestep>\s*(\d+\.?\d*)\s+to\s+(\d+\.?\d*)\s*</timestep>", re.IGNORECASE | re.DOTALL)
+DEFAULT_STRUCTURE_KEYWORDS = ["analyze", "compare", "deduce", "however", "therefore", "because", "step", "observe", "notice",
+                              "identify", "wait"]
+
+
+def extract_think_content(completion: str) -> Optional[str]:
+    """Stripped content of the LAST <think>...</think> block, or None (main.py:240-245)."""
+    blocks = _THINK_RE.findall(completion)
+    return blocks[-1].strip() if blocks else None
+
+
+def _think_metric(completions, count: Callable, weight: float, cap: int) -> list[float]:
+    """weight x min(count(think), cap) per completion; 0.0 when there is no (or an empty) think block."""
+    out = []
+    for c in completions:
+        think = extract_think_content(_text_of(c))
+        out.append(max(0.0, weight * min(count(think), cap)) if think else 0.0)
+    return out
+
+
+def reward_timestep_pair(completions, weight: float = 0.2, max_count: int = 1, **kwargs) -> list[float]:
+    """<timestep> a to b </timestep> pairs inside the think block, capped (main.py:248-275)."""
+    return _think_metric(completions, lambda t: len(_TIMESTEP_RE.findall(t)), weight, max_count)
+
+
+def reward_think_length(completions, weight: float = 0.001, max_length: int = 500, **kwargs) -> list[float]:
+    """Characters of the think block, capped (main.py:278-299)."""
+    return _think_metric(completions, len, weight, max_length)
+
+
+def reward_keyword_usage(completions, keywords: Optional[Sequence[str]] = None, weight: float = 0.1, max_count: int = 2, **kwargs) -> list[float]:
+    """How many of the structure keywords occur in the lower-cased think block, capped (main.py:317-343)."""
+    words = DEFAULT_STRUCTURE_KEYWORDS if keywords is None else keywords
+    return _think_metric(completions, lambda t: sum(1 for w in words if w in t.lower()), weight, max_count)
+
+
+def reward_paragraph_structure(completions, weight: float = 0.05, max_paragraphs: int = 2, **kwargs) -> list[float]:
+    """Non-blank lines of the think block, capped (main.py:346-366)."""
+    return _think_metric(completions, lambda t: sum(1 for p in t.split("\n") if p.strip()), weight, max_paragraphs)
+
+
+# main.py:422-428 (diversity_reward_func is commented out there: it needs rouge_score)
+metric_funcs_registry: dict = {
+    "reward_timestep_pair": reward_timestep_pair,
+    "reward_think_length": reward_think_length,
+    "reward_keyword_usage": reward_keyword_usage,
+    "reward_paragraph_structure": reward_paragraph_structure,
+}

@@ -302,7 +302,7 @@ class TimeR1_Trainer:
             out = np.zeros((G, len(self.reward_funcs)), np.float32)
             for i, rf in enumerate(self.reward_funcs):
                 out[:, i] = np.asarray(rf(prompts=prompts, completions=completions, **cols), np.float32)
-            self._last_completions = completions
+            self._last_completions, self._last_reward_kwargs = completions, dict(prompts=prompts, **cols)
             return out
 
         dr = self._device_reward_path()
@@ -512,9 +512,10 @@ class TimeR1_Trainer_ft(TimeR1_Trainer):
         self._metrics["clip_ratio/region_mean"].append(clip_low + clip_high)
         comps = getattr(self, "_last_completions", None)
         if comps is not None:
-            for mf in self.metric_funcs:
-                vals = mf(completions=comps)
-                self._metrics[f"metrics/{mf.__name__}"].append(float(np.mean(vals)))
+            kw = getattr(self, "_last_reward_kwargs", {})
+            for mf in self.metric_funcs:                      # same protocol as the reward functions (:673-691)
+                vals = np.asarray(mf(completions=comps, **kw), np.float32)
+                self._metrics[f"metrics/{mf.__name__}"].append(float(vals.mean()))
 
 
 # ------------------------------------------------------------------------------------------------
