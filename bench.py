@@ -331,6 +331,8 @@ def run_ours(args):
     run = config.RunConfig(num_generations=args.group_size, max_completion_length=args.completion_len)
     if os.environ.get("T1_SIDE_CTAS"):
         run.side_ctas = int(os.environ["T1_SIDE_CTAS"])
+    if os.environ.get("T1_DECODE_FOLD"):
+        run.decode_fold_norm = os.environ["T1_DECODE_FOLD"] == "1"
     if os.environ.get("T1_DECODE_CTAS"):
         run.decode_ctas = int(os.environ["T1_DECODE_CTAS"])
     G, C = run.num_generations, run.max_completion_length

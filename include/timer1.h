@@ -86,6 +86,21 @@ void t1_stream_gemm_max_ctas(int n);
 int t1_stream_gemm_resnorm(const void* x, long long ldx, const void* W, long long ldw, void* y, long long ldy, int M, int N,
                            int K, void* resid, const void* norm_w, float eps, void* h_out, void* workspace,
                            long long workspace_bytes, cudaStream_t stream);
+/* RMSNorm FOLDED into the two GEMMs around it, no norm kernel and no grid-wide wait (decode chain o_proj -> [residual add,
+ * post-attention norm] -> gate_up and down_proj -> [residual add, next input norm] -> qkv; HF Q25:805-827).
+ * Producer half: y = x W^T is not stored; resid[M, N] += bf16(y) in place, z_out[M, N] = bf16(norm_w[n] * resid[m, n]) and
+ * parts_out[N / 128][MP] (MP = 16 / 32 / 64 for M <= 16 / 32 / 64) = per-row sums of resid^2 over each 128-column slab.
+ * N % 128 == 0; resid / z_out contiguous [M, N]. */
+int t1_stream_gemm_fold(const void* x, long long ldx, const void* W, long long ldw, int M, int N, int K, void* resid,
+                        const void* norm_w, void* z_out, float* parts_out, void* workspace, long long workspace_bytes,
+                        cudaStream_t stream);
+/* Consumer half: y[m, n] = r[m] * sum_k W[n, k] x[m, k] (+ bias[n]) with r[m] = rsqrt(sum_i in_parts[i][m] / K + eps): the
+ * row factor of the RMSNorm is constant along k, so it multiplies the fp32 accumulator in the epilogue; with x = z_out and
+ * in_parts = parts_out of t1_stream_gemm_fold this is W . rmsnorm(resid).  swiglu != 0: N = 2 * I and y is [M, I] as in
+ * t1_stream_gemm_swiglu. */
+int t1_stream_gemm_scaled(const void* x, long long ldx, const void* W, long long ldw, const void* bias, void* y, long long ldy,
+                          int M, int N, int K, int swiglu, const float* in_parts, int in_nparts, float eps, void* workspace,
+                          long long workspace_bytes, cudaStream_t stream);
 /* y[M, I] = silu(x Wg^T) * (x Wu^T), W = [Wg; Wu] ([2I, K]): the decode step's gate_up projection fused with the SwiGLU
  * (HF Q25:611-624) in one weight stream; same arithmetic per element as t1_stream_gemm (bf16) + t1_swiglu (bit-identical when
  * the stream-K cut points coincide, as for the 7B decode shapes).  I % 64 == 0. */

@@ -27,7 +27,7 @@ def close(a, b, atol, rtol, what=""):
 
 
 # ------------------------------------------------------------------ norms
-@pytest.mark.parametrize("T,D", [(7, 256), (130, 1280), (65, 3584), (33, 5120)])
+@pytest.mark.parametrize("T,D", [(7, 256), (130, 1280), (65, 3584), (33, 5120), (1000, 3584), (700, 1280), (333, 8192)])
 def test_rmsnorm_fwd_bwd(T, D):
     from time_r1_b200 import ops
 

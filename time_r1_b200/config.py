@@ -173,6 +173,7 @@ class RunConfig:
     # instead of 7).  Measured neutral on B200 (3.53 vs 3.49 ms per step): what looked like kernel-boundary latency is
     # the finishing-time spread of the 148 streaming CTAs, which the fused tail has to wait out as well.
     decode_fuse_norm: bool = False
+    decode_fold_norm: bool = False      # RMSNorm folded into the GEMMs around it (t1_stream_gemm_fold / _scaled)
     # overlap the prompt rows of the reference-model scoring pass (tensor-bound, independent of the sampled tokens) with the
     # decode (HBM-bound): the decode's weight-streaming GEMMs keep to `decode_ctas` SMs on a high-priority stream, the
     # reference prefill runs on a side stream with its GEMMs capped at `side_ctas` CTAs.  0 = off.

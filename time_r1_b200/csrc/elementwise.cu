@@ -101,65 +101,114 @@ norm_fwd_kernel(const bf16* x, const bf16* __restrict__ delta, bf16* x_out, cons
 
 // RMSNorm backward. Each CTA walks rows r = blockIdx.x, +gridDim.x, ...; keeps fp32 partial dw in registers and
 // flushes with one atomicAdd per column at the end.  dx_out = (dres ? dres : 0) + dx.
-__global__ void __launch_bounds__(256)
+// HBM-bound (3 reads + 1 write of [T, D] bf16).  A row is a serial chain load -> block reduction -> store, so the rows in
+// flight per SM set the bandwidth: operands stay packed (bf16) in registers, NIT is the compile-time number of 8-wide
+// vectors per thread (D = 3584 needs 2, not the 4 of the D <= 8192 worst case), two CTAs share an SM, each with the next
+// row's x / dy already loading while the current row reduces, and the two row sums (x^2, g*w*x) share ONE barrier.
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  float2 t;
+  t = unpack_bf16x2(u.x); f[0] = t.x; f[1] = t.y;
+  t = unpack_bf16x2(u.y); f[2] = t.x; f[3] = t.y;
+  t = unpack_bf16x2(u.z); f[4] = t.x; f[5] = t.y;
+  t = unpack_bf16x2(u.w); f[6] = t.x; f[7] = t.y;
+}
+
+template <int NIT>
+__global__ void __launch_bounds__(256, NIT <= 2 ? 2 : 1)
 rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ w,
                    const bf16* __restrict__ dres, bf16* __restrict__ dx, float* __restrict__ dw, int T, int D,
                    float eps) {
-  __shared__ float red[33];
+  __shared__ float red[2][2][8];               // [row parity][sum kind][warp]
   const int nv = D >> 3;
-  float dwacc[4][8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+  float dwacc[NIT][8];
+  uint4 wq[NIT], xq[NIT], gq[NIT];
 #pragma unroll
-  for (int it = 0; it < 4; ++it)
+  for (int it = 0; it < NIT; ++it) {
+    const int i = threadIdx.x + it * 256;
 #pragma unroll
     for (int j = 0; j < 8; ++j) dwacc[it][j] = 0.f;
-  float wv[4][8];
-#pragma unroll
-  for (int it = 0; it < 4; ++it) {
-    const int i = threadIdx.x + it * 256;
-    if (i < nv) load8(w + i * 8, wv[it]);
+    wq[it] = i < nv ? *reinterpret_cast<const uint4*>(w + i * 8) : zero4;
   }
-  for (size_t row = blockIdx.x; row < (size_t)T; row += gridDim.x) {
-    float xv[4][8], gv[4][8];
+  size_t row = blockIdx.x;
+  if (row < (size_t)T) {
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int i = threadIdx.x + it * 256;
+      xq[it] = i < nv ? *reinterpret_cast<const uint4*>(x + row * D + i * 8) : zero4;
+      gq[it] = i < nv ? *reinterpret_cast<const uint4*>(dy + row * D + i * 8) : zero4;
+    }
+  }
+  for (int n = 0; row < (size_t)T; row += gridDim.x, ++n) {
+    // next row's operands (and this row's residual gradient) start loading before the reduction below
+    const size_t nrow = row + gridDim.x;
+    uint4 xn[NIT], gn[NIT], rq[NIT];
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int i = threadIdx.x + it * 256;
+      const bool on = i < nv;
+      rq[it] = (dres && on) ? *reinterpret_cast<const uint4*>(dres + row * D + i * 8) : zero4;
+      xn[it] = (on && nrow < (size_t)T) ? *reinterpret_cast<const uint4*>(x + nrow * D + i * 8) : zero4;
+      gn[it] = (on && nrow < (size_t)T) ? *reinterpret_cast<const uint4*>(dy + nrow * D + i * 8) : zero4;
+    }
     float sq = 0.f, dot = 0.f;
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      const int i = threadIdx.x + it * 256;
-      if (i < nv) {
-        load8(x + row * D + i * 8, xv[it]);
-        load8(dy + row * D + i * 8, gv[it]);
+    for (int it = 0; it < NIT; ++it) {
+      float xv[8], gv[8], wv[8];
+      unpack8(xq[it], xv);
+      unpack8(gq[it], gv);
+      unpack8(wq[it], wv);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          sq += xv[it][j] * xv[it][j];
-          dot += gv[it][j] * wv[it][j] * xv[it][j];
-        }
+      for (int j = 0; j < 8; ++j) {             // padding vectors are zero: they add nothing
+        sq += xv[j] * xv[j];
+        dot += gv[j] * wv[j] * xv[j];
       }
     }
-    const float rstd = rsqrtf(block_sum(sq, red) / (float)D + eps);
-    const float c = block_sum(dot, red) * rstd * rstd / (float)D;  // mean(g*w*xhat) * rstd, with xhat = x*rstd
+    sq = warp_sum(sq);
+    dot = warp_sum(dot);
+    float(*rb)[8] = red[n & 1];                  // parity buffers: the barrier of row n+1 orders reuse at row n+2
+    if (lane == 0) {
+      rb[0][wid] = sq;
+      rb[1][wid] = dot;
+    }
+    __syncthreads();
+    sq = 0.f;
+    dot = 0.f;
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
+    for (int k = 0; k < 8; ++k) {
+      sq += rb[0][k];
+      dot += rb[1][k];
+    }
+    const float rstd = rsqrtf(sq / (float)D + eps);
+    const float c = dot * rstd * rstd / (float)D;  // mean(g*w*xhat) * rstd, with xhat = x*rstd
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
       const int i = threadIdx.x + it * 256;
-      if (i < nv) {
-        float o[8];
+      float xv[8], gv[8], wv[8], o[8];
+      unpack8(xq[it], xv);
+      unpack8(gq[it], gv);
+      unpack8(wq[it], wv);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float xhat = xv[it][j] * rstd;
-          dwacc[it][j] += gv[it][j] * xhat;
-          o[j] = rstd * (gv[it][j] * wv[it][j]) - xv[it][j] * rstd * c;
-        }
-        if (dres) {
-          float r[8];
-          load8(dres + row * D + i * 8, r);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] += r[j];
-        }
-        store8(dx + row * D + i * 8, o);
+      for (int j = 0; j < 8; ++j) {
+        const float xhat = xv[j] * rstd;
+        dwacc[it][j] += gv[j] * xhat;
+        o[j] = rstd * (gv[j] * wv[j]) - xv[j] * rstd * c;
       }
+      if (dres) {
+        float r[8];
+        unpack8(rq[it], r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += r[j];
+      }
+      if (i < nv) store8(dx + row * D + i * 8, o);
+      xq[it] = xn[it];
+      gq[it] = gn[it];
     }
   }
   if (dw) {
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
+    for (int it = 0; it < NIT; ++it) {
       const int i = threadIdx.x + it * 256;
       if (i < nv)
 #pragma unroll
@@ -468,9 +517,18 @@ extern "C" int t1_rmsnorm_bwd(const void* dy, const void* x, const void* w, cons
                               int T, int D, float eps, cudaStream_t stream) {
   if (T == 0) return T1_OK;
   T1_CHECK_ARG(T > 0 && D > 0 && D % 8 == 0 && D <= 8192, "t1_rmsnorm_bwd: D=%d must be a multiple of 8 and <= 8192", D);
-  const int grid = T < 4 * t1_num_sms() ? T : 4 * t1_num_sms();
-  rmsnorm_bwd_kernel<<<grid, 256, 0, stream>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w, (const bf16*)dres,
-                                               (bf16*)dx, dw, T, D, eps);
+  const int nit = (D / 8 + 255) / 256;
+  const int per_sm = nit <= 2 ? 2 : 1;           // resident CTAs per SM (register budget, see the kernel)
+  const int grid = T < per_sm * t1_num_sms() ? T : per_sm * t1_num_sms();
+  if (nit <= 1)
+    rmsnorm_bwd_kernel<1><<<grid, 256, 0, stream>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w, (const bf16*)dres,
+                                                    (bf16*)dx, dw, T, D, eps);
+  else if (nit == 2)
+    rmsnorm_bwd_kernel<2><<<grid, 256, 0, stream>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w, (const bf16*)dres,
+                                                    (bf16*)dx, dw, T, D, eps);
+  else
+    rmsnorm_bwd_kernel<4><<<grid, 256, 0, stream>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w, (const bf16*)dres,
+                                                    (bf16*)dx, dw, T, D, eps);
   T1_CUDA_LAUNCH_CHECK("t1_rmsnorm_bwd");
   return T1_OK;
 }

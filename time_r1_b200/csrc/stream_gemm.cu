@@ -23,7 +23,7 @@ constexpr int SG_BM = 128;              // weight rows per slab
 constexpr int SG_BK = 64;               // 64 bf16 = one 128-byte swizzle row
 constexpr int SG_W_BYTES = SG_BM * SG_BK * 2;
 constexpr int SG_MAX_STAGES = 24;
-constexpr int SG_HEADER = 1024;         // barriers + tmem pointer + flags
+constexpr int SG_HEADER = 2048;         // barriers + tmem pointer + flags (0..511), folded-norm row factors and scratch (512..1535)
 constexpr int SG_THREADS = 192;
 constexpr int SG_COUNTER_BYTES = 65536; // slab counters at the head of the workspace (N <= 2M rows)
 
@@ -72,6 +72,18 @@ struct SgParams {
   int total_items;    // slabs * segs
   int* sched_counter; // zero on entry, reset by the CTA that performs the last fetch
   unsigned long long* dbg;   // optional [4] globaltimer stamps of CTA 0: start, weights issued, dependency resolved, done
+  // RMSNorm folded into the GEMMs on either side of it (no norm kernel, no grid-wide wait):
+  //   producer (t1_stream_gemm_fold): a finished slab adds its y columns to the residual stream h, writes
+  //   z = bf16(norm_w * h) -- the operand the NEXT GEMM streams against -- and the slab's per-row sum of h^2;
+  //   consumer (t1_stream_gemm_scaled): x = z; the per-row factor r[m] = rsqrt(sum_slabs(parts) / K + eps), which is
+  //   constant along k, multiplies the fp32 accumulator in the epilogue:  r[m] * sum_k W[n,k] z[m,k] = W . rmsnorm(h).
+  bf16* fold_x;         // residual stream [M, N], updated in place (nullptr: plain epilogue)
+  const bf16* fold_w;   // norm weight [N]
+  bf16* fold_z;         // [M, N]
+  float* fold_parts;    // [slabs][MP] per-row partial sums of h^2 (each written by exactly one CTA: deterministic)
+  const float* in_parts;  // consumer: [in_nparts][MP] (nullptr: x is already normalised)
+  int in_nparts;
+  float in_eps;
 };
 #ifdef T1_SG_DBG
 __device__ unsigned long long g_cta_t[3][512];     // per-CTA start / first-data / end stamps of the last launch
@@ -223,6 +235,31 @@ stream_gemm_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_const
     const int q = warp_idx & 3;
     const int et = (warp_idx - 2) * 32 + lane;   // 0..127
     const int r = q * 32 + lane;                 // weight row inside the slab == TMEM lane
+    float* r_s = reinterpret_cast<float*>(smem + 512);   // [MP] row factors of a folded RMSNorm (header bytes 512..767)
+    if (p.in_parts) {
+      // all 128 threads fetch (one L2 round trip for <= 4 independent loads each), then MP threads finish in a fixed order
+      float* r_tmp = reinterpret_cast<float*>(smem + 1024);   // [128] (header bytes 1024..1535)
+      constexpr int GROUPS = 128 / MP;
+      const int m = et % MP, g0 = et / MP;
+      float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+      const int np = p.in_nparts;
+      int i = g0;
+      for (; i + 3 * GROUPS < np; i += 4 * GROUPS) {
+        const float a = __ldcg(p.in_parts + i * MP + m), b = __ldcg(p.in_parts + (i + GROUPS) * MP + m);
+        const float c = __ldcg(p.in_parts + (i + 2 * GROUPS) * MP + m), d = __ldcg(p.in_parts + (i + 3 * GROUPS) * MP + m);
+        v0 += a; v1 += b; v2 += c; v3 += d;
+      }
+      for (; i < np; i += GROUPS) v0 += __ldcg(p.in_parts + i * MP + m);
+      r_tmp[et] = (v0 + v1) + (v2 + v3);
+      epi_bar_sync();
+      if (et < MP) {
+        float ssq = 0.f;
+#pragma unroll
+        for (int g = 0; g < GROUPS; ++g) ssq += r_tmp[g * MP + et];
+        r_s[et] = rsqrtf(ssq / (float)p.K + p.in_eps);
+      }
+      epi_bar_sync();
+    }
     int it = 0;
     for (int u = u0; u < u1; ++it) {
       const int slab = u / KB, kb0 = u - slab * KB;
@@ -275,7 +312,44 @@ stream_gemm_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_const
           }
         }
       }
-      if (p.swiglu) {
+      if (finish && p.in_parts) {
+#pragma unroll
+        for (int m = 0; m < MP; ++m) v[m] = __float_as_uint(__uint_as_float(v[m]) * r_s[m]);
+      }
+      if (p.fold_x) {
+        // residual add + norm-weight scaling + per-row sum of squares of this slab's 128 columns (N % 128 == 0)
+        if (finish) {
+          const float gw = __bfloat162float(p.fold_w[n]);
+          bf16 xold[MP];
+#pragma unroll
+          for (int m = 0; m < MP; ++m)             // all residual loads in flight together (one L2 round trip, not MP)
+            xold[m] = m < p.M ? p.fold_x[(long long)m * p.N + n] : __float2bfloat16(0.f);
+          float sq[MP];
+#pragma unroll
+          for (int m = 0; m < MP; ++m) {
+            sq[m] = 0.f;
+            if (m < p.M) {
+              const float y = __bfloat162float(__float2bfloat16(__uint_as_float(v[m])));
+              const bf16 hn = __float2bfloat16(__bfloat162float(xold[m]) + y);  // hidden = residual + hidden in bf16 (HF Q25:805-827)
+              p.fold_x[(long long)m * p.N + n] = hn;
+              const float hf = __bfloat162float(hn);
+              p.fold_z[(long long)m * p.N + n] = __float2bfloat16(gw * hf);
+              sq[m] = hf * hf;
+            }
+          }
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1)   // MP independent butterflies: the shuffles of different rows overlap
+#pragma unroll
+            for (int m = 0; m < MP; ++m) sq[m] += __shfl_xor_sync(0xffffffffu, sq[m], off);
+          if (lane == 0) {
+#pragma unroll
+            for (int m = 0; m < MP; ++m) xs[(warp_idx - 2) * MP + m] = sq[m];
+          }
+          epi_bar_sync();
+          if (et < MP) p.fold_parts[slab * MP + et] = xs[et] + xs[MP + et] + xs[2 * MP + et] + xs[3 * MP + et];
+          epi_bar_sync();                          // xs is rewritten by the next finished slab
+        }
+      } else if (p.swiglu) {
         // lanes 0..63 hold the gate rows, lanes 64..127 the matching up rows: hand the up values over through shared
         // memory, then y = silu(gate) * up on the bf16-rounded GEMM outputs (bit-identical to gemm -> t1_swiglu)
         if (finish) {
@@ -798,6 +872,12 @@ struct SgTail {
   const void* norm_w = nullptr;
   void* h_out = nullptr;
   float eps = 0.f;
+  // folded RMSNorm (see SgParams): producer side / consumer side
+  void* fold_resid = nullptr;
+  void* fold_z = nullptr;
+  float* fold_parts = nullptr;
+  const float* in_parts = nullptr;
+  int in_nparts = 0;
 };
 
 static int stream_gemm_impl(const void* x, long long ldx, const void* W, long long ldw, const void* bias, void* y,
@@ -811,7 +891,7 @@ static int stream_gemm_impl(const void* x, long long ldx, const void* W, long lo
   const int MP = M <= 16 ? 16 : (M <= 32 ? 32 : 64);
   const int stage_bytes = SG_W_BYTES + MP * SG_BK * 2;
   const int half_n = N / 2;
-  const int xs_bytes = swiglu ? MP * 64 * 4 : 0;
+  const int xs_bytes = swiglu ? MP * 64 * 4 : (tail.fold_resid ? 4 * MP * 4 : 0);
   if (swiglu) T1_CHECK_ARG(N % 128 == 0 && !out_f32, "t1_stream_gemm_swiglu: N = 2*I with I %% 64 == 0 and bf16 output required (N=%d)", N);
   if (g_stages < 0) {
     g_stages = env_int("T1_STREAM_STAGES", 0);
@@ -862,6 +942,14 @@ static int stream_gemm_impl(const void* x, long long ldx, const void* W, long lo
   p.tail_w = reinterpret_cast<const bf16*>(tail.norm_w);
   p.tail_h = reinterpret_cast<bf16*>(tail.h_out);
   p.tail_eps = tail.eps;
+  p.fold_x = reinterpret_cast<bf16*>(tail.fold_resid);
+  p.fold_w = reinterpret_cast<const bf16*>(tail.fold_resid ? tail.norm_w : nullptr);
+  p.fold_z = reinterpret_cast<bf16*>(tail.fold_z);
+  p.fold_parts = tail.fold_parts;
+  p.in_parts = tail.in_parts;
+  p.in_nparts = tail.in_nparts;
+  p.in_eps = tail.eps;
+  const bool folded = tail.fold_resid || tail.in_parts;       // only the statically split kernel carries the folded norm
   p.segs = 1;
   p.seg_k = kblocks;
   p.total_items = slabs;
@@ -879,7 +967,7 @@ static int stream_gemm_impl(const void* x, long long ldx, const void* W, long lo
   // pay off when there are many slabs per SM (lm_head: last CTA done at 177 us vs 187 us static); splitting slabs into
   // k-segments does not (gate_up 57 vs 50 us, down 68 vs 30 us: per-item partial tiles + the segment reduction cost more
   // than the balance gains), so mode 1 only takes GEMMs with >= 4 slabs per SM.  Mode 2 forces the k-split (experiments).
-  if (g_dynamic && !tail.resid && (g_dynamic >= 2 || slabs >= 4 * t1_num_sms())) {
+  if (g_dynamic && !tail.resid && !folded && (g_dynamic >= 2 || slabs >= 4 * t1_num_sms())) {
     // items = (slab, k-segment): at most 8 per SM, segments of >= 8 k-blocks (128 KB of weights)
     const int max_items = 8 * t1_num_sms();
     int segs = 1;
@@ -944,6 +1032,40 @@ extern "C" int t1_stream_gemm_resnorm(const void* x, long long ldx, const void* 
   t.h_out = h_out;
   t.eps = eps;
   return stream_gemm_impl(x, ldx, W, ldw, nullptr, y, ldy, M, N, K, 0, 0, workspace, workspace_bytes, stream, t);
+}
+
+// RMSNorm folded into the two GEMMs around it (decode chain: o_proj -> [residual, post-attention norm] -> gate_up and
+// down_proj -> [residual, next input norm] -> qkv; HF Q25:805-827).  Producer half:  y = x W^T is NOT stored; instead
+//   resid[M, N] += bf16(y)  (in place),  z_out[M, N] = bf16(norm_w[n] * resid[m, n]),
+//   parts_out[slab][MP] = sum over the slab's 128 columns of resid[m, n]^2   (MP = 16 / 32 / 64 for M <= 16 / 32 / 64),
+// so the consumer (t1_stream_gemm_scaled with x = z_out, in_parts = parts_out, in_nparts = N / 128) needs no norm kernel
+// in between.  N % 128 == 0; resid / z_out contiguous [M, N].
+extern "C" int t1_stream_gemm_fold(const void* x, long long ldx, const void* W, long long ldw, int M, int N, int K, void* resid,
+                                   const void* norm_w, void* z_out, float* parts_out, void* workspace,
+                                   long long workspace_bytes, cudaStream_t stream) {
+  T1_CHECK_ARG(resid && norm_w && z_out && parts_out, "t1_stream_gemm_fold: null pointer");
+  T1_CHECK_ARG(N % 128 == 0, "t1_stream_gemm_fold: N=%d must be a multiple of 128", N);
+  SgTail t;
+  t.fold_resid = resid;
+  t.norm_w = norm_w;
+  t.fold_z = z_out;
+  t.fold_parts = parts_out;
+  return stream_gemm_impl(x, ldx, W, ldw, nullptr, z_out /*unused*/, N, M, N, K, 0, 0, workspace, workspace_bytes, stream, t);
+}
+
+// Consumer half:  y[m, n] = r[m] * sum_k W[n, k] x[m, k] (+ bias[n]),  r[m] = rsqrt(sum_i in_parts[i][m] / K + eps),
+// i.e. W . rmsnorm(h) when x = norm_w * h came from t1_stream_gemm_fold.  swiglu != 0: N = 2 * I, output [M, I] as
+// t1_stream_gemm_swiglu.
+extern "C" int t1_stream_gemm_scaled(const void* x, long long ldx, const void* W, long long ldw, const void* bias, void* y,
+                                     long long ldy, int M, int N, int K, int swiglu, const float* in_parts, int in_nparts,
+                                     float eps, void* workspace, long long workspace_bytes, cudaStream_t stream) {
+  T1_CHECK_ARG(in_parts && in_nparts > 0, "t1_stream_gemm_scaled: in_parts required");
+  T1_CHECK_ARG(!swiglu || (N % 128 == 0), "t1_stream_gemm_scaled: swiglu needs N = 2*I with I %% 64 == 0");
+  SgTail t;
+  t.in_parts = in_parts;
+  t.in_nparts = in_nparts;
+  t.eps = eps;
+  return stream_gemm_impl(x, ldx, W, ldw, bias, y, ldy, M, N, K, 0, swiglu ? 1 : 0, workspace, workspace_bytes, stream, t);
 }
 
 #ifdef T1_SG_DBG

@@ -465,6 +465,7 @@ class Engine:
             act=torch.empty((B, cfg.intermediate_size), device=d, dtype=BF16),
             down=torch.empty((B, cfg.hidden_size), device=d, dtype=BF16),
             hN=torch.empty((B, cfg.hidden_size), device=d, dtype=BF16),
+            fold_parts=torch.zeros((2, max(1, cfg.hidden_size // 128), 64), device=d, dtype=F32),
             logits=torch.empty((B, cfg.vocab_size), device=d, dtype=F32),
             step=torch.zeros(1, device=d, dtype=I32), next_ids=torch.zeros(B, device=d, dtype=I32),
             finished=torch.zeros(B, device=d, dtype=I32), out_ids=torch.zeros((B, C), device=d, dtype=I32),
@@ -525,8 +526,33 @@ class Engine:
             s = stream_ptr()
             ops.gather_rows(self.p("model.embed_tokens.weight"), st["next_ids"], out=x)
             fuse_norm = self.run.decode_fuse_norm and cfg.hidden_size % 8 == 0
+            # folded norms: the o / down GEMM epilogues update the residual stream and emit z = norm_w * resid plus per-slab
+            # row sums of squares; the next GEMM streams against z and applies the row factor in its epilogue
+            fold = (self.run.decode_fold_norm and not fuse_norm and self.run.decode_attn == "cluster" and cfg.hidden_size % 128 == 0
+                    and cfg.intermediate_size % 64 == 0)
+            D = cfg.hidden_size
+            fp = st["fold_parts"]
             for l in range(L):
                 pre = f"model.layers.{l}."
+                if fold:
+                    last = l == L - 1
+                    if l == 0:
+                        ops.rmsnorm(x, self.p(pre + "input_layernorm.weight"), eps, out=h)
+                        ops.stream_gemm(h, self.p(pre + "self_attn.qkv.weight"), ws, out=qkv, bias=self.p(pre + "self_attn.qkv.bias"))
+                    else:
+                        ops.stream_gemm_scaled(h, self.p(pre + "self_attn.qkv.weight"), ws, fp[1], D // 128, eps, out=qkv,
+                                               bias=self.p(pre + "self_attn.qkv.bias"))
+                    call("t1_decode_attn_cluster", ptr(qkv), qkv.stride(0), ptr(tab[l]), st["kv_maps"][l].ctypes.data, n, G, Hq, Hkv, hd,
+                         st["cpad"], ptr(st["step"]), ptr(attn), attn.stride(0), scale, 0, s)
+                    ops.stream_gemm_fold(attn, self.p(pre + "self_attn.o_proj.weight"), ws, x,
+                                         self.p(pre + "post_attention_layernorm.weight"), h, fp[0])
+                    ops.stream_gemm_scaled(h, self.p(pre + "mlp.gate_up.weight"), ws, fp[0], D // 128, eps, out=act, swiglu=True)
+                    if last:      # the final norm feeds the dynamically scheduled lm_head GEMM: kept as a kernel
+                        ops.stream_gemm(act, self.p(pre + "mlp.down_proj.weight"), ws, out=down)
+                    else:
+                        ops.stream_gemm_fold(act, self.p(pre + "mlp.down_proj.weight"), ws, x,
+                                             self.p(f"model.layers.{l + 1}.input_layernorm.weight"), h, fp[1])
+                    continue
                 if l == 0 or not fuse_norm:
                     ops.rmsnorm(x, self.p(pre + "input_layernorm.weight"), eps, delta=down if (l > 0 and not fuse_norm) else None, out=h)
                 ops.stream_gemm(h, self.p(pre + "self_attn.qkv.weight"), ws, out=qkv, bias=self.p(pre + "self_attn.qkv.bias"))

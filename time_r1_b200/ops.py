@@ -177,6 +177,35 @@ def stream_gemm_resnorm(x, w, workspace, resid, norm_w, eps, h_out, out=None):
     return out
 
 
+def stream_gemm_fold(x, w, workspace, resid, norm_w, z_out, parts_out):
+    """resid += bf16(x @ w^T) in place; z_out = bf16(norm_w * resid); parts_out[N/128, MP] = per-row partial sums of
+    resid^2 — the producer half of an RMSNorm folded into the GEMMs around it (see stream_gemm_scaled)."""
+    M, K = x.shape
+    N = w.shape[0]
+    MP = 16 if M <= 16 else (32 if M <= 32 else 64)
+    assert x.stride(1) == 1 and w.stride(1) == 1 and w.shape[1] == K and N % 128 == 0
+    assert resid.shape == (M, N) and resid.is_contiguous() and z_out.shape == (M, N) and z_out.is_contiguous()
+    assert parts_out.dtype == F32 and parts_out.is_contiguous() and parts_out.numel() >= (N // 128) * MP
+    call("t1_stream_gemm_fold", ptr(x), x.stride(0), ptr(w), w.stride(0), M, N, K, ptr(resid), ptr(norm_w), ptr(z_out),
+         ptr(parts_out), ptr(workspace), workspace.numel(), stream_ptr())
+    return z_out
+
+
+def stream_gemm_scaled(z, w, workspace, parts, n_parts, eps, out=None, bias=None, swiglu=False):
+    """out = rmsnorm-row-factor * (z @ w^T) (+bias) [then SwiGLU]: the consumer half of a folded RMSNorm; z / parts come
+    from stream_gemm_fold (n_parts = hidden / 128)."""
+    M, K = z.shape
+    N = w.shape[0]
+    cols = N // 2 if swiglu else N
+    assert z.stride(1) == 1 and w.stride(1) == 1 and w.shape[1] == K and parts.dtype == F32
+    if out is None:
+        out = torch.empty((M, cols), device=z.device, dtype=BF16)
+    assert out.shape == (M, cols) and out.stride(1) == 1 and out.dtype == BF16
+    call("t1_stream_gemm_scaled", ptr(z), z.stride(0), ptr(w), w.stride(0), ptr(bias), ptr(out), out.stride(0), M, N, K,
+         1 if swiglu else 0, ptr(parts), int(n_parts), float(eps), ptr(workspace), workspace.numel(), stream_ptr())
+    return out
+
+
 def linear(x, w, out=None, bias=None, accumulate=False, out_dtype=BF16):
     """Dispatch on the row count: <= 64 rows stream the weights (HBM-bound), otherwise the tcgen05 tile kernel."""
     if x.shape[0] <= 64 and w.shape[0] % 16 == 0 and x.shape[1] % 32 == 0 and (bias is None or bias.dtype == BF16):

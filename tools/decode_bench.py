@@ -50,6 +50,8 @@ def main():
         lib.load().t1_stream_gemm_max_ctas(int(os.environ["T1_BENCH_MAX_CTAS"]))
     for impl, pdl, stages, ctas in variants:
         run = config.RunConfig(num_generations=G, max_completion_length=C, beta=0.0, decode_impl=impl, decode_pdl=pdl)
+        if os.environ.get("T1_DECODE_FOLD"):
+            run.decode_fold_norm = os.environ["T1_DECODE_FOLD"] == "1"
         eng = engine.Engine.__new__(engine.Engine)      # decode only: skip the optimizer-state allocation
         eng.cfg, eng.w, eng.run, eng.dev = cfg, mw, run, dev
         eng.ref = None
