@@ -78,7 +78,14 @@ norm_fwd_kernel(const bf16* x, const bf16* __restrict__ delta, bf16* x_out, cons
     }
     rstd = rsqrtf(block_sum(var, red) / (float)D + eps);
   } else {
-    rstd = rsqrtf(block_sum(sq, red) / (float)D + eps);
+    // one barrier instead of block_sum's three: the CTA owns one row, so `red` is written once
+    sq = warp_sum(sq);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sq;
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k];       // blockDim.x == 256
+    rstd = rsqrtf(t / (float)D + eps);
   }
 #pragma unroll
   for (int it = 0; it < 4; ++it) {
