@@ -421,16 +421,21 @@ def run_ours(args):
         print(json.dumps({"ncu_range": "one step: eager launches + decode replays 0 and C-2", "decode_replays_per_step": C - 1,
                           "launches_per_decode_step": eng._last_decode_state["launches_per_step"]}), flush=True)
         return
-    if args.phase_times and rank == 0:
+    # the diagnostic steps run on EVERY rank (a step contains the optimizer's reduce-scatter / all-gather: a step taken by
+    # rank 0 alone would leave the other ranks' collectives unmatched and hang the job); only rank 0 prints
+    if args.phase_times:
         tm = {}
         one_step(args.warmup, False, timers=tm)
-        print("[phase ms]", json.dumps({k: round(v, 1) for k, v in engine.finish_timers(tm).items()}), file=sys.stderr)
-    if args.kernel_times and rank == 0:
+        phases = engine.finish_timers(tm)
+        if rank == 0:
+            print("[phase ms]", json.dumps({k: round(v, 1) for k, v in phases.items()}), file=sys.stderr)
+    if args.kernel_times:
         lib.CALL_PROFILER.start()
         one_step(args.warmup + 1, False)
         lib.CALL_PROFILER.stop()
         summ = lib.CALL_PROFILER.summary()
-        print("[kernel ms, eager part of one step]", json.dumps({k: [v[0], round(v[1], 2)] for k, v in summ.items()}), file=sys.stderr)
+        if rank == 0:
+            print("[kernel ms, eager part of one step]", json.dumps({k: [v[0], round(v[1], 2)] for k, v in summ.items()}), file=sys.stderr)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
