@@ -131,6 +131,7 @@ class FragmentTokenizer:
     """Byte-level vocabulary for the toy model (2043 ordinary ids + eos/pad): ids 0..255 are the raw bytes, the rest are
     whole template answers, so random completions produce parsable and unparsable texts, with and without the format."""
     eos_token_id = 2043
+    is_byte_level_bpe = True          # batch_decode below IS the byte-table walk (detok.DetokTable.supports)
 
     def __init__(self):
         from time_r1_b200.detok import DetokTable, byte_level_alphabet

@@ -73,3 +73,28 @@ def test_token_bytes_falls_back_to_utf8_for_chars_outside_the_alphabet():
     from time_r1_b200.detok import token_bytes
 
     assert token_bytes("Ġto") == b" to" and token_bytes("<日本>") == "<日本>".encode() and token_bytes("Ċ") == b"\n"
+
+
+def test_supports_only_byte_level_tokenizers_without_cleanup():
+    from transformers import PreTrainedTokenizerFast
+
+    from time_r1_b200.detok import DetokTable
+
+    tok = _byte_level_tokenizer()
+    hf = PreTrainedTokenizerFast(tokenizer_object=tok, eos_token="<|im_end|>", clean_up_tokenization_spaces=False)
+    assert DetokTable.supports(hf)
+    assert DetokTable.supports(type("Processor", (), {"tokenizer": hf})())            # an AutoProcessor holds the tokenizer
+    cleaned = PreTrainedTokenizerFast(tokenizer_object=tok, eos_token="<|im_end|>", clean_up_tokenization_spaces=True)
+    assert not DetokTable.supports(cleaned)
+
+    from tokenizers import Tokenizer, decoders, models
+
+    wp = Tokenizer(models.WordPiece(vocab={"[UNK]": 0, "a": 1, "##b": 2}, unk_token="[UNK]"))
+    wp.decoder = decoders.WordPiece()
+    assert not DetokTable.supports(PreTrainedTokenizerFast(tokenizer_object=wp, clean_up_tokenization_spaces=False))
+
+    class Stub:                                   # the trainer tests' stub: decodes by template, no vocabulary
+        def batch_decode(self, ids, skip_special_tokens=True):
+            return []
+
+    assert not DetokTable.supports(Stub()) and not DetokTable.supports(None)

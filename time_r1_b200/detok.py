@@ -70,6 +70,22 @@ class DetokTable:
         return t.to(device) if device is not None else t
 
     @staticmethod
+    def supports(tokenizer) -> bool:
+        """True when batch_decode of this tokenizer IS the table walk: a byte-level BPE decoder (tokenizers `ByteLevel`, or a
+        tokenizer that declares `is_byte_level_bpe = True`), a readable vocabulary and no post-hoc clean-up of the decoded
+        string (`clean_up_tokenization_spaces`, off for Qwen2 / Qwen2.5-VL)."""
+        tok = getattr(tokenizer, "tokenizer", tokenizer)
+        if tok is None or not (hasattr(tok, "get_vocab") and hasattr(tok, "all_special_ids")):
+            return False
+        if getattr(tok, "clean_up_tokenization_spaces", False):
+            return False
+        if getattr(tok, "is_byte_level_bpe", False):
+            return True
+        backend = getattr(tok, "backend_tokenizer", None)
+        decoder = getattr(backend, "decoder", None)
+        return type(decoder).__name__ == "ByteLevel"
+
+    @staticmethod
     def from_tokenizer(tokenizer, device=None, vocab_size: Optional[int] = None) -> "DetokTable":
         """Build the table from an HF tokenizer (or a processor holding one) whose decoder is byte-level BPE.
         ids without a vocabulary entry (the padding of the embedding matrix) decode to nothing."""

@@ -313,17 +313,17 @@ class TimeR1_Trainer:
 
     def _device_reward_path(self):
         """rewards.DeviceRewards when every reward function is one of the registry's, the tokenizer is byte-level BPE
-        with a readable vocabulary and nothing else needs the decoded strings (metric functions, `device_rewards=False`
+        with a readable vocabulary and no string clean-up (detok.DetokTable.supports) and nothing else needs the decoded strings (metric functions, `device_rewards=False`
         in the arguments); None otherwise -> the host protocol of timer1_trainer.py:642-698."""
         if not hasattr(self, "_device_rewards"):
             self._device_rewards = None
             from .rewards import DeviceRewards
 
+            from .detok import DetokTable
+
             tok = getattr(self.processing_class, "tokenizer", self.processing_class)
             if (getattr(self.args, "device_rewards", True) and not self.metric_funcs and DeviceRewards.supports(self.reward_funcs)
-                    and hasattr(tok, "get_vocab") and hasattr(tok, "all_special_ids")):
-                from .detok import DetokTable
-
+                    and DetokTable.supports(tok)):
                 table = DetokTable.from_tokenizer(tok, self.device, vocab_size=self.model_cfg.vocab_size)
                 self._device_rewards = DeviceRewards(self.reward_funcs, table)
         return self._device_rewards
