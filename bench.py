@@ -303,7 +303,8 @@ def decode_step_microbench(eng, Ps, G: int, C: int):
     st["next_ids"].copy_(snap[0]); st["finished"].copy_(snap[1]); st["out_ids"].copy_(snap[2])
     ts.sort()
     ms = ts[len(ts) // 2]
-    return {"bound": "hbm", "kernel": "captured decode step (stream_gemm_kernel x%d + decode_attn_tc x%d + norms + sampler)" % (4 * L + 1, L),
+    return {"bound": "hbm", "kernel": "captured decode step (stream_gemm_kernel x%d%s + decode_attn_tc x%d + sampler)" % (
+                4 * L + 1, " with the RMSNorms folded into their epilogues" if eng.run.decode_fold_norm else " + norm kernels", L),
             "launches": st["launches_per_step"], "weight_bytes": w_bytes, "kv_bytes": kv_bytes, "ms": round(ms, 4),
             "achieved": round((w_bytes + kv_bytes) / ms / 1e6, 1), "unit": "GB/s"}
 
