@@ -197,3 +197,29 @@ def test_zero2_sharded_step_equals_unsharded_gloo_world2():
     for rank, p, metric in res:
         assert torch.allclose(p, ref, atol=1e-6), f"rank {rank}: sharded step differs from the unsharded one"
         assert metric == [0.5, 1.0]
+
+
+@pytest.mark.parametrize("grid", [[(147, 6, 12)], [(8, 26, 46)], [(60, 16, 28)], [(384, 6, 10)], [(2, 8, 12), (3, 6, 10)], [(16, 32, 32)]])
+def test_window_plan_matches_hf_get_window_index_on_timerft_grids(grid):
+    """cfg4: TimeRFT-shaped clips have many temporal slots with tiny, ragged spatial grids.  The host-side
+    window plan (permutation + per-row window ranges) against HF's own Qwen2.5-VL `get_window_index` (Q25:411-451, the
+    class timer1_trainer.py:244 instantiates) — only window_size / merge size / patch size matter, so the HF tower is built
+    with one tiny block."""
+    torch = pytest.importorskip("torch")
+    pytest.importorskip("transformers")
+    from transformers.models.qwen2_5_vl.configuration_qwen2_5_vl import Qwen2_5_VLVisionConfig
+    from transformers.models.qwen2_5_vl.modeling_qwen2_5_vl import Qwen2_5_VisionTransformerPretrainedModel
+
+    from time_r1_b200 import config, indexing
+
+    tower = Qwen2_5_VisionTransformerPretrainedModel(
+        Qwen2_5_VLVisionConfig(depth=1, hidden_size=32, num_heads=2, intermediate_size=64, out_hidden_size=32, fullatt_block_indexes=[0]))
+    cfg = config.ModelConfig()
+    assert (tower.window_size, tower.spatial_merge_size, tower.patch_size) == (cfg.window_size, cfg.spatial_merge_size, cfg.patch_size)
+    widx, cu = tower.get_window_index(torch.tensor(grid))
+    cu = torch.unique_consecutive(torch.tensor(cu)).numpy()          # as the forward does (Q25:476)
+    plan = indexing.vision_plan(cfg, grid)
+    assert np.array_equal(plan.window_index, widx.numpy())
+    for a, b in zip(cu[:-1], cu[1:]):
+        assert (plan.win_lo[a:b] == a).all() and (plan.win_hi[a:b] == b).all()
+    assert cu[-1] == plan.n_patches
