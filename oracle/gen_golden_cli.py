@@ -68,6 +68,37 @@ def main():
         assert [ref.reward_funcs_registry[f] for f in script_args.reward_funcs]            # main.py:548
         out[name] = dict(argv=argv, script_args=dataclasses.asdict(script_args), training_args=dataclasses.asdict(training_args),
                          model_args=dataclasses.asdict(model_args))
+    # main.main() itself (main.py:549-585) up to the trainer construction: dataset building from an annotation file, the
+    # registry lookups and the constructor call must reach the drop-in with kwargs its signature accepts
+    import inspect
+    import tempfile
+
+    from time_r1_b200.trainer import TimeR1_Trainer as DropIn
+
+    seen = {}
+
+    class Recorder:
+        def __init__(self, **kw):
+            inspect.signature(DropIn.__init__).bind(None, **kw)          # TypeError if main.py passes something unknown
+            seen.update(kwargs=sorted(kw), n_rows=len(kw["train_dataset"]), row_keys=sorted(kw["train_dataset"][0]),
+                        reward_funcs=[f.__name__ for f in kw["reward_funcs"]], metric_funcs=[f.__name__ for f in kw["metric_funcs"]],
+                        callbacks=[type(c).__name__ for c in kw["callbacks"]])
+            raise KeyboardInterrupt                                       # stop main() here: no CUDA in this container
+
+    ann = [dict(video=os.path.join(REF, "assets/OHOFG.mp4"), timestamp=[1.0, 5.5], sentence="Person opens a door.", duration=30.0,
+                video_start=None, video_end=None, qid=i) for i in range(3)]
+    with tempfile.NamedTemporaryFile("w", suffix=".json", delete=False) as tf:
+        json.dump(ann, tf)
+    ref.TimeR1_Trainer = Recorder
+    parser = TrlParser((ref.GRPOScriptArguments, ref.MY_GRPOConfig, ModelConfig))
+    script_args, training_args, model_args = parser.parse_args_and_config(TRAIN_RL_SF + ["--train_data_path", tf.name])
+    try:
+        ref.main(script_args, training_args, model_args)
+    except KeyboardInterrupt:
+        pass
+    os.unlink(tf.name)
+    assert seen and seen["n_rows"] == 3, seen
+    out["main_constructor_call"] = seen
     with open(os.path.join(OUT, "cli_golden.json"), "w") as f:
         json.dump(out, f, indent=0, sort_keys=True)
     print("wrote cli_golden.json;", len(out["train_rl.sh"]["training_args"]), "training fields")

@@ -81,3 +81,21 @@ def test_config_file_supplies_defaults(tmp_path):
     cfg.write_text("num_generations: 4\nreward_funcs: [iou]\nfix_vit: true\n")
     s, t, m = cli.TrlParser((S, T, cli.ModelConfig)).parse_args_and_config(["--config", str(cfg), "--num_generations", "6"])
     assert t.num_generations == 6 and s.reward_funcs == ["iou"] and t.fix_vit is True
+
+
+def test_drop_in_constructor_accepts_what_main_py_passes():
+    """oracle/gen_golden_cli.py ran the unmodified main.main() (main.py:549-585) with the drop-in in place of the trainer
+    class and recorded the constructor call it makes; the drop-in's signature must bind exactly those kwargs, and the
+    dataset rows must carry the columns the reward protocol repeats G times (main.py:455-468)."""
+    import inspect
+
+    from time_r1_b200 import rewards
+    from time_r1_b200.trainer import TimeR1_Trainer, TimeR1_Trainer_ft
+
+    call = json.load(open(GOLD))["main_constructor_call"]
+    for cls in (TimeR1_Trainer, TimeR1_Trainer_ft):
+        inspect.signature(cls.__init__).bind(None, **{k: None for k in call["kwargs"]})
+    assert call["reward_funcs"] == [rewards.reward_funcs_registry[k].__name__ for k in ("iou_v2", "format")]
+    assert call["metric_funcs"] == [f.__name__ for f in rewards.metric_funcs_registry.values()]
+    assert {"solution", "durations", "problem", "video_path", "video_start", "video_end", "task_type", "choices", "preprocessed_path"} == set(call["row_keys"])
+    assert call["callbacks"] == ["StopAfterNEpochsCallback"]

@@ -116,6 +116,8 @@ def _is_conversational(example: dict) -> bool:
 
 
 class TimeR1_Trainer:
+    _logs_metric_funcs = False       # the base trainer stores metric_funcs and never calls them (timer1_trainer.py:330)
+
     def __init__(
         self,
         model: Union[str, tuple],
@@ -312,9 +314,10 @@ class TimeR1_Trainer:
         return prompt, reward_fn
 
     def _device_reward_path(self):
-        """rewards.DeviceRewards when every reward function is one of the registry's, the tokenizer is byte-level BPE
-        with a readable vocabulary and no string clean-up (detok.DetokTable.supports) and nothing else needs the decoded strings (metric functions, `device_rewards=False`
-        in the arguments); None otherwise -> the host protocol of timer1_trainer.py:642-698."""
+        """rewards.DeviceRewards when every reward function is one of the registry's, the tokenizer is byte-level BPE with a
+        readable vocabulary and no string clean-up (detok.DetokTable.supports) and nothing else needs the decoded strings
+        (the fine-tune trainer's metric functions — the base trainer only stores them, timer1_trainer.py:330 — or
+        `device_rewards=False` in the arguments); None otherwise -> the host protocol of timer1_trainer.py:642-698."""
         if not hasattr(self, "_device_rewards"):
             self._device_rewards = None
             from .rewards import DeviceRewards
@@ -322,7 +325,8 @@ class TimeR1_Trainer:
             from .detok import DetokTable
 
             tok = getattr(self.processing_class, "tokenizer", self.processing_class)
-            if (getattr(self.args, "device_rewards", True) and not self.metric_funcs and DeviceRewards.supports(self.reward_funcs)
+            needs_text = self._logs_metric_funcs and bool(self.metric_funcs)
+            if (getattr(self.args, "device_rewards", True) and not needs_text and DeviceRewards.supports(self.reward_funcs)
                     and DetokTable.supports(tok)):
                 table = DetokTable.from_tokenizer(tok, self.device, vocab_size=self.model_cfg.vocab_size)
                 self._device_rewards = DeviceRewards(self.reward_funcs, table)
@@ -505,6 +509,8 @@ class TimeR1_Trainer_ft(TimeR1_Trainer):
     """Fine-tune variant (src/time_r1/rl/timer1_trainer_ft.py): dataset rows carry pre-decoded tensors
     (`preprocessed_path`/video_inputs.pt, :551-556) — here rows carry the processed tensors directly — metric functions are
     logged, never added to the reward (:670-691), and clip-ratio metrics are reported (:820-842)."""
+
+    _logs_metric_funcs = True        # metrics/<name> are logged from the decoded completions (:670-691, 790-795)
 
     def _extra_metrics(self, clip_low: float, clip_high: float):
         self._metrics["clip_ratio/low_mean"].append(clip_low)
