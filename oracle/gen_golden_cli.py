@@ -34,6 +34,17 @@ TRAIN_RL_SF = """--deepspeed scripts/zero3_offload.json --output_dir ./logs/sf -
 --is_early_stopping true --save_only_model false""".split()
 
 
+# scripts/finetune/run_charades.sh:17-48 (finetune.py, TimeR1_Trainer_ft)
+RUN_CHARADES = """--deepspeed scripts/zero3_offload.json --output_dir ./logs/ft --model_name_or_path ./ckpts/Qwen2.5-VL-3B-Instruct_my
+--train_data_path ./dataset/finetune/charades/charades_annotation/train.json --video_folder xxx
+--preprocessed_data_path ./dataset/finetune/charades/Charades_preprocessed_data_maxpix_3584 --dataset_name xxx
+--max_prompt_length 8192 --max_completion_length 1024 --num_generations 8 --per_device_train_batch_size 1
+--gradient_accumulation_steps 2 --logging_steps 1 --bf16 --torch_dtype bfloat16 --data_seed 42 --gradient_checkpointing true
+--attn_implementation flash_attention_2 --fix_vit true --slide_window false --num_train_epochs 2 --run_name ft
+--report_to tensorboard --reward_funcs iou format --temperature 1.0 --beta 0.0 --prompt_type v1 --is_curriculum_learning false
+--logging_dir ./logs/finetune/ft --save_steps 100 --use_grpo false --save_only_model true""".split()
+
+
 def import_reference_main_with_shim():
     sys.path.insert(0, ROOT)
     from time_r1_b200 import cli
@@ -68,6 +79,13 @@ def main():
         assert [ref.reward_funcs_registry[f] for f in script_args.reward_funcs]            # main.py:548
         out[name] = dict(argv=argv, script_args=dataclasses.asdict(script_args), training_args=dataclasses.asdict(training_args),
                          model_args=dataclasses.asdict(model_args))
+    import finetune as ref_ft                                                               # same shim, finetune.py
+
+    assert ref_ft.TimeR1_Trainer_ft.__module__.startswith("time_r1_b200")
+    parser = TrlParser((ref_ft.GRPOScriptArguments, ref_ft.MY_GRPOConfig, ModelConfig))
+    script_args, training_args, model_args = parser.parse_args_and_config(RUN_CHARADES)
+    out["run_charades.sh"] = dict(argv=RUN_CHARADES, script_args=dataclasses.asdict(script_args),
+                                  training_args=dataclasses.asdict(training_args), model_args=dataclasses.asdict(model_args))
     # main.main() itself (main.py:549-585) up to the trainer construction: dataset building from an annotation file, the
     # registry lookups and the constructor call must reach the drop-in with kwargs its signature accepts
     import inspect

@@ -39,6 +39,37 @@ def _reference_style_dataclasses():
     return GRPOScriptArguments, MY_GRPOConfig
 
 
+def _finetune_style_script_arguments():
+    from time_r1_b200 import cli
+
+    @dataclass
+    class GRPOScriptArguments(cli.ScriptArguments):            # finetune.py's variant: adds preprocessed_data_path
+        reward_funcs: list[str] = field(default_factory=lambda: ["iou", "format"])
+        max_pixels: Optional[int] = field(default=12845056)
+        min_pixels: Optional[int] = field(default=3136)
+        train_data_path: str = field(default="./dataset/finetune/charades/Charades/charades_annotation/train.json")
+        eval_data_path: str = field(default="./dataset/finetune/charades/Charades/charades_annotation/val.json")
+        video_folder: str = field(default="./dataset/finetune/charades/Charades/Charades_v1")
+        preprocessed_data_path: Optional[str] = field(default="")
+        is_curriculum_learning: bool = field(default=False)
+
+    return GRPOScriptArguments
+
+
+def test_finetune_launch_script_flags():
+    """scripts/finetune/run_charades.sh:17-48 through finetune.py's own dataclasses (golden) vs the restated ones: only the
+    flags the script passes are compared for the script arguments (finetune.py's defaults for the rest are its own)."""
+    from time_r1_b200 import cli
+
+    g = json.load(open(GOLD))["run_charades.sh"]
+    _, T = _reference_style_dataclasses()
+    s, t, m = cli.TrlParser((_finetune_style_script_arguments(), T, cli.ModelConfig)).parse_args_and_config(g["argv"])
+    assert dataclasses.asdict(t) == g["training_args"] and dataclasses.asdict(m) == g["model_args"]
+    for k in ("train_data_path", "video_folder", "preprocessed_data_path", "dataset_name", "reward_funcs", "is_curriculum_learning"):
+        assert getattr(s, k) == g["script_args"][k], k
+    assert t.beta == 0.0 and t.use_grpo is False and t.max_completion_length == 1024 and t.save_only_model is True
+
+
 @pytest.mark.parametrize("script", ["train_rl.sh", "train_rl_SF.sh"])
 def test_launch_script_flags_parse_like_the_reference_main(script):
     from time_r1_b200 import cli
