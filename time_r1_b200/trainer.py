@@ -37,6 +37,30 @@ QUESTION_TEMPLATE_TG_v1 = (
     'Then, provide the start and end times (in seconds, precise to two decimal places) in the format "start time to '
     'end time" within the <answer> </answer> tags. For example: "12.54 to 17.83".'
 )
+# timer1_trainer_ft.py:67-71 (prompt_type v2: answer only; v3: step-by-step <timestep> analysis)
+QUESTION_TEMPLATE_TG_v2 = (
+    'To accurately pinpoint the event "[EVENT]" in the video, determine the precise time period of the event.\n'
+    '\n'
+    'Provide the start and end times (in seconds, precise to two decimal places) in the format "start time to end time" within the <answer> </answer> tags. For example: "12.54 to 17.83".'
+)
+QUESTION_TEMPLATE_TG_v3 = (
+    'Carefully analyze the video content to determine the precise time period during which "[EVENT]" occurs.  Within the `<think>` tags, provide a detailed description of your thought process, following the format below:\n'
+    '```\n'
+    '<think>\n'
+    'Step-by-step Analysis:\n'
+    '<timestep>Time period 1 (start time to end time)</timestep>: Describe the video content within this time period and determine if it is related to "[EVENT]".\n'
+    '<timestep>Time period 2 (start time to end time)</timestep>: Describe the video content within this time period and determine if it is related to "[EVENT]".\n'
+    'Based on the above analysis, state the precise time period during which "[EVENT]" occurs.\n'
+    '</think>\n'
+    '```\n'
+    'Finally, in the `<answer>` tags, provide the start and end times of "[EVENT]" in the format "start time to end time" (in seconds, precise to two decimal places). For example: "12.54 to 17.83".\n'
+    '```\n'
+    '<answer>\n'
+    'start time to end time\n'
+    '</answer>\n'
+    '```'
+)
+QUESTION_TEMPLATES = {"v1": QUESTION_TEMPLATE_TG_v1, "v2": QUESTION_TEMPLATE_TG_v2, "v3": QUESTION_TEMPLATE_TG_v3}
 
 
 @dataclass
@@ -230,8 +254,12 @@ class TimeR1_Trainer:
         idx = idx[self.rank::self.world]
         return [[self.train_dataset[i]] for i in idx]
 
+    _prompt_types = ("v1",)          # timer1_trainer.py:490-492 only knows v1
+
     def make_conversation_video(self, example: dict) -> list:
-        text = QUESTION_TEMPLATE_TG_v1.replace("[EVENT]", example["problem"])
+        if self.prompt_type not in self._prompt_types:
+            raise ValueError(f"prompt_type {self.prompt_type!r} is not one of {self._prompt_types} for {type(self).__name__}")
+        text = QUESTION_TEMPLATES[self.prompt_type].replace("[EVENT]", example["problem"])
         return [{"role": "user", "content": [
             {"type": "text", "text": text},
             {"type": "video", "video": example["video_path"], "video_start": example.get("video_start"),
@@ -511,6 +539,7 @@ class TimeR1_Trainer_ft(TimeR1_Trainer):
     logged, never added to the reward (:670-691), and clip-ratio metrics are reported (:820-842)."""
 
     _logs_metric_funcs = True        # metrics/<name> are logged from the decoded completions (:670-691, 790-795)
+    _prompt_types = ("v1", "v2", "v3")   # timer1_trainer_ft.py:511-518
 
     def _extra_metrics(self, clip_low: float, clip_high: float):
         self._metrics["clip_ratio/low_mean"].append(clip_low)
