@@ -223,3 +223,43 @@ def test_window_plan_matches_hf_get_window_index_on_timerft_grids(grid):
     for a, b in zip(cu[:-1], cu[1:]):
         assert (plan.win_lo[a:b] == a).all() and (plan.win_hi[a:b] == b).all()
     assert cu[-1] == plan.n_patches
+
+
+def _clip_metrics_worker(rank, world, port, q):
+    import collections
+    import types
+
+    import torch.distributed as dist
+
+    from time_r1_b200.trainer import TimeR1_Trainer_ft
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    local = torch.tensor([[0.125, 0.5], [0.375, 0.25]][rank])              # this rank's (low, high) clip fractions
+    mean = local.clone()
+    dist.all_reduce(mean)
+    mean /= world                                                          # what _log_metrics hands over (AVG all-reduce)
+    me = types.SimpleNamespace(_metrics=collections.defaultdict(list), _local_clip=local, world=world, metric_funcs=[], _last_completions=None)
+    TimeR1_Trainer_ft._extra_metrics(me, float(mean[0]), float(mean[1]))
+    q.put((rank, {k: v[0] for k, v in me._metrics.items()}))
+    dist.destroy_process_group()
+
+
+def test_ft_clip_ratio_metrics_across_two_ranks_gloo():
+    """timer1_trainer_ft.py:820-842: gather the per-rank fractions, log nanmean / nanmin(low) / nanmax(high) — here one
+    AVG all-reduce (in _log_metrics) plus one MIN all-reduce on (low, -high)."""
+    import torch.multiprocessing as mp
+
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_clip_metrics_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in ps:
+        p.join(60)
+    for rank, m in res:
+        assert m == {"clip_ratio/low_mean": 0.25, "clip_ratio/low_min": 0.125, "clip_ratio/high_mean": 0.375,
+                     "clip_ratio/high_max": 0.5, "clip_ratio/region_mean": 0.625}, (rank, m)

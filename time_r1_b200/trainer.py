@@ -403,6 +403,7 @@ class TimeR1_Trainer:
         rpf = out["rewards_per_func"].mean(0)
         vec = torch.cat([stats[3:4], rpf, out["rewards"].mean().reshape(1), out["reward_std"].mean().reshape(1),
                          stats[1:2], stats[2:3], stats[5:7]])
+        self._local_clip = stats[5:7]                       # this rank's (low, high) clip fractions, before the average
         if self.world > 1:
             import torch.distributed as dist
 
@@ -542,8 +543,19 @@ class TimeR1_Trainer_ft(TimeR1_Trainer):
     _prompt_types = ("v1", "v2", "v3")   # timer1_trainer_ft.py:511-518
 
     def _extra_metrics(self, clip_low: float, clip_high: float):
+        # :820-842 — mean over ranks of each rank's fraction, plus the smallest low / largest high fraction of any rank
+        import torch
+
+        ext = torch.stack([self._local_clip[0], -self._local_clip[1]])
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.all_reduce(ext, op=dist.ReduceOp.MIN)
+        low_min, neg_high_max = ext.tolist()
         self._metrics["clip_ratio/low_mean"].append(clip_low)
+        self._metrics["clip_ratio/low_min"].append(low_min)
         self._metrics["clip_ratio/high_mean"].append(clip_high)
+        self._metrics["clip_ratio/high_max"].append(-neg_high_max)
         self._metrics["clip_ratio/region_mean"].append(clip_low + clip_high)
         comps = getattr(self, "_last_completions", None)
         if comps is not None:
