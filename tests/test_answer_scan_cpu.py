@@ -127,3 +127,23 @@ def test_long_digit_runs_stay_linear(host):
     s, e, v, f = scan(host, [t, t.replace(b".5", b" to 2")], 0)
     assert time.time() - t0 < 5.0
     assert list(v) == [0, 1] and s[1] == float("inf") and e[1] == 2.0
+
+
+def test_property_random_unicode_text(host):
+    """hypothesis: arbitrary Unicode text interleaved with the tokens the patterns care about — the scanner and CPython's
+    `re` must agree on every example (all three modes)."""
+    hyp = pytest.importorskip("hypothesis")
+    st = hyp.strategies
+
+    piece = st.one_of(st.sampled_from(sc._PIECES), st.text(max_size=6),
+                      st.text(alphabet=st.characters(whitelist_categories=("Nd", "Zs", "Cc")), max_size=4),
+                      st.integers(0, 10 ** 25).map(str), st.floats(0, 1e6, allow_nan=False).map(lambda f: f"{f:.3f}"))
+    texts = st.lists(piece, max_size=14).map("".join)
+
+    @hyp.settings(max_examples=400, deadline=None, suppress_health_check=list(hyp.HealthCheck))
+    @hyp.given(st.lists(texts, min_size=1, max_size=8))
+    def run(batch):
+        for mode in (0, 1, 2):
+            check_rows(host, batch, mode)
+
+    run()
