@@ -20,6 +20,9 @@
 // HBM-bound: algorithmic bytes per launch = 2 * Hkv * 128 * 2 * sum_groups(P + G * step) (+ q, out).
 // The cache must hold finite values everywhere (it is allocated zeroed): masked keys are multiplied by P = 0.
 #include "t1_common.cuh"
+#ifdef T1_SOFTMAX_POLY_EXP2
+#include "fast_exp2.cuh"
+#endif
 #include <cooperative_groups.h>
 #include <stdlib.h>
 #include <string.h>
@@ -67,6 +70,13 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// Experiment switch (T1_EXTRA_NVCC=-DT1_SOFTMAX_POLY_EXP2): every second exponential of a score pair on the FMA pipe
+// (fast_exp2.cuh, relative error 7.5e-5, far inside bf16) instead of the MUFU, which the softmax saturates.  Default: MUFU.
+#ifdef T1_SOFTMAX_POLY_EXP2
+#define EX2_B(x) fast_exp2::exp2<3>(x)
+#else
+#define EX2_B(x) ex2_approx(x)
+#endif
 __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
                                              uint32_t accumulate) {
   asm volatile(
@@ -397,7 +407,7 @@ decode_attn_tc_kernel(const bf16* __restrict__ q, long long ldq, int Hq, int Hkv
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const float p0 = ex2_approx(fmaf(__uint_as_float(sv[2 * j]), scale_log2, neg_m));
-        const float p1 = ex2_approx(fmaf(__uint_as_float(sv[2 * j + 1]), scale_log2, neg_m));
+        const float p1 = EX2_B(fmaf(__uint_as_float(sv[2 * j + 1]), scale_log2, neg_m));
         rs += p0 + p1;
         pk[j] = pack_bf16x2(p0, p1);
       }
