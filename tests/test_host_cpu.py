@@ -240,7 +240,7 @@ def _clip_metrics_worker(rank, world, port, q):
     dist.all_reduce(mean)
     mean /= world                                                          # what _log_metrics hands over (AVG all-reduce)
     me = types.SimpleNamespace(_metrics=collections.defaultdict(list), _local_clip=local, world=world, metric_funcs=[], _last_completions=None)
-    TimeR1_Trainer_ft._extra_metrics(me, float(mean[0]), float(mean[1]))
+    TimeR1_Trainer_ft._extra_metrics(me, float(mean[0]), float(mean[1]), [])
     q.put((rank, {k: v[0] for k, v in me._metrics.items()}))
     dist.destroy_process_group()
 

@@ -136,3 +136,104 @@ def test_base_trainer_rejects_other_prompt_types_and_keeps_metric_funcs_silent(t
         tr.compute_loss(None, [tr.train_dataset[0]])
     with pytest.raises(ValueError):
         tr.compute_loss(None, [tr.train_dataset[0], tr.train_dataset[1]])          # per-device batch must be 1
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# uneven dataset shards, per-group metric functions, global sample filter
+# ------------------------------------------------------------------------------------------------------------------
+def _uneven_worker(rank, world, port, q, n_rows, accum, epochs):
+    import os
+
+    import torch.distributed as dist
+
+    from time_r1_b200 import rewards
+    from time_r1_b200.trainer import GRPOArguments, TimeR1_Trainer
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rewards._iou_on_device = lambda mode, completions, solution, durations: [0.5] * len(completions)
+    args = GRPOArguments(output_dir="/tmp/unused", num_generations=2, max_completion_length=4, beta=0.0, gradient_accumulation_steps=accum,
+                         num_train_epochs=epochs, logging_steps=1000, save_strategy="no")
+    tr = make_trainer(TimeR1_Trainer, args, [rewards.iou_timestamp_reward])
+    tr.train_dataset = rows(n_rows)
+    tr.world, tr.rank = world, rank
+
+    class CollectiveEngine(StandInEngine):        # every optimizer step holds a collective, like Engine.optimizer_step at world > 1
+        def optimizer_step(self, lr=None):
+            t = torch.ones(1)
+            dist.all_reduce(t)                   # would hang (-> test timeout) if the ranks disagreed on the step count
+            return super().optimizer_step(lr)
+
+    tr.engine = CollectiveEngine(2, 4)
+    lens = [len(tr.get_train_dataloader(e)) for e in range(2)]
+    seen = sorted(int(mb[0]["problem"].split()[1]) for mb in tr.get_train_dataloader(0))
+    tr.train()
+    q.put((rank, lens, tr.state.max_steps, tr.state.global_step, tr.engine.steps, seen))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_rows,accum,epochs", [(7, 2, 3), (5, 1, 2), (9, 4, 2)])
+def test_uneven_dataset_gives_every_rank_the_same_step_count_gloo(n_rows, accum, epochs):
+    """len(dataset) % world != 0 (train_2k5.json: 2500 rows on 8 ranks with accum 2): the shuffled index list is padded by
+    wrap-around like DistributedSampler, so loader lengths, max_steps and the number of optimizer steps (each of which
+    holds a collective) agree on all ranks and train() returns on every rank."""
+    import socket
+
+    import torch.multiprocessing as mp
+
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_uneven_worker, args=(r, world, port, q, n_rows, accum, epochs)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in range(world))
+    for p in ps:
+        p.join(60)
+    (_, lens0, max0, gs0, st0, seen0), (_, lens1, max1, gs1, st1, seen1) = res
+    L = -(-n_rows // world)
+    assert lens0 == lens1 == [L, L]
+    assert max0 == max1 == int(np.ceil(epochs * max(1, L // accum)))
+    assert gs0 == gs1 == st0 == st1 == max0
+    assert set(seen0) | set(seen1) == set(range(n_rows))          # every row is dealt out; the padding repeats rows, never drops one
+
+
+def test_metric_funcs_are_computed_from_each_groups_own_completions(tmp_path, monkeypatch):
+    """gradient_accumulation_steps=2: both prompt-groups of an optimizer step log metrics/<fn> from THEIR completions
+    (timer1_trainer_ft.py:670-691), not from the last group's."""
+    from time_r1_b200 import rewards
+    from time_r1_b200.trainer import GRPOArguments, TimeR1_Trainer_ft
+
+    monkeypatch.setattr(rewards, "_iou_on_device", lambda mode, completions, solution, durations: [0.5] * len(completions))
+    calls = []
+
+    def think_chars(completions, **kw):
+        vals = [float(len(c)) for c in completions]
+        calls.append((kw["problem"][0], vals))
+        return vals
+
+    args = GRPOArguments(output_dir=str(tmp_path), num_generations=2, max_completion_length=4, beta=0.0, gradient_accumulation_steps=2,
+                         max_steps=1, logging_steps=1, save_strategy="no")
+    tr = make_trainer(TimeR1_Trainer_ft, args, [rewards.iou_timestamp_reward], metric_funcs=[think_chars])
+
+    class Tok(TemplateTokenizer):
+        def batch_decode(self, ids, skip_special_tokens=True):
+            return ["x" * (1 + int(r[0]) % 50) for r in np.asarray(ids)]
+
+    tr.processing_class = Tok()
+    tr.train()
+    assert len(calls) == 2 and calls[0][0] != calls[1][0]           # one call per group, each with its own dataset row
+    assert calls[0][1] != calls[1][1]
+    want = (np.mean(calls[0][1]) + np.mean(calls[1][1])) / 2        # log() averages the per-group entries
+    assert tr.state.log_history[0]["metrics/think_chars"] == pytest.approx(want)
+
+
+def test_fix_vit_false_is_an_error_not_a_silent_freeze():
+    import inspect
+
+    from time_r1_b200 import trainer
+
+    src = inspect.getsource(trainer.TimeR1_Trainer.__init__)
+    assert "raise NotImplementedError(\"fix_vit=False" in src and "ViT blocks stay frozen (only merger + LLM train)\")" not in src

@@ -171,6 +171,10 @@ class GreedyFilter:
                                 "duration": s.get("duration"), "output_text": text})
         return records
 
+    def difficulties(self, samples: Sequence[dict]) -> dict:
+        """{qid: {difficulty, pred}} of these samples (what one evaluate.py shard + calc_difficulty.py produce)."""
+        return fill_difficulty(self.rollout(samples))
+
     def run(self, samples: Sequence[dict], k: int = 2500) -> tuple:
         """One filtering epoch: rollout -> difficulty -> 0 < IoU <= 0.7 selection.  Returns (selected, annotated)."""
         records = self.rollout(samples)

@@ -236,8 +236,14 @@ class TimeR1_Trainer:
             weight_decay=getattr(a, "weight_decay", 0.0), max_grad_norm=getattr(a, "max_grad_norm", 1.0),
             gradient_accumulation_steps=a.gradient_accumulation_steps, fix_vit=True, seed=getattr(a, "seed", 42))
         if not getattr(a, "fix_vit", False):
-            # every reference script passes --fix_vit true; ViT-block gradients are not built
-            print("[time_r1_b200] note: fix_vit=False requested; ViT blocks stay frozen (only merger + LLM train)")
+            # the reference default is fix_vit=False (main.py:46-49) but every shipped script passes --fix_vit true; ViT-block
+            # gradients are not built, and silently freezing the tower would train a different parameter set
+            raise NotImplementedError("fix_vit=False (ViT-block gradients) is not built: pass --fix_vit true as every reference "
+                                      "script does (scripts/posttrain/train_rl.sh:34); merger + LLM train, ViT blocks stay frozen")
+        if getattr(a, "deepspeed", None) and self.rank == 0:
+            print(f"[time_r1_b200] note: --deepspeed {a.deepspeed} is accepted for CLI compatibility and NOT applied: parameters and "
+                  "gradients are replicated bf16, fp32 master weights + AdamW state are sharded 1/world per rank in HBM (ZeRO-2 "
+                  "semantics, no CPU offload)")
         self.engine = _engine.Engine(self.model_cfg, self.weights, self.run, with_ref=a.beta != 0.0, rank=self.rank,
                                      world_size=self.world, process_group=pg)
         self.model = self.engine
@@ -245,14 +251,23 @@ class TimeR1_Trainer:
             or self.model_cfg.eos_token_id
 
     # ------------------------------------------------------------------ data
-    def get_train_dataloader(self) -> list:
-        """This rank's micro-batches for one epoch: lists of `per_device_train_batch_size` (=1) examples."""
+    def _epoch_indices(self, epoch: int = 0) -> list:
+        """This rank's dataset indices for one epoch.  The shuffled list is padded by wrap-around to a multiple of the world
+        size before it is dealt out (what torch's DistributedSampler / accelerate do under HF Trainer), so EVERY rank sees
+        the same number of micro-batches: step counts, max_steps and the collectives of optimizer_step stay matched."""
         n = len(self.train_dataset)
         idx = list(range(n))
-        rng = random.Random(getattr(self.args, "data_seed", None) or getattr(self.args, "seed", 42))
-        rng.shuffle(idx)
-        idx = idx[self.rank::self.world]
-        return [[self.train_dataset[i]] for i in idx]
+        seed = getattr(self.args, "data_seed", None)
+        seed = getattr(self.args, "seed", 42) if seed is None else seed
+        random.Random(seed + epoch).shuffle(idx)
+        total = -(-n // self.world) * self.world
+        idx = (idx * (total // max(1, n) + 1))[:total] if n else idx
+        return idx[self.rank:total:self.world]
+
+    def get_train_dataloader(self, epoch: int = 0) -> list:
+        """This rank's micro-batches for one epoch: lists of `per_device_train_batch_size` (=1) examples; the same length
+        on every rank (main.py:599-605 derives max_steps from it)."""
+        return [[self.train_dataset[i]] for i in self._epoch_indices(epoch)]
 
     _prompt_types = ("v1",)          # timer1_trainer.py:490-492 only knows v1
 
@@ -309,13 +324,28 @@ class TimeR1_Trainer:
         rank, rank + world, ... (evaluate.py --curr_idx / --total_idx).  Returns (selected_rows, annotated_rows)."""
         from .filtering import GreedyFilter
 
-        rows = list(self.train_dataset if samples is None else samples)[self.rank::self.world]
-        rows = [dict(r, qid=r.get("qid", i), timestamp=r.get("timestamp", r.get("solution"))) for i, r in enumerate(rows)]
+        all_rows = list(self.train_dataset if samples is None else samples)
+        # default qid = GLOBAL row index, so that the per-rank shards merge without collisions
+        all_rows = [dict(r, qid=r.get("qid", i), timestamp=r.get("timestamp", r.get("solution"))) for i, r in enumerate(all_rows)]
+        rows = all_rows[self.rank::self.world]
         pc = self.processing_class
         if pc is None:
             raise RuntimeError("a processing_class with decode() is required to turn completions into text")
         decode = lambda ids: pc.decode(ids, skip_special_tokens=False)
-        return GreedyFilter(self.engine, self._prompt_from_example, decode, max_new_tokens=max_new_tokens, batch=batch).run(rows, k)
+        flt = GreedyFilter(self.engine, self._prompt_from_example, decode, max_new_tokens=max_new_tokens, batch=batch)
+        if self.world == 1:
+            return flt.run(rows, k)
+        # the reference joins every shard's predictions first (calc_difficulty.py:40-66) and takes ONE difficulty-sorted
+        # linspace subsample of the merged list (process_data.py:61-80): annotate locally, gather, select globally
+        import torch.distributed as dist
+
+        from .filtering import attach_difficulty, select_0070
+
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, flt.difficulties(rows))
+        difficulty = {qid: d for part in gathered for qid, d in part.items()}
+        annotated = attach_difficulty(all_rows, difficulty)                 # original row order, every rank identical
+        return select_0070(annotated, k), annotated
 
     # ------------------------------------------------------------------ one micro-step
     def _prepare(self, example: dict):
@@ -332,7 +362,7 @@ class TimeR1_Trainer:
             out = np.zeros((G, len(self.reward_funcs)), np.float32)
             for i, rf in enumerate(self.reward_funcs):
                 out[:, i] = np.asarray(rf(prompts=prompts, completions=completions, **cols), np.float32)
-            self._last_completions, self._last_reward_kwargs = completions, dict(prompts=prompts, **cols)
+            reward_fn.last = (completions, dict(prompts=prompts, **cols))      # THIS group's texts, for its metric functions
             return out
 
         dr = self._device_reward_path()
@@ -384,8 +414,8 @@ class TimeR1_Trainer:
         seed = self.run.seed + 7919 * (self.state.global_step * self.world + self.rank)
         outs = self.engine.grpo_multi_step([p for p, _ in prepared], [r for _, r in prepared], seed=seed, loss_scale=1.0 / accum,
                                            vit_prefetch=handle)
-        for out in outs:
-            self._log_metrics(out)
+        for out, (_, rf) in zip(outs, prepared):
+            self._log_metrics(out, getattr(rf, "last", None))
         return [o["loss"] for o in outs]
 
     def _prefetch_next(self, micro_batches: list):
@@ -396,13 +426,16 @@ class TimeR1_Trainer:
         prepared = [self._prepare(inputs[0]) for inputs in micro_batches]
         self._prefetched = (micro_batches, prepared, self.engine.prefetch_vit([p for p, _ in prepared]))
 
-    def _log_metrics(self, out: dict):
+    def _log_metrics(self, out: dict, texts=None):
+        """Metrics of ONE prompt-group (timer1_trainer.py:740-777); `texts` = (completions, reward kwargs) of that group
+        when the host reward protocol decoded them."""
         import torch
 
         stats = out["stats"]
         rpf = out["rewards_per_func"].mean(0)
+        extra = self._extra_local(texts)                    # subclass: per-rank values that are averaged over ranks
         vec = torch.cat([stats[3:4], rpf, out["rewards"].mean().reshape(1), out["reward_std"].mean().reshape(1),
-                         stats[1:2], stats[2:3], stats[5:7]])
+                         stats[1:2], stats[2:3], stats[5:7], torch.tensor(extra, dtype=stats.dtype, device=stats.device)])
         self._local_clip = stats[5:7]                       # this rank's (low, high) clip fractions, before the average
         if self.world > 1:
             import torch.distributed as dist
@@ -418,9 +451,12 @@ class TimeR1_Trainer:
         if self.beta != 0.0:
             self._metrics["kl"].append(v[3 + n])
         self._metrics["generation_entropy"].append(v[4 + n])
-        self._extra_metrics(v[5 + n], v[6 + n])
+        self._extra_metrics(v[5 + n], v[6 + n], v[7 + n:])
 
-    def _extra_metrics(self, clip_low: float, clip_high: float):
+    def _extra_local(self, texts) -> list:
+        return []
+
+    def _extra_metrics(self, clip_low: float, clip_high: float, extra: list):
         pass
 
     def log(self, logs: dict, start_time: Optional[float] = None) -> None:
@@ -436,13 +472,16 @@ class TimeR1_Trainer:
     # ------------------------------------------------------------------ loop
     def train(self, resume_from_checkpoint: Optional[str] = None):
         a = self.args
-        loader = self.get_train_dataloader()
-        accum = a.gradient_accumulation_steps
-        steps_per_epoch = max(1, math.ceil(len(loader) / accum))
+        loader = self.get_train_dataloader(0)
+        accum = max(1, a.gradient_accumulation_steps)
+        # HF Trainer arithmetic (trainer.py:_inner_training_loop, 4.51.1), from the per-rank loader length that is common to
+        # all ranks: update steps per epoch = len // accum (at least 1) for max_steps; an epoch's trailing partial
+        # accumulation still performs an optimizer step.
+        steps_per_epoch = max(1, len(loader) // accum)
         if getattr(a, "max_steps", -1) and a.max_steps > 0:
             max_steps = a.max_steps
         else:
-            max_steps = math.ceil(a.num_train_epochs * len(loader) / accum)
+            max_steps = math.ceil(a.num_train_epochs * steps_per_epoch)
         if self.state.max_steps <= 0:
             self.state.max_steps = max_steps
         start_step = 0
@@ -455,19 +494,19 @@ class TimeR1_Trainer:
         epoch = 0
         losses = []
         while self.state.global_step < total and not self.control.should_training_stop:
-            loader = self.get_train_dataloader() if epoch > 0 else loader
-            stop = len(loader) - len(loader) % accum or len(loader)
+            loader = self.get_train_dataloader(epoch) if epoch > 0 else loader
+            n_mb = len(loader)
             micro = loader[0:accum]
-            for i in range(0, stop, accum):
+            for i in range(0, n_mb, accum):
                 losses.extend(self._accum_step(micro))
-                nxt = loader[i + accum:i + 2 * accum] if i + accum < stop else None
+                nxt = loader[i + accum:i + 2 * accum] if i + accum < n_mb else None
                 if nxt and self.state.global_step + 1 < total:
                     self._prefetch_next(nxt)
                 done = self.state.global_step - start_step
                 lr = a.learning_rate * max(0.0, 1.0 - done / max(1, total - start_step))   # linear decay, no warm-up
                 gnorm = self.engine.optimizer_step(lr=lr)
                 self.state.global_step += 1
-                self.state.epoch = epoch + min(1.0, (i + accum) / max(1, len(loader)))
+                self.state.epoch = epoch + min(1.0, (i + accum) / max(1, n_mb))
                 if self.state.global_step % max(1, a.logging_steps) == 0:
                     loss_val = float(sum(l.item() for l in losses))
                     losses = []
@@ -496,6 +535,11 @@ class TimeR1_Trainer:
             return
         os.makedirs(output_dir, exist_ok=True)
         save_checkpoint_dir(output_dir, self.model_cfg, self.weights)
+        # HF Trainer saves processing_class into every checkpoint: scripts/posttrain/train_rl_SF.sh:76-105 feeds checkpoint-N
+        # straight into evaluate.py / vLLM (AutoProcessor.from_pretrained) and into the next round as --model_name_or_path
+        pc = self.processing_class
+        if pc is not None and hasattr(pc, "save_pretrained"):
+            pc.save_pretrained(output_dir)
 
     def _save_checkpoint(self):
         import torch
@@ -515,9 +559,12 @@ class TimeR1_Trainer:
     def _load_checkpoint(self, d: str) -> int:
         import torch
 
-        cfg, w = load_checkpoint(d, self.device, self.world)
-        self.weights.train.buf.copy_(w.train.buf)
-        self.weights.frozen.buf.copy_(w.frozen.buf)
+        from .weights import param_specs
+
+        shapes = lambda c: [(sp.name, tuple(sp.shape)) for sp in param_specs(c)]
+        if shapes(read_checkpoint_config(d)) != shapes(self.model_cfg):
+            raise ValueError(f"checkpoint {d} was written for another model configuration (tensor names / shapes differ)")
+        self.weights.load_state_dict(read_state_dict(d))      # straight into the live flat buffers: no second copy in HBM
         opt = os.path.join(d, f"optimizer_rank{self.rank}.pt")
         if os.path.exists(opt):
             s = torch.load(opt, map_location=self.device)
@@ -542,7 +589,15 @@ class TimeR1_Trainer_ft(TimeR1_Trainer):
     _logs_metric_funcs = True        # metrics/<name> are logged from the decoded completions (:670-691, 790-795)
     _prompt_types = ("v1", "v2", "v3")   # timer1_trainer_ft.py:511-518
 
-    def _extra_metrics(self, clip_low: float, clip_high: float):
+    def _extra_local(self, texts) -> list:
+        """metrics/<fn> of THIS group's completions (timer1_trainer_ft.py:670-691): same protocol as the reward functions;
+        the per-rank means are averaged over ranks in the fused all-reduce (:790-795 gathers, then averages)."""
+        if texts is None:
+            return []
+        comps, kw = texts
+        return [float(np.asarray(mf(completions=comps, **kw), np.float32).mean()) for mf in self.metric_funcs]
+
+    def _extra_metrics(self, clip_low: float, clip_high: float, extra: list):
         # :820-842 — mean over ranks of each rank's fraction, plus the smallest low / largest high fraction of any rank
         import torch
 
@@ -557,12 +612,8 @@ class TimeR1_Trainer_ft(TimeR1_Trainer):
         self._metrics["clip_ratio/high_mean"].append(clip_high)
         self._metrics["clip_ratio/high_max"].append(-neg_high_max)
         self._metrics["clip_ratio/region_mean"].append(clip_low + clip_high)
-        comps = getattr(self, "_last_completions", None)
-        if comps is not None:
-            kw = getattr(self, "_last_reward_kwargs", {})
-            for mf in self.metric_funcs:                      # same protocol as the reward functions (:673-691)
-                vals = np.asarray(mf(completions=comps, **kw), np.float32)
-                self._metrics[f"metrics/{mf.__name__}"].append(float(vals.mean()))
+        for mf, val in zip(self.metric_funcs, extra):
+            self._metrics[f"metrics/{mf.__name__}"].append(val)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -597,6 +648,9 @@ def save_checkpoint_dir(path: str, cfg: ModelConfig, weights) -> None:
     sd = {k: v.detach().contiguous().cpu() for k, v in weights.export_state_dict().items()}
     with open(os.path.join(path, "config.json"), "w") as f:
         json.dump(hf_config_dict(cfg), f, indent=1)
+    with open(os.path.join(path, "generation_config.json"), "w") as f:      # what the released checkpoints ship (vllm_infer.py:112)
+        json.dump({"bos_token_id": cfg.pad_token_id, "pad_token_id": cfg.pad_token_id, "do_sample": True,
+                   "eos_token_id": [int(t) for t in cfg.stop_token_ids]}, f, indent=1)
     try:
         from safetensors.torch import save_file
 
@@ -605,20 +659,22 @@ def save_checkpoint_dir(path: str, cfg: ModelConfig, weights) -> None:
         torch.save(sd, os.path.join(path, "pytorch_model.bin"))
 
 
-def load_checkpoint(path: str, device, world_size: int = 1):
-    import glob
-
-    import torch
-
-    from .weights import ModelWeights
-
-    cfg = from_hf_config(json.load(open(os.path.join(path, "config.json"))))
+def read_checkpoint_config(path: str) -> ModelConfig:
     hf = json.load(open(os.path.join(path, "config.json")))
+    cfg = from_hf_config(hf)
     for k in ("eos_token_id", "pad_token_id"):
         if isinstance(hf.get(k), int):
             setattr(cfg, k, hf[k])
     cfg.stop_token_ids = (cfg.eos_token_id, cfg.pad_token_id)
-    w = ModelWeights(cfg, device, world_size=world_size)
+    return cfg
+
+
+def read_state_dict(path: str) -> dict:
+    """HF-checkpoint tensors of a directory (safetensors shards or pytorch_model.bin) on the host, released-checkpoint names."""
+    import glob
+
+    import torch
+
     sd: dict = {}
     files = sorted(glob.glob(os.path.join(path, "*.safetensors")))
     if files:
@@ -629,9 +685,13 @@ def load_checkpoint(path: str, device, world_size: int = 1):
     else:
         sd = torch.load(os.path.join(path, "pytorch_model.bin"), map_location="cpu")
     # transformers >= 4.52 nests the towers ("model.visual.*", "model.language_model.*"): normalise to released names
-    norm = {}
-    for k, v in sd.items():
-        k = k.replace("model.visual.", "visual.").replace("model.language_model.", "model.")
-        norm[k] = v
-    w.load_state_dict(norm)
+    return {k.replace("model.visual.", "visual.").replace("model.language_model.", "model."): v for k, v in sd.items()}
+
+
+def load_checkpoint(path: str, device, world_size: int = 1):
+    from .weights import ModelWeights
+
+    cfg = read_checkpoint_config(path)
+    w = ModelWeights(cfg, device, world_size=world_size)
+    w.load_state_dict(read_state_dict(path))
     return cfg, w
