@@ -57,6 +57,11 @@ def parse_args():
                     help="device: template completions are detokenised, parsed and scored on the GPU; host: regex parse on the host")
     ap.add_argument("--no-vit-prefetch", dest="vit_prefetch", action="store_false",
                     help="do not overlap the next step's frozen ViT blocks with this step's optimizer phase")
+    ap.add_argument("--verify", default=None, metavar="OUT.pt",
+                    help="numerical invariance check of the multi-GPU path instead of a benchmark: ONE optimizer step over a fixed "
+                         "global batch of 8 teacher-forced prompt-groups dealt over the ranks; writes loss / grad-norm / strided "
+                         "samples of the averaged gradient and of the post-step weights to OUT.pt (compare runs at different N with "
+                         "tools/verify_compare.py)")
     ap.add_argument("--phase-times", action="store_true", help="print a per-phase breakdown to stderr")
     ap.add_argument("--kernel-times", action="store_true", help="print per-entry-point CUDA-event totals of one extra step to stderr")
     ap.add_argument("--ncu-range", action="store_true",
@@ -611,8 +616,72 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_verify(args):
+    """Same global batch at any world size -> same loss, gradient and post-step weights up to bf16 rounding (SURVEY §4 iii).
+    8 prompt-groups with FIXED completions and rewards (no sampling: the test is about the data split, the backward's
+    accumulation and the NCCL reduce-scatter / all-gather of optimizer_step); rank r takes groups r, r + W, ..."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from time_r1_b200 import config, engine, lib, ops, weights
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    pg = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        pg = dist.group.WORLD
+    lib.load()
+    cfg = config.PRESETS[args.model]()
+    G, C, NGLOBAL = args.group_size, 16, 8
+    assert NGLOBAL % world == 0
+    run = config.RunConfig(num_generations=G, max_completion_length=C, learning_rate=1e-3)
+    mw = weights.ModelWeights(cfg, dev, world_size=world)
+    mw.init_random(seed=0)
+    eng = engine.Engine(cfg, mw, run, rank=rank, world_size=world, process_group=pg)
+    with torch.no_grad():      # policy != reference model, so the KL term and its gradient are live
+        eng.w.train["model.layers.1.mlp.down_proj.weight"].mul_(1.25)
+    grid = (4, 32, 32)
+    losses = []
+    for gi in range(rank, NGLOBAL, world):
+        ids, frames_host, g = synthetic_prompt(cfg, grid, gi, 0, dev)
+        rng = np.random.default_rng(1000 + gi)
+        comp = torch.from_numpy(rng.integers(0, 151643, (G, C))).int()
+        comp[gi % G, 5 + gi] = cfg.eos_token_id
+        comp[gi % G, 6 + gi:] = cfg.pad_token_id
+        rewards = rng.random((G, 2)).astype(np.float32)
+        prompt = engine.Prompt(input_ids=ids, pixel_values=None, grid_thw=g, second_per_grid_ts=[1.0], frames=frames_host.to(dev))
+        out = eng.grpo_step(prompt, lambda c, r=rewards: r, completion_override=comp, loss_scale=world / NGLOBAL)
+        losses.append(out["loss"].double())
+    stride = 1021
+    gsample = eng.grads.buf[::stride].float().clone()
+    loss = torch.stack(losses).sum().reshape(1) / world      # each rank holds (its groups) x world / 8: the DP mean equals the N=1 sum
+    if world > 1:
+        dist.all_reduce(gsample, op=dist.ReduceOp.AVG)
+        dist.all_reduce(loss, op=dist.ReduceOp.SUM)
+    w_before = eng.w.train.buf[::stride].float().clone()
+    gnorm = eng.optimizer_step(lr=1e-3)
+    torch.cuda.synchronize()
+    w_after = eng.w.train.buf[::stride].float().clone()
+    if rank == 0:
+        rec = {"world": world, "loss": float(loss.item()), "grad_norm": float(gnorm.item()), "grad_sample": gsample.cpu(),
+               "w_before": w_before.cpu(), "w_after": w_after.cpu(), "stride": stride, "model": args.model, "groups": NGLOBAL, "G": G, "C": C}
+        torch.save(rec, args.verify)
+        print(json.dumps({"verify": {"world": world, "loss": rec["loss"], "grad_norm": rec["grad_norm"],
+                                     "grad_sample_l2": float(gsample.norm().item()), "out": args.verify}}), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     args = parse_args()
+    if args.verify:
+        return run_verify(args)
     if args.impl == "reference":
         run_reference(args)
     elif args.impl == "hf_gpu":

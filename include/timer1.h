@@ -225,6 +225,10 @@ int t1_layernorm(const void* x, const void* delta, void* x_out, const void* w, c
 /* dx = dres + d(rmsnorm)/dx; dw (fp32, caller-zeroed) += sum_t dy * xhat. */
 int t1_rmsnorm_bwd(const void* dy, const void* x, const void* w, const void* dres, void* dx, float* dw, int T, int D,
                    float eps, cudaStream_t stream);
+/* LayerNorm backward for the Qwen2-VL PatchMerger ln_q (modeling_qwen2_vl.py:313-326; trainable under --fix_vit,
+ * timer1_trainer.py:272-280): dx (may be NULL) = d(layernorm)/dx; dw / db (fp32, caller-zeroed) += sum_t dy * xhat / dy. */
+int t1_layernorm_bwd(const void* dy, const void* x, const void* w, void* dx, float* dw, float* db, int T, int D, float eps,
+                     cudaStream_t stream);
 /* cos/sin[t, i] of pos[axis_id[i], t] * inv_freq[i]: M-RoPE (Q25:595-608,659-665) and ViT 2-D RoPE (Q25:382-409). */
 int t1_rope_table(const int* pos, int T, const int* axis_id, const float* inv_freq, int half, float* cos_t,
                   float* sin_t, cudaStream_t stream);

@@ -436,17 +436,25 @@ def generate(w, cfg, input_ids, pixel_values, grid_thw, G, max_new_tokens, tempe
     return out
 
 
-def score_completions(w, cfg, prompt_ids, completion_ids, pixel_values, grid_thw, second_per_grid_ts=None):
+def score_completions(w, cfg, prompt_ids, completion_ids, pixel_values, grid_thw, second_per_grid_ts=None, tail_only=False):
     """Teacher-forced per-token logp / entropy of each completion, reference layout: returns [G, C] each
-    (position P-1+c predicts completion token c).  timer1_trainer.py:601-612."""
+    (position P-1+c predicts completion token c).  timer1_trainer.py:601-612.
+    tail_only: apply lm_head to the rows whose logits are returned only (identical values; the reference computes and
+    discards the prompt rows' logits, which is what the CPU baseline times with tail_only=False)."""
     P = len(prompt_ids)
     ve = vit_forward(w, cfg, pixel_values, grid_thw)
+    head = w["model.embed_tokens.weight"] if cfg["tie_word_embeddings"] else w["lm_head.weight"]
     lps, ents = [], []
     for row in completion_ids:
         ids = list(prompt_ids) + [int(t) for t in row]
         x = embed_with_vision(w, cfg, ids, ve)
         pos, _ = mrope_positions(cfg, ids, grid_thw, second_per_grid_ts)
-        lp, ent = per_token_logps(llm_forward(w, cfg, x, pos), ids)
-        lps.append(lp[P - 1:])
-        ents.append(ent[P - 1:])
+        if tail_only:
+            hN = llm_forward(w, cfg, x, pos, return_hidden=True)
+            lp, ent = per_token_logps(hN[P - 1:] @ head.t(), ids[P - 1:])
+        else:
+            lp, ent = per_token_logps(llm_forward(w, cfg, x, pos), ids)
+            lp, ent = lp[P - 1:], ent[P - 1:]
+        lps.append(lp)
+        ents.append(ent)
     return torch.stack(lps), torch.stack(ents)

@@ -104,9 +104,13 @@ def test_sampled_rollout_and_decode_logits_consistency():
             assert row[int(comp[g, c])] >= kth
 
 
-@pytest.mark.parametrize("use_grpo,beta", [(False, 0.04), (True, 0.04), (False, 0.0)])
-def test_grpo_step_loss_and_gradients_match_oracle(use_grpo, beta):
-    O, cfg, ocfg, w_or, eng, prompt, pix, ids, grid = build(beta=beta, use_grpo=use_grpo)
+@pytest.mark.parametrize("family,use_grpo,beta", [("qwen2_5_vl", False, 0.04), ("qwen2_5_vl", True, 0.04), ("qwen2_5_vl", False, 0.0),
+                                                  ("qwen2_vl", False, 0.04), ("qwen2_vl", True, 0.0)])
+def test_grpo_step_loss_and_gradients_match_oracle(family, use_grpo, beta):
+    """Both model families (BASELINE.json names Qwen2-VL, the reference instantiates Qwen2.5-VL): the Qwen2-VL step runs the
+    LayerNorm merger backward (t1_layernorm_bwd; HF modeling_qwen2_vl.py:313-326).  Anchored bars for the same inputs live in
+    tests/test_parity_7b_width_gpu.py; the fixed bars below are the older, looser ones."""
+    O, cfg, ocfg, w_or, eng, prompt, pix, ids, grid = build(family, beta=beta, use_grpo=use_grpo)
     G, C = 4, 12
     rng = np.random.default_rng(9)
     comp = torch.from_numpy(rng.integers(10, 2000, (G, C))).int()
@@ -126,6 +130,8 @@ def test_grpo_step_loss_and_gradients_match_oracle(use_grpo, beta):
              "model.layers.1.mlp.down_proj.weight", "model.layers.0.input_layernorm.weight", "model.norm.weight",
              "lm_head.weight", "model.embed_tokens.weight", "visual.merger.mlp.0.weight", "visual.merger.mlp.2.bias",
              "visual.merger.ln_q.weight", "model.layers.1.self_attn.o_proj.weight", "model.layers.1.self_attn.v_proj.weight"]
+    if family == "qwen2_vl":
+        watch.append("visual.merger.ln_q.bias")
     for k in watch:
         w_pol[k].requires_grad_(True)
     lp, ent = O.score_completions(w_pol, ocfg, list(ids), comp.numpy(), pix, grid)
@@ -202,3 +208,33 @@ def test_rollout_stops_at_eos_pads_and_masks_like_the_reference():
     assert mask.sum(1).tolist() == [k + 1] * G and lengths.tolist() == [k + 1] * G
     # early exit: the step counter stopped at the first all-finished check (check_every = 32), not at C - 1
     assert int(eng2._last_decode_state["step"].item()) <= 32
+
+
+@pytest.mark.parametrize("sampled", [False, True])
+def test_kept_activation_levels_give_the_same_gradients(sampled):
+    """Engine._save_level: 0 = recompute everything from the layer-input checkpoints, 1 = keep gate_up, 2 = also keep q/k/v,
+    attention output and LSE.  cfg3 / cfg5 fall back to the lower levels when HBM runs short: every level must produce the
+    same loss and the same gradients (the kept tensors ARE what the recompute would produce)."""
+    from time_r1_b200 import config, engine, weights
+
+    res = []
+    for level in (0, 1, 2):
+        O, cfg, ocfg, w_or, eng, prompt, pix, ids, grid = build(beta=0.04)
+        eng.save_gate_up = level
+        G, C = 4, 12
+        rng = np.random.default_rng(9)
+        rewards = rng.random((G, 2)).astype(np.float32)
+        if sampled:      # rollout path: the prefill's kept rows are reused by the policy scoring pass
+            out = eng.grpo_step(prompt, lambda c: rewards, seed=5)
+        else:
+            comp = torch.from_numpy(rng.integers(10, 2000, (G, C))).int()
+            out = eng.grpo_step(prompt, lambda c: rewards, completion_override=comp)
+        torch.cuda.synchronize()
+        res.append((out["loss"].item(), out["completion_ids"].cpu().clone(), out["logp"].cpu().clone(), eng.grads.buf.float().cpu().clone()))
+    for level in (1, 2):
+        assert torch.equal(res[level][1], res[0][1]), "same seed -> same completions at every level"
+        assert abs(res[level][0] - res[0][0]) < 1e-6
+        assert torch.allclose(res[level][2], res[0][2], atol=1e-5)
+        g0, g = res[0][3], res[level][3]
+        cos = torch.nn.functional.cosine_similarity(g0.double(), g.double(), dim=0).item()
+        assert cos > 0.99999 and (g - g0).abs().max().item() <= 2.0 ** -7 * g0.abs().max().item(), (level, cos)

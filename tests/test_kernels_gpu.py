@@ -27,6 +27,28 @@ def close(a, b, atol, rtol, what=""):
 
 
 # ------------------------------------------------------------------ norms
+@pytest.mark.parametrize("T,D,need_dx", [(5, 160, True), (300, 1280, True), (2048, 1280, False), (33, 2560, True)])
+def test_layernorm_bwd_matches_autograd(T, D, need_dx):
+    """Qwen2-VL PatchMerger ln_q backward (HF modeling_qwen2_vl.py:313-326) vs torch autograd in fp32 on the same bf16 inputs."""
+    from time_r1_b200 import ops
+
+    x, dy = rnd(T, D, seed=1, scale=2.0), rnd(T, D, seed=2)
+    w, b = (1 + 0.1 * rnd(D, seed=3).float()).to(BF16), rnd(D, seed=4, scale=0.1)
+    dw, db = torch.zeros(D, device=DEV), torch.zeros(D, device=DEV)
+    dx = ops.layernorm_bwd(dy, x, w, 1e-6, dw, db, need_dx=need_dx)
+    xr = x.float().requires_grad_(True)
+    wr, br = w.float().requires_grad_(True), b.float().requires_grad_(True)
+    torch.nn.functional.layer_norm(xr, (D,), wr, br, 1e-6).backward(dy.float())
+    assert (dx is None) == (not need_dx)
+    if need_dx:
+        close(dx, xr.grad, 2e-3 * xr.grad.abs().max().item(), 2.0 ** -7, "dx")
+    close(dw, wr.grad, 1e-4 * wr.grad.abs().max().item(), 1e-4, "dw")
+    close(db, br.grad, 1e-4 * br.grad.abs().max().item(), 1e-4, "db")
+    y = ops.layernorm(x.clone(), w, b, 1e-6)        # and the forward it differentiates
+    close(y, torch.nn.functional.layer_norm(x.float(), (D,), w.float(), b.float(), 1e-6), 1e-2, 2.0 ** -7, "fwd")
+
+
+
 @pytest.mark.parametrize("T,D", [(7, 256), (130, 1280), (65, 3584), (33, 5120), (1000, 3584), (700, 1280), (333, 8192)])
 def test_rmsnorm_fwd_bwd(T, D):
     from time_r1_b200 import ops

@@ -224,6 +224,91 @@ rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, cons
   }
 }
 
+// LayerNorm backward (Qwen2-VL PatchMerger ln_q, HF modeling_qwen2_vl.py:313-326): with xhat = (x - mean) * rstd and
+// gw = dy * w,  dx = rstd * (gw - mean(gw) - xhat * mean(gw * xhat)),  dw += dy * xhat,  db += dy.
+// Same walk as the RMSNorm backward (CTA strides over rows, fp32 partial dw / db in registers, one atomicAdd per column at
+// the end); the merger's [N, 1280] is a small fraction of a step, so rows are processed one at a time.
+template <int NIT>
+__global__ void __launch_bounds__(256)
+layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ w,
+                     bf16* __restrict__ dx, float* __restrict__ dw, float* __restrict__ db, int T, int D, float eps) {
+  __shared__ float red[33];
+  const int nv = D >> 3;
+  float dwacc[NIT][8], dbacc[NIT][8], wv[NIT][8];
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int i = threadIdx.x + it * 256;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dwacc[it][j] = dbacc[it][j] = wv[it][j] = 0.f;
+    if (i < nv) load8(w + i * 8, wv[it]);
+  }
+  for (size_t row = blockIdx.x; row < (size_t)T; row += gridDim.x) {
+    float xv[NIT][8], gv[NIT][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int i = threadIdx.x + it * 256;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) xv[it][j] = gv[it][j] = 0.f;
+      if (i < nv) {
+        load8(x + row * D + i * 8, xv[it]);
+        load8(dy + row * D + i * 8, gv[it]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += xv[it][j];
+    }
+    const float mean = block_sum(sum, red) / (float)D;
+    float var = 0.f;
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int i = threadIdx.x + it * 256;
+      if (i < nv)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) var += (xv[it][j] - mean) * (xv[it][j] - mean);
+    }
+    const float rstd = rsqrtf(block_sum(var, red) / (float)D + eps);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int i = threadIdx.x + it * 256;
+      if (i < nv)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xhat = (xv[it][j] - mean) * rstd, gw = gv[it][j] * wv[it][j];
+          s1 += gw;
+          s2 += gw * xhat;
+        }
+    }
+    const float m1 = block_sum(s1, red) / (float)D;
+    const float m2 = block_sum(s2, red) / (float)D;
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int i = threadIdx.x + it * 256;
+      if (i < nv) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xhat = (xv[it][j] - mean) * rstd;
+          dwacc[it][j] += gv[it][j] * xhat;
+          dbacc[it][j] += gv[it][j];
+          o[j] = rstd * (gv[it][j] * wv[it][j] - m1 - xhat * m2);
+        }
+        if (dx) store8(dx + row * D + i * 8, o);
+      }
+    }
+  }
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int i = threadIdx.x + it * 256;
+    if (i < nv)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (dw) atomicAdd(dw + i * 8 + j, dwacc[it][j]);
+        if (db) atomicAdd(db + i * 8 + j, dbacc[it][j]);
+      }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // RoPE: table build + rotation.  Channel i of the half-dim uses position axis axis_id[i] and inv_freq[i].
 //   table[t, i] = cos/sin(pos[axis_id[i], t] * inv_freq[i])
@@ -537,6 +622,21 @@ extern "C" int t1_rmsnorm_bwd(const void* dy, const void* x, const void* w, cons
     rmsnorm_bwd_kernel<4><<<grid, 256, 0, stream>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w, (const bf16*)dres,
                                                     (bf16*)dx, dw, T, D, eps);
   T1_CUDA_LAUNCH_CHECK("t1_rmsnorm_bwd");
+  return T1_OK;
+}
+
+// dx may be NULL (the merger's input is the frozen ViT output: only dw / db are needed).  dw / db accumulate (fp32).
+extern "C" int t1_layernorm_bwd(const void* dy, const void* x, const void* w, void* dx, float* dw, float* db, int T, int D,
+                                float eps, cudaStream_t stream) {
+  if (T == 0) return T1_OK;
+  T1_CHECK_ARG(T > 0 && D > 0 && D % 8 == 0 && D <= 4096, "t1_layernorm_bwd: D=%d must be a multiple of 8 and <= 4096", D);
+  const int nit = (D / 8 + 255) / 256;
+  const int grid = T < 2 * t1_num_sms() ? T : 2 * t1_num_sms();
+  if (nit <= 1)
+    layernorm_bwd_kernel<1><<<grid, 256, 0, stream>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w, (bf16*)dx, dw, db, T, D, eps);
+  else
+    layernorm_bwd_kernel<2><<<grid, 256, 0, stream>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w, (bf16*)dx, dw, db, T, D, eps);
+  T1_CUDA_LAUNCH_CHECK("t1_layernorm_bwd");
   return T1_OK;
 }
 

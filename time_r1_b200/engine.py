@@ -974,15 +974,14 @@ class Engine:
 
     def _merger_backward(self, st: ScoreState, dve: torch.Tensor, acc: bool):
         cfg = self.cfg
-        if not cfg.is_q25:
-            raise NotImplementedError("merger backward is built for the Qwen2.5-VL (RMSNorm) merger; the Qwen2-VL LayerNorm variant is forward-only")
         plan, x_vit = st.plan, st.x_vit
         keep: dict = {}
         N, vd, unit = plan.n_patches, cfg.vit_hidden, cfg.merge_unit
         Nv = N // unit
         # recompute the merger forward from the saved ViT output
         self.merger(x_vit, None, plan, "policy", keep=keep)
-        dm = ops.gather_rows(dve, self._i32(plan.window_index))            # back to window order
+        # Qwen2.5-VL: back to window order (Q25:512-513); Qwen2-VL has no post-merger permutation (Q2:771-790)
+        dm = ops.gather_rows(dve, self._i32(plan.window_index)) if cfg.is_q25 else dve
         W0, W2 = self.p("visual.merger.mlp.0.weight"), self.p("visual.merger.mlp.2.weight")
         f32s = torch.zeros(max(unit * vd, cfg.hidden_size), device=self.dev, dtype=F32)
         self._wgrad(dm, keep["g1"], "visual.merger.mlp.2.weight", acc)
@@ -996,7 +995,11 @@ class Engine:
         self._small_grad(f32s[:unit * vd], "visual.merger.mlp.0.bias", acc)
         dy4 = self._dgrad(da1, W0)
         f32s.zero_()
-        ops.rmsnorm_bwd(dy4.view(N, vd), x_vit, self.p("visual.merger.ln_q.weight"), 1e-6, f32s[:vd])
+        if cfg.is_q25:
+            ops.rmsnorm_bwd(dy4.view(N, vd), x_vit, self.p("visual.merger.ln_q.weight"), 1e-6, f32s[:vd])
+        else:      # Qwen2-VL: LayerNorm(eps 1e-6) with bias (HF modeling_qwen2_vl.py:313-326); the ViT output needs no gradient
+            ops.layernorm_bwd(dy4.view(N, vd), x_vit, self.p("visual.merger.ln_q.weight"), 1e-6, f32s[:vd], f32s[vd:2 * vd], need_dx=False)
+            self._small_grad(f32s[vd:2 * vd], "visual.merger.ln_q.bias", acc)
         self._small_grad(f32s[:vd], "visual.merger.ln_q.weight", acc)
 
     # ------------------------------------------------------------------------------------------

@@ -43,6 +43,7 @@ _SIGNATURES: dict[str, list] = {
     "t1_rmsnorm": [vp, vp, vp, vp, vp, i32, i32, f32, vp],
     "t1_layernorm": [vp, vp, vp, vp, vp, vp, i32, i32, f32, vp],
     "t1_rmsnorm_bwd": [vp, vp, vp, vp, vp, vp, i32, i32, f32, vp],
+    "t1_layernorm_bwd": [vp, vp, vp, vp, vp, vp, i32, i32, f32, vp],
     "t1_rope_table": [vp, i32, vp, vp, i32, vp, vp, vp],
     "t1_rope_apply": [vp, i64, i32, i32, i32, vp, vp, i32, i32, vp, i64, vp],
     "t1_copy_cols": [vp, i64, vp, i64, i32, i32, vp],

@@ -255,6 +255,15 @@ def rmsnorm_bwd(dy, x, w, eps, dw_f32, dres=None, out=None):
     return out
 
 
+def layernorm_bwd(dy, x, w, eps, dw_f32, db_f32, need_dx=True):
+    """LayerNorm backward (Qwen2-VL merger): dw_f32 / db_f32 accumulate; returns dx (or None when need_dx is False)."""
+    T, D = x.shape
+    _chk(dy, BF16, "dy"); _chk(x, BF16, "x")
+    out = torch.empty_like(x) if need_dx else None
+    call("t1_layernorm_bwd", ptr(dy), ptr(x), ptr(w), ptr(out), ptr(dw_f32), ptr(db_f32), T, D, float(eps), stream_ptr())
+    return out
+
+
 def rope_table(pos, axis_id, inv_freq):
     """pos [n_axes, T] int32 -> (cos, sin) [T, half] fp32 with channel i using axis axis_id[i]."""
     T = pos.shape[1]

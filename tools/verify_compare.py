@@ -1,0 +1,29 @@
+"""Compare two `bench.py --verify OUT.pt` records (same global batch at different world sizes): loss, gradient norm, the
+strided sample of the DP-averaged gradient and the post-step weights must agree to bf16 rounding.
+    python tools/verify_compare.py gpurun_out/verify_n1.pt gpurun_out/verify_n8.pt"""
+import json
+import sys
+
+import torch
+
+a, b = (torch.load(p) for p in sys.argv[1:3])
+ga, gb = a["grad_sample"].double(), b["grad_sample"].double()
+da, db = (a["w_after"] - a["w_before"]).double(), (b["w_after"] - b["w_before"]).double()
+moved = (da != 0) | (db != 0)
+rec = {
+    "worlds": [a["world"], b["world"]],
+    "loss": [a["loss"], b["loss"]], "loss_rel_diff": abs(a["loss"] - b["loss"]) / max(1e-12, abs(a["loss"])),
+    "grad_norm": [a["grad_norm"], b["grad_norm"]], "grad_norm_rel_diff": abs(a["grad_norm"] - b["grad_norm"]) / a["grad_norm"],
+    "grad_sample_rel_l2": float((ga - gb).norm() / ga.norm()),
+    "grad_sample_cosine": float(torch.nn.functional.cosine_similarity(ga, gb, dim=0)),
+    "weights_before_identical": bool(torch.equal(a["w_before"], b["w_before"])),
+    "update_cosine": float(torch.nn.functional.cosine_similarity(da, db, dim=0)),
+    "post_step_weights_bit_equal_frac": float((a["w_after"] == b["w_after"]).double().mean()),
+    "post_step_weights_max_abs_diff": float((a["w_after"] - b["w_after"]).abs().max()),
+    "moved_frac": float(moved.double().mean()), "n_sample": int(ga.numel()),
+}
+print(json.dumps(rec))
+ok = (rec["loss_rel_diff"] < 2e-3 and rec["grad_norm_rel_diff"] < 1e-2 and rec["grad_sample_rel_l2"] < 3e-2
+      and rec["weights_before_identical"] and rec["update_cosine"] > 0.97)
+print("VERIFY", "OK" if ok else "MISMATCH")
+sys.exit(0 if ok else 1)
