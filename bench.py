@@ -657,7 +657,7 @@ def run_verify(args):
         prompt = engine.Prompt(input_ids=ids, pixel_values=None, grid_thw=g, second_per_grid_ts=[1.0], frames=frames_host.to(dev))
         out = eng.grpo_step(prompt, lambda c, r=rewards: r, completion_override=comp, loss_scale=world / NGLOBAL)
         losses.append(out["loss"].double())
-    stride = 1021
+    stride = 16381
     gsample = eng.grads.buf[::stride].float().clone()
     loss = torch.stack(losses).sum().reshape(1) / world      # each rank holds (its groups) x world / 8: the DP mean equals the N=1 sum
     if world > 1:

@@ -98,11 +98,11 @@ def test_trainer_rejects_unsupported_paths():
     cfg = config.toy()
     mw = weights.ModelWeights(cfg, "cuda")
     mw.init_random(seed=1)
-    tr = TimeR1_Trainer(model=(cfg, mw), reward_funcs=rewards.format_reward, args=GRPOArguments(num_generations=2, max_completion_length=4, beta=0.0),
+    tr = TimeR1_Trainer(model=(cfg, mw), reward_funcs=rewards.format_reward, args=GRPOArguments(num_generations=2, max_completion_length=4, beta=0.0, fix_vit=True),
                         train_dataset=[], processing_class=StubTokenizer())
     with pytest.raises(ValueError):
         tr.compute_loss(tr.model, [{}, {}])
     with pytest.raises(NotImplementedError):
         tr.compute_loss(tr.model, [dict(problem="x", video_path="/nope.mp4")])
     with pytest.raises(NotImplementedError):
-        TimeR1_Trainer(model=(cfg, mw), reward_funcs=["some/reward-model"], args=GRPOArguments())
+        TimeR1_Trainer(model=(cfg, mw), reward_funcs=["some/reward-model"], args=GRPOArguments(fix_vit=True))

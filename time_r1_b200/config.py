@@ -124,7 +124,8 @@ def from_hf_config(d: dict) -> ModelConfig:
         vocab_size=t["vocab_size"], rms_norm_eps=t.get("rms_norm_eps", 1e-6), rope_theta=t.get("rope_theta", 1e6),
         mrope_section=tuple(rope.get("mrope_section", (16, 24, 24))),
         tie_word_embeddings=d.get("tie_word_embeddings", t.get("tie_word_embeddings", False)),
-        vit_hidden=v.get("hidden_size", v.get("embed_dim", 1280)), vit_depth=v.get("depth", 32),
+        # Qwen2-VL: embed_dim is the ViT width and vision hidden_size the merger's output width; Qwen2.5-VL: hidden_size is the width
+        vit_hidden=v.get("embed_dim", 1280) if fam == "qwen2_vl" else v.get("hidden_size", 1280), vit_depth=v.get("depth", 32),
         vit_heads=v.get("num_heads", 16),
         vit_intermediate=v.get("intermediate_size", int(v.get("embed_dim", 1280) * v.get("mlp_ratio", 4))),
         patch_size=v.get("patch_size", 14), temporal_patch_size=v.get("temporal_patch_size", 2),

@@ -280,18 +280,88 @@ class TimeR1_Trainer:
             {"type": "video", "video": example["video_path"], "video_start": example.get("video_start"),
              "video_end": example.get("video_end"), "total_pixels": 3584 * 28 * 28, "min_pixels": 16 * 28 * 28}]}]
 
+    def _host_prompt_inputs(self, example: dict, frames, fps: float) -> dict:
+        """What the reference does between the video reader and `generate` (timer1_trainer.py:536-556,
+        timer1_trainer_ft.py:543-566), minus the pixel work: chat template -> tokenise -> expand the single <|video_pad|>
+        to one token per merged patch (what the HF processor does from video_grid_thw).  The frames [T, 3, H, W] (0..255,
+        already resized by fetch_video_v3 to multiples of 28 inside the pixel budget, vision_process.py:440-475) stay
+        pixels: rescale / normalise / patchify run on the device (t1_video_patchify).  second_per_grid_ts =
+        temporal_patch_size / fps, as the HF processor derives it from `fps=`."""
+        import torch
+
+        cfg = self.model_cfg
+        pc = self.processing_class
+        if pc is None or not hasattr(pc, "apply_chat_template"):
+            raise RuntimeError("a processing_class with apply_chat_template() and a tokenizer is required to build prompts from raw rows")
+        fr = frames if isinstance(frames, torch.Tensor) else torch.as_tensor(np.asarray(frames))
+        if fr.dim() != 4 or fr.shape[1] != cfg.in_channels:
+            raise ValueError(f"video frames must be [T, {cfg.in_channels}, H, W], got {tuple(fr.shape)}")
+        T, _, H, W = fr.shape
+        unit = cfg.patch_size * cfg.spatial_merge_size
+        if H % unit or W % unit:
+            raise ValueError(f"frame size {H}x{W} is not a multiple of {unit}: resize with smart_resize first (vision_process.py:60-90)")
+        if T % cfg.temporal_patch_size:                       # the HF video processor repeats the last frame
+            fr = torch.cat([fr, fr[-1:].expand(cfg.temporal_patch_size - T % cfg.temporal_patch_size, -1, -1, -1)], 0)
+            T = fr.shape[0]
+        grid = (T // cfg.temporal_patch_size, H // cfg.patch_size, W // cfg.patch_size)
+        nv = grid[0] * grid[1] * grid[2] // cfg.merge_unit
+        text = pc.apply_chat_template(self.make_conversation_video(example), tokenize=False, add_generation_prompt=True)
+        tok = getattr(pc, "tokenizer", pc)
+        ids = tok(text, add_special_tokens=False)["input_ids"]
+        ids = np.asarray(ids[0] if len(ids) and isinstance(ids[0], (list, tuple, np.ndarray)) else ids, dtype=np.int64).reshape(-1)
+        where = np.nonzero(ids == cfg.video_token_id)[0]
+        if len(where) != 1:
+            raise ValueError(f"the chat template must produce exactly one video placeholder token ({cfg.video_token_id}), found {len(where)}")
+        ids = np.concatenate([ids[:where[0]], np.full(nv, cfg.video_token_id, np.int64), ids[where[0] + 1:]])
+        if fr.dtype != torch.uint8:
+            fr = fr.to(torch.float32)
+        return dict(input_ids=ids, video_frames=fr, video_grid_thw=np.array([grid]),
+                    second_per_grid_ts=[cfg.temporal_patch_size / float(fps)])
+
+    def _default_vision_processor(self, example: dict) -> dict:
+        """main.py rows (`video_path` only, main.py:455-468): the reference's own reader, `process_vision_info_v3`
+        (src/utils/vision_process.py:547-578, decord + bicubic resize on the host) when that package is importable — this
+        repository's `src/` is a namespace package, so with the reference checkout on PYTHONPATH `src.utils` resolves there."""
+        try:
+            from src.utils import process_vision_info_v3
+        except Exception as e:
+            raise NotImplementedError(
+                "raw video decoding (timer1_trainer.py:518-534) is the reference's host-side reader: put the reference checkout "
+                "on PYTHONPATH (src.utils.process_vision_info_v3 needs decord / torchvision), or pass vision_processor="
+                "callable(example) -> {input_ids, pixel_values_videos | video_frames, video_grid_thw, second_per_grid_ts}, or "
+                f"pre-processed dataset rows ({type(e).__name__}: {e})") from e
+        messages = [{"role": "user", "content": [{"type": "video", "video": example["video_path"], "total_pixels": 3584 * 28 * 28,
+                                                  "min_pixels": 16 * 28 * 28}]}]                      # timer1_trainer.py:518-530
+        _, video_inputs, video_kwargs = process_vision_info_v3([messages], return_video_kwargs=True)
+        return self._host_prompt_inputs(example, video_inputs[0], video_kwargs["fps"][0])
+
+    @staticmethod
+    def _unwrap_ft(example: dict):
+        """`_ft` rows (finetune.py:596-621, timer1_trainer_ft.py:551-566): video_inputs = [torch.load(video_inputs.pt)] (a list
+        holding the list process_vision_info_v3 returned), video_kwargs = [{"fps": [f]}]; tolerate the un-nested forms."""
+        v = example["video_inputs"]
+        while isinstance(v, (list, tuple)):
+            v = v[0]
+        kw = example.get("video_kwargs", {"fps": 2.0})
+        while isinstance(kw, (list, tuple)):
+            kw = kw[0]
+        fps = kw.get("fps", 2.0)
+        while isinstance(fps, (list, tuple)):
+            fps = fps[0]
+        return v, float(fps)
+
     def _prompt_from_example(self, example: dict):
         import torch
 
         from .engine import Prompt
 
         if "input_ids" not in example:
-            if self.vision_processor is None:
-                raise NotImplementedError(
-                    "raw video decoding + HF processor (timer1_trainer.py:518-556) is a host-side stage outside this "
-                    "engine; pass vision_processor=callable(example) -> {input_ids, pixel_values_videos, video_grid_thw, "
-                    "second_per_grid_ts} or pre-processed dataset rows")
-            example = {**example, **self.vision_processor(example)}
+            if example.get("video_inputs") is not None:
+                example = {**example, **self._host_prompt_inputs(example, *self._unwrap_ft(example))}
+            elif self.vision_processor is not None:
+                example = {**example, **self.vision_processor(example)}
+            else:
+                example = {**example, **self._default_vision_processor(example)}
         grid = [tuple(int(v) for v in g) for g in np.asarray(example["video_grid_thw"]).reshape(-1, 3)]
         if example.get("video_frames") is not None:
             # resized frames [T, 3, H, W] (uint8 / fp32, 0..255) as fetch_video_v3 returns them (vision_process.py:440-475):
@@ -358,6 +428,8 @@ class TimeR1_Trainer:
             completions = self._decode(comp_ids)
             if _is_conversational(example):
                 completions = [[{"role": "assistant", "content": c}] for c in completions]
+            # every dataset column except prompt / completion (timer1_trainer.py:685-694); the tensors this engine's
+            # pre-processed layout adds are not dataset columns of the reference and stay out
             cols = {k: [example[k]] * G for k in example if k not in ("prompt", "completion", "input_ids", "pixel_values_videos", "video_frames", "video_grid_thw", "second_per_grid_ts")}
             out = np.zeros((G, len(self.reward_funcs)), np.float32)
             for i, rf in enumerate(self.reward_funcs):
@@ -628,7 +700,10 @@ def hf_config_dict(cfg: ModelConfig) -> dict:
         vision.update(intermediate_size=cfg.vit_intermediate, window_size=cfg.window_size,
                       fullatt_block_indexes=list(cfg.fullatt_block_indexes), tokens_per_second=cfg.tokens_per_second)
     else:
-        vision.update(embed_dim=cfg.vit_hidden, mlp_ratio=cfg.vit_intermediate / cfg.vit_hidden)
+        ratio = cfg.vit_intermediate / cfg.vit_hidden            # Qwen2VLVisionConfig.mlp_ratio is an int (4 in every release)
+        # Qwen2VLVisionConfig: embed_dim = ViT width, hidden_size = the merger's OUTPUT width (the LLM hidden size)
+        vision.update(embed_dim=cfg.vit_hidden, hidden_size=cfg.hidden_size, mlp_ratio=int(ratio) if ratio == int(ratio) else ratio)
+        vision.pop("out_hidden_size")
     return {
         "model_type": "qwen2_5_vl" if q25 else "qwen2_vl",
         "architectures": ["Qwen2_5_VLForConditionalGeneration" if q25 else "Qwen2VLForConditionalGeneration"],
