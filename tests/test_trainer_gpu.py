@@ -106,3 +106,39 @@ def test_trainer_rejects_unsupported_paths():
         tr.compute_loss(tr.model, [dict(problem="x", video_path="/nope.mp4")])
     with pytest.raises(NotImplementedError):
         TimeR1_Trainer(model=(cfg, mw), reward_funcs=["some/reward-model"], args=GRPOArguments(fix_vit=True))
+
+
+def test_ft_trainer_on_the_real_engine_with_finetune_py_rows(tmp_path):
+    """TimeR1_Trainer_ft end to end on the CUDA engine from finetune.py-layout rows (video_inputs = [[frames]], video_kwargs =
+    [{"fps": [f]}], timer1_trainer_ft.py:551-566): host tokenise + pad expansion, device patchify, rollout, scoring, metric
+    functions per group, clip-ratio metrics, optimizer step."""
+    from src.time_r1 import TimeR1_Trainer_ft
+    from test_dropin_rows_cpu import FakeProcessor
+    from time_r1_b200 import config, rewards, weights
+    from time_r1_b200.trainer import GRPOArguments
+
+    cfg = config.toy()
+    mw = weights.ModelWeights(cfg, "cuda")
+    mw.init_random(seed=1, std=0.05)
+
+    class Proc(FakeProcessor, StubTokenizer):
+        pass
+
+    g = torch.Generator().manual_seed(0)
+    data = [dict(problem=f"event {i}", video_path=f"/v/{i}.mp4", video_start=None, video_end=None, solution=(2.0 + i, 9.0 + i), durations=30.0,
+                 preprocessed_path=f"/pre/{i}", use_preprocessed=[True],
+                 video_inputs=[[torch.randint(0, 256, (4, 3, 112, 112 + 56 * (i % 2)), generator=g).float()]], video_kwargs=[{"fps": [2.0]}])
+            for i in range(4)]
+    args = GRPOArguments(output_dir=str(tmp_path), num_generations=4, max_completion_length=6, temperature=1.0, beta=0.04, learning_rate=1e-4,
+                         gradient_accumulation_steps=2, max_steps=2, logging_steps=1, fix_vit=True, save_strategy="no", prompt_type="v2")
+    tr = TimeR1_Trainer_ft(model=(cfg, mw), reward_funcs=[rewards.iou_timestamp_reward, rewards.format_reward],
+                           metric_funcs=list(rewards.metric_funcs_registry.values()), args=args, train_dataset=data, processing_class=Proc(cfg))
+    w0 = mw.train.buf.clone()
+    tr.train()
+    assert tr.state.global_step == 2 and not torch.equal(w0, mw.train.buf)
+    log = tr.state.log_history[-1]
+    for key in ["loss", "grad_norm", "completion_length", "rewards/iou_timestamp_reward", "rewards/format_reward", "reward", "reward_std", "kl",
+                "generation_entropy", "clip_ratio/low_mean", "clip_ratio/low_min", "clip_ratio/high_mean", "clip_ratio/high_max",
+                "clip_ratio/region_mean"] + [f"metrics/{k}" for k in rewards.metric_funcs_registry]:
+        assert key in log and np.isfinite(log[key]), key
+    assert "provide the start and end times" in tr.processing_class.seen[0]["content"][0]["text"].lower()      # prompt v2
