@@ -485,6 +485,10 @@ def run_ours(args):
             nxt = make_prompts(e2e)                  # e2e: the H2D copy of the next step's frames is issued here
             pending[e2e] = (nxt, eng.prefetch_vit(nxt))
         gn = eng.optimizer_step()
+        if timers is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            timers["_events"].append(("optimizer(+vit prefetch issue)", ev))
         if e2e:
             return float(sum(o["loss"].item() for o in outs)), float(gn.item())   # D2H of the step's result
         return outs[0]["loss"], gn

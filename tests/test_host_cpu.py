@@ -263,3 +263,68 @@ def test_ft_clip_ratio_metrics_across_two_ranks_gloo():
     for rank, m in res:
         assert m == {"clip_ratio/low_mean": 0.25, "clip_ratio/low_min": 0.125, "clip_ratio/high_mean": 0.375,
                      "clip_ratio/high_max": 0.5, "clip_ratio/region_mean": 0.625}, (rank, m)
+
+
+def _bucket_worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    from time_r1_b200.dist_utils import BucketPlan
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n = 4096
+    plan = BucketPlan(n, world, n_buckets=5, align=16)
+    param = torch.randn(n, generator=torch.Generator().manual_seed(0))
+    grad = torch.randn(n, generator=torch.Generator().manual_seed(100 + rank))
+    master = plan.gather_shard(param, rank, torch.empty(plan.shard))
+    shard_g = torch.zeros(plan.shard)
+    # the backward finishes the buffer from its end: hand the buckets out as the "final from" offset moves down
+    order = []
+    plan.reset()
+    for done_from in (n, 3000, 2999, 1700, 900, 0):
+        for b in plan.ready_buckets(done_from):
+            order.append(b)
+            plan.reduce_scatter(b, grad, shard_g, rank)
+    assert plan.ready_buckets(0) == []
+    m = 0.1 * shard_g
+    v = 0.001 * shard_g * shard_g
+    new = master - 1e-3 * (m / 0.1) / ((v / 0.001).sqrt() + 1e-8)
+    for b in range(len(plan)):
+        lo, hi = plan.slice_of(b, rank)
+        a, z = plan.shard_range(b)
+        param[lo:hi] = new[a:z]                      # AdamW writes the slice in place
+        plan.all_gather(b, param, rank)
+    q.put((rank, param.clone(), order, plan.bounds))
+    dist.destroy_process_group()
+
+
+def test_bucketed_zero2_exchange_equals_unsharded_step_gloo_world2():
+    """dist_utils.BucketPlan (the engine's overlapped ZeRO-2 exchange): buckets handed out in backward order, reduce-scatter
+    per bucket into the contiguous shard, AdamW per slice, in-place all-gather == one unsharded AdamW step on the mean gradient."""
+    import torch.multiprocessing as mp
+
+    from time_r1_b200.dist_utils import BucketPlan
+
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_bucket_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = sorted((q.get(timeout=120) for _ in range(world)), key=lambda t: t[0])
+    for p in ps:
+        p.join(60)
+    n = 4096
+    param = torch.randn(n, generator=torch.Generator().manual_seed(0))
+    grad = sum(torch.randn(n, generator=torch.Generator().manual_seed(100 + r)) for r in range(world)) / world
+    ref = param - 1e-3 * grad / (grad.abs() + 1e-8)
+    for rank, p, order, bounds in res:
+        assert torch.allclose(p, ref, atol=1e-6), f"rank {rank}"
+        assert order == sorted(order, reverse=True) and len(order) == len(bounds)       # last bucket first, each exactly once
+    # layout facts the engine relies on
+    plan = BucketPlan(7_667_998_720, 8)
+    assert len(plan) == 32 and plan.shard * 8 == plan.numel and all((hi - lo) % (8 * 512) == 0 for lo, hi in plan.bounds)
+    assert [plan.shard_range(b)[1] - plan.shard_range(b)[0] for b in range(32)] == plan.slice_len
+    one = BucketPlan(4096, 1)
+    assert one.bounds == [(0, 4096)] and one.slice_of(0, 0) == (0, 4096)

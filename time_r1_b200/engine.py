@@ -83,16 +83,38 @@ class Engine:
         self.ref: FlatParams | None = weights.train.clone() if (with_ref and run.beta != 0.0) else None
         self.grads = weights.train.like(zero=True)
         self.grad_fresh = True
-        # ---- ZeRO-style shard of the optimizer state over the flat trainable buffer ----
+        # ---- ZeRO-2 shard of the optimizer state over the flat trainable buffer, in buckets (dist_utils.BucketPlan) ----
+        import os as _os
+
+        from .dist_utils import BucketPlan
+
         n = weights.train.numel
-        assert n % (world_size * 4) == 0
-        self.shard = n // world_size
-        self.shard_lo = rank * self.shard
+        assert n % (world_size * 512) == 0
+        self.plan = BucketPlan(n, world_size, n_buckets=int(_os.environ.get("T1_ZERO_BUCKETS", getattr(run, "zero_buckets", 32))))
+        self.shard = self.plan.shard
+        self.shard_lo = 0 if world_size == 1 else None          # one contiguous range only without sharding
         self.master = torch.empty(self.shard, device=self.dev, dtype=F32)
-        ops.bf16_to_f32(weights.train.buf[self.shard_lo:self.shard_lo + self.shard], self.master)
+        self.reset_master_from_params()
         self.adam_m = torch.zeros(self.shard, device=self.dev, dtype=F32)
         self.adam_v = torch.zeros(self.shard, device=self.dev, dtype=F32)
+        self.shard_g = torch.empty(self.shard, device=self.dev, dtype=BF16) if world_size > 1 else None
         self.opt_step = 0
+        # gradient reduce-scatter overlapped with the LAST micro-batch's backward: bucket b is reduced on NCCL's stream as soon
+        # as the backward has finished every gradient at or above its start; a communicator limited to a few CTAs leaves the
+        # tensor-bound backward its SMs (the collective has the whole backward to hide in)
+        self.zero_overlap = world_size > 1 and _os.environ.get("T1_ZERO_OVERLAP", "1") != "0" and getattr(run, "zero_overlap", True)
+        self.nccl_ctas = int(_os.environ.get("T1_NCCL_MAX_CTAS", getattr(run, "zero_nccl_ctas", 8)))
+        self.pg_rs = process_group
+        if self.zero_overlap and self.nccl_ctas > 0:
+            import torch.distributed as dist
+
+            if dist.get_backend(process_group) == "nccl":
+                opts = dist.ProcessGroupNCCL.Options()
+                opts.config.max_ctas = self.nccl_ctas
+                opts.config.min_ctas = 1
+                self.pg_rs = dist.new_group(backend="nccl", pg_options=opts)      # collective call: every rank builds an Engine
+        self._grad_version = 0
+        self._rs = None          # {"version", "works"}: reduce-scatters issued during the last backward
         # ---- rotary constants (computed the way HF does, in fp32 on the host) ----
         hd = cfg.head_dim
         self.inv_freq_llm = (1.0 / (cfg.rope_theta ** (torch.arange(0, hd, 2, dtype=F32) / hd))).to(self.dev)
@@ -143,6 +165,25 @@ class Engine:
         if keep is None:
             return None
         return {k: (v if k == "lse" else [t[lo:hi] for t in v]) for k, v in keep.items()}
+
+    def reset_master_from_params(self):
+        """fp32 master weights of this rank's shard <- the bf16 parameters (construction, checkpoints without optimizer state)."""
+        for b in range(len(self.plan)):
+            lo, hi = self.plan.slice_of(b, self.rank)
+            a, z = self.plan.shard_range(b)
+            ops.bf16_to_f32(self.w.train.buf[lo:hi], self.master[a:z])
+
+    def _reduce_ready(self, done_from: int):
+        """Issue the asynchronous reduce-scatter of every bucket whose gradients are final (all offsets >= done_from)."""
+        rs = self._rs
+        if rs is None:
+            return
+        for b in self.plan.ready_buckets(done_from):
+            if not rs["works"]:
+                sms = torch.cuda.get_device_properties(self.dev).multi_processor_count
+                load_lib().t1_gemm_max_ctas(max(1, sms - self.nccl_ctas) if self.nccl_ctas > 0 else 0)
+                rs["capped"] = True
+            rs["works"].append(self.plan.reduce_scatter(b, self.grads.buf, self.shard_g, self.rank, group=self.pg_rs, async_op=True))
 
     # ------------------------------------------------------------------------------------------
     # parameter access
@@ -859,9 +900,25 @@ class Engine:
     def _small_grad(self, f32: torch.Tensor, name: str, acc: bool):
         ops.f32_to_bf16(f32, self._gview(name).view(-1), accumulate=acc)
 
-    def backward(self, st: ScoreState, dlogp: torch.Tensor):
-        """Accumulate d loss / d params into self.grads given d loss / d logp [G, C] (fp32)."""
+    def backward(self, st: ScoreState, dlogp: torch.Tensor, overlap_reduce: bool = False):
+        """Accumulate d loss / d params into self.grads given d loss / d logp [G, C] (fp32).
+        overlap_reduce: this is the LAST backward before optimizer_step — reduce-scatter each gradient bucket as soon as it
+        is final (no-op at world size 1 or with T1_ZERO_OVERLAP=0)."""
         cfg = self.cfg
+        self._grad_version += 1
+        self._rs = None
+        if overlap_reduce and self.zero_overlap:
+            self.plan.reset()
+            self._rs = dict(version=self._grad_version, works=[], capped=False)
+        try:
+            self._backward(st, dlogp)
+        finally:
+            if self._rs is not None and self._rs.get("capped"):
+                load_lib().t1_gemm_max_ctas(0)
+
+    def _backward(self, st: ScoreState, dlogp: torch.Tensor):
+        cfg = self.cfg
+        off = lambda name: self.grads.layout[name][0]
         if not self.run.fix_vit:
             raise NotImplementedError("ViT-block gradients (fix_vit=False) are not built; every reference script sets --fix_vit true")
         acc = not self.grad_fresh
@@ -892,12 +949,16 @@ class Engine:
             ops.gemm(dlog, st.hsel[a:b], out=self._gview(head_name), accumulate=acc or not first, a_t=True, b_t=True)
             first = False
             del dlog
+        if not cfg.tie_word_embeddings:
+            self._reduce_ready(off(head_name))                              # lm_head is the last tensor of the flat buffer
         dh = torch.zeros((T, D), device=dev, dtype=BF16)
         ops.scatter_rows(dhsel, st.logit_rows, dh, accumulate=True)         # prompt row P-1 receives G contributions
         # ---- final norm ----
         f32s = torch.zeros(max(cfg.qkv_dim, 2 * D), device=dev, dtype=F32)
         dx = ops.rmsnorm_bwd(dh, st.ckpt[L], self.p("model.norm.weight"), eps, f32s[:D])
         self._small_grad(f32s[:D], "model.norm.weight", acc)
+        if not cfg.tie_word_embeddings:
+            self._reduce_ready(off("model.norm.weight"))
         del dh
         # ---- layers, last to first, recomputing each from its checkpointed input ----
         h = torch.empty((T, D), device=dev, dtype=BF16)
@@ -964,12 +1025,15 @@ class Engine:
             f32s.zero_()
             dx = ops.rmsnorm_bwd(dhh, x_in, self.p(pre + "input_layernorm.weight"), eps, f32s[:D], dres=dxm, out=xm)
             self._small_grad(f32s[:D], pre + "input_layernorm.weight", acc)
+            if not cfg.tie_word_embeddings:
+                self._reduce_ready(off(pre + "input_layernorm.weight"))    # layer l is complete: everything above it is final
             dx = dx.clone() if l > 0 else dx                                 # xm is overwritten by the next recompute
         # ---- embeddings: text rows scatter-add into the table gradient; vision rows flow into the merger ----
         ops.scatter_rows(dx, st.text_scatter_idx, self._gview(embed_name), accumulate=True)
         if st.vision_rows.numel() > 0:
             dve = ops.gather_rows(dx, st.vision_rows)                       # [Nv, D] in original merged-token order
             self._merger_backward(st, dve, acc)
+        self._reduce_ready(0)
         self.grad_fresh = False
 
     def _merger_backward(self, st: ScoreState, dve: torch.Tensor, acc: bool):
@@ -1006,32 +1070,47 @@ class Engine:
     # optimizer: global-norm clip + AdamW on this rank's shard of the flat buffer (ZeRO-2 semantics)
     # ------------------------------------------------------------------------------------------
     def optimizer_step(self, lr: float | None = None, grad_scale: float = 1.0) -> torch.Tensor:
-        """Returns the (pre-clip) global gradient norm as a 1-element device tensor."""
+        """Returns the (pre-clip) global gradient norm as a 1-element device tensor.
+        world > 1: bucketed reduce-scatter (those issued during the last backward are only waited for) -> grad norm ->
+        per bucket AdamW on this rank's slice + asynchronous IN-PLACE all-gather of the bucket (bucket b's gather runs under
+        bucket b+1's AdamW); the main stream waits for the gathers before it returns to the caller's work."""
         run = self.run
         lr = run.learning_rate if lr is None else lr
         g = self.grads.buf
+        plan = self.plan
         if self.world > 1:
             import torch.distributed as dist
 
-            shard_g = torch.empty(self.shard, device=self.dev, dtype=BF16)
-            dist.reduce_scatter_tensor(shard_g, g, op=dist.ReduceOp.AVG, group=self.pg)   # DP-mean of the gradients
+            rs = self._rs
+            if rs is None or rs["version"] != self._grad_version:      # nothing (valid) in flight: reduce everything now
+                plan.reset()
+                rs = dict(works=[])
+            for b in plan.ready_buckets(0):
+                rs["works"].append(plan.reduce_scatter(b, g, self.shard_g, self.rank, group=self.pg, async_op=True))
+            for w in rs["works"]:
+                if w is not None:
+                    w.wait()                                            # stream-level: orders the main stream after the collective
+            self._rs = None
+            shard_g = self.shard_g
         else:
             shard_g = g
         gsq = torch.zeros(1, device=self.dev, dtype=F32)
         ops.sumsq(shard_g, gsq)
         if self.world > 1:
-            import torch.distributed as dist
-
             dist.all_reduce(gsq, group=self.pg)
         self.opt_step += 1
-        p_shard = self.w.train.buf[self.shard_lo:self.shard_lo + self.shard]
-        ops.adamw(self.master, self.adam_m, self.adam_v, shard_g, p_shard, lr, run.adam_beta1, run.adam_beta2,
-                  run.adam_eps, run.weight_decay, self.opt_step, gnorm_sq=gsq, max_norm=run.max_grad_norm,
-                  grad_scale=grad_scale)
-        if self.world > 1:
-            import torch.distributed as dist
-
-            dist.all_gather_into_tensor(self.w.train.buf, p_shard.clone(), group=self.pg)
+        works = []
+        for b in range(len(plan)):
+            lo, hi = plan.slice_of(b, self.rank)
+            a, z = plan.shard_range(b)
+            ops.adamw(self.master[a:z], self.adam_m[a:z], self.adam_v[a:z], shard_g[a:z], self.w.train.buf[lo:hi], lr, run.adam_beta1,
+                      run.adam_beta2, run.adam_eps, run.weight_decay, self.opt_step, gnorm_sq=gsq, max_norm=run.max_grad_norm,
+                      grad_scale=grad_scale)
+            if self.world > 1:
+                works.append(plan.all_gather(b, self.w.train.buf, self.rank, group=self.pg, async_op=True))
+        for w in works:
+            if w is not None:
+                w.wait()
         self.grad_fresh = True
         self._invalidate_after_update()
         return gsq.sqrt() * grad_scale
@@ -1050,13 +1129,16 @@ class Engine:
                                     timers=timers, vit_prefetch=vit_prefetch)[0]
 
     def grpo_multi_step(self, prompts: list, reward_fns: list, seed: int | None = None, completion_overrides=None,
-                        loss_scale: float = 1.0, timers: dict | None = None, vit_prefetch: dict | None = None) -> list:
+                        loss_scale: float = 1.0, timers: dict | None = None, vit_prefetch: dict | None = None,
+                        last_before_optimizer: bool = True) -> list:
         """The micro-batches of ONE optimizer step (gradient accumulation, train_rl.sh:27), each a prompt-group:
         ViT per group -> joint rollout (shared weight stream) -> per group: mask, policy/ref scoring, rewards (host
         callback), advantage, loss, backward (gradients accumulate).
         reward_fn(completion_ids_host [G, C] int64 numpy) -> rewards_per_func [G, n_funcs] float32 numpy; a reward_fn
         carrying a `.device` attribute (callable: completion ids [G, C] int32 device tensor -> [G, n_funcs] fp32 device
         tensor, e.g. rewards.DeviceRewards) is evaluated on the device instead and the completions are not copied out.
+        last_before_optimizer: optimizer_step follows this call (the gradient buckets of the last group's backward are
+        reduce-scattered while that backward still runs; a later backward simply invalidates them).
         Returns one dict of device tensors per group."""
         run, cfg = self.run, self.cfg
         G, C = run.num_generations, run.max_completion_length
@@ -1132,7 +1214,7 @@ class Engine:
             loss, dlogp, stats = ops.grpo_loss(logp, ref_logp, ent, adv, mask, run.beta, run.epsilon_low, run.epsilon_high,
                                                run.use_grpo, loss_scale=loss_scale)
             mark("reward_loss")
-            self.backward(st, dlogp)
+            self.backward(st, dlogp, overlap_reduce=last_before_optimizer and gi == len(prompts) - 1)
             mark("backward")
             del st
             outs.append(dict(loss=loss, stats=stats, rewards=rewards, rewards_per_func=rpf_dev, advantages=adv, reward_std=std,

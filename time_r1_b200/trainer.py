@@ -625,7 +625,8 @@ class TimeR1_Trainer:
         if not getattr(self.args, "save_only_model", False):
             os.makedirs(d, exist_ok=True)
             torch.save({"master": self.engine.master, "m": self.engine.adam_m, "v": self.engine.adam_v,
-                        "opt_step": self.engine.opt_step, "shard_lo": self.engine.shard_lo},
+                        "opt_step": self.engine.opt_step, "world": self.world, "rank": self.rank,
+                        "buckets": getattr(getattr(self.engine, "plan", None), "bounds", None)},
                        os.path.join(d, f"optimizer_rank{self.rank}.pt"))
 
     def _load_checkpoint(self, d: str) -> int:
@@ -640,12 +641,14 @@ class TimeR1_Trainer:
         opt = os.path.join(d, f"optimizer_rank{self.rank}.pt")
         if os.path.exists(opt):
             s = torch.load(opt, map_location=self.device)
+            plan = getattr(self.engine, "plan", None)
+            if s.get("world", self.world) != self.world or (plan is not None and s.get("buckets") not in (None, plan.bounds)):
+                raise ValueError(f"{opt} was written with another world size / bucket layout: the sharded optimizer state does not "
+                                 "line up (resume with the same number of ranks, or delete optimizer_rank*.pt to restart AdamW)")
             self.engine.master.copy_(s["master"]); self.engine.adam_m.copy_(s["m"]); self.engine.adam_v.copy_(s["v"])
             self.engine.opt_step = s["opt_step"]
         else:
-            from . import ops
-
-            ops.bf16_to_f32(self.weights.train.buf[self.engine.shard_lo:self.engine.shard_lo + self.engine.shard], self.engine.master)
+            self.engine.reset_master_from_params()
         st = os.path.join(d, "trainer_state.json")
         return json.load(open(st)).get("global_step", 0) if os.path.exists(st) else 0
 
