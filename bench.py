@@ -47,7 +47,11 @@ def parse_args():
     ap.add_argument("--model", default="qwen2.5-vl-7b")
     ap.add_argument("--slots", type=int, default=16, help="temporal slots of 32x32 patches (16 -> cfg2, 32 -> cfg3, 64 -> cfg5)")
     ap.add_argument("--grid", default=None, help="t,h,w patch grid of the video instead of (slots,32,32), e.g. 147,6,12 = a 147 s "
-                    "TimeRFT clip at 84x168 (cfg4, SURVEY 8d); frames are 2t x 3 x 14h x 14w")
+                    "TimeRFT clip at 84x168 (cfg4, SURVEY 8d); frames are 2t x 3 x 14h x 14w; 'timerft' = a different TimeRFT-shaped "
+                    "clip per prompt-group (cfg4: (147,6,12), (8,26,46), (60,16,28), (384,6,10) dealt over ranks and micro-batches)")
+    ap.add_argument("--filter-pass", type=int, default=0, metavar="N",
+                    help="cfg4: after the timed steps run ONE per-epoch sample-filtering pass (train_rl_SF.sh:71-111) over N synthetic "
+                         "samples per rank — greedy rollout, difficulty = 100 x IoU, 0 < IoU <= 0.7 selection — and report its throughput")
     ap.add_argument("--group-size", type=int, default=8)
     ap.add_argument("--completion-len", type=int, default=200)
     ap.add_argument("--groups-per-step", type=int, default=2,
@@ -71,11 +75,23 @@ def parse_args():
     return ap.parse_args()
 
 
-def grid_of(args):
+# cfg4: TimeRFT clips at 360x640 through the reference's smart_resize — an 8.9 s, a 30 s, a 147 s (dataset mean)
+# and a >= 384 s video
+TIMERFT_GRIDS = [(147, 6, 12), (8, 26, 46), (60, 16, 28), (384, 6, 10)]
+
+
+def grid_of(args, index: int = 0):
+    """Patch grid of prompt-group `index` (global index over ranks and micro-batches)."""
+    if args.grid == "timerft":
+        return TIMERFT_GRIDS[index % len(TIMERFT_GRIDS)]
     return tuple(int(v) for v in args.grid.split(",")) if args.grid else (args.slots, 32, 32)
 
 
 def workload_name(args):
+    if args.grid == "timerft":
+        gs = ", ".join(f"({t},{h},{w})" for t, h, w in TIMERFT_GRIDS)
+        return (f"cfg4: {args.model} dims, TimeRFT-shaped clips {gs} dealt over prompt-groups, G={args.group_size}, C={args.completion_len}, "
+                f"{args.groups_per_step} prompt-group(s) per GPU per optimizer step")
     t, h, w = grid_of(args)
     return (f"cfg2-family: {args.model} dims, grid ({t},{h},{w}) = {t * h * w // 4} vision tokens, "
             f"G={args.group_size}, C={args.completion_len}, {args.groups_per_step} prompt-group(s) per GPU per optimizer step "
@@ -413,6 +429,49 @@ def decode_step_microbench(eng, Ps, G: int, C: int):
             "achieved": round((w_bytes + kv_bytes) / ms / 1e6, 1), "unit": "GB/s"}
 
 
+def filter_pass(args, eng, cfg, rank, world, dev):
+    """One per-epoch sample-filtering pass (scripts/posttrain/train_rl_SF.sh:71-111) over --filter-pass synthetic TimeRFT-shaped
+    samples per rank: greedy rollout (T = 0, 64 new tokens: random-init models never stop) batched 4 prompts per decode
+    batch, difficulty = 100 x IoU on the device (t1_iou_reward mode 2), 0 < IoU <= 0.7 + difficulty-sorted linspace
+    selection over the rows of ALL ranks (process_data.py:61-80).  Device-timed, max over ranks."""
+    import torch
+    import torch.distributed as dist
+
+    from time_r1_b200 import engine, filtering
+
+    rows = json.load(open(os.path.join(ROOT, "tests", "golden", "iou_train_2k5.json")))
+    n = args.filter_pass
+    samples = []
+    for i in range(n):
+        gidx = rank * n + i
+        ids, frames_host, grid = synthetic_prompt(cfg, TIMERFT_GRIDS[gidx % len(TIMERFT_GRIDS)], 10_000 + gidx, 0, dev)
+        row = rows[gidx % len(rows)]
+        samples.append(dict(qid=gidx, timestamp=row["gt"], duration=row["duration"],
+                            _prompt=engine.Prompt(input_ids=ids, pixel_values=None, grid_thw=grid, second_per_grid_ts=[1.0],
+                                                  frames=frames_host.to(dev, non_blocking=True))))
+    decode = lambda ids: bytes(int(t) % 256 for t in ids).decode("latin-1")
+    flt = filtering.GreedyFilter(eng, lambda s: s["_prompt"], decode, max_new_tokens=64, batch=4)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    diff = flt.difficulties(samples)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    merged = diff
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        parts = [None] * world
+        dist.all_gather_object(parts, diff)
+        merged = {k: v for p_ in parts for k, v in p_.items()}
+    annotated = [dict(qid=q, difficulty=d["difficulty"], pred=d["pred"]) for q, d in sorted(merged.items())]
+    selected = filtering.select_0070(annotated, k=max(1, len(annotated) // 2))
+    return {"samples": n * world, "ms": round(float(ms.item()), 1), "samples_per_s": round(n * world / (float(ms.item()) / 1e3), 2),
+            "max_new_tokens": 64, "decode_batch": 4, "annotated": len(annotated), "selected_0070": len(selected)}
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -449,7 +508,7 @@ def run_ours(args):
     eng = engine.Engine(cfg, mw, run, rank=rank, world_size=world, process_group=pg)
     NG = args.groups_per_step
     rewards = [TemplateRewards(G, rank * NG + i, args.reward_route) for i in range(NG)]
-    inputs = [synthetic_prompt(cfg, grid_of(args), rank * NG + i, 0, dev) for i in range(NG)]
+    inputs = [synthetic_prompt(cfg, grid_of(args, rank * NG + i), rank * NG + i, 0, dev) for i in range(NG)]
     ids, frames_host, grid = inputs[0]
     P = len(ids)
     # `value` runs with pixel_values_videos resident in HBM (the processor output, fp32 [N, 1176]); `e2e` starts from the
@@ -560,6 +619,7 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else {}
     prof = ops.PROFILER.summary()
     ms_e2e = timed(args.steps, True, 200)
+    filt = filter_pass(args, eng, cfg, rank, world, dev) if args.filter_pass > 0 else None
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -570,7 +630,10 @@ def run_ours(args):
     gm = prof.get("gemm_bf16_tn", dict(launches=0, flops=0.0, ms=1.0))
     gemm_tflops = gm["flops"] / max(gm["ms"], 1e-9) / 1e9
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
-    algo = {k: v * NG for k, v in flops.step_flops(cfg, grid, P, G, C).items()}
+    algo = {}
+    for ids_i, _, grid_i in inputs:                   # this rank's prompt-groups (they differ under --grid timerft)
+        for k, v in flops.step_flops(cfg, grid_i, len(ids_i), G, C).items():
+            algo[k] = algo.get(k, 0.0) + v
     roofline = {
         "bound": "tensor", "kernel": "gemm_bf16_tn (tcgen05)", "achieved": round(gemm_tflops, 1), "peak": peak_tf, "unit": "TFLOP/s",
         "frac": round(gemm_tflops / peak_tf, 4), "traffic": NCU_GEMM_TRAFFIC["bytes"], "traffic_note": NCU_GEMM_TRAFFIC["note"], "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback",
@@ -596,7 +659,7 @@ def run_ours(args):
         "config": {"workload": workload_name(args), "prompt_tokens": P, "vision_tokens": (P - 120), "group_size": G, "groups_per_step": NG,
                    "completion_len": C, "parallelism": f"dp{world}+zero2-sharded-adamw", "l2": "inputs larger than L2 (>=16 GB of weights streamed per pass)"},
         "clocks": clocks,
-        "e2e": {"value": round(e2e_value, 4), "unit": UNIT, "h2d_bytes_per_step": int(NG * (frames_host.numel() + ids.size * 4)), "input": "uint8 frames [2*slots, 3, 448, 448] from pinned host memory -> t1_video_patchify on the device", "d2h_bytes_per_step": int(NG * ((G * C * 4 if args.reward_route == "host" else 0) + 4) + 4),
+        "e2e": {"value": round(e2e_value, 4), "unit": UNIT, "h2d_bytes_per_step": int(sum(inp[1].numel() + inp[0].size * 4 for inp in inputs)), "input": "uint8 frames [2*slots, 3, 448, 448] from pinned host memory -> t1_video_patchify on the device", "d2h_bytes_per_step": int(NG * ((G * C * 4 if args.reward_route == "host" else 0) + 4) + 4),
                 "d2h": "per-group loss + grad norm" + (" + completion ids for the host reward parse" if args.reward_route == "host" else "; completions are detokenised and parsed on the device")},
         "gpu_launches": launches,
         "reward_route": args.reward_route,
@@ -606,6 +669,9 @@ def run_ours(args):
         "roofline_decode": dec,
         "attn": attn,
     }
+    if filt is not None:
+        line["filter_pass"] = filt
+    line["save_level"] = getattr(eng, "last_save_level", None)
     if gpu_ref is not None:
         keep = ("value", "unit", "ms_per_step", "steps", "warmup", "how", "phase_s_per_step", "hbm_gb", "unavailable")
         line["gpu_reference"] = {k: gpu_ref[k] for k in keep if k in gpu_ref}

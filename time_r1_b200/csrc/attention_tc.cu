@@ -1,8 +1,12 @@
-// tcgen05 / TMEM / TMA flash-attention forward (head_dim 128) over the packed token axis of attention.cu.
+// tcgen05 / TMEM / TMA flash-attention forward (head_dim 128 or 80) over the packed token axis of attention.cu.
 //
-// Same masking model and call sites as t1_attn_fwd (LLM prefill / packed GRPO scoring; HF Q25:740-755 reached from
-// src/time_r1/rl/timer1_trainer.py:452-457,569-573) — this is the Blackwell-native replacement of the HMMA kernel for
-// the tensor-bound LLM shapes.  One CTA = 128 query rows x one q head, looping over 128-key tiles:
+// Same masking model and call sites as t1_attn_fwd (LLM prefill / packed GRPO scoring, HF Q25:740-755; and the ViT's
+// windowed / per-slot full attention, head_dim 80, non-causal [lo, hi) row ranges, HF Q25:244-261,498-509 / Q2:771-790 —
+// both reached from src/time_r1/rl/timer1_trainer.py:452-457,569-573) — the Blackwell-native replacement of the HMMA
+// kernel.  head_dim 80 = 5 UMMA K-steps of 16 for S = Q K^T and an N = 80 accumulator for O += P V; the Q / K / V tiles keep
+// the [128 x 128] two-atom shared-memory layout (the second 64-column TMA box of a head overlaps its neighbour or is
+// zero-filled past the last head; only the first 80 columns are ever addressed by an MMA).
+// One CTA = 128 query rows x one q head, looping over 128-key tiles:
 //   warp 0       TMA producer : Q tile once, K/V tiles (2 x [128 x 64] SWIZZLE_128B boxes each) into a 2-stage ring
 //   warp 1       MMA issuer   : S = Q K^T   (tcgen05.mma M128 N128 K16 x 8, both operands K-major) -> TMEM S[it & 1]
 //                               O += P V    (A = P read from TMEM — the bf16 probabilities are packed back into the S
@@ -25,7 +29,6 @@ namespace {
 
 constexpr int TQ = 128;   // query rows per CTA
 constexpr int TK = 128;   // keys per tile
-constexpr int HD = 128;
 constexpr int ATOM_BYTES = 128 * 128;            // [128 rows x 64 bf16] box
 constexpr int TILE_BYTES = 2 * ATOM_BYTES;       // [128 x 128] bf16
 constexpr int NS = 4;                  // softmax threads per query row
@@ -71,6 +74,7 @@ struct Range {
   __device__ __forceinline__ int tile(int idx) const { return idx < tA_end ? idx : tB_start + (idx - tA_end); }
 };
 
+template <int HD>
 __global__ void __launch_bounds__(FA_TC_THREADS, 1)   // 576 threads: 96 registers is the most that still launches
 fa_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                  const __grid_constant__ CUtensorMap tm_v, bf16* __restrict__ O, long long ldo, float* __restrict__ LSE2, long long lse_ld,
@@ -216,7 +220,7 @@ fa_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     }
   } else {
     // ===================== softmax warps: NS threads per query row, 128/NS key columns each =====================
-    constexpr int CW = TK / NS;                         // key columns (and output columns) per thread
+    constexpr int CW = TK / NS;                         // key columns per thread; O columns [part * 32, part * 32 + 32) n [0, HD)
     constexpr int NCH = CW / 32;                        // 32-column TMEM chunks per thread
     const int quad = warp_idx & 3;                      // TMEM lane quadrant this warp may touch
     const int part = (warp_idx - 2) >> 2;               // which column slice
@@ -224,6 +228,8 @@ fa_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     const bool valid = my_row < T;
     const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
     const uint32_t tmem_o = t_lane + 256 + part * CW;
+    const bool o_on = part * CW < HD;                   // warp-uniform: head_dim 80 leaves the last column slice empty
+    const int o_w = HD - part * CW < CW ? HD - part * CW : CW;   // valid output columns of this slice (80: 32, 32, 16, -)
     float m_ref = -INFINITY, l = 0.f;
     for (int it = 0; it < ntiles; ++it) {
       const int j0 = tr.tile(it) * TK, j1 = j0 + TK;
@@ -267,8 +273,9 @@ fa_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         m_ref = tmax;
         l *= alpha;
       }
-      if (it > 0 && __any_sync(0xffffffffu, grow)) {
-        // rare after the first tiles: O is rescaled in place once PV(it-1) has retired
+      if (it > 0 && __any_sync(0xffffffffu, grow) && o_on) {
+        // rare after the first tiles: O is rescaled in place once PV(it-1) has retired (columns past head_dim inside the
+        // slice hold whatever TMEM held: scaled and written back, never read)
         mbar_wait(&pv_done[(it - 1) & 1], ((it - 1) >> 1) & 1);
         tc_fence_after();
 #pragma unroll 1
@@ -317,17 +324,18 @@ fa_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 #pragma unroll 1
     for (int c = 0; c < NCH; ++c) {
       uint32_t ov[32];
-      if (ntiles > 0) {
+      if (ntiles > 0 && o_on) {
         tmem_ld_32x32b_x32(tmem_o + c * 32, ov);
         tmem_ld_wait();
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) ov[j] = 0;
       }
-      if (valid) {
+      if (valid && o_on) {
         bf16* op = O + (long long)(my_row - q_row0) * ldo + (long long)h * HD + part * CW + c * 32;
 #pragma unroll
         for (int j8 = 0; j8 < 4; ++j8) {
+          if (j8 * 8 >= o_w) break;
           uint4 pk;
           pk.x = pack_bf16x2(__uint_as_float(ov[j8 * 8 + 0]) * inv, __uint_as_float(ov[j8 * 8 + 1]) * inv);
           pk.y = pack_bf16x2(__uint_as_float(ov[j8 * 8 + 2]) * inv, __uint_as_float(ov[j8 * 8 + 3]) * inv);
@@ -348,7 +356,7 @@ fa_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 
 }  // namespace
 
-// Same contract as t1_attn_fwd, head_dim == 128 only; additionally only query rows [q_row0, T) are processed and Q / O
+// Same contract as t1_attn_fwd, head_dim 128 (LLM) or 80 (ViT); additionally only query rows [q_row0, T) are processed and Q / O
 // point at row q_row0 (row_lo / row_hi / LSE2 / K / V keep absolute packed-row indexing; LSE2 is [Hq, lse_ld], lse_ld <= 0 -> T); Q/K/V token strides must be multiples of 8 and the head
 // column offsets multiples of 64 (true for the fused qkv layout).
 extern "C" int t1_attn_fwd_tc(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv,
@@ -357,7 +365,8 @@ extern "C" int t1_attn_fwd_tc(const void* Q, long long ldq, const void* K, long 
                               cudaStream_t stream) {
   if (T - q_row0 <= 0) return T1_OK;
   T1_CHECK_ARG(q_row0 >= 0, "t1_attn_fwd_tc: q_row0 must be >= 0");
-  T1_CHECK_ARG(head_dim == 128, "t1_attn_fwd_tc: head_dim must be 128 (got %d)", head_dim);
+  T1_CHECK_ARG(head_dim == 128 || head_dim == 80, "t1_attn_fwd_tc: head_dim must be 128 or 80 (got %d)", head_dim);
+  const int HD = head_dim;
   T1_CHECK_ARG(Q && K && V && O && row_lo && row_hi, "t1_attn_fwd_tc: null pointer");
   T1_CHECK_ARG(Hkv > 0 && Hq % Hkv == 0, "t1_attn_fwd_tc: Hq=%d must be a multiple of Hkv=%d", Hq, Hkv);
   T1_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0, "t1_attn_fwd_tc: strides must be multiples of 8");
@@ -372,7 +381,8 @@ extern "C" int t1_attn_fwd_tc(const void* Q, long long ldq, const void* K, long 
   static bool set = false;
   static uint32_t lbo = ATOM_BYTES, sbo = 1024;
   if (!set) {
-    cudaError_t e = cudaFuncSetAttribute(fa_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_TC_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(fa_fwd_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_TC_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(fa_fwd_tc_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_TC_SMEM);
     if (e != cudaSuccess) {
       t1_set_error("t1_attn_fwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return T1_ERR_CUDA;
@@ -382,8 +392,12 @@ extern "C" int t1_attn_fwd_tc(const void* Q, long long ldq, const void* K, long 
     set = true;
   }
   dim3 grid((T - q_row0 + TQ - 1) / TQ, Hq);
-  fa_fwd_tc_kernel<<<grid, FA_TC_THREADS, FA_TC_SMEM, stream>>>(tq, tk, tv, (bf16*)O, ldo, LSE2, lse_ld > 0 ? lse_ld : T, row_lo, row_hi, shared_len,
-                                                               T, q_row0, Hq / Hkv, scale * 1.4426950408889634f, lbo, sbo);
+  if (HD == 128)
+    fa_fwd_tc_kernel<128><<<grid, FA_TC_THREADS, FA_TC_SMEM, stream>>>(tq, tk, tv, (bf16*)O, ldo, LSE2, lse_ld > 0 ? lse_ld : T, row_lo, row_hi,
+                                                                      shared_len, T, q_row0, Hq / Hkv, scale * 1.4426950408889634f, lbo, sbo);
+  else
+    fa_fwd_tc_kernel<80><<<grid, FA_TC_THREADS, FA_TC_SMEM, stream>>>(tq, tk, tv, (bf16*)O, ldo, LSE2, lse_ld > 0 ? lse_ld : T, row_lo, row_hi,
+                                                                     shared_len, T, q_row0, Hq / Hkv, scale * 1.4426950408889634f, lbo, sbo);
   T1_CUDA_LAUNCH_CHECK("t1_attn_fwd_tc");
   return T1_OK;
 }

@@ -103,7 +103,7 @@ class Engine:
         # as the backward has finished every gradient at or above its start; a communicator limited to a few CTAs leaves the
         # tensor-bound backward its SMs (the collective has the whole backward to hide in)
         self.zero_overlap = world_size > 1 and _os.environ.get("T1_ZERO_OVERLAP", "1") != "0" and getattr(run, "zero_overlap", True)
-        self.nccl_ctas = int(_os.environ.get("T1_NCCL_MAX_CTAS", getattr(run, "zero_nccl_ctas", 8)))
+        self.nccl_ctas = int(_os.environ.get("T1_NCCL_MAX_CTAS", getattr(run, "zero_nccl_ctas", 4)))
         self.pg_rs = process_group
         if self.zero_overlap and self.nccl_ctas > 0:
             import torch.distributed as dist
@@ -222,6 +222,9 @@ class Engine:
         win_lo, win_hi = self._i32(plan.win_lo), self._i32(plan.win_hi)
         full_lo, full_hi = self._i32(plan.full_lo), self._i32(plan.full_hi)
         scale = hd ** -0.5
+        import os as _os
+
+        vit_attn = ops.attn_fwd_tc if (hd in (80, 128) and _os.environ.get("T1_VIT_ATTN", "tc") != "hmma") else ops.attn_fwd
         delta = None
         h = torch.empty_like(x)
         qkv = torch.empty((N, 3 * vd), device=self.dev, dtype=BF16)
@@ -239,8 +242,9 @@ class Engine:
             ops.rope_apply(qkv, 0, 2 * H, hd, cos, sin)                     # q and k heads are contiguous
             full = (not cfg.is_q25) or (i in cfg.fullatt_block_indexes)
             lo, hi = (full_lo, full_hi) if full else (win_lo, win_hi)
-            ops.attn_fwd(qkv[:, :vd], qkv[:, vd:2 * vd], qkv[:, 2 * vd:], lo, hi, 0, H, H, hd, scale, out=attn,
-                         need_lse=False)
+            # windowed (64-token) / per-slot full attention, non-causal: tcgen05 kernel for head_dim 80 / 128 (the released
+            # ViTs are 80), HMMA kernel for anything else
+            vit_attn(qkv[:, :vd], qkv[:, vd:2 * vd], qkv[:, 2 * vd:], lo, hi, 0, H, H, hd, scale, out=attn, need_lse=False)
             ops.gemm(attn, g(pre + "attn.proj.weight"), out=proj, bias=g(pre + "attn.proj.bias"))
             if cfg.is_q25:
                 ops.rmsnorm(x, g(pre + "norm2.weight"), 1e-6, delta=proj, out=h)
@@ -703,6 +707,7 @@ class Engine:
         st["out_ids"].fill_(cfg.pad_token_id)
         st["seed_dev"].fill_(int(seed))
         save_level = self._save_level(len(prompts), max(indexing.packed_rows(P_, G, C)[0] for P_ in Ps)) if keep_prefill else 0
+        self.last_save_level = save_level        # reported by bench.py: which fallback the free HBM allowed
         for gi, (prompt, emb, grp) in enumerate(zip(prompts, vision_embeds, st["groups"])):
             ids = np.asarray(prompt.input_ids)
             P = grp["P"]
@@ -1033,7 +1038,8 @@ class Engine:
         if st.vision_rows.numel() > 0:
             dve = ops.gather_rows(dx, st.vision_rows)                       # [Nv, D] in original merged-token order
             self._merger_backward(st, dve, acc)
-        self._reduce_ready(0)
+        # the buckets that only became final here (embedding table, merger) are reduced by optimizer_step on the full-speed
+        # communicator: nothing is left to hide them behind
         self.grad_fresh = False
 
     def _merger_backward(self, st: ScoreState, dve: torch.Tensor, acc: bool):
