@@ -451,6 +451,7 @@ def filter_pass(args, eng, cfg, rank, world, dev):
                                                   frames=frames_host.to(dev, non_blocking=True))))
     decode = lambda ids: bytes(int(t) % 256 for t in ids).decode("latin-1")
     flt = filtering.GreedyFilter(eng, lambda s: s["_prompt"], decode, max_new_tokens=64, batch=4)
+    flt.difficulties(samples[:4])                  # warm-up: captures the decode graph of this batch shape
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()

@@ -224,7 +224,11 @@ class Engine:
         scale = hd ** -0.5
         import os as _os
 
-        vit_attn = ops.attn_fwd_tc if (hd in (80, 128) and _os.environ.get("T1_VIT_ATTN", "tc") != "hmma") else ops.attn_fwd
+        # measured on B200, 16384 tokens x 16 heads x 80 (profiles/r02_vit_attn_bench.txt): per-slot FULL attention (1024 keys)
+        # tcgen05 0.209 ms vs FA2-varlen 0.300 vs HMMA 0.423; 64-token WINDOWS tcgen05 0.107 vs FA2 0.088 vs HMMA 0.061 (one
+        # half-masked 128 x 128 tile per CTA: fixed cost, not tensor time) -> "auto" takes the faster kernel per block kind
+        mode = _os.environ.get("T1_VIT_ATTN", getattr(self.run, "vit_attn", "auto"))
+        tc_ok = hd in (80, 128)
         delta = None
         h = torch.empty_like(x)
         qkv = torch.empty((N, 3 * vd), device=self.dev, dtype=BF16)
@@ -244,7 +248,9 @@ class Engine:
             lo, hi = (full_lo, full_hi) if full else (win_lo, win_hi)
             # windowed (64-token) / per-slot full attention, non-causal: tcgen05 kernel for head_dim 80 / 128 (the released
             # ViTs are 80), HMMA kernel for anything else
-            vit_attn(qkv[:, :vd], qkv[:, vd:2 * vd], qkv[:, 2 * vd:], lo, hi, 0, H, H, hd, scale, out=attn, need_lse=False)
+            use_tc = tc_ok and (mode == "tc" or (mode == "auto" and full))
+            (ops.attn_fwd_tc if use_tc else ops.attn_fwd)(qkv[:, :vd], qkv[:, vd:2 * vd], qkv[:, 2 * vd:], lo, hi, 0, H, H, hd, scale,
+                                                          out=attn, need_lse=False)
             ops.gemm(attn, g(pre + "attn.proj.weight"), out=proj, bias=g(pre + "attn.proj.bias"))
             if cfg.is_q25:
                 ops.rmsnorm(x, g(pre + "norm2.weight"), 1e-6, delta=proj, out=h)
@@ -707,7 +713,8 @@ class Engine:
         st["out_ids"].fill_(cfg.pad_token_id)
         st["seed_dev"].fill_(int(seed))
         save_level = self._save_level(len(prompts), max(indexing.packed_rows(P_, G, C)[0] for P_ in Ps)) if keep_prefill else 0
-        self.last_save_level = save_level        # reported by bench.py: which fallback the free HBM allowed
+        if keep_prefill:
+            self.last_save_level = save_level    # reported by bench.py: which fallback the free HBM allowed
         for gi, (prompt, emb, grp) in enumerate(zip(prompts, vision_embeds, st["groups"])):
             ids = np.asarray(prompt.input_ids)
             P = grp["P"]
