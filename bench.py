@@ -717,32 +717,41 @@ def run_verify(args):
     with torch.no_grad():      # policy != reference model, so the KL term and its gradient are live
         eng.w.train["model.layers.1.mlp.down_proj.weight"].mul_(1.25)
     grid = (4, 32, 32)
-    losses = []
-    for gi in range(rank, NGLOBAL, world):
-        ids, frames_host, g = synthetic_prompt(cfg, grid, gi, 0, dev)
-        rng = np.random.default_rng(1000 + gi)
-        comp = torch.from_numpy(rng.integers(0, 151643, (G, C))).int()
-        comp[gi % G, 5 + gi] = cfg.eos_token_id
-        comp[gi % G, 6 + gi:] = cfg.pad_token_id
-        rewards = rng.random((G, 2)).astype(np.float32)
-        prompt = engine.Prompt(input_ids=ids, pixel_values=None, grid_thw=g, second_per_grid_ts=[1.0], frames=frames_host.to(dev))
-        out = eng.grpo_step(prompt, lambda c, r=rewards: r, completion_override=comp, loss_scale=world / NGLOBAL)
-        losses.append(out["loss"].double())
     stride = 16381
-    gsample = eng.grads.buf[::stride].float().clone()
-    loss = torch.stack(losses).sum().reshape(1) / world      # each rank holds (its groups) x world / 8: the DP mean equals the N=1 sum
-    if world > 1:
-        dist.all_reduce(gsample, op=dist.ReduceOp.AVG)
-        dist.all_reduce(loss, op=dist.ReduceOp.SUM)
-    w_before = eng.w.train.buf[::stride].float().clone()
-    gnorm = eng.optimizer_step(lr=1e-3)
+    # TWO optimizer steps: the second one starts while the first one's parameter all-gather may still be in flight (lazy
+    # per-bucket waits in Engine.p) and its loss depends on the updated weights
+    for it in range(2):
+        losses = []
+        for gi in range(rank, NGLOBAL, world):
+            ids, frames_host, g = synthetic_prompt(cfg, grid, gi, 0, dev)
+            rng = np.random.default_rng(1000 + gi + 100 * it)
+            comp = torch.from_numpy(rng.integers(0, 151643, (G, C))).int()
+            comp[gi % G, 5 + gi] = cfg.eos_token_id
+            comp[gi % G, 6 + gi:] = cfg.pad_token_id
+            rewards = rng.random((G, 2)).astype(np.float32)
+            prompt = engine.Prompt(input_ids=ids, pixel_values=None, grid_thw=g, second_per_grid_ts=[1.0], frames=frames_host.to(dev))
+            out = eng.grpo_step(prompt, lambda c, r=rewards: r, completion_override=comp, loss_scale=world / NGLOBAL,
+                                last_before_optimizer=gi + world >= NGLOBAL)
+            losses.append(out["loss"].double())
+        gsample = eng.grads.buf[::stride].float().clone()
+        loss = torch.stack(losses).sum().reshape(1) / world      # each rank holds (its groups) x world / 8: the DP mean equals the N=1 sum
+        if world > 1:
+            dist.all_reduce(gsample, op=dist.ReduceOp.AVG)
+            dist.all_reduce(loss, op=dist.ReduceOp.SUM)
+        if it == 0:
+            eng.sync_params()
+            w_before = eng.w.train.buf[::stride].float().clone()
+            loss0, gsample0 = loss.clone(), gsample
+        gnorm = eng.optimizer_step(lr=1e-3)
+    eng.sync_params()
     torch.cuda.synchronize()
     w_after = eng.w.train.buf[::stride].float().clone()
     if rank == 0:
-        rec = {"world": world, "loss": float(loss.item()), "grad_norm": float(gnorm.item()), "grad_sample": gsample.cpu(),
+        rec = {"world": world, "loss": float(loss0.item()), "loss_step2": float(loss.item()), "grad_norm": float(gnorm.item()),
+               "grad_sample": gsample0.cpu(), "grad_sample_step2": gsample.cpu(),
                "w_before": w_before.cpu(), "w_after": w_after.cpu(), "stride": stride, "model": args.model, "groups": NGLOBAL, "G": G, "C": C}
         torch.save(rec, args.verify)
-        print(json.dumps({"verify": {"world": world, "loss": rec["loss"], "grad_norm": rec["grad_norm"],
+        print(json.dumps({"verify": {"world": world, "loss": rec["loss"], "loss_step2": rec["loss_step2"], "grad_norm": rec["grad_norm"],
                                      "grad_sample_l2": float(gsample.norm().item()), "out": args.verify}}), flush=True)
     if world > 1:
         dist.barrier()

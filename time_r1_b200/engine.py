@@ -115,6 +115,25 @@ class Engine:
                 self.pg_rs = dist.new_group(backend="nccl", pg_options=opts)      # collective call: every rank builds an Engine
         self._grad_version = 0
         self._rs = None          # {"version", "works"}: reduce-scatters issued during the last backward
+        # parameter all-gather left in flight by optimizer_step: {bucket: work}; consumers wait per bucket (Engine.p), so the
+        # next step's merger / prefill (which read the buckets in the order they are gathered) start under the gather
+        self._ag_pending: dict = {}
+        self._ag_capped = False
+        self.lazy_gather = world_size > 1 and _os.environ.get("T1_LAZY_GATHER", "1") != "0" and getattr(run, "zero_lazy_gather", True)
+        self.pg_ag = process_group
+        ag_ctas = int(_os.environ.get("T1_NCCL_AG_CTAS", getattr(run, "zero_ag_ctas", 8)))
+        self.ag_ctas = ag_ctas
+        if self.lazy_gather and ag_ctas > 0:
+            import torch.distributed as dist
+
+            if dist.get_backend(process_group) == "nccl":
+                if ag_ctas == self.nccl_ctas and self.pg_rs is not process_group:
+                    self.pg_ag = self.pg_rs
+                else:
+                    opts = dist.ProcessGroupNCCL.Options()
+                    opts.config.max_ctas = ag_ctas
+                    opts.config.min_ctas = 1
+                    self.pg_ag = dist.new_group(backend="nccl", pg_options=opts)
         # ---- rotary constants (computed the way HF does, in fp32 on the host) ----
         hd = cfg.head_dim
         self.inv_freq_llm = (1.0 / (cfg.rope_theta ** (torch.arange(0, hd, 2, dtype=F32) / hd))).to(self.dev)
@@ -191,7 +210,48 @@ class Engine:
     def p(self, name: str, wset: str = "policy") -> torch.Tensor:
         if wset == "ref" and self.ref is not None and name in self.ref:
             return self.ref[name]
+        if self._ag_pending and name in self.w.train:
+            self._wait_param(name)
         return self.w.get(name)
+
+    def _wait_param(self, name: str):
+        """The all-gather of the last optimizer step may still be in flight (optimizer_step(lazy_gather=True)): order the
+        current stream after the gathers of the buckets that hold `name`, in bucket order (they complete in that order)."""
+        lo, shape = self.w.train.layout[name]
+        n = 1
+        for d in shape:
+            n *= d
+        hi = lo + n
+        pend = self._ag_pending
+        last = -1
+        for b in sorted(pend):
+            blo, bhi = self.plan.bounds[b]
+            if blo < hi and bhi > lo:
+                last = b
+        if last < 0:
+            return
+        for b in sorted(pend):
+            if b > last:
+                break
+            w = pend.pop(b)
+            if w is not None:
+                w.wait()
+        if not pend:
+            self._end_lazy_gather()
+
+    def _end_lazy_gather(self):
+        if self._ag_capped:
+            load_lib().t1_gemm_max_ctas(0)
+            self._ag_capped = False
+
+    def sync_params(self):
+        """Order the current stream after every outstanding parameter all-gather (before anything that reads the flat
+        parameter buffer outside Engine.p(): checkpoint export, graph replays, direct buffer access)."""
+        for b in sorted(self._ag_pending):
+            w = self._ag_pending.pop(b)
+            if w is not None:
+                w.wait()
+        self._end_lazy_gather()
 
     def lm_head(self, wset: str = "policy") -> torch.Tensor:
         return self.p("model.embed_tokens.weight" if self.cfg.tie_word_embeddings else "lm_head.weight", wset)
@@ -754,6 +814,7 @@ class Engine:
             self._sample(st, logits0, 0, G, temperature, top_k, int(seed) + 7919 * (gi + 1), 0, 0, 0,
                          st["finished"][sl], st["out_ids"][sl], st["next_ids"][sl])
         n_steps = C - 1
+        self.sync_params()           # the captured decode step reads every weight through raw pointers
         if before_decode is not None:
             before_decode()          # side-stream work that overlaps the decode loop is enqueued after the prompt prefills
         if n_steps > 0:
@@ -1082,8 +1143,10 @@ class Engine:
     # ------------------------------------------------------------------------------------------
     # optimizer: global-norm clip + AdamW on this rank's shard of the flat buffer (ZeRO-2 semantics)
     # ------------------------------------------------------------------------------------------
-    def optimizer_step(self, lr: float | None = None, grad_scale: float = 1.0) -> torch.Tensor:
+    def optimizer_step(self, lr: float | None = None, grad_scale: float = 1.0, lazy_gather: bool | None = None) -> torch.Tensor:
         """Returns the (pre-clip) global gradient norm as a 1-element device tensor.
+        lazy_gather (default: Engine.lazy_gather): do not wait for the all-gathers here; every later read of a trained
+        parameter through Engine.p() waits for just the buckets it touches (sync_params() waits for all).
         world > 1: bucketed reduce-scatter (those issued during the last backward are only waited for) -> grad norm ->
         per bucket AdamW on this rank's slice + asynchronous IN-PLACE all-gather of the bucket (bucket b's gather runs under
         bucket b+1's AdamW); the main stream waits for the gathers before it returns to the caller's work."""
@@ -1112,6 +1175,8 @@ class Engine:
         if self.world > 1:
             dist.all_reduce(gsq, group=self.pg)
         self.opt_step += 1
+        self.sync_params()                 # gathers of an earlier step (none in the normal flow: the next step consumed them)
+        lazy = self.lazy_gather if lazy_gather is None else (lazy_gather and self.world > 1)
         works = []
         for b in range(len(plan)):
             lo, hi = plan.slice_of(b, self.rank)
@@ -1120,10 +1185,17 @@ class Engine:
                       run.adam_beta2, run.adam_eps, run.weight_decay, self.opt_step, gnorm_sq=gsq, max_norm=run.max_grad_norm,
                       grad_scale=grad_scale)
             if self.world > 1:
-                works.append(plan.all_gather(b, self.w.train.buf, self.rank, group=self.pg, async_op=True))
-        for w in works:
-            if w is not None:
-                w.wait()
+                works.append(plan.all_gather(b, self.w.train.buf, self.rank, group=self.pg_ag if lazy else self.pg, async_op=True))
+        if lazy:
+            self._ag_pending = {b: w for b, w in enumerate(works)}
+            if self.ag_ctas > 0:           # leave the gather its SMs while the next step's first GEMMs run beside it
+                sms = torch.cuda.get_device_properties(self.dev).multi_processor_count
+                load_lib().t1_gemm_max_ctas(max(1, sms - self.ag_ctas))
+                self._ag_capped = True
+        else:
+            for w in works:
+                if w is not None:
+                    w.wait()
         self.grad_fresh = True
         self._invalidate_after_update()
         return gsq.sqrt() * grad_scale
@@ -1135,11 +1207,12 @@ class Engine:
     # one complete GRPO micro-step for one prompt group
     # ------------------------------------------------------------------------------------------
     def grpo_step(self, prompt: Prompt, reward_fn, seed: int | None = None, completion_override=None,
-                  loss_scale: float = 1.0, timers: dict | None = None, vit_prefetch: dict | None = None):
+                  loss_scale: float = 1.0, timers: dict | None = None, vit_prefetch: dict | None = None,
+                  last_before_optimizer: bool = True):
         """One prompt-group: see grpo_multi_step."""
         ov = None if completion_override is None else [completion_override]
         return self.grpo_multi_step([prompt], [reward_fn], seed=seed, completion_overrides=ov, loss_scale=loss_scale,
-                                    timers=timers, vit_prefetch=vit_prefetch)[0]
+                                    timers=timers, vit_prefetch=vit_prefetch, last_before_optimizer=last_before_optimizer)[0]
 
     def grpo_multi_step(self, prompts: list, reward_fns: list, seed: int | None = None, completion_overrides=None,
                         loss_scale: float = 1.0, timers: dict | None = None, vit_prefetch: dict | None = None,

@@ -606,6 +606,8 @@ class TimeR1_Trainer:
         if not self.state.is_world_process_zero:
             return
         os.makedirs(output_dir, exist_ok=True)
+        if hasattr(self.engine, "sync_params"):
+            self.engine.sync_params()          # the last optimizer step's parameter all-gather may still be in flight
         save_checkpoint_dir(output_dir, self.model_cfg, self.weights)
         # HF Trainer saves processing_class into every checkpoint: scripts/posttrain/train_rl_SF.sh:76-105 feeds checkpoint-N
         # straight into evaluate.py / vLLM (AutoProcessor.from_pretrained) and into the next round as --model_name_or_path

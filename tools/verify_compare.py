@@ -22,8 +22,14 @@ rec = {
     "post_step_weights_max_abs_diff": float((a["w_after"] - b["w_after"]).abs().max()),
     "moved_frac": float(moved.double().mean()), "n_sample": int(ga.numel()),
 }
+if "loss_step2" in a and "loss_step2" in b:      # second optimizer step: computed on the updated (lazily all-gathered) weights
+    g2a, g2b = a["grad_sample_step2"].double(), b["grad_sample_step2"].double()
+    rec["loss_step2"] = [a["loss_step2"], b["loss_step2"]]
+    rec["loss_step2_rel_diff"] = abs(a["loss_step2"] - b["loss_step2"]) / max(1e-12, abs(a["loss_step2"]))
+    rec["grad_sample_step2_rel_l2"] = float((g2a - g2b).norm() / g2a.norm())
 print(json.dumps(rec))
 ok = (rec["loss_rel_diff"] < 2e-3 and rec["grad_norm_rel_diff"] < 1e-2 and rec["grad_sample_rel_l2"] < 3e-2
-      and rec["weights_before_identical"] and rec["update_cosine"] > 0.97)
+      and rec["weights_before_identical"] and rec["update_cosine"] > 0.97
+      and rec.get("loss_step2_rel_diff", 0.0) < 2e-2 and rec.get("grad_sample_step2_rel_l2", 0.0) < 0.1)
 print("VERIFY", "OK" if ok else "MISMATCH")
 sys.exit(0 if ok else 1)
