@@ -92,3 +92,24 @@ def test_gemm_swiglu_epilogue(M, I, K, with_bias):
     assert torch.equal(got, want), (got.float() - want.float()).abs().max().item()
     assert torch.equal(gu, gu_ref)
     assert torch.equal(ops.gemm_swiglu(a, w, bias=b), want)
+
+
+@pytest.mark.parametrize("M,N,K", [(130, 72, 64), (257, 200, 128), (1000, 1280, 1176), (96, 3584, 256)])
+def test_gemm_tma_store_epilogue_strided_output_and_neighbours(M, N, K):
+    """bf16 outputs leave through TMA tensor stores ([32 x 64] boxes): rows >= M and columns >= N are clipped by the TMA unit —
+    the columns NEXT to a strided output view (the other projections of a fused buffer) and the rows after it stay untouched."""
+    from time_r1_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    b = torch.randn(N, K, device="cuda", generator=g).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda", generator=g).to(torch.bfloat16)
+    buf = torch.full((M + 40, N + 136), 7.0, device="cuda", dtype=torch.bfloat16)
+    out = buf[8:8 + M, 64:64 + N]
+    ops.gemm(a, b, out=out, bias=bias)
+    torch.cuda.synchronize()
+    ref = a.float() @ b.float().t() + bias.float()
+    assert (out.float() - ref).abs().max().item() <= 1e-2 * ref.abs().max().item() + 1e-3
+    guard = buf.clone()
+    guard[8:8 + M, 64:64 + N] = 7.0
+    assert (guard == 7.0).all(), "the TMA store wrote outside the output view"

@@ -10,7 +10,11 @@
 //   warp 0      TMA producer   : cp.async.bulk.tensor 2D loads of 128x64 (A) and 256x64 (B) bf16 boxes, SWIZZLE_128B
 //   warp 1      MMA issuer     : one thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=256, K=16)
 //   warp 2      TMEM allocator : 512 columns = two 128x256 fp32 accumulators (double buffered)
-//   warps 4..7  epilogue       : tcgen05.ld 32x32b -> registers -> bias / accumulate / convert -> global
+//   warps 4..7  epilogue       : tcgen05.ld 32x32b -> registers -> bias / SwiGLU / convert -> bf16 rows staged in shared
+//                                memory (SWIZZLE_128B, one [32 x 64] box per warp, double buffered) -> TMA tensor store
+//                                (cp.async.bulk.tensor .. global.shared::cta, SASS UTMASTG): full 128-byte rows leave the SM
+//                                as whole lines instead of 32 x 16-byte fragments of 32 different rows per warp store.
+//                                fp32 outputs and accumulating (read-modify-write) outputs keep the direct register path.
 // Pipelines: smem ring (full/empty mbarriers, 4 stages of 48 KB) and TMEM ring (tmem_full/tmem_empty).
 #include "t1_common.cuh"
 #include <stdlib.h>
@@ -25,7 +29,10 @@ constexpr int A_BYTES = BM * BK * 2;
 constexpr int B_BYTES_MAX = BN_MAX * BK * 2;
 constexpr int UMMA_K = 16;
 constexpr int NUM_THREADS = 256;
-constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES_MAX) + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int EPI_BOX_BYTES = 32 * 128;                  // [32 rows x 64 bf16] staging box of one epilogue warp
+constexpr int EPI_STAGE_BYTES = 4 * 2 * EPI_BOX_BYTES;   // 4 warps x 2 buffers = 32 KB
+constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES_MAX) + EPI_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
 enum : int {
   GEMM_OUT_F32 = 1,     // D is fp32 (else bf16)
@@ -35,6 +42,7 @@ enum : int {
   GEMM_B_MN = 16,       // B is given as row-major [K, N] (N contiguous)
   GEMM_SWIGLU = 32,     // B = [W_gate; W_up] ([2N, K], K-major): D[M, N] = silu(A Wg^T + bg) * (A Wu^T + bu), bf16; each
                         // 256-wide tile pairs 128 gate rows with their 128 up rows (t1_gemm_swiglu)
+  GEMM_TMA_STORE = 64,  // (internal) the epilogue stores through the tensor maps of D (and of the gate / up halves of D2)
 };
 constexpr int MN_ATOM_BYTES = BK * 128;   // MN-major smem atom: [64 k-rows x 64 elements], SWIZZLE_128B
 
@@ -49,8 +57,9 @@ struct EpiParams {
 
 template <bool A_MN, bool B_MN, int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, int M, int N,
-                    int K, int group_m, EpiParams epi) {
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                    const __grid_constant__ CUtensorMap tma_d, const __grid_constant__ CUtensorMap tma_d2g,
+                    const __grid_constant__ CUtensorMap tma_d2u, int M, int N, int K, int group_m, EpiParams epi) {
   static_assert(BN % 16 == 0 && BN <= BN_MAX && (!B_MN || BN % 64 == 0), "tile width");
   constexpr int B_BYTES = BN * BK * 2;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -58,7 +67,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_tiles = smem;
   uint8_t* b_tiles = smem + STAGES * A_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * (A_BYTES + B_BYTES_MAX));
+  uint8_t* epi_stage = smem + STAGES * (A_BYTES + B_BYTES_MAX);          // 1024-byte aligned (48 KB stages)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + EPI_STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
@@ -181,6 +191,26 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     const bool out_f32 = epi.flags & GEMM_OUT_F32;
     const bool accum = epi.flags & GEMM_ACCUMULATE;
     const bool bias_f32 = epi.flags & GEMM_BIAS_F32;
+    const bool tma_out = (epi.flags & GEMM_TMA_STORE) && BN % 64 == 0;
+    // ---- TMA-store path: this warp's two [32 x 64] bf16 staging boxes; lane 0 owns the bulk async-groups ----
+    uint8_t* my_stage = epi_stage + q * 2 * EPI_BOX_BYTES;
+    uint32_t n_store = 0;
+    // pk = this lane's 64 bf16 of the chunk (32 packed words): row `lane` of the box, 16-byte units XOR-swizzled by row & 7
+    auto store_box = [&](const CUtensorMap* tm, int col, int row0, const uint32_t* pk) {
+      uint8_t* buf = my_stage + (n_store & 1) * EPI_BOX_BYTES;
+      if (lane == 0) bulk_wait_group_read<1>();          // the group that last read this buffer (two stores ago) is done
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<uint4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(tm, buf, col, row0);                // rows >= M and columns >= the map's extent are clipped by the TMA unit
+        bulk_commit_group();
+      }
+      ++n_store;
+    };
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       int m_blk, n_blk;
@@ -191,7 +221,60 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       tc_fence_after();
       const int row = m_blk * BM + q * 32 + lane;
       const uint32_t taddr_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-      if (swiglu) {
+      if (swiglu && tma_out) {
+        // as below, 64 output columns at a time: y, and (when kept for the backward) g and u, leave through TMA stores
+        const int row0 = m_blk * BM + q * 32;
+#pragma unroll 1
+        for (int c = 0; c < BNO / 64; ++c) {
+          const int col0 = n_blk * BNO + c * 64;
+          if (col0 >= N) break;  // warp-uniform
+          uint32_t og[32], ou[32];
+          {
+            uint32_t vg[32], vu[32];
+#pragma unroll
+            for (int hlf = 0; hlf < 2; ++hlf) {
+              tmem_ld_32x32b_x32(taddr_row + c * 64 + hlf * 32, vg);
+              tmem_ld_32x32b_x32(taddr_row + BNO + c * 64 + hlf * 32, vu);
+              tmem_ld_wait();
+              if (epi.bias) {      // bf16 bias [2N]: gate part then up part (columns past N hold clipped garbage: skip the loads)
+#pragma unroll
+                for (int g8 = 0; g8 < 4; ++g8) {
+                  const int col = col0 + hlf * 32 + g8 * 8;
+                  if (col < N) {
+                    const uint4 bg = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(epi.bias) + col);
+                    const uint4 bu = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(epi.bias) + N + col);
+                    const uint32_t* pg = reinterpret_cast<const uint32_t*>(&bg);
+                    const uint32_t* pu = reinterpret_cast<const uint32_t*>(&bu);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                      const float2 a = unpack_bf16x2(pg[j]), b = unpack_bf16x2(pu[j]);
+                      vg[g8 * 8 + 2 * j] = __float_as_uint(__uint_as_float(vg[g8 * 8 + 2 * j]) + a.x);
+                      vg[g8 * 8 + 2 * j + 1] = __float_as_uint(__uint_as_float(vg[g8 * 8 + 2 * j + 1]) + a.y);
+                      vu[g8 * 8 + 2 * j] = __float_as_uint(__uint_as_float(vu[g8 * 8 + 2 * j]) + b.x);
+                      vu[g8 * 8 + 2 * j + 1] = __float_as_uint(__uint_as_float(vu[g8 * 8 + 2 * j + 1]) + b.y);
+                    }
+                  }
+                }
+              }
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                og[hlf * 16 + j] = pack_bf16x2(__uint_as_float(vg[2 * j]), __uint_as_float(vg[2 * j + 1]));
+                ou[hlf * 16 + j] = pack_bf16x2(__uint_as_float(vu[2 * j]), __uint_as_float(vu[2 * j + 1]));
+              }
+            }
+          }
+          if (epi.D2) {
+            store_box(&tma_d2g, col0, row0, og);
+            store_box(&tma_d2u, col0, row0, ou);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {      // y = silu(g) * u on the bf16-rounded projections, in place over og
+            const float2 gg = unpack_bf16x2(og[j]), uu = unpack_bf16x2(ou[j]);
+            og[j] = pack_bf16x2(gg.x * (1.0f / (1.0f + __expf(-gg.x))) * uu.x, gg.y * (1.0f / (1.0f + __expf(-gg.y))) * uu.y);
+          }
+          store_box(&tma_d, col0, row0, og);
+        }
+      } else if (swiglu) {
         // TMEM columns [0, BN/2) hold the gate projection of output columns n_blk*BNO + j, columns [BN/2, BN) the up
         // projection of the same columns: y = silu(g) * u on the bf16-rounded projections (== gemm -> t1_swiglu)
 #pragma unroll 1
@@ -238,6 +321,46 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
               }
             }
           }
+        }
+      } else if (tma_out) {
+        const int row0 = m_blk * BM + q * 32;
+#pragma unroll 1
+        for (int c = 0; c < BN / 64; ++c) {
+          const int col0 = n_blk * BN + c * 64;
+          if (col0 >= N) break;  // warp-uniform
+          uint32_t pk[32];
+#pragma unroll
+          for (int hlf = 0; hlf < 2; ++hlf) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(taddr_row + c * 64 + hlf * 32, v);
+            tmem_ld_wait();
+            if (epi.bias) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const int col = col0 + hlf * 32 + g * 8;
+                if (col < N) {
+                  float b8[8];
+                  if (bias_f32) {
+                    const float4* bp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(epi.bias) + col);
+                    const float4 b0 = bp[0], b1 = bp[1];
+                    b8[0] = b0.x; b8[1] = b0.y; b8[2] = b0.z; b8[3] = b0.w; b8[4] = b1.x; b8[5] = b1.y; b8[6] = b1.z; b8[7] = b1.w;
+                  } else {
+                    const uint4 b = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(epi.bias) + col);
+                    float2 t;
+                    t = unpack_bf16x2(b.x); b8[0] = t.x; b8[1] = t.y;
+                    t = unpack_bf16x2(b.y); b8[2] = t.x; b8[3] = t.y;
+                    t = unpack_bf16x2(b.z); b8[4] = t.x; b8[5] = t.y;
+                    t = unpack_bf16x2(b.w); b8[6] = t.x; b8[7] = t.y;
+                  }
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) v[g * 8 + j] = __float_as_uint(__uint_as_float(v[g * 8 + j]) + b8[j]);
+                }
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) pk[hlf * 16 + j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+          }
+          store_box(&tma_d, col0, row0, pk);
         }
       } else
 #pragma unroll 1
@@ -303,6 +426,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       tc_fence_before();
       mbar_arrive(&tmem_empty_bar[acc]);
     }
+    if (tma_out && lane == 0) bulk_wait_group<0>();      // every store of this warp has landed before the CTA retires
   }
 
   tc_fence_before();
@@ -358,6 +482,23 @@ static int gemm_impl(const void* A, long long lda, const void* B, long long ldb,
   const int num_tiles = num_m * num_n;
   int grid = num_tiles < sms ? num_tiles : sms;
   if (g_gemm_max_ctas > 0 && g_gemm_max_ctas < grid) grid = g_gemm_max_ctas;     // leave the other SMs to a concurrent stream
+  // TMA-store epilogue for bf16, non-accumulating outputs (T1_GEMM_EPI=direct restores the register path for A/B runs)
+  CUtensorMap td = ta, tdg = ta, tdu = ta;
+  {
+    static const char* env = getenv("T1_GEMM_EPI");
+    const bool want = !(env && env[0] == 'd') && !(flags & (GEMM_OUT_F32 | GEMM_ACCUMULATE)) && BN % 64 == 0;
+    if (want) {
+      rc = t1_make_tmap_bf16(&td, D, M, N, ldd, 32, 64);
+      if (rc) return rc;
+      if (swiglu && D2) {
+        rc = t1_make_tmap_bf16(&tdg, D2, M, N, ldd2, 32, 64);
+        if (rc) return rc;
+        rc = t1_make_tmap_bf16(&tdu, reinterpret_cast<const bf16*>(D2) + N, M, N, ldd2, 32, 64);
+        if (rc) return rc;
+      }
+      flags |= GEMM_TMA_STORE;
+    }
+  }
   EpiParams epi{D, bias, ldd, flags, swiglu ? D2 : nullptr, ldd2};
   // DRAM-traffic model for the raster order (L2 = 126 MB; measured with ncu on the gate_up wgrad, M=37888 N=3584 K=5888:
   // m-fastest re-read dY 14x = 6.3 GB per launch).  An operand that fits in ~48 MB of L2 is read once whatever the order;
@@ -386,7 +527,7 @@ static int gemm_impl(const void* A, long long lda, const void* B, long long ldb,
       attr_set = (le == cudaSuccess);                                                                                         \
     }                                                                                                                         \
     if (le == cudaSuccess)                                                                                                    \
-      gemm_bf16_tn_kernel<AMN, BMN, BNV><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, M, N, K, group_m, epi);            \
+      gemm_bf16_tn_kernel<AMN, BMN, BNV><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, td, tdg, tdu, M, N, K, group_m, epi); \
   } while (0)
 #define T1_GEMM_BY_MAJOR(BNV)                                   \
   do {                                                          \

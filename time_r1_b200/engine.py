@@ -119,7 +119,10 @@ class Engine:
         # next step's merger / prefill (which read the buckets in the order they are gathered) start under the gather
         self._ag_pending: dict = {}
         self._ag_capped = False
-        self.lazy_gather = world_size > 1 and _os.environ.get("T1_LAZY_GATHER", "1") != "0" and getattr(run, "zero_lazy_gather", True)
+        # measured at N=2 (profiles/r02_lazy_gather_n2.log): optimizer phase 41.5 -> 27.8 ms but the next step's ViT / merger
+        # phase 55.9 -> 86.1 ms (the CTA-limited gather is slow and the GEMMs beside it run capped): 1465 -> 1474 ms per step.
+        # Correct (two-step N-invariance run) but a net loss: OFF by default, T1_LAZY_GATHER=1 enables it
+        self.lazy_gather = world_size > 1 and _os.environ.get("T1_LAZY_GATHER", "0") == "1" and getattr(run, "zero_lazy_gather", True)
         self.pg_ag = process_group
         ag_ctas = int(_os.environ.get("T1_NCCL_AG_CTAS", getattr(run, "zero_ag_ctas", 8)))
         self.ag_ctas = ag_ctas
