@@ -55,6 +55,246 @@ struct EpiParams {
   long long ldd2;
 };
 
+// Per-warp state of the TMA-store epilogue: this warp's two [32 x 64] bf16 staging boxes; lane 0 owns the bulk async-groups.
+struct EpiWarp {
+  uint8_t* stage;
+  uint32_t n_store;
+};
+
+// Epilogue of ONE accumulator tile for one epilogue warp (32 rows starting at row_base, TMEM lanes of this warp's quadrant;
+// taddr_row = TMEM address of the tile's column 0 for that quadrant).  Shared by the 1-CTA and the 2-CTA (cta_group::2) kernels.
+template <int BN>
+__device__ __forceinline__ void gemm_epilogue_tile(const EpiParams& epi, const CUtensorMap* tma_d_p, const CUtensorMap* tma_d2g_p,
+                                                   const CUtensorMap* tma_d2u_p, uint32_t taddr_row, int row_base, int n_blk, int M,
+                                                   int N, int lane, EpiWarp& ew) {
+  const bool swiglu = epi.flags & GEMM_SWIGLU;
+  const int BNO = swiglu ? BN / 2 : BN;
+  const bool out_f32 = epi.flags & GEMM_OUT_F32;
+  const bool accum = epi.flags & GEMM_ACCUMULATE;
+  const bool bias_f32 = epi.flags & GEMM_BIAS_F32;
+  const bool tma_out = (epi.flags & GEMM_TMA_STORE) && BN % 64 == 0;
+    // ---- TMA-store path: this warp's two [32 x 64] bf16 staging boxes; lane 0 owns the bulk async-groups ----
+      // pk = this lane's 64 bf16 of the chunk (32 packed words): row `lane` of the box, 16-byte units XOR-swizzled by row & 7
+  auto store_box = [&](const CUtensorMap* tm, int col, int row0, const uint32_t* pk) {
+    uint8_t* buf = ew.stage + (ew.n_store & 1) * EPI_BOX_BYTES;
+    if (lane == 0) bulk_wait_group_read<1>();          // the group that last read this buffer (two stores ago) is done
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      *reinterpret_cast<uint4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(tm, buf, col, row0);                // rows >= M and columns >= the map's extent are clipped by the TMA unit
+      bulk_commit_group();
+    }
+    ++ew.n_store;
+  };
+  const int row = row_base + lane;
+      if (swiglu && tma_out) {
+        // as below, 64 output columns at a time: y, and (when kept for the backward) g and u, leave through TMA stores
+        const int row0 = row_base;
+#pragma unroll 1
+        for (int c = 0; c < BNO / 64; ++c) {
+          const int col0 = n_blk * BNO + c * 64;
+          if (col0 >= N) break;  // warp-uniform
+          uint32_t og[32], ou[32];
+          {
+            uint32_t vg[32], vu[32];
+#pragma unroll
+            for (int hlf = 0; hlf < 2; ++hlf) {
+              tmem_ld_32x32b_x32(taddr_row + c * 64 + hlf * 32, vg);
+              tmem_ld_32x32b_x32(taddr_row + BNO + c * 64 + hlf * 32, vu);
+              tmem_ld_wait();
+              if (epi.bias) {      // bf16 bias [2N]: gate part then up part (columns past N hold clipped garbage: skip the loads)
+#pragma unroll
+                for (int g8 = 0; g8 < 4; ++g8) {
+                  const int col = col0 + hlf * 32 + g8 * 8;
+                  if (col < N) {
+                    const uint4 bg = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(epi.bias) + col);
+                    const uint4 bu = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(epi.bias) + N + col);
+                    const uint32_t* pg = reinterpret_cast<const uint32_t*>(&bg);
+                    const uint32_t* pu = reinterpret_cast<const uint32_t*>(&bu);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                      const float2 a = unpack_bf16x2(pg[j]), b = unpack_bf16x2(pu[j]);
+                      vg[g8 * 8 + 2 * j] = __float_as_uint(__uint_as_float(vg[g8 * 8 + 2 * j]) + a.x);
+                      vg[g8 * 8 + 2 * j + 1] = __float_as_uint(__uint_as_float(vg[g8 * 8 + 2 * j + 1]) + a.y);
+                      vu[g8 * 8 + 2 * j] = __float_as_uint(__uint_as_float(vu[g8 * 8 + 2 * j]) + b.x);
+                      vu[g8 * 8 + 2 * j + 1] = __float_as_uint(__uint_as_float(vu[g8 * 8 + 2 * j + 1]) + b.y);
+                    }
+                  }
+                }
+              }
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                og[hlf * 16 + j] = pack_bf16x2(__uint_as_float(vg[2 * j]), __uint_as_float(vg[2 * j + 1]));
+                ou[hlf * 16 + j] = pack_bf16x2(__uint_as_float(vu[2 * j]), __uint_as_float(vu[2 * j + 1]));
+              }
+            }
+          }
+          if (epi.D2) {
+            store_box(tma_d2g_p, col0, row0, og);
+            store_box(tma_d2u_p, col0, row0, ou);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {      // y = silu(g) * u on the bf16-rounded projections, in place over og
+            const float2 gg = unpack_bf16x2(og[j]), uu = unpack_bf16x2(ou[j]);
+            og[j] = pack_bf16x2(gg.x * (1.0f / (1.0f + __expf(-gg.x))) * uu.x, gg.y * (1.0f / (1.0f + __expf(-gg.y))) * uu.y);
+          }
+          store_box(tma_d_p, col0, row0, og);
+        }
+      } else if (swiglu) {
+        // TMEM columns [0, BN/2) hold the gate projection of output columns n_blk*BNO + j, columns [BN/2, BN) the up
+        // projection of the same columns: y = silu(g) * u on the bf16-rounded projections (== gemm -> t1_swiglu)
+#pragma unroll 1
+        for (int c = 0; c < BNO / 32; ++c) {
+          const int col0 = n_blk * BNO + c * 32;
+          if (col0 >= N) break;  // warp-uniform
+          uint32_t vg[32], vu[32];
+          tmem_ld_32x32b_x32(taddr_row + c * 32, vg);
+          tmem_ld_32x32b_x32(taddr_row + BNO + c * 32, vu);
+          tmem_ld_wait();
+          if (row < M) {
+#pragma unroll
+            for (int g8 = 0; g8 < 4; ++g8) {
+              const int col = col0 + g8 * 8;
+              if (col < N) {
+                float fg[8], fu[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { fg[j] = __uint_as_float(vg[g8 * 8 + j]); fu[j] = __uint_as_float(vu[g8 * 8 + j]); }
+                if (epi.bias) {      // bf16 bias [2N]: gate part then up part
+                  const uint4 bg = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(epi.bias) + col);
+                  const uint4 bu = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(epi.bias) + N + col);
+                  const uint32_t* pg = reinterpret_cast<const uint32_t*>(&bg);
+                  const uint32_t* pu = reinterpret_cast<const uint32_t*>(&bu);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const float2 a = unpack_bf16x2(pg[j]), b = unpack_bf16x2(pu[j]);
+                    fg[2 * j] += a.x; fg[2 * j + 1] += a.y; fu[2 * j] += b.x; fu[2 * j + 1] += b.y;
+                  }
+                }
+                uint32_t og[4], ou[4], oy[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  og[j] = pack_bf16x2(fg[2 * j], fg[2 * j + 1]);
+                  ou[j] = pack_bf16x2(fu[2 * j], fu[2 * j + 1]);
+                  const float2 gg = unpack_bf16x2(og[j]), uu = unpack_bf16x2(ou[j]);
+                  oy[j] = pack_bf16x2(gg.x * (1.0f / (1.0f + __expf(-gg.x))) * uu.x, gg.y * (1.0f / (1.0f + __expf(-gg.y))) * uu.y);
+                }
+                *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(epi.D) + (long long)row * epi.ldd + col) = make_uint4(oy[0], oy[1], oy[2], oy[3]);
+                if (epi.D2) {
+                  bf16* d2 = reinterpret_cast<bf16*>(epi.D2) + (long long)row * epi.ldd2;
+                  *reinterpret_cast<uint4*>(d2 + col) = make_uint4(og[0], og[1], og[2], og[3]);
+                  *reinterpret_cast<uint4*>(d2 + N + col) = make_uint4(ou[0], ou[1], ou[2], ou[3]);
+                }
+              }
+            }
+          }
+        }
+      } else if (tma_out) {
+        const int row0 = row_base;
+#pragma unroll 1
+        for (int c = 0; c < BN / 64; ++c) {
+          const int col0 = n_blk * BN + c * 64;
+          if (col0 >= N) break;  // warp-uniform
+          uint32_t pk[32];
+#pragma unroll
+          for (int hlf = 0; hlf < 2; ++hlf) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(taddr_row + c * 64 + hlf * 32, v);
+            tmem_ld_wait();
+            if (epi.bias) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const int col = col0 + hlf * 32 + g * 8;
+                if (col < N) {
+                  float b8[8];
+                  if (bias_f32) {
+                    const float4* bp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(epi.bias) + col);
+                    const float4 b0 = bp[0], b1 = bp[1];
+                    b8[0] = b0.x; b8[1] = b0.y; b8[2] = b0.z; b8[3] = b0.w; b8[4] = b1.x; b8[5] = b1.y; b8[6] = b1.z; b8[7] = b1.w;
+                  } else {
+                    const uint4 b = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(epi.bias) + col);
+                    float2 t;
+                    t = unpack_bf16x2(b.x); b8[0] = t.x; b8[1] = t.y;
+                    t = unpack_bf16x2(b.y); b8[2] = t.x; b8[3] = t.y;
+                    t = unpack_bf16x2(b.z); b8[4] = t.x; b8[5] = t.y;
+                    t = unpack_bf16x2(b.w); b8[6] = t.x; b8[7] = t.y;
+                  }
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) v[g * 8 + j] = __float_as_uint(__uint_as_float(v[g * 8 + j]) + b8[j]);
+                }
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) pk[hlf * 16 + j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+          }
+          store_box(tma_d_p, col0, row0, pk);
+        }
+      } else
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {      // BN is a multiple of 32 for every instantiated width
+        const int col0 = n_blk * BN + c * 32;
+        if (col0 >= N) break;  // warp-uniform
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr_row + c * 32, v);
+        tmem_ld_wait();
+        if (row < M) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int col = col0 + g * 8;
+            if (col < N) {  // N % 8 == 0 is enforced on the host
+              float f[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
+              if (epi.bias) {
+                if (bias_f32) {
+                  const float4* bp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(epi.bias) + col);
+                  float4 b0 = bp[0], b1 = bp[1];
+                  f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                  f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+                } else {
+                  uint4 b = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(epi.bias) + col);
+                  float2 t;
+                  t = unpack_bf16x2(b.x); f[0] += t.x; f[1] += t.y;
+                  t = unpack_bf16x2(b.y); f[2] += t.x; f[3] += t.y;
+                  t = unpack_bf16x2(b.z); f[4] += t.x; f[5] += t.y;
+                  t = unpack_bf16x2(b.w); f[6] += t.x; f[7] += t.y;
+                }
+              }
+              if (out_f32) {
+                float4* dp = reinterpret_cast<float4*>(reinterpret_cast<float*>(epi.D) + (long long)row * epi.ldd + col);
+                if (accum) {
+                  float4 o0 = dp[0], o1 = dp[1];
+                  f[0] += o0.x; f[1] += o0.y; f[2] += o0.z; f[3] += o0.w;
+                  f[4] += o1.x; f[5] += o1.y; f[6] += o1.z; f[7] += o1.w;
+                }
+                dp[0] = make_float4(f[0], f[1], f[2], f[3]);
+                dp[1] = make_float4(f[4], f[5], f[6], f[7]);
+              } else {
+                uint4* dp = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(epi.D) + (long long)row * epi.ldd + col);
+                if (accum) {
+                  uint4 o = *dp;
+                  float2 t;
+                  t = unpack_bf16x2(o.x); f[0] += t.x; f[1] += t.y;
+                  t = unpack_bf16x2(o.y); f[2] += t.x; f[3] += t.y;
+                  t = unpack_bf16x2(o.z); f[4] += t.x; f[5] += t.y;
+                  t = unpack_bf16x2(o.w); f[6] += t.x; f[7] += t.y;
+                }
+                uint4 o;
+                o.x = pack_bf16x2(f[0], f[1]);
+                o.y = pack_bf16x2(f[2], f[3]);
+                o.z = pack_bf16x2(f[4], f[5]);
+                o.w = pack_bf16x2(f[6], f[7]);
+                *dp = o;
+              }
+            }
+          }
+        }
+      }
+}
+
 template <bool A_MN, bool B_MN, int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
@@ -188,29 +428,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   } else if (warp_idx >= 4) {
     // ===================== epilogue =====================
     const int q = warp_idx & 3;  // TMEM lane quadrant this warp may access
-    const bool out_f32 = epi.flags & GEMM_OUT_F32;
-    const bool accum = epi.flags & GEMM_ACCUMULATE;
-    const bool bias_f32 = epi.flags & GEMM_BIAS_F32;
-    const bool tma_out = (epi.flags & GEMM_TMA_STORE) && BN % 64 == 0;
-    // ---- TMA-store path: this warp's two [32 x 64] bf16 staging boxes; lane 0 owns the bulk async-groups ----
-    uint8_t* my_stage = epi_stage + q * 2 * EPI_BOX_BYTES;
-    uint32_t n_store = 0;
-    // pk = this lane's 64 bf16 of the chunk (32 packed words): row `lane` of the box, 16-byte units XOR-swizzled by row & 7
-    auto store_box = [&](const CUtensorMap* tm, int col, int row0, const uint32_t* pk) {
-      uint8_t* buf = my_stage + (n_store & 1) * EPI_BOX_BYTES;
-      if (lane == 0) bulk_wait_group_read<1>();          // the group that last read this buffer (two stores ago) is done
-      __syncwarp();
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        *reinterpret_cast<uint4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) {
-        tma_store_2d(tm, buf, col, row0);                // rows >= M and columns >= the map's extent are clipped by the TMA unit
-        bulk_commit_group();
-      }
-      ++n_store;
-    };
+    EpiWarp ew{epi_stage + q * 2 * EPI_BOX_BYTES, 0u};
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       int m_blk, n_blk;
@@ -219,214 +437,12 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
-      const int row = m_blk * BM + q * 32 + lane;
-      const uint32_t taddr_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-      if (swiglu && tma_out) {
-        // as below, 64 output columns at a time: y, and (when kept for the backward) g and u, leave through TMA stores
-        const int row0 = m_blk * BM + q * 32;
-#pragma unroll 1
-        for (int c = 0; c < BNO / 64; ++c) {
-          const int col0 = n_blk * BNO + c * 64;
-          if (col0 >= N) break;  // warp-uniform
-          uint32_t og[32], ou[32];
-          {
-            uint32_t vg[32], vu[32];
-#pragma unroll
-            for (int hlf = 0; hlf < 2; ++hlf) {
-              tmem_ld_32x32b_x32(taddr_row + c * 64 + hlf * 32, vg);
-              tmem_ld_32x32b_x32(taddr_row + BNO + c * 64 + hlf * 32, vu);
-              tmem_ld_wait();
-              if (epi.bias) {      // bf16 bias [2N]: gate part then up part (columns past N hold clipped garbage: skip the loads)
-#pragma unroll
-                for (int g8 = 0; g8 < 4; ++g8) {
-                  const int col = col0 + hlf * 32 + g8 * 8;
-                  if (col < N) {
-                    const uint4 bg = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(epi.bias) + col);
-                    const uint4 bu = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(epi.bias) + N + col);
-                    const uint32_t* pg = reinterpret_cast<const uint32_t*>(&bg);
-                    const uint32_t* pu = reinterpret_cast<const uint32_t*>(&bu);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                      const float2 a = unpack_bf16x2(pg[j]), b = unpack_bf16x2(pu[j]);
-                      vg[g8 * 8 + 2 * j] = __float_as_uint(__uint_as_float(vg[g8 * 8 + 2 * j]) + a.x);
-                      vg[g8 * 8 + 2 * j + 1] = __float_as_uint(__uint_as_float(vg[g8 * 8 + 2 * j + 1]) + a.y);
-                      vu[g8 * 8 + 2 * j] = __float_as_uint(__uint_as_float(vu[g8 * 8 + 2 * j]) + b.x);
-                      vu[g8 * 8 + 2 * j + 1] = __float_as_uint(__uint_as_float(vu[g8 * 8 + 2 * j + 1]) + b.y);
-                    }
-                  }
-                }
-              }
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                og[hlf * 16 + j] = pack_bf16x2(__uint_as_float(vg[2 * j]), __uint_as_float(vg[2 * j + 1]));
-                ou[hlf * 16 + j] = pack_bf16x2(__uint_as_float(vu[2 * j]), __uint_as_float(vu[2 * j + 1]));
-              }
-            }
-          }
-          if (epi.D2) {
-            store_box(&tma_d2g, col0, row0, og);
-            store_box(&tma_d2u, col0, row0, ou);
-          }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {      // y = silu(g) * u on the bf16-rounded projections, in place over og
-            const float2 gg = unpack_bf16x2(og[j]), uu = unpack_bf16x2(ou[j]);
-            og[j] = pack_bf16x2(gg.x * (1.0f / (1.0f + __expf(-gg.x))) * uu.x, gg.y * (1.0f / (1.0f + __expf(-gg.y))) * uu.y);
-          }
-          store_box(&tma_d, col0, row0, og);
-        }
-      } else if (swiglu) {
-        // TMEM columns [0, BN/2) hold the gate projection of output columns n_blk*BNO + j, columns [BN/2, BN) the up
-        // projection of the same columns: y = silu(g) * u on the bf16-rounded projections (== gemm -> t1_swiglu)
-#pragma unroll 1
-        for (int c = 0; c < BNO / 32; ++c) {
-          const int col0 = n_blk * BNO + c * 32;
-          if (col0 >= N) break;  // warp-uniform
-          uint32_t vg[32], vu[32];
-          tmem_ld_32x32b_x32(taddr_row + c * 32, vg);
-          tmem_ld_32x32b_x32(taddr_row + BNO + c * 32, vu);
-          tmem_ld_wait();
-          if (row < M) {
-#pragma unroll
-            for (int g8 = 0; g8 < 4; ++g8) {
-              const int col = col0 + g8 * 8;
-              if (col < N) {
-                float fg[8], fu[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) { fg[j] = __uint_as_float(vg[g8 * 8 + j]); fu[j] = __uint_as_float(vu[g8 * 8 + j]); }
-                if (epi.bias) {      // bf16 bias [2N]: gate part then up part
-                  const uint4 bg = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(epi.bias) + col);
-                  const uint4 bu = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(epi.bias) + N + col);
-                  const uint32_t* pg = reinterpret_cast<const uint32_t*>(&bg);
-                  const uint32_t* pu = reinterpret_cast<const uint32_t*>(&bu);
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    const float2 a = unpack_bf16x2(pg[j]), b = unpack_bf16x2(pu[j]);
-                    fg[2 * j] += a.x; fg[2 * j + 1] += a.y; fu[2 * j] += b.x; fu[2 * j + 1] += b.y;
-                  }
-                }
-                uint32_t og[4], ou[4], oy[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  og[j] = pack_bf16x2(fg[2 * j], fg[2 * j + 1]);
-                  ou[j] = pack_bf16x2(fu[2 * j], fu[2 * j + 1]);
-                  const float2 gg = unpack_bf16x2(og[j]), uu = unpack_bf16x2(ou[j]);
-                  oy[j] = pack_bf16x2(gg.x * (1.0f / (1.0f + __expf(-gg.x))) * uu.x, gg.y * (1.0f / (1.0f + __expf(-gg.y))) * uu.y);
-                }
-                *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(epi.D) + (long long)row * epi.ldd + col) = make_uint4(oy[0], oy[1], oy[2], oy[3]);
-                if (epi.D2) {
-                  bf16* d2 = reinterpret_cast<bf16*>(epi.D2) + (long long)row * epi.ldd2;
-                  *reinterpret_cast<uint4*>(d2 + col) = make_uint4(og[0], og[1], og[2], og[3]);
-                  *reinterpret_cast<uint4*>(d2 + N + col) = make_uint4(ou[0], ou[1], ou[2], ou[3]);
-                }
-              }
-            }
-          }
-        }
-      } else if (tma_out) {
-        const int row0 = m_blk * BM + q * 32;
-#pragma unroll 1
-        for (int c = 0; c < BN / 64; ++c) {
-          const int col0 = n_blk * BN + c * 64;
-          if (col0 >= N) break;  // warp-uniform
-          uint32_t pk[32];
-#pragma unroll
-          for (int hlf = 0; hlf < 2; ++hlf) {
-            uint32_t v[32];
-            tmem_ld_32x32b_x32(taddr_row + c * 64 + hlf * 32, v);
-            tmem_ld_wait();
-            if (epi.bias) {
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                const int col = col0 + hlf * 32 + g * 8;
-                if (col < N) {
-                  float b8[8];
-                  if (bias_f32) {
-                    const float4* bp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(epi.bias) + col);
-                    const float4 b0 = bp[0], b1 = bp[1];
-                    b8[0] = b0.x; b8[1] = b0.y; b8[2] = b0.z; b8[3] = b0.w; b8[4] = b1.x; b8[5] = b1.y; b8[6] = b1.z; b8[7] = b1.w;
-                  } else {
-                    const uint4 b = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(epi.bias) + col);
-                    float2 t;
-                    t = unpack_bf16x2(b.x); b8[0] = t.x; b8[1] = t.y;
-                    t = unpack_bf16x2(b.y); b8[2] = t.x; b8[3] = t.y;
-                    t = unpack_bf16x2(b.z); b8[4] = t.x; b8[5] = t.y;
-                    t = unpack_bf16x2(b.w); b8[6] = t.x; b8[7] = t.y;
-                  }
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) v[g * 8 + j] = __float_as_uint(__uint_as_float(v[g * 8 + j]) + b8[j]);
-                }
-              }
-            }
-#pragma unroll
-            for (int j = 0; j < 16; ++j) pk[hlf * 16 + j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-          }
-          store_box(&tma_d, col0, row0, pk);
-        }
-      } else
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {      // BN is a multiple of 32 for every instantiated width
-        const int col0 = n_blk * BN + c * 32;
-        if (col0 >= N) break;  // warp-uniform
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(taddr_row + c * 32, v);
-        tmem_ld_wait();
-        if (row < M) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int col = col0 + g * 8;
-            if (col < N) {  // N % 8 == 0 is enforced on the host
-              float f[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
-              if (epi.bias) {
-                if (bias_f32) {
-                  const float4* bp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(epi.bias) + col);
-                  float4 b0 = bp[0], b1 = bp[1];
-                  f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-                  f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-                } else {
-                  uint4 b = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(epi.bias) + col);
-                  float2 t;
-                  t = unpack_bf16x2(b.x); f[0] += t.x; f[1] += t.y;
-                  t = unpack_bf16x2(b.y); f[2] += t.x; f[3] += t.y;
-                  t = unpack_bf16x2(b.z); f[4] += t.x; f[5] += t.y;
-                  t = unpack_bf16x2(b.w); f[6] += t.x; f[7] += t.y;
-                }
-              }
-              if (out_f32) {
-                float4* dp = reinterpret_cast<float4*>(reinterpret_cast<float*>(epi.D) + (long long)row * epi.ldd + col);
-                if (accum) {
-                  float4 o0 = dp[0], o1 = dp[1];
-                  f[0] += o0.x; f[1] += o0.y; f[2] += o0.z; f[3] += o0.w;
-                  f[4] += o1.x; f[5] += o1.y; f[6] += o1.z; f[7] += o1.w;
-                }
-                dp[0] = make_float4(f[0], f[1], f[2], f[3]);
-                dp[1] = make_float4(f[4], f[5], f[6], f[7]);
-              } else {
-                uint4* dp = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(epi.D) + (long long)row * epi.ldd + col);
-                if (accum) {
-                  uint4 o = *dp;
-                  float2 t;
-                  t = unpack_bf16x2(o.x); f[0] += t.x; f[1] += t.y;
-                  t = unpack_bf16x2(o.y); f[2] += t.x; f[3] += t.y;
-                  t = unpack_bf16x2(o.z); f[4] += t.x; f[5] += t.y;
-                  t = unpack_bf16x2(o.w); f[6] += t.x; f[7] += t.y;
-                }
-                uint4 o;
-                o.x = pack_bf16x2(f[0], f[1]);
-                o.y = pack_bf16x2(f[2], f[3]);
-                o.z = pack_bf16x2(f[4], f[5]);
-                o.w = pack_bf16x2(f[6], f[7]);
-                *dp = o;
-              }
-            }
-          }
-        }
-      }
+      gemm_epilogue_tile<BN>(epi, &tma_d, &tma_d2g, &tma_d2u, tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN, m_blk * BM + q * 32, n_blk,
+                             M, N, lane, ew);
       tc_fence_before();
       mbar_arrive(&tmem_empty_bar[acc]);
     }
-    if (tma_out && lane == 0) bulk_wait_group<0>();      // every store of this warp has landed before the CTA retires
+    if ((epi.flags & GEMM_TMA_STORE) && lane == 0) bulk_wait_group<0>();      // every store of this warp has landed before the CTA retires
   }
 
   tc_fence_before();
@@ -434,6 +450,228 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   if (warp_idx == 2) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
+  }
+}
+
+
+// =====================================================================================================================
+// 2-CTA variant (tcgen05 cta_group::2): a thread-block CLUSTER of two CTAs (an SM pair) computes one 256 x 256 output tile.
+// UMMA M = 256: each CTA supplies its own 128 rows of A and HALF of the B tile (128 of the 256 N rows), the MMA (issued by
+// the leader CTA only) reads both CTAs' shared memory and writes 128 accumulator rows x 256 columns into EACH CTA's TMEM.
+// Per SM and per k-block that is 32 KB of operands for 2 x 128 x 256 x 64 MACs instead of 48 KB: the SS MMA is fed from
+// shared memory, and the 1-CTA form is shared-memory-bandwidth bound (its tensor pipe peaks at ~82 %).
+//   both CTAs, warp 0 : TMA producer for its halves; every load completes on the LEADER's full barrier
+//                       (cp.async.bulk.tensor ... .cta_group::2, barrier address with the peer bit cleared)
+//   leader,   warp 1  : tcgen05.mma.cta_group::2; tcgen05.commit ... multicast::cluster releases the smem stage / publishes
+//                       the accumulator in BOTH CTAs
+//   both CTAs, warp 2 : tcgen05.alloc.cta_group::2 (512 columns: two 256-column accumulators)
+//   both CTAs, w 4..7 : epilogue of the CTA's own 128 rows (same code as the 1-CTA kernel); "accumulator free" arrives on the
+//                       leader's barrier (mbarrier.arrive.shared::cluster)
+// =====================================================================================================================
+constexpr int STAGES2 = 6;
+constexpr int B2_BYTES = 128 * BK * 2;                       // this CTA's half of the B tile
+constexpr int STAGE2_BYTES = A_BYTES + B2_BYTES;             // 32 KB
+constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + EPI_STAGE_BYTES + 1024 + 256;
+static_assert(SMEM2_BYTES <= 227 * 1024, "shared memory budget (2-CTA kernel)");
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;              // shared::cluster address of the same offset in the pair's CTA 0
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const void* desc, uint64_t* leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(desc), "r"(smem_u32(leader_bar) & PEER_BIT_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ss_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once the MMAs issued so far have retired) on the barrier at this shared-memory offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2sm_multicast(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_BIT_MASK) : "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_result) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "n"(kCols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                     const __grid_constant__ CUtensorMap tma_d, const __grid_constant__ CUtensorMap tma_d2g,
+                     const __grid_constant__ CUtensorMap tma_d2u, int M, int N, int K, int group_m, EpiParams epi) {
+  constexpr int BN = 256;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* a_tiles = smem;
+  uint8_t* b_tiles = smem + STAGES2 * A_BYTES;
+  uint8_t* epi_stage = smem + STAGES2 * STAGE2_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + EPI_STAGE_BYTES);   // used in the leader CTA
+  uint64_t* empty_bar = full_bar + STAGES2;                                          // each CTA: released by the multicast commit
+  uint64_t* tmem_full_bar = empty_bar + STAGES2;                                     // each CTA
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;                                      // leader: 2 x 128 epilogue threads
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const bool swiglu = epi.flags & GEMM_SWIGLU;
+  const int BNO = swiglu ? BN / 2 : BN;
+  const int num_m = (M + 2 * BM - 1) / (2 * BM);           // 256-row tiles
+  const int num_n = (N + BNO - 1) / BNO;
+  const int num_tiles = num_m * num_n;
+  const int num_k = (K + BK - 1) / BK;
+  const int tiles_per_group = group_m * num_n;
+  auto tile_coords = [&](int tile, int& m_blk, int& n_blk) {
+    const int g = tile / tiles_per_group, rem = tile - g * tiles_per_group;
+    const int m0 = g * group_m;
+    const int gm = min(group_m, num_m - m0);
+    n_blk = rem / gm;
+    m_blk = m0 + (rem - n_blk * gm);
+  };
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+  }
+  if (warp_idx == 1 && lane == 0) {
+    for (int i = 0; i < STAGES2; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 256);
+    }
+    mbar_fence_init();
+  }
+  if (warp_idx == 2) tmem_alloc_2sm<512>(tmem_ptr_smem);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();              // the peer's barriers are initialised and its TMEM is allocated before anything remote happens
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp_idx == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
+        int m_blk, n_blk;
+        tile_coords(tile, m_blk, n_blk);
+        const int m0 = m_blk * 2 * BM + (int)rank * BM;                              // this CTA's 128 A rows
+        // this CTA's half of the B tile: plain = rows n_blk*256 + rank*128; SwiGLU = rank 0 the gate rows, rank 1 the up rows
+        const int n0 = swiglu ? (int)rank * N + n_blk * BNO : n_blk * BN + (int)rank * 128;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE2_BYTES);    // both CTAs' bytes land on this barrier
+          if constexpr (A_MN) {
+#pragma unroll
+            for (int a = 0; a < BM / 64; ++a)
+              tma_load_2d_2sm(a_tiles + stage * A_BYTES + a * MN_ATOM_BYTES, &tma_a, &full_bar[stage], m0 + a * 64, kb * BK);
+          } else {
+            tma_load_2d_2sm(a_tiles + stage * A_BYTES, &tma_a, &full_bar[stage], kb * BK, m0);
+          }
+          if constexpr (B_MN) {
+#pragma unroll
+            for (int b = 0; b < 2; ++b)
+              tma_load_2d_2sm(b_tiles + stage * B2_BYTES + b * MN_ATOM_BYTES, &tma_b, &full_bar[stage], n0 + b * 64, kb * BK);
+          } else {
+            tma_load_2d_2sm(b_tiles + stage * B2_BYTES, &tma_b, &full_bar[stage], kb * BK, n0);
+          }
+          if (++stage == STAGES2) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ===================== MMA issuer (leader CTA, single thread) =====================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN) | (A_MN ? (1u << 15) : 0u) | (B_MN ? (1u << 16) : 0u);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += n_clusters, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(a_tiles + stage * A_BYTES), b_addr = smem_u32(b_tiles + stage * B2_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t a_desc = A_MN ? umma_desc_sw128_mnmajor(a_addr + k * UMMA_K * 128, MN_ATOM_BYTES, 1024)
+                                         : umma_desc_sw128_kmajor(a_addr + k * 32);
+            const uint64_t b_desc = B_MN ? umma_desc_sw128_mnmajor(b_addr + k * UMMA_K * 128, MN_ATOM_BYTES, 1024)
+                                         : umma_desc_sw128_kmajor(b_addr + k * 32);
+            umma_bf16_ss_2sm(tmem_d, a_desc, b_desc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_2sm_multicast(&empty_bar[stage]);      // frees this stage in both CTAs once the MMAs retire
+          if (++stage == STAGES2) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_2sm_multicast(&tmem_full_bar[acc]);      // accumulator complete -> both epilogues
+      }
+    }
+  } else if (warp_idx >= 4) {
+    // ===================== epilogue (both CTAs: own 128 rows of the 256-row tile) =====================
+    const int q = warp_idx & 3;
+    EpiWarp ew{epi_stage + q * 2 * EPI_BOX_BYTES, 0u};
+    int it = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += n_clusters, ++it) {
+      int m_blk, n_blk;
+      tile_coords(tile, m_blk, n_blk);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      gemm_epilogue_tile<BN>(epi, &tma_d, &tma_d2g, &tma_d2u, tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN,
+                             m_blk * 2 * BM + (int)rank * BM + q * 32, n_blk, M, N, lane, ew);
+      tc_fence_before();
+      mbar_arrive_leader(&tmem_empty_bar[acc]);
+    }
+    if ((epi.flags & GEMM_TMA_STORE) && lane == 0) bulk_wait_group<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();              // the peer has read its accumulators and issued its last remote arrive
+  if (warp_idx == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm<512>(tmem_base);
   }
 }
 
@@ -519,6 +757,56 @@ static int gemm_impl(const void* A, long long lda, const void* B, long long ldb,
     if (env && atoi(env) > 0) group_m = atoi(env) < num_m ? atoi(env) : num_m;
   }
   cudaError_t le = cudaSuccess;
+  // ---- 2-CTA (cta_group::2) kernel: 256 x 256 tiles on SM pairs.  T1_GEMM_2CTA=0 keeps everything on the 1-CTA kernel ----
+  {
+    static const char* env2 = getenv("T1_GEMM_2CTA");
+    const bool want2 = !(env2 && env2[0] == '0') && BN == 256 && M > BM && (!a_mn || M % 64 == 0) && (!b_mn || N % 64 == 0);
+    if (want2) {
+      CUtensorMap tb2;
+      rc = b_mn ? t1_make_tmap_bf16(&tb2, B, K, N, ldb, BK, 64)
+                : (swiglu ? t1_make_tmap_bf16(&tb2, B, 2LL * N, K, ldb, 128, BK) : t1_make_tmap_bf16(&tb2, B, N, K, ldb, 128, BK));
+      if (rc) return rc;
+      const int num_m2 = (M + 2 * BM - 1) / (2 * BM);
+      const int tiles2 = num_m2 * num_n;
+      int clusters = tiles2 < sms / 2 ? tiles2 : sms / 2;
+      if (g_gemm_max_ctas > 0 && g_gemm_max_ctas / 2 < clusters) clusters = g_gemm_max_ctas / 2 > 0 ? g_gemm_max_ctas / 2 : 1;
+      int group_m2 = (group_m + 1) / 2;
+      if (group_m2 > num_m2) group_m2 = num_m2;
+      if (group_m2 < 1) group_m2 = 1;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(2 * clusters);
+      cfg.blockDim = dim3(NUM_THREADS);
+      cfg.dynamicSmemBytes = SMEM2_BYTES;
+      cfg.stream = stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+#define T1_GEMM2_LAUNCH(AMN, BMN)                                                                                          \
+  do {                                                                                                                     \
+    static bool attr_set2 = false;                                                                                         \
+    if (!attr_set2) {                                                                                                      \
+      le = cudaFuncSetAttribute(gemm2_bf16_tn_kernel<AMN, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES); \
+      attr_set2 = (le == cudaSuccess);                                                                                     \
+    }                                                                                                                      \
+    if (le == cudaSuccess) le = cudaLaunchKernelEx(&cfg, gemm2_bf16_tn_kernel<AMN, BMN>, ta, tb2, td, tdg, tdu, M, N, K, group_m2, epi); \
+  } while (0)
+      if (a_mn && b_mn) T1_GEMM2_LAUNCH(true, true);
+      else if (a_mn) T1_GEMM2_LAUNCH(true, false);
+      else if (b_mn) T1_GEMM2_LAUNCH(false, true);
+      else T1_GEMM2_LAUNCH(false, false);
+#undef T1_GEMM2_LAUNCH
+      if (le != cudaSuccess) {
+        t1_set_error("t1_gemm_bf16_tn (2-CTA): launch failed: %s", cudaGetErrorString(le));
+        return T1_ERR_CUDA;
+      }
+      t1_count_launch();
+      return T1_OK;
+    }
+  }
 #define T1_GEMM_LAUNCH(AMN, BMN, BNV)                                                                                         \
   do {                                                                                                                        \
     static bool attr_set = false;                                                                                             \
