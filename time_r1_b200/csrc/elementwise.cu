@@ -6,6 +6,7 @@
 // src/time_r1/rl/timer1_trainer.py:452-457,569-573 executes.  All math in fp32, bf16 storage, 16-byte vector
 // accesses, one rounding at the end.
 #include "t1_common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -118,6 +119,122 @@ __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
   t = unpack_bf16x2(u.y); f[2] = t.x; f[3] = t.y;
   t = unpack_bf16x2(u.z); f[4] = t.x; f[5] = t.y;
   t = unpack_bf16x2(u.w); f[6] = t.x; f[7] = t.y;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Warp-per-row RMSNorm / LayerNorm forward for the big token batches (prefill, scoring, backward recompute, ViT).
+// The one-CTA-per-row kernel above launches T tiny CTAs (a [16384, 1280] ViT norm = 16384 CTAs of 160 busy threads and a
+// block barrier each): measured ~97 us per launch in the step against a 26 us byte floor.  Here a WARP owns a row — the row
+// (and its delta) sits in registers as packed 16-byte vectors, the reductions are shuffles, no shared memory, no barrier —
+// and a persistent grid of 8-warp CTAs strides over the rows, so every SM keeps dozens of independent 16-byte loads in flight.
+// NV = 16-byte vectors per lane (D <= 256 * NV).  Same arithmetic and roundings as norm_fwd_kernel.
+// ---------------------------------------------------------------------------------------------
+template <bool kLayerNorm, int NV>
+__global__ void __launch_bounds__(256)
+norm_fwd_rows_kernel(const bf16* x, const bf16* __restrict__ delta, bf16* x_out, const bf16* __restrict__ w,
+                     const bf16* __restrict__ b, bf16* __restrict__ y, int T, int D, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int nv = D >> 3;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < T; row += warps) {
+    const size_t base = (size_t)row * D;
+    uint4 xq[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = lane + i * 32;
+      xq[i] = v < nv ? *reinterpret_cast<const uint4*>(x + base + v * 8) : zero4;
+    }
+    if (delta) {
+      uint4 dq[NV];
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int v = lane + i * 32;
+        dq[i] = v < nv ? *reinterpret_cast<const uint4*>(delta + base + v * 8) : zero4;
+      }
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int v = lane + i * 32;
+        float a[8], d[8];
+        unpack8(xq[i], a);
+        unpack8(dq[i], d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] += d[j];
+        xq[i].x = pack_bf16x2(a[0], a[1]);        // the norm sees exactly the bf16 values later consumers of x will read
+        xq[i].y = pack_bf16x2(a[2], a[3]);
+        xq[i].z = pack_bf16x2(a[4], a[5]);
+        xq[i].w = pack_bf16x2(a[6], a[7]);
+        if (v < nv) *reinterpret_cast<uint4*>(x_out + base + v * 8) = xq[i];
+      }
+    }
+    float sum = 0.f, sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float a[8];
+      unpack8(xq[i], a);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        sum += a[j];
+        sq += a[j] * a[j];
+      }
+    }
+    float mean = 0.f, rstd;
+    if (kLayerNorm) {
+      mean = warp_sum(sum) / (float)D;
+      float var = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        if (lane + i * 32 < nv) {
+          float a[8];
+          unpack8(xq[i], a);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) var += (a[j] - mean) * (a[j] - mean);
+        }
+      }
+      rstd = rsqrtf(warp_sum(var) / (float)D + eps);
+    } else {
+      rstd = rsqrtf(warp_sum(sq) / (float)D + eps);
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = lane + i * 32;
+      if (v < nv) {
+        float a[8], wv[8], o[8];
+        unpack8(xq[i], a);
+        load8(w + v * 8, wv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (a[j] - mean) * rstd * wv[j];
+        if (kLayerNorm && b) {
+          float bv[8];
+          load8(b + v * 8, bv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += bv[j];
+        }
+        store8(y + base + v * 8, o);
+      }
+    }
+  }
+}
+
+template <bool kLayerNorm>
+static bool launch_norm_rows(const void* x, const void* delta, void* x_out, const void* w, const void* b, void* y, int T, int D,
+                             float eps, cudaStream_t stream) {
+  const int nvl = (D / 8 + 31) / 32;            // vectors per lane
+  static const char* env = getenv("T1_NORM_ROWS");
+  if (env && env[0] == '0') return false;       // A/B switch: the one-CTA-per-row kernel
+  // measured on B200 (profiles/r02_norm_ab.txt): [16384, 1280] + delta 34.8 us here vs 55.3 us for the CTA-per-row kernel,
+  // but [5888, 3584] + delta 55.3 vs 43.0 us (14 vectors per lane cost 200 registers: one CTA per SM) -> narrow rows only
+  if (T <= 64 || nvl > 5) return false;         // decode-sized batches keep the PDL-aware kernel
+  const int want = (T + 7) / 8;
+  const int cap = 8 * t1_num_sms();
+  const int grid = want < cap ? want : cap;
+#define T1_NORM_ROWS(NVV)                                                                                                    \
+  norm_fwd_rows_kernel<kLayerNorm, NVV><<<grid, 256, 0, stream>>>((const bf16*)x, (const bf16*)delta, (bf16*)x_out, (const bf16*)w, \
+                                                                  (const bf16*)b, (bf16*)y, T, D, eps)
+  if (nvl <= 2) T1_NORM_ROWS(2);
+  else T1_NORM_ROWS(5);
+#undef T1_NORM_ROWS
+  return true;
 }
 
 template <int NIT>
@@ -586,6 +703,10 @@ extern "C" int t1_rmsnorm(const void* x, const void* delta, void* x_out, const v
   if (T == 0) return T1_OK;
   T1_CHECK_ARG(T > 0 && D > 0 && D % 8 == 0 && D <= 8192, "t1_rmsnorm: D=%d must be a multiple of 8 and <= 8192", D);
   T1_CHECK_ARG(!delta || x_out, "t1_rmsnorm: x_out is required when delta is given");
+  if (launch_norm_rows<false>(x, delta, x_out, w, nullptr, y, T, D, eps, stream)) {
+    T1_CUDA_LAUNCH_CHECK("t1_rmsnorm");
+    return T1_OK;
+  }
   if (t1_launch(norm_fwd_kernel<false>, dim3(T), dim3(256), 0, stream, (const bf16*)x, (const bf16*)delta, (bf16*)x_out,
                 (const bf16*)w, (const bf16*)nullptr, (bf16*)y, D, eps) != cudaSuccess) {
     t1_set_error("t1_rmsnorm: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -600,6 +721,10 @@ extern "C" int t1_layernorm(const void* x, const void* delta, void* x_out, const
   if (T == 0) return T1_OK;
   T1_CHECK_ARG(T > 0 && D > 0 && D % 8 == 0 && D <= 8192, "t1_layernorm: D=%d must be a multiple of 8 and <= 8192", D);
   T1_CHECK_ARG(!delta || x_out, "t1_layernorm: x_out is required when delta is given");
+  if (launch_norm_rows<true>(x, delta, x_out, w, b, y, T, D, eps, stream)) {
+    T1_CUDA_LAUNCH_CHECK("t1_layernorm");
+    return T1_OK;
+  }
   norm_fwd_kernel<true><<<T, 256, 0, stream>>>((const bf16*)x, (const bf16*)delta, (bf16*)x_out, (const bf16*)w, (const bf16*)b, (bf16*)y, D, eps);
   T1_CUDA_LAUNCH_CHECK("t1_layernorm");
   return T1_OK;
