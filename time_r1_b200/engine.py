@@ -73,6 +73,10 @@ class ScoreState:
 
 
 class Engine:
+    # defaults for objects built without __init__ (decode-only tools): no parameter all-gather is ever pending
+    _ag_pending: dict = {}
+    _ag_capped = False
+
     def __init__(self, cfg: ModelConfig, weights: ModelWeights, run: RunConfig, with_ref: bool = True,
                  rank: int = 0, world_size: int = 1, process_group=None):
         if not torch.cuda.is_available():

@@ -18,8 +18,25 @@ lo, hi, shared = make_mask("packed", T, P, C); hi[P + 8 * C:] = 0; lo[P + 8 * C:
 out = torch.empty(T, qd, device="cuda", dtype=torch.bfloat16); lse = torch.empty(Hq, T, device="cuda")
 do = rnd(T, qd, seed=5); g = torch.empty_like(qkv)
 
+act = torch.empty(T, I, device="cuda", dtype=torch.bfloat16)
+dx = torch.empty(T, D, device="cuda", dtype=torch.bfloat16)
+# ViT: one full-attention block of cfg2 (16 slots x 1024 patches, 16 heads x 80)
+from time_r1_b200 import config, indexing
+import numpy as np
+vcfg = config.PRESETS["qwen2.5-vl-7b"]()
+plan = indexing.vision_plan(vcfg, [(16, 32, 32)])
+vqkv = rnd(plan.n_patches, 3 * 1280, seed=7)
+i32 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).cuda()
+flo, fhi = i32(plan.full_lo), i32(plan.full_hi)
+vout = torch.empty(plan.n_patches, 1280, device="cuda", dtype=torch.bfloat16)
+xn = rnd(T, D, seed=9); nw = torch.ones(D, device="cuda", dtype=torch.bfloat16); nh = torch.empty_like(xn); nx = torch.empty_like(xn)
+
 def run():
-    ops.gemm(x, w, out=gu)
+    ops.gemm(x, w, out=gu)                                   # 2-CTA (cta_group::2) GEMM, TMA-store epilogue
+    ops.gemm_swiglu(x, w, out=act, gate_up_out=gu)           # the step's gate_up form: SwiGLU epilogue + kept projection
+    ops.gemm(gu, w, out=dx, b_t=True)                        # dgrad form (B MN-major), K = 37888
+    ops.attn_fwd_tc(vqkv[:, :1280], vqkv[:, 1280:2560], vqkv[:, 2560:], flo, fhi, 0, 16, 16, 80, 80 ** -0.5, out=vout, need_lse=False)
+    ops.rmsnorm(xn, nw, 1e-6, delta=x, out=nh, x_out=nx)
     ops.gemm(gu, x, out=dw, a_t=True, b_t=True)
     ops.attn_fwd_tc(q, k, v, lo, hi, shared, Hq, Hkv, hd, hd ** -0.5, out=out, lse=lse)
     ops.attn_bwd_tc(q, k, v, out, do, lse, lo, hi, shared, Hq, Hkv, hd, hd ** -0.5, g[:, :qd], g[:, qd:qd + kd], g[:, qd + kd:])
