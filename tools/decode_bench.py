@@ -36,12 +36,12 @@ def main():
     mw = weights.ModelWeights(cfg, dev, world_size=1)
     mw.init_random(seed=0)
     rng = np.random.default_rng(0)
-    nv = 4096
+    nv = int(os.environ.get("T1_BENCH_NV", "4096"))       # vision tokens of the prompt (cfg2 4096, cfg3 8192, cfg5 16384)
     prompts, embs = [], []
     for i in range(n_groups):
         text = rng.integers(0, 151643, 110)
         ids = np.concatenate([[151644, 872, 198, 151652], np.full(nv, cfg.video_token_id), [151653], text, [151645, 198, 151644, 77091, 198]]).astype(np.int64)
-        prompts.append(engine.Prompt(input_ids=ids, pixel_values=None, grid_thw=[(16, 32, 32)], second_per_grid_ts=[1.0]))
+        prompts.append(engine.Prompt(input_ids=ids, pixel_values=None, grid_thw=[(nv // 256, 32, 32)], second_per_grid_ts=[1.0]))
         embs.append((torch.randn(nv, cfg.hidden_size, device=dev) * 0.02).to(torch.bfloat16))
     variants = [("legacy", False, 0, 1), ("stream", False, 0, 1), ("stream", True, 0, 1), ("stream", True, 4, 1), ("stream", True, 10, 1),
                 ("stream", True, 5, 2), ("stream", True, 3, 2)]
