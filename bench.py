@@ -304,9 +304,8 @@ class TemplateRewards:
     """Completions are overwritten post hoc with template strings (random-init models never emit <answer> tags —
     SURVEY §0); the strings go through the product's reward path.  route "device" (default): the templates enter as token
     ids of a byte-level vocabulary and are detokenised, parsed and scored on the GPU (t1_detokenize -> t1_parse_answers ->
-    t1_iou_reward; nothing is copied back before the loss); route "host": regex parse on the host + t1_iou_reward."""
-
-    PAD = 256
+    t1_iou_reward; nothing is copied back before the loss) — the vocabulary is Qwen-sized (152064 entries, multi-byte tokens,
+    specials at the Qwen ids), not a 258-entry byte table; route "host": regex parse on the host + t1_iou_reward."""
 
     def __init__(self, G: int, rank: int, route: str = "device"):
         import numpy as np
@@ -331,6 +330,48 @@ class TemplateRewards:
                 texts.append(f"<think>the event spans these frames</think><answer>{s:.2f} to {e:.2f}</answer>")
         return row, dur, texts
 
+    # ---- a Qwen-sized byte-level vocabulary (152064 entries, multi-byte tokens) for the device route -------------------
+    # ids 0..255 = the single bytes; then every 2-character and the common 3/4-character strings of the completion alphabet
+    # (what BPE merges look like: " to", "think", "</", "12", ".5" ...); specials at the Qwen ids (<|endoftext|> 151643,
+    # <|im_end|> 151645); the rest of the table is filler words so its size and byte-offset range match the production table.
+    VOCAB, EOT, IM_END = 152064, 151643, 151645
+
+    @classmethod
+    def _vocabulary(cls):
+        if getattr(cls, "_vocab", None) is None:
+            import itertools
+
+            alphabet = "0123456789. <>/abcdefghijklmnopqrstuvwxyz"
+            entries = [bytes([b]) for b in range(256)]
+            multi = ["".join(p) for p in itertools.product(alphabet, repeat=2)]
+            multi += ["<think>", "</think>", "<answer>", "</answer>", " to ", " to", "the ", "event", "spans", "these", "frames", "unsure",
+                      "think", "answer", " the", "ans", "wer", "fra", "mes", "spa", "eve"]
+            multi += [f"{a}{b}{c}" for a in "0123456789" for b in "0123456789." for c in "0123456789"]
+            entries += [m.encode() for m in dict.fromkeys(multi)]
+            n_real = len(entries)
+            entries += [b"w%05d" % i for i in range(cls.VOCAB - n_real)]
+            entries[cls.EOT], entries[cls.IM_END] = b"<|endoftext|>", b"<|im_end|>"
+            lookup = {}
+            for i, e in enumerate(entries[:n_real]):
+                lookup.setdefault(e, i)
+            cls._vocab = (entries, lookup, max(len(e) for e in entries[:n_real]))
+        return cls._vocab
+
+    @classmethod
+    def _tokenize(cls, text: str):
+        """Greedy longest-match over the vocabulary above (every byte is a token, so it always terminates)."""
+        _, lookup, longest = cls._vocabulary()
+        b = text.encode("utf-8")
+        ids, i = [], 0
+        while i < len(b):
+            for n in range(min(longest, len(b) - i), 0, -1):
+                t = lookup.get(b[i:i + n])
+                if t is not None:
+                    ids.append(t)
+                    i += n
+                    break
+        return ids
+
     def _device_route(self, completion_ids):
         import numpy as np
         import torch
@@ -339,16 +380,16 @@ class TemplateRewards:
         from time_r1_b200.detok import DetokTable
 
         if self._dr is None:
-            table = DetokTable.from_byte_strings([bytes([b]) for b in range(256)] + [b"<|endoftext|>", b"<|im_end|>"], [256, 257],
-                                                 completion_ids.device)
+            entries, _, _ = self._vocabulary()
+            table = DetokTable.from_byte_strings(entries, [self.EOT, self.IM_END], completion_ids.device)
             self._dr = rewards.DeviceRewards([rewards.iou_timestamp_reward_v2, rewards.format_reward], table)
         row, dur, texts = self._templates()
+        toks = [self._tokenize(t) for t in texts]
         C = completion_ids.shape[1]
-        ids = np.full((self.G, max(C, max(len(t) for t in texts) + 1)), self.PAD, np.int32)
-        for g, t in enumerate(texts):
-            b = np.frombuffer(t.encode("utf-8"), np.uint8)
-            ids[g, :len(b)] = b
-            ids[g, len(b)] = 257                                               # <|im_end|>, then padding
+        ids = np.full((self.G, max(C, max(len(t) for t in toks) + 1)), self.EOT, np.int32)
+        for g, t in enumerate(toks):
+            ids[g, :len(t)] = t
+            ids[g, len(t)] = self.IM_END                                       # <|im_end|>, then <|endoftext|> padding
         return self._dr(torch.from_numpy(ids).to(completion_ids.device, non_blocking=True), row["gt"], dur)
 
     def __call__(self, completion_ids):

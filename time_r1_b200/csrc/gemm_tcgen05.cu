@@ -769,7 +769,13 @@ static int gemm_impl(const void* A, long long lda, const void* B, long long ldb,
       const int num_m2 = (M + 2 * BM - 1) / (2 * BM);
       const int tiles2 = num_m2 * num_n;
       int clusters = tiles2 < sms / 2 ? tiles2 : sms / 2;
-      if (g_gemm_max_ctas > 0 && g_gemm_max_ctas / 2 < clusters) clusters = g_gemm_max_ctas / 2 > 0 ? g_gemm_max_ctas / 2 : 1;
+      if (g_gemm_max_ctas > 0) {
+        // SMs are reserved for a concurrent stream (NCCL): each of them may break a different SM pair, and a cluster that finds
+        // no free pair would only start when another one retires — i.e. after the whole persistent loop
+        int free_pairs = sms / 2 - (sms - g_gemm_max_ctas);
+        if (free_pairs < 1) free_pairs = 1;
+        if (free_pairs < clusters) clusters = free_pairs;
+      }
       int group_m2 = (group_m + 1) / 2;
       if (group_m2 > num_m2) group_m2 = num_m2;
       if (group_m2 < 1) group_m2 = 1;
