@@ -25,11 +25,14 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE gemm_bf16_tn launch from the committed ncu --set full capture
-# (profiles/r01_ncu_full_top_kernels_v3.txt): the gate_up projection over the packed scoring rows, the largest GEMM of the
-# step.  Algorithmic bytes of that launch: A 42.2 MB + B 271.6 MB + D 446.2 MB = 760 MB.
-NCU_GEMM_TRAFFIC = {"bytes": 873.8e6, "note": "ncu, one launch M=5888 N=37888 K=3584 (algorithmic 760e6 B, 1.6 TFLOP, 1.090 ms = 1467 TFLOP/s, "
-                                            "tensor pipe 81.6% active); the wgrad form M=37888 N=3584 K=5888 moved 6.6e9 B before the grouped raster"}
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant GEMM from the committed ncu --set full capture
+# (profiles/r02_ncu_full_tensor_kernels.txt): the gate_up projection over the packed scoring rows in the form the step runs it
+# (2-CTA kernel, SwiGLU epilogue, projection kept for the backward).  Algorithmic bytes of that launch: A 42.2 MB + B 271.6 MB +
+# gate_up 446.2 MB + act 223.1 MB = 983 MB.
+NCU_GEMM_TRAFFIC = {"bytes": 1399.2e6, "note": "ncu, one launch of gemm2_bf16_tn (cta_group::2) M=5888 N=2x18944 K=3584 with the SwiGLU epilogue: "
+                                              "1.003 ms, tensor pipe 97.6% active, DRAM read 753.9 MB + write 645.3 MB vs 983 MB algorithmic (the 271.6 MB "
+                                              "weight operand is read ~2.6x: it does not fit the L2 and each die caches its own copy); the plain form "
+                                              "0.964 ms / 98.3%, dgrad 1.125 ms / 99.0% (2.6 GB read: dY re-read 3.6x), wgrad 1.019 ms / 98.2%: none is HBM-bound"}
 METRIC = "grpo_rollout_samples_per_sec"
 UNIT = "samples/s"
 
@@ -677,7 +680,7 @@ def run_ours(args):
         for k, v in flops.step_flops(cfg, grid_i, len(ids_i), G, C).items():
             algo[k] = algo.get(k, 0.0) + v
     roofline = {
-        "bound": "tensor", "kernel": "gemm_bf16_tn (tcgen05)", "achieved": round(gemm_tflops, 1), "peak": peak_tf, "unit": "TFLOP/s",
+        "bound": "tensor", "kernel": "gemm2_bf16_tn (tcgen05 cta_group::2, 256x256 tiles on SM pairs; entry point t1_gemm_bf16_tn / t1_gemm_swiglu)", "achieved": round(gemm_tflops, 1), "peak": peak_tf, "unit": "TFLOP/s",
         "frac": round(gemm_tflops / peak_tf, 4), "traffic": NCU_GEMM_TRAFFIC["bytes"], "traffic_note": NCU_GEMM_TRAFFIC["note"], "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback",
         "launches_per_step": gm["launches"] // max(1, args.steps), "gemm_ms_per_step": round(gm["ms"] / args.steps, 2),
         "gemm_tflop_per_step": round(gm["flops"] / args.steps / 1e12, 1),
