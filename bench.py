@@ -83,10 +83,18 @@ def parse_args():
 TIMERFT_GRIDS = [(147, 6, 12), (8, 26, 46), (60, 16, 28), (384, 6, 10)]
 
 
-def grid_of(args, index: int = 0):
-    """Patch grid of prompt-group `index` (global index over ranks and micro-batches)."""
+def grid_of(args, index: int = 0, world: int = 1):
+    """Patch grid of prompt-group `index` = rank * groups_per_step + micro-batch.  cfg4: the world x groups_per_step clips of one
+    optimizer step (the four TimeRFT shapes in rotation) are dealt to the ranks the way the trainer's dataloader deals a
+    global batch — dist_utils.balanced_deal, even token counts per rank — because the step ends with the slowest rank."""
     if args.grid == "timerft":
-        return TIMERFT_GRIDS[index % len(TIMERFT_GRIDS)]
+        from time_r1_b200.dist_utils import balanced_deal
+
+        ng = args.groups_per_step
+        clips = [TIMERFT_GRIDS[i % len(TIMERFT_GRIDS)] for i in range(world * ng)]
+        order = balanced_deal([t * h * w for t, h, w in clips], world) if not os.environ.get("T1_NO_BALANCE") else list(range(world * ng))
+        rank, a = divmod(index, ng)
+        return clips[order[a * world + rank]] if rank < world else clips[index % len(clips)]
     return tuple(int(v) for v in args.grid.split(",")) if args.grid else (args.slots, 32, 32)
 
 
@@ -553,7 +561,7 @@ def run_ours(args):
     eng = engine.Engine(cfg, mw, run, rank=rank, world_size=world, process_group=pg)
     NG = args.groups_per_step
     rewards = [TemplateRewards(G, rank * NG + i, args.reward_route) for i in range(NG)]
-    inputs = [synthetic_prompt(cfg, grid_of(args, rank * NG + i), rank * NG + i, 0, dev) for i in range(NG)]
+    inputs = [synthetic_prompt(cfg, grid_of(args, rank * NG + i, world), rank * NG + i, 0, dev) for i in range(NG)]
     ids, frames_host, grid = inputs[0]
     P = len(ids)
     # `value` runs with pixel_values_videos resident in HBM (the processor output, fp32 [N, 1176]); `e2e` starts from the

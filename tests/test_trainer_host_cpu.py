@@ -237,3 +237,36 @@ def test_fix_vit_false_is_an_error_not_a_silent_freeze():
 
     src = inspect.getsource(trainer.TimeR1_Trainer.__init__)
     assert "raise NotImplementedError(\"fix_vit=False" in src and "ViT blocks stay frozen (only merger + LLM train)\")" not in src
+
+
+def test_global_batches_are_dealt_evenly_and_keep_their_content():
+    """dist_utils.balanced_deal in the dataloader: every optimizer step still processes the SAME set of samples the plain strided
+    deal would (exact-math: the DP-averaged gradient does not care which rank ran a sample), but per-rank token counts inside a
+    step are even — the step ends when the slowest rank reaches the reduce-scatter."""
+    from time_r1_b200.dist_utils import balanced_deal
+    from time_r1_b200.trainer import GRPOArguments, TimeR1_Trainer
+
+    world, accum, n = 4, 2, 32
+    rng = np.random.default_rng(0)
+    durs = rng.choice([9.0, 30.0, 147.0, 600.0], n)
+    data = [dict(problem=f"event {i}", video_path=f"/v/{i}.mp4", solution=(1.0, 2.0), durations=float(d)) for i, d in enumerate(durs)]
+    per_rank = {}
+    for balance in (False, True):
+        for r in range(world):
+            args = GRPOArguments(num_generations=2, max_completion_length=4, beta=0.0, gradient_accumulation_steps=accum, fix_vit=True)
+            args.balance_ranks = balance
+            tr = make_trainer(TimeR1_Trainer, args, [])
+            tr.train_dataset, tr.world, tr.rank = data, world, r
+            per_rank[(balance, r)] = [int(mb[0]["problem"].split()[1]) for mb in tr.get_train_dataloader(0)]
+    steps = len(per_rank[(True, 0)]) // accum
+    crit = {False: 0.0, True: 0.0}      # sum over steps of the slowest rank's load = the epoch's critical path
+    ideal = 0.0
+    for s in range(steps):
+        sets = {b: sorted(i for r in range(world) for i in per_rank[(b, r)][s * accum:(s + 1) * accum]) for b in (False, True)}
+        assert sets[False] == sets[True], "balancing must not move a sample to another optimizer step"
+        for b in (False, True):
+            loads = [sum(TimeR1_Trainer._sample_cost(data[i]) for i in per_rank[(b, r)][s * accum:(s + 1) * accum]) for r in range(world)]
+            crit[b] += max(loads)
+        ideal += sum(loads) / world
+    assert crit[True] < 0.93 * crit[False] and crit[True] < 1.2 * ideal, (crit, ideal)
+    assert balanced_deal([5, 1, 1, 5], 2) == [0, 3, 1, 2] and sorted(balanced_deal(list(range(12)), 4)) == list(range(12))

@@ -262,7 +262,38 @@ class TimeR1_Trainer:
         random.Random(seed + epoch).shuffle(idx)
         total = -(-n // self.world) * self.world
         idx = (idx * (total // max(1, n) + 1))[:total] if n else idx
+        if self.world > 1 and getattr(self.args, "balance_ranks", True):
+            # inside every global batch (world x gradient_accumulation_steps samples, the SAME set the plain strided deal would
+            # process in that optimizer step) give each rank an even share of the work: the step ends when the slowest rank
+            # reaches the gradient reduce-scatter, and TimeRFT clips differ 2-3x in tokens.  The DP-averaged gradient does not
+            # depend on which rank ran which sample.
+            from .dist_utils import balanced_deal
+
+            chunk = self.world * max(1, getattr(self.args, "gradient_accumulation_steps", 1))
+            out = []
+            for a in range(0, total, chunk):
+                part = idx[a:a + chunk]
+                order = balanced_deal([self._sample_cost(self.train_dataset[i]) for i in part], self.world)
+                out.extend(part[j] for j in order)
+            idx = out
         return idx[self.rank:total:self.world]
+
+    @staticmethod
+    def _sample_cost(row: dict) -> float:
+        """Relative cost of one prompt-group ~ its prompt tokens: known exactly for pre-processed rows, else from the clip
+        duration the way fetch_video_v3 samples it (2 fps, 4..768 frames, vision_process.py:154-199; the per-frame pixel
+        budget shrinks as frames grow, so tokens saturate around 3584 x 28 x 28 / 784 px)."""
+        if row.get("input_ids") is not None:
+            return float(len(row["input_ids"]))
+        if row.get("video_grid_thw") is not None:
+            g = np.asarray(row["video_grid_thw"]).reshape(-1, 3)
+            return float((g[:, 0] * g[:, 1] * g[:, 2]).sum() // 4)
+        dur = row.get("durations", row.get("duration"))
+        try:
+            frames = min(768.0, max(4.0, 2.0 * float(dur)))
+        except (TypeError, ValueError):
+            return 1.0
+        return min(frames * 144.0, 3584.0 + frames * 7.5) + 120.0
 
     def get_train_dataloader(self, epoch: int = 0) -> list:
         """This rank's micro-batches for one epoch: lists of `per_device_train_batch_size` (=1) examples; the same length
