@@ -136,6 +136,12 @@ int t1_attn_fwd(const void* Q, long long ldq, const void* K, long long ldk, cons
 int t1_attn_fwd_tc(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv, void* O,
                    long long ldo, float* LSE2, long long lse_ld, const int* row_lo, const int* row_hi, int shared_len, int T,
                    int Tk, int Hq, int Hkv, int head_dim, float scale, int q_row0, cudaStream_t stream);
+/* Persistent tcgen05 attention for BLOCK-LOCAL masks: every row's [row_lo, row_hi) lies inside the row's own 128-row tile — the
+ * ViT's 64-token windows (HF modeling_qwen2_5_vl.py:244-261 with cu_window_seqlens; the reference runs them through
+ * flash_attn_varlen_func).  Q, K, V: [T, >= H * head_dim] bf16 views with the same head count, head_dim 80 or 128, no LSE. */
+int t1_attn_fwd_tc_win(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv, void* O,
+                       long long ldo, const int* row_lo, const int* row_hi, int T, int H, int head_dim, float scale,
+                       cudaStream_t stream);
 /* Backward of the above (autograd through flash-attn in the reference).  Workspaces: delta_ws [Hq*T] fp32,
  * summ_ws [4*ceil(T/64)] int32.  head_dim in {64, 128}. */
 int t1_attn_bwd(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv, const void* O,

@@ -822,3 +822,30 @@ def test_adamw_and_sumsq_match_torch():
         opt.step()
         close(master, ref_p.detach(), 1e-7, 1e-5, f"adamw master step {step}")
         assert torch.equal(param, master.to(BF16))
+
+
+@pytest.mark.parametrize("T,H,hd,win", [(1024, 4, 80, 64), (1000, 2, 80, 64), (640, 3, 128, 128), (300, 2, 80, 32), (16384, 16, 80, 64)])
+def test_block_local_tcgen05_attention_matches_the_general_kernels(T, H, hd, win):
+    """t1_attn_fwd_tc_win (persistent tcgen05 kernel for the ViT's windows: every row's keys inside its own 128-row tile) vs the
+    general tcgen05 kernel and an fp32 reference; ragged last window / partial last tile included."""
+    from time_r1_b200 import ops
+
+    qkv = rnd(T, 3 * H * hd, seed=T + hd, scale=0.7)
+    vd = H * hd
+    q, k, v = qkv[:, :vd], qkv[:, vd:2 * vd], qkv[:, 2 * vd:]
+    rows = torch.arange(T, device=DEV)
+    lo = (rows // win * win).int()
+    hi = torch.clamp(lo + win, max=T).int()
+    out = torch.full((T, vd), 9.0, device=DEV, dtype=BF16)
+    ops.attn_fwd_tc_win(q, k, v, lo, hi, H, hd, hd ** -0.5, out=out)
+    gen, _ = ops.attn_fwd_tc(q, k, v, lo, hi, 0, H, H, hd, hd ** -0.5, need_lse=False)
+    torch.cuda.synchronize()
+    close(out, gen, 2e-3, 2.0 ** -7, "win vs general tcgen05")
+    a = max(0, T - 512) // win * win          # reference over the last <= 512 + win rows, starting on a window boundary
+    R = T - a
+    qf, kf, vf = (t[a:].float().view(R, H, hd).transpose(0, 1) for t in (q, k, v))
+    sc = torch.einsum("hid,hjd->hij", qf, kf) * hd ** -0.5
+    jj = torch.arange(a, T, device=DEV)
+    vis = (jj[None, :] >= lo[a:, None]) & (jj[None, :] < hi[a:, None])
+    ref = torch.einsum("hij,hjd->ihd", torch.softmax(sc.masked_fill(~vis[None], float("-inf")), -1), vf).reshape(R, vd)
+    close(out[a:], ref, 4e-3, 2.0 ** -6, "win vs fp32")

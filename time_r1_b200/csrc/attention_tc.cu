@@ -354,6 +354,211 @@ fa_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   }
 }
 
+
+// =====================================================================================================================
+// Persistent variant for BLOCK-LOCAL masks: every 128-row query tile attends only to keys of the SAME 128-row tile (the ViT's
+// 64-token windows, HF Q25:244-261 with cu_window_seqlens; checked on the host from the window plan).  The general kernel
+// above spends one CTA — barrier init, TMEM allocation, three TMA loads, one half-masked tile, epilogue, teardown: ~7.7 us of
+// mostly latency — per (tile, head).  Here a CTA is resident for the whole launch and walks (tile, head) items: Q/K/V of item
+// i+1 and i+2 are in flight (2-stage ring) while S(i+1) = QK^T runs under the softmax of item i, and the normalise-and-store
+// of item i-1 is deferred behind the softmax of item i, so no thread ever waits for the tensor pipe.
+// =====================================================================================================================
+constexpr int WIN_STAGE_BYTES = 3 * TILE_BYTES;                      // Q, K, V of one item
+constexpr int FA_WIN_SMEM = 2 * WIN_STAGE_BYTES + 1024 + 256 + 4 * NS * 128 * 4;
+
+template <int HD>
+__global__ void __launch_bounds__(FA_TC_THREADS, 1)
+fa_fwd_win_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                     const __grid_constant__ CUtensorMap tm_v, bf16* __restrict__ O, long long ldo, const int* __restrict__ row_lo,
+                     const int* __restrict__ row_hi, int T, int H, float scale_log2, uint32_t v_lbo, uint32_t v_sbo) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stg = smem;                                               // [2][Q | K | V]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg + 2 * WIN_STAGE_BYTES);
+  uint64_t* full = bars;           // 2  TMA -> MMA: Q, K, V of the stage landed
+  uint64_t* empty = bars + 2;      // 2  PV of the item retired: the stage may be refilled
+  uint64_t* s_full = bars + 4;     // 2
+  uint64_t* p_full = bars + 6;     // 2  (one arrival per softmax warp)
+  uint64_t* o_full = bars + 8;     // 2  PV retired: O of the item is complete
+  uint64_t* o_free = bars + 10;    // 2  (one arrival per softmax warp) the epilogue has read O
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 12);
+  float* s_xch = reinterpret_cast<float*>(bars + 16);   // [2][NS][128] partial row maxima
+  float* s_lx = s_xch + 2 * NS * 128;                   // [2][NS][128] partial row sums
+
+  const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_qt = (T + TQ - 1) / TQ;
+  const int n_items = n_qt * H;
+  const int first = blockIdx.x, stride = gridDim.x;
+  const int n_mine = first < n_items ? (n_items - first + stride - 1) / stride : 0;
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_k);
+    tma_prefetch_desc(&tm_v);
+  }
+  if (warp_idx == 1 && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4 * NS);
+      mbar_init(&o_full[i], 1);
+      mbar_init(&o_free[i], 4 * NS);
+    }
+    mbar_fence_init();
+  }
+  if (warp_idx == 1) tmem_alloc<512>(tmem_ptr_smem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;      // S[2] at columns 0 / 128, O[2] at 256 / 384
+
+  if (warp_idx == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      for (int it = 0; it < n_mine; ++it) {
+        const int item = first + it * stride, qt = item / H, h = item - qt * H;
+        const int st = it & 1, u = it >> 1;
+        uint8_t* sQ = stg + st * WIN_STAGE_BYTES;
+        mbar_wait(&empty[st], (u & 1) ^ 1);
+        mbar_arrive_expect_tx(&full[st], WIN_STAGE_BYTES);
+        tma_load_2d(sQ, &tm_q, &full[st], h * HD, qt * TQ);
+        tma_load_2d(sQ + ATOM_BYTES, &tm_q, &full[st], h * HD + 64, qt * TQ);
+        tma_load_2d(sQ + TILE_BYTES, &tm_k, &full[st], h * HD, qt * TQ);
+        tma_load_2d(sQ + TILE_BYTES + ATOM_BYTES, &tm_k, &full[st], h * HD + 64, qt * TQ);
+        tma_load_2d(sQ + 2 * TILE_BYTES, &tm_v, &full[st], h * HD, qt * TQ);
+        tma_load_2d(sQ + 2 * TILE_BYTES + ATOM_BYTES, &tm_v, &full[st], h * HD + 64, qt * TQ);
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0 && n_mine > 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(TQ, TK);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(TQ, HD) | (1u << 16);     // B (= V) MN-major
+      auto issue_s = [&](int it) {
+        const int st = it & 1, u = it >> 1;
+        const uint8_t* sQ = stg + st * WIN_STAGE_BYTES;
+        mbar_wait(&full[st], u & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < HD / 16; ++ks) {
+          const uint32_t off = (ks >> 2) * ATOM_BYTES + (ks & 3) * 32;
+          umma_bf16_ss(tmem_base + st * 128, umma_desc_sw128_kmajor(smem_u32(sQ + off)),
+                       umma_desc_sw128_kmajor(smem_u32(sQ + TILE_BYTES + off)), idesc_s, ks != 0 ? 1u : 0u);
+        }
+        umma_commit(&s_full[st]);
+      };
+      issue_s(0);
+      for (int it = 0; it < n_mine; ++it) {
+        if (it + 1 < n_mine) issue_s(it + 1);
+        const int st = it & 1, u = it >> 1;
+        mbar_wait(&p_full[st], u & 1);
+        mbar_wait(&o_free[st], (u & 1) ^ 1);        // the epilogue of item it-2 has read this O buffer
+        tc_fence_after();
+        const uint8_t* sV = stg + st * WIN_STAGE_BYTES + 2 * TILE_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < TK / 16; ++kk) {
+          const uint64_t b_desc = umma_desc_sw128_mnmajor(smem_u32(sV + kk * 16 * 128), v_lbo, v_sbo);
+          umma_bf16_ts(tmem_base + 256 + st * 128, tmem_base + st * 128 + (uint32_t)((kk >> 1) * 32 + (kk & 1) * 8), b_desc, idesc_pv,
+                       kk != 0 ? 1u : 0u);
+        }
+        umma_commit(&o_full[st]);
+        umma_commit(&empty[st]);
+      }
+    }
+  } else {
+    // ===================== softmax warps (NS threads per row) + deferred epilogue =====================
+    const int quad = warp_idx & 3, part = (warp_idx - 2) >> 2;
+    const int r = quad * 32 + lane;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const bool o_on = part * 32 < HD;
+    const int o_w = HD - part * 32 < 32 ? HD - part * 32 : 32;
+    auto epilogue = [&](int j) {
+      const int item = first + j * stride, qt = item / H, h = item - qt * H;
+      const int st = j & 1, u = j >> 1;
+      const int row = qt * TQ + r;
+      float l = 0.f;
+#pragma unroll
+      for (int o = 0; o < NS; ++o) l += s_lx[(st * NS + o) * TQ + r];
+      const float inv = l > 0.f ? 1.f / l : 0.f;
+      mbar_wait(&o_full[st], u & 1);
+      tc_fence_after();
+      if (o_on) {
+        uint32_t ov[32];
+        tmem_ld_32x32b_x32(t_lane + 256 + st * 128 + part * 32, ov);
+        tmem_ld_wait();
+        if (row < T) {
+          bf16* op = O + (long long)row * ldo + (long long)h * HD + part * 32;
+#pragma unroll
+          for (int j8 = 0; j8 < 4; ++j8) {
+            if (j8 * 8 >= o_w) break;
+            uint4 pk;
+            pk.x = pack_bf16x2(__uint_as_float(ov[j8 * 8 + 0]) * inv, __uint_as_float(ov[j8 * 8 + 1]) * inv);
+            pk.y = pack_bf16x2(__uint_as_float(ov[j8 * 8 + 2]) * inv, __uint_as_float(ov[j8 * 8 + 3]) * inv);
+            pk.z = pack_bf16x2(__uint_as_float(ov[j8 * 8 + 4]) * inv, __uint_as_float(ov[j8 * 8 + 5]) * inv);
+            pk.w = pack_bf16x2(__uint_as_float(ov[j8 * 8 + 6]) * inv, __uint_as_float(ov[j8 * 8 + 7]) * inv);
+            *reinterpret_cast<uint4*>(op + j8 * 8) = pk;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_free[st]);
+    };
+    for (int it = 0; it < n_mine; ++it) {
+      const int item = first + it * stride, qt = item / H;
+      const int st = it & 1, u = it >> 1;
+      const int q0 = qt * TQ, row = q0 + r;
+      const bool valid = row < T;
+      const int my_lo = valid ? row_lo[row] : 0, my_hi = valid ? row_hi[row] : 0;
+      mbar_wait(&s_full[st], u & 1);
+      tc_fence_after();
+      uint32_t sv[32];
+      tmem_ld_32x32b_x32(t_lane + st * 128 + part * 32, sv);
+      tmem_ld_wait();
+      float tmax = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int key = q0 + part * 32 + j;
+        const float v = (key >= my_lo && key < my_hi) ? __uint_as_float(sv[j]) : -INFINITY;
+        sv[j] = __float_as_uint(v);
+        tmax = fmaxf(tmax, v);
+      }
+      s_xch[(st * NS + part) * TQ + r] = tmax;
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "n"(32 * NS) : "memory");
+#pragma unroll
+      for (int o = 0; o < NS; ++o) tmax = fmaxf(tmax, s_xch[(st * NS + o) * TQ + r]);
+      const float neg_m = (tmax == -INFINITY) ? 0.f : -tmax * scale_log2;
+      float rs = 0.f;
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float p0 = ex2_approx(fmaf(__uint_as_float(sv[2 * j]), scale_log2, neg_m));
+        const float p1 = ex2_approx(fmaf(__uint_as_float(sv[2 * j + 1]), scale_log2, neg_m));
+        rs += p0 + p1;
+        pk[j] = pack_bf16x2(p0, p1);
+      }
+      tmem_st_32x32b_x16(t_lane + st * 128 + part * 32, pk);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[st]);
+      s_lx[(st * NS + part) * TQ + r] = rs;        // read by epilogue(it), one iteration (and at least one bar.sync) later
+      if (it > 0) epilogue(it - 1);
+    }
+    if (n_mine > 0) {
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "n"(32 * NS) : "memory");
+      epilogue(n_mine - 1);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
 }  // namespace
 
 // Same contract as t1_attn_fwd, head_dim 128 (LLM) or 80 (ViT); additionally only query rows [q_row0, T) are processed and Q / O
@@ -399,5 +604,45 @@ extern "C" int t1_attn_fwd_tc(const void* Q, long long ldq, const void* K, long 
     fa_fwd_tc_kernel<80><<<grid, FA_TC_THREADS, FA_TC_SMEM, stream>>>(tq, tk, tv, (bf16*)O, ldo, LSE2, lse_ld > 0 ? lse_ld : T, row_lo, row_hi,
                                                                      shared_len, T, q_row0, Hq / Hkv, scale * 1.4426950408889634f, lbo, sbo);
   T1_CUDA_LAUNCH_CHECK("t1_attn_fwd_tc");
+  return T1_OK;
+}
+
+// Block-local variant (see fa_fwd_win_tc_kernel): the caller guarantees that every row's [lo, hi) lies inside the row's own
+// 128-row tile (the ViT's 64-token windows; time_r1_b200.indexing.vision_plan checks it).  Q, K, V: [T, >= H * head_dim] views
+// (same head count: no GQA in the ViT), no LSE.  head_dim 80 or 128.
+extern "C" int t1_attn_fwd_tc_win(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv, void* O,
+                                  long long ldo, const int* row_lo, const int* row_hi, int T, int H, int head_dim, float scale,
+                                  cudaStream_t stream) {
+  if (T <= 0) return T1_OK;
+  T1_CHECK_ARG(head_dim == 128 || head_dim == 80, "t1_attn_fwd_tc_win: head_dim must be 128 or 80 (got %d)", head_dim);
+  T1_CHECK_ARG(Q && K && V && O && row_lo && row_hi && H > 0, "t1_attn_fwd_tc_win: null pointer");
+  T1_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0, "t1_attn_fwd_tc_win: strides must be multiples of 8");
+  T1_CHECK_ARG((((uintptr_t)Q | (uintptr_t)K | (uintptr_t)V | (uintptr_t)O) & 15) == 0, "t1_attn_fwd_tc_win: 16-byte alignment required");
+  CUtensorMap tq, tk, tv;
+  int rc = t1_make_tmap_bf16(&tq, Q, T, (long long)H * head_dim, ldq, TQ, 64);
+  if (rc) return rc;
+  rc = t1_make_tmap_bf16(&tk, K, T, (long long)H * head_dim, ldk, TK, 64);
+  if (rc) return rc;
+  rc = t1_make_tmap_bf16(&tv, V, T, (long long)H * head_dim, ldv, TK, 64);
+  if (rc) return rc;
+  static bool set = false;
+  if (!set) {
+    cudaError_t e = cudaFuncSetAttribute(fa_fwd_win_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_WIN_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(fa_fwd_win_tc_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_WIN_SMEM);
+    if (e != cudaSuccess) {
+      t1_set_error("t1_attn_fwd_tc_win: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return T1_ERR_CUDA;
+    }
+    set = true;
+  }
+  const int items = ((T + TQ - 1) / TQ) * H;
+  const int grid = items < t1_num_sms() ? items : t1_num_sms();
+  if (head_dim == 128)
+    fa_fwd_win_tc_kernel<128><<<grid, FA_TC_THREADS, FA_WIN_SMEM, stream>>>(tq, tk, tv, (bf16*)O, ldo, row_lo, row_hi, T, H,
+                                                                          scale * 1.4426950408889634f, ATOM_BYTES, 1024);
+  else
+    fa_fwd_win_tc_kernel<80><<<grid, FA_TC_THREADS, FA_WIN_SMEM, stream>>>(tq, tk, tv, (bf16*)O, ldo, row_lo, row_hi, T, H,
+                                                                         scale * 1.4426950408889634f, ATOM_BYTES, 1024);
+  T1_CUDA_LAUNCH_CHECK("t1_attn_fwd_tc_win");
   return T1_OK;
 }

@@ -315,9 +315,13 @@ class Engine:
             lo, hi = (full_lo, full_hi) if full else (win_lo, win_hi)
             # windowed (64-token) / per-slot full attention, non-causal: tcgen05 kernel for head_dim 80 / 128 (the released
             # ViTs are 80), HMMA kernel for anything else
-            use_tc = tc_ok and (mode == "tc" or (mode == "auto" and full))
-            (ops.attn_fwd_tc if use_tc else ops.attn_fwd)(qkv[:, :vd], qkv[:, vd:2 * vd], qkv[:, 2 * vd:], lo, hi, 0, H, H, hd, scale,
-                                                          out=attn, need_lse=False)
+            if not full and tc_ok and plan.win_tile_local and mode in ("auto", "tc"):
+                # 64-token windows that never straddle a 128-row tile: the persistent block-local tcgen05 kernel
+                ops.attn_fwd_tc_win(qkv[:, :vd], qkv[:, vd:2 * vd], qkv[:, 2 * vd:], lo, hi, H, hd, scale, out=attn)
+            else:
+                use_tc = tc_ok and (mode == "tc" or (mode == "auto" and full))
+                (ops.attn_fwd_tc if use_tc else ops.attn_fwd)(qkv[:, :vd], qkv[:, vd:2 * vd], qkv[:, 2 * vd:], lo, hi, 0, H, H, hd, scale,
+                                                              out=attn, need_lse=False)
             ops.gemm(attn, g(pre + "attn.proj.weight"), out=proj, bias=g(pre + "attn.proj.bias"))
             if cfg.is_q25:
                 ops.rmsnorm(x, g(pre + "norm2.weight"), 1e-6, delta=proj, out=h)

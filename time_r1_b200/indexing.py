@@ -23,6 +23,7 @@ class VisionPlan:
     win_hi: np.ndarray
     full_lo: np.ndarray        # [N] int32 per-row key range for full (per temporal slot) blocks
     full_hi: np.ndarray
+    win_tile_local: bool = False   # every row's window lies inside the row's own 128-row tile (-> t1_attn_fwd_tc_win)
 
 
 def _ranges_from_cu(cu: np.ndarray, n: int):
@@ -73,7 +74,9 @@ def vision_plan(cfg: ModelConfig, grid_thw) -> VisionPlan:
         win_lo, win_hi = _ranges_from_cu(np.asarray(cu_win), n)
     else:
         win_lo, win_hi = full_lo, full_hi
-    return VisionPlan(n, perm, widx, np.ascontiguousarray(pos), win_lo, win_hi, full_lo, full_hi)
+    rows = np.arange(n)
+    local = bool(n > 0 and np.all(win_lo // 128 == rows // 128) and np.all((np.maximum(win_hi, 1) - 1) // 128 == rows // 128))
+    return VisionPlan(n, perm, widx, np.ascontiguousarray(pos), win_lo, win_hi, full_lo, full_hi, local)
 
 
 def mrope_positions(cfg: ModelConfig, input_ids, grid_thw, second_per_grid_ts=None):

@@ -61,6 +61,7 @@ _SIGNATURES: dict[str, list] = {
     # attention.cu
     "t1_attn_fwd": [vp, i64, vp, i64, vp, i64, vp, i64, vp, vp, vp, i32, i32, i32, i32, i32, i32, f32, vp],
     "t1_attn_fwd_tc": [vp, i64, vp, i64, vp, i64, vp, i64, vp, i64, vp, vp, i32, i32, i32, i32, i32, i32, f32, i32, vp],
+    "t1_attn_fwd_tc_win": [vp, i64, vp, i64, vp, i64, vp, i64, vp, vp, i32, i32, i32, f32, vp],
     "t1_decode_attn_cluster": [vp, i64, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, i64, f32, i32, vp],
     "t1_encode_tmap_bf16": [vp, vp, i64, i64, i64, i32, i32],
     "t1_video_patchify": [vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp],

@@ -387,6 +387,16 @@ def attn_fwd_tc(q, k, v, row_lo, row_hi, shared_len, Hq, Hkv, head_dim, scale, o
     return out, lse
 
 
+def attn_fwd_tc_win(q, k, v, row_lo, row_hi, H, head_dim, scale, out=None):
+    """Persistent tcgen05 attention for block-local masks (each row's [lo, hi) inside its own 128-row tile: the ViT's windows)."""
+    T = q.shape[0]
+    if out is None:
+        out = torch.empty((T, H * head_dim), device=q.device, dtype=BF16)
+    call("t1_attn_fwd_tc_win", ptr(q), q.stride(0), ptr(k), k.stride(0), ptr(v), v.stride(0), ptr(out), out.stride(0), ptr(row_lo),
+         ptr(row_hi), T, H, head_dim, float(scale), stream_ptr())
+    return out
+
+
 def attn_bwd(q, k, v, o, do, lse, row_lo, row_hi, shared_len, Hq, Hkv, head_dim, scale, dq, dk, dv):
     T, Tk = q.shape[0], k.shape[0]
     delta = torch.empty((Hq, T), device=q.device, dtype=F32)

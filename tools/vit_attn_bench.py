@@ -68,8 +68,15 @@ for mode, (lo, hi) in ranges.items():
     vis = (jj[None, :] >= lo[:R, None]) & (jj[None, :] < hi[:R, None])
     ref = torch.einsum("hij,hjd->ihd", torch.softmax(sc.masked_fill(~vis[None], float("-inf")), -1), vf).reshape(R, vd)
     err = {"tc": float((out_tc[:R].float() - ref).abs().max()), "hmma": float((out_hm[:R].float() - ref).abs().max())}
-    res = {"tcgen05": timed(lambda: ops.attn_fwd_tc(q, k, v, lo, hi, 0, H, H, hd, scale, out=out_tc, need_lse=False)),
-           "hmma": timed(lambda: ops.attn_fwd(q, k, v, lo, hi, 0, H, H, hd, scale, out=out_hm, need_lse=False))}
+    res = {}
+    if mode == "window64":
+        out_w = torch.zeros_like(out_tc)
+        ops.attn_fwd_tc_win(q, k, v, lo, hi, H, hd, scale, out=out_w)
+        err["tc_win"] = float((out_w[:R].float() - ref).abs().max())
+        err["tc_win_vs_hmma_all_rows"] = float((out_w.float() - out_hm.float()).abs().max())
+        res["tcgen05_win (persistent, block-local)"] = timed(lambda: ops.attn_fwd_tc_win(q, k, v, lo, hi, H, hd, scale, out=out_w))
+    res.update({"tcgen05": timed(lambda: ops.attn_fwd_tc(q, k, v, lo, hi, 0, H, H, hd, scale, out=out_tc, need_lse=False)),
+           "hmma": timed(lambda: ops.attn_fwd(q, k, v, lo, hi, 0, H, H, hd, scale, out=out_hm, need_lse=False))})
     if flash_attn_varlen_func is not None:
         cu = cu_of(lo, hi)
         mx = int((cu[1:] - cu[:-1]).max())
