@@ -174,8 +174,12 @@ fa_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 12);
 
   const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int jt = blockIdx.x, j0 = jt * BT, j1 = j0 + BT;
-  const int h = blockIdx.y, hk = h / group;
+  // CTAs are dispatched x-fastest: walk (key tile, head) with the HEAD fastest so that the heavy tiles (low key index: seen by
+  // every later row) of ALL heads start first and the light ones fill the tail (was: per head, so the last heads' heavy
+  // tiles started in the last wave: ncu elapsed / active IPC 0.81); the q heads of a KV group also run side by side
+  const int lin = (int)(blockIdx.x + gridDim.x * blockIdx.y), Hq_ = (int)gridDim.y;
+  const int jt = lin / Hq_, j0 = jt * BT, j1 = j0 + BT;
+  const int h = lin - jt * Hq_, hk = h / group;
   const int nqt = (T + BT - 1) / BT;
 
   if (warp_idx == 0 && lane == 0) {
@@ -443,9 +447,11 @@ fa_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   int* s_red = reinterpret_cast<int*>(v_full + 10);   // 4 ints
 
   const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qt = (int)gridDim.x - 1 - (int)blockIdx.x;      // long rows (most visible keys) first
+  // long rows (most visible keys) first, ACROSS heads: (query tile, head) with the head fastest (see fa_bwd_dkv_tc_kernel)
+  const int lin = (int)(blockIdx.x + gridDim.x * blockIdx.y), Hq_ = (int)gridDim.y;
+  const int qt = (int)gridDim.x - 1 - lin / Hq_;
   const int q0 = qt * BT;
-  const int h = blockIdx.y, hk = h / group;
+  const int h = lin % Hq_, hk = h / group;
 
   if (threadIdx.x == 0) { s_red[0] = INT_MAX; s_red[1] = INT_MIN; s_red[2] = INT_MAX; s_red[3] = INT_MIN; }
   if (warp_idx == 0 && lane == 0) {
