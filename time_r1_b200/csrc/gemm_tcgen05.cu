@@ -469,7 +469,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 //                       leader's barrier (mbarrier.arrive.shared::cluster)
 // =====================================================================================================================
 constexpr int STAGES2 = 6;
-constexpr int B2_BYTES = 128 * BK * 2;                       // this CTA's half of the B tile
+constexpr int B2_BYTES = 128 * BK * 2;                       // this CTA's half of the widest (256-column) B tile
 constexpr int STAGE2_BYTES = A_BYTES + B2_BYTES;             // 32 KB
 constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + EPI_STAGE_BYTES + 1024 + 256;
 static_assert(SMEM2_BYTES <= 227 * 1024, "shared memory budget (2-CTA kernel)");
@@ -518,12 +518,16 @@ __device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
 }
 
-template <bool A_MN, bool B_MN>
+// BN = output-tile width in {256, 192, 128}: narrower tiles quantise better when N / 256 leaves a thin last wave (N = 3584 is
+// 14 tiles of 256 but 18.7 of 192); each CTA then loads BN / 2 rows of B per k-block.  SwiGLU pairs 128 + 128 columns: BN = 256.
+template <bool A_MN, bool B_MN, int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                      const __grid_constant__ CUtensorMap tma_d, const __grid_constant__ CUtensorMap tma_d2g,
                      const __grid_constant__ CUtensorMap tma_d2u, int M, int N, int K, int group_m, EpiParams epi) {
-  constexpr int BN = 256;
+  static_assert(BN % 64 == 0 && BN <= 256 && (!B_MN || (BN / 2) % 64 == 0), "2-CTA tile width");
+  constexpr int HB = BN / 2;                                  // B rows this CTA loads per k-block
+  constexpr int STAGE_TX = A_BYTES + HB * BK * 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_tiles = smem;
@@ -587,10 +591,10 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
         tile_coords(tile, m_blk, n_blk);
         const int m0 = m_blk * 2 * BM + (int)rank * BM;                              // this CTA's 128 A rows
         // this CTA's half of the B tile: plain = rows n_blk*256 + rank*128; SwiGLU = rank 0 the gate rows, rank 1 the up rows
-        const int n0 = swiglu ? (int)rank * N + n_blk * BNO : n_blk * BN + (int)rank * 128;
+        const int n0 = swiglu ? (int)rank * N + n_blk * BNO : n_blk * BN + (int)rank * HB;
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE2_BYTES);    // both CTAs' bytes land on this barrier
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_TX);    // both CTAs' bytes land on this barrier
           if constexpr (A_MN) {
 #pragma unroll
             for (int a = 0; a < BM / 64; ++a)
@@ -600,7 +604,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
           }
           if constexpr (B_MN) {
 #pragma unroll
-            for (int b = 0; b < 2; ++b)
+            for (int b = 0; b < HB / 64; ++b)
               tma_load_2d_2sm(b_tiles + stage * B2_BYTES + b * MN_ATOM_BYTES, &tma_b, &full_bar[stage], n0 + b * 64, kb * BK);
           } else {
             tma_load_2d_2sm(b_tiles + stage * B2_BYTES, &tma_b, &full_bar[stage], kb * BK, n0);
@@ -762,20 +766,39 @@ static int gemm_impl(const void* A, long long lda, const void* B, long long ldb,
     static const char* env2 = getenv("T1_GEMM_2CTA");
     const bool want2 = !(env2 && env2[0] == '0') && BN == 256 && M > BM && (!a_mn || M % 64 == 0) && (!b_mn || N % 64 == 0);
     if (want2) {
-      CUtensorMap tb2;
-      rc = b_mn ? t1_make_tmap_bf16(&tb2, B, K, N, ldb, BK, 64)
-                : (swiglu ? t1_make_tmap_bf16(&tb2, B, 2LL * N, K, ldb, 128, BK) : t1_make_tmap_bf16(&tb2, B, N, K, ldb, 128, BK));
-      if (rc) return rc;
       const int num_m2 = (M + 2 * BM - 1) / (2 * BM);
-      const int tiles2 = num_m2 * num_n;
-      int clusters = tiles2 < sms / 2 ? tiles2 : sms / 2;
+      int max_clusters = sms / 2;
       if (g_gemm_max_ctas > 0) {
         // SMs are reserved for a concurrent stream (NCCL): each of them may break a different SM pair, and a cluster that finds
         // no free pair would only start when another one retires — i.e. after the whole persistent loop
         int free_pairs = sms / 2 - (sms - g_gemm_max_ctas);
         if (free_pairs < 1) free_pairs = 1;
-        if (free_pairs < clusters) clusters = free_pairs;
+        if (free_pairs < max_clusters) max_clusters = free_pairs;
       }
+      // tile width: the persistent loop runs ceil(tiles / clusters) waves of ~(BN + overhead) each; take the cheapest — but only
+      // for short problems (few rows: the completion-row scoring pass; or short K: the ViT).  Measured on B200
+      // (profiles/r02_gemm2_tile_width.txt): 1672 x 3584 x 3584 0.060 -> 0.048 ms, 16384 x 3840 x 1280 0.132 -> 0.110 ms, but
+      // 4216 x 3584 x 18944 0.536 -> 0.611 ms and the whole step 1407 -> 1441 ms when every shape may narrow (more A re-reads)
+      int bn2 = 256;
+      if (!swiglu && (M <= 2048 || K <= 2048)) {
+        static const char* envbn = getenv("T1_GEMM2_BN");
+        double best = 1e30;
+        for (int cand : {256, 192, 128}) {
+          if (b_mn && (cand / 2) % 64) continue;
+          if (envbn && atoi(envbn) != cand) continue;
+          const long long tiles = (long long)num_m2 * ((N + cand - 1) / cand);
+          const double cost = (double)((tiles + max_clusters - 1) / max_clusters) * (cand + 24);
+          if (cost < best - 1e-9) best = cost, bn2 = cand;
+        }
+      }
+      const int BNO2 = swiglu ? 128 : bn2;
+      const int num_n2 = (N + BNO2 - 1) / BNO2;
+      CUtensorMap tb2;
+      rc = b_mn ? t1_make_tmap_bf16(&tb2, B, K, N, ldb, BK, 64)
+                : (swiglu ? t1_make_tmap_bf16(&tb2, B, 2LL * N, K, ldb, 128, BK) : t1_make_tmap_bf16(&tb2, B, N, K, ldb, bn2 / 2, BK));
+      if (rc) return rc;
+      const long long tiles2 = (long long)num_m2 * num_n2;
+      const int clusters = tiles2 < max_clusters ? (int)tiles2 : max_clusters;
       int group_m2 = (group_m + 1) / 2;
       if (group_m2 > num_m2) group_m2 = num_m2;
       if (group_m2 < 1) group_m2 = 1;
@@ -791,19 +814,27 @@ static int gemm_impl(const void* A, long long lda, const void* B, long long ldb,
       attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr;
       cfg.numAttrs = 1;
-#define T1_GEMM2_LAUNCH(AMN, BMN)                                                                                          \
-  do {                                                                                                                     \
-    static bool attr_set2 = false;                                                                                         \
-    if (!attr_set2) {                                                                                                      \
-      le = cudaFuncSetAttribute(gemm2_bf16_tn_kernel<AMN, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES); \
-      attr_set2 = (le == cudaSuccess);                                                                                     \
-    }                                                                                                                      \
-    if (le == cudaSuccess) le = cudaLaunchKernelEx(&cfg, gemm2_bf16_tn_kernel<AMN, BMN>, ta, tb2, td, tdg, tdu, M, N, K, group_m2, epi); \
+#define T1_GEMM2_LAUNCH(AMN, BMN, BNV)                                                                                          \
+  do {                                                                                                                          \
+    static bool attr_set2 = false;                                                                                              \
+    if (!attr_set2) {                                                                                                           \
+      le = cudaFuncSetAttribute(gemm2_bf16_tn_kernel<AMN, BMN, BNV>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES); \
+      attr_set2 = (le == cudaSuccess);                                                                                          \
+    }                                                                                                                           \
+    if (le == cudaSuccess)                                                                                                      \
+      le = cudaLaunchKernelEx(&cfg, gemm2_bf16_tn_kernel<AMN, BMN, BNV>, ta, tb2, td, tdg, tdu, M, N, K, group_m2, epi);          \
   } while (0)
-      if (a_mn && b_mn) T1_GEMM2_LAUNCH(true, true);
-      else if (a_mn) T1_GEMM2_LAUNCH(true, false);
-      else if (b_mn) T1_GEMM2_LAUNCH(false, true);
-      else T1_GEMM2_LAUNCH(false, false);
+#define T1_GEMM2_BY_BN(AMN, BMN)                         \
+  do {                                                   \
+    if (bn2 == 256) T1_GEMM2_LAUNCH(AMN, BMN, 256);      \
+    else if (bn2 == 128) T1_GEMM2_LAUNCH(AMN, BMN, 128); \
+    else T1_GEMM2_LAUNCH(AMN, false, 192);               \
+  } while (0)
+      if (a_mn && b_mn) T1_GEMM2_BY_BN(true, true);
+      else if (a_mn) T1_GEMM2_BY_BN(true, false);
+      else if (b_mn) T1_GEMM2_BY_BN(false, true);
+      else T1_GEMM2_BY_BN(false, false);
+#undef T1_GEMM2_BY_BN
 #undef T1_GEMM2_LAUNCH
       if (le != cudaSuccess) {
         t1_set_error("t1_gemm_bf16_tn (2-CTA): launch failed: %s", cudaGetErrorString(le));

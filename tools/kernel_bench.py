@@ -30,7 +30,7 @@ def timeit(fn, iters=10, warmup=3, flush=None):
 def bench_gemm():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     shapes = [(5836, 4608, 3584), (5836, 3584, 3584), (5836, 37888, 3584), (5836, 3584, 18944), (1600, 152064, 3584),
-              (16384, 1280, 1176), (16384, 3840, 1280), (16384, 6912, 1280), (8192, 8192, 8192), (37888, 3584, 5840)]
+              (1672, 3584, 3584), (1672, 3584, 18944), (1672, 4608, 3584), (4216, 3584, 18944), (16384, 1280, 1176), (16384, 3840, 1280), (16384, 6912, 1280), (8192, 8192, 8192), (37888, 3584, 5840)]
     for M, N, K in shapes:
         a = torch.randn(M, K, device="cuda").to(torch.bfloat16)
         b = torch.randn(N, K, device="cuda").to(torch.bfloat16)
