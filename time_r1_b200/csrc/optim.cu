@@ -3,6 +3,7 @@
 // accelerator.backward (HF trainer.py:2493,1760; scripts/zero3_offload.json:24-31).  HBM-bound: 16 B read + 14 B
 // written per parameter (fp32 master/m/v + bf16 grad in; fp32 master/m/v + bf16 param out).
 #include "t1_common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -30,7 +31,14 @@ sumsq_bf16_kernel(const bf16* __restrict__ g, long long n, float* __restrict__ o
 
 // torch.optim.AdamW semantics (decoupled weight decay, bias correction), gradient pre-scaled by
 // grad_scale * clip where clip = min(1, max_norm / (sqrt(*gnorm_sq * grad_scale^2) + 1e-6)) as in clip_grad_norm_.
-__global__ void __launch_bounds__(256)
+// 128-thread CTAs, 92 registers, four independent chunks per thread per trip with every load issued before the first use.
+// Built to test whether AdamW can run UNDER the next step's frozen ViT blocks (side stream): one such CTA fits in the registers
+// a persistent tcgen05 GEMM CTA leaves free on an SM.  Measured (profiles/r02_adamw_coresident.txt): a single CTA per SM only
+// sustains 2.0 TB/s (116 ms for the 7B shard; 2 per SM 3.7 TB/s, 4 per SM 5.9 TB/s = the HBM floor, 39 ms), so capping the
+// grid at one CTA per SM made the step SLOWER (1407 -> 1419..1430 ms).  Default: 4 CTAs per SM, same speed as the previous
+// 256-thread kernel; T1_ADAMW_CTAS_PER_SM overrides.
+constexpr int ADAMW_UNROLL = 4;
+__global__ void __launch_bounds__(128, 5)
 adamw_kernel(float* __restrict__ master, float* __restrict__ m, float* __restrict__ v, const bf16* __restrict__ grad,
              bf16* __restrict__ param, long long n, float lr, float beta1, float beta2, float eps, float wd, float bc1,
              float bc2, const float* __restrict__ gnorm_sq, float max_norm, float grad_scale) {
@@ -41,30 +49,47 @@ adamw_kernel(float* __restrict__ master, float* __restrict__ m, float* __restric
   }
   const float step_size = lr / bc1;
   const float inv_sqrt_bc2 = rsqrtf(bc2);
+  const float decay = 1.0f - lr * wd;
   const long long n4 = n >> 2;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    float4 p = reinterpret_cast<float4*>(master)[i];
-    float4 mm = reinterpret_cast<float4*>(m)[i];
-    float4 vv = reinterpret_cast<float4*>(v)[i];
-    const uint2 gu = __ldg(reinterpret_cast<const uint2*>(grad) + i);
-    const float2 g01 = unpack_bf16x2(gu.x), g23 = unpack_bf16x2(gu.y);
-    float pa[4] = {p.x, p.y, p.z, p.w}, ma[4] = {mm.x, mm.y, mm.z, mm.w}, va[4] = {vv.x, vv.y, vv.z, vv.w};
-    const float ga[4] = {g01.x * gs, g01.y * gs, g23.x * gs, g23.y * gs};
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += stride * ADAMW_UNROLL) {
+    float4 p[ADAMW_UNROLL], mm[ADAMW_UNROLL], vv[ADAMW_UNROLL];
+    uint2 gu[ADAMW_UNROLL];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      pa[j] *= 1.0f - lr * wd;
-      ma[j] = beta1 * ma[j] + (1.0f - beta1) * ga[j];
-      va[j] = beta2 * va[j] + (1.0f - beta2) * ga[j] * ga[j];
-      const float denom = sqrtf(va[j]) * inv_sqrt_bc2 + eps;
-      pa[j] -= step_size * (ma[j] / denom);
+    for (int u = 0; u < ADAMW_UNROLL; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < n4) {
+        p[u] = reinterpret_cast<const float4*>(master)[i];
+        mm[u] = reinterpret_cast<const float4*>(m)[i];
+        vv[u] = reinterpret_cast<const float4*>(v)[i];
+        gu[u] = __ldg(reinterpret_cast<const uint2*>(grad) + i);
+      }
     }
-    reinterpret_cast<float4*>(master)[i] = make_float4(pa[0], pa[1], pa[2], pa[3]);
-    reinterpret_cast<float4*>(m)[i] = make_float4(ma[0], ma[1], ma[2], ma[3]);
-    reinterpret_cast<float4*>(v)[i] = make_float4(va[0], va[1], va[2], va[3]);
-    uint2 o;
-    o.x = pack_bf16x2(pa[0], pa[1]);
-    o.y = pack_bf16x2(pa[2], pa[3]);
-    reinterpret_cast<uint2*>(param)[i] = o;
+#pragma unroll
+    for (int u = 0; u < ADAMW_UNROLL; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < n4) {
+        const float2 g01 = unpack_bf16x2(gu[u].x), g23 = unpack_bf16x2(gu[u].y);
+        float pa[4] = {p[u].x, p[u].y, p[u].z, p[u].w}, ma[4] = {mm[u].x, mm[u].y, mm[u].z, mm[u].w};
+        float va[4] = {vv[u].x, vv[u].y, vv[u].z, vv[u].w};
+        const float ga[4] = {g01.x * gs, g01.y * gs, g23.x * gs, g23.y * gs};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          pa[j] *= decay;
+          ma[j] = beta1 * ma[j] + (1.0f - beta1) * ga[j];
+          va[j] = beta2 * va[j] + (1.0f - beta2) * ga[j] * ga[j];
+          const float denom = sqrtf(va[j]) * inv_sqrt_bc2 + eps;
+          pa[j] -= step_size * (ma[j] / denom);
+        }
+        reinterpret_cast<float4*>(master)[i] = make_float4(pa[0], pa[1], pa[2], pa[3]);
+        reinterpret_cast<float4*>(m)[i] = make_float4(ma[0], ma[1], ma[2], ma[3]);
+        reinterpret_cast<float4*>(v)[i] = make_float4(va[0], va[1], va[2], va[3]);
+        uint2 o;
+        o.x = pack_bf16x2(pa[0], pa[1]);
+        o.y = pack_bf16x2(pa[2], pa[3]);
+        reinterpret_cast<uint2*>(param)[i] = o;
+      }
+    }
   }
 }
 
@@ -92,9 +117,11 @@ extern "C" int t1_adamw(float* master, float* m, float* v, const void* grad, voi
   T1_CHECK_ARG(n % 4 == 0, "t1_adamw: n must be a multiple of 4 (pad the flat shard)");
   T1_CHECK_ARG(step >= 1 && master && m && v && grad && param, "t1_adamw: bad arguments");
   const float bc1 = 1.0f - powf(beta1, (float)step), bc2 = 1.0f - powf(beta2, (float)step);
-  const long long want = (n / 4 + 255) / 256;
-  const int grid = (int)(want < 16LL * t1_num_sms() ? want : 16LL * t1_num_sms());
-  adamw_kernel<<<grid, 256, 0, stream>>>(master, m, v, (const bf16*)grad, (bf16*)param, n, lr, beta1, beta2, eps, wd, bc1,
+  const long long want = (n / 4 + 128 * ADAMW_UNROLL - 1) / (128 * ADAMW_UNROLL);
+  static const char* env = getenv("T1_ADAMW_CTAS_PER_SM");
+  const long long per_sm = env && atoi(env) > 0 ? atoi(env) : 4;
+  const int grid = (int)(want < per_sm * t1_num_sms() ? (want > 0 ? want : 1) : per_sm * t1_num_sms());
+  adamw_kernel<<<grid, 128, 0, stream>>>(master, m, v, (const bf16*)grad, (bf16*)param, n, lr, beta1, beta2, eps, wd, bc1,
                                          bc2, gnorm_sq, max_norm, grad_scale);
   T1_CUDA_LAUNCH_CHECK("t1_adamw");
   return T1_OK;
