@@ -428,13 +428,22 @@ def attention_microbench(eng, Ps, G: int, C: int):
     n = len(Ps)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=eng.dev)
     Hq, Hkv, hd = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim
+    common = (ptr(st["qkv"]), st["qkv"].stride(0), ptr(st["group_table"][0]), st["kv_maps"][0].ctypes.data, n, G, Hq, Hkv, hd,
+              st["cpad"], ptr(st["step"]), ptr(st["attn"]), st["attn"].stride(0), hd ** -0.5)
+    wide = "attn_ws" in st
+
+    def launch():
+        if wide:
+            call("t1_decode_attn_wide", *common, st["attn_splits"], ptr(st["attn_ws"]), st["attn_ws"].numel(), stream_ptr())
+        else:
+            call("t1_decode_attn_cluster", *common, 0, stream_ptr())
+
     ts = []
     for i in range(13):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        call("t1_decode_attn_cluster", ptr(st["qkv"]), st["qkv"].stride(0), ptr(st["group_table"][0]), st["kv_maps"][0].ctypes.data,
-             n, G, Hq, Hkv, hd, st["cpad"], ptr(st["step"]), ptr(st["attn"]), st["attn"].stride(0), hd ** -0.5, 0, stream_ptr())
+        launch()
         e1.record()
         torch.cuda.synchronize()
         if i >= 3:
@@ -442,8 +451,10 @@ def attention_microbench(eng, Ps, G: int, C: int):
     ts.sort()
     ms = ts[len(ts) // 2]
     kv_bytes = sum(2.0 * Hkv * hd * 2 * (P + G * (step + 1)) for P in Ps) + 2.0 * n * G * Hq * hd * 2
-    return {"kernel": "decode_attn_tc (1 launch, all groups, cluster merge)", "groups": n, "unique_kv_bytes": kv_bytes,
-            "ms": round(ms, 5), "gbs": round(kv_bytes / ms / 1e6, 1)}
+    ctas = (st["attn_splits"] if wide else 8) * Hkv * n
+    return {"kernel": "decode_attn_tc (1 launch, all groups, %s)" % ("wide form: %d CTAs, L2 workspace merge" % ctas if wide
+                                                                      else "cluster form: %d CTAs, DSMEM merge" % ctas),
+            "groups": n, "ctas": ctas, "unique_kv_bytes": kv_bytes, "ms": round(ms, 5), "gbs": round(kv_bytes / ms / 1e6, 1)}
 
 
 def decode_step_microbench(eng, Ps, G: int, C: int):

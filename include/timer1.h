@@ -109,6 +109,13 @@ int t1_stream_gemm_swiglu(const void* x, long long ldx, const void* W, long long
                           cudaStream_t stream);
 /* Tuning: shared-memory ring depth (0 = default, ~108 KB per CTA) and CTAs per SM (1 or 2) of later launches. */
 void t1_stream_gemm_tune(int stages, int ctas_per_sm);
+/* One-shot performance hint for the NEXT t1_stream_gemm* launch (static split): while it waits for its dependency its idle
+ * warps prefetch into L2 up to max_bytes of W_next [N, K] -- the units the launch AFTER it (described by M, N, K, swiglu
+ * layout, fold_producer = t1_stream_gemm_fold) reads first after filling its shared-memory ring -- so the HBM keeps
+ * streaming weights through the latency-bound qkv -> attention -> o part of a decode layer (HF GenerationMixin._sample's
+ * per-token nn.Linear chain, timer1_trainer.py:568-573).  Results never depend on it; max_bytes <= 0 clears the hint. */
+int t1_stream_gemm_prefetch_next(const void* W_next, long long ldw, int M, int N, int K, int swiglu, int fold_producer,
+                                 long long max_bytes);
 /* Diagnostics: CTA 0 of launch i writes 4 %globaltimer stamps {start, weight prefetch issued, dependency resolved,
  * done} to buf[4*(i % slots)] (device memory, uint64); buf = NULL switches it off. */
 void t1_stream_gemm_debug(void* buf, int slots);
@@ -202,6 +209,19 @@ int t1_encode_tmap_bf16(void* out_128_bytes_host, const void* ptr, long long row
 int t1_decode_attn_cluster(const void* q, long long ldq, const void* groups, const void* maps, int n_groups, int G,
                            int Hq, int Hkv, int head_dim, int cpad, const int* step_ptr, void* out, long long ldo,
                            float scale, int cluster_size, cudaStream_t stream);
+/* The same CTA program WITHOUT clusters, sized to fill the machine: `splits` plain CTAs per (group, KV head) (the plan
+ * picks floor(SMs / (n_groups * Hkv)) <= 48: 18 at cfg2 = 144 of 148 SMs, where the 8-CTA clusters use 64), one even
+ * deal of [prefix units | completion units]; the (m, l, O) partials go through an L2-resident workspace, each CTA
+ * arrives on a per-(group, head) counter, spins until its peers have arrived and merges the rows it owns -- still one
+ * launch, no combine kernel, deterministic.  Replaces the same reference call site as t1_decode_attn_cluster (HF
+ * GenerationMixin._sample's per-token attention, src/time_r1/rl/timer1_trainer.py:568-573).
+ * t1_decode_attn_wide_plan: requested = 0 picks splits for the current device; *ws_bytes = workspace size.  The caller
+ * allocates ws (256-byte aligned) and ZEROES it once; every launch leaves the counters zero again.  All CTAs of the
+ * launch must be co-resident (checked: splits * Hkv * n_groups <= SM count). */
+int t1_decode_attn_wide_plan(int n_groups, int Hkv, int requested, int* splits, long long* ws_bytes);
+int t1_decode_attn_wide(const void* q, long long ldq, const void* groups, const void* maps, int n_groups, int G, int Hq,
+                        int Hkv, int head_dim, int cpad, const int* step_ptr, void* out, long long ldo, float scale,
+                        int splits, void* ws, long long ws_bytes, cudaStream_t stream);
 /* temperature -> top-k -> softmax -> multinomial (Philox4x32-10 keyed by seed, counter (row, step)); temperature <= 0
  * is greedy arg-max.  HF 4.51.1 generate defaults.  logits [B, V] fp32 (ld may be 0: shared row);
  * seed_ptr (device, nullable) overrides seed so captured graphs stay seed-independent; writes

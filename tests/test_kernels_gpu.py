@@ -529,13 +529,29 @@ def test_decode_groups_match_single_group_kernels():
 
 
 
+DECODE_ATTN_SHAPES = [(4, 14, 2, [300, 77, 513], 9, 128), (8, 28, 4, [1000, 4216], 130, 256), (8, 28, 4, [517], 63, 256),
+                      (8, 28, 4, [64, 40], 64, 128), (3, 2, 1, [5], 0, 64)]
+
+
 @pytest.mark.parametrize("cluster", [1, 2, 8])
-@pytest.mark.parametrize("G,Hq,Hkv,Ps,step,cpad", [(4, 14, 2, [300, 77, 513], 9, 128), (8, 28, 4, [1000, 4216], 130, 256),
-                                                   (8, 28, 4, [517], 63, 256), (8, 28, 4, [64, 40], 64, 128), (3, 2, 1, [5], 0, 64)])
+@pytest.mark.parametrize("G,Hq,Hkv,Ps,step,cpad", DECODE_ATTN_SHAPES)
 def test_decode_attention_cluster(G, Hq, Hkv, Ps, step, cpad, cluster):
     """Single-launch tcgen05 cluster decode attention (TMA units, DSMEM merge, fused rope + KV append) vs the dense
     fp32 reference over [prompt prefix | own completion slots]; the appended K/V rows are bit-identical to
     t1_decode_rope_append."""
+    _check_decode_attention_tc(G, Hq, Hkv, Ps, step, cpad, ("cluster", cluster))
+
+
+@pytest.mark.parametrize("splits", [0, 1, 3, 11])
+@pytest.mark.parametrize("G,Hq,Hkv,Ps,step,cpad", DECODE_ATTN_SHAPES + [(8, 28, 4, [4216, 4216], 199, 256), (8, 28, 4, [700] * 8, 31, 128)])
+def test_decode_attention_wide(G, Hq, Hkv, Ps, step, cpad, splits):
+    """The same CTA program without clusters on every SM (t1_decode_attn_wide: partials through an L2 workspace behind a
+    device-side arrival counter): same reference, same bit-identical K/V append, and the counters come back to zero so
+    that the launch can be repeated (a third launch checks it).  splits = 0 is the plan's machine-filling choice."""
+    _check_decode_attention_tc(G, Hq, Hkv, Ps, step, cpad, ("wide", splits))
+
+
+def _check_decode_attention_tc(G, Hq, Hkv, Ps, step, cpad, how):
     import numpy as np
     from time_r1_b200 import ops
     from time_r1_b200.lib import call, ptr, stream_ptr
@@ -563,8 +579,20 @@ def test_decode_attention_cluster(G, Hq, Hkv, Ps, step, cpad, cluster):
         call("t1_decode_rope_append", ptr(ref_qkv[gi * G:(gi + 1) * G]), ld, G, Hq, Hkv, hd, ptr(groups[gi]["cos"]),
              ptr(groups[gi]["sin"]), ptr(st), ptr(refK[gi]), ptr(refV[gi]), P, cpad, stream_ptr())
     out = torch.full((n * G, Hq * hd), float("nan"), device=DEV, dtype=BF16)
-    call("t1_decode_attn_cluster", ptr(raw), ld, ptr(tab), maps.ctypes.data, n, G, Hq, Hkv, hd, cpad, ptr(st), ptr(out), out.stride(0),
-         scale, cluster, stream_ptr())
+    if how[0] == "wide":
+        if how[1] * Hkv * n > torch.cuda.get_device_properties(0).multi_processor_count or (G + max(how[1], 1) - 1) // max(how[1], 1) > 8:
+            pytest.skip("this split count does not fit the device / the per-CTA sequence ownership")
+        splits, ws = ops.decode_attn_wide_workspace(n, Hkv, DEV, how[1])
+        assert splits == how[1] or how[1] == 0
+
+        def launch(o):
+            call("t1_decode_attn_wide", ptr(raw), ld, ptr(tab), maps.ctypes.data, n, G, Hq, Hkv, hd, cpad, ptr(st), ptr(o),
+                 o.stride(0), scale, splits, ptr(ws), ws.numel(), stream_ptr())
+    else:
+        def launch(o):
+            call("t1_decode_attn_cluster", ptr(raw), ld, ptr(tab), maps.ctypes.data, n, G, Hq, Hkv, hd, cpad, ptr(st), ptr(o),
+                 o.stride(0), scale, how[1], stream_ptr())
+    launch(out)
     torch.cuda.synchronize()
     for gi, P in enumerate(Ps):
         assert torch.equal(groups[gi]["K"], refK[gi]) and torch.equal(groups[gi]["V"], refV[gi])
@@ -578,9 +606,13 @@ def test_decode_attention_cluster(G, Hq, Hkv, Ps, step, cpad, cluster):
             close(out[gi * G + b], ref, 2e-2, 2e-2, f"cluster decode attn group {gi} seq {b}")
     # deterministic: a second launch on the same inputs (cache already holds this step's row) gives the same bits
     out2 = torch.empty_like(out)
-    call("t1_decode_attn_cluster", ptr(raw), ld, ptr(tab), maps.ctypes.data, n, G, Hq, Hkv, hd, cpad, ptr(st), ptr(out2), out.stride(0),
-         scale, cluster, stream_ptr())
+    launch(out2)
     assert torch.equal(out, out2)
+    if how[0] == "wide":
+        out3 = torch.empty_like(out)
+        launch(out3)
+        assert torch.equal(out, out3)
+        assert int(ws[:256 + n * Hkv * 32].view(torch.int32).abs().sum()) == 0, "arrival counters must be left zeroed"
 
 
 @pytest.mark.parametrize("B,Hq,Hkv,P,step,cpad", [(8, 28, 4, 1000, 0, 256), (8, 28, 4, 517, 130, 256), (4, 12, 2, 250, 37, 128), (3, 2, 1, 64, 5, 128), (20, 28, 4, 300, 17, 128)])

@@ -6,6 +6,7 @@ both are first-class here.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import asdict, dataclass, field, replace
 
 
@@ -168,8 +169,10 @@ class RunConfig:
     decode_impl: str = "stream"
     decode_pdl: bool = True
     # decode attention inside the "stream" step: "cluster" = one launch, split-KV partials merged through distributed
-    # shared memory; "split" = split-KV kernel + combine kernel through a global workspace
-    decode_attn: str = "cluster"
+    # shared memory (64 CTAs at cfg2); "wide" = the same CTA program without clusters on every SM (144 CTAs at cfg2), partials
+    # merged through an L2-resident workspace behind a device-side arrival counter; "split" = split-KV kernel + combine
+    # kernel through a global workspace (HMMA, round 1)
+    decode_attn: str = os.environ.get("T1_DECODE_ATTN", "cluster")
     # fuse the residual add + RMSNorm that follows the o / down projection into that stream GEMM (5 kernels per layer
     # instead of 7).  Measured neutral on B200 (3.53 vs 3.49 ms per step): what looked like kernel-boundary latency is
     # the finishing-time spread of the 148 streaming CTAs, which the fused tail has to wait out as well.
@@ -180,6 +183,10 @@ class RunConfig:
     # 147 instead of 202 kernels per decode step, 3.35 -> 3.23 ms per step on B200 (unlike the fused tail above, nothing
     # waits out the CTA finishing spread twice).  Same math as HF up to where the bf16 roundings fall.
     decode_fold_norm: bool = True
+    # MB of each layer's gate_up weights pulled into L2 (t1_stream_gemm_prefetch_next) by the idle warps of the qkv ("qkv")
+    # or o_proj ("o") GEMM of the same layer while the chain is latency-bound (qkv -> attention -> o); 0 = off
+    decode_prefetch_mb: int = int(os.environ.get("T1_DECODE_PF_MB", "0"))
+    decode_prefetch_at: str = os.environ.get("T1_DECODE_PF_AT", "o")
     # overlap the prompt rows of the reference-model scoring pass (tensor-bound, independent of the sampled tokens) with the
     # decode (HBM-bound): the decode's weight-streaming GEMMs keep to `decode_ctas` SMs on a high-priority stream, the
     # reference prefill runs on a side stream with its GEMMs capped at `side_ctas` CTAs.  0 = off.

@@ -55,6 +55,8 @@ static_assert(NSOFT >= 64 * 8, "the Q-tile build takes one (row, 8-channel chunk
 constexpr int TC_THREADS = 64 + NSOFT;
 constexpr int MAX_S = 16;
 constexpr int MAX_OWN = 8;                       // sequences whose current token one CTA may own (ceil(G / S))
+constexpr int MAX_SPLIT = 48;                    // wide form: CTAs per (group, KV head); sources per row = MAX_SPLIT + 1 <= 64
+constexpr int CNT_STRIDE = 8;                    // wide form: one 32-byte sector of counters per (group, KV head)
 constexpr int MAX_GROUPS = 8;                    // prompt-groups per launch (tensor maps travel as kernel parameters)
 struct MapTable {
   CUtensorMap m[2 * MAX_GROUPS];                 // [group][K, V]
@@ -114,13 +116,30 @@ struct UnitDesc {
   int seq;       // -1: prompt prefix (visible to every row); else the owning sequence
 };
 
+__device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// WIDE = false: one cluster of S CTAs per (group, KV head), partials merged through distributed shared memory.
+// WIDE = true : S = gridDim.x plain CTAs per (group, KV head) -- S is chosen so that the launch fills the machine (18 at
+//   cfg2: 144 of 148 SMs instead of 64) -- and the partials travel through an L2-resident workspace: every CTA stores
+//   its (m, l, O) rows, arrives on a per-(group, head) counter (release), spins until all S have arrived (acquire) and
+//   merges the rows it owns.  All CTAs of the launch are co-resident (host: grid <= SM count, one CTA per SM), so the
+//   spin cannot starve a peer; the last CTA to leave resets the counters for the next launch.
+template <bool WIDE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 decode_attn_tc_kernel(const bf16* __restrict__ q, long long ldq, int Hq, int Hkv, int G, int cpad,
                       const int* __restrict__ step_ptr, bf16* __restrict__ out, long long ldo, float scale_log2,
-                      const DecodeGroup* __restrict__ groups, const __grid_constant__ MapTable maps) {
+                      const DecodeGroup* __restrict__ groups, const __grid_constant__ MapTable maps,
+                      float* __restrict__ ws_o, float* __restrict__ ws_ml, unsigned* __restrict__ ws_cnt) {
   cg::cluster_group cluster = cg::this_cluster();
-  const int S = (int)cluster.num_blocks();
-  const int rank = (int)cluster.block_rank();
+  const int S = WIDE ? (int)gridDim.x : (int)cluster.num_blocks();
+  const int rank = WIDE ? (int)blockIdx.x : (int)cluster.block_rank();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -192,8 +211,16 @@ decode_attn_tc_kernel(const bf16* __restrict__ q, long long ldq, int Hq, int Hkv
   const int UP = (P + UNIT - 1) / UNIT;
   const int UPS = (step + UNIT - 1) / UNIT;    // units per sequence holding slots 0..step-1
   const int UC = G * UPS;
-  const int p_lo = (int)((long long)rank * UP / S), p_hi = (int)((long long)(rank + 1) * UP / S);
-  const int c_lo = (int)((long long)rank * UC / S), c_hi = (int)((long long)(rank + 1) * UC / S);
+  int p_lo, p_hi, c_lo, c_hi;
+  if constexpr (WIDE) {      // one even deal of the concatenated list [prefix units | completion units]
+    const int U = UP + UC;
+    const int u_lo = (int)((long long)rank * U / S), u_hi = (int)((long long)(rank + 1) * U / S);
+    p_lo = min(u_lo, UP), p_hi = min(u_hi, UP);
+    c_lo = max(u_lo, UP) - UP, c_hi = max(u_hi, UP) - UP;
+  } else {
+    p_lo = (int)((long long)rank * UP / S), p_hi = (int)((long long)(rank + 1) * UP / S);
+    c_lo = (int)((long long)rank * UC / S), c_hi = (int)((long long)(rank + 1) * UC / S);
+  }
   const int n_units = (p_hi - p_lo) + (c_hi - c_lo);
   auto unit_desc = [&](int i) {
     UnitDesc d;
@@ -434,7 +461,7 @@ decode_attn_tc_kernel(const bf16* __restrict__ q, long long ldq, int Hq, int Hkv
   DBG(threadIdx.x == 64, 903);
   // Split-phase cluster barrier: arrive = "this CTA is done with its K/V ring" (which becomes a merge receive buffer of
   // the cluster); the work that needs no remote memory (O out of TMEM, the score of this step's token) runs before the wait.
-  cluster.barrier_arrive();
+  if constexpr (!WIDE) cluster.barrier_arrive();
   float* rO = reinterpret_cast<float*>(sKV);            // [64/S local rows][2S sources][128]
   float* rML = rO + 64 * 2 * HD;                        // [64/S local rows][2S sources][2]
   uint32_t ov[32];
@@ -466,6 +493,99 @@ decode_attn_tc_kernel(const bf16* __restrict__ q, long long ldq, int Hq, int Hkv
       l_new = 1.f;
     }
   }
+  // number of merge sources per query row and where the merge reads them from
+  const int NSRC = WIDE ? S + 1 : 2 * S;
+  const int n_local = rank < n_rows ? (n_rows - rank + S - 1) / S : 0;      // rows rank, rank + S, ... are merged here
+  if constexpr (WIDE) {
+    // ---- store: source `rank` = cached-key partial, source S = this step's token (owner of the sequence only) ----
+    const int gh = gi * Hkv + hk;
+    float* wO = ws_o + (size_t)gh * 64 * NSRC * HD;     // [row][source][128]
+    float* wML = ws_ml + (size_t)gh * 64 * NSRC * 2;    // [row][source][m, l]
+    if (valid) {
+      float* dO = wO + ((size_t)r * NSRC + rank) * HD + part * 32;
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4)
+        __stcg(reinterpret_cast<uint4*>(dO) + j4, make_uint4(ov[j4 * 4], ov[j4 * 4 + 1], ov[j4 * 4 + 2], ov[j4 * 4 + 3]));
+      if (part == 0) __stcg(reinterpret_cast<float2*>(wML + ((size_t)r * NSRC + rank) * 2), make_float2(m_ref, l));
+      if (own) {
+        float* dN = wO + ((size_t)r * NSRC + S) * HD + part * 32;
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4)
+          __stcg(reinterpret_cast<float4*>(dN) + j4, *reinterpret_cast<const float4*>(s_vnew + own_o * HD + part * 32 + j4 * 4));
+        if (part == 0) __stcg(reinterpret_cast<float2*>(wML + ((size_t)r * NSRC + S) * 2), make_float2(s_new, l_new));
+      }
+      __threadfence();
+    }
+    DBG(threadIdx.x == 64, 904);
+    __syncthreads();           // every partial row of this CTA is stored and fenced
+    if (threadIdx.x == 64) {   // a softmax thread: it executed griddepcontrol.wait, so the counters are the reset ones
+      unsigned* cnt = ws_cnt + CNT_STRIDE * gh;
+      red_release_add(cnt, 1u);
+      // ~1 us per poll: a peer that never arrives (a co-residency violation) traps after seconds instead of hanging the device
+      unsigned polls = 0;
+      while (ld_acquire(cnt) < (unsigned)S) {
+        if (++polls > (1u << 22)) __trap();
+      }
+      if (atomicAdd(cnt + 1, 1u) == (unsigned)(S - 1)) {      // last one out: nobody spins on cnt any more
+        atomicExch(cnt, 0u);
+        atomicExch(cnt + 1, 0u);
+      }
+    }
+    DBG(threadIdx.x == 64, 905);
+    __syncthreads();           // all S CTAs of this (group, head) have stored their partials
+    DBG(threadIdx.x == 64, 906);
+    if (warp_idx >= 2) {
+      float* s_w = s_xch;                           // [local rows][NSRC]
+      float* s_L = s_lx;                            // [local rows]
+      for (int li = warp_idx - 2; li < n_local; li += NSOFT / 32) {
+        const float* ml = wML + (size_t)(rank + li * S) * NSRC * 2;
+        float mv[2], lv[2];                         // NSRC <= 64: two sources per lane
+        float M = -INFINITY;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int src = lane + 32 * h;
+          mv[h] = -INFINITY;
+          lv[h] = 0.f;
+          if (src < NSRC) {
+            const float2 v = __ldcg(reinterpret_cast<const float2*>(ml + src * 2));
+            mv[h] = v.x;
+            lv[h] = v.y;
+          }
+          if (lv[h] > 0.f) M = fmaxf(M, mv[h]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o));
+        float Ls = 0.f;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int src = lane + 32 * h;
+          const float w = lv[h] > 0.f ? ex2_approx(mv[h] - M) : 0.f;
+          Ls += w * lv[h];
+          if (src < NSRC) s_w[li * NSRC + src] = w;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) Ls += __shfl_xor_sync(0xffffffffu, Ls, o);
+        if (lane == 0) s_L[li] = Ls;
+      }
+      asm volatile("bar.sync 9, %0;" ::"n"(NSOFT) : "memory");
+      for (int e = st_tid; e < n_local * HD; e += NSOFT) {
+        const int li = e >> 7, col = e & (HD - 1);
+        const int row = rank + li * S;
+        const float* po = wO + (size_t)row * NSRC * HD + col;
+        const float* w = s_w + li * NSRC;
+        float acc = 0.f;
+#pragma unroll 8
+        for (int src = 0; src < NSRC; ++src) {
+          const float ws = w[src];
+          const float o = __ldcg(po + src * HD);    // L2: written by other SMs during this launch
+          acc += ws > 0.f ? ws * o : 0.f;           // never-written rows of empty sources are dropped
+        }
+        const float Ls = s_L[li];
+        const int sq = row / ratio, hq = hk * ratio + row % ratio;
+        out[(long long)sq * ldo + (long long)hq * HD + col] = __float2bfloat16(Ls > 0.f ? acc / Ls : 0.f);
+      }
+    }
+  } else {
   cluster.barrier_wait();    // every CTA of the cluster is done with its K/V ring
   DBG(threadIdx.x == 64, 904);
 
@@ -493,7 +613,6 @@ decode_attn_tc_kernel(const bf16* __restrict__ q, long long ldq, int Hq, int Hkv
     // pass 1, one warp per row: lane = source; w = 2^(m - M) (0 for empty sources), L = sum w * l
     float* s_w = s_xch;                           // [local rows][2S]  (the exchange buffers are free now)
     float* s_L = s_lx;                            // [local rows]
-    const int n_local = rank < n_rows ? (n_rows - rank + S - 1) / S : 0;
     for (int li = warp_idx - 2; li < n_local; li += NSOFT / 32) {
       const float* ml = rML + (li * 2 * S) * 2;
       float mv = -INFINITY, lv = 0.f;
@@ -530,6 +649,7 @@ decode_attn_tc_kernel(const bf16* __restrict__ q, long long ldq, int Hq, int Hkv
       const int sq = row / ratio, hq = hk * ratio + row % ratio;
       out[(long long)sq * ldo + (long long)hq * HD + col] = __float2bfloat16(Ls > 0.f ? acc / Ls : 0.f);
     }
+  }
   }
   DBG(threadIdx.x == 64, 907);
   tc_fence_before();
@@ -585,8 +705,8 @@ extern "C" int t1_decode_attn_cluster(const void* q, long long ldq, const void* 
   T1_CHECK_ARG((G + S - 1) / S <= MAX_OWN, "t1_decode_attn_cluster: G=%d too large for cluster size %d", G, S);
   static bool set = false;
   if (!set) {
-    cudaError_t e = cudaFuncSetAttribute(decode_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(decode_attn_tc_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaError_t e = cudaFuncSetAttribute(decode_attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(decode_attn_tc_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     if (e != cudaSuccess) {
       t1_set_error("t1_decode_attn_cluster: cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e));
       return T1_ERR_CUDA;
@@ -607,10 +727,103 @@ extern "C" int t1_decode_attn_cluster(const void* q, long long ldq, const void* 
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = t1_pdl_enabled() ? 2 : 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, decode_attn_tc_kernel, (const bf16*)q, ldq, Hq, Hkv, G, cpad, step_ptr, (bf16*)out,
-                                     ldo, scale * 1.4426950408889634f, (const DecodeGroup*)groups, tbl);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, decode_attn_tc_kernel<false>, (const bf16*)q, ldq, Hq, Hkv, G, cpad, step_ptr, (bf16*)out,
+                                     ldo, scale * 1.4426950408889634f, (const DecodeGroup*)groups, tbl, (float*)nullptr,
+                                     (float*)nullptr, (unsigned*)nullptr);
   if (e != cudaSuccess) {
     t1_set_error("t1_decode_attn_cluster: launch failed: %s", cudaGetErrorString(e));
+    return T1_ERR_CUDA;
+  }
+  t1_count_launch();
+  return T1_OK;
+}
+
+// ---- wide form: the same CTA program on (almost) every SM, partials merged through an L2-resident workspace ----
+static int wide_sm_count() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 0;
+  }
+  return sms;
+}
+static size_t wide_ws_bytes(int n_groups, int Hkv, int S) {
+  const size_t gh = (size_t)n_groups * Hkv;
+  return 256 + gh * CNT_STRIDE * 4 + gh * 64 * (S + 1) * (HD + 2) * sizeof(float);
+}
+
+// Plan of t1_decode_attn_wide for n_groups prompt-groups of Hkv KV heads on the current device: *splits = CTAs per
+// (group, KV head) (the largest count for which the whole launch is co-resident, one CTA per SM; `requested` > 0 overrides
+// it and is validated), *ws_bytes = size of the workspace the caller allocates AND ZEROES ONCE (the launch leaves its
+// counters zeroed again).
+extern "C" int t1_decode_attn_wide_plan(int n_groups, int Hkv, int requested, int* splits, long long* ws_bytes) {
+  T1_CHECK_ARG(n_groups > 0 && n_groups <= MAX_GROUPS && Hkv > 0 && splits && ws_bytes, "t1_decode_attn_wide_plan: bad arguments");
+  const int sms = wide_sm_count();
+  T1_CHECK_ARG(sms > 0, "t1_decode_attn_wide_plan: no CUDA device");
+  const int fit = sms / (n_groups * Hkv);
+  T1_CHECK_ARG(fit >= 1, "t1_decode_attn_wide_plan: %d (group, KV head) pairs do not fit on %d SMs", n_groups * Hkv, sms);
+  int S = requested > 0 ? requested : (fit < MAX_SPLIT ? fit : MAX_SPLIT);
+  if (requested <= 0 && getenv("T1_DECODE_SPLITS")) S = atoi(getenv("T1_DECODE_SPLITS"));
+  T1_CHECK_ARG(S >= 1 && S <= MAX_SPLIT && S <= fit,
+               "t1_decode_attn_wide_plan: %d CTAs per (group, KV head) not in [1, min(%d, %d)] (all CTAs must be co-resident)", S,
+               MAX_SPLIT, fit);
+  *splits = S;
+  *ws_bytes = (long long)wide_ws_bytes(n_groups, Hkv, S);
+  return T1_OK;
+}
+
+// Decode attention of one layer for all prompt-groups in ONE launch of `splits` CTAs per (group, KV head) without
+// clusters (arguments as t1_decode_attn_cluster).  ws / ws_bytes / splits: from t1_decode_attn_wide_plan; the first
+// 256 + n_groups * Hkv * 32 bytes of ws are arrival counters that must be zero before the first launch.  The launch
+// spins on them: it must not share the device with a kernel that waits for it.
+extern "C" int t1_decode_attn_wide(const void* q, long long ldq, const void* groups, const void* maps, int n_groups, int G,
+                                   int Hq, int Hkv, int head_dim, int cpad, const int* step_ptr, void* out, long long ldo,
+                                   float scale, int splits, void* ws, long long ws_bytes, cudaStream_t stream) {
+  T1_CHECK_ARG(head_dim == HD, "t1_decode_attn_wide: head_dim must be 128 (got %d)", head_dim);
+  T1_CHECK_ARG(cpad > 0, "t1_decode_attn_wide: cpad must be positive");
+  T1_CHECK_ARG(n_groups > 0 && G > 0 && Hkv > 0 && Hq % Hkv == 0 && G * (Hq / Hkv) <= 64,
+               "t1_decode_attn_wide: G * Hq/Hkv must be <= 64");
+  T1_CHECK_ARG(q && groups && maps && step_ptr && out && ws, "t1_decode_attn_wide: null pointer");
+  T1_CHECK_ARG(ldq % 8 == 0 && ((uintptr_t)q & 15) == 0, "t1_decode_attn_wide: q must be 16-byte aligned with ldq %% 8 == 0");
+  T1_CHECK_ARG(((uintptr_t)ws & 255) == 0, "t1_decode_attn_wide: ws must be 256-byte aligned");
+  T1_CHECK_ARG(n_groups <= MAX_GROUPS, "t1_decode_attn_wide: at most %d prompt-groups per launch (got %d)", MAX_GROUPS, n_groups);
+  const int S = splits;
+  const int sms = wide_sm_count();
+  T1_CHECK_ARG(S >= 1 && S <= MAX_SPLIT && S * Hkv * n_groups <= sms,
+               "t1_decode_attn_wide: splits=%d: need 1 <= splits <= %d and splits * Hkv * n_groups <= %d SMs", S, MAX_SPLIT, sms);
+  T1_CHECK_ARG((G + S - 1) / S <= MAX_OWN, "t1_decode_attn_wide: G=%d too large for %d splits", G, S);
+  T1_CHECK_ARG(ws_bytes >= (long long)wide_ws_bytes(n_groups, Hkv, S), "t1_decode_attn_wide: workspace too small (%lld < %lld bytes)",
+               ws_bytes, (long long)wide_ws_bytes(n_groups, Hkv, S));
+  MapTable tbl;
+  memset(&tbl, 0, sizeof(tbl));
+  memcpy(&tbl, maps, (size_t)n_groups * 2 * sizeof(CUtensorMap));
+  static bool set = false;
+  if (!set) {
+    cudaError_t e = cudaFuncSetAttribute(decode_attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+    if (e != cudaSuccess) {
+      t1_set_error("t1_decode_attn_wide: cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e));
+      return T1_ERR_CUDA;
+    }
+    set = true;
+  }
+  const size_t gh = (size_t)n_groups * Hkv;
+  unsigned* ws_cnt = reinterpret_cast<unsigned*>(ws);
+  float* ws_ml = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws) + 256 + gh * CNT_STRIDE * 4);
+  float* ws_o = ws_ml + gh * 64 * (S + 1) * 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(S, Hkv, n_groups);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = TC_SMEM;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = t1_pdl_enabled() ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, decode_attn_tc_kernel<true>, (const bf16*)q, ldq, Hq, Hkv, G, cpad, step_ptr, (bf16*)out,
+                                     ldo, scale * 1.4426950408889634f, (const DecodeGroup*)groups, tbl, ws_o, ws_ml, ws_cnt);
+  if (e != cudaSuccess) {
+    t1_set_error("t1_decode_attn_wide: launch failed: %s", cudaGetErrorString(e));
     return T1_ERR_CUDA;
   }
   t1_count_launch();

@@ -84,7 +84,31 @@ struct SgParams {
   const float* in_parts;  // consumer: [in_nparts][MP] (nullptr: x is already normalised)
   int in_nparts;
   float in_eps;
+  // L2 prefetch of the NEXT weight stream (t1_stream_gemm_prefetch_next): while this launch waits for its dependency the
+  // idle epilogue warps pull the units the next GEMM's CTAs read right after their own ring into L2, so the HBM works
+  // through the latency-bound part of the chain (qkv -> attention -> o) instead of idling
+  const bf16* pf_w;       // next W (nullptr: off)
+  long long pf_ldw;
+  int pf_n;               // rows of next W
+  int pf_kblocks, pf_per_cta, pf_total, pf_grid;   // the next launch's unit split
+  int pf_skip, pf_units;  // per CTA of the next launch: units [skip, skip + units) of its range
+  int pf_swiglu, pf_half_n;
 };
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// one 128-byte line per thread and unit: thread et owns weight row et of the slab
+__device__ __forceinline__ void sg_prefetch_next(const SgParams& p, int et) {
+  for (int c = blockIdx.x; c < p.pf_grid; c += gridDim.x) {
+    const int c0 = c * p.pf_per_cta;
+    const int v0 = c0 + p.pf_skip;
+    const int v1 = min(min(v0 + p.pf_units, c0 + p.pf_per_cta), p.pf_total);
+    for (int u = v0; u < v1; ++u) {
+      const int slab = u / p.pf_kblocks, kb = u - slab * p.pf_kblocks;
+      const int row = p.pf_swiglu ? (et < 64 ? slab * 64 + et : p.pf_half_n + slab * 64 + et - 64) : slab * SG_BM + et;
+      if (row < p.pf_n) prefetch_l2(p.pf_w + (long long)row * p.pf_ldw + kb * SG_BK);
+    }
+  }
+}
 #ifdef T1_SG_DBG
 __device__ unsigned long long g_cta_t[3][512];     // per-CTA start / first-data / end stamps of the last launch
 #endif
@@ -231,9 +255,10 @@ stream_gemm_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_const
     }
   } else {
     // ===================== epilogue (warps 2..5 = TMEM lane quadrants 2,3,0,1) =====================
+    const int et = (warp_idx - 2) * 32 + lane;   // 0..127
+    if (p.pf_w) sg_prefetch_next(p, et);         // weights of the next GEMM -> L2 (independent of every dependency)
     pdl_wait();
     const int q = warp_idx & 3;
-    const int et = (warp_idx - 2) * 32 + lane;   // 0..127
     const int r = q * 32 + lane;                 // weight row inside the slab == TMEM lane
     float* r_s = reinterpret_cast<float*>(smem + 512);   // [MP] row factors of a folded RMSNorm (header bytes 512..767)
     if (p.in_parts) {
@@ -867,6 +892,69 @@ extern "C" void t1_stream_gemm_tune(int stages, int ctas_per_sm) {
   g_ctas_per_sm = ctas_per_sm > 0 ? ctas_per_sm : 1;
 }
 
+// The unit split of a launch (shared by the launch itself and by the L2 prefetch hint that describes the NEXT launch).
+struct SgPlan {
+  int MP, stage_bytes, xs_bytes, stages, smem, slabs, kblocks, per, grid, half_n;
+  long long total;
+};
+static SgPlan sg_plan(int M, int N, int K, int swiglu, bool fold_producer) {
+  SgPlan pl;
+  pl.MP = M <= 16 ? 16 : (M <= 32 ? 32 : 64);
+  pl.stage_bytes = SG_W_BYTES + pl.MP * SG_BK * 2;
+  pl.half_n = N / 2;
+  pl.xs_bytes = swiglu ? pl.MP * 64 * 4 : (fold_producer ? 4 * pl.MP * 4 : 0);
+  if (g_stages < 0) {
+    g_stages = env_int("T1_STREAM_STAGES", 0);
+    g_ctas_per_sm = env_int("T1_STREAM_CTAS_PER_SM", 1);
+  }
+  const int env_stages = g_stages, env_ctas = g_ctas_per_sm;
+  // default: ~180 KB of ring per CTA (10 stages at MP = 16).  Measured on B200 inside the captured 7B decode step
+  // (profiles/r01_decode_timeline_v2.txt): 10 stages 3.65 ms/step, 6 stages (two kernels co-resident) 3.71 ms.
+  int stages = env_stages > 0 ? env_stages : (180 * 1024) / pl.stage_bytes;
+  if (stages > SG_MAX_STAGES) stages = SG_MAX_STAGES;
+  while (stages > 2 && SG_HEADER + 1024 + stages * pl.stage_bytes + pl.xs_bytes > 227 * 1024) --stages;
+  pl.stages = stages;
+  pl.smem = SG_HEADER + 1024 + stages * pl.stage_bytes + pl.xs_bytes;
+  pl.slabs = swiglu ? pl.half_n / 64 : (N + SG_BM - 1) / SG_BM;
+  pl.kblocks = (K + SG_BK - 1) / SG_BK;
+  pl.total = (long long)pl.slabs * pl.kblocks;
+  int max_ctas = t1_num_sms() * (env_ctas > 0 ? env_ctas : 1);
+  if (max_ctas > 2 * t1_num_sms()) max_ctas = 2 * t1_num_sms();
+  if (g_max_ctas > 0 && g_max_ctas < max_ctas) max_ctas = g_max_ctas;     // leave SMs to a concurrent stream (experiments)
+  pl.per = (int)((pl.total + max_ctas - 1) / max_ctas);
+  pl.grid = (int)((pl.total + pl.per - 1) / pl.per);
+  return pl;
+}
+
+// One-shot hint consumed by the next statically split t1_stream_gemm* launch (see SgParams::pf_w).
+struct SgPrefetchHint {
+  const void* W = nullptr;
+  long long ldw = 0, bytes = 0;
+  int M = 0, N = 0, K = 0, swiglu = 0, fold_producer = 0;
+};
+static SgPrefetchHint g_pf_hint;
+
+// While the NEXT t1_stream_gemm* launch (any variant on the static split) waits for its dependency, its idle warps
+// prefetch into L2 up to max_bytes of W_next [N, K] -- exactly the units the launch AFTER it (described by M, N, K,
+// swiglu = t1_stream_gemm_swiglu / _scaled(swiglu) layout, fold_producer = t1_stream_gemm_fold) reads first after
+// filling its own shared-memory ring.  Purely a performance hint: results do not depend on it.  max_bytes <= 0 clears.
+extern "C" int t1_stream_gemm_prefetch_next(const void* W_next, long long ldw, int M, int N, int K, int swiglu,
+                                            int fold_producer, long long max_bytes) {
+  g_pf_hint = SgPrefetchHint();
+  if (!W_next || max_bytes <= 0) return T1_OK;
+  T1_CHECK_ARG(M > 0 && M <= 64 && N > 0 && K > 0 && K % 8 == 0 && ldw >= K, "t1_stream_gemm_prefetch_next: bad shape");
+  T1_CHECK_ARG(!swiglu || N % 128 == 0, "t1_stream_gemm_prefetch_next: swiglu needs N = 2*I with I %% 64 == 0");
+  g_pf_hint.W = W_next;
+  g_pf_hint.ldw = ldw;
+  g_pf_hint.bytes = max_bytes;
+  g_pf_hint.M = M;
+  g_pf_hint.N = N;
+  g_pf_hint.K = K;
+  g_pf_hint.swiglu = swiglu ? 1 : 0;
+  g_pf_hint.fold_producer = fold_producer ? 1 : 0;
+  return T1_OK;
+}
+
 struct SgTail {
   void* resid = nullptr;
   const void* norm_w = nullptr;
@@ -888,31 +976,12 @@ static int stream_gemm_impl(const void* x, long long ldx, const void* W, long lo
   T1_CHECK_ARG(N > 0 && K > 0 && K % 8 == 0, "t1_stream_gemm: K %% 8 required (N=%d K=%d)", N, K);
   T1_CHECK_ARG(ldx % 8 == 0 && ldw % 8 == 0 && ldx >= K && ldw >= K, "t1_stream_gemm: ldx/ldw must be multiples of 8 and >= K");
   T1_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)W & 15) == 0, "t1_stream_gemm: operands must be 16-byte aligned");
-  const int MP = M <= 16 ? 16 : (M <= 32 ? 32 : 64);
-  const int stage_bytes = SG_W_BYTES + MP * SG_BK * 2;
-  const int half_n = N / 2;
-  const int xs_bytes = swiglu ? MP * 64 * 4 : (tail.fold_resid ? 4 * MP * 4 : 0);
   if (swiglu) T1_CHECK_ARG(N % 128 == 0 && !out_f32, "t1_stream_gemm_swiglu: N = 2*I with I %% 64 == 0 and bf16 output required (N=%d)", N);
-  if (g_stages < 0) {
-    g_stages = env_int("T1_STREAM_STAGES", 0);
-    g_ctas_per_sm = env_int("T1_STREAM_CTAS_PER_SM", 1);
-  }
-  const int env_stages = g_stages, env_ctas = g_ctas_per_sm;
-  // default: ~180 KB of ring per CTA (10 stages at MP = 16).  Measured on B200 inside the captured 7B decode step
-  // (profiles/r01_decode_timeline_v2.txt): 10 stages 3.65 ms/step, 6 stages (two kernels co-resident) 3.71 ms.
-  int stages = env_stages > 0 ? env_stages : (180 * 1024) / stage_bytes;
-  if (stages > SG_MAX_STAGES) stages = SG_MAX_STAGES;
-  while (stages > 2 && SG_HEADER + 1024 + stages * stage_bytes + xs_bytes > 227 * 1024) --stages;
-  const int smem = SG_HEADER + 1024 + stages * stage_bytes + xs_bytes;
-  const int slabs = swiglu ? half_n / 64 : (N + SG_BM - 1) / SG_BM;
-  const int kblocks = (K + SG_BK - 1) / SG_BK;
-  const long long total = (long long)slabs * kblocks;
+  const SgPlan pl = sg_plan(M, N, K, swiglu, tail.fold_resid != nullptr);
+  const int MP = pl.MP, half_n = pl.half_n, stages = pl.stages, smem = pl.smem, slabs = pl.slabs, kblocks = pl.kblocks;
+  const int per = pl.per, grid = pl.grid;
+  const long long total = pl.total;
   T1_CHECK_ARG(total < (1LL << 30), "t1_stream_gemm: problem too large");
-  int max_ctas = t1_num_sms() * (env_ctas > 0 ? env_ctas : 1);
-  if (max_ctas > 2 * t1_num_sms()) max_ctas = 2 * t1_num_sms();
-  if (g_max_ctas > 0 && g_max_ctas < max_ctas) max_ctas = g_max_ctas;     // leave SMs to a concurrent stream (experiments)
-  const int per = (int)((total + max_ctas - 1) / max_ctas);
-  const int grid = (int)((total + per - 1) / per);
   const long long need = SG_COUNTER_BYTES + (long long)grid * 2 * MP * SG_BM * 4;
   T1_CHECK_ARG(slabs * 4 <= SG_COUNTER_BYTES, "t1_stream_gemm: N=%d exceeds the counter region", N);
   T1_CHECK_ARG(workspace_bytes >= need, "t1_stream_gemm: workspace too small (%lld < %lld)", workspace_bytes, need);
@@ -949,6 +1018,9 @@ static int stream_gemm_impl(const void* x, long long ldx, const void* W, long lo
   p.in_parts = tail.in_parts;
   p.in_nparts = tail.in_nparts;
   p.in_eps = tail.eps;
+  p.pf_w = nullptr;
+  const SgPrefetchHint hint = g_pf_hint;
+  g_pf_hint = SgPrefetchHint();          // one-shot
   const bool folded = tail.fold_resid || tail.in_parts;       // only the statically split kernel carries the folded norm
   p.segs = 1;
   p.seg_k = kblocks;
@@ -990,9 +1062,31 @@ static int stream_gemm_impl(const void* x, long long ldx, const void* W, long lo
     if (MP == 16) rc = launch_stream_dyn<16>(tw, tx, p, grid_dyn, smem, stream);
     else if (MP == 32) rc = launch_stream_dyn<32>(tw, tx, p, grid_dyn, smem, stream);
     else rc = launch_stream_dyn<64>(tw, tx, p, grid_dyn, smem, stream);
-  } else if (MP == 16) rc = launch_stream<16>(tw, tx, p, grid, smem, stream);
-  else if (MP == 32) rc = launch_stream<32>(tw, tx, p, grid, smem, stream);
-  else rc = launch_stream<64>(tw, tx, p, grid, smem, stream);
+  } else {
+    if (hint.W) {        // describe the launch after this one
+      const SgPlan nx = sg_plan(hint.M, hint.N, hint.K, hint.swiglu, hint.fold_producer != 0);
+      if (nx.total < (1LL << 30)) {
+        long long units = hint.bytes / ((long long)SG_W_BYTES * nx.grid);
+        if (units > nx.per - nx.stages) units = nx.per - nx.stages;
+        if (units > 0) {
+          p.pf_w = reinterpret_cast<const bf16*>(hint.W);
+          p.pf_ldw = hint.ldw;
+          p.pf_n = hint.N;
+          p.pf_kblocks = nx.kblocks;
+          p.pf_per_cta = nx.per;
+          p.pf_total = (int)nx.total;
+          p.pf_grid = nx.grid;
+          p.pf_skip = nx.stages;
+          p.pf_units = (int)units;
+          p.pf_swiglu = hint.swiglu;
+          p.pf_half_n = nx.half_n;
+        }
+      }
+    }
+    if (MP == 16) rc = launch_stream<16>(tw, tx, p, grid, smem, stream);
+    else if (MP == 32) rc = launch_stream<32>(tw, tx, p, grid, smem, stream);
+    else rc = launch_stream<64>(tw, tx, p, grid, smem, stream);
+  }
   if (rc) return rc;
   t1_count_launch();
   return T1_OK;

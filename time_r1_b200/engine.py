@@ -611,6 +611,8 @@ class Engine:
             # per-layer TMA tensor maps over every group's K and V cache (t1_decode_attn_cluster)
             flat = [t for l in range(L) for grp in groups for t in grp["kv"][l]]
             st["kv_maps"] = ops.kv_cache_tensor_maps(flat, cfg.num_key_value_heads, cfg.head_dim).reshape(L, n * 2 * 128)
+            if self.run.decode_attn == "wide":
+                st["attn_splits"], st["attn_ws"] = ops.decode_attn_wide_workspace(n, cfg.num_key_value_heads, d)
         self._decode_cache[key] = st
         return st
 
@@ -650,22 +652,43 @@ class Engine:
             fuse_norm = self.run.decode_fuse_norm and cfg.hidden_size % 8 == 0
             # folded norms: the o / down GEMM epilogues update the residual stream and emit z = norm_w * resid plus per-slab
             # row sums of squares; the next GEMM streams against z and applies the row factor in its epilogue
-            fold = (self.run.decode_fold_norm and not fuse_norm and self.run.decode_attn == "cluster" and cfg.hidden_size % 128 == 0
+            wide = self.run.decode_attn == "wide"
+
+            def attn_tc(l):
+                """rope + KV append + shared-prefix attention of layer l, all groups, one tcgen05 launch"""
+                common = (ptr(qkv), qkv.stride(0), ptr(tab[l]), st["kv_maps"][l].ctypes.data, n, G, Hq, Hkv, hd, st["cpad"],
+                          ptr(st["step"]), ptr(attn), attn.stride(0), scale)
+                if wide:      # every SM streams K/V; partials merged through the L2-resident workspace
+                    call("t1_decode_attn_wide", *common, st["attn_splits"], ptr(st["attn_ws"]), st["attn_ws"].numel(), s)
+                else:         # 8-CTA cluster per (group, KV head), partials merged through distributed shared memory
+                    call("t1_decode_attn_cluster", *common, 0, s)
+
+            fold = (self.run.decode_fold_norm and not fuse_norm and self.run.decode_attn in ("cluster", "wide") and cfg.hidden_size % 128 == 0
                     and cfg.intermediate_size % 64 == 0)
             D = cfg.hidden_size
             fp = st["fold_parts"]
+            pf_bytes = int(self.run.decode_prefetch_mb) << 20
+
+            def prefetch_gate_up(l):
+                """hint for the NEXT stream GEMM launch: its idle warps pull layer l's first gate_up units into L2"""
+                w = self.p(f"model.layers.{l}.mlp.gate_up.weight")
+                call("t1_stream_gemm_prefetch_next", ptr(w), w.stride(0), B, w.shape[0], w.shape[1], 1, 0, pf_bytes)
+
             for l in range(L):
                 pre = f"model.layers.{l}."
                 if fold:
                     last = l == L - 1
+                    if pf_bytes and self.run.decode_prefetch_at == "qkv":
+                        prefetch_gate_up(l)
                     if l == 0:
                         ops.rmsnorm(x, self.p(pre + "input_layernorm.weight"), eps, out=h)
                         ops.stream_gemm(h, self.p(pre + "self_attn.qkv.weight"), ws, out=qkv, bias=self.p(pre + "self_attn.qkv.bias"))
                     else:
                         ops.stream_gemm_scaled(h, self.p(pre + "self_attn.qkv.weight"), ws, fp[1], D // 128, eps, out=qkv,
                                                bias=self.p(pre + "self_attn.qkv.bias"))
-                    call("t1_decode_attn_cluster", ptr(qkv), qkv.stride(0), ptr(tab[l]), st["kv_maps"][l].ctypes.data, n, G, Hq, Hkv, hd,
-                         st["cpad"], ptr(st["step"]), ptr(attn), attn.stride(0), scale, 0, s)
+                    attn_tc(l)
+                    if pf_bytes and self.run.decode_prefetch_at == "o":
+                        prefetch_gate_up(l)
                     ops.stream_gemm_fold(attn, self.p(pre + "self_attn.o_proj.weight"), ws, x,
                                          self.p(pre + "post_attention_layernorm.weight"), h, fp[0])
                     ops.stream_gemm_scaled(h, self.p(pre + "mlp.gate_up.weight"), ws, fp[0], D // 128, eps, out=act, swiglu=True)
@@ -679,9 +702,8 @@ class Engine:
                     ops.rmsnorm(x, self.p(pre + "input_layernorm.weight"), eps, delta=down if (l > 0 and not fuse_norm) else None, out=h)
                 ops.stream_gemm(h, self.p(pre + "self_attn.qkv.weight"), ws, out=qkv, bias=self.p(pre + "self_attn.qkv.bias"))
                 # rope + KV append are fused into the attention kernel
-                if self.run.decode_attn == "cluster":
-                    call("t1_decode_attn_cluster", ptr(qkv), qkv.stride(0), ptr(tab[l]), st["kv_maps"][l].ctypes.data, n, G, Hq, Hkv, hd,
-                         st["cpad"], ptr(st["step"]), ptr(attn), attn.stride(0), scale, 0, s)
+                if self.run.decode_attn in ("cluster", "wide"):
+                    attn_tc(l)
                 else:
                     call("t1_decode_attn_groups", ptr(qkv), qkv.stride(0), ptr(tab[l]), n, G, Hq, Hkv, hd, st["max_P"], st["cpad"],
                          ptr(st["step"]), ptr(attn), attn.stride(0), scale, 1, s)

@@ -63,6 +63,8 @@ _SIGNATURES: dict[str, list] = {
     "t1_attn_fwd_tc": [vp, i64, vp, i64, vp, i64, vp, i64, vp, i64, vp, vp, i32, i32, i32, i32, i32, i32, f32, i32, vp],
     "t1_attn_fwd_tc_win": [vp, i64, vp, i64, vp, i64, vp, i64, vp, vp, i32, i32, i32, f32, vp],
     "t1_decode_attn_cluster": [vp, i64, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, i64, f32, i32, vp],
+    "t1_decode_attn_wide_plan": [i32, i32, i32, vp, vp],
+    "t1_decode_attn_wide": [vp, i64, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, i64, f32, i32, vp, i64, vp],
     "t1_encode_tmap_bf16": [vp, vp, i64, i64, i64, i32, i32],
     "t1_video_patchify": [vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp],
     "t1_attn_bwd_tc_workspace_bytes": [i32, i32, i32],
@@ -80,6 +82,7 @@ _SIGNATURES: dict[str, list] = {
     "t1_stream_gemm_swiglu": [vp, i64, vp, i64, vp, vp, i64, i32, i32, i32, vp, i64, vp],
     "t1_stream_gemm_fold": [vp, i64, vp, i64, i32, i32, i32, vp, vp, vp, vp, vp, i64, vp],
     "t1_stream_gemm_scaled": [vp, i64, vp, i64, vp, vp, i64, i32, i32, i32, i32, vp, i32, f32, vp, i64, vp],
+    "t1_stream_gemm_prefetch_next": [vp, i64, i32, i32, i32, i32, i32, i64],
     "t1_stream_gemm_workspace_bytes": [i32],
     "t1_set_pdl": [i32],
     "t1_stream_gemm_tune": [i32, i32],

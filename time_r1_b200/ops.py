@@ -458,6 +458,15 @@ def kv_cache_tensor_maps(caches, Hkv, head_dim):
     return buf
 
 
+def decode_attn_wide_workspace(n_groups, Hkv, device, splits=0):
+    """(splits, zeroed uint8 workspace) for t1_decode_attn_wide on `device` (plan: t1_decode_attn_wide_plan)."""
+    import ctypes
+
+    s, nb = ctypes.c_int(0), ctypes.c_longlong(0)
+    call("t1_decode_attn_wide_plan", int(n_groups), int(Hkv), int(splits), ctypes.byref(s), ctypes.byref(nb))
+    return s.value, torch.zeros(nb.value, device=device, dtype=torch.uint8)
+
+
 def logprob_entropy(logits, target):
     R, V = logits.shape
     lp = torch.empty(R, device=logits.device, dtype=F32)

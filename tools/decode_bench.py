@@ -48,8 +48,16 @@ def main():
     if os.environ.get("T1_BENCH_MAX_CTAS"):
         variants = [("stream", True, 0, 1)]
         lib.load().t1_stream_gemm_max_ctas(int(os.environ["T1_BENCH_MAX_CTAS"]))
-    for impl, pdl, stages, ctas in variants:
+    # T1_BENCH_VARIANTS='[{"decode_attn": "wide"}, {"decode_prefetch_mb": 64}]': RunConfig overrides, one stream/PDL run each
+    overrides = [None] * len(variants)
+    if os.environ.get("T1_BENCH_VARIANTS"):
+        overrides = json.loads(os.environ["T1_BENCH_VARIANTS"])
+        variants = [("stream", True, 0, 1)] * len(overrides)
+    for (impl, pdl, stages, ctas), ov in zip(variants, overrides):
         run = config.RunConfig(num_generations=G, max_completion_length=C, beta=0.0, decode_impl=impl, decode_pdl=pdl)
+        for k, v in (ov or {}).items():
+            assert hasattr(run, k), k
+            setattr(run, k, v)
         if os.environ.get("T1_DECODE_FOLD"):
             run.decode_fold_norm = os.environ["T1_DECODE_FOLD"] == "1"
         eng = engine.Engine.__new__(engine.Engine)      # decode only: skip the optimizer-state allocation
@@ -67,7 +75,7 @@ def main():
         st = eng._last_decode_state
         ms = time_replays(st)
         wbytes = 2.0 * (sum(p.numel() for n, p in mw.named() if n.startswith("model.layers.") and n.endswith("weight") and p.dim() == 2) + cfg.vocab_size * cfg.hidden_size) if hasattr(mw, "named") else 14.14e9
-        print(json.dumps({"impl": impl, "pdl": pdl, "stages": stages, "ctas_per_sm": ctas, "groups": n_groups, "ms_per_decode_step": round(ms, 4),
+        print(json.dumps({"overrides": ov, "impl": impl, "pdl": pdl, "stages": stages, "ctas_per_sm": ctas, "groups": n_groups, "ms_per_decode_step": round(ms, 4),
                           "weight_gbs": round(wbytes / ms / 1e6, 1), "launches_per_step": st["launches_per_step"],
                           "tok0": [int(o[0, 1]) for o in outs]}), flush=True)
         del eng, st
