@@ -740,9 +740,10 @@ extern "C" int t1_attn_bwd(const void* Q, long long ldq, const void* K, long lon
   T1_CHECK_ARG(Hkv > 0 && Hq % Hkv == 0, "t1_attn_bwd: Hq=%d must be a multiple of Hkv=%d", Hq, Hkv);
   switch (head_dim) {
     case 128: return launch_bwd<128>(Q, ldq, K, ldk, V, ldv, O, ldo, dO, lddo, LSE2, delta_ws, summ_ws, dQ, lddq, dK, lddk, dV, lddv, row_lo, row_hi, shared_len, T, Tk, Hq, Hkv, scale, stream);
+    case 80: return launch_bwd<80>(Q, ldq, K, ldk, V, ldv, O, ldo, dO, lddo, LSE2, delta_ws, summ_ws, dQ, lddq, dK, lddk, dV, lddv, row_lo, row_hi, shared_len, T, Tk, Hq, Hkv, scale, stream);
     case 64: return launch_bwd<64>(Q, ldq, K, ldk, V, ldv, O, ldo, dO, lddo, LSE2, delta_ws, summ_ws, dQ, lddq, dK, lddk, dV, lddv, row_lo, row_hi, shared_len, T, Tk, Hq, Hkv, scale, stream);
     default:
-      t1_set_error("t1_attn_bwd: unsupported head_dim %d (64 and 128 are built)", head_dim);
+      t1_set_error("t1_attn_bwd: unsupported head_dim %d (64, 80 and 128 are built)", head_dim);
       return T1_ERR_UNSUPPORTED;
   }
 }

@@ -93,19 +93,37 @@ struct SgParams {
   int pf_kblocks, pf_per_cta, pf_total, pf_grid;   // the next launch's unit split
   int pf_skip, pf_units;  // per CTA of the next launch: units [skip, skip + units) of its range
   int pf_swiglu, pf_half_n;
+  int pf_mode;            // 1: per-line prefetch.global.L2, 2: cp.async.bulk.prefetch.L2 per row segment
 };
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-// one 128-byte line per thread and unit: thread et owns weight row et of the slab
-__device__ __forceinline__ void sg_prefetch_next(const SgParams& p, int et) {
+// The prefetch warp walks the units [skip, skip + units) of every next-launch CTA it is responsible for.
+//   mode 1: one prefetch.global.L2 per 128-byte line (lane l takes rows l, l + 32, l + 64, l + 96 of the slab);
+//   mode 2: the row segments of consecutive units of one slab are contiguous along k, so lane l issues ONE
+//           cp.async.bulk.prefetch.L2 per (row, run of units) -- asynchronous, nothing for the warp to wait on.
+__device__ __forceinline__ void sg_prefetch_next(const SgParams& p, int lane) {
   for (int c = blockIdx.x; c < p.pf_grid; c += gridDim.x) {
     const int c0 = c * p.pf_per_cta;
     const int v0 = c0 + p.pf_skip;
     const int v1 = min(min(v0 + p.pf_units, c0 + p.pf_per_cta), p.pf_total);
-    for (int u = v0; u < v1; ++u) {
+    int u = v0;
+    while (u < v1) {
       const int slab = u / p.pf_kblocks, kb = u - slab * p.pf_kblocks;
-      const int row = p.pf_swiglu ? (et < 64 ? slab * 64 + et : p.pf_half_n + slab * 64 + et - 64) : slab * SG_BM + et;
-      if (row < p.pf_n) prefetch_l2(p.pf_w + (long long)row * p.pf_ldw + kb * SG_BK);
+      const int run = min(v1 - u, p.pf_kblocks - kb);            // units of this slab in the range
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int rr = lane + 32 * j;
+        const int row = p.pf_swiglu ? (rr < 64 ? slab * 64 + rr : p.pf_half_n + slab * 64 + rr - 64) : slab * SG_BM + rr;
+        if (row >= p.pf_n) continue;
+        const bf16* src = p.pf_w + (long long)row * p.pf_ldw + kb * SG_BK;
+        if (p.pf_mode == 2) {
+          const unsigned bytes = (unsigned)run * SG_BK * 2;
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+        } else {
+          for (int i = 0; i < run; ++i) prefetch_l2(src + i * SG_BK);
+        }
+      }
+      u += run;
     }
   }
 }
@@ -119,7 +137,7 @@ __device__ __forceinline__ unsigned long long gtimer() {
 }
 
 template <int MP>
-__global__ void __launch_bounds__(SG_THREADS, 1)
+__global__ void __launch_bounds__(SG_THREADS + 32, 1)
 stream_gemm_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CUtensorMap tma_x, SgParams p) {
   constexpr int X_BYTES = MP * SG_BK * 2;
   constexpr int STAGE_BYTES = SG_W_BYTES + X_BYTES;
@@ -253,10 +271,14 @@ stream_gemm_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_const
         u += kb1 - kb0;
       }
     }
+  } else if (warp_idx == 6) {
+    // ===================== L2 prefetch warp (launched only with a prefetch hint) =====================
+    // off the critical path: the producer / MMA / epilogue warps never wait for it, and it leaves without the final barrier
+    if (p.pf_w) sg_prefetch_next(p, lane);
+    return;
   } else {
     // ===================== epilogue (warps 2..5 = TMEM lane quadrants 2,3,0,1) =====================
     const int et = (warp_idx - 2) * 32 + lane;   // 0..127
-    if (p.pf_w) sg_prefetch_next(p, et);         // weights of the next GEMM -> L2 (independent of every dependency)
     pdl_wait();
     const int q = warp_idx & 3;
     const int r = q * 32 + lane;                 // weight row inside the slab == TMEM lane
@@ -514,7 +536,7 @@ stream_gemm_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_const
   if (threadIdx.x == 64 + 0) g_cta_t[2][blockIdx.x] = gtimer();
 #endif
   tc_fence_before();
-  __syncthreads();
+  asm volatile("bar.sync 2, %0;" ::"n"(SG_THREADS) : "memory");   // warps 0..5 (the prefetch warp has left)
   if (warp_idx == 1) {
     tc_fence_after();
     tmem_dealloc<TMEM_COLS>(tmem_base);
@@ -855,7 +877,7 @@ int launch_stream(const CUtensorMap& tw, const CUtensorMap& tx, SgParams p, int 
     }
     attr_set = true;
   }
-  cudaError_t e = t1_launch(stream_gemm_kernel<MP>, dim3(grid), dim3(SG_THREADS), (size_t)smem, stream, tw, tx, p);
+  cudaError_t e = t1_launch(stream_gemm_kernel<MP>, dim3(grid), dim3(SG_THREADS + (p.pf_w ? 32 : 0)), (size_t)smem, stream, tw, tx, p);
   if (e != cudaSuccess) {
     t1_set_error("t1_stream_gemm: launch failed: %s", cudaGetErrorString(e));
     return T1_ERR_CUDA;
@@ -1080,6 +1102,7 @@ static int stream_gemm_impl(const void* x, long long ldx, const void* W, long lo
           p.pf_units = (int)units;
           p.pf_swiglu = hint.swiglu;
           p.pf_half_n = nx.half_n;
+          p.pf_mode = env_int("T1_STREAM_PF_MODE", 2);
         }
       }
     }

@@ -119,14 +119,17 @@ class FlatParams:
 
 
 class ModelWeights:
-    """frozen (ViT) + train (merger + LLM) flat parameter sets."""
+    """frozen (ViT) + train (merger + LLM) flat parameter sets.  train_vit=True (the reference's default fix_vit=False,
+    main.py:46-49 / timer1_trainer.py:272-280): the ViT patch-embed and blocks live at the START of the trainable buffer
+    (their gradients are the last to become final in the backward) and `frozen` is empty."""
 
-    def __init__(self, cfg: ModelConfig, device="cuda", world_size: int = 1):
+    def __init__(self, cfg: ModelConfig, device="cuda", world_size: int = 1, train_vit: bool = False):
         self.cfg = cfg
+        self.train_vit = bool(train_vit)
         specs = param_specs(cfg)
-        self.frozen = FlatParams([s for s in specs if s.group == "vit"], device)
+        self.frozen = FlatParams([s for s in specs if s.group == "vit" and not train_vit], device)
         # pad so the flat trainable buffer splits evenly into world_size shards of whole 128-element blocks
-        self.train = FlatParams([s for s in specs if s.group != "vit"], device, pad_to=ALIGN * world_size * 4)
+        self.train = FlatParams([s for s in specs if s.group != "vit" or train_vit], device, pad_to=ALIGN * world_size * 4)
         self.kinds = {s.name: s.kind for s in specs}
 
     def get(self, name: str) -> torch.Tensor:
@@ -136,7 +139,7 @@ class ModelWeights:
     @torch.no_grad()
     def init_random(self, seed: int = 0, std: float = 0.02):
         """HF-style init (initializer_range 0.02, norm weights 1, biases N(0, std)) generated on the device."""
-        g = torch.Generator(device=self.frozen.buf.device).manual_seed(seed)
+        g = torch.Generator(device=self.train.buf.device).manual_seed(seed)
         for fp in (self.frozen, self.train):
             for sp in fp.specs:
                 v = fp[sp.name]
@@ -158,13 +161,13 @@ class ModelWeights:
         vi, ip = cfg.vit_intermediate, cfg.vit_inter_padded
         for i in range(cfg.vit_depth):
             p = f"visual.blocks.{i}.mlp."
-            w = self.frozen[p + "gate_up.weight"]
+            w = self.get(p + "gate_up.weight")
             w[vi:ip].zero_()
             w[ip + vi:].zero_()
-            b = self.frozen[p + "gate_up.bias"]
+            b = self.get(p + "gate_up.bias")
             b[vi:ip].zero_()
             b[ip + vi:].zero_()
-            self.frozen[p + "down_proj.weight"][:, vi:].zero_()
+            self.get(p + "down_proj.weight")[:, vi:].zero_()
 
     # ---- HF checkpoint-name mapping ----
     def _hf_slices(self):

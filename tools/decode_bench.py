@@ -56,6 +56,9 @@ def main():
     for (impl, pdl, stages, ctas), ov in zip(variants, overrides):
         run = config.RunConfig(num_generations=G, max_completion_length=C, beta=0.0, decode_impl=impl, decode_pdl=pdl)
         for k, v in (ov or {}).items():
+            if k == "env":          # environment switches read by the library at launch / capture time
+                os.environ.update({a: str(b) for a, b in v.items()})
+                continue
             assert hasattr(run, k), k
             setattr(run, k, v)
         if os.environ.get("T1_DECODE_FOLD"):
