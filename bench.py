@@ -64,6 +64,9 @@ def parse_args():
                     help="device: template completions are detokenised, parsed and scored on the GPU; host: regex parse on the host")
     ap.add_argument("--no-vit-prefetch", dest="vit_prefetch", action="store_false",
                     help="do not overlap the next step's frozen ViT blocks with this step's optimizer phase")
+    ap.add_argument("--train-vit", action="store_true",
+                    help="fix_vit=False (the reference's default, main.py:46-49; every shipped script passes --fix_vit true): the ViT "
+                         "patch-embed and blocks are trained too -- ViT-block backward, a separate reference-model tower, no ViT prefetch")
     ap.add_argument("--verify", default=None, metavar="OUT.pt",
                     help="numerical invariance check of the multi-GPU path instead of a benchmark: ONE optimizer step over a fixed "
                          "global batch of 8 teacher-forced prompt-groups dealt over the ranks; writes loss / grad-norm / strided "
@@ -559,7 +562,7 @@ def run_ours(args):
     if world == 1 and not args.no_gpu_reference and not args.ncu_range:
         gpu_ref = gpu_reference_leg(args)          # before this process allocates its 175 GB
     cfg = config.PRESETS[args.model]()
-    run = config.RunConfig(num_generations=args.group_size, max_completion_length=args.completion_len)
+    run = config.RunConfig(num_generations=args.group_size, max_completion_length=args.completion_len, fix_vit=not args.train_vit)
     if os.environ.get("T1_SIDE_CTAS"):
         run.side_ctas = int(os.environ["T1_SIDE_CTAS"])
     if os.environ.get("T1_DECODE_FOLD"):
@@ -567,7 +570,7 @@ def run_ours(args):
     if os.environ.get("T1_DECODE_CTAS"):
         run.decode_ctas = int(os.environ["T1_DECODE_CTAS"])
     G, C = run.num_generations, run.max_completion_length
-    mw = weights.ModelWeights(cfg, dev, world_size=world)
+    mw = weights.ModelWeights(cfg, dev, world_size=world, train_vit=args.train_vit)
     mw.init_random(seed=0)          # same weights on every rank (data parallel)
     eng = engine.Engine(cfg, mw, run, rank=rank, world_size=world, process_group=pg)
     NG = args.groups_per_step
@@ -721,7 +724,7 @@ def run_ours(args):
         "ms_per_step": round(ms_per_step, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
         "config": {"workload": workload_name(args), "prompt_tokens": P, "vision_tokens": (P - 120), "group_size": G, "groups_per_step": NG,
-                   "completion_len": C, "parallelism": f"dp{world}+zero2-sharded-adamw", "l2": "inputs larger than L2 (>=16 GB of weights streamed per pass)"},
+                   "completion_len": C, "fix_vit": not args.train_vit, "parallelism": f"dp{world}+zero2-sharded-adamw", "l2": "inputs larger than L2 (>=16 GB of weights streamed per pass)"},
         "clocks": clocks,
         "e2e": {"value": round(e2e_value, 4), "unit": UNIT, "h2d_bytes_per_step": int(sum(inp[1].numel() + inp[0].size * 4 for inp in inputs)), "input": "uint8 frames [2*slots, 3, 448, 448] from pinned host memory -> t1_video_patchify on the device", "d2h_bytes_per_step": int(NG * ((G * C * 4 if args.reward_route == "host" else 0) + 4) + 4),
                 "d2h": "per-group loss + grad norm" + (" + completion ids for the host reward parse" if args.reward_route == "host" else "; completions are detokenised and parsed on the device")},

@@ -13,16 +13,16 @@ pytestmark = pytest.mark.gpu
 
 
 
-def build(family="qwen2_5_vl", beta=0.04, use_grpo=False, G=4, C=12):
+def build(family="qwen2_5_vl", beta=0.04, use_grpo=False, G=4, C=12, fix_vit=True):
     from oracle import qwen_vl_oracle as O
     from time_r1_b200 import config, engine, weights
 
     cfg = config.toy(family)
     ocfg = O.default_cfg(**{k: v for k, v in cfg.to_dict().items() if k in O.default_cfg()})
     w_or = O.seeded_weights(ocfg, seed=7, std=0.05)
-    mw = weights.ModelWeights(cfg, "cuda")
+    mw = weights.ModelWeights(cfg, "cuda", train_vit=not fix_vit)
     mw.load_state_dict(w_or)
-    run = config.RunConfig(num_generations=G, max_completion_length=C, beta=beta, use_grpo=use_grpo, learning_rate=1e-3)
+    run = config.RunConfig(num_generations=G, max_completion_length=C, beta=beta, use_grpo=use_grpo, learning_rate=1e-3, fix_vit=fix_vit)
     eng = engine.Engine(cfg, mw, run)
     rng = np.random.default_rng(3)
     grid = [(2, 8, 12)]
@@ -158,6 +158,84 @@ def test_grpo_step_loss_and_gradients_match_oracle(family, use_grpo, beta):
         err = (g - g_ref).abs().max().item() / denom
         cos = torch.nn.functional.cosine_similarity(g.flatten(), g_ref.flatten(), dim=0).item()
         assert err < 0.08 and cos > 0.99, f"{k}: rel err {err:.3f}, cosine {cos:.4f}"
+
+
+@pytest.mark.parametrize("family,beta", [("qwen2_5_vl", 0.04), ("qwen2_vl", 0.04), ("qwen2_5_vl", 0.0)])
+def test_vit_block_gradients_match_oracle_with_fix_vit_false(family, beta):
+    """fix_vit=False (the reference default, main.py:46-49; timer1_trainer.py:272-280 leaves model.visual trainable): the ViT
+    patch-embed and every block receive gradients -- windowed + full attention backward at head_dim 80, RMSNorm / LayerNorm,
+    SwiGLU / QuickGELU MLP, rotary inverse, the padded MLP columns staying exactly zero -- against autograd on the fp32 oracle.
+    Two accumulated micro-steps check the accumulate path as well (gradient == 2 x the single-step gradient)."""
+    O, cfg, ocfg, w_or, eng, prompt, pix, ids, grid = build(family, beta=beta, fix_vit=False)
+    assert eng.w.frozen.numel == 0 and "visual.blocks.0.attn.qkv.weight" in eng.w.train
+    G, C = 4, 12
+    rng = np.random.default_rng(9)
+    comp = torch.from_numpy(rng.integers(10, 2000, (G, C))).int()
+    comp[1, 5] = cfg.eos_token_id
+    comp[1, 6:] = cfg.pad_token_id
+    rewards = rng.random((G, 2)).astype(np.float32)
+    with torch.no_grad():    # policy != reference INSIDE the tower: the reference pass must run its own (unperturbed) ViT
+        eng.w.train["visual.blocks.1.attn.proj.weight"].mul_(1.25)
+        eng.w.train["model.layers.1.mlp.down_proj.weight"].mul_(1.5)
+    out = eng.grpo_step(prompt, lambda c: rewards, completion_override=comp)
+    w_pol = {k: v.clone() for k, v in w_or.items()}
+    w_pol["visual.blocks.1.attn.proj.weight"] = (w_pol["visual.blocks.1.attn.proj.weight"].to(torch.bfloat16) * 1.25).float()
+    w_pol["model.layers.1.mlp.down_proj.weight"] = (w_pol["model.layers.1.mlp.down_proj.weight"].to(torch.bfloat16) * 1.5).float()
+    mlp = (["mlp.gate_proj.weight", "mlp.up_proj.bias", "mlp.down_proj.weight", "mlp.down_proj.bias"] if family == "qwen2_5_vl"
+           else ["mlp.fc1.weight", "mlp.fc1.bias", "mlp.fc2.weight", "mlp.fc2.bias", "norm1.bias", "norm2.bias"])
+    watch = ["visual.patch_embed.proj.weight", "visual.merger.mlp.0.weight", "model.layers.0.self_attn.q_proj.weight"]
+    for i in range(cfg.vit_depth):
+        watch += [f"visual.blocks.{i}.{n}" for n in ["norm1.weight", "norm2.weight", "attn.qkv.weight", "attn.qkv.bias",
+                                                     "attn.proj.weight", "attn.proj.bias"] + mlp]
+    for k in watch:
+        w_pol[k].requires_grad_(True)
+    lp, ent = O.score_completions(w_pol, ocfg, list(ids), comp.numpy(), pix, grid)
+    with torch.no_grad():
+        lp_ref, _ = O.score_completions(w_or, ocfg, list(ids), comp.numpy(), pix, grid)
+    mask = O.completion_mask(comp.long(), cfg.eos_token_id)
+    loss, metrics, adv = O.grpo_loss(lp, lp_ref, mask, torch.from_numpy(rewards), G, beta, entropy=ent.detach())
+    loss.backward()
+    assert abs(out["loss"].item() - loss.item()) < 2e-2 * max(1.0, abs(loss.item()))
+    if beta:
+        assert metrics["kl"] > 1e-4 and abs(out["stats"][1].item() - metrics["kl"]) < 2e-2 * max(1.0, metrics["kl"])
+        assert (out["ref_logp"].cpu() - lp_ref).abs().max().item() < 5e-2
+    from time_r1_b200.weights import ModelWeights
+    gw = ModelWeights.__new__(ModelWeights)
+    gw.cfg, gw.train, gw.frozen = cfg, eng.grads, eng.w.frozen
+    sd = {k: v.float().cpu().clone() for k, v in gw.export_state_dict().items()}
+    for k in watch:
+        g_ref = w_pol[k].grad
+        g = sd[k].reshape(g_ref.shape)
+        err = (g - g_ref).abs().max().item() / (g_ref.abs().max().item() + 1e-12)
+        cos = torch.nn.functional.cosine_similarity(g.flatten(), g_ref.flatten(), dim=0).item()
+        assert err < 0.08 and cos > 0.99, f"{k}: rel err {err:.3f}, cosine {cos:.4f}"
+    if family == "qwen2_5_vl":      # zero-padded MLP rows / columns (3420 -> 3456 in the 7B tower) never receive a gradient
+        vi, ip = cfg.vit_intermediate, cfg.vit_inter_padded
+        assert ip > vi
+        gu, dn = eng.grads["visual.blocks.0.mlp.gate_up.weight"], eng.grads["visual.blocks.0.mlp.down_proj.weight"]
+        assert gu[vi:ip].abs().max().item() == 0 and gu[ip + vi:].abs().max().item() == 0 and dn[:, vi:].abs().max().item() == 0
+        assert eng.grads["visual.blocks.0.mlp.gate_up.bias"][vi:ip].abs().max().item() == 0
+    # accumulation: a second identical micro-step doubles every gradient
+    g1 = eng.grads.buf.float().clone()
+    eng.grpo_step(prompt, lambda c: rewards, completion_override=comp)
+    g2 = eng.grads.buf.float()
+    assert torch.allclose(g2, 2 * g1, rtol=2e-2, atol=2e-2 * g1.abs().max().item())
+    # the optimizer moves the tower, the reference copy keeps the initial one
+    before = eng.w.train["visual.blocks.0.attn.qkv.weight"].clone()
+    eng.optimizer_step(lr=1e-3)
+    torch.cuda.synchronize()
+    assert not torch.equal(eng.w.train["visual.blocks.0.attn.qkv.weight"], before)
+    if beta:
+        assert torch.equal(eng.ref["visual.blocks.0.attn.qkv.weight"], before)
+
+
+def test_fix_vit_mismatch_between_run_and_weights_raises():
+    from time_r1_b200 import config, engine, weights
+
+    cfg = config.toy()
+    mw = weights.ModelWeights(cfg, "cuda")
+    with pytest.raises(ValueError, match="train_vit"):
+        engine.Engine(cfg, mw, config.RunConfig(num_generations=2, max_completion_length=4, fix_vit=False))
 
 
 def test_optimizer_step_moves_weights_like_torch_adamw():

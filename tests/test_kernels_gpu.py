@@ -256,7 +256,7 @@ def test_attention_forward_tcgen05(kind, T, P, C, Hq, Hkv):
 
 @pytest.mark.parametrize("kind,T,P,C,Hq,Hkv,hd", [
     ("causal", 200, 0, 0, 4, 2, 128), ("packed", 531, 203, 41, 14, 2, 128), ("packed", 300, 100, 50, 2, 1, 64),
-    ("window", 300, 0, 0, 2, 2, 128),
+    ("window", 300, 0, 0, 2, 2, 128), ("window", 1000, 0, 0, 16, 16, 80), ("causal", 130, 0, 0, 2, 2, 80),
 ])
 def test_attention_backward(kind, T, P, C, Hq, Hkv, hd):
     from time_r1_b200 import ops

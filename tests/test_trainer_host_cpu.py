@@ -230,13 +230,32 @@ def test_metric_funcs_are_computed_from_each_groups_own_completions(tmp_path, mo
     assert tr.state.log_history[0]["metrics/think_chars"] == pytest.approx(want)
 
 
-def test_fix_vit_false_is_an_error_not_a_silent_freeze():
+def test_fix_vit_false_moves_the_vit_into_the_trainable_buffer():
+    """fix_vit=False is the reference default (main.py:46-49; timer1_trainer.py:272-280 then leaves model.visual trainable): the
+    ViT tensors join the trainable flat buffer (they get gradients, AdamW state and ZeRO shards like everything else), ahead of
+    the merger so that the backward still finishes the buffer from its end to its start; checkpoints round-trip unchanged."""
     import inspect
 
-    from time_r1_b200 import trainer
+    import torch
+
+    from time_r1_b200 import config, trainer, weights
 
     src = inspect.getsource(trainer.TimeR1_Trainer.__init__)
-    assert "raise NotImplementedError(\"fix_vit=False" in src and "ViT blocks stay frozen (only merger + LLM train)\")" not in src
+    assert "fix_vit=fix_vit" in src and "train_vit=not fix_vit" in src and "NotImplementedError(\"fix_vit" not in src
+    for fam in ("qwen2_5_vl", "qwen2_vl"):
+        cfg = config.toy(fam)
+        frozen = weights.ModelWeights(cfg, "cpu", world_size=2)
+        train = weights.ModelWeights(cfg, "cpu", world_size=2, train_vit=True)
+        assert train.frozen.numel == 0 and not train.frozen.specs
+        vit_names = [s.name for s in frozen.frozen.specs]
+        assert vit_names and all(n in train.train and n not in frozen.train for n in vit_names)
+        lay = train.train.layout
+        assert max(lay[n][0] for n in vit_names) < lay["visual.merger.ln_q.weight"][0] < lay["model.embed_tokens.weight"][0]
+        assert train.train.numel % (weights.ALIGN * 2 * 4) == 0
+        frozen.init_random(seed=3)
+        train.load_state_dict(frozen.export_state_dict())
+        a, b = frozen.export_state_dict(), train.export_state_dict()
+        assert a.keys() == b.keys() and all(torch.equal(a[k], b[k]) for k in a)
 
 
 def test_global_batches_are_dealt_evenly_and_keep_their_content():

@@ -70,6 +70,7 @@ class ScoreState:
     k_qkv: list | None = None   # per-layer post-rope q, k, v [Tp, qkv_dim], attention output [Tp, Hq*hd] and LSE [Hq, Tp]
     k_attn: list | None = None  #   kept from the forward passes: the backward then also skips the qkv GEMM, rope and the
     k_lse: list | None = None   #   attention forward of its recompute
+    vit_keep: dict | None = None  # fix_vit=False: what Engine.vit_blocks(keep=...) recorded for the ViT-block backward
 
 
 class Engine:
@@ -82,6 +83,9 @@ class Engine:
         if not torch.cuda.is_available():
             raise RuntimeError("time_r1_b200.Engine needs a CUDA device (sm_100a); there is no CPU fallback")
         self.cfg, self.w, self.run = cfg, weights, run
+        if bool(getattr(weights, "train_vit", False)) != (not run.fix_vit):
+            raise ValueError(f"RunConfig.fix_vit={run.fix_vit} needs ModelWeights(train_vit={not run.fix_vit}): the ViT blocks live in the "
+                             "trainable flat buffer exactly when they receive gradients")
         self.dev = weights.train.buf.device
         self.rank, self.world, self.pg = rank, world_size, process_group
         self.ref: FlatParams | None = weights.train.clone() if (with_ref and run.beta != 0.0) else None
@@ -269,9 +273,12 @@ class Engine:
     # ------------------------------------------------------------------------------------------
     # ViT
     # ------------------------------------------------------------------------------------------
-    def vit_blocks(self, pixel_values, grid_thw, frames=None) -> tuple[torch.Tensor, torch.Tensor, indexing.VisionPlan]:
+    def vit_blocks(self, pixel_values, grid_thw, frames=None, wset: str = "policy",
+                   keep: dict | None = None) -> tuple[torch.Tensor, torch.Tensor, indexing.VisionPlan]:
         """Patch-embed + all vision blocks. Returns (x, pending_delta, plan): the merger's input is x + pending_delta
-        (the last block's MLP output, whose residual add is fused into the merger norm)."""
+        (the last block's MLP output, whose residual add is fused into the merger norm).
+        keep (fix_vit=False): receives what _vit_backward needs -- the window-ordered pixel rows, the rotary tables, the window /
+        full-attention row bounds and every block's input (the checkpoints the block recompute starts from)."""
         cfg = self.cfg
         plan = indexing.vision_plan(cfg, grid_thw)
         N, vd, H, hd = plan.n_patches, cfg.vit_hidden, cfg.vit_heads, cfg.vit_head_dim
@@ -284,7 +291,8 @@ class Engine:
         else:
             assert pixel_values.shape == (N, cfg.patch_dim) and pixel_values.dtype == F32
             pix = ops.gather_rows_f32(pixel_values, perm)                   # cast + window-order permutation
-        x = ops.gemm(pix, self.w.get("visual.patch_embed.proj.weight"))     # Conv3d == GEMM
+        g = lambda name: self.p(name, wset)
+        x = ops.gemm(pix, g("visual.patch_embed.proj.weight"))              # Conv3d == GEMM
         cos, sin = ops.rope_table(self._i32(plan.pos_hw), self.axis_vit, self.inv_freq_vit)
         win_lo, win_hi = self._i32(plan.win_lo), self._i32(plan.win_hi)
         full_lo, full_hi = self._i32(plan.full_lo), self._i32(plan.full_hi)
@@ -302,13 +310,16 @@ class Engine:
         attn = torch.empty((N, vd), device=self.dev, dtype=BF16)
         proj = torch.empty((N, vd), device=self.dev, dtype=BF16)
         down = torch.empty((N, vd), device=self.dev, dtype=BF16)
+        if keep is not None:
+            keep.update(pix=pix, cos=cos, sin=sin, win=(win_lo, win_hi), full=(full_lo, full_hi), ckpt=[])
         for i in range(cfg.vit_depth):
             pre = f"visual.blocks.{i}."
-            g = self.w.get
             if cfg.is_q25:
                 ops.rmsnorm(x, g(pre + "norm1.weight"), 1e-6, delta=delta, out=h)
             else:
                 ops.layernorm(x, g(pre + "norm1.weight"), g(pre + "norm1.bias"), 1e-6, delta=delta, out=h)
+            if keep is not None:
+                keep["ckpt"].append(x.clone())                              # x now holds this block's input (delta added in place)
             ops.gemm(h, g(pre + "attn.qkv.weight"), out=qkv, bias=g(pre + "attn.qkv.bias"))
             ops.rope_apply(qkv, 0, 2 * H, hd, cos, sin)                     # q and k heads are contiguous
             full = (not cfg.is_q25) or (i in cfg.fullatt_block_indexes)
@@ -417,9 +428,18 @@ class Engine:
         return dict(kv_prefix=kv, h_last=h_last, event=ev, P=P, ref=True)
 
     def vit_forward(self, prompt: Prompt, wset: str = "policy"):
-        x, delta, plan = self.vit_blocks(prompt.pixel_values, prompt.grid_thw, frames=prompt.frames)
+        x, delta, plan = self.vit_blocks(prompt.pixel_values, prompt.grid_thw, frames=prompt.frames,
+                                         wset=wset if not self.run.fix_vit else "policy")
         emb = self.merger(x, delta, plan, wset)
         return emb, x, plan
+
+    def _ref_embeds(self, prompt: Prompt, x_vit: torch.Tensor, plan: indexing.VisionPlan) -> torch.Tensor:
+        """Vision embeddings under the REFERENCE model (timer1_trainer.py:613-632).  Frozen ViT blocks (--fix_vit) are shared
+        with the policy, so only the merger is run again; with fix_vit=False the reference keeps its own (initial) tower."""
+        if self.run.fix_vit:
+            return self.merger(x_vit, None, plan, "ref")
+        x, delta, _ = self.vit_blocks(prompt.pixel_values, prompt.grid_thw, frames=prompt.frames, wset="ref")
+        return self.merger(x, delta, plan, "ref")
 
     # ------------------------------------------------------------------------------------------
     # LLM forward over a packed token axis
@@ -944,7 +964,7 @@ class Engine:
         return lp, ent, lse
 
     def score(self, prompt: Prompt, completion_ids: torch.Tensor, vision_embeds: torch.Tensor, wset: str = "policy",
-              save: bool = False, x_vit=None, plan=None, prefill=None):
+              save: bool = False, x_vit=None, plan=None, prefill=None, vit_keep=None):
         """Returns (logp [G, C], entropy [G, C], state-or-None)."""
         si = self._score_inputs(prompt, completion_ids)
         G, C, R = si["G"], si["C"], si["R"]
@@ -985,7 +1005,7 @@ class Engine:
         if save:
             state = ScoreState(P=si["P"], G=G, C=C, Tp=si["Tp"], ckpt=ckpt, cos=cos, sin=sin, lo=si["lo"], hi=si["hi"],
                                ids_packed=si["ids_packed"], text_scatter_idx=si["text_idx"], vision_rows=si["vision_rows"],
-                               logit_rows=si["logit_rows"], targets=si["targets"], hsel=hsel, lse=lse, x_vit=x_vit, plan=plan,
+                               logit_rows=si["logit_rows"], targets=si["targets"], hsel=hsel, lse=lse, x_vit=x_vit, plan=plan, vit_keep=vit_keep,
                                **({("gu" if k == "gu" else "k_" + k): v for k, v in keep_full.items()} if keep_full else {}))
         return lp[:R].view(G, C), ent[:R].view(G, C), state
 
@@ -1025,8 +1045,9 @@ class Engine:
     def _backward(self, st: ScoreState, dlogp: torch.Tensor):
         cfg = self.cfg
         off = lambda name: self.grads.layout[name][0]
-        if not self.run.fix_vit:
-            raise NotImplementedError("ViT-block gradients (fix_vit=False) are not built; every reference script sets --fix_vit true")
+        train_vit = not self.run.fix_vit
+        if train_vit and st.vit_keep is None and st.vision_rows.numel() > 0:
+            raise RuntimeError("fix_vit=False: the scoring state carries no ViT checkpoints (vit_blocks(keep=...) -> score(vit_keep=...))")
         acc = not self.grad_fresh
         L, Hq, Hkv, hd, I, D = cfg.num_hidden_layers, cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim, cfg.intermediate_size, cfg.hidden_size
         qd, kd = Hq * hd, Hkv * hd
@@ -1138,12 +1159,19 @@ class Engine:
         ops.scatter_rows(dx, st.text_scatter_idx, self._gview(embed_name), accumulate=True)
         if st.vision_rows.numel() > 0:
             dve = ops.gather_rows(dx, st.vision_rows)                       # [Nv, D] in original merged-token order
-            self._merger_backward(st, dve, acc)
-        # the buckets that only became final here (embedding table, merger) are reduced by optimizer_step on the full-speed
-        # communicator: nothing is left to hide them behind
+            dx_vit = self._merger_backward(st, dve, acc, need_dx=train_vit)
+            if train_vit:
+                if not cfg.tie_word_embeddings:
+                    self._reduce_ready(off("visual.merger.ln_q.weight"))
+                self._vit_backward(st, dx_vit, acc)
+        elif not acc:
+            self.grads.buf[:off(embed_name)].zero_()                        # no vision tokens: nothing wrote the tower's gradients
+        # the buckets that only became final here (embedding table, merger; with fix_vit=False the first ViT blocks) are reduced
+        # by optimizer_step on the full-speed communicator: nothing is left to hide them behind
         self.grad_fresh = False
 
-    def _merger_backward(self, st: ScoreState, dve: torch.Tensor, acc: bool):
+    def _merger_backward(self, st: ScoreState, dve: torch.Tensor, acc: bool, need_dx: bool = False):
+        """PatchMerger backward; returns d loss / d (final ViT stream) [N, vit_hidden] in window order when need_dx."""
         cfg = self.cfg
         plan, x_vit = st.plan, st.x_vit
         keep: dict = {}
@@ -1167,11 +1195,107 @@ class Engine:
         dy4 = self._dgrad(da1, W0)
         f32s.zero_()
         if cfg.is_q25:
-            ops.rmsnorm_bwd(dy4.view(N, vd), x_vit, self.p("visual.merger.ln_q.weight"), 1e-6, f32s[:vd])
-        else:      # Qwen2-VL: LayerNorm(eps 1e-6) with bias (HF modeling_qwen2_vl.py:313-326); the ViT output needs no gradient
-            ops.layernorm_bwd(dy4.view(N, vd), x_vit, self.p("visual.merger.ln_q.weight"), 1e-6, f32s[:vd], f32s[vd:2 * vd], need_dx=False)
+            dxv = ops.rmsnorm_bwd(dy4.view(N, vd), x_vit, self.p("visual.merger.ln_q.weight"), 1e-6, f32s[:vd])
+        else:      # Qwen2-VL: LayerNorm(eps 1e-6) with bias (HF modeling_qwen2_vl.py:313-326); frozen ViT blocks need no dx
+            dxv = ops.layernorm_bwd(dy4.view(N, vd), x_vit, self.p("visual.merger.ln_q.weight"), 1e-6, f32s[:vd], f32s[vd:2 * vd],
+                                    need_dx=need_dx)
             self._small_grad(f32s[vd:2 * vd], "visual.merger.ln_q.bias", acc)
         self._small_grad(f32s[:vd], "visual.merger.ln_q.weight", acc)
+        return dxv if need_dx else None
+
+    def _vit_backward(self, st: ScoreState, dx: torch.Tensor, acc: bool):
+        """ViT blocks + patch-embed backward (fix_vit=False, the reference's default: main.py:46-49, timer1_trainer.py:272-280
+        leaves model.visual trainable).  dx [N, vit_hidden]: gradient of the final ViT stream, window order.  Every block is
+        recomputed from its checkpointed input (gradient checkpointing, train_rl.sh:32) and differentiated in place:
+        HF Q25:281-300 (block), Q25:244-261 (attention, non-causal inside [lo, hi)), Q25:108-121 (SwiGLU MLP) /
+        Q2:  QuickGELU MLP with LayerNorm."""
+        cfg, kp, plan = self.cfg, st.vit_keep, st.plan
+        q25 = cfg.is_q25
+        N, vd, H, hd = plan.n_patches, cfg.vit_hidden, cfg.vit_heads, cfg.vit_head_dim
+        iw = cfg.vit_inter_padded if q25 else cfg.vit_intermediate
+        scale = hd ** -0.5
+        dev = self.dev
+        off = lambda name: self.grads.layout[name][0]
+        cos, sin = kp["cos"], kp["sin"]
+        e = lambda *shape: torch.empty(shape, device=dev, dtype=BF16)
+        h, qkv, attn, proj, xm, h2 = e(N, vd), e(N, 3 * vd), e(N, vd), e(N, vd), e(N, vd), e(N, vd)
+        pre_act = e(N, 2 * iw) if q25 else e(N, iw)          # gate_up projection (Q2.5) / fc1 output (Q2)
+        act = e(N, iw)
+        dqkv = e(N, 3 * vd)
+        lse = torch.empty((H, N), device=dev, dtype=F32)
+        f32s = torch.zeros(max(3 * vd, 2 * iw), device=dev, dtype=F32)
+        f32b = torch.zeros(vd, device=dev, dtype=F32)
+
+        def bias_grad(dy, name):
+            f32s.zero_()
+            n = dy.shape[1]
+            ops.colsum(dy, f32s[:n])
+            self._small_grad(f32s[:n], name, acc)
+
+        def norm_fwd(x, name, delta=None, out=None, x_out=None):
+            if q25:
+                return ops.rmsnorm(x, self.p(name + ".weight"), 1e-6, delta=delta, out=out, x_out=x_out)
+            return ops.layernorm(x, self.p(name + ".weight"), self.p(name + ".bias"), 1e-6, delta=delta, out=out, x_out=x_out)
+
+        def norm_bwd(dy, x, name, dres, out):
+            """out = dres + d norm(x) / dx ; accumulates the norm's weight (and bias) gradient."""
+            f32s.zero_()
+            if q25:
+                r = ops.rmsnorm_bwd(dy, x, self.p(name + ".weight"), 1e-6, f32s[:vd], dres=dres, out=out)
+            else:
+                f32b.zero_()
+                r = ops.layernorm_bwd(dy, x, self.p(name + ".weight"), 1e-6, f32s[:vd], f32b, out=out)
+                ops.add_(r, dres)
+                self._small_grad(f32b, name + ".bias", acc)
+            self._small_grad(f32s[:vd], name + ".weight", acc)
+            return r
+
+        for i in range(cfg.vit_depth - 1, -1, -1):
+            pre = f"visual.blocks.{i}."
+            x_in = kp["ckpt"][i]
+            kp["ckpt"][i] = None
+            w_up, w_dn = ("mlp.gate_up", "mlp.down_proj") if q25 else ("mlp.fc1", "mlp.fc2")
+            Wqkv, Wp = self.p(pre + "attn.qkv.weight"), self.p(pre + "attn.proj.weight")
+            Wu, Wd = self.p(pre + w_up + ".weight"), self.p(pre + w_dn + ".weight")
+            # ---- recompute the block from its input ----
+            norm_fwd(x_in, pre + "norm1", out=h)
+            ops.gemm(h, Wqkv, out=qkv, bias=self.p(pre + "attn.qkv.bias"))
+            ops.rope_apply(qkv, 0, 2 * H, hd, cos, sin)
+            full = (not q25) or (i in cfg.fullatt_block_indexes)
+            lo, hi = kp["full"] if full else kp["win"]
+            q, k, v = qkv[:, :vd], qkv[:, vd:2 * vd], qkv[:, 2 * vd:]
+            ops.attn_fwd(q, k, v, lo, hi, 0, H, H, hd, scale, out=attn, lse=lse)
+            ops.gemm(attn, Wp, out=proj, bias=self.p(pre + "attn.proj.bias"))
+            norm_fwd(x_in, pre + "norm2", delta=proj, out=h2, x_out=xm)
+            if q25:
+                ops.gemm_swiglu(h2, Wu, bias=self.p(pre + w_up + ".bias"), out=act, gate_up_out=pre_act)
+            else:
+                ops.gemm(h2, Wu, out=pre_act, bias=self.p(pre + w_up + ".bias"))
+                ops.act(pre_act, 1, out=act)
+            # ---- MLP backward ----
+            self._wgrad(dx, act, pre + w_dn + ".weight", acc)
+            bias_grad(dx, pre + w_dn + ".bias")
+            dact = self._dgrad(dx, Wd, out=act)
+            dpre = ops.swiglu_bwd(dact, pre_act, out=pre_act) if q25 else ops.act_bwd(dact, pre_act, 1, out=pre_act)
+            self._wgrad(dpre, h2, pre + w_up + ".weight", acc)
+            bias_grad(dpre, pre + w_up + ".bias")
+            dh2 = self._dgrad(dpre, Wu, out=h2)
+            dxm = norm_bwd(dh2, xm, pre + "norm2", dres=dx, out=proj)
+            # ---- attention backward (dxm is also the gradient of the projection output) ----
+            self._wgrad(dxm, attn, pre + "attn.proj.weight", acc)
+            bias_grad(dxm, pre + "attn.proj.bias")
+            dattn = self._dgrad(dxm, Wp)
+            ops.attn_bwd(q, k, v, attn, dattn, lse, lo, hi, 0, H, H, hd, scale, dqkv[:, :vd], dqkv[:, vd:2 * vd], dqkv[:, 2 * vd:])
+            del dattn
+            ops.rope_apply(dqkv, 0, 2 * H, hd, cos, sin, inverse=True)
+            bias_grad(dqkv, pre + "attn.qkv.bias")
+            self._wgrad(dqkv, h, pre + "attn.qkv.weight", acc)
+            dh = self._dgrad(dqkv, Wqkv, out=h)
+            dx = norm_bwd(dh, x_in, pre + "norm1", dres=dxm, out=xm).clone()     # xm is overwritten by the next recompute
+            if not cfg.tie_word_embeddings:
+                self._reduce_ready(off(pre + "norm1.weight"))                # block i is complete: everything above it is final
+        # ---- patch-embed (Conv3d == GEMM, no bias): dW = dx^T pixels ----
+        self._wgrad(dx, kp["pix"], "visual.patch_embed.proj.weight", acc)
 
     # ------------------------------------------------------------------------------------------
     # optimizer: global-norm clip + AdamW on this rank's shard of the flat buffer (ZeRO-2 semantics)
@@ -1271,16 +1395,20 @@ class Engine:
 
         mark("start")
         vit = []
+        vkeeps = []
         if vit_prefetch is not None:
             assert vit_prefetch["n"] == len(prompts)
             torch.cuda.current_stream().wait_event(vit_prefetch["event"])
         for pi, prompt in enumerate(prompts):
+            vkeep = None if run.fix_vit else {}
             if vit_prefetch is not None:
+                assert run.fix_vit, "prefetch_vit runs FROZEN blocks only"
                 x_vit, delta, plan = vit_prefetch["results"][pi]
             else:
-                x_vit, delta, plan = self.vit_blocks(prompt.pixel_values, prompt.grid_thw, frames=prompt.frames)
+                x_vit, delta, plan = self.vit_blocks(prompt.pixel_values, prompt.grid_thw, frames=prompt.frames, keep=vkeep)
             emb = self.merger(x_vit, delta, plan, "policy")                 # x_vit now holds the final ViT stream
             vit.append((emb, x_vit, plan))
+            vkeeps.append(vkeep)
         mark("vit")
         prefills = [None] * len(prompts)
         ref_handles = [None] * len(prompts)
@@ -1288,7 +1416,7 @@ class Engine:
                        and cfg.head_dim == 128 and self._decode_impl() == "stream")
         def launch_ref_prefills():
             for gi, (prompt, (emb, x_vit, plan)) in enumerate(zip(prompts, vit)):
-                ref_handles[gi] = self.ref_prefill_async(prompt, self.merger(x_vit, None, plan, "ref"), G, C)
+                ref_handles[gi] = self.ref_prefill_async(prompt, self._ref_embeds(prompt, x_vit, plan), G, C)
 
         if completion_overrides is None:
             reuse = run.reuse_prefill and cfg.head_dim == 128
@@ -1307,7 +1435,9 @@ class Engine:
         outs = []
         for gi, (prompt, reward_fn, comp, (emb, x_vit, plan)) in enumerate(zip(prompts, reward_fns, comps, vit)):
             mask, lengths = ops.eos_mask(comp, cfg.eos_token_id)
-            logp, ent, st = self.score(prompt, comp, emb, "policy", save=True, x_vit=x_vit, plan=plan, prefill=prefills[gi])
+            logp, ent, st = self.score(prompt, comp, emb, "policy", save=True, x_vit=x_vit, plan=plan, prefill=prefills[gi],
+                                       vit_keep=vkeeps[gi])
+            vkeeps[gi] = None
             prefills[gi] = None
             mark("score_policy")
             ref_logp = None
@@ -1318,7 +1448,7 @@ class Engine:
                     ref_logp, _, _ = self.score(prompt, comp, None, "ref", prefill=ref_handles[gi])
                     ref_handles[gi] = None
                 else:
-                    emb_ref = self.merger(x_vit, None, plan, "ref")
+                    emb_ref = self._ref_embeds(prompt, x_vit, plan)
                     ref_logp, _, _ = self.score(prompt, comp, emb_ref, "ref")
             mark("score_ref")
             on_device = getattr(reward_fn, "device", None)

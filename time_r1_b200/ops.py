@@ -255,11 +255,14 @@ def rmsnorm_bwd(dy, x, w, eps, dw_f32, dres=None, out=None):
     return out
 
 
-def layernorm_bwd(dy, x, w, eps, dw_f32, db_f32, need_dx=True):
-    """LayerNorm backward (Qwen2-VL merger): dw_f32 / db_f32 accumulate; returns dx (or None when need_dx is False)."""
+def layernorm_bwd(dy, x, w, eps, dw_f32, db_f32, need_dx=True, out=None):
+    """LayerNorm backward (Qwen2-VL merger and ViT blocks): dw_f32 / db_f32 accumulate; returns dx (or None when need_dx is False)."""
     T, D = x.shape
     _chk(dy, BF16, "dy"); _chk(x, BF16, "x")
-    out = torch.empty_like(x) if need_dx else None
+    if need_dx and out is None:
+        out = torch.empty_like(x)
+    if not need_dx:
+        out = None
     call("t1_layernorm_bwd", ptr(dy), ptr(x), ptr(w), ptr(out), ptr(dw_f32), ptr(db_f32), T, D, float(eps), stream_ptr())
     return out
 

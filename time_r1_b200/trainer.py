@@ -211,14 +211,19 @@ class TimeR1_Trainer:
         lib.load()
 
         # ---- model ----
+        # fix_vit (main.py:46-49, default False; every shipped script passes true): false leaves model.visual trainable
+        # (timer1_trainer.py:272-280) -> the ViT patch-embed and blocks join the trainable flat buffer and receive gradients
+        fix_vit = bool(getattr(a, "fix_vit", False))
         if isinstance(model, tuple):
             self.model_cfg, self.weights = model
+            if bool(getattr(self.weights, "train_vit", False)) != (not fix_vit):
+                raise ValueError(f"fix_vit={fix_vit} needs a (ModelConfig, ModelWeights) pair built with train_vit={not fix_vit}")
         elif isinstance(model, str) and model.startswith("random:"):
             self.model_cfg = PRESETS[model.split(":", 1)[1]]()
-            self.weights = _weights.ModelWeights(self.model_cfg, self.device, world_size=self.world)
+            self.weights = _weights.ModelWeights(self.model_cfg, self.device, world_size=self.world, train_vit=not fix_vit)
             self.weights.init_random(seed=getattr(a, "seed", 42))
         elif isinstance(model, str):
-            self.model_cfg, self.weights = load_checkpoint(model, self.device, self.world)
+            self.model_cfg, self.weights = load_checkpoint(model, self.device, self.world, train_vit=not fix_vit)
             if self.processing_class is None:
                 try:
                     from transformers import AutoProcessor
@@ -234,12 +239,7 @@ class TimeR1_Trainer:
             use_grpo=self.use_grpo, learning_rate=a.learning_rate, adam_beta1=getattr(a, "adam_beta1", 0.9),
             adam_beta2=getattr(a, "adam_beta2", 0.999), adam_eps=getattr(a, "adam_epsilon", 1e-8),
             weight_decay=getattr(a, "weight_decay", 0.0), max_grad_norm=getattr(a, "max_grad_norm", 1.0),
-            gradient_accumulation_steps=a.gradient_accumulation_steps, fix_vit=True, seed=getattr(a, "seed", 42))
-        if not getattr(a, "fix_vit", False):
-            # the reference default is fix_vit=False (main.py:46-49) but every shipped script passes --fix_vit true; ViT-block
-            # gradients are not built, and silently freezing the tower would train a different parameter set
-            raise NotImplementedError("fix_vit=False (ViT-block gradients) is not built: pass --fix_vit true as every reference "
-                                      "script does (scripts/posttrain/train_rl.sh:34); merger + LLM train, ViT blocks stay frozen")
+            gradient_accumulation_steps=a.gradient_accumulation_steps, fix_vit=fix_vit, seed=getattr(a, "seed", 42))
         if getattr(a, "deepspeed", None) and self.rank == 0:
             print(f"[time_r1_b200] note: --deepspeed {a.deepspeed} is accepted for CLI compatibility and NOT applied: parameters and "
                   "gradients are replicated bf16, fp32 master weights + AdamW state are sharded 1/world per rank in HBM (ZeRO-2 "
@@ -799,10 +799,10 @@ def read_state_dict(path: str) -> dict:
     return {k.replace("model.visual.", "visual.").replace("model.language_model.", "model."): v for k, v in sd.items()}
 
 
-def load_checkpoint(path: str, device, world_size: int = 1):
+def load_checkpoint(path: str, device, world_size: int = 1, train_vit: bool = False):
     from .weights import ModelWeights
 
     cfg = read_checkpoint_config(path)
-    w = ModelWeights(cfg, device, world_size=world_size)
+    w = ModelWeights(cfg, device, world_size=world_size, train_vit=train_vit)
     w.load_state_dict(read_state_dict(path))
     return cfg, w
