@@ -81,6 +81,29 @@ def test_greedy_rollout_follows_oracle_argmax():
         assert row[tok] >= row.max() - 0.05 * (row.max() - row.min()), f"token {c} is not a near-argmax"
 
 
+def test_decode_attention_forms_roll_out_the_same_tokens():
+    """RunConfig.decode_attn: "cluster", "wide" and "auto" (cluster below decode_attn_wide_min_prompt prompt tokens, wide from
+    there on) are the same arithmetic up to the merge order of the split-KV partials: greedy rollouts agree, and "auto" takes
+    the form its threshold says."""
+    import dataclasses
+
+    from time_r1_b200 import engine
+
+    O, cfg, ocfg, w_or, eng, prompt, pix, ids, grid = build(beta=0.0)
+    G, C = 4, 10
+    emb, _, _ = eng.vit_forward(prompt)
+    outs, forms = {}, {}
+    for name, over in (("cluster", dict(decode_attn="cluster")), ("wide", dict(decode_attn="wide")),
+                       ("auto_short", dict(decode_attn="auto", decode_attn_wide_min_prompt=10 ** 6)),
+                       ("auto_long", dict(decode_attn="auto", decode_attn_wide_min_prompt=16))):
+        e2 = engine.Engine(cfg, eng.w, dataclasses.replace(eng.run, **over), with_ref=False)
+        outs[name] = e2.rollout(prompt, emb, G, C, temperature=0.0, top_k=0, seed=1).cpu()
+        forms[name] = e2._last_decode_state["attn_form"]
+    assert forms == dict(cluster="cluster", wide="wide", auto_short="cluster", auto_long="wide")
+    for name in ("wide", "auto_short", "auto_long"):
+        assert torch.equal(outs[name], outs["cluster"]), name
+
+
 def test_sampled_rollout_and_decode_logits_consistency():
     """Sampled tokens scored by the packed scoring pass must have the log-probs the decode path sampled from:
     decode (prefix-shared KV + skinny GEMMs) and scoring (packed tcgen05 path) are two routes to the same logits."""

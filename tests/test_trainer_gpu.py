@@ -91,6 +91,35 @@ def test_trainer_runs_like_main_py(tmp_path):
     assert hf["architectures"] == ["Qwen2_5_VLForConditionalGeneration"]
 
 
+def test_trainer_with_fix_vit_false_trains_and_round_trips_the_tower(tmp_path):
+    """--fix_vit false (main.py:46-49 default): the trainer builds / accepts train_vit weights, the ViT tensors move under AdamW,
+    the reference copy keeps the initial tower, and the checkpoint reloads (into either layout) bit-equal."""
+    from src.time_r1 import TimeR1_Trainer
+    from time_r1_b200 import config, rewards, weights
+    from time_r1_b200.trainer import GRPOArguments, load_checkpoint
+
+    cfg = config.toy()
+    mw = weights.ModelWeights(cfg, "cuda", train_vit=True)
+    mw.init_random(seed=1, std=0.05)
+    args = GRPOArguments(output_dir=str(tmp_path), num_generations=4, max_completion_length=6, temperature=1.0, beta=0.04,
+                         learning_rate=1e-3, gradient_accumulation_steps=2, max_steps=2, logging_steps=1, fix_vit=False, save_strategy="no")
+    with pytest.raises(ValueError, match="train_vit"):
+        TimeR1_Trainer(model=(cfg, weights.ModelWeights(cfg, "cuda")), reward_funcs=[rewards.format_reward], args=args,
+                       train_dataset=make_dataset(cfg), processing_class=StubTokenizer())
+    tr = TimeR1_Trainer(model=(cfg, mw), reward_funcs=[rewards.iou_timestamp_reward_v2, rewards.format_reward], metric_funcs=[],
+                        args=args, train_dataset=make_dataset(cfg), processing_class=StubTokenizer())
+    name = "visual.blocks.1.attn.qkv.weight"
+    w0 = mw.train[name].clone()
+    tr.train()
+    assert tr.state.global_step == 2 and np.isfinite(tr.state.log_history[-1]["loss"]) and tr.state.log_history[-1]["grad_norm"] > 0
+    assert not torch.equal(mw.train[name], w0) and torch.equal(tr.engine.ref[name], w0)
+    tr.save_model(str(tmp_path / "final"))
+    for train_vit in (True, False):
+        _, w2 = load_checkpoint(str(tmp_path / "final"), "cuda", train_vit=train_vit)
+        a, b = mw.export_state_dict(), w2.export_state_dict()
+        assert a.keys() == b.keys() and all(torch.equal(a[k], b[k]) for k in a)
+
+
 def test_trainer_rejects_unsupported_paths():
     from time_r1_b200 import config, rewards, weights
     from time_r1_b200.trainer import GRPOArguments, TimeR1_Trainer

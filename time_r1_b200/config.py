@@ -172,7 +172,11 @@ class RunConfig:
     # shared memory (64 CTAs at cfg2); "wide" = the same CTA program without clusters on every SM (144 CTAs at cfg2), partials
     # merged through an L2-resident workspace behind a device-side arrival counter; "split" = split-KV kernel + combine
     # kernel through a global workspace (HMMA, round 1)
-    decode_attn: str = os.environ.get("T1_DECODE_ATTN", "cluster")
+    # kernel (HMMA, round 1); "auto" (default) = cluster below decode_attn_wide_min_prompt prompt tokens, wide from there on:
+    # measured per decode step (2 groups, 7B): cfg2 (P 4216) cluster 3.260 / wide 3.279 ms, cfg3 (P 8312) 3.394 / 3.383,
+    # cfg5 (P 16504) 3.665 / 3.546 (profiles/r02_decode_wide_vs_cluster_by_context.txt)
+    decode_attn: str = os.environ.get("T1_DECODE_ATTN", "auto")
+    decode_attn_wide_min_prompt: int = 8192
     # fuse the residual add + RMSNorm that follows the o / down projection into that stream GEMM (5 kernels per layer
     # instead of 7).  Measured neutral on B200 (3.53 vs 3.49 ms per step): what looked like kernel-boundary latency is
     # the finishing-time spread of the 148 streaming CTAs, which the fused tail has to wait out as well.

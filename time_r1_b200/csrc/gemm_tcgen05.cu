@@ -764,7 +764,11 @@ static int gemm_impl(const void* A, long long lda, const void* B, long long ldb,
   // ---- 2-CTA (cta_group::2) kernel: 256 x 256 tiles on SM pairs.  T1_GEMM_2CTA=0 keeps everything on the 1-CTA kernel ----
   {
     static const char* env2 = getenv("T1_GEMM_2CTA");
-    const bool want2 = !(env2 && env2[0] == '0') && BN == 256 && M > BM && (!a_mn || M % 64 == 0) && (!b_mn || N % 64 == 0);
+    // a cap at or below half the machine means "keep to a few SMs beside another stream's kernels" (the reference-model prefill
+    // beside the decode, RunConfig.side_ctas): which SMs are free is the other stream's choice and they need not form pairs, so
+    // those launches stay on the 1-CTA kernel (a cluster would wait for a whole pair)
+    const bool few = g_gemm_max_ctas > 0 && g_gemm_max_ctas <= sms / 2;
+    const bool want2 = !(env2 && env2[0] == '0') && !few && BN == 256 && M > BM && (!a_mn || M % 64 == 0) && (!b_mn || N % 64 == 0);
     if (want2) {
       const int num_m2 = (M + 2 * BM - 1) / (2 * BM);
       int max_clusters = sms / 2;

@@ -631,7 +631,13 @@ class Engine:
             # per-layer TMA tensor maps over every group's K and V cache (t1_decode_attn_cluster)
             flat = [t for l in range(L) for grp in groups for t in grp["kv"][l]]
             st["kv_maps"] = ops.kv_cache_tensor_maps(flat, cfg.num_key_value_heads, cfg.head_dim).reshape(L, n * 2 * 128)
-            if self.run.decode_attn == "wide":
+            # "auto": the cluster form holds 8 CTAs per (group, KV head) -- P / 1024 128-key units per CTA; from ~8 units per
+            # CTA on, the wide form's 144 streaming CTAs win (profiles/r02_decode_wide_vs_cluster_by_context.txt)
+            form = self.run.decode_attn
+            if form == "auto":
+                form = "wide" if max(Ps) >= int(getattr(self.run, "decode_attn_wide_min_prompt", 8192)) else "cluster"
+            st["attn_form"] = form
+            if form == "wide":
                 st["attn_splits"], st["attn_ws"] = ops.decode_attn_wide_workspace(n, cfg.num_key_value_heads, d)
         self._decode_cache[key] = st
         return st
@@ -672,7 +678,8 @@ class Engine:
             fuse_norm = self.run.decode_fuse_norm and cfg.hidden_size % 8 == 0
             # folded norms: the o / down GEMM epilogues update the residual stream and emit z = norm_w * resid plus per-slab
             # row sums of squares; the next GEMM streams against z and applies the row factor in its epilogue
-            wide = self.run.decode_attn == "wide"
+            form = st.get("attn_form", self.run.decode_attn)
+            wide = form == "wide"
 
             def attn_tc(l):
                 """rope + KV append + shared-prefix attention of layer l, all groups, one tcgen05 launch"""
@@ -683,7 +690,7 @@ class Engine:
                 else:         # 8-CTA cluster per (group, KV head), partials merged through distributed shared memory
                     call("t1_decode_attn_cluster", *common, 0, s)
 
-            fold = (self.run.decode_fold_norm and not fuse_norm and self.run.decode_attn in ("cluster", "wide") and cfg.hidden_size % 128 == 0
+            fold = (self.run.decode_fold_norm and not fuse_norm and form in ("cluster", "wide") and cfg.hidden_size % 128 == 0
                     and cfg.intermediate_size % 64 == 0)
             D = cfg.hidden_size
             fp = st["fold_parts"]
@@ -722,7 +729,7 @@ class Engine:
                     ops.rmsnorm(x, self.p(pre + "input_layernorm.weight"), eps, delta=down if (l > 0 and not fuse_norm) else None, out=h)
                 ops.stream_gemm(h, self.p(pre + "self_attn.qkv.weight"), ws, out=qkv, bias=self.p(pre + "self_attn.qkv.bias"))
                 # rope + KV append are fused into the attention kernel
-                if self.run.decode_attn in ("cluster", "wide"):
+                if form in ("cluster", "wide"):
                     attn_tc(l)
                 else:
                     call("t1_decode_attn_groups", ptr(qkv), qkv.stride(0), ptr(tab[l]), n, G, Hq, Hkv, hd, st["max_P"], st["cpad"],
