@@ -489,8 +489,11 @@ def decode_step_microbench(eng, Ps, G: int, C: int):
     st["next_ids"].copy_(snap[0]); st["finished"].copy_(snap[1]); st["out_ids"].copy_(snap[2])
     ts.sort()
     ms = ts[len(ts) // 2]
-    return {"bound": "hbm", "kernel": "captured decode step (stream_gemm_kernel x%d%s + decode_attn_tc x%d + sampler)" % (
-                4 * L + 1, " with the RMSNorms folded into their epilogues" if eng.run.decode_fold_norm else " + norm kernels", L),
+    paired = eng.run.decode_fold_norm and getattr(eng.run, "decode_pair", False) and st["launches_per_step"] < 4 * L
+    gemms = ("stream_gemm_pair_kernel x%d (o_proj + gate_up, down_proj + next qkv: one launch each, RMSNorms folded, arrival counter "
+             "between the two GEMMs) + stream_gemm_kernel x3" % (2 * L - 1)) if paired else (
+        "stream_gemm_kernel x%d%s" % (4 * L + 1, " with the RMSNorms folded into their epilogues" if eng.run.decode_fold_norm else " + norm kernels"))
+    return {"bound": "hbm", "kernel": "captured decode step (%s + decode_attn_tc x%d + sampler)" % (gemms, L),
             "launches": st["launches_per_step"], "weight_bytes": w_bytes, "kv_bytes": kv_bytes, "ms": round(ms, 4),
             "achieved": round((w_bytes + kv_bytes) / ms / 1e6, 1), "unit": "GB/s"}
 

@@ -101,6 +101,17 @@ int t1_stream_gemm_fold(const void* x, long long ldx, const void* W, long long l
 int t1_stream_gemm_scaled(const void* x, long long ldx, const void* W, long long ldw, const void* bias, void* y, long long ldy,
                           int M, int N, int K, int swiglu, const float* in_parts, int in_nparts, float eps, void* workspace,
                           long long workspace_bytes, cudaStream_t stream);
+/* t1_stream_gemm_fold(x, W_a -> resid, z, parts) immediately followed by t1_stream_gemm_scaled(z, W_b, parts -> y) as ONE
+ * launch: the o_proj -> [residual, post-attention norm] -> gate_up (swiglu != 0: N_b = 2 * I, y [M, I]) and down_proj ->
+ * [residual, next layer's input norm] -> qkv (+ bias) pairs of one decode step (HF Q25:805-827; the nn.Linear calls of
+ * GenerationMixin._sample driven from timer1_trainer.py:568-573).  The boundary between the two GEMMs is a device-side arrival
+ * counter instead of a kernel boundary and the weight stream runs through it; same unit split and summation order as the two
+ * separate launches, so y, resid, z and parts are bit-identical to them.  N_a % 128 == 0; the grid (<= one CTA per SM) must be
+ * resident at once. */
+int t1_stream_gemm_fold_pair(const void* x, long long ldx, const void* W_a, long long ldw_a, int M, int N_a, int K_a, void* resid,
+                             const void* norm_w, void* z, float* parts, const void* W_b, long long ldw_b, const void* bias_b,
+                             void* y, long long ldy, int N_b, int swiglu, float eps, void* workspace, long long workspace_bytes,
+                             cudaStream_t stream);
 /* y[M, I] = silu(x Wg^T) * (x Wu^T), W = [Wg; Wu] ([2I, K]): the decode step's gate_up projection fused with the SwiGLU
  * (HF Q25:611-624) in one weight stream; same arithmetic per element as t1_stream_gemm (bf16) + t1_swiglu (bit-identical when
  * the stream-K cut points coincide, as for the 7B decode shapes).  I % 64 == 0. */

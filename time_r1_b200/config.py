@@ -187,6 +187,13 @@ class RunConfig:
     # 147 instead of 202 kernels per decode step, 3.35 -> 3.23 ms per step on B200 (unlike the fused tail above, nothing
     # waits out the CTA finishing spread twice).  Same math as HF up to where the bf16 roundings fall.
     decode_fold_norm: bool = True
+    # with the folded norms: launch o_proj + gate_up and down_proj + the next layer's qkv as ONE kernel each
+    # (t1_stream_gemm_fold_pair: device-side arrival counter between the two GEMMs, the weight stream never stops at it);
+    # 92 instead of 147 kernels per decode step, bit-identical tokens.  Measured (profiles/r02_decode_pair_ab.txt,
+    # r02_decode_timeline_pair.txt): the counter is passed 7.8 / 6.2 us after CTA 0's phase A -- no earlier than the kernel
+    # boundary it replaces (7.3 / 7.0 us: both wait for the slowest CTA's fix-up, not for the launch machinery) -- and the
+    # two-phase producer issues its loads slower (gate_up 49 vs 40 us): 3.66 vs 3.20 ms per decode step.  OFF by default.
+    decode_pair: bool = os.environ.get("T1_DECODE_PAIR", "0") == "1"
     # MB of each layer's gate_up weights pulled into L2 (t1_stream_gemm_prefetch_next) by the idle warps of the qkv ("qkv")
     # or o_proj ("o") GEMM of the same layer while the chain is latency-bound (qkv -> attention -> o); 0 = off
     decode_prefetch_mb: int = int(os.environ.get("T1_DECODE_PF_MB", "0"))

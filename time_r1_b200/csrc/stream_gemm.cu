@@ -136,6 +136,190 @@ __device__ __forceinline__ unsigned long long gtimer() {
   return t;
 }
 
+// Epilogue of the units [u0, u1) of one GEMM (warps 2..5 = TMEM lane quadrants 2,3,0,1): accumulator out of TMEM, the
+// stream-K fix-up of split slabs, then the plain / SwiGLU / folded-norm store.  it0 = accumulator-buffer parity counter on
+// entry (the paired kernel runs two GEMMs back to back through the same TMEM double buffer); returns the counter on exit.
+template <int MP>
+__device__ __forceinline__ int sg_epilogue(const SgParams& p, uint8_t* smem, int warp_idx, int lane, uint32_t tmem_base,
+                                           uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar, int* s_flag, float* xs, int u0,
+                                           int u1, int it0) {
+  const int et = (warp_idx - 2) * 32 + lane;   // 0..127
+  const int KB = p.kblocks;
+  const int q = warp_idx & 3;
+  const int r = q * 32 + lane;                 // weight row inside the slab == TMEM lane
+  float* r_s = reinterpret_cast<float*>(smem + 512);   // [MP] row factors of a folded RMSNorm (header bytes 512..767)
+  if (p.in_parts) {
+    // all 128 threads fetch (one L2 round trip for <= 4 independent loads each), then MP threads finish in a fixed order
+    float* r_tmp = reinterpret_cast<float*>(smem + 1024);   // [128] (header bytes 1024..1535)
+    constexpr int GROUPS = 128 / MP;
+    const int m = et % MP, g0 = et / MP;
+    float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+    const int np = p.in_nparts;
+    int i = g0;
+    for (; i + 3 * GROUPS < np; i += 4 * GROUPS) {
+      const float a = __ldcg(p.in_parts + i * MP + m), b = __ldcg(p.in_parts + (i + GROUPS) * MP + m);
+      const float c = __ldcg(p.in_parts + (i + 2 * GROUPS) * MP + m), d = __ldcg(p.in_parts + (i + 3 * GROUPS) * MP + m);
+      v0 += a; v1 += b; v2 += c; v3 += d;
+    }
+    for (; i < np; i += GROUPS) v0 += __ldcg(p.in_parts + i * MP + m);
+    r_tmp[et] = (v0 + v1) + (v2 + v3);
+    epi_bar_sync();
+    if (et < MP) {
+      float ssq = 0.f;
+#pragma unroll
+      for (int g = 0; g < GROUPS; ++g) ssq += r_tmp[g * MP + et];
+      r_s[et] = rsqrtf(ssq / (float)p.K + p.in_eps);
+    }
+    epi_bar_sync();
+  }
+  int it = it0;
+  for (int u = u0; u < u1; ++it) {
+    const int slab = u / KB, kb0 = u - slab * KB;
+    const int kb1 = min(KB, kb0 + (u1 - u));
+    const int acc = it & 1;
+    const uint32_t acc_phase = (it >> 1) & 1;
+    mbar_wait(&tmem_full_bar[acc], acc_phase);
+    tc_fence_after();
+    uint32_t v[MP];
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * MP;
+    if constexpr (MP == 16) {
+      tmem_ld_32x32b_x16(taddr, v);
+    } else {
+#pragma unroll
+      for (int c = 0; c < MP / 32; ++c) tmem_ld_32x32b_x32(taddr + c * 32, v + c * 32);
+    }
+    tmem_ld_wait();
+    tc_fence_before();
+    mbar_arrive(&tmem_empty_bar[acc]);          // accumulator is in registers: the MMA warp may reuse it
+    const int n = slab * SG_BM + r;
+    const bool whole = (kb0 == 0 && kb1 == KB);
+    bool finish = whole;
+    int c_first = 0, c_last = 0;
+    if (!whole) {
+      float* mine = p.ws + ((size_t)(blockIdx.x * 2 + (it == it0 ? 0 : 1)) * MP) * SG_BM;
+#pragma unroll
+      for (int m = 0; m < MP; ++m) mine[m * SG_BM + r] = __uint_as_float(v[m]);
+      __threadfence();
+      epi_bar_sync();
+      c_first = (slab * KB) / p.per_cta;
+      c_last = ((slab + 1) * KB - 1) / p.per_cta;
+      if (et == 0) {
+        const int old = atomicAdd(&p.counters[slab], 1);
+        const int last = (old == c_last - c_first) ? 1 : 0;
+        if (last) p.counters[slab] = 0;         // self-resetting: the next launch finds zeros
+        *s_flag = last;
+      }
+      epi_bar_sync();
+      finish = *s_flag != 0;
+      epi_bar_sync();                            // s_flag may be rewritten by the next segment
+      if (finish) {
+        __threadfence();
+#pragma unroll
+        for (int m = 0; m < MP; ++m) v[m] = 0u;
+        // the partial tiles of FB contributors are fetched together (one L2 round trip per batch instead of one per
+        // contributor: this sum sits on the chain's critical path at every split slab) and added in the fixed order c_first..c_last
+        constexpr int FB = MP == 16 ? 4 : (MP == 32 ? 2 : 1);
+        for (int c = c_first; c <= c_last; c += FB) {
+          float t[FB][MP];
+#pragma unroll
+          for (int j = 0; j < FB; ++j) {
+            const int cc = min(c + j, c_last);
+            const int slot = (slab == (cc * p.per_cta) / KB) ? 0 : 1;
+            const float* part = p.ws + ((size_t)(cc * 2 + slot) * MP) * SG_BM;
+#pragma unroll
+            for (int m = 0; m < MP; ++m) t[j][m] = __ldcg(part + m * SG_BM + r);
+          }
+#pragma unroll
+          for (int j = 0; j < FB; ++j) {
+            if (c + j <= c_last) {
+#pragma unroll
+              for (int m = 0; m < MP; ++m) v[m] = __float_as_uint(__uint_as_float(v[m]) + t[j][m]);
+            }
+          }
+        }
+      }
+    }
+    if (finish && p.in_parts) {
+#pragma unroll
+      for (int m = 0; m < MP; ++m) v[m] = __float_as_uint(__uint_as_float(v[m]) * r_s[m]);
+    }
+    if (p.fold_x) {
+      // residual add + norm-weight scaling + per-row sum of squares of this slab's 128 columns (N % 128 == 0)
+      if (finish) {
+        const float gw = __bfloat162float(p.fold_w[n]);
+        bf16 xold[MP];
+#pragma unroll
+        for (int m = 0; m < MP; ++m)             // all residual loads in flight together (one L2 round trip, not MP)
+          xold[m] = m < p.M ? p.fold_x[(long long)m * p.N + n] : __float2bfloat16(0.f);
+        float sq[MP];
+#pragma unroll
+        for (int m = 0; m < MP; ++m) {
+          sq[m] = 0.f;
+          if (m < p.M) {
+            const float y = __bfloat162float(__float2bfloat16(__uint_as_float(v[m])));
+            const bf16 hn = __float2bfloat16(__bfloat162float(xold[m]) + y);  // hidden = residual + hidden in bf16 (HF Q25:805-827)
+            p.fold_x[(long long)m * p.N + n] = hn;
+            const float hf = __bfloat162float(hn);
+            p.fold_z[(long long)m * p.N + n] = __float2bfloat16(gw * hf);
+            sq[m] = hf * hf;
+          }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1)   // MP independent butterflies: the shuffles of different rows overlap
+#pragma unroll
+          for (int m = 0; m < MP; ++m) sq[m] += __shfl_xor_sync(0xffffffffu, sq[m], off);
+        if (lane == 0) {
+#pragma unroll
+          for (int m = 0; m < MP; ++m) xs[(warp_idx - 2) * MP + m] = sq[m];
+        }
+        epi_bar_sync();
+        if (et < MP) p.fold_parts[slab * MP + et] = xs[et] + xs[MP + et] + xs[2 * MP + et] + xs[3 * MP + et];
+        epi_bar_sync();                          // xs is rewritten by the next finished slab
+      }
+    } else if (p.swiglu) {
+      // lanes 0..63 hold the gate rows, lanes 64..127 the matching up rows: hand the up values over through shared
+      // memory, then y = silu(gate) * up on the bf16-rounded GEMM outputs (bit-identical to gemm -> t1_swiglu)
+      if (finish) {
+        const int col = slab * 64 + (r & 63);
+        if (r >= 64) {
+          const float b = (p.bias && col < p.half_n) ? __bfloat162float(p.bias[p.half_n + col]) : 0.f;
+#pragma unroll
+          for (int m = 0; m < MP; ++m) xs[m * 64 + (r - 64)] = __bfloat162float(__float2bfloat16(__uint_as_float(v[m]) + b));
+        }
+        epi_bar_sync();
+        if (r < 64 && col < p.half_n) {
+          const float b = p.bias ? __bfloat162float(p.bias[col]) : 0.f;
+          bf16* yp = reinterpret_cast<bf16*>(p.y) + col;
+#pragma unroll
+          for (int m = 0; m < MP; ++m) {
+            if (m < p.M) {
+              const float g = __bfloat162float(__float2bfloat16(__uint_as_float(v[m]) + b));
+              const float u = xs[m * 64 + r];
+              yp[(long long)m * p.ldy] = __float2bfloat16(g * (1.0f / (1.0f + __expf(-g))) * u);
+            }
+          }
+        }
+        epi_bar_sync();                          // xs is rewritten by the next finished slab
+      }
+    } else if (finish && n < p.N) {
+      const float b = p.bias ? __bfloat162float(p.bias[n]) : 0.f;
+      if (p.out_f32) {
+        float* yp = reinterpret_cast<float*>(p.y) + n;
+#pragma unroll
+        for (int m = 0; m < MP; ++m)
+          if (m < p.M) yp[(long long)m * p.ldy] = __uint_as_float(v[m]) + b;
+      } else {
+        bf16* yp = reinterpret_cast<bf16*>(p.y) + n;
+#pragma unroll
+        for (int m = 0; m < MP; ++m)
+          if (m < p.M) yp[(long long)m * p.ldy] = __float2bfloat16(__uint_as_float(v[m]) + b);
+      }
+    }
+    u += kb1 - kb0;
+  }
+  return it;
+}
+
 template <int MP>
 __global__ void __launch_bounds__(SG_THREADS + 32, 1)
 stream_gemm_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CUtensorMap tma_x, SgParams p) {
@@ -198,40 +382,45 @@ stream_gemm_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_const
       asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
       const int n = u1 - u0;
       const int pre = min(n, stages);
+      // This one thread issues every load of the CTA (one 18 KB unit every ~700 cycles at the HBM rate), so the steady state
+      // carries no division: (slab, k-block) advance incrementally.  Measured with the paired kernel (same loop): five run-time
+      // divisions per unit made the ISSUE the bottleneck (gate_up 67 us instead of 40).
+      const int swg = p.swiglu, half_n = p.half_n;
+      const int slab0 = u0 / KB, kb0 = u0 - slab0 * KB;
+      int slab = slab0, kb = kb0;
       // weights first: they do not depend on the previous kernel
       for (int i = 0; i < pre; ++i) {
-        const int u = u0 + i;
-        const int slab = u / KB, kb = u - slab * KB;
         mbar_arrive_expect_tx(&full_bar[i], STAGE_BYTES);
-        if (p.swiglu) {
+        if (swg) {
           tma_load_2d_hint(tiles + i * STAGE_BYTES, &tma_w, &full_bar[i], kb * SG_BK, slab * 64, pol_stream);
-          tma_load_2d_hint(tiles + i * STAGE_BYTES + 64 * 128, &tma_w, &full_bar[i], kb * SG_BK, p.half_n + slab * 64, pol_stream);
+          tma_load_2d_hint(tiles + i * STAGE_BYTES + 64 * 128, &tma_w, &full_bar[i], kb * SG_BK, half_n + slab * 64, pol_stream);
         } else {
           tma_load_2d_hint(tiles + i * STAGE_BYTES, &tma_w, &full_bar[i], kb * SG_BK, slab * SG_BM, pol_stream);
         }
+        if (++kb == KB) { kb = 0; ++slab; }
       }
       if (dbg) p.dbg[1] = gtimer();
       pdl_wait();
       if (dbg) p.dbg[2] = gtimer();
-      for (int i = 0; i < pre; ++i) {
-        const int u = u0 + i;
-        const int kb = u % KB;
-        tma_load_2d_hint(tiles + i * STAGE_BYTES + SG_W_BYTES, &tma_x, &full_bar[i], kb * SG_BK, 0, pol_keep);
+      for (int i = 0, kx = kb0; i < pre; ++i) {
+        tma_load_2d_hint(tiles + i * STAGE_BYTES + SG_W_BYTES, &tma_x, &full_bar[i], kx * SG_BK, 0, pol_keep);
+        if (++kx == KB) kx = 0;
       }
       int stage = pre == stages ? 0 : pre;
       uint32_t phase = pre == stages ? 1 : 0;   // parity of the NEXT use of `stage`
       for (int i = pre; i < n; ++i) {
-        const int u = u0 + i;
-        const int slab = u / KB, kb = u - slab * KB;
+        uint8_t* dst = tiles + stage * STAGE_BYTES;
+        uint64_t* bar = &full_bar[stage];
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-        if (p.swiglu) {
-          tma_load_2d_hint(tiles + stage * STAGE_BYTES, &tma_w, &full_bar[stage], kb * SG_BK, slab * 64, pol_stream);
-          tma_load_2d_hint(tiles + stage * STAGE_BYTES + 64 * 128, &tma_w, &full_bar[stage], kb * SG_BK, p.half_n + slab * 64, pol_stream);
+        mbar_arrive_expect_tx(bar, STAGE_BYTES);
+        if (swg) {
+          tma_load_2d_hint(dst, &tma_w, bar, kb * SG_BK, slab * 64, pol_stream);
+          tma_load_2d_hint(dst + 64 * 128, &tma_w, bar, kb * SG_BK, half_n + slab * 64, pol_stream);
         } else {
-          tma_load_2d_hint(tiles + stage * STAGE_BYTES, &tma_w, &full_bar[stage], kb * SG_BK, slab * SG_BM, pol_stream);
+          tma_load_2d_hint(dst, &tma_w, bar, kb * SG_BK, slab * SG_BM, pol_stream);
         }
-        tma_load_2d_hint(tiles + stage * STAGE_BYTES + SG_W_BYTES, &tma_x, &full_bar[stage], kb * SG_BK, 0, pol_keep);
+        tma_load_2d_hint(dst + SG_W_BYTES, &tma_x, bar, kb * SG_BK, 0, pol_keep);
+        if (++kb == KB) { kb = 0; ++slab; }
         if (++stage == stages) {
           stage = 0;
           phase ^= 1;
@@ -280,163 +469,7 @@ stream_gemm_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_const
     // ===================== epilogue (warps 2..5 = TMEM lane quadrants 2,3,0,1) =====================
     const int et = (warp_idx - 2) * 32 + lane;   // 0..127
     pdl_wait();
-    const int q = warp_idx & 3;
-    const int r = q * 32 + lane;                 // weight row inside the slab == TMEM lane
-    float* r_s = reinterpret_cast<float*>(smem + 512);   // [MP] row factors of a folded RMSNorm (header bytes 512..767)
-    if (p.in_parts) {
-      // all 128 threads fetch (one L2 round trip for <= 4 independent loads each), then MP threads finish in a fixed order
-      float* r_tmp = reinterpret_cast<float*>(smem + 1024);   // [128] (header bytes 1024..1535)
-      constexpr int GROUPS = 128 / MP;
-      const int m = et % MP, g0 = et / MP;
-      float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
-      const int np = p.in_nparts;
-      int i = g0;
-      for (; i + 3 * GROUPS < np; i += 4 * GROUPS) {
-        const float a = __ldcg(p.in_parts + i * MP + m), b = __ldcg(p.in_parts + (i + GROUPS) * MP + m);
-        const float c = __ldcg(p.in_parts + (i + 2 * GROUPS) * MP + m), d = __ldcg(p.in_parts + (i + 3 * GROUPS) * MP + m);
-        v0 += a; v1 += b; v2 += c; v3 += d;
-      }
-      for (; i < np; i += GROUPS) v0 += __ldcg(p.in_parts + i * MP + m);
-      r_tmp[et] = (v0 + v1) + (v2 + v3);
-      epi_bar_sync();
-      if (et < MP) {
-        float ssq = 0.f;
-#pragma unroll
-        for (int g = 0; g < GROUPS; ++g) ssq += r_tmp[g * MP + et];
-        r_s[et] = rsqrtf(ssq / (float)p.K + p.in_eps);
-      }
-      epi_bar_sync();
-    }
-    int it = 0;
-    for (int u = u0; u < u1; ++it) {
-      const int slab = u / KB, kb0 = u - slab * KB;
-      const int kb1 = min(KB, kb0 + (u1 - u));
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
-      mbar_wait(&tmem_full_bar[acc], acc_phase);
-      tc_fence_after();
-      uint32_t v[MP];
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * MP;
-      if constexpr (MP == 16) {
-        tmem_ld_32x32b_x16(taddr, v);
-      } else {
-#pragma unroll
-        for (int c = 0; c < MP / 32; ++c) tmem_ld_32x32b_x32(taddr + c * 32, v + c * 32);
-      }
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(&tmem_empty_bar[acc]);          // accumulator is in registers: the MMA warp may reuse it
-      const int n = slab * SG_BM + r;
-      const bool whole = (kb0 == 0 && kb1 == KB);
-      bool finish = whole;
-      int c_first = 0, c_last = 0;
-      if (!whole) {
-        float* mine = p.ws + ((size_t)(blockIdx.x * 2 + (it == 0 ? 0 : 1)) * MP) * SG_BM;
-#pragma unroll
-        for (int m = 0; m < MP; ++m) mine[m * SG_BM + r] = __uint_as_float(v[m]);
-        __threadfence();
-        epi_bar_sync();
-        c_first = (slab * KB) / p.per_cta;
-        c_last = ((slab + 1) * KB - 1) / p.per_cta;
-        if (et == 0) {
-          const int old = atomicAdd(&p.counters[slab], 1);
-          const int last = (old == c_last - c_first) ? 1 : 0;
-          if (last) p.counters[slab] = 0;         // self-resetting: the next launch finds zeros
-          *s_flag = last;
-        }
-        epi_bar_sync();
-        finish = *s_flag != 0;
-        epi_bar_sync();                            // s_flag may be rewritten by the next segment
-        if (finish) {
-          __threadfence();
-#pragma unroll
-          for (int m = 0; m < MP; ++m) v[m] = 0u;
-          for (int c = c_first; c <= c_last; ++c) {
-            const int slot = (slab == (c * p.per_cta) / KB) ? 0 : 1;
-            const float* part = p.ws + ((size_t)(c * 2 + slot) * MP) * SG_BM;
-#pragma unroll
-            for (int m = 0; m < MP; ++m) v[m] = __float_as_uint(__uint_as_float(v[m]) + __ldcg(part + m * SG_BM + r));
-          }
-        }
-      }
-      if (finish && p.in_parts) {
-#pragma unroll
-        for (int m = 0; m < MP; ++m) v[m] = __float_as_uint(__uint_as_float(v[m]) * r_s[m]);
-      }
-      if (p.fold_x) {
-        // residual add + norm-weight scaling + per-row sum of squares of this slab's 128 columns (N % 128 == 0)
-        if (finish) {
-          const float gw = __bfloat162float(p.fold_w[n]);
-          bf16 xold[MP];
-#pragma unroll
-          for (int m = 0; m < MP; ++m)             // all residual loads in flight together (one L2 round trip, not MP)
-            xold[m] = m < p.M ? p.fold_x[(long long)m * p.N + n] : __float2bfloat16(0.f);
-          float sq[MP];
-#pragma unroll
-          for (int m = 0; m < MP; ++m) {
-            sq[m] = 0.f;
-            if (m < p.M) {
-              const float y = __bfloat162float(__float2bfloat16(__uint_as_float(v[m])));
-              const bf16 hn = __float2bfloat16(__bfloat162float(xold[m]) + y);  // hidden = residual + hidden in bf16 (HF Q25:805-827)
-              p.fold_x[(long long)m * p.N + n] = hn;
-              const float hf = __bfloat162float(hn);
-              p.fold_z[(long long)m * p.N + n] = __float2bfloat16(gw * hf);
-              sq[m] = hf * hf;
-            }
-          }
-#pragma unroll
-          for (int off = 16; off > 0; off >>= 1)   // MP independent butterflies: the shuffles of different rows overlap
-#pragma unroll
-            for (int m = 0; m < MP; ++m) sq[m] += __shfl_xor_sync(0xffffffffu, sq[m], off);
-          if (lane == 0) {
-#pragma unroll
-            for (int m = 0; m < MP; ++m) xs[(warp_idx - 2) * MP + m] = sq[m];
-          }
-          epi_bar_sync();
-          if (et < MP) p.fold_parts[slab * MP + et] = xs[et] + xs[MP + et] + xs[2 * MP + et] + xs[3 * MP + et];
-          epi_bar_sync();                          // xs is rewritten by the next finished slab
-        }
-      } else if (p.swiglu) {
-        // lanes 0..63 hold the gate rows, lanes 64..127 the matching up rows: hand the up values over through shared
-        // memory, then y = silu(gate) * up on the bf16-rounded GEMM outputs (bit-identical to gemm -> t1_swiglu)
-        if (finish) {
-          const int col = slab * 64 + (r & 63);
-          if (r >= 64) {
-            const float b = (p.bias && col < p.half_n) ? __bfloat162float(p.bias[p.half_n + col]) : 0.f;
-#pragma unroll
-            for (int m = 0; m < MP; ++m) xs[m * 64 + (r - 64)] = __bfloat162float(__float2bfloat16(__uint_as_float(v[m]) + b));
-          }
-          epi_bar_sync();
-          if (r < 64 && col < p.half_n) {
-            const float b = p.bias ? __bfloat162float(p.bias[col]) : 0.f;
-            bf16* yp = reinterpret_cast<bf16*>(p.y) + col;
-#pragma unroll
-            for (int m = 0; m < MP; ++m) {
-              if (m < p.M) {
-                const float g = __bfloat162float(__float2bfloat16(__uint_as_float(v[m]) + b));
-                const float u = xs[m * 64 + r];
-                yp[(long long)m * p.ldy] = __float2bfloat16(g * (1.0f / (1.0f + __expf(-g))) * u);
-              }
-            }
-          }
-          epi_bar_sync();                          // xs is rewritten by the next finished slab
-        }
-      } else if (finish && n < p.N) {
-        const float b = p.bias ? __bfloat162float(p.bias[n]) : 0.f;
-        if (p.out_f32) {
-          float* yp = reinterpret_cast<float*>(p.y) + n;
-#pragma unroll
-          for (int m = 0; m < MP; ++m)
-            if (m < p.M) yp[(long long)m * p.ldy] = __uint_as_float(v[m]) + b;
-        } else {
-          bf16* yp = reinterpret_cast<bf16*>(p.y) + n;
-#pragma unroll
-          for (int m = 0; m < MP; ++m)
-            if (m < p.M) yp[(long long)m * p.ldy] = __float2bfloat16(__uint_as_float(v[m]) + b);
-        }
-      }
-      u += kb1 - kb0;
-    }
+    sg_epilogue<MP>(p, smem, warp_idx, lane, tmem_base, tmem_full_bar, tmem_empty_bar, s_flag, xs, u0, u1, 0);
     if (p.tail_x) {
       // ---- residual + RMSNorm: a grid-wide arrive counter, then CTA b (b < M) normalises row b ----
       // Every CTA of the launch is resident at the same time (grid <= SM count, one CTA per SM), so the M row-CTAs may
@@ -543,6 +576,246 @@ stream_gemm_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_const
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// TWO dependent GEMMs of the decode chain in ONE launch (t1_stream_gemm_fold_pair): phase A is the producer half of a
+// folded RMSNorm (o_proj or down_proj: residual add, z = norm_w * resid, per-slab row sums of squares), phase B the
+// consumer half streaming against z (gate_up with SwiGLU, or the next layer's qkv).  Between two kernels that boundary
+// costs the grid teardown, the memory flush and the dependent launch on top of the slowest CTA's fix-up; here it is a
+// device-side arrival counter every CTA of the (fully resident) grid increments after its phase-A stores:
+//   * the TMA producer never stops: phase-B WEIGHT tiles enter the ring as soon as phase-A stages retire; only the small
+//     z tiles of phase B wait for the counter (acquire + fence.proxy.async before the first TMA read of z);
+//   * the MMA warp runs straight through both unit ranges (same ring, same TMEM double buffer);
+//   * the epilogue warps arrive after phase A, read the row factors once the counter is complete, run phase B, and the
+//     last CTA to leave re-arms the counters.
+// Same unit split, same arithmetic and the same summation order as t1_stream_gemm_fold followed by
+// t1_stream_gemm_scaled: bit-identical results.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ int ld_acquire_cta_shared(const int* p) {
+  int v;
+  asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_cta_shared(int* p, int v) {
+  asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+
+template <int MP>
+__global__ void __launch_bounds__(SG_THREADS, 1)
+stream_gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_w0, const __grid_constant__ CUtensorMap tma_x0,
+                        const __grid_constant__ CUtensorMap tma_w1, const __grid_constant__ CUtensorMap tma_x1,
+                        const __grid_constant__ SgParams p0, const __grid_constant__ SgParams p1, int* pair_counter) {
+  constexpr int X_BYTES = MP * SG_BK * 2;
+  constexpr int STAGE_BYTES = SG_W_BYTES + X_BYTES;
+  constexpr uint32_t TMEM_COLS = (2 * MP < 32) ? 32 : 2 * MP;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty_bar = full_bar + SG_MAX_STAGES;
+  uint64_t* tmem_full_bar = empty_bar + SG_MAX_STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  int* s_flag = reinterpret_cast<int*>(tmem_ptr_smem + 1);
+  uint8_t* tiles = smem + SG_HEADER;
+  const int stages = p0.stages;
+  float* xs = reinterpret_cast<float*>(tiles + stages * STAGE_BYTES);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int u0 = blockIdx.x * p0.per_cta;
+  const int u1 = max(u0, min(u0 + p0.per_cta, p0.total_units));
+  const int v0 = blockIdx.x * p1.per_cta;
+  const int v1 = max(v0, min(v0 + p1.per_cta, p1.total_units));
+  const int nA = u1 - u0, nB = v1 - v0;
+  // ONE thread per CTA (epilogue thread 0) polls the global arrival counter, with back-off: 2 x 148 threads spinning on one L2
+  // line delay the very arrivals they wait for (measured: 4.41 instead of 3.20 ms per decode step).  It hands the result to the
+  // TMA producer through this shared-memory flag.
+  int* pair_flag = s_flag + 2;
+
+  if (warp_idx == 0 && lane == 0) {
+    *pair_flag = 0;
+    tma_prefetch_desc(&tma_w0);
+    tma_prefetch_desc(&tma_x0);
+    tma_prefetch_desc(&tma_w1);
+    tma_prefetch_desc(&tma_x1);
+    for (int i = 0; i < stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 128);
+    }
+    mbar_fence_init();
+  }
+  if (warp_idx == 1) tmem_alloc<TMEM_COLS>(tmem_ptr_smem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_trigger();
+
+  if (warp_idx == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0 && nA + nB > 0) {
+      uint64_t pol_stream, pol_keep;
+      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+      asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+      const int total = nA + nB;
+      // This one thread issues every load of the CTA (a unit every ~700 cycles at the HBM rate): no division in the steady
+      // state -- ring slot, wrap parity and (slab, k-block) of the W and of the x cursor advance incrementally.  (First version:
+      // five run-time divisions per unit made the ISSUE the bottleneck, gate_up 67 instead of 40 us.)  Each TMA instruction
+      // names its tensor map directly.
+      const int KBa = p0.kblocks, KBb = p1.kblocks, swb = p1.swiglu, halfb = p1.half_n;
+      const int slabB0 = v0 / KBb, kbB0 = v0 - slabB0 * KBb;
+      struct Cur { int g, st, wrap, slab, kb; };
+      Cur cw, cx;
+      cw.g = 0; cw.st = 0; cw.wrap = 0;
+      if (nA > 0) { cw.slab = u0 / KBa; cw.kb = u0 - cw.slab * KBa; } else { cw.slab = slabB0; cw.kb = kbB0; }
+      cx = cw;
+      auto advance = [&](Cur& c) {
+        const bool was_a = c.g < nA;
+        ++c.g;
+        if (++c.st == stages) { c.st = 0; ++c.wrap; }
+        if (was_a && c.g == nA) { c.slab = slabB0; c.kb = kbB0; }
+        else if (++c.kb == (was_a ? KBa : KBb)) { c.kb = 0; ++c.slab; }
+      };
+      auto do_w = [&]() {
+        uint8_t* dst = tiles + cw.st * STAGE_BYTES;
+        uint64_t* bar = &full_bar[cw.st];
+        mbar_arrive_expect_tx(bar, STAGE_BYTES);
+        if (cw.g < nA) {                                 // phase A: fold producer, never SwiGLU
+          tma_load_2d_hint(dst, &tma_w0, bar, cw.kb * SG_BK, cw.slab * SG_BM, pol_stream);
+        } else if (swb) {
+          tma_load_2d_hint(dst, &tma_w1, bar, cw.kb * SG_BK, cw.slab * 64, pol_stream);
+          tma_load_2d_hint(dst + 64 * 128, &tma_w1, bar, cw.kb * SG_BK, halfb + cw.slab * 64, pol_stream);
+        } else {
+          tma_load_2d_hint(dst, &tma_w1, bar, cw.kb * SG_BK, cw.slab * SG_BM, pol_stream);
+        }
+        advance(cw);
+      };
+      auto do_x = [&]() {
+        uint8_t* dst = tiles + cx.st * STAGE_BYTES + SG_W_BYTES;
+        if (cx.g < nA) tma_load_2d_hint(dst, &tma_x0, &full_bar[cx.st], cx.kb * SG_BK, 0, pol_keep);
+        else tma_load_2d_hint(dst, &tma_x1, &full_bar[cx.st], cx.kb * SG_BK, 0, pol_keep);
+        advance(cx);
+      };
+      const bool dbg = p0.dbg && blockIdx.x == 0;
+      if (dbg) p0.dbg[0] = gtimer();
+      const int pre = min(total, stages);
+      for (int i = 0; i < pre; ++i) do_w();              // weights first: they depend on nothing
+      if (dbg) p0.dbg[1] = gtimer();
+      pdl_wait();
+      if (dbg) p0.dbg[2] = gtimer();
+      const int preA = min(pre, nA);
+      while (cx.g < preA) do_x();
+      bool bar_ok = false;
+      auto pass_barrier = [&](bool spin) {
+        if (!spin && ld_acquire_cta_shared(pair_flag) == 0) return;
+        while (ld_acquire_cta_shared(pair_flag) == 0) {}
+        asm volatile("fence.proxy.async;" ::: "memory");   // z was written through the generic proxy, TMA reads it through the async proxy
+        bar_ok = true;
+        if (dbg && p1.dbg) p1.dbg[1] = gtimer();
+      };
+      // cx.g = first unit whose x tile has not been requested: == cw.g through phase A, stuck at the first phase-B unit until
+      // the arrival counter is complete
+      while (cw.g < total) {
+        const int g = cw.g;
+        if (!bar_ok && g >= nA) {
+          // the slot's previous occupant must be able to retire without this thread: a phase-B unit only can once its z tile is requested
+          if (g - stages >= cx.g) pass_barrier(true);
+          else if (cx.g < g) pass_barrier(false);
+        }
+        if (bar_ok) {
+          while (cx.g < g) do_x();
+        }
+        mbar_wait(&empty_bar[cw.st], (cw.wrap & 1) ^ 1);
+        do_w();
+        if (g < nA || bar_ok) do_x();
+      }
+      if (cx.g < total) {
+        if (!bar_ok) pass_barrier(true);
+        while (cx.g < total) do_x();
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ===================== MMA issuer (single thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(SG_BM, MP);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int ph = 0; ph < 2; ++ph) {
+        const int KB = ph ? p1.kblocks : p0.kblocks;
+        const int a = ph ? v0 : u0, b = ph ? v1 : u1;
+        for (int u = a; u < b; ++it) {
+          const int slab = u / KB, kb0 = u - slab * KB;
+          const int kb1 = min(KB, kb0 + (b - u));
+          const int acc = it & 1;
+          const uint32_t acc_phase = (it >> 1) & 1;
+          mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + acc * MP;
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint64_t a_desc = umma_desc_sw128_kmajor(smem_u32(tiles + stage * STAGE_BYTES));
+            const uint64_t b_desc = umma_desc_sw128_kmajor(smem_u32(tiles + stage * STAGE_BYTES + SG_W_BYTES));
+#pragma unroll
+            for (int k = 0; k < SG_BK / 16; ++k)
+              umma_bf16_ss(tmem_d, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            umma_commit(&empty_bar[stage]);
+            if (++stage == stages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          umma_commit(&tmem_full_bar[acc]);
+          u += kb1 - kb0;
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int et = (warp_idx - 2) * 32 + lane;
+    pdl_wait();
+    const bool dbg = p0.dbg && p1.dbg && blockIdx.x == 0 && et == 0;
+    int it = sg_epilogue<MP>(p0, smem, warp_idx, lane, tmem_base, tmem_full_bar, tmem_empty_bar, s_flag, xs, u0, u1, 0);
+    if (dbg) p0.dbg[3] = p1.dbg[0] = gtimer();
+    __threadfence();                               // this CTA's residual / z / parts stores are visible device-wide
+    epi_bar_sync();
+    if (et == 0) {
+      atomicAdd(pair_counter, 1);
+      while (ld_acquire_gpu(pair_counter) < (int)gridDim.x) __nanosleep(64);
+      __threadfence();
+      st_release_cta_shared(pair_flag, 1);         // the TMA producer may request the z tiles
+    }
+    epi_bar_sync();
+    if (dbg) p1.dbg[2] = gtimer();
+    sg_epilogue<MP>(p1, smem, warp_idx, lane, tmem_base, tmem_full_bar, tmem_empty_bar, s_flag, xs, v0, v1, it);
+    epi_bar_sync();
+    if (dbg) p1.dbg[3] = gtimer();
+    if (et == 0) {                                 // the last CTA to leave re-arms both counters for the next launch
+      const int old = atomicAdd(pair_counter + 1, 1);
+      if (old == (int)gridDim.x - 1) {
+        pair_counter[1] = 0;
+        pair_counter[0] = 0;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 1) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
 
 // ---------------------------------------------------------------------------------------------
 // Dynamically scheduled variant.  The 148 CTAs of a static equal split do NOT finish together: per-SM streaming rates
@@ -885,6 +1158,27 @@ int launch_stream(const CUtensorMap& tw, const CUtensorMap& tx, SgParams p, int 
   return T1_OK;
 }
 
+template <int MP>
+int launch_stream_pair(const CUtensorMap& tw0, const CUtensorMap& tx0, const CUtensorMap& tw1, const CUtensorMap& tx1, SgParams p0,
+                       SgParams p1, int* pair_counter, int grid, int smem, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(stream_gemm_pair_kernel<MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) {
+      t1_set_error("t1_stream_gemm_fold_pair: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return T1_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  cudaError_t e = t1_launch(stream_gemm_pair_kernel<MP>, dim3(grid), dim3(SG_THREADS), (size_t)smem, stream, tw0, tx0, tw1, tx1, p0, p1,
+                            pair_counter);
+  if (e != cudaSuccess) {
+    t1_set_error("t1_stream_gemm_fold_pair: launch failed: %s", cudaGetErrorString(e));
+    return T1_ERR_CUDA;
+  }
+  return T1_OK;
+}
+
 }  // namespace
 
 // Workspace bytes a caller must provide for t1_stream_gemm with up to max_m rows: slab counters (the first 64 KB, which
@@ -1183,6 +1477,100 @@ extern "C" int t1_stream_gemm_scaled(const void* x, long long ldx, const void* W
   t.in_nparts = in_nparts;
   t.eps = eps;
   return stream_gemm_impl(x, ldx, W, ldw, bias, y, ldy, M, N, K, 0, swiglu ? 1 : 0, workspace, workspace_bytes, stream, t);
+}
+
+// t1_stream_gemm_fold(x, W_a -> resid, z, parts) immediately followed by t1_stream_gemm_scaled(z, W_b, parts -> y) as ONE
+// launch (stream_gemm_pair_kernel): the decode chain's o_proj -> [residual, post-attention norm] -> gate_up (swiglu != 0:
+// N_b = 2 * I, y [M, I]) and down_proj -> [residual, next input norm] -> qkv (bias) pairs, HF Q25:805-827.  The boundary between
+// the two GEMMs is a device-side arrival counter instead of a kernel boundary; the weight stream does not stop at it.
+// Same unit split and summation order as the two separate launches: bit-identical y, resid, z and parts.
+// N_a % 128 == 0; every CTA of the launch must be resident at once (grid <= SM count: true for the default one CTA per SM).
+extern "C" int t1_stream_gemm_fold_pair(const void* x, long long ldx, const void* W_a, long long ldw_a, int M, int N_a, int K_a,
+                                        void* resid, const void* norm_w, void* z, float* parts, const void* W_b, long long ldw_b,
+                                        const void* bias_b, void* y, long long ldy, int N_b, int swiglu, float eps, void* workspace,
+                                        long long workspace_bytes, cudaStream_t stream) {
+  T1_CHECK_ARG(x && W_a && W_b && y && workspace && resid && norm_w && z && parts, "t1_stream_gemm_fold_pair: null pointer");
+  T1_CHECK_ARG(M > 0 && M <= 64, "t1_stream_gemm_fold_pair: M=%d must be in [1, 64]", M);
+  T1_CHECK_ARG(N_a > 0 && N_a % 128 == 0 && K_a > 0 && K_a % 8 == 0 && N_b > 0, "t1_stream_gemm_fold_pair: N_a %% 128, K_a %% 8 required");
+  T1_CHECK_ARG(ldx % 8 == 0 && ldw_a % 8 == 0 && ldw_b % 8 == 0 && ldx >= K_a && ldw_a >= K_a && ldw_b >= N_a,
+               "t1_stream_gemm_fold_pair: leading dimensions must be multiples of 8 and cover K");
+  T1_CHECK_ARG((((uintptr_t)x | (uintptr_t)W_a | (uintptr_t)W_b | (uintptr_t)z | (uintptr_t)workspace) & 15) == 0,
+               "t1_stream_gemm_fold_pair: operands must be 16-byte aligned");
+  if (swiglu) T1_CHECK_ARG(N_b % 128 == 0, "t1_stream_gemm_fold_pair: swiglu needs N_b = 2*I with I %% 64 == 0 (N_b=%d)", N_b);
+  const SgPlan pa = sg_plan(M, N_a, K_a, 0, true);
+  const SgPlan pb = sg_plan(M, N_b, N_a, swiglu, false);
+  const int MP = pa.MP;
+  const int stages = pa.stages < pb.stages ? pa.stages : pb.stages;
+  const int xs_bytes = pa.xs_bytes > pb.xs_bytes ? pa.xs_bytes : pb.xs_bytes;
+  const int smem = SG_HEADER + 1024 + stages * pa.stage_bytes + xs_bytes;
+  const int grid = pa.grid > pb.grid ? pa.grid : pb.grid;
+  T1_CHECK_ARG(pa.total < (1LL << 30) && pb.total < (1LL << 30), "t1_stream_gemm_fold_pair: problem too large");
+  T1_CHECK_ARG(grid <= t1_num_sms(), "t1_stream_gemm_fold_pair: needs every CTA resident (grid %d > %d SMs)", grid, t1_num_sms());
+  constexpr int HALF = SG_COUNTER_BYTES / 8;      // ints: phase A counters [0, HALF), phase B counters [HALF, 2 * HALF - 8)
+  T1_CHECK_ARG(pa.slabs <= HALF && pb.slabs <= HALF - 8, "t1_stream_gemm_fold_pair: too many slabs for the counter region");
+  const long long need = SG_COUNTER_BYTES + (long long)grid * 2 * MP * SG_BM * 4;
+  T1_CHECK_ARG(workspace_bytes >= need, "t1_stream_gemm_fold_pair: workspace too small (%lld < %lld)", workspace_bytes, need);
+  CUtensorMap tw0, tx0, tw1, tx1;
+  int rc = t1_make_tmap_bf16(&tw0, W_a, N_a, K_a, ldw_a, SG_BM, SG_BK);
+  if (rc) return rc;
+  rc = t1_make_tmap_bf16(&tx0, x, M, K_a, ldx, MP, SG_BK);
+  if (rc) return rc;
+  rc = t1_make_tmap_bf16(&tw1, W_b, N_b, N_a, ldw_b, swiglu ? 64 : SG_BM, SG_BK);
+  if (rc) return rc;
+  rc = t1_make_tmap_bf16(&tx1, z, M, N_a, N_a, MP, SG_BK);
+  if (rc) return rc;
+  int* counters = reinterpret_cast<int*>(workspace);
+  float* ws = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + SG_COUNTER_BYTES);
+  SgParams p[2];
+  for (int i = 0; i < 2; ++i) {
+    const SgPlan& pl = i ? pb : pa;
+    SgParams& q = p[i];
+    q.y = i ? y : z;
+    q.bias = i ? (const bf16*)bias_b : nullptr;
+    q.ws = ws;
+    q.counters = counters + (i ? HALF : 0);
+    q.ldy = i ? ldy : N_a;
+    q.M = M;
+    q.N = i ? N_b : N_a;
+    q.K = i ? N_a : K_a;
+    q.kblocks = pl.kblocks;
+    q.total_units = (int)pl.total;
+    q.per_cta = pl.per;
+    q.stages = stages;
+    q.out_f32 = 0;
+    q.swiglu = i ? (swiglu ? 1 : 0) : 0;
+    q.half_n = pl.half_n;
+    q.tail_x = nullptr;
+    q.tail_w = nullptr;
+    q.tail_h = nullptr;
+    q.tail_eps = 0.f;
+    q.tail_counter = nullptr;
+    q.segs = 1;
+    q.seg_k = pl.kblocks;
+    q.total_items = pl.slabs;
+    q.sched_counter = nullptr;
+    q.dbg = nullptr;
+    if (g_dbg && g_dbg_slots > 0) {      // diagnostics: one record per GEMM of the pair, as the separate launches would write
+      q.dbg = g_dbg + 4 * (size_t)(g_dbg_next % g_dbg_slots);
+      ++g_dbg_next;
+    }
+    q.fold_x = i ? nullptr : reinterpret_cast<bf16*>(resid);
+    q.fold_w = i ? nullptr : reinterpret_cast<const bf16*>(norm_w);
+    q.fold_z = i ? nullptr : reinterpret_cast<bf16*>(z);
+    q.fold_parts = i ? nullptr : parts;
+    q.in_parts = i ? parts : nullptr;
+    q.in_nparts = i ? N_a / 128 : 0;
+    q.in_eps = eps;
+    q.pf_w = nullptr;
+  }
+  g_pf_hint = SgPrefetchHint();
+  int* pair_counter = counters + SG_COUNTER_BYTES / 4 - 5;      // words -5, -4 of the counter region (zero on entry, re-armed on exit)
+  if (MP == 16) rc = launch_stream_pair<16>(tw0, tx0, tw1, tx1, p[0], p[1], pair_counter, grid, smem, stream);
+  else if (MP == 32) rc = launch_stream_pair<32>(tw0, tx0, tw1, tx1, p[0], p[1], pair_counter, grid, smem, stream);
+  else rc = launch_stream_pair<64>(tw0, tx0, tw1, tx1, p[0], p[1], pair_counter, grid, smem, stream);
+  if (rc) return rc;
+  t1_count_launch();
+  return T1_OK;
 }
 
 #ifdef T1_SG_DBG

@@ -701,8 +701,27 @@ class Engine:
                 w = self.p(f"model.layers.{l}.mlp.gate_up.weight")
                 call("t1_stream_gemm_prefetch_next", ptr(w), w.stride(0), B, w.shape[0], w.shape[1], 1, 0, pf_bytes)
 
+            # paired launches (RunConfig.decode_pair): o_proj + gate_up and down_proj + the next layer's qkv run as ONE kernel
+            # each (t1_stream_gemm_fold_pair) -- 3 kernels per layer instead of 5, the GEMM -> GEMM boundary is an arrival counter
+            pair = fold and self.run.decode_pair and not pf_bytes and st.get("decode_ctas", 0) in (0, None)
             for l in range(L):
                 pre = f"model.layers.{l}."
+                if pair:
+                    last = l == L - 1
+                    if l == 0:
+                        ops.rmsnorm(x, self.p(pre + "input_layernorm.weight"), eps, out=h)
+                        ops.stream_gemm(h, self.p(pre + "self_attn.qkv.weight"), ws, out=qkv, bias=self.p(pre + "self_attn.qkv.bias"))
+                    attn_tc(l)
+                    ops.stream_gemm_fold_pair(attn, self.p(pre + "self_attn.o_proj.weight"), ws, x, self.p(pre + "post_attention_layernorm.weight"),
+                                              h, fp[0], self.p(pre + "mlp.gate_up.weight"), eps, out=act, swiglu=True)
+                    if last:      # the final norm feeds the dynamically scheduled lm_head GEMM: kept as a kernel
+                        ops.stream_gemm(act, self.p(pre + "mlp.down_proj.weight"), ws, out=down)
+                    else:
+                        nxt = f"model.layers.{l + 1}."
+                        ops.stream_gemm_fold_pair(act, self.p(pre + "mlp.down_proj.weight"), ws, x, self.p(nxt + "input_layernorm.weight"),
+                                                  h, fp[1], self.p(nxt + "self_attn.qkv.weight"), eps, out=qkv,
+                                                  bias=self.p(nxt + "self_attn.qkv.bias"))
+                    continue
                 if fold:
                     last = l == L - 1
                     if pf_bytes and self.run.decode_prefetch_at == "qkv":

@@ -82,6 +82,7 @@ _SIGNATURES: dict[str, list] = {
     "t1_stream_gemm_swiglu": [vp, i64, vp, i64, vp, vp, i64, i32, i32, i32, vp, i64, vp],
     "t1_stream_gemm_fold": [vp, i64, vp, i64, i32, i32, i32, vp, vp, vp, vp, vp, i64, vp],
     "t1_stream_gemm_scaled": [vp, i64, vp, i64, vp, vp, i64, i32, i32, i32, i32, vp, i32, f32, vp, i64, vp],
+    "t1_stream_gemm_fold_pair": [vp, i64, vp, i64, i32, i32, i32, vp, vp, vp, vp, vp, i64, vp, vp, i64, i32, i32, f32, vp, i64, vp],
     "t1_stream_gemm_prefetch_next": [vp, i64, i32, i32, i32, i32, i32, i64],
     "t1_stream_gemm_workspace_bytes": [i32],
     "t1_set_pdl": [i32],

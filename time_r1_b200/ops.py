@@ -206,6 +206,25 @@ def stream_gemm_scaled(z, w, workspace, parts, n_parts, eps, out=None, bias=None
     return out
 
 
+def stream_gemm_fold_pair(x, w_a, workspace, resid, norm_w, z, parts, w_b, eps, out=None, bias=None, swiglu=False):
+    """stream_gemm_fold(x, w_a -> resid, z, parts) + stream_gemm_scaled(z, w_b, parts -> out) in ONE launch (bit-identical to
+    the two): the boundary between the GEMMs is a device-side arrival counter and the weight stream runs through it."""
+    M, K = x.shape
+    Na, Nb = w_a.shape[0], w_b.shape[0]
+    MP = 16 if M <= 16 else (32 if M <= 32 else 64)
+    cols = Nb // 2 if swiglu else Nb
+    assert x.stride(1) == 1 and w_a.stride(1) == 1 and w_b.stride(1) == 1 and w_a.shape[1] == K and w_b.shape[1] == Na and Na % 128 == 0
+    assert resid.shape == (M, Na) and resid.is_contiguous() and z.shape == (M, Na) and z.is_contiguous()
+    assert parts.dtype == F32 and parts.is_contiguous() and parts.numel() >= (Na // 128) * MP
+    if out is None:
+        out = torch.empty((M, cols), device=x.device, dtype=BF16)
+    assert out.shape == (M, cols) and out.stride(1) == 1 and out.dtype == BF16
+    call("t1_stream_gemm_fold_pair", ptr(x), x.stride(0), ptr(w_a), w_a.stride(0), M, Na, K, ptr(resid), ptr(norm_w), ptr(z), ptr(parts),
+         ptr(w_b), w_b.stride(0), ptr(bias), ptr(out), out.stride(0), Nb, 1 if swiglu else 0, float(eps), ptr(workspace),
+         workspace.numel(), stream_ptr())
+    return out
+
+
 def linear(x, w, out=None, bias=None, accumulate=False, out_dtype=BF16):
     """Dispatch on the row count: <= 64 rows stream the weights (HBM-bound), otherwise the tcgen05 tile kernel."""
     if x.shape[0] <= 64 and w.shape[0] % 16 == 0 and x.shape[1] % 32 == 0 and (bias is None or bias.dtype == BF16):

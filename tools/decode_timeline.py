@@ -28,8 +28,10 @@ def main():
         prompts.append(engine.Prompt(input_ids=ids, pixel_values=None, grid_thw=[(16, 32, 32)], second_per_grid_ts=[1.0]))
         embs.append((torch.randn(nv, cfg.hidden_size, device=dev) * 0.02).to(torch.bfloat16))
     nl = 4 * cfg.num_hidden_layers + 1
-    for pdl, stages, ctas in [(0, 0, 1), (1, 0, 1), (1, 10, 1)]:
-        run = config.RunConfig(num_generations=G, max_completion_length=200, beta=0.0, decode_impl="stream", decode_pdl=bool(pdl))
+    for pdl, stages, ctas in ([(1, 0, 1)] if os.environ.get("T1_TIMELINE_PAIR") else [(0, 0, 1), (1, 0, 1), (1, 10, 1)]):
+        run = config.RunConfig(num_generations=G, max_completion_length=200, beta=0.0, decode_impl="stream", decode_pdl=bool(pdl),
+                               decode_pair=os.environ.get("T1_TIMELINE_PAIR", "0") == "1")     # paired: one record per GEMM all the same
+        # (phase-B record of a pair: start = this CTA arrived at the counter, issued = z tiles requested, dep_ok = counter complete)
         eng = make_engine(cfg, mw, run, dev)
         lib.load().t1_stream_gemm_tune(stages, ctas)
         dbg = torch.zeros(nl * 4, device=dev, dtype=torch.int64)
