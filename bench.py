@@ -779,12 +779,14 @@ def run_verify(args):
     cfg = config.PRESETS[args.model]()
     G, C, NGLOBAL = args.group_size, 16, 8
     assert NGLOBAL % world == 0
-    run = config.RunConfig(num_generations=G, max_completion_length=C, learning_rate=1e-3)
-    mw = weights.ModelWeights(cfg, dev, world_size=world)
+    run = config.RunConfig(num_generations=G, max_completion_length=C, learning_rate=1e-3, fix_vit=not args.train_vit)
+    mw = weights.ModelWeights(cfg, dev, world_size=world, train_vit=args.train_vit)
     mw.init_random(seed=0)
     eng = engine.Engine(cfg, mw, run, rank=rank, world_size=world, process_group=pg)
     with torch.no_grad():      # policy != reference model, so the KL term and its gradient are live
         eng.w.train["model.layers.1.mlp.down_proj.weight"].mul_(1.25)
+        if args.train_vit:     # ... inside the vision tower as well (the reference model keeps its own tower)
+            eng.w.train["visual.blocks.3.attn.proj.weight"].mul_(1.25)
     grid = (4, 32, 32)
     stride = 16381
     # TWO optimizer steps: the second one starts while the first one's parameter all-gather may still be in flight (lazy
@@ -803,6 +805,16 @@ def run_verify(args):
                                 last_before_optimizer=gi + world >= NGLOBAL)
             losses.append(out["loss"].double())
         gsample = eng.grads.buf[::stride].float().clone()
+        if it == 0 and args.train_vit:     # the tower's share of the gradient: fp32 DP mean of the ranks' accumulated gradients
+            n_vit = eng.grads.layout["visual.merger.ln_q.weight"][0]
+            gv = eng.grads.buf[:n_vit].float()
+            if world > 1:
+                dist.all_reduce(gv, op=dist.ReduceOp.AVG)
+            vit_norm = float(gv.norm().item())
+            vit_blocks_norms = [float(gv[eng.grads.layout[f"visual.blocks.{b}.norm1.weight"][0]:
+                                         (eng.grads.layout[f"visual.blocks.{b + 1}.norm1.weight"][0] if b + 1 < cfg.vit_depth else n_vit)].norm().item())
+                                for b in range(cfg.vit_depth)]
+            del gv
         loss = torch.stack(losses).sum().reshape(1) / world      # each rank holds (its groups) x world / 8: the DP mean equals the N=1 sum
         if world > 1:
             dist.all_reduce(gsample, op=dist.ReduceOp.AVG)
@@ -812,13 +824,18 @@ def run_verify(args):
             w_before = eng.w.train.buf[::stride].float().clone()
             loss0, gsample0 = loss.clone(), gsample
         gnorm = eng.optimizer_step(lr=1e-3)
+        if it == 0:
+            gnorm1 = float(gnorm.item())
     eng.sync_params()
     torch.cuda.synchronize()
     w_after = eng.w.train.buf[::stride].float().clone()
     if rank == 0:
         rec = {"world": world, "loss": float(loss0.item()), "loss_step2": float(loss.item()), "grad_norm": float(gnorm.item()),
+               "grad_norm_step1": gnorm1,
                "grad_sample": gsample0.cpu(), "grad_sample_step2": gsample.cpu(),
                "w_before": w_before.cpu(), "w_after": w_after.cpu(), "stride": stride, "model": args.model, "groups": NGLOBAL, "G": G, "C": C}
+        if args.train_vit:
+            rec["vit_grad_norm"], rec["vit_block_grad_norms"] = vit_norm, vit_blocks_norms
         torch.save(rec, args.verify)
         print(json.dumps({"verify": {"world": world, "loss": rec["loss"], "loss_step2": rec["loss_step2"], "grad_norm": rec["grad_norm"],
                                      "grad_sample_l2": float(gsample.norm().item()), "out": args.verify}}), flush=True)

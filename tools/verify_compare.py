@@ -13,7 +13,11 @@ moved = (da != 0) | (db != 0)
 rec = {
     "worlds": [a["world"], b["world"]],
     "loss": [a["loss"], b["loss"]], "loss_rel_diff": abs(a["loss"] - b["loss"]) / max(1e-12, abs(a["loss"])),
-    "grad_norm": [a["grad_norm"], b["grad_norm"]], "grad_norm_rel_diff": abs(a["grad_norm"] - b["grad_norm"]) / a["grad_norm"],
+    # records written before "grad_norm_step1" existed hold only the LAST step's norm (step 2: computed on weights that moved by
+    # +-lr per element under Adam's first step, so rounding-level gradient differences are amplified; looser bar below)
+    "grad_norm": [a.get("grad_norm_step1", a["grad_norm"]), b.get("grad_norm_step1", b["grad_norm"])],
+    "grad_norm_rel_diff": abs(a.get("grad_norm_step1", a["grad_norm"]) - b.get("grad_norm_step1", b["grad_norm"])) / a.get("grad_norm_step1", a["grad_norm"]),
+    "grad_norm_step2": [a["grad_norm"], b["grad_norm"]], "grad_norm_step2_rel_diff": abs(a["grad_norm"] - b["grad_norm"]) / a["grad_norm"],
     "grad_sample_rel_l2": float((ga - gb).norm() / ga.norm()),
     "grad_sample_cosine": float(torch.nn.functional.cosine_similarity(ga, gb, dim=0)),
     "weights_before_identical": bool(torch.equal(a["w_before"], b["w_before"])),
@@ -27,8 +31,14 @@ if "loss_step2" in a and "loss_step2" in b:      # second optimizer step: comput
     rec["loss_step2"] = [a["loss_step2"], b["loss_step2"]]
     rec["loss_step2_rel_diff"] = abs(a["loss_step2"] - b["loss_step2"]) / max(1e-12, abs(a["loss_step2"]))
     rec["grad_sample_step2_rel_l2"] = float((g2a - g2b).norm() / g2a.norm())
+if "vit_grad_norm" in a and "vit_grad_norm" in b:   # fix_vit=False: the vision tower's share (fp32 DP mean of the per-rank accumulations)
+    rec["vit_grad_norm"] = [a["vit_grad_norm"], b["vit_grad_norm"]]
+    rec["vit_block_grad_norm_max_rel_diff"] = max(abs(x - y) / max(x, 1e-30) for x, y in zip(a["vit_block_grad_norms"], b["vit_block_grad_norms"]))
+    rec["vit_block_grad_norms_first_last"] = [a["vit_block_grad_norms"][0], a["vit_block_grad_norms"][-1]]
 print(json.dumps(rec))
-ok = (rec["loss_rel_diff"] < 2e-3 and rec["grad_norm_rel_diff"] < 1e-2 and rec["grad_sample_rel_l2"] < 3e-2
+step1 = "grad_norm_step1" in a and "grad_norm_step1" in b
+ok = (rec["loss_rel_diff"] < 2e-3 and rec["grad_norm_rel_diff"] < (2e-3 if step1 else 1e-2) and rec["grad_norm_step2_rel_diff"] < 3e-2
+      and rec.get("vit_block_grad_norm_max_rel_diff", 0.0) < 5e-3 and rec["grad_sample_rel_l2"] < 3e-2
       and rec["weights_before_identical"] and rec["update_cosine"] > 0.97
       and rec.get("loss_step2_rel_diff", 0.0) < 2e-2 and rec.get("grad_sample_step2_rel_l2", 0.0) < 0.1)
 print("VERIFY", "OK" if ok else "MISMATCH")
