@@ -345,6 +345,18 @@ int t1_grpo_loss(const float* logp, const float* old_logp, const float* ref_logp
 /* log_softmax gather + entropy per row of fp32 logits (timer1_trainer.py:458-481). */
 int t1_logprob_entropy(const float* logits, long long ld, int rows, int V, const int* target, float* out_logp,
                        float* out_entropy, float* out_lse, cudaStream_t stream);
+/* lm_head fused with the log-softmax statistics -- timer1_trainer.py:452-481 (logits -> log_softmax -> gather -> exp/sum entropy,
+ * per row in a Python loop) without the logits tensor: t1_gemm_lse_parts runs x = A B^T (B = lm_head [V, K]) on the tcgen05 GEMM and
+ * keeps, per 256-column tile and row, {max, sum exp(x - max), sum exp(x - max) * x, x[target[row]] or -inf} in
+ * parts[ceil(N / 256)][M][4] (fp32); t1_lse_merge folds the tiles into log p(target), entropy and log-sum-exp per row (any output
+ * may be NULL).  Same quantities as t1_gemm_bf16_tn (fp32 out) + t1_logprob_entropy. */
+int t1_gemm_lse_parts(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K, const int* target,
+                      float* parts, cudaStream_t stream);
+int t1_lse_merge(const float* parts, int n_tiles, int M, float* logp, float* entropy, float* lse, cudaStream_t stream);
+/* The backward's recomputed lm_head GEMM with t1_logits_backward in its epilogue: dlogits[M, N] (bf16) = dlogp[row] *
+ * (1[col == target[row]] - exp(x - lse[row])), x = A B^T read from the accumulator (autograd of timer1_trainer.py:458-481). */
+int t1_gemm_dlogits(const void* A, long long lda, const void* B, long long ldb, void* dlogits, long long ldd, int M, int N, int K,
+                    const int* target, const float* lse, const float* dlogp, cudaStream_t stream);
 /* dlogits = dlogp * (onehot(target) - softmax) in bf16 (autograd of the above). */
 int t1_logits_backward(const float* logits, long long ld, int rows, int V, const int* target, const float* lse,
                        const float* dlogp, void* dlogits, long long ldd, cudaStream_t stream);

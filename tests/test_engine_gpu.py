@@ -339,3 +339,24 @@ def test_kept_activation_levels_give_the_same_gradients(sampled):
         g0, g = res[0][3], res[level][3]
         cos = torch.nn.functional.cosine_similarity(g0.double(), g.double(), dim=0).item()
         assert cos > 0.99999 and (g - g0).abs().max().item() <= 2.0 ** -7 * g0.abs().max().item(), (level, cos)
+
+
+def test_fused_head_step_equals_the_unfused_one():
+    """RunConfig.fused_head (lm_head + log-softmax statistics / softmax backward in the GEMM epilogue, no logits in HBM) gives the
+    same log-probs, entropy, loss and gradients as the GEMM -> fp32 logits -> t1_logprob_entropy / t1_logits_backward chain."""
+    res = []
+    for fused in (False, True):
+        O, cfg, ocfg, w_or, eng, prompt, pix, ids, grid = build(beta=0.04)
+        eng.run.fused_head = fused
+        G, C = 4, 12
+        rng = np.random.default_rng(9)
+        comp = torch.from_numpy(rng.integers(10, 2000, (G, C))).int()
+        rewards = rng.random((G, 2)).astype(np.float32)
+        out = eng.grpo_step(prompt, lambda c: rewards, completion_override=comp)
+        torch.cuda.synchronize()
+        res.append((out["loss"].item(), out["logp"].cpu().clone(), out["entropy"].cpu().clone(), eng.grads.buf.float().cpu().clone()))
+    assert abs(res[0][0] - res[1][0]) < 1e-6
+    assert torch.allclose(res[0][1], res[1][1], atol=2e-5) and torch.allclose(res[0][2], res[1][2], atol=1e-4)
+    g0, g1 = res[0][3], res[1][3]
+    assert torch.nn.functional.cosine_similarity(g0.double(), g1.double(), dim=0).item() > 0.99999
+    assert (g1 - g0).abs().max().item() <= 2.0 ** -6 * g0.abs().max().item()

@@ -767,6 +767,31 @@ def test_logprob_entropy_and_logits_backward():
     close(d, la.grad, 1e-5, 1e-2, "dlogits (bf16)")
 
 
+@pytest.mark.parametrize("M,V,K", [(64, 2048, 256), (5, 1000, 264), (300, 19008, 512), (1600, 152064, 3584), (130, 4096, 128)])
+def test_fused_lm_head_matches_the_unfused_chain(M, V, K):
+    """t1_gemm_lse_parts + t1_lse_merge == GEMM (fp32 logits) -> t1_logprob_entropy, and t1_gemm_dlogits == GEMM ->
+    t1_logits_backward: the same accumulators, the statistics folded per 256-column tile (partial last tile, 1-CTA and 2-CTA
+    kernels, rows past a 128-row tile edge); also against torch fp32 on the bf16 operands."""
+    from time_r1_b200 import ops
+
+    h, w = rnd(M, K, seed=M + 1, scale=1.0), rnd(V, K, seed=V + 2, scale=2.0 / math.sqrt(K))
+    tgt = torch.randint(0, V, (M,), device=DEV, dtype=torch.int32, generator=torch.Generator(device=DEV).manual_seed(3))
+    tgt[0], tgt[-1] = 0, V - 1
+    logits = ops.gemm(h, w, out_dtype=torch.float32)
+    lp0, ent0, lse0 = ops.logprob_entropy(logits, tgt)
+    lp, ent, lse = ops.head_logprob_entropy(h, w, tgt)
+    close(lse, lse0, 2e-5, 2e-6, "lse fused vs unfused")
+    close(lp, lp0, 2e-5, 2e-6, "logp fused vs unfused")
+    close(ent, ent0, 1e-4, 1e-5, "entropy fused vs unfused")
+    ref = torch.log_softmax(h.float() @ w.float().t(), -1)
+    close(lp, ref.gather(1, tgt.long()[:, None])[:, 0], 2e-3, 1e-3, "logp vs torch")
+    close(ent, -(ref.exp() * ref).sum(-1), 2e-3, 1e-3, "entropy vs torch")
+    dlogp = torch.randn(M, device=DEV, generator=torch.Generator(device=DEV).manual_seed(4))
+    d0 = ops.logits_backward(logits, tgt, lse0, dlogp)
+    d = ops.head_dlogits(h, w, tgt, lse0, dlogp)
+    assert torch.equal(d, d0), f"dlogits fused vs unfused: max diff {(d.float() - d0.float()).abs().max().item():.3g}"
+
+
 @pytest.mark.parametrize("use_grpo", [False, True])
 @pytest.mark.parametrize("beta", [0.0, 0.04])
 def test_grpo_loss_matches_autograd(use_grpo, beta):

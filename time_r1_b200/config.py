@@ -160,6 +160,10 @@ class RunConfig:
     ref_quirk_mrope: bool = True   # scoring pass omits second_per_grid_ts (timer1_trainer.py:601-607)
     seed: int = 42
     logit_chunk_rows: int = 2048
+    # lm_head fused with log-softmax / gather / entropy (forward) and with the softmax backward (recompute) in the tcgen05 GEMM
+    # epilogue: fp32 logits never reach HBM (t1_gemm_lse_parts + t1_lse_merge, t1_gemm_dlogits); False = GEMM -> fp32 logits chunk
+    # -> t1_logprob_entropy / t1_logits_backward (the A/B arm)
+    fused_head: bool = os.environ.get("T1_FUSED_HEAD", "1") != "0"
     # what the forward passes keep for the backward besides the layer inputs: 0 / False = nothing (recompute all),
     # 1 = gate_up projections, 2 / True = + q/k/v, attention output, LSE; "auto" = as much as the free HBM allows
     save_gate_up: object = "auto"

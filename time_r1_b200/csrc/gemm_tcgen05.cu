@@ -43,6 +43,8 @@ enum : int {
   GEMM_SWIGLU = 32,     // B = [W_gate; W_up] ([2N, K], K-major): D[M, N] = silu(A Wg^T + bg) * (A Wu^T + bu), bf16; each
                         // 256-wide tile pairs 128 gate rows with their 128 up rows (t1_gemm_swiglu)
   GEMM_TMA_STORE = 64,  // (internal) the epilogue stores through the tensor maps of D (and of the gate / up halves of D2)
+  GEMM_LSE_PARTS = 128, // (t1_gemm_lse_parts) no D: per (256-column tile, row) softmax statistics of the accumulator row
+  GEMM_DLOGITS = 256,   // (t1_gemm_dlogits) D = bf16(dlogp[row] * (1[col == target[row]] - exp(acc - lse[row])))
 };
 constexpr int MN_ATOM_BYTES = BK * 128;   // MN-major smem atom: [64 k-rows x 64 elements], SWIZZLE_128B
 
@@ -53,6 +55,10 @@ struct EpiParams {
   int flags;
   void* D2;         // SWIGLU: optional [M, 2N] bf16 copy of the gate_up projection (kept for the backward pass)
   long long ldd2;
+  // fused lm_head epilogues (timer1_trainer.py:452-481: logits -> log_softmax -> gather -> entropy, never materialised here)
+  const int* tgt;        // [M] target column per row
+  const float* row_lse;  // [M] log-sum-exp per row   (DLOGITS)
+  const float* row_g;    // [M] d loss / d logp       (DLOGITS)
 };
 
 // Per-warp state of the TMA-store epilogue: this warp's two [32 x 64] bf16 staging boxes; lane 0 owns the bulk async-groups.
@@ -91,7 +97,56 @@ __device__ __forceinline__ void gemm_epilogue_tile(const EpiParams& epi, const C
     ++ew.n_store;
   };
   const int row = row_base + lane;
-      if (swiglu && tma_out) {
+  const bool dlog = epi.flags & GEMM_DLOGITS;
+  int d_tgt = -1;
+  float d_lse = 0.f, d_g = 0.f;
+  if (dlog && row < M) {
+    d_tgt = epi.tgt[row];
+    d_lse = epi.row_lse[row];
+    d_g = epi.row_g[row];
+  }
+  // dlogits: v[j] (accumulator of column col0 + j) -> dlogp * (onehot - softmax), the formula of t1_logits_backward
+  auto dlog_x32 = [&](uint32_t* v, int col0) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      v[j] = __float_as_uint(d_g * (((col0 + j) == d_tgt ? 1.f : 0.f) - expf(__uint_as_float(v[j]) - d_lse)));
+  };
+      if (epi.flags & GEMM_LSE_PARTS) {
+        // one TMEM lane == one logits row: running max, sum exp(x - max), sum exp(x - max) * x and the target's logit over this
+        // tile's columns, all in this thread's registers (no cross-thread traffic); t1_lse_merge folds the tiles of a row
+        float m = -INFINITY, ssum = 0.f, tsum = 0.f, tl = -INFINITY;
+        const int tg = row < M ? epi.tgt[row] : -1;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          const int col0 = n_blk * BN + c * 32;
+          if (col0 >= N) break;  // warp-uniform
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(taddr_row + c * 32, v);
+          tmem_ld_wait();
+          const int nv = min(32, N - col0);
+          float cm = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < nv) cm = fmaxf(cm, __uint_as_float(v[j]));
+          if (cm > m) {
+            const float sc = expf(m - cm);
+            ssum *= sc;
+            tsum *= sc;
+            m = cm;
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (j < nv) {
+              const float x = __uint_as_float(v[j]);
+              const float e = expf(x - m);
+              ssum += e;
+              tsum += e * x;
+              if (col0 + j == tg) tl = x;
+            }
+          }
+        }
+        if (row < M) reinterpret_cast<float4*>(epi.D)[(long long)n_blk * M + row] = make_float4(m, ssum, tsum, tl);
+      } else if (swiglu && tma_out) {
         // as below, 64 output columns at a time: y, and (when kept for the backward) g and u, leave through TMA stores
         const int row0 = row_base;
 #pragma unroll 1
@@ -227,6 +282,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const EpiParams& epi, const C
                 }
               }
             }
+            if (dlog) dlog_x32(v, col0 + hlf * 32);
 #pragma unroll
             for (int j = 0; j < 16; ++j) pk[hlf * 16 + j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
           }
@@ -240,6 +296,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const EpiParams& epi, const C
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr_row + c * 32, v);
         tmem_ld_wait();
+        if (dlog) dlog_x32(v, col0);
         if (row < M) {
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
@@ -685,7 +742,8 @@ static int g_gemm_max_ctas = 0;   // t1_gemm_max_ctas(): cap on the persistent g
 extern "C" void t1_gemm_max_ctas(int n) { g_gemm_max_ctas = n > 0 ? n : 0; }
 
 static int gemm_impl(const void* A, long long lda, const void* B, long long ldb, void* D, long long ldd, int M, int N, int K,
-                     const void* bias, int flags, void* D2, long long ldd2, cudaStream_t stream) {
+                     const void* bias, int flags, void* D2, long long ldd2, cudaStream_t stream, const int* tgt = nullptr,
+                     const float* row_lse = nullptr, const float* row_g = nullptr) {
   T1_CHECK_ARG(A && B && D, "t1_gemm_bf16_tn: null operand");
   T1_CHECK_ARG(M > 0 && N > 0 && K > 0, "t1_gemm_bf16_tn: empty problem M=%d N=%d K=%d", M, N, K);
   T1_CHECK_ARG(N % 8 == 0 && ldd % 8 == 0, "t1_gemm_bf16_tn: N and ldd must be multiples of 8 (N=%d ldd=%lld)", N, ldd);
@@ -703,7 +761,7 @@ static int gemm_impl(const void* A, long long lda, const void* B, long long ldb,
   const int num_m = (M + BM - 1) / BM;
   const int sms = t1_num_sms();
   int BN = 256;
-  {
+  if (!(flags & GEMM_LSE_PARTS)) {
     static const char* env = getenv("T1_GEMM_BN");
     if (env && (atoi(env) == 192 || (atoi(env) == 224 && !b_mn))) BN = atoi(env);
   }
@@ -728,7 +786,7 @@ static int gemm_impl(const void* A, long long lda, const void* B, long long ldb,
   CUtensorMap td = ta, tdg = ta, tdu = ta;
   {
     static const char* env = getenv("T1_GEMM_EPI");
-    const bool want = !(env && env[0] == 'd') && !(flags & (GEMM_OUT_F32 | GEMM_ACCUMULATE)) && BN % 64 == 0;
+    const bool want = !(env && env[0] == 'd') && !(flags & (GEMM_OUT_F32 | GEMM_ACCUMULATE | GEMM_LSE_PARTS)) && BN % 64 == 0;
     if (want) {
       rc = t1_make_tmap_bf16(&td, D, M, N, ldd, 32, 64);
       if (rc) return rc;
@@ -741,7 +799,7 @@ static int gemm_impl(const void* A, long long lda, const void* B, long long ldb,
       flags |= GEMM_TMA_STORE;
     }
   }
-  EpiParams epi{D, bias, ldd, flags, swiglu ? D2 : nullptr, ldd2};
+  EpiParams epi{D, bias, ldd, flags, swiglu ? D2 : nullptr, ldd2, tgt, row_lse, row_g};
   // DRAM-traffic model for the raster order (L2 = 126 MB; measured with ncu on the gate_up wgrad, M=37888 N=3584 K=5888:
   // m-fastest re-read dY 14x = 6.3 GB per launch).  An operand that fits in ~48 MB of L2 is read once whatever the order;
   // otherwise keep a group of A row-blocks resident (<= 40 MB) while B streams past it.
@@ -784,7 +842,7 @@ static int gemm_impl(const void* A, long long lda, const void* B, long long ldb,
       // (profiles/r02_gemm2_tile_width.txt): 1672 x 3584 x 3584 0.060 -> 0.048 ms, 16384 x 3840 x 1280 0.132 -> 0.110 ms, but
       // 4216 x 3584 x 18944 0.536 -> 0.611 ms and the whole step 1407 -> 1441 ms when every shape may narrow (more A re-reads)
       int bn2 = 256;
-      if (!swiglu && (M <= 2048 || K <= 2048)) {
+      if (!swiglu && !(flags & GEMM_LSE_PARTS) && (M <= 2048 || K <= 2048)) {      // (the statistics tiles are 256 columns by contract)
         static const char* envbn = getenv("T1_GEMM2_BN");
         double best = 1e30;
         for (int cand : {256, 192, 128}) {
@@ -895,4 +953,22 @@ extern "C" int t1_gemm_bf16_tn(const void* A, long long lda, const void* B, long
 extern "C" int t1_gemm_swiglu(const void* A, long long lda, const void* W, long long ldw, const void* bias, void* act,
                               long long ld_act, void* gate_up, long long ld_gate_up, int M, int I, int K, cudaStream_t stream) {
   return gemm_impl(A, lda, W, ldw, act, ld_act, M, I, K, bias, GEMM_SWIGLU, gate_up, ld_gate_up, stream);
+}
+
+// ---- lm_head fused with the log-softmax statistics (timer1_trainer.py:452-481): logits never reach HBM ----
+// parts[ceil(N / 256)][M][4] fp32 = per 256-column tile and row: {max, sum exp(x - max), sum exp(x - max) * x, x[target[row]] if the
+// target falls into the tile else -inf} of x = A B^T (fp32 accumulators).  t1_lse_merge folds the tiles into logp / entropy / lse.
+extern "C" int t1_gemm_lse_parts(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K, const int* target,
+                                 float* parts, cudaStream_t stream) {
+  T1_CHECK_ARG(target && parts && ((uintptr_t)parts & 15) == 0, "t1_gemm_lse_parts: target / parts (16-byte aligned) required");
+  // D is only used as the parts pointer; ldd is irrelevant (pass N to satisfy the generic checks)
+  return gemm_impl(A, lda, B, ldb, parts, (N + 7) / 8 * 8, M, N, K, nullptr, GEMM_OUT_F32 | GEMM_LSE_PARTS, nullptr, 0, stream, target);
+}
+
+// dlogits[M, N] (bf16) = dlogp[row] * (1[col == target[row]] - exp(x - lse[row])) with x = A B^T straight from the accumulator:
+// the recomputed lm_head GEMM of the backward with t1_logits_backward in its epilogue (no fp32 logits in HBM).
+extern "C" int t1_gemm_dlogits(const void* A, long long lda, const void* B, long long ldb, void* dlogits, long long ldd, int M, int N,
+                               int K, const int* target, const float* lse, const float* dlogp, cudaStream_t stream) {
+  T1_CHECK_ARG(target && lse && dlogp, "t1_gemm_dlogits: target / lse / dlogp required");
+  return gemm_impl(A, lda, B, ldb, dlogits, ldd, M, N, K, nullptr, GEMM_DLOGITS, nullptr, 0, stream, target, lse, dlogp);
 }

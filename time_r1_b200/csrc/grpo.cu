@@ -225,6 +225,47 @@ logprob_entropy_kernel(const float* __restrict__ logits, long long ld, int V, co
   }
 }
 
+// Fold the per-tile softmax statistics of t1_gemm_lse_parts (parts[n_tiles][M][4] = max, sum exp(x - max), sum exp(x - max) * x,
+// target logit or -inf) into log p(target), entropy and log-sum-exp per row: one warp per row, same formulas as above.
+__global__ void lse_merge_kernel(const float4* __restrict__ parts, int n_tiles, int M, float* __restrict__ out_logp,
+                                 float* __restrict__ out_entropy, float* __restrict__ out_lse) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= M) return;
+  float m = -INFINITY, s = 0.f, t = 0.f, tl = -INFINITY;
+  for (int i = lane; i < n_tiles; i += 32) {
+    const float4 p = parts[(size_t)i * M + r];
+    if (p.x > m) {
+      const float sc = expf(m - p.x);
+      s *= sc;
+      t *= sc;
+      m = p.x;
+    }
+    const float e = (p.x == -INFINITY) ? 0.f : expf(p.x - m);
+    s += p.y * e;
+    t += p.z * e;
+    tl = fmaxf(tl, p.w);
+  }
+  float gm = m;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) gm = fmaxf(gm, __shfl_xor_sync(0xffffffffu, gm, o));
+  const float sc = (m == -INFINITY) ? 0.f : expf(m - gm);
+  s *= sc;
+  t *= sc;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    t += __shfl_xor_sync(0xffffffffu, t, o);
+    tl = fmaxf(tl, __shfl_xor_sync(0xffffffffu, tl, o));
+  }
+  if (lane == 0) {
+    const float lse = gm + logf(s);
+    if (out_lse) out_lse[r] = lse;
+    if (out_logp) out_logp[r] = tl - lse;
+    if (out_entropy) out_entropy[r] = lse - t / s;
+  }
+}
+
 // dlogits[r, v] = dlogp[r] * (1[v == target[r]] - exp(x - lse[r]))   (bf16 out, fp32 in)
 __global__ void __launch_bounds__(1024, 1)
 logits_backward_kernel(const float* __restrict__ logits, long long ld, int V, const int* __restrict__ target,
@@ -318,6 +359,14 @@ extern "C" int t1_logprob_entropy(const float* logits, long long ld, int rows, i
   T1_CHECK_ARG(ld % 4 == 0 && ((uintptr_t)logits & 15) == 0, "t1_logprob_entropy: logits rows must be 16-byte aligned");
   logprob_entropy_kernel<<<rows, 1024, 0, stream>>>(logits, ld, V, target, out_logp, out_entropy, out_lse);
   T1_CUDA_LAUNCH_CHECK("t1_logprob_entropy");
+  return T1_OK;
+}
+
+extern "C" int t1_lse_merge(const float* parts, int n_tiles, int M, float* logp, float* entropy, float* lse, cudaStream_t stream) {
+  if (M == 0) return T1_OK;
+  T1_CHECK_ARG(parts && n_tiles > 0 && M > 0 && ((uintptr_t)parts & 15) == 0, "t1_lse_merge: bad arguments");
+  lse_merge_kernel<<<(M * 32 + 255) / 256, 256, 0, stream>>>(reinterpret_cast<const float4*>(parts), n_tiles, M, logp, entropy, lse);
+  T1_CUDA_LAUNCH_CHECK("t1_lse_merge");
   return T1_OK;
 }
 

@@ -976,6 +976,9 @@ class Engine:
                     R=R, Rp=Rp)
 
     def _head_forward(self, hsel: torch.Tensor, targets: torch.Tensor, wset: str):
+        if getattr(self.run, "fused_head", True):
+            # lm_head + log-softmax + gather + entropy in the GEMM epilogue (timer1_trainer.py:452-481): no logits in HBM
+            return ops.head_logprob_entropy(hsel, self.lm_head(wset), targets)
         Rp = hsel.shape[0]
         lp = torch.empty(Rp, device=self.dev, dtype=F32)
         ent = torch.empty(Rp, device=self.dev, dtype=F32)
@@ -1095,9 +1098,12 @@ class Engine:
         first = True
         for a in range(0, Rp, step):
             b = min(Rp, a + step)
-            logits = ops.gemm(st.hsel[a:b], W, out_dtype=F32)               # recompute (1.7 TFLOP at cfg2)
-            dlog = ops.logits_backward(logits, st.targets[a:b], st.lse[a:b], dl[a:b])
-            del logits
+            if getattr(self.run, "fused_head", True):   # recompute (1.7 TFLOP at cfg2) with the softmax backward in the epilogue
+                dlog = ops.head_dlogits(st.hsel[a:b], W, st.targets[a:b], st.lse[a:b], dl[a:b])
+            else:
+                logits = ops.gemm(st.hsel[a:b], W, out_dtype=F32)
+                dlog = ops.logits_backward(logits, st.targets[a:b], st.lse[a:b], dl[a:b])
+                del logits
             ops.gemm(dlog, W, out=dhsel[a:b], b_t=True)
             ops.gemm(dlog, st.hsel[a:b], out=self._gview(head_name), accumulate=acc or not first, a_t=True, b_t=True)
             first = False

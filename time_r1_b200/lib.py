@@ -35,6 +35,9 @@ _SIGNATURES: dict[str, list] = {
     "t1_grpo_loss": [vp, vp, vp, vp, vp, vp, i32, i32, f32, f32, f32, i32, f32, vp, vp, vp, vp],
     "t1_logprob_entropy": [vp, i64, i32, i32, vp, vp, vp, vp, vp],
     "t1_logits_backward": [vp, i64, i32, i32, vp, vp, vp, vp, i64, vp],
+    "t1_gemm_lse_parts": [vp, i64, vp, i64, i32, i32, i32, vp, vp, vp],
+    "t1_lse_merge": [vp, i32, i32, vp, vp, vp, vp],
+    "t1_gemm_dlogits": [vp, i64, vp, i64, vp, i64, i32, i32, i32, vp, vp, vp, vp],
     "t1_eos_mask": [vp, i32, i32, i32, vp, vp, vp],
     # answer_scan.cu
     "t1_detokenize": [vp, i32, i32, vp, vp, vp, vp, i32, i32, vp, i32, vp, vp],

@@ -498,6 +498,40 @@ def logprob_entropy(logits, target):
     return lp, ent, lse
 
 
+def head_logprob_entropy(h, w, target):
+    """log p(target), entropy and log-sum-exp per row of softmax(h @ w^T) WITHOUT the logits tensor: the tcgen05 GEMM keeps per
+    256-column tile and row (max, sum exp, sum exp * x, target logit) and t1_lse_merge folds the tiles."""
+    M, K = h.shape
+    V = w.shape[0]
+    assert h.dtype == BF16 and w.dtype == BF16 and h.stride(1) == 1 and w.stride(1) == 1 and w.shape[1] == K
+    assert target.dtype == I32 and target.numel() == M and target.is_contiguous()
+    n_tiles = (V + 255) // 256
+    parts = torch.empty((n_tiles, M, 4), device=h.device, dtype=F32)
+    e0 = PROFILER.begin()
+    call("t1_gemm_lse_parts", ptr(h), h.stride(0), ptr(w), w.stride(0), M, V, K, ptr(target), ptr(parts), stream_ptr())
+    PROFILER.end("gemm_bf16_tn", 2.0 * M * V * K, 2.0 * (M * K + V * K) + 16.0 * n_tiles * M, e0)
+    lp = torch.empty(M, device=h.device, dtype=F32)
+    ent = torch.empty(M, device=h.device, dtype=F32)
+    lse = torch.empty(M, device=h.device, dtype=F32)
+    call("t1_lse_merge", ptr(parts), n_tiles, M, ptr(lp), ptr(ent), ptr(lse), stream_ptr())
+    return lp, ent, lse
+
+
+def head_dlogits(h, w, target, lse, dlogp, out=None):
+    """bf16 dlogits = dlogp * (onehot(target) - softmax(h @ w^T)) straight from the GEMM accumulator (no fp32 logits)."""
+    M, K = h.shape
+    V = w.shape[0]
+    if out is None:
+        out = torch.empty((M, V), device=h.device, dtype=BF16)
+    assert out.shape == (M, V) and out.dtype == BF16 and out.stride(1) == 1
+    assert target.dtype == I32 and lse.dtype == F32 and dlogp.dtype == F32
+    e0 = PROFILER.begin()
+    call("t1_gemm_dlogits", ptr(h), h.stride(0), ptr(w), w.stride(0), ptr(out), out.stride(0), M, V, K, ptr(target), ptr(lse),
+         ptr(dlogp), stream_ptr())
+    PROFILER.end("gemm_bf16_tn", 2.0 * M * V * K, 2.0 * (M * K + V * K) + 2.0 * M * V, e0)
+    return out
+
+
 def logits_backward(logits, target, lse, dlogp, out=None):
     R, V = logits.shape
     if out is None:
