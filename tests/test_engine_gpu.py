@@ -104,6 +104,23 @@ def test_decode_attention_forms_roll_out_the_same_tokens():
         assert torch.equal(outs[name], outs["cluster"]), name
 
 
+def test_eager_multi_step_decode_equals_the_captured_graph():
+    """use_graph=False runs the decode steps back to back on one stream with programmatic dependent launch: kernels down the chain
+    read the previous step's state (step counter, K/V rows) BEFORE their griddepcontrol.wait, so each step's first kernel must be a
+    plain stream-order boundary (a graph launch is one by construction).  Regression: sampled eager != sampled graph on the same
+    engine before that boundary existed."""
+    O, cfg, ocfg, w_or, eng, prompt, pix, ids, grid = build(beta=0.0)
+    G, C = 4, 24
+    emb, _, _ = eng.vit_forward(prompt)
+    a = eng.rollout(prompt, emb, G, C, temperature=1.0, top_k=50, seed=11)
+    for _ in range(3):
+        b = eng.rollout(prompt, emb, G, C, temperature=1.0, top_k=50, seed=11, use_graph=False)
+        assert torch.equal(a, b)
+    c = eng.rollout(prompt, emb, G, C, temperature=0.0, top_k=0, seed=1)
+    d = eng.rollout(prompt, emb, G, C, temperature=0.0, top_k=0, seed=1, use_graph=False)
+    assert torch.equal(c, d)
+
+
 def test_sampled_rollout_and_decode_logits_consistency():
     """Sampled tokens scored by the packed scoring pass must have the log-probs the decode path sampled from:
     decode (prefix-shared KV + skinny GEMMs) and scoring (packed tcgen05 path) are two routes to the same logits."""

@@ -670,11 +670,16 @@ class Engine:
         x, h, qkv, attn, o, gu, act, down = st["x"], st["h"], st["qkv"], st["attn"], st["o"], st["gu"], st["act"], st["down"]
         ws, tab = st["gemm_ws"], st["group_table"]
         from .lib import load
-        load().t1_set_pdl(1 if self.run.decode_pdl else 0)
         load().t1_stream_gemm_max_ctas(int(st.get("decode_ctas", 0)))      # leave SMs to the overlapped reference prefill
         try:
             s = stream_ptr()
+            # The step's FIRST kernel is launched in plain stream order (no programmatic edge): kernels further down the chain read
+            # state of the previous step before their own griddepcontrol.wait (the attention prologue reads the step counter and
+            # prefetches K/V), which is only safe if nothing of this step starts before the previous step has completed.  Inside a
+            # captured graph this is the graph boundary anyway; it matters for eager multi-step runs (use_graph=False).
+            load().t1_set_pdl(0)
             ops.gather_rows(self.p("model.embed_tokens.weight"), st["next_ids"], out=x)
+            load().t1_set_pdl(1 if self.run.decode_pdl else 0)
             fuse_norm = self.run.decode_fuse_norm and cfg.hidden_size % 8 == 0
             # folded norms: the o / down GEMM epilogues update the residual stream and emit z = norm_w * resid plus per-slab
             # row sums of squares; the next GEMM streams against z and applies the row factor in its epilogue
