@@ -198,6 +198,11 @@ class RunConfig:
     # boundary it replaces (7.3 / 7.0 us: both wait for the slowest CTA's fix-up, not for the launch machinery) -- and the
     # two-phase producer issues its loads slower (gate_up 49 vs 40 us): 3.66 vs 3.20 ms per decode step.  OFF by default.
     decode_pair: bool = os.environ.get("T1_DECODE_PAIR", "0") == "1"
+    # CTAs of the decode step's o_proj GEMM: 0 = one per SM, -1 = only as many as the cluster-form attention launch leaves free
+    # (148 - 8 * Hkv * groups), n > 0 = that many
+    decode_o_ctas: int = int(os.environ.get("T1_DECODE_O_CTAS", "0"))
+    decode_qkv_ctas: int = int(os.environ.get("T1_DECODE_QKV_CTAS", "0"))
+    decode_down_ctas: int = int(os.environ.get("T1_DECODE_DOWN_CTAS", "0"))
     # MB of each layer's gate_up weights pulled into L2 (t1_stream_gemm_prefetch_next) by the idle warps of the qkv ("qkv")
     # or o_proj ("o") GEMM of the same layer while the chain is latency-bound (qkv -> attention -> o); 0 = off
     decode_prefetch_mb: int = int(os.environ.get("T1_DECODE_PF_MB", "0"))

@@ -1238,6 +1238,21 @@ static SgPlan sg_plan(int M, int N, int K, int swiglu, bool fold_producer) {
   if (max_ctas > 2 * t1_num_sms()) max_ctas = 2 * t1_num_sms();
   if (g_max_ctas > 0 && g_max_ctas < max_ctas) max_ctas = g_max_ctas;     // leave SMs to a concurrent stream (experiments)
   pl.per = (int)((pl.total + max_ctas - 1) / max_ctas);
+  // Small GEMMs -- the weights about fit the rings of the grid (o_proj, qkv of the decode step): nothing streams for long, the
+  // launch is latency-bound and its tail is the split-slab fix-up.  Cut the unit ranges at slab-aligned points (per divides the
+  // slab's k-blocks, or is a multiple of them) when that costs <= 40 % more units per CTA: every CTA then works on ONE slab, writes
+  // one partial tile, and a finisher fetches all its contributors in one batch.  Measured on B200 (7B decode step, o_proj
+  // 1568 units: 11 per CTA on 143 CTAs -> 14 per CTA on 112 CTAs, exactly 4 CTAs per slab): 3.21 -> 3.17 ms per decode step
+  // (profiles/r02_decode_o_ctas_sweep.txt); the streaming-bound GEMMs keep the equal-bytes split (down_proj aligned: slower).
+  const int align = env_int("T1_STREAM_ALIGN", 1);      // (read per call: A/B runs toggle it inside one process)
+  if (align && pl.kblocks > 1 && pl.total <= 3LL * stages * max_ctas / 2) {
+    for (int cand = pl.per; cand <= pl.per + (2 * pl.per + 4) / 5; ++cand) {
+      if (pl.kblocks % cand == 0 || cand % pl.kblocks == 0) {
+        pl.per = cand;
+        break;
+      }
+    }
+  }
   pl.grid = (int)((pl.total + pl.per - 1) / pl.per);
   return pl;
 }

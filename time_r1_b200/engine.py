@@ -709,6 +709,13 @@ class Engine:
             # paired launches (RunConfig.decode_pair): o_proj + gate_up and down_proj + the next layer's qkv run as ONE kernel
             # each (t1_stream_gemm_fold_pair) -- 3 kernels per layer instead of 5, the GEMM -> GEMM boundary is an arrival counter
             pair = fold and self.run.decode_pair and not pf_bytes and st.get("decode_ctas", 0) in (0, None)
+            # CTAs of the o_proj GEMM (0 = all SMs).  The cluster-form attention launch holds 8 * Hkv * n SMs; o_proj CTAs that only
+            # become resident when those exit start their weight load on the chain's critical path
+            o_ctas = int(getattr(self.run, "decode_o_ctas", 0)) if (form == "cluster" and not st.get("decode_ctas", 0)) else 0
+            qkv_ctas = int(getattr(self.run, "decode_qkv_ctas", 0)) if not st.get("decode_ctas", 0) else 0
+            down_ctas = int(getattr(self.run, "decode_down_ctas", 0)) if not st.get("decode_ctas", 0) else 0
+            if o_ctas < 0:
+                o_ctas = max(16, torch.cuda.get_device_properties(self.dev).multi_processor_count - 8 * Hkv * n)
             for l in range(L):
                 pre = f"model.layers.{l}."
                 if pair:
@@ -735,19 +742,31 @@ class Engine:
                         ops.rmsnorm(x, self.p(pre + "input_layernorm.weight"), eps, out=h)
                         ops.stream_gemm(h, self.p(pre + "self_attn.qkv.weight"), ws, out=qkv, bias=self.p(pre + "self_attn.qkv.bias"))
                     else:
+                        if qkv_ctas:
+                            load().t1_stream_gemm_max_ctas(qkv_ctas)
                         ops.stream_gemm_scaled(h, self.p(pre + "self_attn.qkv.weight"), ws, fp[1], D // 128, eps, out=qkv,
                                                bias=self.p(pre + "self_attn.qkv.bias"))
+                        if qkv_ctas:
+                            load().t1_stream_gemm_max_ctas(int(st.get("decode_ctas", 0)))
                     attn_tc(l)
                     if pf_bytes and self.run.decode_prefetch_at == "o":
                         prefetch_gate_up(l)
+                    if o_ctas:     # o_proj only on SMs the attention launch leaves free: every CTA is resident (ring full) when attention ends
+                        load().t1_stream_gemm_max_ctas(o_ctas)
                     ops.stream_gemm_fold(attn, self.p(pre + "self_attn.o_proj.weight"), ws, x,
                                          self.p(pre + "post_attention_layernorm.weight"), h, fp[0])
+                    if o_ctas:
+                        load().t1_stream_gemm_max_ctas(int(st.get("decode_ctas", 0)))
                     ops.stream_gemm_scaled(h, self.p(pre + "mlp.gate_up.weight"), ws, fp[0], D // 128, eps, out=act, swiglu=True)
                     if last:      # the final norm feeds the dynamically scheduled lm_head GEMM: kept as a kernel
                         ops.stream_gemm(act, self.p(pre + "mlp.down_proj.weight"), ws, out=down)
                     else:
+                        if down_ctas:
+                            load().t1_stream_gemm_max_ctas(down_ctas)
                         ops.stream_gemm_fold(act, self.p(pre + "mlp.down_proj.weight"), ws, x,
                                              self.p(f"model.layers.{l + 1}.input_layernorm.weight"), h, fp[1])
+                        if down_ctas:
+                            load().t1_stream_gemm_max_ctas(int(st.get("decode_ctas", 0)))
                     continue
                 if l == 0 or not fuse_norm:
                     ops.rmsnorm(x, self.p(pre + "input_layernorm.weight"), eps, delta=down if (l > 0 and not fuse_norm) else None, out=h)
