@@ -94,7 +94,14 @@ struct SgParams {
   int pf_skip, pf_units;  // per CTA of the next launch: units [skip, skip + units) of its range
   int pf_swiglu, pf_half_n;
   int pf_mode;            // 1: per-line prefetch.global.L2, 2: cp.async.bulk.prefetch.L2 per row segment
+  int early_resid;        // folded norm: fetch the residual column before the accumulator wait (T1_STREAM_EARLY_RESID=0: after it)
+  int fast_sync;          // split-slab hand-over: bar.sync + ONE acq_rel atomic instead of 128 x membar.gl + atomic + membar.gl
 };
+__device__ __forceinline__ int atom_add_acq_rel_gpu(int* p, int v) {
+  int old;
+  asm volatile("atom.add.acq_rel.gpu.global.s32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+  return old;
+}
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // The prefetch warp walks the units [skip, skip + units) of every next-launch CTA it is responsible for.
@@ -178,6 +185,22 @@ __device__ __forceinline__ int sg_epilogue(const SgParams& p, uint8_t* smem, int
     const int kb1 = min(KB, kb0 + (u1 - u));
     const int acc = it & 1;
     const uint32_t acc_phase = (it >> 1) & 1;
+    // folded norm: this thread's residual column (and norm weight) is fetched BEFORE the accumulator wait -- nothing else writes
+    // column n during the launch (only its own slab's finisher does, below) -- so its L2 round trip leaves the chain's critical path
+    constexpr bool kEarlyResid = MP <= 16;
+    bf16 xold[kEarlyResid ? MP : 1];
+    float gw_early = 0.f;
+    float bias_early = 0.f;          // plain epilogue: this thread's bias element, fetched ahead of the wait for the same reason
+    if (p.bias && !p.swiglu && p.early_resid) {
+      const int n_e = slab * SG_BM + r;
+      if (n_e < p.N) bias_early = __bfloat162float(p.bias[n_e]);
+    }
+    if (kEarlyResid && p.fold_x && p.early_resid) {
+      const int n_e = slab * SG_BM + r;
+      gw_early = __bfloat162float(p.fold_w[n_e]);
+#pragma unroll
+      for (int m = 0; m < (kEarlyResid ? MP : 1); ++m) xold[m] = m < p.M ? __ldcg(p.fold_x + (long long)m * p.N + n_e) : __float2bfloat16(0.f);
+    }
     mbar_wait(&tmem_full_bar[acc], acc_phase);
     tc_fence_after();
     uint32_t v[MP];
@@ -199,12 +222,14 @@ __device__ __forceinline__ int sg_epilogue(const SgParams& p, uint8_t* smem, int
       float* mine = p.ws + ((size_t)(blockIdx.x * 2 + (it == it0 ? 0 : 1)) * MP) * SG_BM;
 #pragma unroll
       for (int m = 0; m < MP; ++m) mine[m * SG_BM + r] = __uint_as_float(v[m]);
-      __threadfence();
+      // release: the partial tile is visible device-wide before the arrival is.  fast_sync: the CTA barrier orders the 128
+      // threads' stores before thread 0's acq_rel atomic (cumulativity), which is also the acquire for the finisher's reads
+      if (!p.fast_sync) __threadfence();
       epi_bar_sync();
       c_first = (slab * KB) / p.per_cta;
       c_last = ((slab + 1) * KB - 1) / p.per_cta;
       if (et == 0) {
-        const int old = atomicAdd(&p.counters[slab], 1);
+        const int old = p.fast_sync ? atom_add_acq_rel_gpu(&p.counters[slab], 1) : atomicAdd(&p.counters[slab], 1);
         const int last = (old == c_last - c_first) ? 1 : 0;
         if (last) p.counters[slab] = 0;         // self-resetting: the next launch finds zeros
         *s_flag = last;
@@ -213,12 +238,12 @@ __device__ __forceinline__ int sg_epilogue(const SgParams& p, uint8_t* smem, int
       finish = *s_flag != 0;
       epi_bar_sync();                            // s_flag may be rewritten by the next segment
       if (finish) {
-        __threadfence();
+        if (!p.fast_sync) __threadfence();
 #pragma unroll
         for (int m = 0; m < MP; ++m) v[m] = 0u;
         // the partial tiles of FB contributors are fetched together (one L2 round trip per batch instead of one per
         // contributor: this sum sits on the chain's critical path at every split slab) and added in the fixed order c_first..c_last
-        constexpr int FB = MP == 16 ? 4 : (MP == 32 ? 2 : 1);
+        constexpr int FB = MP == 16 ? 7 : (MP == 32 ? 2 : 1);      // down_proj at M <= 16: up to 7 contributors per slab -> one batch
         for (int c = c_first; c <= c_last; c += FB) {
           float t[FB][MP];
 #pragma unroll
@@ -246,18 +271,25 @@ __device__ __forceinline__ int sg_epilogue(const SgParams& p, uint8_t* smem, int
     if (p.fold_x) {
       // residual add + norm-weight scaling + per-row sum of squares of this slab's 128 columns (N % 128 == 0)
       if (finish) {
-        const float gw = __bfloat162float(p.fold_w[n]);
-        bf16 xold[MP];
+        float gw;
+        bf16 xo[MP];
+        if (kEarlyResid && p.early_resid) {
+          gw = gw_early;
 #pragma unroll
-        for (int m = 0; m < MP; ++m)             // all residual loads in flight together (one L2 round trip, not MP)
-          xold[m] = m < p.M ? p.fold_x[(long long)m * p.N + n] : __float2bfloat16(0.f);
+          for (int m = 0; m < MP; ++m) xo[m] = xold[kEarlyResid ? m : 0];
+        } else {
+          gw = __bfloat162float(p.fold_w[n]);
+#pragma unroll
+          for (int m = 0; m < MP; ++m)           // all residual loads in flight together (one L2 round trip, not MP)
+            xo[m] = m < p.M ? p.fold_x[(long long)m * p.N + n] : __float2bfloat16(0.f);
+        }
         float sq[MP];
 #pragma unroll
         for (int m = 0; m < MP; ++m) {
           sq[m] = 0.f;
           if (m < p.M) {
             const float y = __bfloat162float(__float2bfloat16(__uint_as_float(v[m])));
-            const bf16 hn = __float2bfloat16(__bfloat162float(xold[m]) + y);  // hidden = residual + hidden in bf16 (HF Q25:805-827)
+            const bf16 hn = __float2bfloat16(__bfloat162float(xo[m]) + y);  // hidden = residual + hidden in bf16 (HF Q25:805-827)
             p.fold_x[(long long)m * p.N + n] = hn;
             const float hf = __bfloat162float(hn);
             p.fold_z[(long long)m * p.N + n] = __float2bfloat16(gw * hf);
@@ -302,7 +334,7 @@ __device__ __forceinline__ int sg_epilogue(const SgParams& p, uint8_t* smem, int
         epi_bar_sync();                          // xs is rewritten by the next finished slab
       }
     } else if (finish && n < p.N) {
-      const float b = p.bias ? __bfloat162float(p.bias[n]) : 0.f;
+      const float b = p.bias ? (p.early_resid ? bias_early : __bfloat162float(p.bias[n])) : 0.f;
       if (p.out_f32) {
         float* yp = reinterpret_cast<float*>(p.y) + n;
 #pragma unroll
@@ -1350,6 +1382,8 @@ static int stream_gemm_impl(const void* x, long long ldx, const void* W, long lo
   p.in_nparts = tail.in_nparts;
   p.in_eps = tail.eps;
   p.pf_w = nullptr;
+  p.early_resid = env_int("T1_STREAM_EARLY_RESID", 1);
+  p.fast_sync = env_int("T1_STREAM_FAST_SYNC", 1);
   const SgPrefetchHint hint = g_pf_hint;
   g_pf_hint = SgPrefetchHint();          // one-shot
   const bool folded = tail.fold_resid || tail.in_parts;       // only the statically split kernel carries the folded norm
@@ -1577,6 +1611,8 @@ extern "C" int t1_stream_gemm_fold_pair(const void* x, long long ldx, const void
     q.in_nparts = i ? N_a / 128 : 0;
     q.in_eps = eps;
     q.pf_w = nullptr;
+    q.early_resid = env_int("T1_STREAM_EARLY_RESID", 1);
+    q.fast_sync = env_int("T1_STREAM_FAST_SYNC", 1);
   }
   g_pf_hint = SgPrefetchHint();
   int* pair_counter = counters + SG_COUNTER_BYTES / 4 - 5;      // words -5, -4 of the counter region (zero on entry, re-armed on exit)
