@@ -327,13 +327,37 @@ decode_attn_tc_kernel(const bf16* __restrict__ q, long long ldq, int Hq, int Hkv
       *reinterpret_cast<float4*>(s8) = *reinterpret_cast<const float4*>(sn + q_c * 8);
       *reinterpret_cast<float4*>(s8 + 4) = *reinterpret_cast<const float4*>(sn + q_c * 8 + 4);
     }
+    // rope factors of this step's k (they do not depend on q either)
+    float kc = 0.f, ks = 0.f;
+    if (st_tid < HD / 2) {
+      kc = cs[st_tid];
+      ks = sn[st_tid];
+    }
     pdl_wait();                                  // q (the fused qkv rows of this step) is complete and visible
+    // every global load that had to wait for the dependency is issued here, together: the query chunk AND this thread's element
+    // of the new k / v rows of the owned sequences (one L2 round trip on the chain's critical path instead of two)
+    uint4 ua = make_uint4(0u, 0u, 0u, 0u), ub = ua;
+    if (q_on) {
+      const int sq = q_row / ratio, hq = hk * ratio + q_row % ratio;
+      const bf16* src = q + (long long)sq * ldq + (long long)hq * HD + q_c * 8;
+      ua = *reinterpret_cast<const uint4*>(src);
+      ub = *reinterpret_cast<const uint4*>(src + HD / 2);
+    }
+    // (the FIRST owned sequence -- the only one when G <= cluster size; further ones load inside the loop below)
+    bf16 kv0 = __float2bfloat16(0.f), kv1 = kv0;     // k pair (threads < HD/2) or v element in kv0 (threads HD/2 .. HD/2 + HD)
+    if (rank < G) {
+      const bf16* src = q + (long long)rank * ldq;
+      if (st_tid < HD / 2) {
+        const bf16* pk = src + (long long)(Hq + hk) * HD + st_tid;
+        kv0 = pk[0];
+        kv1 = pk[HD / 2];
+      } else if (st_tid < HD / 2 + HD) {
+        kv0 = src[(long long)(Hq + Hkv + hk) * HD + (st_tid - HD / 2)];
+      }
+    }
     asm volatile("bar.sync 9, %0;" ::"n"(NSOFT) : "memory");
     if (q_on) {
       const int row = q_row, c = q_c;
-      const int sq = row / ratio, hq = hk * ratio + row % ratio;
-      const bf16* src = q + (long long)sq * ldq + (long long)hq * HD + c * 8;
-      const uint4 ua = *reinterpret_cast<const uint4*>(src), ub = *reinterpret_cast<const uint4*>(src + HD / 2);
       const uint32_t* pa = reinterpret_cast<const uint32_t*>(&ua);
       const uint32_t* pb = reinterpret_cast<const uint32_t*>(&ub);
       uint32_t oa[4], ob[4];
@@ -354,10 +378,18 @@ decode_attn_tc_kernel(const bf16* __restrict__ q, long long ldq, int Hq, int Hkv
     for (int b = rank, o = 0; b < G && o < MAX_OWN; b += S, ++o) {
       const bf16* src = q + (long long)b * ldq;
       const long long slot = (long long)P + (long long)b * cpad + step;
+      if (o > 0) {
+        if (st_tid < HD / 2) {
+          const bf16* pk = src + (long long)(Hq + hk) * HD + st_tid;
+          kv0 = pk[0];
+          kv1 = pk[HD / 2];
+        } else if (st_tid < HD / 2 + HD) {
+          kv0 = src[(long long)(Hq + Hkv + hk) * HD + (st_tid - HD / 2)];
+        }
+      }
       if (st_tid < HD / 2) {
-        const bf16* pk = src + (long long)(Hq + hk) * HD + st_tid;
         float ra, rb;
-        rope_rotate(__bfloat162float(pk[0]), __bfloat162float(pk[HD / 2]), cs[st_tid], sn[st_tid], ra, rb);
+        rope_rotate(__bfloat162float(kv0), __bfloat162float(kv1), kc, ks, ra, rb);
         const bf16 ka = __float2bfloat16(ra), kb = __float2bfloat16(rb);
         bf16* kd = grp.K + (slot * Hkv + hk) * HD + st_tid;
         kd[0] = ka;
@@ -366,7 +398,7 @@ decode_attn_tc_kernel(const bf16* __restrict__ q, long long ldq, int Hq, int Hkv
         s_knew[o * HD + st_tid + HD / 2] = __bfloat162float(kb);
       } else if (st_tid < HD / 2 + HD) {
         const int j = st_tid - HD / 2;
-        const bf16 vv = src[(long long)(Hq + Hkv + hk) * HD + j];
+        const bf16 vv = kv0;
         grp.V[(slot * Hkv + hk) * HD + j] = vv;
         s_vnew[o * HD + j] = __bfloat162float(vv);
       }
