@@ -180,7 +180,10 @@ class RunConfig:
     # measured per decode step (2 groups, 7B): cfg2 (P 4216) cluster 3.260 / wide 3.279 ms, cfg3 (P 8312) 3.394 / 3.383,
     # cfg5 (P 16504) 3.665 / 3.546 (profiles/r02_decode_wide_vs_cluster_by_context.txt)
     decode_attn: str = os.environ.get("T1_DECODE_ATTN", "auto")
-    decode_attn_wide_min_prompt: int = 8192
+    # at the round's final kernels (slab-aligned o_proj on 112 CTAs, hoisted loads) the wide form wins at cfg2's context as well:
+    # P 4216 cluster 3.139 / wide 3.115 ms, P 8312 3.279 / 3.208, P 16504 3.545 / 3.369 (profiles/r02_decode_step_final_by_context.txt,
+    # r02_decode_wide_vs_cluster_cfg2_final.txt); shorter prompts than measured stay on clusters
+    decode_attn_wide_min_prompt: int = 4096
     # fuse the residual add + RMSNorm that follows the o / down projection into that stream GEMM (5 kernels per layer
     # instead of 7).  Measured neutral on B200 (3.53 vs 3.49 ms per step): what looked like kernel-boundary latency is
     # the finishing-time spread of the 148 streaming CTAs, which the fused tail has to wait out as well.

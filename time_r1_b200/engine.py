@@ -631,11 +631,11 @@ class Engine:
             # per-layer TMA tensor maps over every group's K and V cache (t1_decode_attn_cluster)
             flat = [t for l in range(L) for grp in groups for t in grp["kv"][l]]
             st["kv_maps"] = ops.kv_cache_tensor_maps(flat, cfg.num_key_value_heads, cfg.head_dim).reshape(L, n * 2 * 128)
-            # "auto": the cluster form holds 8 CTAs per (group, KV head) -- P / 1024 128-key units per CTA; from ~8 units per
-            # CTA on, the wide form's 144 streaming CTAs win (profiles/r02_decode_wide_vs_cluster_by_context.txt)
+            # "auto": the cluster form holds 8 CTAs per (group, KV head) -- P / 1024 128-key units per CTA; from ~4 units per
+            # CTA on, the wide form's 144 streaming CTAs win (profiles/r02_decode_step_final_by_context.txt)
             form = self.run.decode_attn
             if form == "auto":
-                form = "wide" if max(Ps) >= int(getattr(self.run, "decode_attn_wide_min_prompt", 8192)) else "cluster"
+                form = "wide" if max(Ps) >= int(getattr(self.run, "decode_attn_wide_min_prompt", 4096)) else "cluster"
             st["attn_form"] = form
             if form == "wide":
                 st["attn_splits"], st["attn_ws"] = ops.decode_attn_wide_workspace(n, cfg.num_key_value_heads, d)
