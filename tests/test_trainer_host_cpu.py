@@ -289,3 +289,61 @@ def test_global_batches_are_dealt_evenly_and_keep_their_content():
         ideal += sum(loads) / world
     assert crit[True] < 0.93 * crit[False] and crit[True] < 1.2 * ideal, (crit, ideal)
     assert balanced_deal([5, 1, 1, 5], 2) == [0, 3, 1, 2] and sorted(balanced_deal(list(range(12)), 4)) == list(range(12))
+
+
+@pytest.mark.parametrize("train_vit", [False, True])
+@pytest.mark.parametrize("family", ["qwen2_5_vl", "qwen2_vl"])
+def test_overlapped_reduce_scatter_never_takes_a_bucket_before_its_gradients_are_final(family, train_vit):
+    """Engine._backward / _vit_backward call _reduce_ready(offset) as the backward walks the flat buffer from its end (lm_head)
+    to its start (merger; with fix_vit=False the ViT blocks, then the patch-embed): replay that call sequence on the BucketPlan
+    and check, for every bucket, that each tensor it overlaps was final when the bucket was handed to NCCL (the order in which the
+    backward finishes tensors: lm_head, final norm, layers L-1..0, embedding scatter, merger, ViT blocks depth-1..0, patch-embed),
+    that no bucket is handed out twice, and that optimizer_step's ready_buckets(0) collects the rest."""
+    from time_r1_b200 import config, weights
+    from time_r1_b200.dist_utils import BucketPlan
+
+    cfg = config.toy(family)
+    world = 2
+    mw = weights.ModelWeights(cfg, "cpu", world_size=world, train_vit=train_vit)
+    lay = mw.train.layout
+    off = lambda n: lay[n][0]
+    L, depth = cfg.num_hidden_layers, cfg.vit_depth
+    # when is a tensor final?  (index into the sequence of _reduce_ready calls below; the call happens AFTER the work it names)
+    calls = [("lm_head.weight", off("lm_head.weight")), ("model.norm.weight", off("model.norm.weight"))]
+    calls += [(f"model.layers.{l}.", off(f"model.layers.{l}.input_layernorm.weight")) for l in range(L - 1, -1, -1)]
+    if train_vit:
+        calls.append(("visual.merger.", off("visual.merger.ln_q.weight")))        # after the embedding scatter and the merger backward
+        calls += [(f"visual.blocks.{i}.", off(f"visual.blocks.{i}.norm1.weight")) for i in range(depth - 1, -1, -1)]
+    calls.append(("<optimizer_step>", 0))
+
+    def final_at(name):
+        if name in ("model.embed_tokens.weight",) or name.startswith("visual.merger."):
+            key = "visual.merger." if train_vit else "<optimizer_step>"
+        elif name == "visual.patch_embed.proj.weight":
+            key = "<optimizer_step>"
+        elif name.startswith("visual.blocks."):
+            key = ".".join(name.split(".")[:3]) + "."
+        elif name.startswith("model.layers."):
+            key = ".".join(name.split(".")[:3]) + "."
+        else:
+            key = name
+        return next(i for i, (k, _) in enumerate(calls) if k == key)
+
+    for n_buckets in (4, 7, 32):
+        plan = BucketPlan(mw.train.numel, world, n_buckets=n_buckets)
+        issued = {}
+        done_prev = None
+        for t, (_, done_from) in enumerate(calls):
+            assert done_prev is None or done_from <= done_prev, "the backward walks the buffer from its end to its start"
+            done_prev = done_from
+            for b in plan.ready_buckets(done_from):
+                assert b not in issued
+                issued[b] = t
+        assert sorted(issued) == list(range(len(plan)))
+        for name, (o, shape) in lay.items():
+            n = 1
+            for d in shape:
+                n *= d
+            for b, (lo, hi) in enumerate(plan.bounds):
+                if lo < o + n and hi > o:
+                    assert issued[b] >= final_at(name), (name, b, n_buckets)
