@@ -606,11 +606,19 @@ decode_attn_tc_kernel(const bf16* __restrict__ q, long long ldq, int Hq, int Hkv
         const float* po = wO + (size_t)row * NSRC * HD + col;
         const float* w = s_w + li * NSRC;
         float acc = 0.f;
-#pragma unroll 8
-        for (int src = 0; src < NSRC; ++src) {
-          const float ws = w[src];
-          const float o = __ldcg(po + src * HD);    // L2: written by other SMs during this launch
-          acc += ws > 0.f ? ws * o : 0.f;           // never-written rows of empty sources are dropped
+        // every source's partial of this element is requested before the first one is used (L2: written by other SMs during this
+        // launch): one round trip per element instead of one per 8 sources; same summation order
+        for (int s0 = 0; s0 < NSRC; s0 += 32) {
+          float o[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) o[j] = (s0 + j < NSRC) ? __ldcg(po + (s0 + j) * HD) : 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (s0 + j < NSRC) {
+              const float ws = w[s0 + j];
+              acc += ws > 0.f ? ws * o[j] : 0.f;    // never-written rows of empty sources are dropped
+            }
+          }
         }
         const float Ls = s_L[li];
         const int sq = row / ratio, hq = hk * ratio + row % ratio;
